@@ -1,0 +1,77 @@
+"""In-tree native builds: the CUDA library (sm_100a) and, for the test side, the CPU oracle.
+
+Nothing here needs a GPU: nvcc cross-compiles sm_100a on the CPU box and the resulting
+``bmfr_b200/libbmfr_b200.so`` travels to the GPU box with the repo snapshot.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+CSRC = ROOT / "bmfr_b200" / "csrc"
+LIB = ROOT / "bmfr_b200" / "libbmfr_b200.so"
+BUILD_DIR = ROOT / "bmfr_b200" / "_build"
+
+CUDA_SOURCES = ["bmfr_kernels.cu", "bmfr_pipeline.cu", "synth.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    "--fmad=false",  # contraction only where fmaf() is written; see csrc/bmfr_device.cuh
+    "-Xcompiler", "-fPIC,-fopenmp,-ffp-contract=off,-O2",
+    "-Xptxas", "-v",
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and Path(cand).exists():
+            return cand
+    raise RuntimeError("nvcc not found: the CUDA library cannot be built (there is no CPU fallback)")
+
+
+def _digest(paths, extra: str) -> str:
+    h = hashlib.sha256(extra.encode())
+    for p in sorted(paths):
+        h.update(str(p.name).encode())
+        h.update(p.read_bytes())
+    return h.hexdigest()
+
+
+def build_library(force: bool = False, verbose: bool = False, extra_flags=()) -> Path:
+    """Compile csrc/*.cu into bmfr_b200/libbmfr_b200.so (skipped when sources are unchanged)."""
+    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + [ROOT / "include" / "bmfr_b200.h"]
+    stamp = BUILD_DIR / "lib.sha256"
+    digest = _digest(deps, " ".join(NVCC_FLAGS + list(extra_flags)))
+    if not force and LIB.exists() and stamp.exists() and stamp.read_text() == digest:
+        return LIB
+    if not (CSRC / CUDA_SOURCES[0]).exists():
+        raise RuntimeError(f"sources missing under {CSRC}")
+    BUILD_DIR.mkdir(parents=True, exist_ok=True)
+    nvcc = _nvcc()
+    objs = []
+    for src in CUDA_SOURCES:
+        obj = BUILD_DIR / (src + ".o")
+        cmd = [nvcc, *NVCC_FLAGS, *extra_flags, "-c", str(CSRC / src), "-o", str(obj)]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        (BUILD_DIR / (src + ".log")).write_text(r.stdout + r.stderr)
+        if verbose or r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}")
+        objs.append(str(obj))
+    cmd = [nvcc, "-shared", "-o", str(LIB), *objs, "-Xcompiler", "-fopenmp", "-lgomp"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("link of libbmfr_b200.so failed")
+    stamp.write_text(digest)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build_library(force="--force" in sys.argv, verbose=True))

@@ -1,0 +1,500 @@
+// Device-side building blocks of the BMFR hot path (sm_100a).
+//
+// Arithmetic convention (DESIGN.md "Arithmetic"): this translation unit is compiled with
+// --fmad=false, so every a*b+c written with operators is two correctly rounded IEEE operations,
+// evaluated left to right exactly like the CPU oracle (gcc -ffp-contract=off).  That is what makes
+// the reprojection outputs (accept mask, spp, floor(prev pixel)) and every other per-pixel stage
+// bit-identical to the oracle on the same inputs.  Fused multiply-adds are used only where written
+// explicitly as fmaf(): inside the least-squares fit, whose results are compared within tolerance.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "../../include/bmfr_b200.h"
+#include "bmfr_kernels.h"
+
+struct f3 {
+    float x, y, z;
+};
+
+__device__ __forceinline__ f3 make_f3(float x, float y, float z) { return f3{x, y, z}; }
+__device__ __forceinline__ f3 load_f3(const float* __restrict__ b, size_t i) {
+    return f3{b[i * 3], b[i * 3 + 1], b[i * 3 + 2]};
+}
+__device__ __forceinline__ void store_f3(float* __restrict__ b, size_t i, f3 v) {
+    b[i * 3] = v.x;
+    b[i * 3 + 1] = v.y;
+    b[i * 3 + 2] = v.z;
+}
+__device__ __forceinline__ float dot3(f3 a, f3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+__device__ __forceinline__ f3 sub3(f3 a, f3 b) { return f3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+
+__device__ __forceinline__ size_t pix_index(const KParams& P, int x, int y) {
+    return (size_t)(y - P.row0) * (size_t)P.W + (size_t)x;
+}
+
+// mirror(), bmfr.cl:209-216
+__device__ __forceinline__ int mirror_index(int i, int size) {
+    if (i < 0) return -i - 1;
+    if (i >= size) return 2 * size - i - 1;
+    return i;
+}
+
+// scale(), bmfr.cl:200-205
+__device__ __forceinline__ float scale_feature(float v, float mn, float mx) {
+    const float d = mx - mn;
+    if (fabsf(d) > 1.0f) return (v - mn) / d;
+    return v - mn;
+}
+
+// random(), bmfr.cl:162-171 — integer hash; float(a) / float(UINT_MAX) == float(a) * 2^-32 exactly
+__host__ __device__ __forceinline__ float bmfr_random(unsigned int a) {
+    a = (a + 0x7ed55d16u) + (a << 12);
+    a = (a ^ 0xc761c23cu) ^ (a >> 19);
+    a = (a + 0x165667b1u) + (a << 5);
+    a = (a + 0xd3a2646cu) ^ (a << 9);
+    a = (a + 0xfd7046c5u) + (a << 3);
+    a = (a ^ 0xb55a4f09u) ^ (a >> 16);
+    return (float)a / 4294967296.0f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1 per work-item: accumulate_noisy_data, bmfr.cl:319-453, for the (already mirrored) pixel x,y.
+// ---------------------------------------------------------------------------------------------
+struct K1Pixel {
+    f3 normal, position, new_color;
+    float prev_x, prev_y;
+    unsigned char accept, spp;
+};
+
+__device__ __forceinline__ K1Pixel k1_pixel(const KParams& P, int x, int y) {
+    K1Pixel r;
+    const size_t lp = pix_index(P, x, y);
+    const f3 wp = load_f3(P.cur_positions, lp);
+    const f3 n = load_f3(P.cur_normals, lp);
+    const f3 cur = load_f3(P.cur_noisy, lp);
+    float pfx = (float)x, pfy = (float)y;  // bmfr.cl:325
+    unsigned int accept = 0;
+    float blend_alpha = 1.f;
+    f3 prev = make_f3(0.f, 0.f, 0.f);
+    float sample_spp = 0.f;
+
+    if (P.frame > 0) {
+        const float* M = P.cam;
+        // dot(M.s048c, (p,1)) etc., left to right; bmfr.cl:343-349
+        float cx = ((M[0] * wp.x + M[4] * wp.y) + M[8] * wp.z) + M[12] * 1.f;
+        float cy = ((M[1] * wp.x + M[5] * wp.y) + M[9] * wp.z) + M[13] * 1.f;
+        const float cw = ((M[3] * wp.x + M[7] * wp.y) + M[11] * wp.z) + M[15] * 1.f;
+        cx = cx / cw;
+        cy = cy / cw;
+        cx = (cx + 1.f) / 2.f;
+        cy = (cy + 1.f) / 2.f;
+        pfx = cx * (float)P.W - P.poff_x;  // bmfr.cl:352-355
+        pfy = cy * (float)P.H - P.poff_y1;
+        const int pix = __float2int_rd(pfx);  // convert_int2_rtn, bmfr.cl:356
+        const int piy = __float2int_rd(pfy);
+        const float frx = pfx - (float)pix, fry = pfy - (float)piy;
+        const float omx = 1.f - frx, omy = 1.f - fry;
+        const float w[4] = {omx * omy, frx * omy, omx * fry, frx * fry};  // bmfr.cl:367-370
+        float total = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int sx = pix + (i & 1), sy = piy + (i >> 1);
+            if (sx >= 0 && sy >= 0 && sx < P.W && sy < P.H) {  // bmfr.cl:380-381
+                if (sy < P.row0 || sy >= P.row1) {  // strip + halo does not hold this row
+                    *P.oob_flag = 1;
+                    continue;
+                }
+                const size_t ls = pix_index(P, sx, sy);
+                const f3 pd = sub3(load_f3(P.prev_positions, ls), wp);
+                if (dot3(pd, pd) < P.pos_limit) {  // bmfr.cl:388-393
+                    const f3 nd = sub3(load_f3(P.prev_normals, ls), n);
+                    if (dot3(nd, nd) < P.nrm_limit) {  // bmfr.cl:401-404
+                        accept |= 1u << i;
+                        sample_spp = sample_spp + w[i] * (float)P.prev_spp[ls];
+                        const f3 pc = load_f3(P.prev_noisy_acc, ls);
+                        prev.x = prev.x + w[i] * pc.x;
+                        prev.y = prev.y + w[i] * pc.y;
+                        prev.z = prev.z + w[i] * pc.z;
+                        total = total + w[i];
+                    }
+                }
+            }
+        }
+        if (total > 0.f) {  // bmfr.cl:421-429
+            prev.x = prev.x / total;
+            prev.y = prev.y / total;
+            prev.z = prev.z / total;
+            sample_spp = sample_spp / total;
+            blend_alpha = 1.f / (sample_spp + 1.f);
+            blend_alpha = fmaxf(blend_alpha, P.blend_alpha);
+        }
+    }
+    unsigned int new_spp = 1;  // bmfr.cl:433-441
+    if (blend_alpha < 1.f) {
+        if (sample_spp > 254.f) {
+            new_spp = 255;
+        } else {
+            int s = __float2int_rn(sample_spp);  // convert_uchar_sat_rte
+            s = min(max(s, 0), 255);
+            new_spp = (unsigned int)(s + 1) & 0xFFu;
+        }
+    }
+    const float oma = 1.f - blend_alpha;
+    r.new_color = make_f3(blend_alpha * cur.x + oma * prev.x, blend_alpha * cur.y + oma * prev.y,
+                          blend_alpha * cur.z + oma * prev.z);  // bmfr.cl:444-445
+    r.normal = n;
+    r.position = wp;
+    r.prev_x = pfx;
+    r.prev_y = pfy;
+    r.accept = (unsigned char)accept;
+    r.spp = (unsigned char)new_spp;
+    return r;
+}
+
+// The 13 values K1 stores per work-item (bmfr.cl:448-476): features, NaN scrubbed.
+__device__ __forceinline__ void k1_features(const K1Pixel& r, float* f) {
+    f[0] = 1.f;
+    f[1] = r.normal.x;
+    f[2] = r.normal.y;
+    f[3] = r.normal.z;
+    f[4] = r.position.x;
+    f[5] = r.position.y;
+    f[6] = r.position.z;
+    f[7] = r.position.x * r.position.x;
+    f[8] = r.position.y * r.position.y;
+    f[9] = r.position.z * r.position.z;
+    f[10] = r.new_color.x;
+    f[11] = r.new_color.y;
+    f[12] = r.new_color.z;
+#pragma unroll
+    for (int i = 0; i < BMFR_BUFFER_COUNT; ++i)
+        if (isnan(f[i])) f[i] = 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3 per pixel: weighted_sum, bmfr.cl:725-750.  w = 30 weights, mm = 12 min/max of the block.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ f3 k3_pixel(f3 n, f3 p, const float* __restrict__ w, const float* __restrict__ mm) {
+    float feat[BMFR_FEATURES] = {1.f, n.x, n.y, n.z, p.x, p.y, p.z, p.x * p.x, p.y * p.y, p.z * p.z};
+    f3 c = make_f3(0.f, 0.f, 0.f);
+#pragma unroll
+    for (int f = 0; f < BMFR_FEATURES; ++f) {
+        float v = feat[f];
+        if (f >= BMFR_FEATURES_NOT_SCALED)
+            v = scale_feature(v, mm[(f - BMFR_FEATURES_NOT_SCALED) * 2], mm[(f - BMFR_FEATURES_NOT_SCALED) * 2 + 1]);
+        c.x = c.x + w[f * 3 + 0] * v;
+        c.y = c.y + w[f * 3 + 1] * v;
+        c.z = c.z + w[f * 3 + 2] * v;
+    }
+    c.x = c.x < 0.f ? 0.f : c.x;  // keeps NaN like the reference, bmfr.cl:750
+    c.y = c.y < 0.f ? 0.f : c.y;
+    c.z = c.z < 0.f ? 0.f : c.z;
+    return c;
+}
+
+// group_index of weighted_sum, bmfr.cl:718-722
+__device__ __forceinline__ int k3_group(const KParams& P, int x, int y) {
+    return ((x + 16 - P.off_x) >> 5) + ((y + 16 - P.off_y) >> 5) * P.blocks_x;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4 per pixel: accumulate_filtered_data, bmfr.cl:778-856.
+// ---------------------------------------------------------------------------------------------
+#ifndef BMFR_FAST_POW
+#define BMFR_FAST_POW 0
+#endif
+__device__ __forceinline__ float tone_map(float v) {  // clamp(powr(max(0,v), 0.454545f), 0, 1)
+    v = fmaxf(0.f, v);
+#if BMFR_FAST_POW
+    v = exp2f(0.454545f * __log2f(v));
+#else
+    v = powf(v, 0.454545f);
+#endif
+    return fminf(fmaxf(v, 0.f), 1.f);
+}
+
+__device__ __forceinline__ void k4_pixel(const KParams& P, size_t lp, f3 filtered, float prev_x, float prev_y,
+                                         unsigned int accept, f3& accum, f3& tone) {
+    f3 prev = make_f3(0.f, 0.f, 0.f);
+    float blend_alpha = 1.f;
+    if (P.frame > 0 && accept > 0) {
+        const int pix = __float2int_rd(prev_x), piy = __float2int_rd(prev_y);
+        const float frx = prev_x - (float)pix, fry = prev_y - (float)piy;
+        const float omx = 1.f - frx, omy = 1.f - fry;
+        const float w[4] = {omx * omy, frx * omy, omx * fry, frx * fry};
+        float total = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (accept & (1u << i)) {  // taps are trusted, not re-checked: bmfr.cl:801-832
+                const int sx = pix + (i & 1), sy = piy + (i >> 1);
+                if (sy < P.row0 || sy >= P.row1) {
+                    *P.oob_flag = 1;
+                    continue;
+                }
+                total = total + w[i];
+                const f3 pc = load_f3(P.accum_prev, pix_index(P, sx, sy));
+                prev.x = prev.x + w[i] * pc.x;
+                prev.y = prev.y + w[i] * pc.y;
+                prev.z = prev.z + w[i] * pc.z;
+            }
+        }
+        if (total > 0.f) {
+            blend_alpha = 1.f / (float)P.cur_spp[lp];  // bmfr.cl:838-839
+            blend_alpha = fmaxf(blend_alpha, P.second_blend_alpha);
+            prev.x = prev.x / total;
+            prev.y = prev.y / total;
+            prev.z = prev.z / total;
+        }
+    }
+    const float oma = 1.f - blend_alpha;
+    accum = make_f3(blend_alpha * filtered.x + oma * prev.x, blend_alpha * filtered.y + oma * prev.y,
+                    blend_alpha * filtered.z + oma * prev.z);
+    const f3 alb = load_f3(P.albedo, lp);
+    tone = make_f3(tone_map(alb.x * accum.x), tone_map(alb.y * accum.y), tone_map(alb.z * accum.z));
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5 helpers: taa, bmfr.cl:184-198,893-973.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ f3 rgb_to_ycocg(f3 c) {
+    return make_f3((c.x * 1.f + c.y * 2.f) + c.z * 1.f, (c.x * 2.f + c.y * 0.f) + c.z * -2.f,
+                   (c.x * -1.f + c.y * 2.f) + c.z * -1.f);
+}
+__device__ __forceinline__ f3 ycocg_to_rgb(f3 c) {
+    return make_f3((c.x * 0.25f + c.y * 0.25f) + c.z * -0.25f, (c.x * 0.25f + c.y * 0.f) + c.z * 0.25f,
+                   (c.x * 0.25f + c.y * -0.25f) + c.z * -0.25f);
+}
+__device__ __forceinline__ f3 min3(f3 a, f3 b) { return make_f3(fminf(a.x, b.x), fminf(a.y, b.y), fminf(a.z, b.z)); }
+__device__ __forceinline__ f3 max3(f3 a, f3 b) { return make_f3(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z)); }
+
+struct TaaBox {
+    f3 min_box, min_cross, max_box, max_cross;
+};
+__device__ __forceinline__ void taa_box_init(TaaBox& b) {
+    b.min_box = b.min_cross = make_f3(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F);
+    b.max_box = b.max_cross = make_f3(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+}
+__device__ __forceinline__ void taa_box_add(TaaBox& b, f3 rgb, bool cross) {
+    const f3 s = rgb_to_ycocg(rgb);
+    if (cross) {
+        b.min_cross = min3(b.min_cross, s);
+        b.max_cross = max3(b.max_cross, s);
+    }
+    b.min_box = min3(b.min_box, s);
+    b.max_box = max3(b.max_box, s);
+}
+
+// Everything of taa after the 3x3 neighbourhood: bilinear history fetch, clamp, blend (bmfr.cl:922-973).
+__device__ __forceinline__ f3 taa_resolve(const KParams& P, f3 my_new, const TaaBox& b, float prev_x, float prev_y,
+                                          int pix, int piy) {
+    f3 prev = make_f3(0.f, 0.f, 0.f);
+    float total = 0.f;
+    const float frx = prev_x - (float)pix, fry = prev_y - (float)piy;
+    const float omx = 1.f - frx, omy = 1.f - fry;
+    const float w[4] = {omx * omy, frx * omy, omx * fry, frx * fry};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int dx = i & 1, dy = i >> 1;
+        const bool ok_y = dy ? (piy < P.H - 1) : (piy >= 0);
+        const bool ok_x = dx ? (pix < P.W - 1) : (pix >= 0);
+        if (ok_x && ok_y) {
+            const int sy = piy + dy;
+            if (sy < P.row0 || sy >= P.row1) {
+                *P.oob_flag = 1;
+                continue;
+            }
+            const f3 pc = load_f3(P.result_prev, pix_index(P, pix + dx, sy));
+            prev.x = prev.x + w[i] * pc.x;
+            prev.y = prev.y + w[i] * pc.y;
+            prev.z = prev.z + w[i] * pc.z;
+            total = total + w[i];
+        }
+    }
+    prev.x = prev.x / total;  // may be 0/0 on the image edge, as in bmfr.cl:962
+    prev.y = prev.y / total;
+    prev.z = prev.z / total;
+    const f3 py = rgb_to_ycocg(prev);
+    const f3 mn = make_f3((b.min_box.x + b.min_cross.x) / 2.f, (b.min_box.y + b.min_cross.y) / 2.f,
+                          (b.min_box.z + b.min_cross.z) / 2.f);
+    const f3 mx = make_f3((b.max_box.x + b.max_cross.x) / 2.f, (b.max_box.y + b.max_cross.y) / 2.f,
+                          (b.max_box.z + b.max_cross.z) / 2.f);
+    // clamp(x, lo, hi) = fmin(fmax(x, lo), hi)
+    const f3 cl = make_f3(fminf(fmaxf(py.x, mn.x), mx.x), fminf(fmaxf(py.y, mn.y), mx.y), fminf(fmaxf(py.z, mn.z), mx.z));
+    const f3 pr = ycocg_to_rgb(cl);
+    const float a = P.taa_blend_alpha, oma = 1.f - P.taa_blend_alpha;
+    return make_f3(a * my_new.x + oma * pr.x, a * my_new.y + oma * pr.y, a * my_new.z + oma * pr.z);
+}
+
+// ---------------------------------------------------------------------------------------------
+// The fit: fitter, bmfr.cl:490-700, for one 32x32 block held in registers.
+//
+// The reference runs a Householder QR of the 1024x13 matrix with 577 work-group barriers and 193
+// passes over global memory per block.  Here the matrix never leaves registers: thread `tid` owns
+// rows tid + 256*s (the reference's IN_ACCESS ownership, bmfr.cl:90-97), the QR is a two-level
+// TSQR — each warp factors its own 128 rows with shuffles only, then one warp factors the eight
+// stacked 10x13 triangles — and the back-substitution runs in that same warp.  R of a QR with a
+// positive diagonal is unique, so this computes the reference's R(0..9, 0..12) up to rounding.
+// ---------------------------------------------------------------------------------------------
+
+// One Householder step k on a tall matrix distributed over a warp: lane l holds NS rows, columns
+// 0..12, in a[s][c].  The pivot row of step k is slot 0 of lane k; slot 0 of lanes < k holds the
+// finished rows of R.  Mirrors bmfr.cl:553-655 for col = k < 10 (u_k = a_kk - |x|, R_kk = +|x|).
+template <int NS, int K>
+__device__ __forceinline__ void householder_step(float (&a)[NS][BMFR_BUFFER_COUNT], int lane) {
+    constexpr int NC = BMFR_BUFFER_COUNT;
+    // column k restricted to the rows below the pivot
+    float u[NS];
+    u[0] = (lane > K) ? a[0][K] : 0.f;
+#pragma unroll
+    for (int s = 1; s < NS; ++s) u[s] = a[s][K];
+    // S_j = sum_{rows below pivot} a_rk * a_rj for j = k..12 (S_k = sigma), one batched reduction
+    float S[NC];
+#pragma unroll
+    for (int j = K; j < NC; ++j) {
+        float acc = u[0] * a[0][j];
+#pragma unroll
+        for (int s = 1; s < NS; ++s) acc = fmaf(u[s], a[s][j], acc);
+        S[j] = acc;
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+#pragma unroll
+        for (int j = K; j < NC; ++j) S[j] += __shfl_xor_sync(0xffffffffu, S[j], m);
+    }
+    // pivot row, broadcast from lane k
+    float piv[NC];
+#pragma unroll
+    for (int j = K; j < NC; ++j) piv[j] = __shfl_sync(0xffffffffu, a[0][j], K);
+    const float alpha = piv[K];
+    const float norm = sqrtf(fmaf(alpha, alpha, S[K]));
+    // u_k = alpha - |x| ; written without cancellation when alpha > 0
+    const float vk = (alpha > 0.f) ? -S[K] / (alpha + norm) : alpha - norm;
+    const float ulen2 = fmaf(vk, vk, S[K]);  // u_length_squared, bmfr.cl:582-585
+    const float inv = 2.f / ulen2;
+    if (lane == K) u[0] = vk;
+#pragma unroll
+    for (int j = K + 1; j < NC; ++j) {
+        const float coef = fmaf(vk, piv[j], S[j]) * inv;  // 2 * dot / u_length_squared, bmfr.cl:650
+#pragma unroll
+        for (int s = 0; s < NS; ++s) a[s][j] = fmaf(-u[s], coef, a[s][j]);
+    }
+    if (lane == K) a[0][K] = norm;  // R_kk
+}
+
+template <int NS, int K>
+struct HouseholderLoop {
+    static __device__ __forceinline__ void run(float (&a)[NS][BMFR_BUFFER_COUNT], int lane) {
+        householder_step<NS, K>(a, lane);
+        HouseholderLoop<NS, K + 1>::run(a, lane);
+    }
+};
+template <int NS>
+struct HouseholderLoop<NS, BMFR_FEATURES> {
+    static __device__ __forceinline__ void run(float (&)[NS][BMFR_BUFFER_COUNT], int) {}
+};
+
+struct FitShared {
+    float red[BMFR_FIT_THREADS / 32][2 * BMFR_FEATURES_SCALED];          // per-warp min/max
+    float rstack[BMFR_FIT_THREADS / 32][BMFR_FEATURES][BMFR_BUFFER_COUNT];  // per-warp R (10x13)
+};
+
+// a[s][c]: the 13 K1 values of rows tid + 256*s.  On return weights/mins_maxs of `group` are written.
+__device__ __forceinline__ void block_fit(float (&a)[BMFR_ROWS_PER_THREAD][BMFR_BUFFER_COUNT], FitShared& sh,
+                                          const double* __restrict__ noise, float* __restrict__ weights,
+                                          float* __restrict__ mins_maxs, int group) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NSC = BMFR_FEATURES_SCALED, NNS = BMFR_FEATURES_NOT_SCALED;
+
+    // (i) block min / max of the six scaled features, bmfr.cl:511-535.  min/max are exact, so the
+    // tree shape is irrelevant and mins_maxs matches the reference bit for bit.
+    float mn[NSC], mx[NSC];
+#pragma unroll
+    for (int f = 0; f < NSC; ++f) {
+        mn[f] = fminf(fminf(a[0][NNS + f], a[1][NNS + f]), fminf(a[2][NNS + f], a[3][NNS + f]));
+        mx[f] = fmaxf(fmaxf(a[0][NNS + f], a[1][NNS + f]), fmaxf(a[2][NNS + f], a[3][NNS + f]));
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+#pragma unroll
+        for (int f = 0; f < NSC; ++f) {
+            mn[f] = fminf(mn[f], __shfl_xor_sync(0xffffffffu, mn[f], m));
+            mx[f] = fmaxf(mx[f], __shfl_xor_sync(0xffffffffu, mx[f], m));
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int f = 0; f < NSC; ++f) {
+            sh.red[warp][2 * f] = mn[f];
+            sh.red[warp][2 * f + 1] = mx[f];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int f = 0; f < NSC; ++f) {
+        float lo = sh.red[0][2 * f], hi = sh.red[0][2 * f + 1];
+#pragma unroll
+        for (int w = 1; w < BMFR_FIT_THREADS / 32; ++w) {
+            lo = fminf(lo, sh.red[w][2 * f]);
+            hi = fmaxf(hi, sh.red[w][2 * f + 1]);
+        }
+        mn[f] = lo;
+        mx[f] = hi;
+    }
+    if (tid < 2 * NSC) mins_maxs[(size_t)group * 2 * NSC + tid] = (tid & 1) ? mx[tid >> 1] : mn[tid >> 1];
+
+    // scale (bmfr.cl:538-541), then the noise of the first touch (bmfr.cl:623-627) on columns 1..9
+    // — in fp64 like the reference's double literal NOISE_AMOUNT, rounded to fp32 once.
+#pragma unroll
+    for (int s = 0; s < BMFR_ROWS_PER_THREAD; ++s) {
+#pragma unroll
+        for (int f = 0; f < NSC; ++f) a[s][NNS + f] = scale_feature(a[s][NNS + f], mn[f], mx[f]);
+#pragma unroll
+        for (int c = 1; c < BMFR_FEATURES; ++c)
+            a[s][c] = (float)((double)a[s][c] + noise[(c - 1) * BMFR_BLOCK_PIXELS + tid + BMFR_FIT_THREADS * s]);
+    }
+
+    // (ii) level 1 of the TSQR: every warp factors its own 128 rows
+    HouseholderLoop<BMFR_ROWS_PER_THREAD, 0>::run(a, lane);
+    if (lane < BMFR_FEATURES) {
+#pragma unroll
+        for (int c = 0; c < BMFR_BUFFER_COUNT; ++c) sh.rstack[warp][lane][c] = (c >= lane) ? a[0][c] : 0.f;
+    }
+    __syncthreads();
+
+    // level 2 + (iii) back-substitution in warp 0: 80 stacked rows, three per lane
+    if (warp == 0) {
+        constexpr int NS2 = 3;
+        float b[NS2][BMFR_BUFFER_COUNT];
+        const float* flat = &sh.rstack[0][0][0];
+#pragma unroll
+        for (int s = 0; s < NS2; ++s) {
+            const int row = lane + 32 * s;
+#pragma unroll
+            for (int c = 0; c < BMFR_BUFFER_COUNT; ++c)
+                b[s][c] = (row < (BMFR_FIT_THREADS / 32) * BMFR_FEATURES) ? flat[row * BMFR_BUFFER_COUNT + c] : 0.f;
+        }
+        HouseholderLoop<NS2, 0>::run(b, lane);
+        // lane i < 10 now holds row i of R: b[0][i..12].  Solve R x = rhs for the three channels.
+        float rhs[3] = {b[0][10], b[0][11], b[0][12]};
+        float x[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = BMFR_FEATURES - 1; i >= 0; --i) {
+            const float d = __shfl_sync(0xffffffffu, b[0][i], i);  // R_ii
+            float xi[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                xi[c] = __shfl_sync(0xffffffffu, rhs[c], i) / d;
+                if (lane == i) x[c] = xi[c];
+                if (lane < i) rhs[c] = fmaf(-b[0][i], xi[c], rhs[c]);
+            }
+        }
+        if (lane < BMFR_FEATURES) {
+            float* wout = weights + ((size_t)group * BMFR_FEATURES + lane) * 3;  // bmfr.cl:694-699
+            wout[0] = x[0];
+            wout[1] = x[1];
+            wout[2] = x[2];
+        }
+    }
+}

@@ -1,0 +1,61 @@
+// Kernel parameter block and launcher prototypes shared by the pipeline and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "../../include/bmfr_b200.h"
+
+#define BMFR_FIT_THREADS 256  // LOCAL_SIZE, bmfr.cpp:116
+#define BMFR_ROWS_PER_THREAD 4
+
+// Everything a kernel of one frame needs; passed by value as a __grid_constant__.
+struct KParams {
+    int W, H;            // IMAGE_WIDTH / IMAGE_HEIGHT (full image)
+    int row0, row1;      // image rows held in the per-pixel buffers; buffer row = y - row0
+    int frame;           // frame_number
+    int off_x, off_y;    // BLOCK_OFFSETS[frame % 16], bmfr.cl:267-285
+    int blocks_x;        // WORKSET_WITH_MARGINS_WIDTH / 32
+    int blocks_y;        // WORKSET_WITH_MARGINS_HEIGHT / 32
+    int by0, by1;        // block rows to process this frame (whole image: 0..blocks_y)
+    int py0, py1;        // image rows the per-pixel stages (K3,K4) cover; K5 covers own_y0..own_y1
+    int own_y0, own_y1;
+    float cam[16];       // prev_frame_camera_matrix
+    float poff_x;        // pixel_offset.x
+    float poff_y1;       // 1 - pixel_offset.y  (bmfr.cl:353-355)
+    float blend_alpha, second_blend_alpha, taa_blend_alpha;
+    float pos_limit, nrm_limit;
+    const float* cur_normals;
+    const float* prev_normals;
+    const float* cur_positions;
+    const float* prev_positions;
+    const float* cur_noisy;       // this frame's 1-spp input (read-only)
+    const float* prev_noisy_acc;  // previous_noisy
+    float* cur_noisy_acc;         // what the reference stores back into current_noisy (bmfr.cl:481)
+    const unsigned char* prev_spp;
+    unsigned char* cur_spp;
+    float2* prev_pixels;          // out_prev_frame_pixel / in_prev_frame_pixel
+    unsigned char* accept;        // accept_bools
+    float* tmp_data;              // STAGED only
+    float* weights;
+    float* mins_maxs;
+    const double* noise;          // [9][1024] add_random() increments of this frame
+    const float* albedo;
+    float* filtered;              // STAGED only
+    const float* accum_prev;      // accumulated_prev_frame
+    float* accum_cur;             // accumulated_frame
+    float* tone_mapped;           // STAGED only
+    const float* result_prev;     // prev_frame (taa)
+    float* result_cur;            // result_frame
+    float* user_out;              // optional copy of result rows for the caller
+    int* oob_flag;                // set when a gather needed a row outside [row0,row1)
+};
+
+
+void bmfr_host_block_offset(int frame, int* ox, int* oy);
+cudaError_t launch_noise_tile(double* d_noise, double noise_amount, int frame, cudaStream_t st);
+cudaError_t launch_k1(const KParams& P, cudaStream_t st);
+cudaError_t launch_k2(const KParams& P, cudaStream_t st);
+cudaError_t launch_k3(const KParams& P, cudaStream_t st);
+cudaError_t launch_k4(const KParams& P, cudaStream_t st);
+cudaError_t launch_k5(const KParams& P, cudaStream_t st);
+cudaError_t launch_fit(const KParams& P, cudaStream_t st);
+cudaError_t launch_post(const KParams& P, cudaStream_t st);

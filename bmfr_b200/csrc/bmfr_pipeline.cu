@@ -1,0 +1,543 @@
+// Host pipeline + C ABI (include/bmfr_b200.h).  Replaces the OpenCL setup and the frame loop of
+// /root/reference/opencl/bmfr.cpp: buffer creation (:315-343), static argument binding (:349-384),
+// per-frame argument binding and the five launches (:429-476), the double-buffer swap (:483-484)
+// and the per-kernel event timers (:386-397,488-506).  The arithmetic lives in bmfr_kernels.cu.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "../../include/bmfr_b200.h"
+#include "bmfr_error.h"
+#include "bmfr_kernels.h"
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_last_error[512] = "";
+
+int bmfr_set_error(int status, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+    va_end(ap);
+    return status;
+}
+
+int bmfr_check_cuda(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return BMFR_OK;
+    int st = BMFR_ERR_CUDA;
+    if (e == cudaErrorMemoryAllocation) st = BMFR_ERR_OUT_OF_MEMORY;
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInvalidDevice) st = BMFR_ERR_NO_DEVICE;
+    return bmfr_set_error(st, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+}
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int kProfileSlots = 256;  // stage timers are kept for the last kProfileSlots frames
+constexpr int kHostSlots = 3;       // upload ring of the host-pointer entry: current, previous, next
+
+// Double_buffer<T> of bmfr.cpp:122-135: two equal buffers and a swap().
+template <class T>
+struct DoubleBuffer {
+    T* buf[2] = {nullptr, nullptr};
+    bool swapped = false;
+    T* current() const { return swapped ? buf[0] : buf[1]; }
+    T* previous() const { return swapped ? buf[1] : buf[0]; }
+    void swap() { swapped = !swapped; }
+};
+
+struct StageEvents {
+    cudaEvent_t ev[7] = {};  // boundaries: before K1, after K1, K2, K3, K4, K5 (FUSED: before, after fit, after post)
+    int frame = -1;
+    bool created = false;
+};
+
+}  // namespace
+
+struct bmfr_ctx {
+    bmfr_params prm;
+    bmfr_geometry geo;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+
+    // the reference's 15 buffers (bmfr.cpp:315-343); normals/positions/noisy inputs belong to the caller
+    DoubleBuffer<float> noisy_acc;          // noisy_buffer after K1's in-place store
+    DoubleBuffer<unsigned char> spp;        // spp_buffer
+    DoubleBuffer<float> accum;              // out_buffer
+    DoubleBuffer<float> result;             // result_buffer
+    float2* prev_pixels = nullptr;          // prev_pixels_buffer
+    unsigned char* accept = nullptr;        // accept_buffer
+    float* tmp_data = nullptr;              // in_buffer (STAGED)
+    float* filtered = nullptr;              // filtered_buffer (STAGED)
+    float* tone_mapped = nullptr;           // tone_mapped_buffer (STAGED)
+    float* weights = nullptr;               // weights_buffer
+    float* mins_maxs = nullptr;             // mins_maxs_buffer
+    double* noise = nullptr;
+    int* d_oob = nullptr;
+    int tmp_block_rows = 0;
+
+    const float* prev_normals = nullptr;    // normals_buffer.previous(): the caller's pointer of the last call
+    const float* prev_positions = nullptr;
+    bool has_prev = false;
+    long long launches = 0;
+
+    // host-pointer entry
+    float* up[4][kHostSlots] = {};          // albedo, normal, position, noisy upload ring
+    cudaEvent_t up_done[kHostSlots] = {};   // H2D of the slot finished
+    cudaEvent_t frame_done[kHostSlots] = {};  // kernels that read the slot finished
+    cudaEvent_t d2h_done[2] = {};
+    long long host_frames = 0;
+    bool host_ready = false;
+
+    std::vector<StageEvents> prof;
+};
+
+static size_t rows_of(const bmfr_ctx* c) { return (size_t)(c->geo.row1 - c->geo.row0); }
+
+template <class T>
+static int dev_alloc(T** p, size_t count, const char* what) {
+    cudaError_t e = cudaMalloc((void**)p, count * sizeof(T) > 0 ? count * sizeof(T) : 16);
+    if (e != cudaSuccess) return bmfr_check_cuda(e, what);
+    return BMFR_OK;
+}
+
+static void free_ctx(bmfr_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->prm.device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->h2d_stream) { cudaStreamSynchronize(c->h2d_stream); cudaStreamDestroy(c->h2d_stream); }
+    if (c->d2h_stream) { cudaStreamSynchronize(c->d2h_stream); cudaStreamDestroy(c->d2h_stream); }
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(c->noisy_acc.buf[i]);
+        cudaFree(c->spp.buf[i]);
+        cudaFree(c->accum.buf[i]);
+        cudaFree(c->result.buf[i]);
+        if (c->d2h_done[i]) cudaEventDestroy(c->d2h_done[i]);
+    }
+    cudaFree(c->prev_pixels);
+    cudaFree(c->accept);
+    cudaFree(c->tmp_data);
+    cudaFree(c->filtered);
+    cudaFree(c->tone_mapped);
+    cudaFree(c->weights);
+    cudaFree(c->mins_maxs);
+    cudaFree(c->noise);
+    cudaFree(c->d_oob);
+    for (int k = 0; k < 4; ++k)
+        for (int s = 0; s < kHostSlots; ++s) cudaFree(c->up[k][s]);
+    for (int s = 0; s < kHostSlots; ++s) {
+        if (c->up_done[s]) cudaEventDestroy(c->up_done[s]);
+        if (c->frame_done[s]) cudaEventDestroy(c->frame_done[s]);
+    }
+    for (auto& p : c->prof)
+        if (p.created)
+            for (auto& e : p.ev) cudaEventDestroy(e);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" {
+
+const char* bmfr_last_error(void) { return g_last_error; }
+int bmfr_abi_version(void) { return BMFR_B200_ABI_VERSION; }
+
+void bmfr_default_params(bmfr_params* p, int width, int height) {
+    if (!p) return;
+    memset(p, 0, sizeof(*p));
+    p->width = width;
+    p->height = height;
+    p->device = 0;
+    p->mode = BMFR_MODE_FUSED;
+    p->noise_amount = 1e-2;          // bmfr.cpp:58
+    p->blend_alpha = 0.2f;           // bmfr.cpp:60
+    p->second_blend_alpha = 0.1f;    // bmfr.cpp:61
+    p->taa_blend_alpha = 0.2f;       // bmfr.cpp:62
+    p->position_limit_squared = 0.f;
+    p->normal_limit_squared = 0.f;
+    bmfr_synth_limits(&p->position_limit_squared, &p->normal_limit_squared);
+    p->tmp_half = 0;
+    p->profile = 0;
+}
+
+void bmfr_block_offset(int frame, int* off_x, int* off_y) {
+    int x, y;
+    bmfr_host_block_offset(frame, &x, &y);
+    if (off_x) *off_x = x;
+    if (off_y) *off_y = y;
+}
+
+int bmfr_create(const bmfr_params* params, bmfr_ctx** out_ctx) {
+    if (!params || !out_ctx) return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_create: null argument");
+    *out_ctx = nullptr;
+    const bmfr_params& p = *params;
+    // "x and y are always less than one size out of bounds if image dimensions are bigger than
+    // BLOCK_EDGE_LENGTH" (bmfr.cl:312-313): mirror() needs at least one block edge of image.
+    if (p.width < BMFR_BLOCK_EDGE || p.height < BMFR_BLOCK_EDGE)
+        return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_create: image %dx%d smaller than one 32x32 block",
+                              p.width, p.height);
+    if (p.mode != BMFR_MODE_STAGED && p.mode != BMFR_MODE_FUSED)
+        return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_create: unknown mode %d", p.mode);
+    if (p.tmp_half != 0)
+        return bmfr_set_error(BMFR_ERR_UNSUPPORTED,
+                              "bmfr_create: USE_HALF_PRECISION_IN_TMP_DATA=1 is not built (fp32 fitter only)");
+    const bool whole = (p.strip_y0 == 0 && p.strip_y1 == 0);
+    if (!whole && (p.strip_y0 < 0 || p.strip_y1 > p.height || p.strip_y0 >= p.strip_y1 || p.halo_rows < 0))
+        return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_create: bad strip [%d,%d) halo %d", p.strip_y0,
+                              p.strip_y1, p.halo_rows);
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return bmfr_set_error(BMFR_ERR_NO_DEVICE, "bmfr_create: no CUDA device (%s); this library has no CPU path",
+                              e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (p.device < 0 || p.device >= ndev)
+        return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_create: device %d of %d", p.device, ndev);
+    BMFR_CUDA_TRY(cudaSetDevice(p.device));
+
+    bmfr_ctx* c = new (std::nothrow) bmfr_ctx();
+    if (!c) return bmfr_set_error(BMFR_ERR_OUT_OF_MEMORY, "bmfr_create: host allocation failed");
+    c->prm = p;
+    bmfr_geometry& g = c->geo;
+    g.width = p.width;
+    g.height = p.height;
+    g.workset_width = BMFR_BLOCK_EDGE * ((p.width + BMFR_BLOCK_EDGE - 1) / BMFR_BLOCK_EDGE);    // bmfr.cpp:107-108
+    g.workset_height = BMFR_BLOCK_EDGE * ((p.height + BMFR_BLOCK_EDGE - 1) / BMFR_BLOCK_EDGE);  // bmfr.cpp:109-110
+    g.margin_width = g.workset_width + BMFR_BLOCK_EDGE;                                         // bmfr.cpp:111
+    g.margin_height = g.workset_height + BMFR_BLOCK_EDGE;                                       // bmfr.cpp:112
+    g.blocks_x = g.margin_width / BMFR_BLOCK_EDGE;
+    g.blocks_y = g.margin_height / BMFR_BLOCK_EDGE;
+    if (whole) {
+        g.own_y0 = 0; g.own_y1 = p.height; g.row0 = 0; g.row1 = p.height;
+        g.block_row0 = 0; g.block_row1 = g.blocks_y;
+    } else {
+        g.own_y0 = p.strip_y0; g.own_y1 = p.strip_y1;
+        g.row0 = p.strip_y0 - p.halo_rows < 0 ? 0 : p.strip_y0 - p.halo_rows;
+        g.row1 = p.strip_y1 + p.halo_rows > p.height ? p.height : p.strip_y1 + p.halo_rows;
+        const int py0 = g.own_y0 > 0 ? g.own_y0 - 1 : 0, py1 = g.own_y1 < p.height ? g.own_y1 + 1 : p.height;
+        g.block_row0 = (py0 + 16 - 14) >> 5;            // largest offset.y is 14, smallest -16 (bmfr.cl:268-285)
+        g.block_row1 = ((py1 - 1 + 16 + 16) >> 5) + 1;
+        if (g.block_row1 > g.blocks_y) g.block_row1 = g.blocks_y;
+    }
+    c->tmp_block_rows = g.block_row1 - g.block_row0;
+
+    int st = BMFR_OK;
+    auto fail = [&](int s) { free_ctx(c); return s; };
+    if (p.stream) {
+        c->stream = (cudaStream_t)p.stream;
+    } else {
+        if ((st = bmfr_check_cuda(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "stream")) != 0) return fail(st);
+        c->own_stream = true;
+    }
+    const size_t npix = rows_of(c) * (size_t)p.width;
+    const size_t nb = (size_t)g.blocks_x * g.blocks_y;
+    for (int i = 0; i < 2 && st == 0; ++i) {
+        if (st == 0) st = dev_alloc(&c->noisy_acc.buf[i], npix * 3, "noisy_acc");
+        if (st == 0) st = dev_alloc(&c->spp.buf[i], npix, "spp");
+        if (st == 0) st = dev_alloc(&c->accum.buf[i], npix * 3, "accum");
+        if (st == 0) st = dev_alloc(&c->result.buf[i], npix * 3, "result");
+    }
+    if (st == 0) st = dev_alloc(&c->prev_pixels, npix, "prev_pixels");
+    if (st == 0) st = dev_alloc(&c->accept, npix, "accept");
+    if (st == 0) st = dev_alloc(&c->weights, nb * BMFR_FEATURES * 3, "weights");
+    if (st == 0) st = dev_alloc(&c->mins_maxs, nb * BMFR_FEATURES_SCALED * 2, "mins_maxs");
+    if (st == 0) st = dev_alloc(&c->noise, (size_t)(BMFR_FEATURES - 1) * BMFR_BLOCK_PIXELS, "noise");
+    if (st == 0) st = dev_alloc(&c->d_oob, 1, "oob flag");
+    if (st == 0 && p.mode == BMFR_MODE_STAGED) {
+        st = dev_alloc(&c->tmp_data, (size_t)c->tmp_block_rows * g.blocks_x * BMFR_BUFFER_COUNT * BMFR_BLOCK_PIXELS, "tmp_data");
+        if (st == 0) st = dev_alloc(&c->filtered, npix * 3, "filtered");
+        if (st == 0) st = dev_alloc(&c->tone_mapped, npix * 3, "tone_mapped");
+    }
+    if (st != 0) return fail(st);
+    if ((st = bmfr_check_cuda(cudaMemsetAsync(c->d_oob, 0, sizeof(int), c->stream), "memset")) != 0) return fail(st);
+    // weights of blocks a strip never fits stay defined
+    if ((st = bmfr_check_cuda(cudaMemsetAsync(c->weights, 0, nb * BMFR_FEATURES * 3 * sizeof(float), c->stream), "memset")) != 0) return fail(st);
+    if ((st = bmfr_check_cuda(cudaMemsetAsync(c->mins_maxs, 0, nb * BMFR_FEATURES_SCALED * 2 * sizeof(float), c->stream), "memset")) != 0) return fail(st);
+    if (p.profile) c->prof.resize(kProfileSlots);
+    if ((st = bmfr_check_cuda(cudaStreamSynchronize(c->stream), "create sync")) != 0) return fail(st);
+    *out_ctx = c;
+    return BMFR_OK;
+}
+
+void bmfr_destroy(bmfr_ctx* ctx) { free_ctx(ctx); }
+
+int bmfr_get_geometry(const bmfr_ctx* ctx, bmfr_geometry* out) {
+    if (!ctx || !out) return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_get_geometry: null argument");
+    *out = ctx->geo;
+    return BMFR_OK;
+}
+
+long long bmfr_kernel_launches(const bmfr_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"
+
+// Per-frame argument binding, bmfr.cpp:429-474.
+static void fill_params(bmfr_ctx* c, KParams& P, int frame, const float* d_albedo, const float* d_normal,
+                        const float* d_position, const float* d_noisy, const float* cam_prev, const float* pixel_offset,
+                        float* d_out) {
+    const bmfr_geometry& g = c->geo;
+    memset(&P, 0, sizeof(P));
+    P.W = g.width; P.H = g.height; P.row0 = g.row0; P.row1 = g.row1; P.frame = frame;
+    bmfr_host_block_offset(frame, &P.off_x, &P.off_y);
+    P.blocks_x = g.blocks_x; P.blocks_y = g.blocks_y;
+    P.own_y0 = g.own_y0; P.own_y1 = g.own_y1;
+    const bool whole = (g.own_y0 == 0 && g.own_y1 == g.height);
+    if (whole) {
+        P.py0 = 0; P.py1 = g.height; P.by0 = 0; P.by1 = g.blocks_y;
+    } else {
+        P.py0 = g.own_y0 > 0 ? g.own_y0 - 1 : 0;
+        P.py1 = g.own_y1 < g.height ? g.own_y1 + 1 : g.height;
+        P.by0 = (P.py0 + 16 - P.off_y) >> 5;
+        P.by1 = ((P.py1 - 1 + 16 - P.off_y) >> 5) + 1;
+    }
+    if (cam_prev) memcpy(P.cam, cam_prev, 16 * sizeof(float));
+    P.poff_x = pixel_offset ? pixel_offset[0] : 0.f;
+    P.poff_y1 = 1.f - (pixel_offset ? pixel_offset[1] : 0.f);
+    P.blend_alpha = c->prm.blend_alpha;
+    P.second_blend_alpha = c->prm.second_blend_alpha;
+    P.taa_blend_alpha = c->prm.taa_blend_alpha;
+    P.pos_limit = c->prm.position_limit_squared;
+    P.nrm_limit = c->prm.normal_limit_squared;
+    P.cur_normals = d_normal; P.prev_normals = c->prev_normals;
+    P.cur_positions = d_position; P.prev_positions = c->prev_positions;
+    P.cur_noisy = d_noisy;
+    P.prev_noisy_acc = c->noisy_acc.previous(); P.cur_noisy_acc = c->noisy_acc.current();
+    P.prev_spp = c->spp.previous(); P.cur_spp = c->spp.current();
+    P.prev_pixels = c->prev_pixels; P.accept = c->accept;
+    P.tmp_data = c->tmp_data; P.weights = c->weights; P.mins_maxs = c->mins_maxs; P.noise = c->noise;
+    P.albedo = d_albedo; P.filtered = c->filtered;
+    P.accum_prev = c->accum.previous(); P.accum_cur = c->accum.current();
+    P.tone_mapped = c->tone_mapped;
+    P.result_prev = c->result.previous(); P.result_cur = c->result.current();
+    P.user_out = d_out; P.oob_flag = c->d_oob;
+}
+
+static StageEvents* prof_slot(bmfr_ctx* c, int frame) {
+    if (c->prof.empty()) return nullptr;
+    StageEvents& s = c->prof[(size_t)(frame >= 0 ? frame : 0) % kProfileSlots];
+    if (!s.created) {
+        for (auto& e : s.ev)
+            if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+        s.created = true;
+    }
+    s.frame = frame;
+    return &s;
+}
+
+#define LAUNCH_TRY(call, name)                              \
+    do {                                                    \
+        int _st = bmfr_check_cuda((call), name);            \
+        if (_st != 0) return _st;                           \
+        ++c->launches;                                      \
+    } while (0)
+#define MARK(i)                                             \
+    do {                                                    \
+        if (pe) BMFR_CUDA_TRY(cudaEventRecord(pe->ev[i], c->stream)); \
+    } while (0)
+
+static int run_frame(bmfr_ctx* c, const KParams& P, int frame) {
+    StageEvents* pe = prof_slot(c, frame);
+    LAUNCH_TRY(launch_noise_tile(c->noise, c->prm.noise_amount, frame, c->stream), "noise_tile_kernel");
+    MARK(0);
+    if (c->prm.mode == BMFR_MODE_STAGED) {
+        LAUNCH_TRY(launch_k1(P, c->stream), "accumulate_noisy_data");
+        MARK(1);
+        LAUNCH_TRY(launch_k2(P, c->stream), "fitter");
+        MARK(2);
+        LAUNCH_TRY(launch_k3(P, c->stream), "weighted_sum");
+        MARK(3);
+        LAUNCH_TRY(launch_k4(P, c->stream), "accumulate_filtered_data");
+        MARK(4);
+        LAUNCH_TRY(launch_k5(P, c->stream), "taa");
+        MARK(5);
+    } else {
+        LAUNCH_TRY(launch_fit(P, c->stream), "fit_kernel");
+        MARK(1);
+        LAUNCH_TRY(launch_post(P, c->stream), "post_kernel");
+        MARK(2);
+    }
+    return BMFR_OK;
+}
+
+extern "C" {
+
+int bmfr_denoise_frame(bmfr_ctx* c, int frame, const float* d_albedo, const float* d_normal, const float* d_position,
+                       const float* d_noisy, const float cam_prev[16], const float pixel_offset[2], float* d_out) {
+    if (!c || !d_albedo || !d_normal || !d_position || !d_noisy || !pixel_offset || frame < 0)
+        return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_denoise_frame: null argument or negative frame");
+    if (frame > 0 && !cam_prev)
+        return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_denoise_frame: frame %d needs cam_prev", frame);
+    if (frame > 0 && !c->has_prev)
+        return bmfr_set_error(BMFR_ERR_SEQUENCE, "bmfr_denoise_frame: frame %d submitted before any frame 0", frame);
+    BMFR_CUDA_TRY(cudaSetDevice(c->prm.device));
+    KParams P;
+    fill_params(c, P, frame, d_albedo, d_normal, d_position, d_noisy, cam_prev, pixel_offset, d_out);
+    int st = run_frame(c, P, frame);
+    if (st != 0) return st;
+    // swap all double buffers, bmfr.cpp:483-484
+    c->noisy_acc.swap(); c->spp.swap(); c->accum.swap(); c->result.swap();
+    c->prev_normals = d_normal;
+    c->prev_positions = d_position;
+    c->has_prev = true;
+    return BMFR_OK;
+}
+
+static int host_path_init(bmfr_ctx* c) {
+    if (c->host_ready) return BMFR_OK;
+    const size_t n = rows_of(c) * (size_t)c->geo.width * 3;
+    for (int k = 0; k < 4; ++k)
+        for (int s = 0; s < kHostSlots; ++s) {
+            int st = dev_alloc(&c->up[k][s], n, "upload ring");
+            if (st != 0) return st;
+        }
+    BMFR_CUDA_TRY(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
+    BMFR_CUDA_TRY(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+    for (int s = 0; s < kHostSlots; ++s) {
+        BMFR_CUDA_TRY(cudaEventCreateWithFlags(&c->up_done[s], cudaEventDisableTiming));
+        BMFR_CUDA_TRY(cudaEventCreateWithFlags(&c->frame_done[s], cudaEventDisableTiming));
+    }
+    for (int i = 0; i < 2; ++i) BMFR_CUDA_TRY(cudaEventCreateWithFlags(&c->d2h_done[i], cudaEventDisableTiming));
+    c->host_ready = true;
+    return BMFR_OK;
+}
+
+int bmfr_denoise_frame_host(bmfr_ctx* c, int frame, const float* h_albedo, const float* h_normal,
+                            const float* h_position, const float* h_noisy, const float cam_prev[16],
+                            const float pixel_offset[2], float* h_out) {
+    if (!c || !h_albedo || !h_normal || !h_position || !h_noisy || !pixel_offset)
+        return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_denoise_frame_host: null argument");
+    BMFR_CUDA_TRY(cudaSetDevice(c->prm.device));
+    int st = host_path_init(c);
+    if (st != 0) return st;
+    const size_t bytes = rows_of(c) * (size_t)c->geo.width * 3 * sizeof(float);
+    const int slot = (int)(c->host_frames % kHostSlots);
+    // the slot was last read by the kernels of the call three frames ago (as "previous" two ago)
+    if (c->host_frames >= kHostSlots) BMFR_CUDA_TRY(cudaStreamWaitEvent(c->h2d_stream, c->frame_done[slot], 0));
+    const float* src[4] = {h_albedo, h_normal, h_position, h_noisy};
+    for (int k = 0; k < 4; ++k)  // bmfr.cpp:420-427
+        BMFR_CUDA_TRY(cudaMemcpyAsync(c->up[k][slot], src[k], bytes, cudaMemcpyHostToDevice, c->h2d_stream));
+    BMFR_CUDA_TRY(cudaEventRecord(c->up_done[slot], c->h2d_stream));
+    BMFR_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->up_done[slot], 0));
+    // result.current() of this frame was last read by the D2H of two frames ago
+    const int rslot = (int)(c->host_frames & 1);
+    if (c->host_frames >= 2) BMFR_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->d2h_done[rslot], 0));
+    float* d_result = c->result.current();
+    st = bmfr_denoise_frame(c, frame, c->up[0][slot], c->up[1][slot], c->up[2][slot], c->up[3][slot], cam_prev,
+                            pixel_offset, nullptr);
+    if (st != 0) return st;
+    // the previous frame's slot is released once this frame's kernels (which read it as "previous") are done
+    BMFR_CUDA_TRY(cudaEventRecord(c->frame_done[slot], c->stream));
+    if (c->host_frames >= 1) {
+        const int pslot = (int)((c->host_frames - 1) % kHostSlots);
+        BMFR_CUDA_TRY(cudaEventRecord(c->frame_done[pslot], c->stream));
+    }
+    if (h_out) {  // bmfr.cpp:479-480
+        BMFR_CUDA_TRY(cudaStreamWaitEvent(c->d2h_stream, c->frame_done[slot], 0));
+        const size_t off = (size_t)(c->geo.own_y0 - c->geo.row0) * c->geo.width * 3;
+        const size_t obytes = (size_t)(c->geo.own_y1 - c->geo.own_y0) * c->geo.width * 3 * sizeof(float);
+        BMFR_CUDA_TRY(cudaMemcpyAsync(h_out + off, d_result + off, obytes, cudaMemcpyDeviceToHost, c->d2h_stream));
+    }
+    BMFR_CUDA_TRY(cudaEventRecord(c->d2h_done[rslot], c->d2h_stream));
+    ++c->host_frames;
+    return BMFR_OK;
+}
+
+int bmfr_sync(bmfr_ctx* c) {
+    if (!c) return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_sync: null context");
+    BMFR_CUDA_TRY(cudaSetDevice(c->prm.device));
+    if (c->h2d_stream) BMFR_CUDA_TRY(cudaStreamSynchronize(c->h2d_stream));
+    BMFR_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (c->d2h_stream) BMFR_CUDA_TRY(cudaStreamSynchronize(c->d2h_stream));
+    int oob = 0;
+    BMFR_CUDA_TRY(cudaMemcpy(&oob, c->d_oob, sizeof(int), cudaMemcpyDeviceToHost));
+    if (oob) {
+        cudaMemset(c->d_oob, 0, sizeof(int));
+        return bmfr_set_error(BMFR_ERR_HALO_TOO_SMALL,
+                              "bmfr_sync: a gather or block left rows [%d,%d) held by this strip (halo_rows=%d too small "
+                              "for the camera motion)", c->geo.row0, c->geo.row1, c->prm.halo_rows);
+    }
+    return BMFR_OK;
+}
+
+int bmfr_get_buffer(bmfr_ctx* c, int buffer, void** d_ptr, size_t* bytes) {
+    if (!c || !d_ptr || !bytes) return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_get_buffer: null argument");
+    const size_t npix = rows_of(c) * (size_t)c->geo.width;
+    const size_t nb = (size_t)c->geo.blocks_x * c->geo.blocks_y;
+    void* p = nullptr;
+    size_t n = 0;
+    // after the swap at the end of a frame the buffers that frame wrote are the "previous" halves
+    switch (buffer) {
+        case BMFR_BUF_NOISY_ACC: p = c->noisy_acc.previous(); n = npix * 12; break;
+        case BMFR_BUF_SPP: p = c->spp.previous(); n = npix; break;
+        case BMFR_BUF_PREV_PIXELS: p = c->prev_pixels; n = npix * 8; break;
+        case BMFR_BUF_ACCEPT: p = c->accept; n = npix; break;
+        case BMFR_BUF_TMP_DATA: p = c->tmp_data; n = (size_t)c->tmp_block_rows * c->geo.blocks_x * BMFR_BUFFER_COUNT * BMFR_BLOCK_PIXELS * 4; break;
+        case BMFR_BUF_WEIGHTS: p = c->weights; n = nb * BMFR_FEATURES * 3 * 4; break;
+        case BMFR_BUF_MINS_MAXS: p = c->mins_maxs; n = nb * BMFR_FEATURES_SCALED * 2 * 4; break;
+        case BMFR_BUF_FILTERED: p = c->filtered; n = npix * 12; break;
+        case BMFR_BUF_ACCUM: p = c->accum.previous(); n = npix * 12; break;
+        case BMFR_BUF_TONE_MAPPED: p = c->tone_mapped; n = npix * 12; break;
+        case BMFR_BUF_RESULT: p = c->result.previous(); n = npix * 12; break;
+        case BMFR_BUF_NOISE_TILE: p = c->noise; n = (size_t)(BMFR_FEATURES - 1) * BMFR_BLOCK_PIXELS * 8; break;
+        default: return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_get_buffer: unknown buffer %d", buffer);
+    }
+    if (!p)
+        return bmfr_set_error(BMFR_ERR_UNSUPPORTED, "bmfr_get_buffer: buffer %d is not materialised in this mode", buffer);
+    *d_ptr = p;
+    *bytes = n;
+    return BMFR_OK;
+}
+
+int bmfr_read_buffer(bmfr_ctx* c, int buffer, void* h_dst, size_t bytes) {
+    void* p;
+    size_t n;
+    int st = bmfr_get_buffer(c, buffer, &p, &n);
+    if (st != 0) return st;
+    if (!h_dst || bytes > n) return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_read_buffer: %zu bytes requested, buffer has %zu", bytes, n);
+    st = bmfr_sync(c);
+    if (st != 0) return st;
+    BMFR_CUDA_TRY(cudaMemcpy(h_dst, p, bytes, cudaMemcpyDeviceToHost));
+    return BMFR_OK;
+}
+
+int bmfr_get_stage_ms(bmfr_ctx* c, int frame, float ms[BMFR_STAGE_COUNT]) {
+    if (!c || !ms) return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_get_stage_ms: null argument");
+    if (c->prof.empty()) return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_get_stage_ms: context created with profile=0");
+    StageEvents& s = c->prof[(size_t)frame % kProfileSlots];
+    if (!s.created || s.frame != frame) return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_get_stage_ms: frame %d not recorded", frame);
+    for (int i = 0; i < BMFR_STAGE_COUNT; ++i) ms[i] = 0.f;
+    if (c->prm.mode == BMFR_MODE_STAGED) {
+        BMFR_CUDA_TRY(cudaEventSynchronize(s.ev[5]));
+        for (int i = 0; i < 5; ++i) BMFR_CUDA_TRY(cudaEventElapsedTime(&ms[i], s.ev[i], s.ev[i + 1]));
+        BMFR_CUDA_TRY(cudaEventElapsedTime(&ms[BMFR_STAGE_TOTAL], s.ev[0], s.ev[5]));  // K1 start -> K5 end, bmfr.cpp:497-502
+    } else {
+        BMFR_CUDA_TRY(cudaEventSynchronize(s.ev[2]));
+        BMFR_CUDA_TRY(cudaEventElapsedTime(&ms[BMFR_STAGE_FITTER], s.ev[0], s.ev[1]));
+        BMFR_CUDA_TRY(cudaEventElapsedTime(&ms[BMFR_STAGE_TAA], s.ev[1], s.ev[2]));
+        BMFR_CUDA_TRY(cudaEventElapsedTime(&ms[BMFR_STAGE_TOTAL], s.ev[0], s.ev[2]));
+    }
+    return BMFR_OK;
+}
+
+int bmfr_get_halo_plan(const bmfr_ctx* c, int side, bmfr_halo_plan* out) {
+    if (!c || !out || (side != 0 && side != 1)) return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_get_halo_plan: bad argument");
+    const bmfr_geometry& g = c->geo;
+    const int halo = c->prm.halo_rows;
+    if (side == 0) {
+        out->recv_y0 = g.row0; out->recv_y1 = g.own_y0;
+        out->send_y0 = g.own_y0; out->send_y1 = (g.own_y0 > 0) ? ((g.own_y0 + halo < g.own_y1) ? g.own_y0 + halo : g.own_y1) : g.own_y0;
+    } else {
+        out->recv_y0 = g.own_y1; out->recv_y1 = g.row1;
+        out->send_y1 = g.own_y1; out->send_y0 = (g.own_y1 < g.height) ? ((g.own_y1 - halo > g.own_y0) ? g.own_y1 - halo : g.own_y0) : g.own_y1;
+    }
+    return BMFR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,125 @@
+"""TEST INFRASTRUCTURE — builds the two CPU checkers (see oracle/bmfr_oracle.h).
+
+  port      : oracle/bmfr_oracle.c -> oracle/libbmfr_oracle.so               (always)
+  reference : /root/reference/opencl/bmfr.cl, compiled as C++ through oracle/cl_shim/,
+              -> oracle/_ref/libbmfr_clref.so   (only where /root/reference exists; the GPU box
+              uses the prebuilt file that travels with the repo snapshot)
+
+The reference's sources are read where they lie; nothing of them is written outside oracle/_ref/,
+and the intermediate files are removed after the compile.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import re
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+REFERENCE = Path(os.environ.get("BMFR_REFERENCE_DIR", "/root/reference")) / "opencl"
+PORT_LIB = HERE / "libbmfr_oracle.so"
+REF_DIR = HERE / "_ref"
+REF_LIB = REF_DIR / "libbmfr_clref.so"
+
+CFLAGS = ["-O2", "-ffp-contract=off", "-fno-fast-math", "-fopenmp", "-fPIC", "-shared"]
+
+# OpenCL C constructs that C++ cannot express through the shim header alone.  Each rewrite is purely
+# syntactic, must match exactly `count` times, and is listed in DESIGN.md.
+REWRITES = [
+    # work-group-local variable declarations (as opposed to __local pointer qualifiers)
+    (r"__local float u_length_squared, dot, block_min, block_max, vec_length;",
+     "CLSHIM_WG_LOCAL float u_length_squared, dot, block_min, block_max, vec_length;", 1),
+    (r"local float3 divider;", "CLSHIM_WG_LOCAL float3 divider;", 1),
+    # the one vector ternary of the file (C++ cannot overload ?:)
+    (r"color = color < 0.f ? 0.f : color;", "color = vec_ternary(color < 0.f, 0.f, color);", 1),
+]
+
+
+def _stamp(paths, extra=""):
+    h = hashlib.sha256(extra.encode())
+    for p in paths:
+        h.update(Path(p).read_bytes())
+    return h.hexdigest()
+
+
+def build_port(force=False) -> Path:
+    src = [HERE / "bmfr_oracle.c", HERE / "bmfr_oracle.h"]
+    stamp = HERE / "_build" / "port.sha256"
+    digest = _stamp(src, " ".join(CFLAGS))
+    if not force and PORT_LIB.exists() and stamp.exists() and stamp.read_text() == digest:
+        return PORT_LIB
+    stamp.parent.mkdir(exist_ok=True)
+    cmd = ["gcc", "-std=gnu11", *CFLAGS, "-o", str(PORT_LIB), str(src[0]), "-lm"]
+    subprocess.run(cmd, check=True)
+    stamp.write_text(digest)
+    return PORT_LIB
+
+
+def _defines_from_bmfr_cpp(text: str) -> str:
+    """The -D options bmfr.cpp:205-232 derives from its own #defines (bmfr.cpp:56-118)."""
+    def strings_of(name):
+        m = re.search(r"#define %s \\\n((?:\".*\"\\?\n)+)" % name, text)
+        if not m:
+            raise RuntimeError(f"{name} not found in bmfr.cpp")
+        return "".join(re.findall(r"\"(.*?)\"", m.group(1)))
+    not_scaled, scaled = strings_of("NOT_SCALED_FEATURE_BUFFERS"), strings_of("SCALED_FEATURE_BUFFERS")
+    n_ns = not_scaled.count(",")          # bmfr.cpp:195-196
+    n_s = scaled.count(",") + 1           # bmfr.cpp:198-199
+    buffers = n_ns + n_s + 3              # bmfr.cpp:202
+    out = [
+        "// generated from /root/reference/opencl/bmfr.cpp by oracle/build_oracle.py — do not commit",
+        f"#define BUFFER_COUNT {buffers}",
+        f"#define FEATURES_NOT_SCALED {n_ns}",
+        f"#define FEATURES_SCALED {n_s}",
+        f"#define FEATURE_BUFFERS {not_scaled}{scaled}",
+        f"#define R_EDGE {buffers - 2}",
+    ]
+    for name in ("LOCAL_WIDTH", "LOCAL_HEIGHT", "BLOCK_EDGE_LENGTH", "LOCAL_SIZE", "COMPRESSED_R", "CACHE_TMP_DATA",
+                 "ADD_REQD_WG_SIZE"):
+        m = re.search(r"^#define %s (\d+)\s*$" % name, text, re.M)
+        if not m:
+            raise RuntimeError(f"{name} not found in bmfr.cpp")
+        out.append(f"#define {name} {m.group(1)}")
+    out.append("#define BLOCK_PIXELS (BLOCK_EDGE_LENGTH * BLOCK_EDGE_LENGTH)")
+    return "\n".join(out) + "\n"
+
+
+def build_reference(force=False):
+    """Returns the path of the reference-kernel library, or None when it cannot be (re)built."""
+    cl, cpp = REFERENCE / "bmfr.cl", REFERENCE / "bmfr.cpp"
+    shim = [HERE / "cl_shim" / "cl_shim.hpp", HERE / "cl_shim" / "cl_host.cpp", HERE / "bmfr_oracle.h"]
+    if not cl.exists() or not cpp.exists():
+        return REF_LIB if REF_LIB.exists() else None   # GPU box: use what travelled
+    digest = _stamp([cl, cpp, *shim, Path(__file__)], " ".join(CFLAGS))
+    stamp = REF_DIR / "ref.sha256"
+    if not force and REF_LIB.exists() and stamp.exists() and stamp.read_text() == digest:
+        return REF_LIB
+    work = REF_DIR / "gen"
+    work.mkdir(parents=True, exist_ok=True)
+    try:
+        src = cl.read_text()
+        for old, new, count in REWRITES:
+            if src.count(old) != count:
+                raise RuntimeError(f"rewrite {old!r}: expected {count} match(es), found {src.count(old)}")
+            src = src.replace(old, new)
+        (work / "bmfr_cl.gen.inc").write_text(src)
+        (work / "bmfr_defines.gen.h").write_text(_defines_from_bmfr_cpp(cpp.read_text()))
+        cmd = ["g++", "-std=gnu++17", *CFLAGS, "-Wno-narrowing", "-Wno-attributes", "-I", str(work),
+               "-o", str(REF_LIB), str(HERE / "cl_shim" / "cl_host.cpp"), "-lm"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("g++ failed on the shim build of bmfr.cl")
+        stamp.write_text(digest)
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+    return REF_LIB
+
+
+if __name__ == "__main__":
+    force = "--force" in sys.argv
+    print("port     :", build_port(force))
+    print("reference:", build_reference(force))
