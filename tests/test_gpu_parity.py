@@ -1,0 +1,62 @@
+"""Parity proper: the CUDA path, called through the C ABI, against the CPU oracle on the same
+seeded synthetic inputs.  Integer buffers and the per-pixel fp32 stages that contain no reduction
+must be bit-exact; fitted / accumulated colour must be within the north star's tolerance
+(per-pixel relative error <= 1e-3, PSNR >= 60 dB)."""
+import numpy as np
+import pytest
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+KEEP_FUSED = ("noisy_acc", "spp", "prev_pixels", "accept", "weights", "mins_maxs", "accum", "result", "noise_tile")
+KEEP_STAGED = KEEP_FUSED + ("tmp_data", "filtered", "tone_mapped")
+
+
+def _check_frames(cuda, ref, staged):
+    worst = dict(rel=0.0, psnr=1e9)
+    for f, (c, r) in enumerate(zip(cuda, ref)):
+        for k in util.INTEGER_BUFFERS:
+            assert util.bits_equal(c[k], r[k]), f"frame {f}: {k} differs in {(c[k] != r[k]).sum()} pixels"
+        for k in ("noisy_acc", "prev_pixels", "noise_tile") + (("tmp_data",) if staged else ()):
+            assert util.bits_equal(c[k], r[k]), f"frame {f}: {k} not bit-identical"
+        # floor(prev pixel) is what the north star names; it follows from the float equality above
+        assert np.array_equal(np.floor(c["prev_pixels"]), np.floor(r["prev_pixels"]))
+        assert util.floats_equal_mod_zero_sign(c["mins_maxs"], r["mins_maxs"]), f"frame {f}: mins_maxs differ"
+        for k in util.COLOUR_BUFFERS + (("filtered", "tone_mapped") if staged else ()):
+            rel, psnr = util.assert_colour_close(c[k], r[k], f"frame {f} {k}")
+            worst["rel"], worst["psnr"] = max(worst["rel"], rel), min(worst["psnr"], psnr)
+    return worst
+
+
+@pytest.mark.parametrize("mode", ["staged", "fused"])
+@pytest.mark.parametrize("size", [(160, 96), (200, 120), (416, 250)])
+def test_sequence_matches_oracle(mode, size):
+    """20 frames: every BLOCK_OFFSETS entry, ragged sizes (not multiples of 32), frame-0 path."""
+    w, h = size
+    keep = KEEP_STAGED if mode == "staged" else KEEP_FUSED
+    ref = util.run_oracle("port", w, h, 20, keep=keep)
+    cuda = util.run_cuda(w, h, 20, mode=mode, keep=keep)
+    worst = _check_frames(cuda, ref, mode == "staged")
+    print(f"{mode} {w}x{h}: worst rel {worst['rel']:.2e}, worst PSNR {worst['psnr']:.1f} dB")
+
+
+def test_jittered_offsets_match_oracle():
+    ref = util.run_oracle("port", 200, 120, 8, keep=KEEP_FUSED, jitter=True)
+    cuda = util.run_cuda(200, 120, 8, mode="fused", keep=KEEP_FUSED, jitter=True)
+    _check_frames(cuda, ref, False)
+
+
+def test_720p_matches_oracle():
+    """BASELINE.json configs[1] geometry, first frames."""
+    ref = util.run_oracle("port", 1280, 720, 4, keep=KEEP_FUSED)
+    cuda = util.run_cuda(1280, 720, 4, mode="fused", keep=KEEP_FUSED)
+    _check_frames(cuda, ref, False)
+
+
+def test_staged_and_fused_agree_bitwise():
+    """Both kernel structures run the same per-pixel code: every shared buffer is bit-identical."""
+    a = util.run_cuda(416, 250, 6, mode="staged", keep=KEEP_FUSED, every_frame=False)[0]
+    b = util.run_cuda(416, 250, 6, mode="fused", keep=KEEP_FUSED, every_frame=False)[0]
+    for k in KEEP_FUSED:
+        assert util.bits_equal(a[k], b[k]), k
