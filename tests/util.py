@@ -77,3 +77,44 @@ def assert_colour_close(a, b, what):
     assert rel <= REL, f"{what}: max relative error {rel:.3e} > {REL} (eps floor {EPS})"
     assert psnr >= PSNR_DB, f"{what}: PSNR {psnr:.1f} dB < {PSNR_DB}"
     return rel, psnr
+
+
+# ------------------------------------------------------------------------------------------------
+# one interface over the four implementations, for tests that feed hand-made inputs
+# ------------------------------------------------------------------------------------------------
+BACKENDS_CPU = ("port", "reference")
+BACKENDS_GPU = ("cuda-staged", "cuda-fused")
+
+
+class Runner:
+    """backend: "port" | "reference" (CPU checkers) | "cuda-staged" | "cuda-fused" (the product)."""
+
+    def __init__(self, backend, width, height, **params):
+        self.backend, self.W, self.H = backend, width, height
+        pl, nl = synth.limits()
+        params.setdefault("position_limit_squared", pl)
+        params.setdefault("normal_limit_squared", nl)
+        if backend.startswith("cuda"):
+            self.impl = Denoiser(width, height, mode=backend.split("-")[1], **params)
+        else:
+            self.impl = Oracle(backend, width, height, keep_tmp=1, **params)
+
+    def frame(self, f, albedo, normal, position, noisy, cam_prev, pixel_offset):
+        if self.backend.startswith("cuda"):
+            self.impl.denoise_frame_host(f, albedo, normal, position, noisy, cam_prev, pixel_offset)
+        else:
+            self.impl.frame(f, albedo, normal, position, noisy, cam_prev, pixel_offset)
+
+    def get(self, name):
+        return self.impl.read(name) if self.backend.startswith("cuda") else self.impl.buffer(name)
+
+    def close(self):
+        self.impl.close()
+
+
+def backend_params(gpu_too=True):
+    import pytest
+    ps = [pytest.param(b, id=b) for b in BACKENDS_CPU]
+    if gpu_too:
+        ps += [pytest.param(b, id=b, marks=pytest.mark.gpu) for b in BACKENDS_GPU]
+    return ps
