@@ -197,8 +197,11 @@ def run_single_gpu(args):
         raise SystemExit("bench.py: no CUDA device — the bmfr_b200 path has no CPU fallback")
     w, h = args.width or SINGLE_GPU_WORKLOAD[0], args.height or SINGLE_GPU_WORKLOAD[1]
     torch.cuda.set_device(0)
-    stream = torch.cuda.current_stream()
+    # an explicit stream: torch's default stream has handle 0, which the C ABI reads as "create one"
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     sp = stream.cuda_stream
+    assert sp != 0
 
     # inputs resident in HBM: 60 frames x 4 images (5.97 GB at 1080p, far larger than the 126 MB L2)
     inputs = torch.empty((FRAMES, 4, h, w, 3), dtype=torch.float32, device="cuda")

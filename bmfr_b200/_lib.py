@@ -5,8 +5,12 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
+import os
+
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "libbmfr_b200.so"
+# BMFR_B200_LIB selects another build of the same library (kernel-tuning experiments); it is still
+# this package's CUDA library, never a fallback.
+LIB_PATH = Path(os.environ.get("BMFR_B200_LIB") or PKG / "libbmfr_b200.so")
 
 STATUS = {0: "BMFR_OK", -1: "BMFR_ERR_INVALID_ARGUMENT", -2: "BMFR_ERR_NO_DEVICE", -3: "BMFR_ERR_CUDA",
           -4: "BMFR_ERR_OUT_OF_MEMORY", -5: "BMFR_ERR_UNSUPPORTED", -6: "BMFR_ERR_HALO_TOO_SMALL",

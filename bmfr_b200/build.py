@@ -42,8 +42,11 @@ def _digest(paths, extra: str) -> str:
     return h.hexdigest()
 
 
-def build_library(force: bool = False, verbose: bool = False, extra_flags=()) -> Path:
-    """Compile csrc/*.cu into bmfr_b200/libbmfr_b200.so (skipped when sources are unchanged)."""
+def build_library(force: bool = False, verbose: bool = False, extra_flags=(), out: Path | None = None) -> Path:
+    """Compile csrc/*.cu into bmfr_b200/libbmfr_b200.so (skipped when sources are unchanged).
+    `out` + `extra_flags` build a tuning variant next to it (see scripts/)."""
+    if out is not None:
+        return _build_variant(out, list(extra_flags), verbose)
     deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + [ROOT / "include" / "bmfr_b200.h"]
     stamp = BUILD_DIR / "lib.sha256"
     digest = _digest(deps, " ".join(NVCC_FLAGS + list(extra_flags)))
@@ -71,6 +74,24 @@ def build_library(force: bool = False, verbose: bool = False, extra_flags=()) ->
         raise RuntimeError("link of libbmfr_b200.so failed")
     stamp.write_text(digest)
     return LIB
+
+
+def _build_variant(out: Path, extra_flags, verbose):
+    nvcc = _nvcc()
+    vdir = BUILD_DIR / out.stem
+    vdir.mkdir(parents=True, exist_ok=True)
+    objs = []
+    for src in CUDA_SOURCES:
+        obj = vdir / (src + ".o")
+        r = subprocess.run([nvcc, *NVCC_FLAGS, *extra_flags, "-c", str(CSRC / src), "-o", str(obj)], capture_output=True, text=True)
+        (vdir / (src + ".log")).write_text(r.stdout + r.stderr)
+        if verbose or r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}")
+        objs.append(str(obj))
+    subprocess.run([nvcc, "-shared", "-o", str(out), *objs, "-Xcompiler", "-fopenmp", "-lgomp"], check=True)
+    return out
 
 
 if __name__ == "__main__":

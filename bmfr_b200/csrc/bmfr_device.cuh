@@ -41,12 +41,15 @@ __device__ __forceinline__ int mirror_index(int i, int size) {
     return i;
 }
 
-// scale(), bmfr.cl:200-205
-__device__ __forceinline__ float scale_feature(float v, float mn, float mx) {
+// scale(), bmfr.cl:200-205: (v - min) / (max - min) if |max - min| > 1 else v - min.
+// The block-uniform divisor is inverted once (scale_factor) and applied as a multiply in both the
+// fit and the weighted sum, so the two stay consistent; the scaled value differs from the
+// reference's quotient by at most one ulp (inside the colour tolerance; mins_maxs stay exact).
+__device__ __forceinline__ float scale_factor(float mn, float mx) {
     const float d = mx - mn;
-    if (fabsf(d) > 1.0f) return (v - mn) / d;
-    return v - mn;
+    return (fabsf(d) > 1.0f) ? 1.0f / d : 1.0f;
 }
+__device__ __forceinline__ float scale_feature(float v, float mn, float inv) { return (v - mn) * inv; }
 
 // random(), bmfr.cl:162-171 — integer hash; float(a) / float(UINT_MAX) == float(a) * 2^-32 exactly
 __host__ __device__ __forceinline__ float bmfr_random(unsigned int a) {
@@ -98,28 +101,38 @@ __device__ __forceinline__ K1Pixel k1_pixel(const KParams& P, int x, int y) {
         const float omx = 1.f - frx, omy = 1.f - fry;
         const float w[4] = {omx * omy, frx * omy, omx * fry, frx * fry};  // bmfr.cl:367-370
         float total = 0.f;
+        // The four taps are fetched unconditionally from clamped addresses (one round of independent
+        // loads instead of three dependent ones) and the reference's nested tests (bmfr.cl:380-404)
+        // become predicates; a rejected tap contributes nothing, exactly as in the branchy form.
+        const int rlo = P.row0, rhi = P.row1 - 1;
+        f3 tp[4], tn[4], tc[4];
+        float ts[4];
+        bool valid[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int sx = pix + (i & 1), sy = piy + (i >> 1);
-            if (sx >= 0 && sy >= 0 && sx < P.W && sy < P.H) {  // bmfr.cl:380-381
-                if (sy < P.row0 || sy >= P.row1) {  // strip + halo does not hold this row
-                    *P.oob_flag = 1;
-                    continue;
-                }
-                const size_t ls = pix_index(P, sx, sy);
-                const f3 pd = sub3(load_f3(P.prev_positions, ls), wp);
-                if (dot3(pd, pd) < P.pos_limit) {  // bmfr.cl:388-393
-                    const f3 nd = sub3(load_f3(P.prev_normals, ls), n);
-                    if (dot3(nd, nd) < P.nrm_limit) {  // bmfr.cl:401-404
-                        accept |= 1u << i;
-                        sample_spp = sample_spp + w[i] * (float)P.prev_spp[ls];
-                        const f3 pc = load_f3(P.prev_noisy_acc, ls);
-                        prev.x = prev.x + w[i] * pc.x;
-                        prev.y = prev.y + w[i] * pc.y;
-                        prev.z = prev.z + w[i] * pc.z;
-                        total = total + w[i];
-                    }
-                }
+            const bool inimg = sx >= 0 && sy >= 0 && sx < P.W && sy < P.H;  // bmfr.cl:380-381
+            const bool held = sy >= P.row0 && sy < P.row1;
+            if (inimg && !held) *P.oob_flag = 1;  // strip + halo does not hold this row
+            valid[i] = inimg && held;
+            const size_t ls = pix_index(P, min(max(sx, 0), P.W - 1), min(max(sy, rlo), rhi));
+            tp[i] = load_f3(P.prev_positions, ls);
+            tn[i] = load_f3(P.prev_normals, ls);
+            tc[i] = load_f3(P.prev_noisy_acc, ls);
+            ts[i] = (float)P.prev_spp[ls];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const f3 pd = sub3(tp[i], wp);
+            const f3 nd = sub3(tn[i], n);
+            const bool ok = valid[i] && (dot3(pd, pd) < P.pos_limit) && (dot3(nd, nd) < P.nrm_limit);  // bmfr.cl:388-404
+            if (ok) {
+                accept |= 1u << i;
+                sample_spp = sample_spp + w[i] * ts[i];
+                prev.x = prev.x + w[i] * tc[i].x;
+                prev.y = prev.y + w[i] * tc[i].y;
+                prev.z = prev.z + w[i] * tc[i].z;
+                total = total + w[i];
             }
         }
         if (total > 0.f) {  // bmfr.cl:421-429
@@ -174,19 +187,20 @@ __device__ __forceinline__ void k1_features(const K1Pixel& r, float* f) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// K3 per pixel: weighted_sum, bmfr.cl:725-750.  w = 30 weights, mm = 12 min/max of the block.
+// K3 per pixel: weighted_sum, bmfr.cl:725-750.  w = 30 weights, mi = 6 (min, 1/range) pairs of the
+// block.  The sum is compared with the reference within tolerance, so it is written with fmaf().
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ f3 k3_pixel(f3 n, f3 p, const float* __restrict__ w, const float* __restrict__ mm) {
+__device__ __forceinline__ f3 k3_pixel(f3 n, f3 p, const float* __restrict__ w, const float* __restrict__ mi) {
     float feat[BMFR_FEATURES] = {1.f, n.x, n.y, n.z, p.x, p.y, p.z, p.x * p.x, p.y * p.y, p.z * p.z};
     f3 c = make_f3(0.f, 0.f, 0.f);
 #pragma unroll
     for (int f = 0; f < BMFR_FEATURES; ++f) {
         float v = feat[f];
         if (f >= BMFR_FEATURES_NOT_SCALED)
-            v = scale_feature(v, mm[(f - BMFR_FEATURES_NOT_SCALED) * 2], mm[(f - BMFR_FEATURES_NOT_SCALED) * 2 + 1]);
-        c.x = c.x + w[f * 3 + 0] * v;
-        c.y = c.y + w[f * 3 + 1] * v;
-        c.z = c.z + w[f * 3 + 2] * v;
+            v = scale_feature(v, mi[(f - BMFR_FEATURES_NOT_SCALED) * 2], mi[(f - BMFR_FEATURES_NOT_SCALED) * 2 + 1]);
+        c.x = fmaf(w[f * 3 + 0], v, c.x);
+        c.y = fmaf(w[f * 3 + 1], v, c.y);
+        c.z = fmaf(w[f * 3 + 2], v, c.z);
     }
     c.x = c.x < 0.f ? 0.f : c.x;  // keeps NaN like the reference, bmfr.cl:750
     c.y = c.y < 0.f ? 0.f : c.y;
@@ -203,11 +217,13 @@ __device__ __forceinline__ int k3_group(const KParams& P, int x, int y) {
 // K4 per pixel: accumulate_filtered_data, bmfr.cl:778-856.
 // ---------------------------------------------------------------------------------------------
 #ifndef BMFR_FAST_POW
-#define BMFR_FAST_POW 0
+#define BMFR_FAST_POW 1
 #endif
 __device__ __forceinline__ float tone_map(float v) {  // clamp(powr(max(0,v), 0.454545f), 0, 1)
     v = fmaxf(0.f, v);
 #if BMFR_FAST_POW
+    // powr through the SFU: |error| of __log2f is ~2^-22 absolute, so the result is within a few
+    // 1e-7 relative of powf on [0, 2^10] — three orders below the colour tolerance
     v = exp2f(0.454545f * __log2f(v));
 #else
     v = powf(v, 0.454545f);
@@ -276,8 +292,7 @@ __device__ __forceinline__ void taa_box_init(TaaBox& b) {
     b.min_box = b.min_cross = make_f3(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F);
     b.max_box = b.max_cross = make_f3(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
 }
-__device__ __forceinline__ void taa_box_add(TaaBox& b, f3 rgb, bool cross) {
-    const f3 s = rgb_to_ycocg(rgb);
+__device__ __forceinline__ void taa_box_add_ycocg(TaaBox& b, f3 s, bool cross) {
     if (cross) {
         b.min_cross = min3(b.min_cross, s);
         b.max_cross = max3(b.max_cross, s);
@@ -285,6 +300,7 @@ __device__ __forceinline__ void taa_box_add(TaaBox& b, f3 rgb, bool cross) {
     b.min_box = min3(b.min_box, s);
     b.max_box = max3(b.max_box, s);
 }
+__device__ __forceinline__ void taa_box_add(TaaBox& b, f3 rgb, bool cross) { taa_box_add_ycocg(b, rgb_to_ycocg(rgb), cross); }
 
 // Everything of taa after the 3x3 neighbourhood: bilinear history fetch, clamp, blend (bmfr.cl:922-973).
 __device__ __forceinline__ f3 taa_resolve(const KParams& P, f3 my_new, const TaaBox& b, float prev_x, float prev_y,
@@ -330,80 +346,107 @@ __device__ __forceinline__ f3 taa_resolve(const KParams& P, f3 my_new, const Taa
 // ---------------------------------------------------------------------------------------------
 // The fit: fitter, bmfr.cl:490-700, for one 32x32 block held in registers.
 //
-// The reference runs a Householder QR of the 1024x13 matrix with 577 work-group barriers and 193
-// passes over global memory per block.  Here the matrix never leaves registers: thread `tid` owns
-// rows tid + 256*s (the reference's IN_ACCESS ownership, bmfr.cl:90-97), the QR is a two-level
-// TSQR — each warp factors its own 128 rows with shuffles only, then one warp factors the eight
-// stacked 10x13 triangles — and the back-substitution runs in that same warp.  R of a QR with a
-// positive diagonal is unique, so this computes the reference's R(0..9, 0..12) up to rounding.
+// The reference runs a Householder QR of the 1024x13 matrix [features | colour] with 577 work-group
+// barriers and 193 passes over global memory per block, then back-substitutes R(0..9,0..9) x =
+// R(0..9,10..12).  Here the matrix never leaves registers: thread `tid` owns rows tid + 256*s (the
+// reference's IN_ACCESS ownership, bmfr.cl:90-97) and R is computed by a two-level TSQR — each warp
+// factors its own 128 rows without any block barrier, then one warp factors the eight stacked 10x13
+// triangles and back-substitutes.
+//
+// Each reflector is taken against a virtual zero pivot row appended to the matrix.  With pivot
+// entry 0 the reference's formulas (bmfr.cl:580-587,650) collapse: |x| = sqrt(S_k), u_k = -|x|,
+// u_length_squared = 2 S_k, and a_j -= a_k * S_j / S_k with S_j = a_k . a_j, R_kj = S_j / sqrt(S_k)
+// — i.e. one modified-Gram-Schmidt step on the augmented matrix, which is the Householder QR of
+// [0; A] (Bjorck) and backward stable for the least-squares solution.  It needs no pivot broadcast
+// and no per-lane masks.  R of a QR with positive diagonal is unique, so this is the reference's
+// R(0..9, 0..12) up to fp32 rounding (tests: colour within 1e-3 relative of the oracle).
+//
+// The per-reflector reduction of the 13-k sums S_j over a warp goes through shared memory as a
+// transpose (n stores, a few 128-bit loads and a short add tree per lane) instead of 5*n shuffles.
 // ---------------------------------------------------------------------------------------------
+#define BMFR_FIT_WARPS (BMFR_FIT_THREADS / 32)
+#define BMFR_RED_STRIDE 36  // floats per row of the transpose buffer: 16-byte aligned, bank-shifted
 
-// One Householder step k on a tall matrix distributed over a warp: lane l holds NS rows, columns
-// 0..12, in a[s][c].  The pivot row of step k is slot 0 of lane k; slot 0 of lanes < k holds the
-// finished rows of R.  Mirrors bmfr.cl:553-655 for col = k < 10 (u_k = a_kk - |x|, R_kk = +|x|).
+struct FitShared {
+    float red[BMFR_FIT_WARPS][BMFR_BUFFER_COUNT][BMFR_RED_STRIDE];  // per-warp transpose buffer
+    float coef[BMFR_FIT_WARPS][16];                                   // per-warp S_j / S_k broadcast
+    float rstack[BMFR_FIT_WARPS * BMFR_FEATURES + 16][BMFR_BUFFER_COUNT];  // level-1 R factors, stacked (zero padded to 96)
+    float rfinal[BMFR_FEATURES][BMFR_BUFFER_COUNT];                   // level-2 R
+    float minmax[BMFR_FIT_WARPS][2 * BMFR_FEATURES_SCALED];
+};
+
+// One reflector (column K) of a matrix whose rows are spread over a warp, NS rows per lane.
+// rrow receives row K of R (entries K..12).
 template <int NS, int K>
-__device__ __forceinline__ void householder_step(float (&a)[NS][BMFR_BUFFER_COUNT], int lane) {
-    constexpr int NC = BMFR_BUFFER_COUNT;
-    // column k restricted to the rows below the pivot
-    float u[NS];
-    u[0] = (lane > K) ? a[0][K] : 0.f;
+__device__ __forceinline__ void reflector_step(float (&a)[NS][BMFR_BUFFER_COUNT], float* __restrict__ red,
+                                               float* __restrict__ coefbuf, float* __restrict__ rrow, int lane) {
+    constexpr int N = BMFR_BUFFER_COUNT - K;   // columns K..12 take part
+    constexpr int PARTS = (N > 8) ? 2 : 4;     // lanes that share one column's 32 partial sums
+    constexpr int VALS = 32 / PARTS;           // columns handled per pass: 16 or 8
+    constexpr int LEN = 32 / PARTS;            // partial sums per lane: 16 or 8
+    // partial S_j = sum over this lane's rows of a_k * a_j
 #pragma unroll
-    for (int s = 1; s < NS; ++s) u[s] = a[s][K];
-    // S_j = sum_{rows below pivot} a_rk * a_rj for j = k..12 (S_k = sigma), one batched reduction
-    float S[NC];
+    for (int j = 0; j < N; ++j) {
+        float acc = a[0][K] * a[0][K + j];
 #pragma unroll
-    for (int j = K; j < NC; ++j) {
-        float acc = u[0] * a[0][j];
-#pragma unroll
-        for (int s = 1; s < NS; ++s) acc = fmaf(u[s], a[s][j], acc);
-        S[j] = acc;
+        for (int s = 1; s < NS; ++s) acc = fmaf(a[s][K], a[s][K + j], acc);
+        red[j * BMFR_RED_STRIDE + lane] = acc;
+    }
+    __syncwarp();
+    const int jj = lane % VALS, q = lane / VALS;
+    float t = 0.f;
+    if (jj < N) {
+        const float4* src = reinterpret_cast<const float4*>(red + jj * BMFR_RED_STRIDE + q * LEN);
+        float4 v0 = src[0], v1 = src[1];
+        float t0 = (v0.x + v0.y) + (v0.z + v0.w), t1 = (v1.x + v1.y) + (v1.z + v1.w);
+        if (LEN == 16) {
+            float4 v2 = src[2], v3 = src[3];
+            t0 += (v2.x + v2.y) + (v2.z + v2.w);
+            t1 += (v3.x + v3.y) + (v3.z + v3.w);
+        }
+        t = t0 + t1;
     }
 #pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) {
-#pragma unroll
-        for (int j = K; j < NC; ++j) S[j] += __shfl_xor_sync(0xffffffffu, S[j], m);
+    for (int m = VALS; m < 32; m <<= 1) t += __shfl_xor_sync(0xffffffffu, t, m);
+    const float sk = __shfl_sync(0xffffffffu, t, 0);  // S_k = |a_k|^2
+    const float c = t * (1.0f / sk);                  // 2 * dot / u_length_squared of bmfr.cl:650
+    if (lane < N) {
+        rrow[K + lane] = c * sqrtf(sk);               // R_kj ; R_kk = sqrt(S_k) = vec_length, bmfr.cl:583
+        coefbuf[lane] = c;
     }
-    // pivot row, broadcast from lane k
-    float piv[NC];
+    __syncwarp();
+    float cj[16];
 #pragma unroll
-    for (int j = K; j < NC; ++j) piv[j] = __shfl_sync(0xffffffffu, a[0][j], K);
-    const float alpha = piv[K];
-    const float norm = sqrtf(fmaf(alpha, alpha, S[K]));
-    // u_k = alpha - |x| ; written without cancellation when alpha > 0
-    const float vk = (alpha > 0.f) ? -S[K] / (alpha + norm) : alpha - norm;
-    const float ulen2 = fmaf(vk, vk, S[K]);  // u_length_squared, bmfr.cl:582-585
-    const float inv = 2.f / ulen2;
-    if (lane == K) u[0] = vk;
-#pragma unroll
-    for (int j = K + 1; j < NC; ++j) {
-        const float coef = fmaf(vk, piv[j], S[j]) * inv;  // 2 * dot / u_length_squared, bmfr.cl:650
-#pragma unroll
-        for (int s = 0; s < NS; ++s) a[s][j] = fmaf(-u[s], coef, a[s][j]);
+    for (int i = 0; i < (N + 3) / 4; ++i) {
+        const float4 v = reinterpret_cast<const float4*>(coefbuf)[i];
+        cj[4 * i] = v.x; cj[4 * i + 1] = v.y; cj[4 * i + 2] = v.z; cj[4 * i + 3] = v.w;
     }
-    if (lane == K) a[0][K] = norm;  // R_kk
+#pragma unroll
+    for (int j = 1; j < N; ++j) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) a[s][K + j] = fmaf(-a[s][K], cj[j], a[s][K + j]);
+    }
 }
 
 template <int NS, int K>
-struct HouseholderLoop {
-    static __device__ __forceinline__ void run(float (&a)[NS][BMFR_BUFFER_COUNT], int lane) {
-        householder_step<NS, K>(a, lane);
-        HouseholderLoop<NS, K + 1>::run(a, lane);
+struct ReflectorLoop {
+    static __device__ __forceinline__ void run(float (&a)[NS][BMFR_BUFFER_COUNT], float* red, float* coefbuf,
+                                               float (*rrows)[BMFR_BUFFER_COUNT], int lane) {
+        reflector_step<NS, K>(a, red, coefbuf, rrows[K], lane);
+        ReflectorLoop<NS, K + 1>::run(a, red, coefbuf, rrows, lane);
     }
 };
 template <int NS>
-struct HouseholderLoop<NS, BMFR_FEATURES> {
-    static __device__ __forceinline__ void run(float (&)[NS][BMFR_BUFFER_COUNT], int) {}
+struct ReflectorLoop<NS, BMFR_FEATURES> {
+    static __device__ __forceinline__ void run(float (&)[NS][BMFR_BUFFER_COUNT], float*, float*,
+                                               float (*)[BMFR_BUFFER_COUNT], int) {}
 };
 
-struct FitShared {
-    float red[BMFR_FIT_THREADS / 32][2 * BMFR_FEATURES_SCALED];          // per-warp min/max
-    float rstack[BMFR_FIT_THREADS / 32][BMFR_FEATURES][BMFR_BUFFER_COUNT];  // per-warp R (10x13)
-};
-
-// a[s][c]: the 13 K1 values of rows tid + 256*s.  On return weights/mins_maxs of `group` are written.
+// a[s][c]: the 13 K1 values of rows tid + 256*s.  On return weights / mins_maxs / mins_inv of `group`
+// are written.
 __device__ __forceinline__ void block_fit(float (&a)[BMFR_ROWS_PER_THREAD][BMFR_BUFFER_COUNT], FitShared& sh,
                                           const double* __restrict__ noise, float* __restrict__ weights,
-                                          float* __restrict__ mins_maxs, int group) {
+                                          float* __restrict__ mins_maxs, float* __restrict__ mins_inv, int group) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NSC = BMFR_FEATURES_SCALED, NNS = BMFR_FEATURES_NOT_SCALED;
 
@@ -426,68 +469,75 @@ __device__ __forceinline__ void block_fit(float (&a)[BMFR_ROWS_PER_THREAD][BMFR_
     if (lane == 0) {
 #pragma unroll
         for (int f = 0; f < NSC; ++f) {
-            sh.red[warp][2 * f] = mn[f];
-            sh.red[warp][2 * f + 1] = mx[f];
+            sh.minmax[warp][2 * f] = mn[f];
+            sh.minmax[warp][2 * f + 1] = mx[f];
         }
     }
+    if (tid < 16 * BMFR_BUFFER_COUNT) (&sh.rstack[BMFR_FIT_WARPS * BMFR_FEATURES][0])[tid] = 0.f;  // padding rows
     __syncthreads();
+    float inv[NSC];
 #pragma unroll
     for (int f = 0; f < NSC; ++f) {
-        float lo = sh.red[0][2 * f], hi = sh.red[0][2 * f + 1];
+        float lo = sh.minmax[0][2 * f], hi = sh.minmax[0][2 * f + 1];
 #pragma unroll
-        for (int w = 1; w < BMFR_FIT_THREADS / 32; ++w) {
-            lo = fminf(lo, sh.red[w][2 * f]);
-            hi = fmaxf(hi, sh.red[w][2 * f + 1]);
+        for (int w = 1; w < BMFR_FIT_WARPS; ++w) {
+            lo = fminf(lo, sh.minmax[w][2 * f]);
+            hi = fmaxf(hi, sh.minmax[w][2 * f + 1]);
         }
         mn[f] = lo;
         mx[f] = hi;
+        inv[f] = scale_factor(lo, hi);
     }
-    if (tid < 2 * NSC) mins_maxs[(size_t)group * 2 * NSC + tid] = (tid & 1) ? mx[tid >> 1] : mn[tid >> 1];
+    if (tid < 2 * NSC) {
+        mins_maxs[(size_t)group * 2 * NSC + tid] = (tid & 1) ? mx[tid >> 1] : mn[tid >> 1];
+        mins_inv[(size_t)group * 2 * NSC + tid] = (tid & 1) ? inv[tid >> 1] : mn[tid >> 1];
+    }
 
     // scale (bmfr.cl:538-541), then the noise of the first touch (bmfr.cl:623-627) on columns 1..9
     // — in fp64 like the reference's double literal NOISE_AMOUNT, rounded to fp32 once.
 #pragma unroll
     for (int s = 0; s < BMFR_ROWS_PER_THREAD; ++s) {
 #pragma unroll
-        for (int f = 0; f < NSC; ++f) a[s][NNS + f] = scale_feature(a[s][NNS + f], mn[f], mx[f]);
+        for (int f = 0; f < NSC; ++f) a[s][NNS + f] = scale_feature(a[s][NNS + f], mn[f], inv[f]);
 #pragma unroll
         for (int c = 1; c < BMFR_FEATURES; ++c)
-            a[s][c] = (float)((double)a[s][c] + noise[(c - 1) * BMFR_BLOCK_PIXELS + tid + BMFR_FIT_THREADS * s]);
+            a[s][c] = (float)((double)a[s][c] + __ldg(&noise[(c - 1) * BMFR_BLOCK_PIXELS + tid + BMFR_FIT_THREADS * s]));
     }
 
-    // (ii) level 1 of the TSQR: every warp factors its own 128 rows
-    HouseholderLoop<BMFR_ROWS_PER_THREAD, 0>::run(a, lane);
-    if (lane < BMFR_FEATURES) {
-#pragma unroll
-        for (int c = 0; c < BMFR_BUFFER_COUNT; ++c) sh.rstack[warp][lane][c] = (c >= lane) ? a[0][c] : 0.f;
-    }
+    // (ii) level 1 of the TSQR: every warp factors its own 128 rows, no block barrier
+    ReflectorLoop<BMFR_ROWS_PER_THREAD, 0>::run(a, &sh.red[warp][0][0], sh.coef[warp],
+                                                &sh.rstack[warp * BMFR_FEATURES], lane);
     __syncthreads();
 
-    // level 2 + (iii) back-substitution in warp 0: 80 stacked rows, three per lane
+    // level 2 + (iii) back-substitution in warp 0: 80 stacked rows (+16 zero rows), three per lane
     if (warp == 0) {
         constexpr int NS2 = 3;
         float b[NS2][BMFR_BUFFER_COUNT];
-        const float* flat = &sh.rstack[0][0][0];
 #pragma unroll
         for (int s = 0; s < NS2; ++s) {
             const int row = lane + 32 * s;
+            const int k = row % BMFR_FEATURES;  // rows of a level-1 R are zero left of their diagonal
 #pragma unroll
             for (int c = 0; c < BMFR_BUFFER_COUNT; ++c)
-                b[s][c] = (row < (BMFR_FIT_THREADS / 32) * BMFR_FEATURES) ? flat[row * BMFR_BUFFER_COUNT + c] : 0.f;
+                b[s][c] = (row >= BMFR_FIT_WARPS * BMFR_FEATURES || c >= k) ? sh.rstack[row][c] : 0.f;
         }
-        HouseholderLoop<NS2, 0>::run(b, lane);
-        // lane i < 10 now holds row i of R: b[0][i..12].  Solve R x = rhs for the three channels.
-        float rhs[3] = {b[0][10], b[0][11], b[0][12]};
+        ReflectorLoop<NS2, 0>::run(b, &sh.red[0][0][0], sh.coef[0], sh.rfinal, lane);
+        __syncwarp();
+        // lane i < 10 takes row i of R; solve R x = rhs for the three channels (bmfr.cl:659-692)
+        const int r = lane < BMFR_FEATURES ? lane : 0;
+        float row[BMFR_BUFFER_COUNT];
+#pragma unroll
+        for (int c = 0; c < BMFR_BUFFER_COUNT; ++c) row[c] = sh.rfinal[r][c];
+        float rhs[3] = {row[10], row[11], row[12]};
         float x[3] = {0.f, 0.f, 0.f};
 #pragma unroll
         for (int i = BMFR_FEATURES - 1; i >= 0; --i) {
-            const float d = __shfl_sync(0xffffffffu, b[0][i], i);  // R_ii
-            float xi[3];
+            const float d = __shfl_sync(0xffffffffu, row[i], i);  // R_ii
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                xi[c] = __shfl_sync(0xffffffffu, rhs[c], i) / d;
-                if (lane == i) x[c] = xi[c];
-                if (lane < i) rhs[c] = fmaf(-b[0][i], xi[c], rhs[c]);
+                const float xi = __shfl_sync(0xffffffffu, rhs[c], i) / d;
+                if (lane == i) x[c] = xi;
+                if (lane < i) rhs[c] = fmaf(-row[i], xi, rhs[c]);
             }
         }
         if (lane < BMFR_FEATURES) {

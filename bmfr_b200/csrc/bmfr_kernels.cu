@@ -52,9 +52,12 @@ __global__ void __launch_bounds__(256) k1_accumulate_noisy_kernel(const __grid_c
     }
 }
 
+#ifndef BMFR_FIT_MIN_BLOCKS
+#define BMFR_FIT_MIN_BLOCKS 2
+#endif
 // STAGED K2: one CTA per block, reads K1's block-planar tmp_data (bmfr.cl:490-700).
-__global__ void __launch_bounds__(BMFR_FIT_THREADS) k2_fitter_kernel(const __grid_constant__ KParams P) {
-    __shared__ FitShared sh;
+__global__ void __launch_bounds__(BMFR_FIT_THREADS, BMFR_FIT_MIN_BLOCKS) k2_fitter_kernel(const __grid_constant__ KParams P) {
+    __shared__ __align__(16) FitShared sh;
     const int bx = blockIdx.x, by = P.by0 + blockIdx.y;
     const int group = by * P.blocks_x + bx;
     const float* t = P.tmp_data + ((size_t)((by - P.by0) * P.blocks_x + bx) * BMFR_BUFFER_COUNT) * BMFR_BLOCK_PIXELS;
@@ -64,12 +67,15 @@ __global__ void __launch_bounds__(BMFR_FIT_THREADS) k2_fitter_kernel(const __gri
 #pragma unroll
         for (int c = 0; c < BMFR_BUFFER_COUNT; ++c)
             a[s][c] = t[(size_t)c * BMFR_BLOCK_PIXELS + threadIdx.x + BMFR_FIT_THREADS * s];
-    block_fit(a, sh, P.noise, P.weights, P.mins_maxs, group);
+    block_fit(a, sh, P.noise, P.weights, P.mins_maxs, P.mins_inv, group);
 }
 
 // FUSED K1+K2: one CTA per 32x32 block; thread tid owns work-items tid + 256*s of the block.
-__global__ void __launch_bounds__(BMFR_FIT_THREADS) fit_kernel(const __grid_constant__ KParams P) {
-    __shared__ FitShared sh;
+#ifndef BMFR_FIT_MIN_BLOCKS
+#define BMFR_FIT_MIN_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(BMFR_FIT_THREADS, BMFR_FIT_MIN_BLOCKS) fit_kernel(const __grid_constant__ KParams P) {
+    __shared__ __align__(16) FitShared sh;
     const int bx = blockIdx.x, by = P.by0 + blockIdx.y;
     const int group = by * P.blocks_x + bx;
     const int tid = threadIdx.x;
@@ -96,7 +102,7 @@ __global__ void __launch_bounds__(BMFR_FIT_THREADS) fit_kernel(const __grid_cons
             P.accept[lp] = r.accept;
         }
     }
-    block_fit(a, sh, P.noise, P.weights, P.mins_maxs, group);
+    block_fit(a, sh, P.noise, P.weights, P.mins_maxs, P.mins_inv, group);
 }
 
 // --------------------------------------------------------------------------------------------
@@ -109,7 +115,7 @@ __global__ void __launch_bounds__(256) k3_weighted_sum_kernel(const __grid_const
     const size_t lp = pix_index(P, x, y);
     const int g = k3_group(P, x, y);
     const f3 c = k3_pixel(load_f3(P.cur_normals, lp), load_f3(P.cur_positions, lp),
-                          P.weights + (size_t)g * BMFR_FEATURES * 3, P.mins_maxs + (size_t)g * BMFR_FEATURES_SCALED * 2);
+                          P.weights + (size_t)g * BMFR_FEATURES * 3, P.mins_inv + (size_t)g * BMFR_FEATURES_SCALED * 2);
     store_f3(P.filtered, lp, c);
 }
 
@@ -165,12 +171,12 @@ __global__ void __launch_bounds__(256) k5_taa_kernel(const __grid_constant__ KPa
 #define POST_TILE 32
 #define POST_HALO (POST_TILE + 2)
 
-__device__ __forceinline__ bool post_eval(const KParams& P, int x, int y, const float* w, const float* mm, bool interior,
+__device__ __forceinline__ bool post_eval(const KParams& P, int x, int y, const float* w, const float* mi, bool interior,
                                           f3& tone) {
     // returns false when (x,y) is outside the rows this context evaluates
     if (x < 0 || x >= P.W || y < P.py0 || y >= P.py1) return false;
     const size_t lp = pix_index(P, x, y);
-    const f3 filtered = k3_pixel(load_f3(P.cur_normals, lp), load_f3(P.cur_positions, lp), w, mm);
+    const f3 filtered = k3_pixel(load_f3(P.cur_normals, lp), load_f3(P.cur_positions, lp), w, mi);
     const float2 pp = P.prev_pixels[lp];
     f3 accum;
     k4_pixel(P, lp, filtered, pp.x, pp.y, P.accept[lp], accum, tone);
@@ -178,9 +184,10 @@ __device__ __forceinline__ bool post_eval(const KParams& P, int x, int y, const 
     return true;
 }
 
-__global__ void __launch_bounds__(256) post_kernel(const __grid_constant__ KParams P) {
-    __shared__ float s_tone[POST_HALO][POST_HALO][3];
-    __shared__ float s_w[BMFR_FEATURES * 3 + BMFR_FEATURES_SCALED * 2];
+__global__ void __launch_bounds__(256, 3) post_kernel(const __grid_constant__ KParams P) {
+    // tone-mapped colour of the tile + ring, already converted to YCoCg for the 3x3 clamp of taa
+    __shared__ float s_ycc[POST_HALO][POST_HALO][3];
+    __shared__ __align__(16) float s_w[BMFR_FEATURES * 3 + BMFR_FEATURES_SCALED * 2 + 2];
     const int bx = blockIdx.x, by = P.by0 + blockIdx.y;
     const int group = by * P.blocks_x + bx;
     const int tid = threadIdx.x;
@@ -188,23 +195,26 @@ __global__ void __launch_bounds__(256) post_kernel(const __grid_constant__ KPara
 
     if (tid < BMFR_FEATURES * 3) s_w[tid] = P.weights[(size_t)group * BMFR_FEATURES * 3 + tid];
     else if (tid < BMFR_FEATURES * 3 + BMFR_FEATURES_SCALED * 2)
-        s_w[tid] = P.mins_maxs[(size_t)group * BMFR_FEATURES_SCALED * 2 + tid - BMFR_FEATURES * 3];
+        s_w[tid] = P.mins_inv[(size_t)group * BMFR_FEATURES_SCALED * 2 + tid - BMFR_FEATURES * 3];
     __syncthreads();
-    float w[BMFR_FEATURES * 3], mm[BMFR_FEATURES_SCALED * 2];
+    float w[BMFR_FEATURES * 3], mi[BMFR_FEATURES_SCALED * 2];
 #pragma unroll
     for (int i = 0; i < BMFR_FEATURES * 3; ++i) w[i] = s_w[i];
 #pragma unroll
-    for (int i = 0; i < BMFR_FEATURES_SCALED * 2; ++i) mm[i] = s_w[BMFR_FEATURES * 3 + i];
+    for (int i = 0; i < BMFR_FEATURES_SCALED * 2; ++i) mi[i] = s_w[BMFR_FEATURES * 3 + i];
 
-    // phase A, interior: thread owns (tid&31, tid>>5 + 8*s)
+    // phase A, interior: thread owns (tid&31, tid>>5 + 8*s); its own tone-mapped RGB stays in registers
+    f3 mine[4];
+    bool have[4];
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
         const int tx = tid & 31, ty = (tid >> 5) + 8 * s;
-        f3 tone;
-        if (post_eval(P, x0 + tx, y0 + ty, w, mm, true, tone)) {
-            s_tone[ty + 1][tx + 1][0] = tone.x;
-            s_tone[ty + 1][tx + 1][1] = tone.y;
-            s_tone[ty + 1][tx + 1][2] = tone.z;
+        have[s] = post_eval(P, x0 + tx, y0 + ty, w, mi, true, mine[s]);
+        if (have[s]) {
+            const f3 y = rgb_to_ycocg(mine[s]);
+            s_ycc[ty + 1][tx + 1][0] = y.x;
+            s_ycc[ty + 1][tx + 1][1] = y.y;
+            s_ycc[ty + 1][tx + 1][2] = y.z;
         }
     }
     // phase A, ring: 4*33 = 132 pixels, coefficients looked up per pixel
@@ -220,10 +230,11 @@ __global__ void __launch_bounds__(256) post_kernel(const __grid_constant__ KPara
             const int g = k3_group(P, x, y);
             f3 tone;
             post_eval(P, x, y, P.weights + (size_t)g * BMFR_FEATURES * 3,
-                      P.mins_maxs + (size_t)g * BMFR_FEATURES_SCALED * 2, false, tone);
-            s_tone[hy][hx][0] = tone.x;
-            s_tone[hy][hx][1] = tone.y;
-            s_tone[hy][hx][2] = tone.z;
+                      P.mins_inv + (size_t)g * BMFR_FEATURES_SCALED * 2, false, tone);
+            const f3 yc = rgb_to_ycocg(tone);
+            s_ycc[hy][hx][0] = yc.x;
+            s_ycc[hy][hx][1] = yc.y;
+            s_ycc[hy][hx][2] = yc.z;
         }
     }
     __syncthreads();
@@ -233,9 +244,9 @@ __global__ void __launch_bounds__(256) post_kernel(const __grid_constant__ KPara
     for (int s = 0; s < 4; ++s) {
         const int tx = tid & 31, ty = (tid >> 5) + 8 * s;
         const int x = x0 + tx, y = y0 + ty;
-        if (x < 0 || x >= P.W || y < P.own_y0 || y >= P.own_y1) continue;
+        if (!have[s] || y < P.own_y0 || y >= P.own_y1) continue;
         const size_t lp = pix_index(P, x, y);
-        const f3 my_new = make_f3(s_tone[ty + 1][tx + 1][0], s_tone[ty + 1][tx + 1][1], s_tone[ty + 1][tx + 1][2]);
+        const f3 my_new = mine[s];
         const float2 pp = P.prev_pixels[lp];
         const int pix = __float2int_rd(pp.x), piy = __float2int_rd(pp.y);
         f3 out;
@@ -250,9 +261,8 @@ __global__ void __launch_bounds__(256) post_kernel(const __grid_constant__ KPara
                 for (int dx = -1; dx <= 1; ++dx) {
                     const int sx = x + dx, sy = y + dy;
                     if (sx >= 0 && sy >= 0 && sx < P.W && sy < P.H) {
-                        const float* t = s_tone[ty + 1 + dy][tx + 1 + dx];
-                        const f3 sc = (dx == 0 && dy == 0) ? my_new : make_f3(t[0], t[1], t[2]);
-                        taa_box_add(box, sc, dx == 0 || dy == 0);
+                        const float* t = s_ycc[ty + 1 + dy][tx + 1 + dx];
+                        taa_box_add_ycocg(box, make_f3(t[0], t[1], t[2]), dx == 0 || dy == 0);
                     }
                 }
             out = taa_resolve(P, my_new, box, pp.x, pp.y, pix, piy);

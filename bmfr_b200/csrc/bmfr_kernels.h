@@ -37,6 +37,7 @@ struct KParams {
     float* tmp_data;              // STAGED only
     float* weights;
     float* mins_maxs;
+    float* mins_inv;              // (min, 1/range or 1) per block and scaled feature, see scale_factor()
     const double* noise;          // [9][1024] add_random() increments of this frame
     const float* albedo;
     float* filtered;              // STAGED only

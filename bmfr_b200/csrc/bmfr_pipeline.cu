@@ -80,6 +80,7 @@ struct bmfr_ctx {
     float* tone_mapped = nullptr;           // tone_mapped_buffer (STAGED)
     float* weights = nullptr;               // weights_buffer
     float* mins_maxs = nullptr;             // mins_maxs_buffer
+    float* mins_inv = nullptr;              // (min, 1/range) twin of mins_maxs used by the weighted sum
     double* noise = nullptr;
     int* d_oob = nullptr;
     int tmp_block_rows = 0;
@@ -129,6 +130,7 @@ static void free_ctx(bmfr_ctx* c) {
     cudaFree(c->tone_mapped);
     cudaFree(c->weights);
     cudaFree(c->mins_maxs);
+    cudaFree(c->mins_inv);
     cudaFree(c->noise);
     cudaFree(c->d_oob);
     for (int k = 0; k < 4; ++k)
@@ -248,6 +250,7 @@ int bmfr_create(const bmfr_params* params, bmfr_ctx** out_ctx) {
     if (st == 0) st = dev_alloc(&c->accept, npix, "accept");
     if (st == 0) st = dev_alloc(&c->weights, nb * BMFR_FEATURES * 3, "weights");
     if (st == 0) st = dev_alloc(&c->mins_maxs, nb * BMFR_FEATURES_SCALED * 2, "mins_maxs");
+    if (st == 0) st = dev_alloc(&c->mins_inv, nb * BMFR_FEATURES_SCALED * 2, "mins_inv");
     if (st == 0) st = dev_alloc(&c->noise, (size_t)(BMFR_FEATURES - 1) * BMFR_BLOCK_PIXELS, "noise");
     if (st == 0) st = dev_alloc(&c->d_oob, 1, "oob flag");
     if (st == 0 && p.mode == BMFR_MODE_STAGED) {
@@ -260,6 +263,7 @@ int bmfr_create(const bmfr_params* params, bmfr_ctx** out_ctx) {
     // weights of blocks a strip never fits stay defined
     if ((st = bmfr_check_cuda(cudaMemsetAsync(c->weights, 0, nb * BMFR_FEATURES * 3 * sizeof(float), c->stream), "memset")) != 0) return fail(st);
     if ((st = bmfr_check_cuda(cudaMemsetAsync(c->mins_maxs, 0, nb * BMFR_FEATURES_SCALED * 2 * sizeof(float), c->stream), "memset")) != 0) return fail(st);
+    if ((st = bmfr_check_cuda(cudaMemsetAsync(c->mins_inv, 0, nb * BMFR_FEATURES_SCALED * 2 * sizeof(float), c->stream), "memset")) != 0) return fail(st);
     if (p.profile) c->prof.resize(kProfileSlots);
     if ((st = bmfr_check_cuda(cudaStreamSynchronize(c->stream), "create sync")) != 0) return fail(st);
     *out_ctx = c;
@@ -311,7 +315,7 @@ static void fill_params(bmfr_ctx* c, KParams& P, int frame, const float* d_albed
     P.prev_noisy_acc = c->noisy_acc.previous(); P.cur_noisy_acc = c->noisy_acc.current();
     P.prev_spp = c->spp.previous(); P.cur_spp = c->spp.current();
     P.prev_pixels = c->prev_pixels; P.accept = c->accept;
-    P.tmp_data = c->tmp_data; P.weights = c->weights; P.mins_maxs = c->mins_maxs; P.noise = c->noise;
+    P.tmp_data = c->tmp_data; P.weights = c->weights; P.mins_maxs = c->mins_maxs; P.mins_inv = c->mins_inv; P.noise = c->noise;
     P.albedo = d_albedo; P.filtered = c->filtered;
     P.accum_prev = c->accum.previous(); P.accum_cur = c->accum.current();
     P.tone_mapped = c->tone_mapped;

@@ -1,0 +1,232 @@
+"""Strip sharding of one frame over several GPUs along block rows.
+
+The reference is single-device; this is the B200-side answer to the 4K / 8K configs of BASELINE.json.
+Rank r owns a contiguous band of image rows (a whole number of 32-row block rows) and stores
+`halo_rows` extra rows on each interior side.  Per frame:
+
+  1. every rank runs the two fused kernels on its strip: blocks that straddle a strip boundary are
+     fitted redundantly by both neighbours from identical data, so their coefficients are identical
+     bits and no coefficient exchange is needed;
+  2. the four temporal state buffers (accumulated noisy colour, spp, accumulated filtered colour,
+     TAA result) have their halo rows refreshed from the owning neighbour — the only communication,
+     neighbour-to-neighbour, no collective reduction.
+
+Ownership is fixed, so the sharded output equals the single-GPU output bit for bit as long as
+`halo_rows >= 34 + max vertical reprojection distance`; a gather that leaves strip + halo raises
+BMFR_ERR_HALO_TOO_SMALL instead of silently diverging.
+"""
+from __future__ import annotations
+
+import json
+import os
+import time
+
+import numpy as np
+
+from . import synth
+from .denoiser import Denoiser
+
+STATE_BUFFERS = ("noisy_acc", "spp", "accum", "result")   # what frame f+1 gathers from frame f
+_BYTES_PER_PIXEL = dict(noisy_acc=12, spp=1, accum=12, result=12)
+DEFAULT_HALO = 48
+
+
+def partition(height: int, n: int):
+    """Contiguous bands of block rows, sizes differing by at most one block row (e.g. 69 -> 35/34)."""
+    nb = (height + 31) // 32
+    if n < 1 or n > nb:
+        raise ValueError(f"cannot split {nb} block rows over {n} ranks")
+    base, extra = divmod(nb, n)
+    out, b = [], 0
+    for r in range(n):
+        rows = base + (1 if r < extra else 0)
+        out.append((min(b * 32, height), min((b + rows) * 32, height)))
+        b += rows
+    return out
+
+
+def storage_rows(strip, height, halo):
+    return max(0, strip[0] - halo), min(height, strip[1] + halo)
+
+
+def halo_messages(strips, height, halo):
+    """[(src_rank, dst_rank, y0, y1)]: image rows [y0,y1) owned by src that dst stores as halo."""
+    msgs = []
+    for r, (y0, y1) in enumerate(strips):
+        lo, hi = storage_rows((y0, y1), height, halo)
+        for s, (sy0, sy1) in enumerate(strips):
+            if s == r:
+                continue
+            a, b = max(lo, sy0), min(hi, sy1)
+            if a < b:
+                msgs.append((s, r, a, b))
+    return msgs
+
+
+def check_partition(strips, height, halo):
+    if halo < 34:
+        raise ValueError("halo_rows must cover one block row plus the TAA ring (>= 34) plus the camera motion")
+    for (y0, y1) in strips:
+        if y1 - y0 < 32 and y1 != height:
+            raise ValueError("strips must hold at least one block row")
+
+
+class _DevBuf:
+    """Exposes a raw device pointer through __cuda_array_interface__ so torch can address it."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+
+
+def _as_tensor(ptr, nbytes, device):
+    import torch
+    return torch.as_tensor(_DevBuf(ptr, nbytes), device=device)
+
+
+class StripContext:
+    """One rank's strip: a Denoiser created with strip_y0/strip_y1/halo_rows + views of its state."""
+
+    def __init__(self, width, height, strip, halo, device=0, stream=0, mode="fused", **kw):
+        self.W, self.H, self.strip, self.halo, self.device = width, height, strip, halo, device
+        whole = strip == (0, height)
+        self.d = Denoiser(width, height, mode=mode, device=device, stream=stream,
+                          strip=None if whole else strip, halo_rows=0 if whole else halo, **kw)
+        g = self.d.geometry
+        self.row0, self.row1 = g.row0, g.row1
+        self._views = {}
+
+    def rows_view(self, name, y0, y1):
+        """uint8 tensor over image rows [y0,y1) of the state buffer as of the last frame."""
+        ptr, nbytes = self.d.buffer_ptr(name)
+        key = (name, ptr)
+        if key not in self._views:
+            self._views[key] = _as_tensor(ptr, nbytes, f"cuda:{self.device}")
+        pitch = self.W * _BYTES_PER_PIXEL[name]
+        return self._views[key][(y0 - self.row0) * pitch:(y1 - self.row0) * pitch]
+
+    def close(self):
+        self.d.close()
+
+
+class LocalStripSet:
+    """All ranks' strips inside ONE process on ONE GPU, exchanging halos with device copies.  This is
+    how the strip logic is verified bit for bit on a single-GPU box (ranks emulated over all ranks'
+    data, as B200_PROFILING.md prescribes when there are fewer GPUs than ranks)."""
+
+    def __init__(self, width, height, n, halo=DEFAULT_HALO, device=0, mode="fused", **kw):
+        import torch
+        self.W, self.H, self.n = width, height, n
+        self.strips = partition(height, n)
+        check_partition(self.strips, height, halo)
+        # one explicit stream for all strips and for the halo copies (torch's default stream has
+        # handle 0, which the C ABI reads as "create a private stream")
+        self._stream = torch.cuda.Stream()
+        torch.cuda.set_stream(self._stream)
+        self.stream = self._stream.cuda_stream
+        self.ctx = [StripContext(width, height, s, halo, device, self.stream, mode, **kw) for s in self.strips]
+        self.msgs = halo_messages(self.strips, height, halo)
+
+    def denoise_frame(self, frame, full_inputs, cam_prev, pixel_offset, out_full):
+        """full_inputs: four torch CUDA tensors [H, W, 3]; out_full: [H, W, 3] receives owned rows."""
+        for c in self.ctx:
+            ptrs = [t[c.row0:c.row1].data_ptr() for t in full_inputs]
+            c.d.denoise_frame(frame, *ptrs, cam_prev, pixel_offset, out_full[c.row0:c.row1].data_ptr())
+        for name in STATE_BUFFERS:
+            for src, dst, y0, y1 in self.msgs:
+                self.ctx[dst].rows_view(name, y0, y1).copy_(self.ctx[src].rows_view(name, y0, y1))
+
+    def sync(self):
+        for c in self.ctx:
+            c.d.sync()
+
+    def close(self):
+        for c in self.ctx:
+            c.close()
+
+
+def exchange_distributed(views_by_name, msgs, rank):
+    """Neighbour halo refresh with torch.distributed point-to-point ops (NCCL on GPUs, gloo on CPU).
+    views_by_name(name, y0, y1) -> contiguous uint8 tensor over those image rows."""
+    import torch.distributed as dist
+    ops = []
+    for name in STATE_BUFFERS:
+        for src, dst, y0, y1 in msgs:
+            if src == rank:
+                ops.append(dist.P2POp(dist.isend, views_by_name(name, y0, y1), dst))
+            elif dst == rank:
+                ops.append(dist.P2POp(dist.irecv, views_by_name(name, y0, y1), src))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+
+# ------------------------------------------------------------------------------------------------
+# bench.py --gpus N (N > 1): 3840x2160 strip-sharded, one rank per GPU
+# ------------------------------------------------------------------------------------------------
+def bench_sharded(args, workload, frames):
+    import torch
+    import torch.distributed as dist
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    w, h = args.width or workload[0], args.height or workload[1]
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    halo = DEFAULT_HALO
+    strips = partition(h, world)
+    check_partition(strips, h, halo)
+    msgs = halo_messages(strips, h, halo)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    sp = stream.cuda_stream
+    ctx = StripContext(w, h, strips[rank], halo, local, sp, args.mode)
+    rows = ctx.row1 - ctx.row0
+    inputs = torch.empty((frames, 4, rows, w, 3), dtype=torch.float32, device="cuda")
+    for f in range(frames):
+        synth.frame_device(w, h, f, [inputs[f, k].data_ptr() for k in range(4)], y0=ctx.row0, y1=ctx.row1, stream=sp)
+    cams = [synth.camera(max(f - 1, 0), w, h)[0] for f in range(frames)]
+    offs = [synth.camera(f, w, h)[1] for f in range(frames)]
+    out = torch.empty((rows, w, 3), dtype=torch.float32, device="cuda")
+
+    def run_sequence():
+        for f in range(frames):
+            ctx.d.denoise_frame(f, inputs[f, 0].data_ptr(), inputs[f, 1].data_ptr(), inputs[f, 2].data_ptr(),
+                                inputs[f, 3].data_ptr(), cams[f], offs[f], out.data_ptr())
+            exchange_distributed(ctx.rows_view, msgs, rank)
+
+    for _ in range(args.warmup):
+        run_sequence()
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    l0 = ctx.d.kernel_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        run_sequence()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ctx.d.sync()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)      # max over ranks
+    total_ms = float(ms.item())
+    launches = ctx.d.kernel_launches - l0
+    halo_bytes = sum((y1 - y0) * w * sum(_BYTES_PER_PIXEL.values()) for s, d_, y0, y1 in msgs if d_ == rank)
+    if rank == 0:
+        fps = frames * args.steps / (total_ms * 1e-3)
+        line = {
+            "metric": "frames/sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "ms_per_frame": total_ms / args.steps / frames,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{w}x{h} x{frames} frames synth-v1 strip-sharded over {world} GPUs along block rows",
+                       "mode": args.mode, "strips": strips, "halo_rows": halo,
+                       "parallelism": f"strips{world}", "exchange": "NCCL send/recv of state halo rows, neighbours only",
+                       "l2": "inputs larger than L2; no explicit flush"},
+            "halo_bytes_per_frame_rank0": halo_bytes, "gpu_launches": int(launches), "roofline": None,
+            "cpu_baseline": None, "e2e": None,
+        }
+        print(json.dumps(line))
+    ctx.close()
+    dist.destroy_process_group()

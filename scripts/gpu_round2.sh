@@ -1,0 +1,26 @@
+#!/bin/bash
+# parity tests, bench of the default build + tuning variants, ncu captures, OpenCL probe
+TAG=${1:-r01b}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+python scripts/probe_opencl.py > $OUT/opencl_probe.log 2>&1
+python -m pytest tests -m gpu -x -q > $OUT/pytest.log 2>&1
+PT=$?
+echo "pytest exit $PT"; tail -12 $OUT/pytest.log
+[ $PT -ne 0 ] && exit $PT
+python bench.py --steps 3 --warmup 3 --all-modes > $OUT/bench.json 2> $OUT/bench.err
+BE=$?
+echo "bench exit $BE"; python scripts/show_bench.py $OUT/bench.json; tail -5 $OUT/bench.err
+[ $BE -ne 0 ] && exit $BE
+for V in bmfr_b200/libbmfr_b200_*.so; do
+  [ -f "$V" ] || continue
+  N=$(basename $V .so)
+  BMFR_B200_LIB=$PWD/$V python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu > $OUT/bench_$N.json 2>> $OUT/bench.err
+  echo "== variant $N"; python scripts/show_bench.py $OUT/bench_$N.json
+done
+SHORT="python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu"
+$SHORT > $OUT/plain.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv $SHORT > $OUT/ncu_launches.log 2>&1
+$SHORT > $OUT/plain2.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:'fit_kernel|post_kernel' -s 40 -c 2 -f -o $OUT/prof $SHORT > $OUT/ncu_full.log 2>&1
+ls $OUT
