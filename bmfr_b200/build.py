@@ -76,6 +76,17 @@ def build_library(force: bool = False, verbose: bool = False, extra_flags=(), ou
     return LIB
 
 
+def build_driver(force: bool = False) -> Path:
+    """bmfr_run: the reference's driver program (tasks(), bmfr.cpp:179-556) on top of the C ABI."""
+    exe, src = ROOT / "bmfr_b200" / "bmfr_run", CSRC / "bmfr_main.cpp"
+    build_library()
+    if not force and exe.exists() and exe.stat().st_mtime > max(src.stat().st_mtime, LIB.stat().st_mtime):
+        return exe
+    subprocess.run(["g++", "-std=c++17", "-O2", str(src), "-o", str(exe), f"-L{LIB.parent}", "-lbmfr_b200",
+                    f"-Wl,-rpath,{LIB.parent}", "-Wl,-rpath,$ORIGIN"], check=True)
+    return exe
+
+
 def _build_variant(out: Path, extra_flags, verbose):
     nvcc = _nvcc()
     vdir = BUILD_DIR / out.stem
@@ -96,3 +107,4 @@ def _build_variant(out: Path, extra_flags, verbose):
 
 if __name__ == "__main__":
     print(build_library(force="--force" in sys.argv, verbose=True))
+    print(build_driver(force="--force" in sys.argv))

@@ -19,19 +19,22 @@ struct f3 {
 };
 
 __device__ __forceinline__ f3 make_f3(float x, float y, float z) { return f3{x, y, z}; }
-__device__ __forceinline__ f3 load_f3(const float* __restrict__ b, size_t i) {
-    return f3{b[i * 3], b[i * 3 + 1], b[i * 3 + 2]};
+// Pixel indices are 32-bit (an 8K strip has 33 M pixels, 100 M floats); one widening per access.
+__device__ __forceinline__ f3 load_f3(const float* __restrict__ b, unsigned int i) {
+    const float* p = b + (size_t)(i * 3u);
+    return f3{__ldg(p), __ldg(p + 1), __ldg(p + 2)};
 }
-__device__ __forceinline__ void store_f3(float* __restrict__ b, size_t i, f3 v) {
-    b[i * 3] = v.x;
-    b[i * 3 + 1] = v.y;
-    b[i * 3 + 2] = v.z;
+__device__ __forceinline__ void store_f3(float* __restrict__ b, unsigned int i, f3 v) {
+    float* p = b + (size_t)(i * 3u);
+    p[0] = v.x;
+    p[1] = v.y;
+    p[2] = v.z;
 }
 __device__ __forceinline__ float dot3(f3 a, f3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
 __device__ __forceinline__ f3 sub3(f3 a, f3 b) { return f3{a.x - b.x, a.y - b.y, a.z - b.z}; }
 
-__device__ __forceinline__ size_t pix_index(const KParams& P, int x, int y) {
-    return (size_t)(y - P.row0) * (size_t)P.W + (size_t)x;
+__device__ __forceinline__ unsigned int pix_index(const KParams& P, int x, int y) {
+    return (unsigned int)((y - P.row0) * P.W + x);
 }
 
 // mirror(), bmfr.cl:209-216
@@ -71,9 +74,11 @@ struct K1Pixel {
     unsigned char accept, spp;
 };
 
+// STRIP = the context holds only a band of rows: gathers are checked against it (oob_flag).
+template <bool STRIP>
 __device__ __forceinline__ K1Pixel k1_pixel(const KParams& P, int x, int y) {
     K1Pixel r;
-    const size_t lp = pix_index(P, x, y);
+    const unsigned int lp = pix_index(P, x, y);
     const f3 wp = load_f3(P.cur_positions, lp);
     const f3 n = load_f3(P.cur_normals, lp);
     const f3 cur = load_f3(P.cur_noisy, lp);
@@ -112,14 +117,17 @@ __device__ __forceinline__ K1Pixel k1_pixel(const KParams& P, int x, int y) {
         for (int i = 0; i < 4; ++i) {
             const int sx = pix + (i & 1), sy = piy + (i >> 1);
             const bool inimg = sx >= 0 && sy >= 0 && sx < P.W && sy < P.H;  // bmfr.cl:380-381
-            const bool held = sy >= P.row0 && sy < P.row1;
-            if (inimg && !held) *P.oob_flag = 1;  // strip + halo does not hold this row
+            bool held = true;
+            if (STRIP) {
+                held = sy >= P.row0 && sy < P.row1;
+                if (inimg && !held) *P.oob_flag = 1;  // strip + halo does not hold this row
+            }
             valid[i] = inimg && held;
-            const size_t ls = pix_index(P, min(max(sx, 0), P.W - 1), min(max(sy, rlo), rhi));
+            const unsigned int ls = pix_index(P, min(max(sx, 0), P.W - 1), min(max(sy, rlo), rhi));
             tp[i] = load_f3(P.prev_positions, ls);
             tn[i] = load_f3(P.prev_normals, ls);
             tc[i] = load_f3(P.prev_noisy_acc, ls);
-            ts[i] = (float)P.prev_spp[ls];
+            ts[i] = (float)__ldg(P.prev_spp + ls);
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -166,24 +174,24 @@ __device__ __forceinline__ K1Pixel k1_pixel(const KParams& P, int x, int y) {
     return r;
 }
 
-// The 13 values K1 stores per work-item (bmfr.cl:448-476): features, NaN scrubbed.
+// The 13 values K1 stores per work-item (bmfr.cl:448-476): features with NaN replaced by 0.  A NaN
+// position gives a NaN square, so scrubbing the position first yields the same 13 values.
+__device__ __forceinline__ float scrub_nan(float v) { return isnan(v) ? 0.f : v; }
 __device__ __forceinline__ void k1_features(const K1Pixel& r, float* f) {
+    const float px = scrub_nan(r.position.x), py = scrub_nan(r.position.y), pz = scrub_nan(r.position.z);
     f[0] = 1.f;
-    f[1] = r.normal.x;
-    f[2] = r.normal.y;
-    f[3] = r.normal.z;
-    f[4] = r.position.x;
-    f[5] = r.position.y;
-    f[6] = r.position.z;
-    f[7] = r.position.x * r.position.x;
-    f[8] = r.position.y * r.position.y;
-    f[9] = r.position.z * r.position.z;
-    f[10] = r.new_color.x;
-    f[11] = r.new_color.y;
-    f[12] = r.new_color.z;
-#pragma unroll
-    for (int i = 0; i < BMFR_BUFFER_COUNT; ++i)
-        if (isnan(f[i])) f[i] = 0.f;
+    f[1] = scrub_nan(r.normal.x);
+    f[2] = scrub_nan(r.normal.y);
+    f[3] = scrub_nan(r.normal.z);
+    f[4] = px;
+    f[5] = py;
+    f[6] = pz;
+    f[7] = px * px;
+    f[8] = py * py;
+    f[9] = pz * pz;
+    f[10] = scrub_nan(r.new_color.x);
+    f[11] = scrub_nan(r.new_color.y);
+    f[12] = scrub_nan(r.new_color.z);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -231,7 +239,7 @@ __device__ __forceinline__ float tone_map(float v) {  // clamp(powr(max(0,v), 0.
     return fminf(fmaxf(v, 0.f), 1.f);
 }
 
-__device__ __forceinline__ void k4_pixel(const KParams& P, size_t lp, f3 filtered, float prev_x, float prev_y,
+__device__ __forceinline__ void k4_pixel(const KParams& P, unsigned int lp, f3 filtered, float prev_x, float prev_y,
                                          unsigned int accept, f3& accum, f3& tone) {
     f3 prev = make_f3(0.f, 0.f, 0.f);
     float blend_alpha = 1.f;

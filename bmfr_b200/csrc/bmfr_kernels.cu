@@ -26,6 +26,7 @@ __global__ void noise_tile_kernel(double* __restrict__ noise, double noise_amoun
 // --------------------------------------------------------------------------------------------
 // STAGED K1: one thread per work-item of the margin-extended domain (bmfr.cl:310-484).
 // --------------------------------------------------------------------------------------------
+template <bool STRIP>
 __global__ void __launch_bounds__(256) k1_accumulate_noisy_kernel(const __grid_constant__ KParams P) {
     const int gx = blockIdx.x * 32 + threadIdx.x;
     const int gy = P.by0 * 32 + blockIdx.y * 8 + threadIdx.y;
@@ -35,7 +36,7 @@ __global__ void __launch_bounds__(256) k1_accumulate_noisy_kernel(const __grid_c
         *P.oob_flag = 1;
         return;
     }
-    const K1Pixel r = k1_pixel(P, x, y);
+    const K1Pixel r = k1_pixel<STRIP>(P, x, y);
     float f[BMFR_BUFFER_COUNT];
     k1_features(r, f);
     const int bx = gx >> 5, by = gy >> 5;
@@ -74,6 +75,7 @@ __global__ void __launch_bounds__(BMFR_FIT_THREADS, BMFR_FIT_MIN_BLOCKS) k2_fitt
 #ifndef BMFR_FIT_MIN_BLOCKS
 #define BMFR_FIT_MIN_BLOCKS 2
 #endif
+template <bool STRIP>
 __global__ void __launch_bounds__(BMFR_FIT_THREADS, BMFR_FIT_MIN_BLOCKS) fit_kernel(const __grid_constant__ KParams P) {
     __shared__ __align__(16) FitShared sh;
     const int bx = blockIdx.x, by = P.by0 + blockIdx.y;
@@ -86,13 +88,13 @@ __global__ void __launch_bounds__(BMFR_FIT_THREADS, BMFR_FIT_MIN_BLOCKS) fit_ker
         const int y_in = (tid >> 5) + 8 * s;
         const int ux = bx * 32 + x_in - 16 + P.off_x, uy = by * 32 + y_in - 16 + P.off_y;
         const int x = mirror_index(ux, P.W), y = mirror_index(uy, P.H);
-        if (y < P.row0 || y >= P.row1) {
+        if (STRIP && (y < P.row0 || y >= P.row1)) {
             *P.oob_flag = 1;
 #pragma unroll
             for (int c = 0; c < BMFR_BUFFER_COUNT; ++c) a[s][c] = 0.f;
             continue;
         }
-        const K1Pixel r = k1_pixel(P, x, y);
+        const K1Pixel r = k1_pixel<STRIP>(P, x, y);
         k1_features(r, a[s]);
         if (ux >= 0 && ux < P.W && uy >= 0 && uy < P.H) {
             const size_t lp = pix_index(P, x, y);
@@ -291,11 +293,14 @@ cudaError_t launch_noise_tile(double* d_noise, double noise_amount, int frame, c
     return cudaGetLastError();
 }
 
+// a context that holds only a band of rows (strip + halo) checks its gathers against the band
+static bool is_strip(const KParams& P) { return P.row0 != 0 || P.row1 != P.H; }
 static dim3 pixel_grid(const KParams& P, int y0, int y1) { return dim3((P.W + 31) / 32, (y1 - y0 + 7) / 8); }
 
 cudaError_t launch_k1(const KParams& P, cudaStream_t st) {
     dim3 grid(P.blocks_x, (P.by1 - P.by0) * 4), block(32, 8);
-    k1_accumulate_noisy_kernel<<<grid, block, 0, st>>>(P);
+    if (is_strip(P)) k1_accumulate_noisy_kernel<true><<<grid, block, 0, st>>>(P);
+    else k1_accumulate_noisy_kernel<false><<<grid, block, 0, st>>>(P);
     return cudaGetLastError();
 }
 cudaError_t launch_k2(const KParams& P, cudaStream_t st) {
@@ -317,7 +322,8 @@ cudaError_t launch_k5(const KParams& P, cudaStream_t st) {
 }
 cudaError_t launch_fit(const KParams& P, cudaStream_t st) {
     dim3 grid(P.blocks_x, P.by1 - P.by0);
-    fit_kernel<<<grid, BMFR_FIT_THREADS, 0, st>>>(P);
+    if (is_strip(P)) fit_kernel<true><<<grid, BMFR_FIT_THREADS, 0, st>>>(P);
+    else fit_kernel<false><<<grid, BMFR_FIT_THREADS, 0, st>>>(P);
     return cudaGetLastError();
 }
 cudaError_t launch_post(const KParams& P, cudaStream_t st) {
