@@ -33,6 +33,7 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 FRAMES = 60
+FUSED_KERNELS = ("reproject_kernel", "fit_qr_kernel", "fit_solve_kernel", "post_kernel")
 SINGLE_GPU_WORKLOAD = (1920, 1080)
 SHARDED_WORKLOAD = (3840, 2160)
 
@@ -53,8 +54,11 @@ def algorithmic_bytes(w, h):
         "weighted_sum": 24 * P + 168 * NB + 12 * P,
         "accumulate_filtered_data": 46 * P + 24 * P,
         "taa": 32 * P + 12 * P,
-        "fit_kernel": 95 * P + 168 * NB,      # fused K1+K2: tmp_data never reaches HBM
-        "post_kernel": 94 * P + 168 * NB,     # fused K3+K4+K5: filtered / tone_mapped never reach HBM
+        # FUSED: tmp_data / filtered / tone_mapped never reach HBM
+        "reproject_kernel": 95 * P,                        # K1 per image pixel: 73 B in, 22 B out
+        "fit_qr_kernel": 36 * P + (8 * 85 * 4 + 96) * NB,  # normals, positions, accumulated colour once; 8 triangles + min/max out
+        "fit_solve_kernel": (8 * 85 * 4 + 120) * NB,       # triangles in, weights out
+        "post_kernel": 94 * P + 168 * NB,                  # K3+K4+K5
     }
 
 
@@ -247,11 +251,15 @@ def run_single_gpu(args):
         run_sequence(dp)
         run_sequence(dp)
         dp.sync()
-        ms = np.array([[dp.stage_ms(f)[k] for k in ("accum_noisy", "fitter", "weighted_sum", "accum_filtered", "taa", "total")]
-                       for f in range(1, FRAMES)])  # frame 0 excluded like bmfr.cpp:392-397
+        if mode == "staged":
+            names = ["accumulate_noisy_data", "fitter", "weighted_sum", "accumulate_filtered_data", "taa"]
+            ms = np.array([[dp.stage_ms(f)[k] for k in ("accum_noisy", "fitter", "weighted_sum", "accum_filtered", "taa", "total")]
+                           for f in range(1, FRAMES)])  # frame 0 excluded like bmfr.cpp:392-397
+        else:
+            names = list(FUSED_KERNELS)
+            ms = np.array([[dp.fused_kernel_ms(f)[k] for k in FUSED_KERNELS] + [0.0, dp.stage_ms(f)["total"]]
+                           for f in range(1, FRAMES)])
         mean = ms.mean(axis=0)
-        names = (["accumulate_noisy_data", "fitter", "weighted_sum", "accumulate_filtered_data", "taa"] if mode == "staged"
-                 else [None, "fit_kernel", None, None, "post_kernel"])
         for i, name in enumerate(names):
             if name:
                 gbs = alg[name] / (mean[i] * 1e-3) / 1e9
@@ -259,7 +267,7 @@ def run_single_gpu(args):
                                  "algorithmic_bytes": alg[name], "achieved_gbs": gbs, "frac": gbs / peak}
         kernels[f"total_{mode}"] = {"ms": float(mean[5])}
         dp.close()
-    own = [k for k in kernels if not k.startswith("total_") and (k in ("fit_kernel", "post_kernel")) == (args.mode == "fused")]
+    own = [k for k in kernels if not k.startswith("total_") and (k in FUSED_KERNELS) == (args.mode == "fused")]
     dom = max(own, key=lambda k: kernels[k]["ms"])
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,

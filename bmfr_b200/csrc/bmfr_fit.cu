@@ -1,0 +1,395 @@
+// FUSED mode, first half of the frame: accumulate_noisy_data + fitter (bmfr.cl:290-485, 490-700)
+// as three sm_100a kernels sized for what each phase is bound by:
+//
+//   reproject_kernel  : K1 for every image pixel, one thread per pixel at full occupancy (gather
+//                       latency bound).  Writes the four per-pixel outputs of bmfr.cl:478-484.
+//                       The block-planar tmp_data of the reference is never written.
+//   fit_qr_kernel     : one CTA per 32x32 block.  Rebuilds the block's 1024x13 matrix in registers
+//                       from the per-pixel buffers (mirrored margins included, bmfr.cl:314-316),
+//                       block min/max + scaling + noise (bmfr.cl:511-542, 623-627), then every
+//                       warp factors its own 128 rows (level 1 of a TSQR) with no block barrier
+//                       and stores its 10x13 triangle.
+//   fit_solve_kernel  : one warp per block: factors the eight stacked triangles (level 2) and
+//                       back-substitutes (bmfr.cl:659-699).
+//
+// Splitting level 2 off keeps seven of eight warps from idling (and holding their registers)
+// while one warp finishes the block.  Compiled with --fmad=false (K1 is bit-exact against the
+// oracle); the fit writes fmaf() explicitly.
+#include "bmfr_kernels.h"
+
+#include "bmfr_device.cuh"
+
+// --------------------------------------------------------------------------------------------
+// K1 per image pixel.  Mirrored margin work-items of the reference recompute an in-image pixel
+// (bmfr.cl:314-325) and store nothing per pixel (bmfr.cl:478), so the image pixels are the whole
+// job; the fit re-derives margin rows from these outputs.
+// --------------------------------------------------------------------------------------------
+template <bool STRIP>
+__global__ void __launch_bounds__(256, 4) reproject_kernel(const __grid_constant__ KParams P) {
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int y = P.k1_y0 + blockIdx.y * 8 + threadIdx.y;
+    if (x >= P.W || y >= P.k1_y1) return;
+    if (STRIP && (y < P.row0 || y >= P.row1)) {
+        *P.oob_flag = 1;
+        return;
+    }
+    const K1Pixel r = k1_pixel<STRIP>(P, x, y);
+    const unsigned int lp = pix_index(P, x, y);
+    store_f3(P.cur_noisy_acc, lp, r.new_color);
+    P.cur_spp[lp] = r.spp;
+    P.prev_pixels[lp] = make_float2(r.prev_x, r.prev_y);
+    P.accept[lp] = r.accept;
+}
+
+// --------------------------------------------------------------------------------------------
+// warp-level helpers
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_min(float v) {
+    float r;
+    asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ float warp_max(float v) {
+    float r;
+    asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ float rcp_approx(float v) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ float rsqrt_approx(float v) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+
+#define QR_RED_STRIDE 36  // floats per column of the transpose buffer: 16-byte aligned rows, bank-shifted
+
+// Sum over the 32 lanes of N per-lane values (one per remaining column): every lane stores its N
+// partials column-major, then PARTS lanes share one column's 32 partials (128-bit loads + a short
+// add tree + log2(PARTS) shuffles).  Returns in lane j < N the total of column j, and in all lanes
+// the total of column 0.
+template <int N>
+__device__ __forceinline__ float warp_column_sums(const float (&part)[BMFR_BUFFER_COUNT], float* __restrict__ red, int lane,
+                                                  float& total0) {
+    constexpr int PARTS = (N > 8) ? 2 : (N > 4) ? 4 : 8;
+    constexpr int VALS = 32 / PARTS;  // columns handled per pass: 16, 8 or 4
+    constexpr int LEN = 32 / PARTS;   // partial sums per lane
+#pragma unroll
+    for (int j = 0; j < N; ++j) red[j * QR_RED_STRIDE + lane] = part[j];
+    __syncwarp();
+    const int jj = lane % VALS, q = lane / VALS;
+    float t = 0.f;
+    if (jj < N) {
+        const float4* src = reinterpret_cast<const float4*>(red + jj * QR_RED_STRIDE + q * LEN);
+        const float4 v0 = src[0];
+        float t0 = (v0.x + v0.y) + (v0.z + v0.w);
+        if (LEN >= 8) {
+            const float4 v1 = src[1];
+            t0 += (v1.x + v1.y) + (v1.z + v1.w);
+        }
+        if (LEN == 16) {
+            const float4 v2 = src[2], v3 = src[3];
+            const float t1 = ((v2.x + v2.y) + (v2.z + v2.w)) + ((v3.x + v3.y) + (v3.z + v3.w));
+            t0 += t1;
+        }
+        t = t0;
+    }
+#pragma unroll
+    for (int m = VALS; m < 32; m <<= 1) t += __shfl_xor_sync(0xffffffffu, t, m);
+    total0 = __shfl_sync(0xffffffffu, t, 0);
+    return t;
+}
+
+// Broadcast of the N elimination coefficients to every lane through shared memory.
+template <int N>
+__device__ __forceinline__ void warp_broadcast(float c, float* __restrict__ coefbuf, int lane, float (&cj)[16]) {
+    if (lane < N) coefbuf[lane] = c;
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < (N + 3) / 4; ++i) {
+        const float4 v = reinterpret_cast<const float4*>(coefbuf)[i];
+        cj[4 * i] = v.x; cj[4 * i + 1] = v.y; cj[4 * i + 2] = v.z; cj[4 * i + 3] = v.w;
+    }
+    // no trailing barrier: the next reflector's stores to `red` come after this __syncwarp, and its
+    // store to `coefbuf` comes after the __syncwarp of its own warp_column_sums
+}
+
+// One reflector against a virtual zero pivot row (see bmfr_device.cuh "The fit"): with S_j = a_k.a_j,
+//   R_kj = S_j / sqrt(S_k),   a_j -= a_k * S_j / S_k   (j > k).
+// `a` holds columns 1..12 (column 0 is the constant 1 and lives in no register); srow receives
+// S_k..S_12, the unnormalised row k of R.  ROWS rows per lane.
+template <int ROWS, int K>
+__device__ __forceinline__ void qr_step(float (&a)[ROWS][BMFR_BUFFER_COUNT - 1], float* __restrict__ red,
+                                        float* __restrict__ coefbuf, float* __restrict__ srow, int lane) {
+    constexpr int N = BMFR_BUFFER_COUNT - K;
+    float part[BMFR_BUFFER_COUNT];
+    if (K == 0) {  // a_0 = 1: the products are plain column sums, S_0 = number of rows
+        part[0] = (float)ROWS;
+#pragma unroll
+        for (int j = 1; j < N; ++j) {
+            float acc = a[0][j - 1];
+#pragma unroll
+            for (int s = 1; s < ROWS; ++s) acc += a[s][j - 1];
+            part[j] = acc;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            float acc = a[0][K - 1] * a[0][K - 1 + j];
+#pragma unroll
+            for (int s = 1; s < ROWS; ++s) acc = fmaf(a[s][K - 1], a[s][K - 1 + j], acc);
+            part[j] = acc;
+        }
+    }
+    float sk;
+    const float t = warp_column_sums<N>(part, red, lane, sk);
+    if (lane < N) srow[K + lane] = t;
+    const float c = t * rcp_approx(sk);  // 2 * dot / u_length_squared of bmfr.cl:650
+    float cj[16];
+    warp_broadcast<N>(c, coefbuf, lane, cj);
+#pragma unroll
+    for (int j = 1; j < N; ++j) {
+#pragma unroll
+        for (int s = 0; s < ROWS; ++s) {
+            if (K == 0) a[s][j - 1] -= cj[j];
+            else a[s][K - 1 + j] = fmaf(-a[s][K - 1], cj[j], a[s][K - 1 + j]);
+        }
+    }
+}
+
+template <int ROWS, int K>
+struct QrLoop {
+    static __device__ __forceinline__ void run(float (&a)[ROWS][BMFR_BUFFER_COUNT - 1], float* red, float* coefbuf,
+                                               float* srows, int lane) {
+        qr_step<ROWS, K>(a, red, coefbuf, srows + K * BMFR_BUFFER_COUNT, lane);
+        QrLoop<ROWS, K + 1>::run(a, red, coefbuf, srows, lane);
+    }
+};
+template <int ROWS>
+struct QrLoop<ROWS, BMFR_FEATURES> {
+    static __device__ __forceinline__ void run(float (&)[ROWS][BMFR_BUFFER_COUNT - 1], float*, float*, float*, int) {}
+};
+
+// --------------------------------------------------------------------------------------------
+// fit_qr_kernel
+// --------------------------------------------------------------------------------------------
+struct QrShared {
+    float red[BMFR_FIT_WARPS][BMFR_BUFFER_COUNT][QR_RED_STRIDE];
+    float coef[BMFR_FIT_WARPS][16];
+    float minmax[BMFR_FIT_WARPS][2 * BMFR_FEATURES_SCALED];
+};
+
+#ifndef BMFR_QR_MIN_BLOCKS
+#define BMFR_QR_MIN_BLOCKS 3
+#endif
+
+template <bool STRIP>
+__global__ void __launch_bounds__(BMFR_FIT_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(const __grid_constant__ KParams P) {
+    __shared__ __align__(16) QrShared sh;
+    const int bx = blockIdx.x, by = P.by0 + blockIdx.y;
+    const int group = by * P.blocks_x + bx;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NSC = BMFR_FEATURES_SCALED, NNS = BMFR_FEATURES_NOT_SCALED, ROWS = BMFR_ROWS_PER_THREAD;
+
+    // a[s][c-1] = column c of row (lane, warp + 8 s) of the block: the 12 non-constant K1 values
+    // (bmfr.cl:448-453), NaN -> 0 (bmfr.cl:468-469), rebuilt from the per-pixel buffers.
+    float a[ROWS][BMFR_BUFFER_COUNT - 1];
+    const int ux = bx * 32 + lane - 16 + P.off_x;
+    const int x = mirror_index(ux, P.W);
+#pragma unroll
+    for (int s = 0; s < ROWS; ++s) {
+        const int uy = by * 32 + warp + 8 * s - 16 + P.off_y;
+        const int y = mirror_index(uy, P.H);
+        if (STRIP && (y < P.row0 || y >= P.row1)) {
+            *P.oob_flag = 1;
+#pragma unroll
+            for (int c = 0; c < BMFR_BUFFER_COUNT - 1; ++c) a[s][c] = 0.f;
+            continue;
+        }
+        const unsigned int lp = pix_index(P, x, y);
+        const f3 n = load_f3(P.cur_normals, lp);
+        const f3 p = load_f3(P.cur_positions, lp);
+        const f3 col = load_f3(P.cur_noisy_acc, lp);
+        const float px = scrub_nan(p.x), py = scrub_nan(p.y), pz = scrub_nan(p.z);
+        a[s][0] = scrub_nan(n.x); a[s][1] = scrub_nan(n.y); a[s][2] = scrub_nan(n.z);
+        a[s][3] = px; a[s][4] = py; a[s][5] = pz;
+        a[s][6] = px * px; a[s][7] = py * py; a[s][8] = pz * pz;
+        a[s][9] = scrub_nan(col.x); a[s][10] = scrub_nan(col.y); a[s][11] = scrub_nan(col.z);
+    }
+
+    // (i) block min / max of the six scaled features, bmfr.cl:511-535 (exact, so order-free)
+#pragma unroll
+    for (int f = 0; f < NSC; ++f) {
+        const int c = NNS - 1 + f;
+        const float lo = fminf(fminf(a[0][c], a[1][c]), fminf(a[2][c], a[3][c]));
+        const float hi = fmaxf(fmaxf(a[0][c], a[1][c]), fmaxf(a[2][c], a[3][c]));
+        const float wlo = warp_min(lo), whi = warp_max(hi);
+        if (lane == 0) {
+            sh.minmax[warp][2 * f] = wlo;
+            sh.minmax[warp][2 * f + 1] = whi;
+        }
+    }
+    __syncthreads();
+    float mn[NSC], inv[NSC];
+#pragma unroll
+    for (int f = 0; f < NSC; ++f) {
+        float lo = sh.minmax[0][2 * f], hi = sh.minmax[0][2 * f + 1];
+#pragma unroll
+        for (int w = 1; w < BMFR_FIT_WARPS; ++w) {
+            lo = fminf(lo, sh.minmax[w][2 * f]);
+            hi = fmaxf(hi, sh.minmax[w][2 * f + 1]);
+        }
+        mn[f] = lo;
+        inv[f] = scale_factor(lo, hi);
+        if (tid == 2 * f) {
+            P.mins_maxs[(size_t)group * 2 * NSC + tid] = lo;
+            P.mins_inv[(size_t)group * 2 * NSC + tid] = lo;
+        }
+        if (tid == 2 * f + 1) {
+            P.mins_maxs[(size_t)group * 2 * NSC + tid] = hi;
+            P.mins_inv[(size_t)group * 2 * NSC + tid] = inv[f];
+        }
+    }
+
+    // scale (bmfr.cl:538-541), then the first-touch noise on columns 1..9 (bmfr.cl:623-627).  The
+    // reference adds a double (NOISE_AMOUNT is a double literal); the tile holds that double rounded
+    // to fp32, which changes a sum by at most one ulp in rare ties — below the fit's own rounding.
+#pragma unroll
+    for (int s = 0; s < ROWS; ++s) {
+#pragma unroll
+        for (int f = 0; f < NSC; ++f) a[s][NNS - 1 + f] = scale_feature(a[s][NNS - 1 + f], mn[f], inv[f]);
+#pragma unroll
+        for (int c = 1; c < BMFR_FEATURES; ++c)
+            a[s][c - 1] += __ldg(&P.noise_f[(c - 1) * BMFR_BLOCK_PIXELS + tid + BMFR_FIT_THREADS * s]);
+    }
+
+    // (ii) level 1 of the TSQR: this warp's 128 rows -> one 10x13 triangle (unnormalised rows)
+    float* srows = P.rstack + ((size_t)(blockIdx.y * P.blocks_x + bx) * BMFR_FIT_WARPS + warp) * (BMFR_FEATURES * BMFR_BUFFER_COUNT);
+    QrLoop<ROWS, 0>::run(a, &sh.red[warp][0][0], sh.coef[warp], srows, lane);
+}
+
+// --------------------------------------------------------------------------------------------
+// fit_solve_kernel: level 2 + back-substitution, one warp per block
+// --------------------------------------------------------------------------------------------
+#define SOLVE_WARPS 4
+
+struct SolveShared {
+    float red[SOLVE_WARPS][BMFR_BUFFER_COUNT][QR_RED_STRIDE];
+    float coef[SOLVE_WARPS][16];
+    float srows[SOLVE_WARPS][BMFR_FEATURES * BMFR_BUFFER_COUNT];
+};
+
+// General reflector on a matrix with all 13 columns in registers (level 2: column 0 is no longer 1).
+template <int ROWS, int K>
+__device__ __forceinline__ void qr_step_full(float (&b)[ROWS][BMFR_BUFFER_COUNT], float* __restrict__ red,
+                                             float* __restrict__ coefbuf, float* __restrict__ srow, int lane) {
+    constexpr int N = BMFR_BUFFER_COUNT - K;
+    float part[BMFR_BUFFER_COUNT];
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        float acc = b[0][K] * b[0][K + j];
+#pragma unroll
+        for (int s = 1; s < ROWS; ++s) acc = fmaf(b[s][K], b[s][K + j], acc);
+        part[j] = acc;
+    }
+    float sk;
+    const float t = warp_column_sums<N>(part, red, lane, sk);
+    if (lane < N) srow[K + lane] = t;
+    const float c = t * rcp_approx(sk);
+    float cj[16];
+    warp_broadcast<N>(c, coefbuf, lane, cj);
+#pragma unroll
+    for (int j = 1; j < N; ++j)
+#pragma unroll
+        for (int s = 0; s < ROWS; ++s) b[s][K + j] = fmaf(-b[s][K], cj[j], b[s][K + j]);
+}
+template <int ROWS, int K>
+struct QrLoopFull {
+    static __device__ __forceinline__ void run(float (&b)[ROWS][BMFR_BUFFER_COUNT], float* red, float* coefbuf, float* srows, int lane) {
+        qr_step_full<ROWS, K>(b, red, coefbuf, srows + K * BMFR_BUFFER_COUNT, lane);
+        QrLoopFull<ROWS, K + 1>::run(b, red, coefbuf, srows, lane);
+    }
+};
+template <int ROWS>
+struct QrLoopFull<ROWS, BMFR_FEATURES> {
+    static __device__ __forceinline__ void run(float (&)[ROWS][BMFR_BUFFER_COUNT], float*, float*, float*, int) {}
+};
+
+__global__ void __launch_bounds__(SOLVE_WARPS * 32) fit_solve_kernel(const __grid_constant__ KParams P) {
+    __shared__ __align__(16) SolveShared sh;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nblocks = P.blocks_x * (P.by1 - P.by0);
+    const int local = blockIdx.x * SOLVE_WARPS + warp;
+    if (local >= nblocks) return;
+    const int group = P.by0 * P.blocks_x + local;
+    const float* st = P.rstack + (size_t)local * (BMFR_FIT_WARPS * BMFR_FEATURES * BMFR_BUFFER_COUNT);
+
+    // 80 stacked rows, three per lane (rows 80..95 are zero).  Row (w, k) of a level-1 factor is
+    // S_kj / sqrt(S_kk) for j >= k and zero left of its diagonal.
+    constexpr int NS2 = 3;
+    float b[NS2][BMFR_BUFFER_COUNT];
+#pragma unroll
+    for (int s = 0; s < NS2; ++s) {
+        const int row = lane + 32 * s;
+        const bool live = row < BMFR_FIT_WARPS * BMFR_FEATURES;
+        const int k = row % BMFR_FEATURES;
+        const float* src = st + (live ? row : 0) * BMFR_BUFFER_COUNT;
+        const float scale = live ? rsqrt_approx(__ldg(src + k)) : 0.f;
+#pragma unroll
+        for (int c = 0; c < BMFR_BUFFER_COUNT; ++c) b[s][c] = (live && c >= k) ? __ldg(src + c) * scale : 0.f;
+    }
+    float* srows = sh.srows[warp];
+    QrLoopFull<NS2, 0>::run(b, &sh.red[warp][0][0], sh.coef[warp], srows, lane);
+    __syncwarp();
+
+    // (iii) back-substitution, bmfr.cl:659-692.  Row i of R is S_ij / sqrt(S_ii); the square root
+    // cancels in R x = rhs, so the unnormalised rows are solved directly: sum_j S_ij x_j = S_i,rhs.
+    const int r = lane < BMFR_FEATURES ? lane : 0;
+    float row[BMFR_BUFFER_COUNT];
+#pragma unroll
+    for (int c = 0; c < BMFR_BUFFER_COUNT; ++c) row[c] = srows[r * BMFR_BUFFER_COUNT + c];
+    float rhs[3] = {row[10], row[11], row[12]};
+    float xs[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = BMFR_FEATURES - 1; i >= 0; --i) {
+        const float dinv = 1.0f / __shfl_sync(0xffffffffu, row[i], i);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float xi = __shfl_sync(0xffffffffu, rhs[c], i) * dinv;
+            if (lane == i) xs[c] = xi;
+            if (lane < i) rhs[c] = fmaf(-row[i], xi, rhs[c]);
+        }
+    }
+    if (lane < BMFR_FEATURES) {  // bmfr.cl:694-699
+        float* wout = P.weights + ((size_t)group * BMFR_FEATURES + lane) * 3;
+        wout[0] = xs[0];
+        wout[1] = xs[1];
+        wout[2] = xs[2];
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+// launchers
+// --------------------------------------------------------------------------------------------
+static bool is_strip(const KParams& P) { return P.row0 != 0 || P.row1 != P.H; }
+
+cudaError_t launch_reproject(const KParams& P, cudaStream_t st) {
+    const dim3 grid((P.W + 31) / 32, (P.k1_y1 - P.k1_y0 + 7) / 8), block(32, 8);
+    if (is_strip(P)) reproject_kernel<true><<<grid, block, 0, st>>>(P);
+    else reproject_kernel<false><<<grid, block, 0, st>>>(P);
+    return cudaGetLastError();
+}
+cudaError_t launch_fit_qr(const KParams& P, cudaStream_t st) {
+    const dim3 grid(P.blocks_x, P.by1 - P.by0);
+    if (is_strip(P)) fit_qr_kernel<true><<<grid, BMFR_FIT_THREADS, 0, st>>>(P);
+    else fit_qr_kernel<false><<<grid, BMFR_FIT_THREADS, 0, st>>>(P);
+    return cudaGetLastError();
+}
+cudaError_t launch_fit_solve(const KParams& P, cudaStream_t st) {
+    const int nblocks = P.blocks_x * (P.by1 - P.by0);
+    fit_solve_kernel<<<(nblocks + SOLVE_WARPS - 1) / SOLVE_WARPS, SOLVE_WARPS * 32, 0, st>>>(P);
+    return cudaGetLastError();
+}

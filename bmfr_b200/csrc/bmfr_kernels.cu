@@ -1,8 +1,6 @@
 // sm_100a kernels of the BMFR per-frame path and their launchers.
 //   STAGED : the reference's five kernels (bmfr.cl:290,490,703,761,860), one launch each
-//   FUSED  : fit_kernel  = accumulate_noisy_data + fitter      (tmp_data stays in registers)
-//            post_kernel = weighted_sum + accumulate_filtered_data + taa (filtered / tone_mapped
-//                          stay in registers / shared memory)
+//   FUSED  : bmfr_fit.cu (reproject + fit) and bmfr_post.cu (weighted sum + accumulation + taa)
 // Compiled with --fmad=false; see bmfr_device.cuh for the arithmetic convention.
 #include "bmfr_kernels.h"
 
@@ -14,13 +12,15 @@
 // once per element per block.  Kept in fp64: NOISE_AMOUNT is a double literal in the reference
 // (bmfr.cpp:58), which makes `value + NOISE_AMOUNT * 2.f * (random - 0.5f)` an fp64 expression.
 // --------------------------------------------------------------------------------------------
-__global__ void noise_tile_kernel(double* __restrict__ noise, double noise_amount, int frame) {
+__global__ void noise_tile_kernel(double* __restrict__ noise, float* __restrict__ noise_f, double noise_amount, int frame) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (BMFR_FEATURES - 1) * BMFR_BLOCK_PIXELS) return;
     // id + sub_vector*256 + feature_buffer*1024 + frame*13*1024 with feature_buffer = 1 + i/1024
     const int seed = i + BMFR_BLOCK_PIXELS + frame * BMFR_BUFFER_COUNT * BMFR_BLOCK_PIXELS;
     const float r = bmfr_random((unsigned int)seed) - 0.5f;
-    noise[i] = (noise_amount * 2.0) * (double)r;
+    const double d = (noise_amount * 2.0) * (double)r;
+    noise[i] = d;
+    noise_f[i] = (float)d;
 }
 
 // --------------------------------------------------------------------------------------------
@@ -68,42 +68,6 @@ __global__ void __launch_bounds__(BMFR_FIT_THREADS, BMFR_FIT_MIN_BLOCKS) k2_fitt
 #pragma unroll
         for (int c = 0; c < BMFR_BUFFER_COUNT; ++c)
             a[s][c] = t[(size_t)c * BMFR_BLOCK_PIXELS + threadIdx.x + BMFR_FIT_THREADS * s];
-    block_fit(a, sh, P.noise, P.weights, P.mins_maxs, P.mins_inv, group);
-}
-
-// FUSED K1+K2: one CTA per 32x32 block; thread tid owns work-items tid + 256*s of the block.
-#ifndef BMFR_FIT_MIN_BLOCKS
-#define BMFR_FIT_MIN_BLOCKS 2
-#endif
-template <bool STRIP>
-__global__ void __launch_bounds__(BMFR_FIT_THREADS, BMFR_FIT_MIN_BLOCKS) fit_kernel(const __grid_constant__ KParams P) {
-    __shared__ __align__(16) FitShared sh;
-    const int bx = blockIdx.x, by = P.by0 + blockIdx.y;
-    const int group = by * P.blocks_x + bx;
-    const int tid = threadIdx.x;
-    const int x_in = tid & 31;
-    float a[BMFR_ROWS_PER_THREAD][BMFR_BUFFER_COUNT];
-#pragma unroll
-    for (int s = 0; s < BMFR_ROWS_PER_THREAD; ++s) {
-        const int y_in = (tid >> 5) + 8 * s;
-        const int ux = bx * 32 + x_in - 16 + P.off_x, uy = by * 32 + y_in - 16 + P.off_y;
-        const int x = mirror_index(ux, P.W), y = mirror_index(uy, P.H);
-        if (STRIP && (y < P.row0 || y >= P.row1)) {
-            *P.oob_flag = 1;
-#pragma unroll
-            for (int c = 0; c < BMFR_BUFFER_COUNT; ++c) a[s][c] = 0.f;
-            continue;
-        }
-        const K1Pixel r = k1_pixel<STRIP>(P, x, y);
-        k1_features(r, a[s]);
-        if (ux >= 0 && ux < P.W && uy >= 0 && uy < P.H) {
-            const size_t lp = pix_index(P, x, y);
-            store_f3(P.cur_noisy_acc, lp, r.new_color);
-            P.cur_spp[lp] = r.spp;
-            P.prev_pixels[lp] = make_float2(r.prev_x, r.prev_y);
-            P.accept[lp] = r.accept;
-        }
-    }
     block_fit(a, sh, P.noise, P.weights, P.mins_maxs, P.mins_inv, group);
 }
 
@@ -164,117 +128,6 @@ __global__ void __launch_bounds__(256) k5_taa_kernel(const __grid_constant__ KPa
 }
 
 // --------------------------------------------------------------------------------------------
-// FUSED K3+K4+K5.  One CTA per tile of the frame's (shifted) block grid, so the 42 fit
-// coefficients are CTA-uniform for the tile interior.  Phase A computes filtered -> accumulated ->
-// tone-mapped for the tile plus a one-pixel ring (the ring is recomputed with the neighbouring
-// blocks' coefficients; identical code and inputs give identical bits) into shared memory;
-// phase B runs taa on the interior from shared memory.
-// --------------------------------------------------------------------------------------------
-#define POST_TILE 32
-#define POST_HALO (POST_TILE + 2)
-
-__device__ __forceinline__ bool post_eval(const KParams& P, int x, int y, const float* w, const float* mi, bool interior,
-                                          f3& tone) {
-    // returns false when (x,y) is outside the rows this context evaluates
-    if (x < 0 || x >= P.W || y < P.py0 || y >= P.py1) return false;
-    const size_t lp = pix_index(P, x, y);
-    const f3 filtered = k3_pixel(load_f3(P.cur_normals, lp), load_f3(P.cur_positions, lp), w, mi);
-    const float2 pp = P.prev_pixels[lp];
-    f3 accum;
-    k4_pixel(P, lp, filtered, pp.x, pp.y, P.accept[lp], accum, tone);
-    if (interior) store_f3(P.accum_cur, lp, accum);
-    return true;
-}
-
-__global__ void __launch_bounds__(256, 3) post_kernel(const __grid_constant__ KParams P) {
-    // tone-mapped colour of the tile + ring, already converted to YCoCg for the 3x3 clamp of taa
-    __shared__ float s_ycc[POST_HALO][POST_HALO][3];
-    __shared__ __align__(16) float s_w[BMFR_FEATURES * 3 + BMFR_FEATURES_SCALED * 2 + 2];
-    const int bx = blockIdx.x, by = P.by0 + blockIdx.y;
-    const int group = by * P.blocks_x + bx;
-    const int tid = threadIdx.x;
-    const int x0 = bx * 32 - 16 + P.off_x, y0 = by * 32 - 16 + P.off_y;  // tile origin in image coordinates
-
-    if (tid < BMFR_FEATURES * 3) s_w[tid] = P.weights[(size_t)group * BMFR_FEATURES * 3 + tid];
-    else if (tid < BMFR_FEATURES * 3 + BMFR_FEATURES_SCALED * 2)
-        s_w[tid] = P.mins_inv[(size_t)group * BMFR_FEATURES_SCALED * 2 + tid - BMFR_FEATURES * 3];
-    __syncthreads();
-    float w[BMFR_FEATURES * 3], mi[BMFR_FEATURES_SCALED * 2];
-#pragma unroll
-    for (int i = 0; i < BMFR_FEATURES * 3; ++i) w[i] = s_w[i];
-#pragma unroll
-    for (int i = 0; i < BMFR_FEATURES_SCALED * 2; ++i) mi[i] = s_w[BMFR_FEATURES * 3 + i];
-
-    // phase A, interior: thread owns (tid&31, tid>>5 + 8*s); its own tone-mapped RGB stays in registers
-    f3 mine[4];
-    bool have[4];
-#pragma unroll
-    for (int s = 0; s < 4; ++s) {
-        const int tx = tid & 31, ty = (tid >> 5) + 8 * s;
-        have[s] = post_eval(P, x0 + tx, y0 + ty, w, mi, true, mine[s]);
-        if (have[s]) {
-            const f3 y = rgb_to_ycocg(mine[s]);
-            s_ycc[ty + 1][tx + 1][0] = y.x;
-            s_ycc[ty + 1][tx + 1][1] = y.y;
-            s_ycc[ty + 1][tx + 1][2] = y.z;
-        }
-    }
-    // phase A, ring: 4*33 = 132 pixels, coefficients looked up per pixel
-    if (tid < 4 * (POST_HALO - 1)) {
-        const int side = tid / (POST_HALO - 1), k = tid % (POST_HALO - 1);
-        int hx, hy;  // halo-tile coordinates 0..33
-        if (side == 0) { hx = k; hy = 0; }
-        else if (side == 1) { hx = POST_HALO - 1; hy = k; }
-        else if (side == 2) { hx = POST_HALO - 1 - k; hy = POST_HALO - 1; }
-        else { hx = 0; hy = POST_HALO - 1 - k; }
-        const int x = x0 + hx - 1, y = y0 + hy - 1;
-        if (x >= 0 && x < P.W && y >= P.py0 && y < P.py1) {
-            const int g = k3_group(P, x, y);
-            f3 tone;
-            post_eval(P, x, y, P.weights + (size_t)g * BMFR_FEATURES * 3,
-                      P.mins_inv + (size_t)g * BMFR_FEATURES_SCALED * 2, false, tone);
-            const f3 yc = rgb_to_ycocg(tone);
-            s_ycc[hy][hx][0] = yc.x;
-            s_ycc[hy][hx][1] = yc.y;
-            s_ycc[hy][hx][2] = yc.z;
-        }
-    }
-    __syncthreads();
-
-    // phase B: taa on the interior pixels this context owns
-#pragma unroll
-    for (int s = 0; s < 4; ++s) {
-        const int tx = tid & 31, ty = (tid >> 5) + 8 * s;
-        const int x = x0 + tx, y = y0 + ty;
-        if (!have[s] || y < P.own_y0 || y >= P.own_y1) continue;
-        const size_t lp = pix_index(P, x, y);
-        const f3 my_new = mine[s];
-        const float2 pp = P.prev_pixels[lp];
-        const int pix = __float2int_rd(pp.x), piy = __float2int_rd(pp.y);
-        f3 out;
-        if (P.frame == 0 || pix < -1 || piy < -1 || pix >= P.W || piy >= P.H) {
-            out = my_new;
-        } else {
-            TaaBox box;
-            taa_box_init(box);
-#pragma unroll
-            for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-                for (int dx = -1; dx <= 1; ++dx) {
-                    const int sx = x + dx, sy = y + dy;
-                    if (sx >= 0 && sy >= 0 && sx < P.W && sy < P.H) {
-                        const float* t = s_ycc[ty + 1 + dy][tx + 1 + dx];
-                        taa_box_add_ycocg(box, make_f3(t[0], t[1], t[2]), dx == 0 || dy == 0);
-                    }
-                }
-            out = taa_resolve(P, my_new, box, pp.x, pp.y, pix, piy);
-        }
-        store_f3(P.result_cur, lp, out);
-        if (P.user_out) store_f3(P.user_out, lp, out);
-    }
-}
-
-// --------------------------------------------------------------------------------------------
 // launchers
 // --------------------------------------------------------------------------------------------
 static const int h_block_offsets[BMFR_BLOCK_OFFSETS_COUNT][2] = {  // BLOCK_OFFSETS, bmfr.cl:268-285
@@ -287,9 +140,9 @@ void bmfr_host_block_offset(int frame, int* ox, int* oy) {
     *oy = h_block_offsets[i][1];
 }
 
-cudaError_t launch_noise_tile(double* d_noise, double noise_amount, int frame, cudaStream_t st) {
+cudaError_t launch_noise_tile(double* d_noise, float* d_noise_f, double noise_amount, int frame, cudaStream_t st) {
     const int n = (BMFR_FEATURES - 1) * BMFR_BLOCK_PIXELS;
-    noise_tile_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_noise, noise_amount, frame);
+    noise_tile_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_noise, d_noise_f, noise_amount, frame);
     return cudaGetLastError();
 }
 
@@ -318,16 +171,5 @@ cudaError_t launch_k4(const KParams& P, cudaStream_t st) {
 }
 cudaError_t launch_k5(const KParams& P, cudaStream_t st) {
     k5_taa_kernel<<<pixel_grid(P, P.own_y0, P.own_y1), dim3(32, 8), 0, st>>>(P);
-    return cudaGetLastError();
-}
-cudaError_t launch_fit(const KParams& P, cudaStream_t st) {
-    dim3 grid(P.blocks_x, P.by1 - P.by0);
-    if (is_strip(P)) fit_kernel<true><<<grid, BMFR_FIT_THREADS, 0, st>>>(P);
-    else fit_kernel<false><<<grid, BMFR_FIT_THREADS, 0, st>>>(P);
-    return cudaGetLastError();
-}
-cudaError_t launch_post(const KParams& P, cudaStream_t st) {
-    dim3 grid(P.blocks_x, P.by1 - P.by0);
-    post_kernel<<<grid, 256, 0, st>>>(P);
     return cudaGetLastError();
 }

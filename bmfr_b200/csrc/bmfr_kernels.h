@@ -18,6 +18,7 @@ struct KParams {
     int by0, by1;        // block rows to process this frame (whole image: 0..blocks_y)
     int py0, py1;        // image rows the per-pixel stages (K3,K4) cover; K5 covers own_y0..own_y1
     int own_y0, own_y1;
+    int k1_y0, k1_y1;    // image rows reproject_kernel covers: every row a block of by0..by1 reads
     float cam[16];       // prev_frame_camera_matrix
     float poff_x;        // pixel_offset.x
     float poff_y1;       // 1 - pixel_offset.y  (bmfr.cl:353-355)
@@ -39,6 +40,8 @@ struct KParams {
     float* mins_maxs;
     float* mins_inv;              // (min, 1/range or 1) per block and scaled feature, see scale_factor()
     const double* noise;          // [9][1024] add_random() increments of this frame
+    const float* noise_f;         // the same tile rounded to fp32 (FUSED fit)
+    float* rstack;                // FUSED: level-1 factors, [block][warp 0..7][k 0..9][j 0..12], rows unnormalised
     const float* albedo;
     float* filtered;              // STAGED only
     const float* accum_prev;      // accumulated_prev_frame
@@ -52,11 +55,13 @@ struct KParams {
 
 
 void bmfr_host_block_offset(int frame, int* ox, int* oy);
-cudaError_t launch_noise_tile(double* d_noise, double noise_amount, int frame, cudaStream_t st);
+cudaError_t launch_noise_tile(double* d_noise, float* d_noise_f, double noise_amount, int frame, cudaStream_t st);
 cudaError_t launch_k1(const KParams& P, cudaStream_t st);
 cudaError_t launch_k2(const KParams& P, cudaStream_t st);
 cudaError_t launch_k3(const KParams& P, cudaStream_t st);
 cudaError_t launch_k4(const KParams& P, cudaStream_t st);
 cudaError_t launch_k5(const KParams& P, cudaStream_t st);
-cudaError_t launch_fit(const KParams& P, cudaStream_t st);
+cudaError_t launch_reproject(const KParams& P, cudaStream_t st);
+cudaError_t launch_fit_qr(const KParams& P, cudaStream_t st);
+cudaError_t launch_fit_solve(const KParams& P, cudaStream_t st);
 cudaError_t launch_post(const KParams& P, cudaStream_t st);

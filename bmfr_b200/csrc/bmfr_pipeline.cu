@@ -54,7 +54,7 @@ struct DoubleBuffer {
 };
 
 struct StageEvents {
-    cudaEvent_t ev[7] = {};  // boundaries: before K1, after K1, K2, K3, K4, K5 (FUSED: before, after fit, after post)
+    cudaEvent_t ev[7] = {};  // boundaries: before K1, after K1, K2, K3, K4, K5 (FUSED: before, after reproject, fit, post)
     int frame = -1;
     bool created = false;
 };
@@ -82,6 +82,8 @@ struct bmfr_ctx {
     float* mins_maxs = nullptr;             // mins_maxs_buffer
     float* mins_inv = nullptr;              // (min, 1/range) twin of mins_maxs used by the weighted sum
     double* noise = nullptr;
+    float* noise_f = nullptr;               // the tile rounded to fp32 (FUSED fit)
+    float* rstack = nullptr;                // FUSED: level-1 triangles of the two-level fit
     int* d_oob = nullptr;
     int tmp_block_rows = 0;
 
@@ -132,6 +134,8 @@ static void free_ctx(bmfr_ctx* c) {
     cudaFree(c->mins_maxs);
     cudaFree(c->mins_inv);
     cudaFree(c->noise);
+    cudaFree(c->noise_f);
+    cudaFree(c->rstack);
     cudaFree(c->d_oob);
     for (int k = 0; k < 4; ++k)
         for (int s = 0; s < kHostSlots; ++s) cudaFree(c->up[k][s]);
@@ -252,7 +256,10 @@ int bmfr_create(const bmfr_params* params, bmfr_ctx** out_ctx) {
     if (st == 0) st = dev_alloc(&c->mins_maxs, nb * BMFR_FEATURES_SCALED * 2, "mins_maxs");
     if (st == 0) st = dev_alloc(&c->mins_inv, nb * BMFR_FEATURES_SCALED * 2, "mins_inv");
     if (st == 0) st = dev_alloc(&c->noise, (size_t)(BMFR_FEATURES - 1) * BMFR_BLOCK_PIXELS, "noise");
+    if (st == 0) st = dev_alloc(&c->noise_f, (size_t)(BMFR_FEATURES - 1) * BMFR_BLOCK_PIXELS, "noise_f");
     if (st == 0) st = dev_alloc(&c->d_oob, 1, "oob flag");
+    if (st == 0 && p.mode == BMFR_MODE_FUSED)
+        st = dev_alloc(&c->rstack, (size_t)c->tmp_block_rows * g.blocks_x * (BMFR_FIT_THREADS / 32) * BMFR_FEATURES * BMFR_BUFFER_COUNT, "rstack");
     if (st == 0 && p.mode == BMFR_MODE_STAGED) {
         st = dev_alloc(&c->tmp_data, (size_t)c->tmp_block_rows * g.blocks_x * BMFR_BUFFER_COUNT * BMFR_BLOCK_PIXELS, "tmp_data");
         if (st == 0) st = dev_alloc(&c->filtered, npix * 3, "filtered");
@@ -301,6 +308,9 @@ static void fill_params(bmfr_ctx* c, KParams& P, int frame, const float* d_albed
         P.by0 = (P.py0 + 16 - P.off_y) >> 5;
         P.by1 = ((P.py1 - 1 + 16 - P.off_y) >> 5) + 1;
     }
+    // rows the blocks by0..by1 cover (mirrored margin rows fold back into the first / last block row)
+    P.k1_y0 = P.by0 * 32 - 16 + P.off_y; if (P.k1_y0 < 0) P.k1_y0 = 0;
+    P.k1_y1 = P.by1 * 32 - 16 + P.off_y; if (P.k1_y1 > g.height) P.k1_y1 = g.height;
     if (cam_prev) memcpy(P.cam, cam_prev, 16 * sizeof(float));
     P.poff_x = pixel_offset ? pixel_offset[0] : 0.f;
     P.poff_y1 = 1.f - (pixel_offset ? pixel_offset[1] : 0.f);
@@ -316,6 +326,7 @@ static void fill_params(bmfr_ctx* c, KParams& P, int frame, const float* d_albed
     P.prev_spp = c->spp.previous(); P.cur_spp = c->spp.current();
     P.prev_pixels = c->prev_pixels; P.accept = c->accept;
     P.tmp_data = c->tmp_data; P.weights = c->weights; P.mins_maxs = c->mins_maxs; P.mins_inv = c->mins_inv; P.noise = c->noise;
+    P.noise_f = c->noise_f; P.rstack = c->rstack;
     P.albedo = d_albedo; P.filtered = c->filtered;
     P.accum_prev = c->accum.previous(); P.accum_cur = c->accum.current();
     P.tone_mapped = c->tone_mapped;
@@ -348,7 +359,7 @@ static StageEvents* prof_slot(bmfr_ctx* c, int frame) {
 
 static int run_frame(bmfr_ctx* c, const KParams& P, int frame) {
     StageEvents* pe = prof_slot(c, frame);
-    LAUNCH_TRY(launch_noise_tile(c->noise, c->prm.noise_amount, frame, c->stream), "noise_tile_kernel");
+    LAUNCH_TRY(launch_noise_tile(c->noise, c->noise_f, c->prm.noise_amount, frame, c->stream), "noise_tile_kernel");
     MARK(0);
     if (c->prm.mode == BMFR_MODE_STAGED) {
         LAUNCH_TRY(launch_k1(P, c->stream), "accumulate_noisy_data");
@@ -362,10 +373,14 @@ static int run_frame(bmfr_ctx* c, const KParams& P, int frame) {
         LAUNCH_TRY(launch_k5(P, c->stream), "taa");
         MARK(5);
     } else {
-        LAUNCH_TRY(launch_fit(P, c->stream), "fit_kernel");
+        LAUNCH_TRY(launch_reproject(P, c->stream), "reproject_kernel");
         MARK(1);
-        LAUNCH_TRY(launch_post(P, c->stream), "post_kernel");
+        LAUNCH_TRY(launch_fit_qr(P, c->stream), "fit_qr_kernel");
         MARK(2);
+        LAUNCH_TRY(launch_fit_solve(P, c->stream), "fit_solve_kernel");
+        MARK(3);
+        LAUNCH_TRY(launch_post(P, c->stream), "post_kernel");
+        MARK(4);
     }
     return BMFR_OK;
 }
@@ -522,11 +537,24 @@ int bmfr_get_stage_ms(bmfr_ctx* c, int frame, float ms[BMFR_STAGE_COUNT]) {
         for (int i = 0; i < 5; ++i) BMFR_CUDA_TRY(cudaEventElapsedTime(&ms[i], s.ev[i], s.ev[i + 1]));
         BMFR_CUDA_TRY(cudaEventElapsedTime(&ms[BMFR_STAGE_TOTAL], s.ev[0], s.ev[5]));  // K1 start -> K5 end, bmfr.cpp:497-502
     } else {
-        BMFR_CUDA_TRY(cudaEventSynchronize(s.ev[2]));
-        BMFR_CUDA_TRY(cudaEventElapsedTime(&ms[BMFR_STAGE_FITTER], s.ev[0], s.ev[1]));
-        BMFR_CUDA_TRY(cudaEventElapsedTime(&ms[BMFR_STAGE_TAA], s.ev[1], s.ev[2]));
-        BMFR_CUDA_TRY(cudaEventElapsedTime(&ms[BMFR_STAGE_TOTAL], s.ev[0], s.ev[2]));
+        // FUSED: reproject -> ACCUM_NOISY, fit_qr + fit_solve -> FITTER, post -> TAA (it contains K3 and K4)
+        BMFR_CUDA_TRY(cudaEventSynchronize(s.ev[4]));
+        BMFR_CUDA_TRY(cudaEventElapsedTime(&ms[BMFR_STAGE_ACCUM_NOISY], s.ev[0], s.ev[1]));
+        BMFR_CUDA_TRY(cudaEventElapsedTime(&ms[BMFR_STAGE_FITTER], s.ev[1], s.ev[3]));
+        BMFR_CUDA_TRY(cudaEventElapsedTime(&ms[BMFR_STAGE_TAA], s.ev[3], s.ev[4]));
+        BMFR_CUDA_TRY(cudaEventElapsedTime(&ms[BMFR_STAGE_TOTAL], s.ev[0], s.ev[4]));
     }
+    return BMFR_OK;
+}
+
+int bmfr_get_fused_kernel_ms(bmfr_ctx* c, int frame, float ms[BMFR_FUSED_KERNEL_COUNT]) {
+    if (!c || !ms) return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_get_fused_kernel_ms: null argument");
+    if (c->prof.empty() || c->prm.mode != BMFR_MODE_FUSED)
+        return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_get_fused_kernel_ms: needs a FUSED context created with profile=1");
+    StageEvents& s = c->prof[(size_t)frame % kProfileSlots];
+    if (!s.created || s.frame != frame) return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_get_fused_kernel_ms: frame %d not recorded", frame);
+    BMFR_CUDA_TRY(cudaEventSynchronize(s.ev[4]));
+    for (int i = 0; i < BMFR_FUSED_KERNEL_COUNT; ++i) BMFR_CUDA_TRY(cudaEventElapsedTime(&ms[i], s.ev[i], s.ev[i + 1]));
     return BMFR_OK;
 }
 

@@ -54,9 +54,14 @@ def test_720p_matches_oracle():
     _check_frames(cuda, ref, False)
 
 
-def test_staged_and_fused_agree_bitwise():
-    """Both kernel structures run the same per-pixel code: every shared buffer is bit-identical."""
+def test_staged_and_fused_agree():
+    """The two kernel structures share the reprojection code (bit-identical K1 outputs, block min/max
+    and noise tile); the fit and the post-fit passes are separate implementations held to the colour
+    tolerance."""
     a = util.run_cuda(416, 250, 6, mode="staged", keep=KEEP_FUSED, every_frame=False)[0]
     b = util.run_cuda(416, 250, 6, mode="fused", keep=KEEP_FUSED, every_frame=False)[0]
-    for k in KEEP_FUSED:
+    for k in ("noisy_acc", "spp", "prev_pixels", "accept", "noise_tile"):
         assert util.bits_equal(a[k], b[k]), k
+    assert util.floats_equal_mod_zero_sign(a["mins_maxs"], b["mins_maxs"])
+    for k in util.COLOUR_BUFFERS:
+        util.assert_colour_close(b[k], a[k], k)
