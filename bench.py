@@ -33,7 +33,7 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 FRAMES = 60
-FUSED_KERNELS = ("reproject_kernel", "fit_qr_kernel", "fit_solve_kernel", "post_kernel")
+FUSED_KERNELS = ("reproject_kernel", "fit_qr_kernel", "post_kernel")
 SINGLE_GPU_WORKLOAD = (1920, 1080)
 SHARDED_WORKLOAD = (3840, 2160)
 
@@ -56,8 +56,7 @@ def algorithmic_bytes(w, h):
         "taa": 32 * P + 12 * P,
         # FUSED: tmp_data / filtered / tone_mapped never reach HBM
         "reproject_kernel": 95 * P,                        # K1 per image pixel: 73 B in, 22 B out
-        "fit_qr_kernel": 36 * P + (8 * 85 * 4 + 96) * NB,  # normals, positions, accumulated colour once; 8 triangles + min/max out
-        "fit_solve_kernel": (8 * 85 * 4 + 120) * NB,       # triangles in, weights out
+        "fit_qr_kernel": 36 * P + 216 * NB,                # normals, positions, accumulated colour once; weights + min/max out
         "post_kernel": 94 * P + 168 * NB,                  # K3+K4+K5
     }
 
@@ -257,7 +256,7 @@ def run_single_gpu(args):
                            for f in range(1, FRAMES)])  # frame 0 excluded like bmfr.cpp:392-397
         else:
             names = list(FUSED_KERNELS)
-            ms = np.array([[dp.fused_kernel_ms(f)[k] for k in FUSED_KERNELS] + [0.0, dp.stage_ms(f)["total"]]
+            ms = np.array([[dp.fused_kernel_ms(f)[k] for k in FUSED_KERNELS] + [0.0, 0.0, dp.stage_ms(f)["total"]]
                            for f in range(1, FRAMES)])
         mean = ms.mean(axis=0)
         for i, name in enumerate(names):

@@ -1,20 +1,18 @@
 // FUSED mode, first half of the frame: accumulate_noisy_data + fitter (bmfr.cl:290-485, 490-700)
-// as three sm_100a kernels sized for what each phase is bound by:
+// as two sm_100a kernels sized for what each phase is bound by:
 //
 //   reproject_kernel  : K1 for every image pixel, one thread per pixel at full occupancy (gather
 //                       latency bound).  Writes the four per-pixel outputs of bmfr.cl:478-484.
 //                       The block-planar tmp_data of the reference is never written.
-//   fit_qr_kernel     : one CTA per 32x32 block.  Rebuilds the block's 1024x13 matrix in registers
-//                       from the per-pixel buffers (mirrored margins included, bmfr.cl:314-316),
-//                       block min/max + scaling + noise (bmfr.cl:511-542, 623-627), then every
-//                       warp factors its own 128 rows (level 1 of a TSQR) with no block barrier
-//                       and stores its 10x13 triangle.
-//   fit_solve_kernel  : one warp per block: factors the eight stacked triangles (level 2) and
-//                       back-substitutes (bmfr.cl:659-699).
+//   fit_qr_kernel     : one CTA (4 warps) per 32x32 block.  Rebuilds the block's 1024x13 matrix in
+//                       registers from the per-pixel buffers (mirrored margins included,
+//                       bmfr.cl:314-316), block min/max + scaling + noise (bmfr.cl:511-542, 623-627),
+//                       then every warp factors its own 256 rows (level 1 of a TSQR) with no block
+//                       barrier.  The last warp to finish factors the four stacked triangles
+//                       (level 2) and back-substitutes (bmfr.cl:659-699) while the other three have
+//                       already returned their registers to the SM.
 //
-// Splitting level 2 off keeps seven of eight warps from idling (and holding their registers)
-// while one warp finishes the block.  Compiled with --fmad=false (K1 is bit-exact against the
-// oracle); the fit writes fmaf() explicitly.
+// Compiled with --fmad=false (K1 is bit-exact against the oracle); the fit writes fmaf() explicitly.
 #include "bmfr_kernels.h"
 
 #include "bmfr_device.cuh"
@@ -174,115 +172,8 @@ struct QrLoop<ROWS, BMFR_FEATURES> {
 };
 
 // --------------------------------------------------------------------------------------------
-// fit_qr_kernel
-// --------------------------------------------------------------------------------------------
-struct QrShared {
-    float red[BMFR_FIT_WARPS][BMFR_BUFFER_COUNT][QR_RED_STRIDE];
-    float coef[BMFR_FIT_WARPS][16];
-    float minmax[BMFR_FIT_WARPS][2 * BMFR_FEATURES_SCALED];
-};
-
-#ifndef BMFR_QR_MIN_BLOCKS
-#define BMFR_QR_MIN_BLOCKS 3
-#endif
-
-template <bool STRIP>
-__global__ void __launch_bounds__(BMFR_FIT_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(const __grid_constant__ KParams P) {
-    __shared__ __align__(16) QrShared sh;
-    const int bx = blockIdx.x, by = P.by0 + blockIdx.y;
-    const int group = by * P.blocks_x + bx;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NSC = BMFR_FEATURES_SCALED, NNS = BMFR_FEATURES_NOT_SCALED, ROWS = BMFR_ROWS_PER_THREAD;
-
-    // a[s][c-1] = column c of row (lane, warp + 8 s) of the block: the 12 non-constant K1 values
-    // (bmfr.cl:448-453), NaN -> 0 (bmfr.cl:468-469), rebuilt from the per-pixel buffers.
-    float a[ROWS][BMFR_BUFFER_COUNT - 1];
-    const int ux = bx * 32 + lane - 16 + P.off_x;
-    const int x = mirror_index(ux, P.W);
-#pragma unroll
-    for (int s = 0; s < ROWS; ++s) {
-        const int uy = by * 32 + warp + 8 * s - 16 + P.off_y;
-        const int y = mirror_index(uy, P.H);
-        if (STRIP && (y < P.row0 || y >= P.row1)) {
-            *P.oob_flag = 1;
-#pragma unroll
-            for (int c = 0; c < BMFR_BUFFER_COUNT - 1; ++c) a[s][c] = 0.f;
-            continue;
-        }
-        const unsigned int lp = pix_index(P, x, y);
-        const f3 n = load_f3(P.cur_normals, lp);
-        const f3 p = load_f3(P.cur_positions, lp);
-        const f3 col = load_f3(P.cur_noisy_acc, lp);
-        const float px = scrub_nan(p.x), py = scrub_nan(p.y), pz = scrub_nan(p.z);
-        a[s][0] = scrub_nan(n.x); a[s][1] = scrub_nan(n.y); a[s][2] = scrub_nan(n.z);
-        a[s][3] = px; a[s][4] = py; a[s][5] = pz;
-        a[s][6] = px * px; a[s][7] = py * py; a[s][8] = pz * pz;
-        a[s][9] = scrub_nan(col.x); a[s][10] = scrub_nan(col.y); a[s][11] = scrub_nan(col.z);
-    }
-
-    // (i) block min / max of the six scaled features, bmfr.cl:511-535 (exact, so order-free)
-#pragma unroll
-    for (int f = 0; f < NSC; ++f) {
-        const int c = NNS - 1 + f;
-        const float lo = fminf(fminf(a[0][c], a[1][c]), fminf(a[2][c], a[3][c]));
-        const float hi = fmaxf(fmaxf(a[0][c], a[1][c]), fmaxf(a[2][c], a[3][c]));
-        const float wlo = warp_min(lo), whi = warp_max(hi);
-        if (lane == 0) {
-            sh.minmax[warp][2 * f] = wlo;
-            sh.minmax[warp][2 * f + 1] = whi;
-        }
-    }
-    __syncthreads();
-    float mn[NSC], inv[NSC];
-#pragma unroll
-    for (int f = 0; f < NSC; ++f) {
-        float lo = sh.minmax[0][2 * f], hi = sh.minmax[0][2 * f + 1];
-#pragma unroll
-        for (int w = 1; w < BMFR_FIT_WARPS; ++w) {
-            lo = fminf(lo, sh.minmax[w][2 * f]);
-            hi = fmaxf(hi, sh.minmax[w][2 * f + 1]);
-        }
-        mn[f] = lo;
-        inv[f] = scale_factor(lo, hi);
-        if (tid == 2 * f) {
-            P.mins_maxs[(size_t)group * 2 * NSC + tid] = lo;
-            P.mins_inv[(size_t)group * 2 * NSC + tid] = lo;
-        }
-        if (tid == 2 * f + 1) {
-            P.mins_maxs[(size_t)group * 2 * NSC + tid] = hi;
-            P.mins_inv[(size_t)group * 2 * NSC + tid] = inv[f];
-        }
-    }
-
-    // scale (bmfr.cl:538-541), then the first-touch noise on columns 1..9 (bmfr.cl:623-627).  The
-    // reference adds a double (NOISE_AMOUNT is a double literal); the tile holds that double rounded
-    // to fp32, which changes a sum by at most one ulp in rare ties — below the fit's own rounding.
-#pragma unroll
-    for (int s = 0; s < ROWS; ++s) {
-#pragma unroll
-        for (int f = 0; f < NSC; ++f) a[s][NNS - 1 + f] = scale_feature(a[s][NNS - 1 + f], mn[f], inv[f]);
-#pragma unroll
-        for (int c = 1; c < BMFR_FEATURES; ++c)
-            a[s][c - 1] += __ldg(&P.noise_f[(c - 1) * BMFR_BLOCK_PIXELS + tid + BMFR_FIT_THREADS * s]);
-    }
-
-    // (ii) level 1 of the TSQR: this warp's 128 rows -> one 10x13 triangle (unnormalised rows)
-    float* srows = P.rstack + ((size_t)(blockIdx.y * P.blocks_x + bx) * BMFR_FIT_WARPS + warp) * (BMFR_FEATURES * BMFR_BUFFER_COUNT);
-    QrLoop<ROWS, 0>::run(a, &sh.red[warp][0][0], sh.coef[warp], srows, lane);
-}
-
-// --------------------------------------------------------------------------------------------
-// fit_solve_kernel: level 2 + back-substitution, one warp per block
-// --------------------------------------------------------------------------------------------
-#define SOLVE_WARPS 4
-
-struct SolveShared {
-    float red[SOLVE_WARPS][BMFR_BUFFER_COUNT][QR_RED_STRIDE];
-    float coef[SOLVE_WARPS][16];
-    float srows[SOLVE_WARPS][BMFR_FEATURES * BMFR_BUFFER_COUNT];
-};
-
 // General reflector on a matrix with all 13 columns in registers (level 2: column 0 is no longer 1).
+// --------------------------------------------------------------------------------------------
 template <int ROWS, int K>
 __device__ __forceinline__ void qr_step_full(float (&b)[ROWS][BMFR_BUFFER_COUNT], float* __restrict__ red,
                                              float* __restrict__ coefbuf, float* __restrict__ srow, int lane) {
@@ -318,31 +209,144 @@ struct QrLoopFull<ROWS, BMFR_FEATURES> {
     static __device__ __forceinline__ void run(float (&)[ROWS][BMFR_BUFFER_COUNT], float*, float*, float*, int) {}
 };
 
-__global__ void __launch_bounds__(SOLVE_WARPS * 32) fit_solve_kernel(const __grid_constant__ KParams P) {
-    __shared__ __align__(16) SolveShared sh;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nblocks = P.blocks_x * (P.by1 - P.by0);
-    const int local = blockIdx.x * SOLVE_WARPS + warp;
-    if (local >= nblocks) return;
-    const int group = P.by0 * P.blocks_x + local;
-    const float* st = P.rstack + (size_t)local * (BMFR_FIT_WARPS * BMFR_FEATURES * BMFR_BUFFER_COUNT);
+// --------------------------------------------------------------------------------------------
+// fit_qr_kernel: 128 threads per block of 32x32 pixels; lane = column, warp w owns rows 8w..8w+7
+// (eight rows per thread, so one warp-wide reduction serves 256 matrix rows).
+// --------------------------------------------------------------------------------------------
+#define QR_THREADS 128
+#define QR_WARPS 4
+#define QR_ROWS 8
+#define QR_TRI (BMFR_FEATURES * BMFR_BUFFER_COUNT)  // floats of one level-1 triangle, stored as a full 10x13
 
-    // 80 stacked rows, three per lane (rows 80..95 are zero).  Row (w, k) of a level-1 factor is
-    // S_kj / sqrt(S_kk) for j >= k and zero left of its diagonal.
-    constexpr int NS2 = 3;
+struct QrShared {
+    float red[QR_WARPS][BMFR_BUFFER_COUNT][QR_RED_STRIDE];
+    float coef[QR_WARPS][16];
+    float minmax[QR_WARPS][2 * BMFR_FEATURES_SCALED];
+    float scale[3 * BMFR_FEATURES_SCALED + 2];  // block min, max, 1/range
+    float tri[QR_WARPS][QR_TRI];                // level-1 triangles (unnormalised rows S_kj)
+    float fin[QR_TRI];                          // level-2 triangle
+    int arrived;
+};
+
+#ifndef BMFR_QR_MIN_BLOCKS
+#define BMFR_QR_MIN_BLOCKS 3
+#endif
+
+template <bool STRIP>
+__global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(const __grid_constant__ KParams P) {
+    __shared__ __align__(16) QrShared sh;
+    const int bx = blockIdx.x, by = P.by0 + blockIdx.y;
+    const int group = by * P.blocks_x + bx;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NSC = BMFR_FEATURES_SCALED, NNS = BMFR_FEATURES_NOT_SCALED, ROWS = QR_ROWS;
+    if (tid == 0) sh.arrived = 0;
+
+    // a[s][c-1] = column c of row (x_in = lane, y_in = 8 warp + s) of the block: the 12 non-constant
+    // K1 values (bmfr.cl:448-453), NaN -> 0 (bmfr.cl:468-469), rebuilt from the per-pixel buffers.
+    float a[ROWS][BMFR_BUFFER_COUNT - 1];
+    const int ux = bx * 32 + lane - 16 + P.off_x;
+    const int x = mirror_index(ux, P.W);
+#pragma unroll
+    for (int s = 0; s < ROWS; ++s) {
+        const int uy = by * 32 + warp * ROWS + s - 16 + P.off_y;
+        const int y = mirror_index(uy, P.H);
+        if (STRIP && (y < P.row0 || y >= P.row1)) {
+            *P.oob_flag = 1;
+#pragma unroll
+            for (int c = 0; c < BMFR_BUFFER_COUNT - 1; ++c) a[s][c] = 0.f;
+            continue;
+        }
+        const unsigned int lp = pix_index(P, x, y);
+        const f3 n = load_f3(P.cur_normals, lp);
+        const f3 p = load_f3(P.cur_positions, lp);
+        const f3 col = load_f3(P.cur_noisy_acc, lp);
+        const float px = scrub_nan(p.x), py = scrub_nan(p.y), pz = scrub_nan(p.z);
+        a[s][0] = scrub_nan(n.x); a[s][1] = scrub_nan(n.y); a[s][2] = scrub_nan(n.z);
+        a[s][3] = px; a[s][4] = py; a[s][5] = pz;
+        a[s][6] = px * px; a[s][7] = py * py; a[s][8] = pz * pz;
+        a[s][9] = scrub_nan(col.x); a[s][10] = scrub_nan(col.y); a[s][11] = scrub_nan(col.z);
+    }
+
+    // (i) block min / max of the six scaled features, bmfr.cl:511-535 (exact, so order-free)
+#pragma unroll
+    for (int f = 0; f < NSC; ++f) {
+        const int c = NNS - 1 + f;
+        float lo = a[0][c], hi = a[0][c];
+#pragma unroll
+        for (int s = 1; s < ROWS; ++s) {
+            lo = fminf(lo, a[s][c]);
+            hi = fmaxf(hi, a[s][c]);
+        }
+        const float wlo = warp_min(lo), whi = warp_max(hi);
+        if (lane == 0) {
+            sh.minmax[warp][2 * f] = wlo;
+            sh.minmax[warp][2 * f + 1] = whi;
+        }
+    }
+    __syncthreads();
+    if (tid < NSC) {  // one thread per scaled feature finishes the reduction and inverts the range once
+        float lo = sh.minmax[0][2 * tid], hi = sh.minmax[0][2 * tid + 1];
+#pragma unroll
+        for (int w = 1; w < QR_WARPS; ++w) {
+            lo = fminf(lo, sh.minmax[w][2 * tid]);
+            hi = fmaxf(hi, sh.minmax[w][2 * tid + 1]);
+        }
+        const float inv = scale_factor(lo, hi);
+        sh.scale[tid] = lo;
+        sh.scale[NSC + tid] = inv;
+        P.mins_maxs[(size_t)group * 2 * NSC + 2 * tid] = lo;
+        P.mins_maxs[(size_t)group * 2 * NSC + 2 * tid + 1] = hi;
+        P.mins_inv[(size_t)group * 2 * NSC + 2 * tid] = lo;
+        P.mins_inv[(size_t)group * 2 * NSC + 2 * tid + 1] = inv;
+    }
+    __syncthreads();
+    float mn[NSC], inv[NSC];
+#pragma unroll
+    for (int f = 0; f < NSC; ++f) {
+        mn[f] = sh.scale[f];
+        inv[f] = sh.scale[NSC + f];
+    }
+
+    // scale (bmfr.cl:538-541), then the first-touch noise on columns 1..9 (bmfr.cl:623-627).  The
+    // reference adds a double (NOISE_AMOUNT is a double literal); the tile holds that double rounded
+    // to fp32, which changes a sum by at most one ulp in rare ties — below the fit's own rounding.
+#pragma unroll
+    for (int s = 0; s < ROWS; ++s) {
+#pragma unroll
+        for (int f = 0; f < NSC; ++f) a[s][NNS - 1 + f] = scale_feature(a[s][NNS - 1 + f], mn[f], inv[f]);
+#pragma unroll
+        for (int c = 1; c < BMFR_FEATURES; ++c)
+            a[s][c - 1] += __ldg(&P.noise_f[(c - 1) * BMFR_BLOCK_PIXELS + (warp * ROWS + s) * 32 + lane]);
+    }
+
+    // (ii) level 1 of the TSQR: this warp's 256 rows -> one 10x13 triangle in shared memory
+    QrLoop<ROWS, 0>::run(a, &sh.red[warp][0][0], sh.coef[warp], sh.tri[warp], lane);
+
+    // The last warp of the block to get here finishes the block; the others are done (their
+    // registers return to the SM while level 2 runs).
+    __threadfence_block();
+    __syncwarp();
+    int last = 0;
+    if (lane == 0) last = (atomicAdd(&sh.arrived, 1) == QR_WARPS - 1);
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (!last) return;
+    __threadfence_block();
+
+    // level 2: the 40 stacked rows (row (w,k) = S_kj / sqrt(S_kk) for j >= k, zero left of the
+    // diagonal), two per lane
+    constexpr int NS2 = 2;
     float b[NS2][BMFR_BUFFER_COUNT];
 #pragma unroll
     for (int s = 0; s < NS2; ++s) {
         const int row = lane + 32 * s;
-        const bool live = row < BMFR_FIT_WARPS * BMFR_FEATURES;
+        const bool live = row < QR_WARPS * BMFR_FEATURES;
         const int k = row % BMFR_FEATURES;
-        const float* src = st + (live ? row : 0) * BMFR_BUFFER_COUNT;
-        const float scale = live ? rsqrt_approx(__ldg(src + k)) : 0.f;
+        const float* src = &sh.tri[0][0] + (live ? row : 0) * BMFR_BUFFER_COUNT;
+        const float scale = live ? rsqrt_approx(src[k]) : 0.f;
 #pragma unroll
-        for (int c = 0; c < BMFR_BUFFER_COUNT; ++c) b[s][c] = (live && c >= k) ? __ldg(src + c) * scale : 0.f;
+        for (int c = 0; c < BMFR_BUFFER_COUNT; ++c) b[s][c] = (live && c >= k) ? src[c] * scale : 0.f;
     }
-    float* srows = sh.srows[warp];
-    QrLoopFull<NS2, 0>::run(b, &sh.red[warp][0][0], sh.coef[warp], srows, lane);
+    QrLoopFull<NS2, 0>::run(b, &sh.red[warp][0][0], sh.coef[warp], sh.fin, lane);
     __syncwarp();
 
     // (iii) back-substitution, bmfr.cl:659-692.  Row i of R is S_ij / sqrt(S_ii); the square root
@@ -350,12 +354,12 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32) fit_solve_kernel(const __gri
     const int r = lane < BMFR_FEATURES ? lane : 0;
     float row[BMFR_BUFFER_COUNT];
 #pragma unroll
-    for (int c = 0; c < BMFR_BUFFER_COUNT; ++c) row[c] = srows[r * BMFR_BUFFER_COUNT + c];
+    for (int c = 0; c < BMFR_BUFFER_COUNT; ++c) row[c] = sh.fin[r * BMFR_BUFFER_COUNT + c];
     float rhs[3] = {row[10], row[11], row[12]};
     float xs[3] = {0.f, 0.f, 0.f};
 #pragma unroll
     for (int i = BMFR_FEATURES - 1; i >= 0; --i) {
-        const float dinv = 1.0f / __shfl_sync(0xffffffffu, row[i], i);
+        const float dinv = rcp_approx(__shfl_sync(0xffffffffu, row[i], i));
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             const float xi = __shfl_sync(0xffffffffu, rhs[c], i) * dinv;
@@ -384,12 +388,7 @@ cudaError_t launch_reproject(const KParams& P, cudaStream_t st) {
 }
 cudaError_t launch_fit_qr(const KParams& P, cudaStream_t st) {
     const dim3 grid(P.blocks_x, P.by1 - P.by0);
-    if (is_strip(P)) fit_qr_kernel<true><<<grid, BMFR_FIT_THREADS, 0, st>>>(P);
-    else fit_qr_kernel<false><<<grid, BMFR_FIT_THREADS, 0, st>>>(P);
-    return cudaGetLastError();
-}
-cudaError_t launch_fit_solve(const KParams& P, cudaStream_t st) {
-    const int nblocks = P.blocks_x * (P.by1 - P.by0);
-    fit_solve_kernel<<<(nblocks + SOLVE_WARPS - 1) / SOLVE_WARPS, SOLVE_WARPS * 32, 0, st>>>(P);
+    if (is_strip(P)) fit_qr_kernel<true><<<grid, QR_THREADS, 0, st>>>(P);
+    else fit_qr_kernel<false><<<grid, QR_THREADS, 0, st>>>(P);
     return cudaGetLastError();
 }

@@ -41,7 +41,6 @@ struct KParams {
     float* mins_inv;              // (min, 1/range or 1) per block and scaled feature, see scale_factor()
     const double* noise;          // [9][1024] add_random() increments of this frame
     const float* noise_f;         // the same tile rounded to fp32 (FUSED fit)
-    float* rstack;                // FUSED: level-1 factors, [block][warp 0..7][k 0..9][j 0..12], rows unnormalised
     const float* albedo;
     float* filtered;              // STAGED only
     const float* accum_prev;      // accumulated_prev_frame
@@ -63,5 +62,4 @@ cudaError_t launch_k4(const KParams& P, cudaStream_t st);
 cudaError_t launch_k5(const KParams& P, cudaStream_t st);
 cudaError_t launch_reproject(const KParams& P, cudaStream_t st);
 cudaError_t launch_fit_qr(const KParams& P, cudaStream_t st);
-cudaError_t launch_fit_solve(const KParams& P, cudaStream_t st);
 cudaError_t launch_post(const KParams& P, cudaStream_t st);

@@ -83,7 +83,6 @@ struct bmfr_ctx {
     float* mins_inv = nullptr;              // (min, 1/range) twin of mins_maxs used by the weighted sum
     double* noise = nullptr;
     float* noise_f = nullptr;               // the tile rounded to fp32 (FUSED fit)
-    float* rstack = nullptr;                // FUSED: level-1 triangles of the two-level fit
     int* d_oob = nullptr;
     int tmp_block_rows = 0;
 
@@ -135,7 +134,6 @@ static void free_ctx(bmfr_ctx* c) {
     cudaFree(c->mins_inv);
     cudaFree(c->noise);
     cudaFree(c->noise_f);
-    cudaFree(c->rstack);
     cudaFree(c->d_oob);
     for (int k = 0; k < 4; ++k)
         for (int s = 0; s < kHostSlots; ++s) cudaFree(c->up[k][s]);
@@ -258,8 +256,6 @@ int bmfr_create(const bmfr_params* params, bmfr_ctx** out_ctx) {
     if (st == 0) st = dev_alloc(&c->noise, (size_t)(BMFR_FEATURES - 1) * BMFR_BLOCK_PIXELS, "noise");
     if (st == 0) st = dev_alloc(&c->noise_f, (size_t)(BMFR_FEATURES - 1) * BMFR_BLOCK_PIXELS, "noise_f");
     if (st == 0) st = dev_alloc(&c->d_oob, 1, "oob flag");
-    if (st == 0 && p.mode == BMFR_MODE_FUSED)
-        st = dev_alloc(&c->rstack, (size_t)c->tmp_block_rows * g.blocks_x * (BMFR_FIT_THREADS / 32) * BMFR_FEATURES * BMFR_BUFFER_COUNT, "rstack");
     if (st == 0 && p.mode == BMFR_MODE_STAGED) {
         st = dev_alloc(&c->tmp_data, (size_t)c->tmp_block_rows * g.blocks_x * BMFR_BUFFER_COUNT * BMFR_BLOCK_PIXELS, "tmp_data");
         if (st == 0) st = dev_alloc(&c->filtered, npix * 3, "filtered");
@@ -326,7 +322,7 @@ static void fill_params(bmfr_ctx* c, KParams& P, int frame, const float* d_albed
     P.prev_spp = c->spp.previous(); P.cur_spp = c->spp.current();
     P.prev_pixels = c->prev_pixels; P.accept = c->accept;
     P.tmp_data = c->tmp_data; P.weights = c->weights; P.mins_maxs = c->mins_maxs; P.mins_inv = c->mins_inv; P.noise = c->noise;
-    P.noise_f = c->noise_f; P.rstack = c->rstack;
+    P.noise_f = c->noise_f;
     P.albedo = d_albedo; P.filtered = c->filtered;
     P.accum_prev = c->accum.previous(); P.accum_cur = c->accum.current();
     P.tone_mapped = c->tone_mapped;
@@ -377,10 +373,8 @@ static int run_frame(bmfr_ctx* c, const KParams& P, int frame) {
         MARK(1);
         LAUNCH_TRY(launch_fit_qr(P, c->stream), "fit_qr_kernel");
         MARK(2);
-        LAUNCH_TRY(launch_fit_solve(P, c->stream), "fit_solve_kernel");
-        MARK(3);
         LAUNCH_TRY(launch_post(P, c->stream), "post_kernel");
-        MARK(4);
+        MARK(3);
     }
     return BMFR_OK;
 }
@@ -537,12 +531,12 @@ int bmfr_get_stage_ms(bmfr_ctx* c, int frame, float ms[BMFR_STAGE_COUNT]) {
         for (int i = 0; i < 5; ++i) BMFR_CUDA_TRY(cudaEventElapsedTime(&ms[i], s.ev[i], s.ev[i + 1]));
         BMFR_CUDA_TRY(cudaEventElapsedTime(&ms[BMFR_STAGE_TOTAL], s.ev[0], s.ev[5]));  // K1 start -> K5 end, bmfr.cpp:497-502
     } else {
-        // FUSED: reproject -> ACCUM_NOISY, fit_qr + fit_solve -> FITTER, post -> TAA (it contains K3 and K4)
-        BMFR_CUDA_TRY(cudaEventSynchronize(s.ev[4]));
+        // FUSED: reproject -> ACCUM_NOISY, fit_qr -> FITTER, post -> TAA (it contains K3 and K4)
+        BMFR_CUDA_TRY(cudaEventSynchronize(s.ev[3]));
         BMFR_CUDA_TRY(cudaEventElapsedTime(&ms[BMFR_STAGE_ACCUM_NOISY], s.ev[0], s.ev[1]));
-        BMFR_CUDA_TRY(cudaEventElapsedTime(&ms[BMFR_STAGE_FITTER], s.ev[1], s.ev[3]));
-        BMFR_CUDA_TRY(cudaEventElapsedTime(&ms[BMFR_STAGE_TAA], s.ev[3], s.ev[4]));
-        BMFR_CUDA_TRY(cudaEventElapsedTime(&ms[BMFR_STAGE_TOTAL], s.ev[0], s.ev[4]));
+        BMFR_CUDA_TRY(cudaEventElapsedTime(&ms[BMFR_STAGE_FITTER], s.ev[1], s.ev[2]));
+        BMFR_CUDA_TRY(cudaEventElapsedTime(&ms[BMFR_STAGE_TAA], s.ev[2], s.ev[3]));
+        BMFR_CUDA_TRY(cudaEventElapsedTime(&ms[BMFR_STAGE_TOTAL], s.ev[0], s.ev[3]));
     }
     return BMFR_OK;
 }
@@ -553,7 +547,7 @@ int bmfr_get_fused_kernel_ms(bmfr_ctx* c, int frame, float ms[BMFR_FUSED_KERNEL_
         return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_get_fused_kernel_ms: needs a FUSED context created with profile=1");
     StageEvents& s = c->prof[(size_t)frame % kProfileSlots];
     if (!s.created || s.frame != frame) return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_get_fused_kernel_ms: frame %d not recorded", frame);
-    BMFR_CUDA_TRY(cudaEventSynchronize(s.ev[4]));
+    BMFR_CUDA_TRY(cudaEventSynchronize(s.ev[BMFR_FUSED_KERNEL_COUNT]));
     for (int i = 0; i < BMFR_FUSED_KERNEL_COUNT; ++i) BMFR_CUDA_TRY(cudaEventElapsedTime(&ms[i], s.ev[i], s.ev[i + 1]));
     return BMFR_OK;
 }

@@ -21,11 +21,12 @@
 
 #define PT_TILE 32
 #define PT_HALO (PT_TILE + 2)
-#define PT_STRIDE 36  // floats per shared-memory row (>= 34)
+#define PT_STRIDE 36   // floats per shared-memory row (>= 34)
+#define PT_COEF 52     // per block: 10 x (w_r, w_g, w_b, -) then 6 x (min, 1/range)
 
 struct PostShared {
     float ycc[3][PT_HALO][PT_STRIDE];
-    float coef[BMFR_FEATURES * 3 + BMFR_FEATURES_SCALED * 2 + 2];
+    float coef[9][PT_COEF];  // this block ([4]) and its eight neighbours (ring pixels), (dy+1)*3 + dx+1
 };
 
 __device__ __forceinline__ float fast_rcp(float v) {
@@ -40,24 +41,29 @@ __device__ __forceinline__ float tone_map_fast(float v) {  // clamp(powr(max(0,v
     return __saturatef(v);
 }
 
-// weighted_sum for one pixel, bmfr.cl:725-750
-__device__ __forceinline__ f3 weighted_sum_px(f3 n, f3 p, const float* __restrict__ w, const float* __restrict__ mi) {
-    const float feat[BMFR_FEATURES] = {1.f,
-                                       n.x,
-                                       n.y,
-                                       n.z,
-                                       (p.x - mi[0]) * mi[1],
-                                       (p.y - mi[2]) * mi[3],
-                                       (p.z - mi[4]) * mi[5],
-                                       (p.x * p.x - mi[6]) * mi[7],
-                                       (p.y * p.y - mi[8]) * mi[9],
-                                       (p.z * p.z - mi[10]) * mi[11]};
-    f3 c = make_f3(w[0], w[1], w[2]);
+// weighted_sum for one pixel, bmfr.cl:725-750.  cf: the block's coefficients in shared memory; every
+// lane of a tile-interior warp reads the same address (broadcast), so the 42 coefficients cost 13
+// 128-bit shared loads per pixel instead of 42 registers for the whole kernel.
+__device__ __forceinline__ f3 weighted_sum_px(f3 n, f3 p, const float* __restrict__ cf) {
+    const float4* c4 = reinterpret_cast<const float4*>(cf);
+    const float4 m0 = c4[10], m1 = c4[11], m2 = c4[12];  // (min, 1/range) of p.x p.y | p.z p.x^2 | p.y^2 p.z^2
+    const float feat[BMFR_FEATURES - 1] = {n.x,
+                                           n.y,
+                                           n.z,
+                                           (p.x - m0.x) * m0.y,
+                                           (p.y - m0.z) * m0.w,
+                                           (p.z - m1.x) * m1.y,
+                                           (p.x * p.x - m1.z) * m1.w,
+                                           (p.y * p.y - m2.x) * m2.y,
+                                           (p.z * p.z - m2.z) * m2.w};
+    const float4 w0 = c4[0];
+    f3 c = make_f3(w0.x, w0.y, w0.z);
 #pragma unroll
     for (int f = 1; f < BMFR_FEATURES; ++f) {
-        c.x = fmaf(w[f * 3 + 0], feat[f], c.x);
-        c.y = fmaf(w[f * 3 + 1], feat[f], c.y);
-        c.z = fmaf(w[f * 3 + 2], feat[f], c.z);
+        const float4 w = c4[f];
+        c.x = fmaf(w.x, feat[f - 1], c.x);
+        c.y = fmaf(w.y, feat[f - 1], c.y);
+        c.z = fmaf(w.z, feat[f - 1], c.z);
     }
     c.x = c.x < 0.f ? 0.f : c.x;  // keeps NaN like the reference, bmfr.cl:750
     c.y = c.y < 0.f ? 0.f : c.y;
@@ -67,11 +73,12 @@ __device__ __forceinline__ f3 weighted_sum_px(f3 n, f3 p, const float* __restric
 
 // accumulate_filtered_data for one pixel, bmfr.cl:778-856.  Returns the tone-mapped colour.
 template <bool STRIP>
-__device__ __forceinline__ f3 accumulate_filtered_px(const KParams& P, unsigned int lp, f3 filtered, float2 pp,
-                                                     unsigned int accept, bool store) {
+__device__ __forceinline__ f3 accumulate_filtered_px(const KParams& P, unsigned int lp, f3 filtered, bool store) {
     f3 prev = make_f3(0.f, 0.f, 0.f);
     float alpha = 1.f;
+    const unsigned int accept = __ldg(P.accept + lp);
     if (P.frame > 0 && accept != 0) {
+        const float2 pp = __ldg(P.prev_pixels + lp);
         const int pix = __float2int_rd(pp.x), piy = __float2int_rd(pp.y);
         const float frx = pp.x - (float)pix, fry = pp.y - (float)piy;
         const float omx = 1.f - frx, omy = 1.f - fry;
@@ -115,60 +122,64 @@ __device__ __forceinline__ f3 from_ycocg(f3 c) {  // bmfr.cl:192-198
     return make_f3(0.25f * (c.x + c.y - c.z), 0.25f * (c.x + c.z), 0.25f * (c.x - c.y - c.z));
 }
 
-// Stores the YCoCg value of image pixel (x,y) at halo cell (hx,hy) and replicates it into the
-// out-of-image cells whose nearest in-image pixel it is.
 __device__ __forceinline__ void put_cell(PostShared& sh, int hx, int hy, f3 v) {
     sh.ycc[0][hy][hx] = v.x;
     sh.ycc[1][hy][hx] = v.y;
     sh.ycc[2][hy][hx] = v.z;
 }
+// Stores the YCoCg value of image pixel (x,y) at halo cell (hx,hy) and replicates it into the
+// out-of-image cells whose nearest in-image pixel it is.
 __device__ __forceinline__ void put_ycc(PostShared& sh, const KParams& P, int hx, int hy, int x, int y, f3 v) {
     put_cell(sh, hx, hy, v);
     const int ex = (x == 0) ? -1 : (x == P.W - 1) ? 1 : 0;
     const int ey = (y == 0) ? -1 : (y == P.H - 1) ? 1 : 0;
+    if ((ex | ey) == 0) return;
     const bool okx = ex != 0 && (unsigned)(hx + ex) < PT_HALO, oky = ey != 0 && (unsigned)(hy + ey) < PT_HALO;
     if (okx) put_cell(sh, hx + ex, hy, v);
     if (oky) put_cell(sh, hx, hy + ey, v);
     if (okx && oky) put_cell(sh, hx + ex, hy + ey, v);
 }
 
+// weighted_sum -> accumulate_filtered_data -> tone map of image pixel (x,y) into halo cell (hx,hy)
 template <bool STRIP>
-__global__ void __launch_bounds__(256, 2) post_kernel(const __grid_constant__ KParams P) {
+__device__ __forceinline__ void phase_a_pixel(PostShared& sh, const KParams& P, const float* cf, int hx, int hy, int x, int y,
+                                              bool store) {
+    const unsigned int lp = pix_index(P, x, y);
+    const f3 filtered = weighted_sum_px(load_f3(P.cur_normals, lp), load_f3(P.cur_positions, lp), cf);
+    const f3 tone = accumulate_filtered_px<STRIP>(P, lp, filtered, store);
+    put_ycc(sh, P, hx, hy, x, y, to_ycocg(tone));
+}
+
+#ifndef BMFR_POST_MIN_BLOCKS
+#define BMFR_POST_MIN_BLOCKS 4
+#endif
+
+template <bool STRIP>
+__global__ void __launch_bounds__(256, BMFR_POST_MIN_BLOCKS) post_kernel(const __grid_constant__ KParams P) {
     __shared__ __align__(16) PostShared sh;
     const int bx = blockIdx.x, by = P.by0 + blockIdx.y;
-    const int group = by * P.blocks_x + bx;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int x0 = bx * 32 - 16 + P.off_x, y0 = by * 32 - 16 + P.off_y;  // tile origin in image coordinates
     constexpr int NW = BMFR_FEATURES * 3, NM = BMFR_FEATURES_SCALED * 2;
 
-    if (tid < NW) sh.coef[tid] = __ldg(P.weights + (size_t)group * NW + tid);
-    else if (tid < NW + NM) sh.coef[tid] = __ldg(P.mins_inv + (size_t)group * NM + tid - NW);
+    // coefficients of the 3x3 block neighbourhood -> shared memory
+    for (int i = tid; i < 9 * (NW + NM); i += 256) {
+        const int nb = i / (NW + NM), k = i % (NW + NM);
+        const int gx = bx + nb % 3 - 1, gy = by + nb / 3 - 1;
+        if (gx < 0 || gx >= P.blocks_x || gy < 0 || gy >= P.blocks_y) continue;
+        const size_t g = (size_t)gy * P.blocks_x + gx;
+        if (k < NW) sh.coef[nb][(k / 3) * 4 + k % 3] = __ldg(P.weights + g * NW + k);
+        else sh.coef[nb][40 + k - NW] = __ldg(P.mins_inv + g * NM + k - NW);
+    }
     __syncthreads();
 
     const int x = x0 + lane;
     const bool col_ok = x >= 0 && x < P.W;
-    f3 mine[4];
-    float2 pp[4];
-    bool have[4];
-    {
-        float w[NW], mi[NM];
+    // phase A, interior: column strip x, rows 4*warp .. 4*warp+3
 #pragma unroll
-        for (int i = 0; i < NW; ++i) w[i] = sh.coef[i];
-#pragma unroll
-        for (int i = 0; i < NM; ++i) mi[i] = sh.coef[NW + i];
-        // phase A, interior
-#pragma unroll
-        for (int s = 0; s < 4; ++s) {
-            const int ty = 4 * warp + s, y = y0 + ty;
-            have[s] = col_ok && y >= P.py0 && y < P.py1;
-            if (have[s]) {
-                const unsigned int lp = pix_index(P, x, y);
-                const f3 filtered = weighted_sum_px(load_f3(P.cur_normals, lp), load_f3(P.cur_positions, lp), w, mi);
-                pp[s] = __ldg(P.prev_pixels + lp);
-                mine[s] = accumulate_filtered_px<STRIP>(P, lp, filtered, pp[s], __ldg(P.accept + lp), true);
-                put_ycc(sh, P, lane + 1, ty + 1, x, y, to_ycocg(mine[s]));
-            }
-        }
+    for (int s = 0; s < 4; ++s) {
+        const int ty = 4 * warp + s, y = y0 + ty;
+        if (col_ok && y >= P.py0 && y < P.py1) phase_a_pixel<STRIP>(sh, P, sh.coef[4], lane + 1, ty + 1, x, y, true);
     }
     // phase A, ring: 4 * 33 = 132 pixels, coefficients of the pixel's own block
     if (tid < 4 * (PT_HALO - 1)) {
@@ -180,23 +191,55 @@ __global__ void __launch_bounds__(256, 2) post_kernel(const __grid_constant__ KP
         else { hx = 0; hy = PT_HALO - 1 - k; }
         const int rx = x0 + hx - 1, ry = y0 + hy - 1;
         if (rx >= 0 && rx < P.W && ry >= P.py0 && ry < P.py1) {
-            const int g = k3_group(P, rx, ry);
-            const unsigned int lp = pix_index(P, rx, ry);
-            float w[NW], mi[NM];
-#pragma unroll
-            for (int i = 0; i < NW; ++i) w[i] = __ldg(P.weights + (size_t)g * NW + i);
-#pragma unroll
-            for (int i = 0; i < NM; ++i) mi[i] = __ldg(P.mins_inv + (size_t)g * NM + i);
-            const f3 filtered = weighted_sum_px(load_f3(P.cur_normals, lp), load_f3(P.cur_positions, lp), w, mi);
-            const f3 tone = accumulate_filtered_px<STRIP>(P, lp, filtered, __ldg(P.prev_pixels + lp), __ldg(P.accept + lp), false);
-            put_ycc(sh, P, hx, hy, rx, ry, to_ycocg(tone));
+            const int nb = ((hy == 0) ? 0 : (hy == PT_HALO - 1) ? 6 : 3) + ((hx == 0) ? 0 : (hx == PT_HALO - 1) ? 2 : 1);
+            phase_a_pixel<STRIP>(sh, P, sh.coef[nb], hx, hy, rx, ry, false);
         }
     }
     __syncthreads();
 
-    // phase B: clamp bounds of the strip's four pixels, plane by plane.  Halo rows 4*warp .. 4*warp+5
-    // cover the 3x3 neighbourhoods of tile rows 4*warp .. 4*warp+3; this thread's column is lane+1.
-    float lo[4][3], hi[4][3];
+    // phase B, step 1: history sample of each of the strip's pixels in YCoCg (bmfr.cl:922-965)
+    f3 hist[4];
+    unsigned int live = 0;  // bit s: pixel s is written; bit 4+s: it takes the temporal path
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const int y = y0 + 4 * warp + s;
+        hist[s] = make_f3(0.f, 0.f, 0.f);
+        if (!(col_ok && y >= P.py0 && y < P.py1 && y >= P.own_y0 && y < P.own_y1)) continue;
+        live |= 1u << s;
+        if (P.frame == 0) continue;
+        const float2 pp = __ldg(P.prev_pixels + pix_index(P, x, y));
+        const int pix = __float2int_rd(pp.x), piy = __float2int_rd(pp.y);
+        if (pix < -1 || piy < -1 || pix >= P.W || piy >= P.H) continue;  // bmfr.cl:884-890
+        live |= 16u << s;
+        const float frx = pp.x - (float)pix, fry = pp.y - (float)piy;
+        const float omx = 1.f - frx, omy = 1.f - fry;
+        const float w[4] = {omx * omy, frx * omy, omx * fry, frx * fry};
+        f3 prev = make_f3(0.f, 0.f, 0.f);
+        float total = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {  // bmfr.cl:929-960
+            const int dx = i & 1, dy = i >> 1;
+            const bool ok_y = dy ? (piy < P.H - 1) : (piy >= 0);
+            const bool ok_x = dx ? (pix < P.W - 1) : (pix >= 0);
+            if (ok_x && ok_y) {
+                const int sy = piy + dy;
+                if (STRIP && (sy < P.row0 || sy >= P.row1)) {
+                    *P.oob_flag = 1;
+                    continue;
+                }
+                const f3 pc = load_f3(P.result_prev, pix_index(P, pix + dx, sy));
+                prev.x = fmaf(w[i], pc.x, prev.x);
+                prev.y = fmaf(w[i], pc.y, prev.y);
+                prev.z = fmaf(w[i], pc.z, prev.z);
+                total += w[i];
+            }
+        }
+        const float inv = fast_rcp(total);  // 0 * inf = NaN on the image edge like the 0/0 of bmfr.cl:962
+        hist[s] = to_ycocg(make_f3(prev.x * inv, prev.y * inv, prev.z * inv));
+    }
+    // step 2: clamp to the neighbourhood box, plane by plane (bmfr.cl:893-920, 967-969).  Halo rows
+    // 4*warp .. 4*warp+5 cover the 3x3 neighbourhoods of the strip; this thread's column is lane+1.
+    f3 mine[4];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         float ctr[6], rmin[6], rmax[6];
@@ -214,49 +257,23 @@ __global__ void __launch_bounds__(256, 2) post_kernel(const __grid_constant__ KP
             const float max_box = fmaxf(fmaxf(rmax[s], rmax[s + 1]), rmax[s + 2]);
             const float min_cross = fminf(fminf(ctr[s], rmin[s + 1]), ctr[s + 2]);
             const float max_cross = fmaxf(fmaxf(ctr[s], rmax[s + 1]), ctr[s + 2]);
-            lo[s][c] = (min_box + min_cross) * 0.5f;  // bmfr.cl:967-968
-            hi[s][c] = (max_box + max_cross) * 0.5f;
+            const float lo = (min_box + min_cross) * 0.5f, hi = (max_box + max_cross) * 0.5f;
+            float& h = (c == 0) ? hist[s].x : (c == 1) ? hist[s].y : hist[s].z;
+            h = fminf(fmaxf(h, lo), hi);
+            float& m = (c == 0) ? mine[s].x : (c == 1) ? mine[s].y : mine[s].z;
+            m = ctr[s + 1];
         }
     }
+    // step 3: blend and store (bmfr.cl:971-973)
+    const float a = P.taa_blend_alpha, oma = 1.f - P.taa_blend_alpha;
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
-        const int y = y0 + 4 * warp + s;
-        if (!have[s] || y < P.own_y0 || y >= P.own_y1) continue;
-        const unsigned int lp = pix_index(P, x, y);
-        const f3 my_new = mine[s];
-        const int pix = __float2int_rd(pp[s].x), piy = __float2int_rd(pp[s].y);
-        f3 out = my_new;
-        if (!(P.frame == 0 || pix < -1 || piy < -1 || pix >= P.W || piy >= P.H)) {  // bmfr.cl:884-890
-            const float frx = pp[s].x - (float)pix, fry = pp[s].y - (float)piy;
-            const float omx = 1.f - frx, omy = 1.f - fry;
-            const float w[4] = {omx * omy, frx * omy, omx * fry, frx * fry};
-            f3 prev = make_f3(0.f, 0.f, 0.f);
-            float total = 0.f;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {  // bmfr.cl:929-960
-                const int dx = i & 1, dy = i >> 1;
-                const bool ok_y = dy ? (piy < P.H - 1) : (piy >= 0);
-                const bool ok_x = dx ? (pix < P.W - 1) : (pix >= 0);
-                if (ok_x && ok_y) {
-                    const int sy = piy + dy;
-                    if (STRIP && (sy < P.row0 || sy >= P.row1)) {
-                        *P.oob_flag = 1;
-                        continue;
-                    }
-                    const f3 pc = load_f3(P.result_prev, pix_index(P, pix + dx, sy));
-                    prev.x = fmaf(w[i], pc.x, prev.x);
-                    prev.y = fmaf(w[i], pc.y, prev.y);
-                    prev.z = fmaf(w[i], pc.z, prev.z);
-                    total += w[i];
-                }
-            }
-            const float inv = 1.0f / total;  // 0/0 on the image edge like bmfr.cl:962
-            const f3 py = to_ycocg(make_f3(prev.x * inv, prev.y * inv, prev.z * inv));
-            const f3 cl = make_f3(fminf(fmaxf(py.x, lo[s][0]), hi[s][0]), fminf(fmaxf(py.y, lo[s][1]), hi[s][1]),
-                                  fminf(fmaxf(py.z, lo[s][2]), hi[s][2]));
-            const f3 pr = from_ycocg(cl);
-            const float a = P.taa_blend_alpha, oma = 1.f - P.taa_blend_alpha;
-            out = make_f3(fmaf(a, my_new.x, oma * pr.x), fmaf(a, my_new.y, oma * pr.y), fmaf(a, my_new.z, oma * pr.z));
+        if (!(live & (1u << s))) continue;
+        const unsigned int lp = pix_index(P, x, y0 + 4 * warp + s);
+        f3 out = from_ycocg(mine[s]);  // this pixel's tone-mapped colour
+        if (live & (16u << s)) {
+            const f3 pr = from_ycocg(hist[s]);
+            out = make_f3(fmaf(a, out.x, oma * pr.x), fmaf(a, out.y, oma * pr.y), fmaf(a, out.z, oma * pr.z));
         }
         store_f3(P.result_cur, lp, out);
         if (P.user_out) store_f3(P.user_out, lp, out);

@@ -14,7 +14,7 @@ import numpy as np
 from . import _lib
 from ._lib import BUF, MODE_FUSED, MODE_STAGED, STAGES, BmfrError, Geometry, HaloPlan, Params
 
-FUSED_KERNELS = ("reproject_kernel", "fit_qr_kernel", "fit_solve_kernel", "post_kernel")
+FUSED_KERNELS = ("reproject_kernel", "fit_qr_kernel", "post_kernel")
 
 _BUF_DTYPE = dict(noisy_acc=np.float32, spp=np.uint8, prev_pixels=np.float32, accept=np.uint8, tmp_data=np.float32,
                   weights=np.float32, mins_maxs=np.float32, filtered=np.float32, accum=np.float32,
@@ -134,8 +134,8 @@ class Denoiser:
         return dict(zip(STAGES, ms))
 
     def fused_kernel_ms(self, frame):
-        """Device time of reproject / fit_qr / fit_solve / post for one frame (FUSED, profile=True)."""
-        ms = (C.c_float * 4)()
+        """Device time of reproject / fit_qr / post for one frame (FUSED, profile=True)."""
+        ms = (C.c_float * 3)()
         _lib.check(self.lib.bmfr_get_fused_kernel_ms(self._h, frame, ms))
         return dict(zip(FUSED_KERNELS, ms))
 

@@ -46,8 +46,8 @@ typedef enum bmfr_status {
 } bmfr_status;
 
 /* Kernel structure.  STAGED launches the reference's five kernels one by one (bmfr.cpp:446-476).
- * FUSED launches four: reproject (accumulate_noisy_data per image pixel), fit_qr + fit_solve (the
- * fitter as a two-level QR straight from the per-pixel buffers) and post (weighted_sum +
+ * FUSED launches three: reproject (accumulate_noisy_data per image pixel), fit_qr (the fitter as a
+ * two-level QR straight from the per-pixel buffers) and post (weighted_sum +
  * accumulate_filtered_data + taa in one pass).  Both produce the same buffers the reference's loop
  * exposes to its caller; FUSED does not materialise tmp_data / filtered / tone_mapped in HBM. */
 typedef enum bmfr_mode { BMFR_MODE_STAGED = 0, BMFR_MODE_FUSED = 1 } bmfr_mode;
@@ -168,11 +168,11 @@ int bmfr_read_buffer(bmfr_ctx* ctx, int buffer, void* h_dst, size_t bytes);
 
 /* Per-stage device time of one frame in ms (params.profile = 1), the quantity the reference
  * collects with OpenCL events (bmfr.cpp:488-506).  FUSED reports reproject in
- * BMFR_STAGE_ACCUM_NOISY, fit_qr + fit_solve in BMFR_STAGE_FITTER, post in BMFR_STAGE_TAA and zero
+ * BMFR_STAGE_ACCUM_NOISY, fit_qr in BMFR_STAGE_FITTER, post in BMFR_STAGE_TAA and zero
  * elsewhere. */
 int bmfr_get_stage_ms(bmfr_ctx* ctx, int frame, float ms[BMFR_STAGE_COUNT]);
-/* FUSED contexts: device time of each of the four kernels of one frame, in launch order. */
-enum { BMFR_FUSED_REPROJECT = 0, BMFR_FUSED_FIT_QR = 1, BMFR_FUSED_FIT_SOLVE = 2, BMFR_FUSED_POST = 3, BMFR_FUSED_KERNEL_COUNT = 4 };
+/* FUSED contexts: device time of each of the three kernels of one frame, in launch order. */
+enum { BMFR_FUSED_REPROJECT = 0, BMFR_FUSED_FIT_QR = 1, BMFR_FUSED_POST = 2, BMFR_FUSED_KERNEL_COUNT = 3 };
 int bmfr_get_fused_kernel_ms(bmfr_ctx* ctx, int frame, float ms[BMFR_FUSED_KERNEL_COUNT]);
 /* Number of kernels this library has launched on the context so far. */
 long long bmfr_kernel_launches(const bmfr_ctx* ctx);

@@ -21,7 +21,7 @@ done
 [ -n "$NO_NCU" ] && exit 0
 SHORT="python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu"
 $SHORT > $OUT/plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'reproject_kernel|fit_qr_kernel|fit_solve_kernel|post_kernel|noise_tile' -s 200 -c 100 --csv --log-file $OUT/launches.csv $SHORT > $OUT/ncu_launches.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'reproject_kernel|fit_qr_kernel|post_kernel|noise_tile' -s 160 -c 80 --csv --log-file $OUT/launches.csv $SHORT > $OUT/ncu_launches.log 2>&1
 $SHORT > $OUT/plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:'reproject_kernel|fit_qr_kernel|fit_solve_kernel|post_kernel' -s 80 -c 4 -f -o $OUT/prof $SHORT > $OUT/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'reproject_kernel|fit_qr_kernel|post_kernel' -s 60 -c 3 -f -o $OUT/prof $SHORT > $OUT/ncu_full.log 2>&1
 ls $OUT
