@@ -4,13 +4,13 @@
 //   reproject_kernel  : K1 for every image pixel, one thread per pixel at full occupancy (gather
 //                       latency bound).  Writes the four per-pixel outputs of bmfr.cl:478-484.
 //                       The block-planar tmp_data of the reference is never written.
-//   fit_qr_kernel     : one CTA (4 warps) per 32x32 block.  Rebuilds the block's 1024x13 matrix in
-//                       registers from the per-pixel buffers (mirrored margins included,
-//                       bmfr.cl:314-316), block min/max + scaling + noise (bmfr.cl:511-542, 623-627),
-//                       then every warp factors its own 256 rows (level 1 of a TSQR) with no block
-//                       barrier.  The last warp to finish factors the four stacked triangles
-//                       (level 2) and back-substitutes (bmfr.cl:659-699) while the other three have
-//                       already returned their registers to the SM.
+//   fit_qr_kernel     : persistent warp-specialised CTAs walking over the 32x32 blocks.  Four
+//                       compute warps rebuild the block's 1024x13 matrix in registers from the
+//                       per-pixel buffers (mirrored margins included, bmfr.cl:314-316; prefetched
+//                       with cp.async one block ahead), block min/max + scaling + noise
+//                       (bmfr.cl:511-542, 623-627), then each factors its own 256 rows (level 1 of a
+//                       TSQR) without a block barrier.  A fifth warp factors the four stacked
+//                       triangles (level 2) and back-substitutes (bmfr.cl:659-699) concurrently.
 //
 // Compiled with --fmad=false (K1 is bit-exact against the oracle); the fit writes fmaf() explicitly.
 #include "bmfr_kernels.h"
@@ -210,23 +210,87 @@ struct QrLoopFull<ROWS, BMFR_FEATURES> {
 };
 
 // --------------------------------------------------------------------------------------------
-// fit_qr_kernel: 128 threads per block of 32x32 pixels; lane = column, warp w owns rows 8w..8w+7
-// (eight rows per thread, so one warp-wide reduction serves 256 matrix rows).
+// fit_qr_kernel: persistent, warp-specialised.
+//
+// A CTA is four compute warps and one solver warp and walks over blocks  b = blockIdx.x + i*gridDim.x.
+//   compute warp w, lane l : rows (x_in = l, y_in = 8w .. 8w+7) of the block, eight rows per thread, so
+//       one warp-wide reduction serves 256 matrix rows.  Each thread prefetches its own 72 input
+//       floats of the NEXT block with cp.async into a private shared-memory slot while it factors
+//       the current one (no load phase, no barrier for the data).  Per block: block min/max through
+//       two 128-thread named barriers, scaling + noise, level 1 of the TSQR (this warp's 256 rows ->
+//       one 10x13 triangle) written to a two-slot shared-memory ring.
+//   solver warp            : waits for the four triangles of a block (mbarrier), factors the 40
+//       stacked rows (level 2), back-substitutes (bmfr.cl:659-699) and writes the weights, while the
+//       compute warps are already on the next block.
 // --------------------------------------------------------------------------------------------
-#define QR_THREADS 128
-#define QR_WARPS 4
+#define QR_COMPUTE_WARPS 4
+#define QR_COMPUTE_THREADS (QR_COMPUTE_WARPS * 32)
+#define QR_THREADS (QR_COMPUTE_THREADS + 32)
 #define QR_ROWS 8
 #define QR_TRI (BMFR_FEATURES * BMFR_BUFFER_COUNT)  // floats of one level-1 triangle, stored as a full 10x13
+#define QR_SLOTS 2
+#define QR_INPUTS (QR_ROWS * 9)                     // floats a compute thread needs per block
 
 struct QrShared {
-    float red[QR_WARPS][BMFR_BUFFER_COUNT][QR_RED_STRIDE];
-    float coef[QR_WARPS][16];
-    float minmax[QR_WARPS][2 * BMFR_FEATURES_SCALED];
-    float scale[3 * BMFR_FEATURES_SCALED + 2];  // block min, max, 1/range
-    float tri[QR_WARPS][QR_TRI];                // level-1 triangles (unnormalised rows S_kj)
-    float fin[QR_TRI];                          // level-2 triangle
-    int arrived;
+    float stage[QR_INPUTS][QR_COMPUTE_THREADS];  // cp.async landing zone, [value][thread]: conflict-free both ways
+    float red[QR_COMPUTE_WARPS + 1][BMFR_BUFFER_COUNT][QR_RED_STRIDE];
+    float coef[QR_COMPUTE_WARPS + 1][16];
+    float minmax[QR_COMPUTE_WARPS][2 * BMFR_FEATURES_SCALED];
+    float scale[2 * BMFR_FEATURES_SCALED + 4];   // block min, 1/range
+    float tri[QR_SLOTS][QR_COMPUTE_WARPS][QR_TRI];  // level-1 triangles (unnormalised rows S_kj)
+    float fin[QR_TRI];                           // level-2 triangle
+    unsigned long long full[QR_SLOTS], empty[QR_SLOTS];
 };
+
+__device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned int parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(b)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void compute_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(QR_COMPUTE_THREADS) : "memory"); }
+__device__ __forceinline__ void cp_async4(float* dst_smem, const float* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// Issues the asynchronous copies of this compute thread's inputs of block (bx, by): normals,
+// positions and accumulated colour of its eight (mirrored, bmfr.cl:314-316) pixels.
+template <bool STRIP>
+__device__ __forceinline__ void qr_prefetch(const KParams& P, QrShared& sh, int bx, int by, int tid) {
+    const int lane = tid & 31, warp = tid >> 5;
+    const int x = mirror_index(bx * 32 + lane - 16 + P.off_x, P.W);
+#pragma unroll
+    for (int s = 0; s < QR_ROWS; ++s) {
+        const int y = mirror_index(by * 32 + warp * QR_ROWS + s - 16 + P.off_y, P.H);
+        if (STRIP && (y < P.row0 || y >= P.row1)) {
+            *P.oob_flag = 1;
+#pragma unroll
+            for (int c = 0; c < 9; ++c) sh.stage[s * 9 + c][tid] = 0.f;
+            continue;
+        }
+        const size_t o = (size_t)(pix_index(P, x, y) * 3u);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            cp_async4(&sh.stage[s * 9 + c][tid], P.cur_normals + o + c);
+            cp_async4(&sh.stage[s * 9 + 3 + c][tid], P.cur_positions + o + c);
+            cp_async4(&sh.stage[s * 9 + 6 + c][tid], P.cur_noisy_acc + o + c);
+        }
+    }
+}
 
 #ifndef BMFR_QR_MIN_BLOCKS
 #define BMFR_QR_MIN_BLOCKS 3
@@ -234,144 +298,159 @@ struct QrShared {
 
 template <bool STRIP>
 __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(const __grid_constant__ KParams P) {
-    __shared__ __align__(16) QrShared sh;
-    const int bx = blockIdx.x, by = P.by0 + blockIdx.y;
-    const int group = by * P.blocks_x + bx;
+    extern __shared__ __align__(16) unsigned char qr_smem[];
+    QrShared& sh = *reinterpret_cast<QrShared*>(qr_smem);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NSC = BMFR_FEATURES_SCALED, NNS = BMFR_FEATURES_NOT_SCALED, ROWS = QR_ROWS;
-    if (tid == 0) sh.arrived = 0;
+    const int nblocks = P.blocks_x * (P.by1 - P.by0);
+    const int first = blockIdx.x, stride = gridDim.x;
+    if (first >= nblocks) return;
+    const int iters = (nblocks - first + stride - 1) / stride;
 
-    // a[s][c-1] = column c of row (x_in = lane, y_in = 8 warp + s) of the block: the 12 non-constant
-    // K1 values (bmfr.cl:448-453), NaN -> 0 (bmfr.cl:468-469), rebuilt from the per-pixel buffers.
-    float a[ROWS][BMFR_BUFFER_COUNT - 1];
-    const int ux = bx * 32 + lane - 16 + P.off_x;
-    const int x = mirror_index(ux, P.W);
+    if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < ROWS; ++s) {
-        const int uy = by * 32 + warp * ROWS + s - 16 + P.off_y;
-        const int y = mirror_index(uy, P.H);
-        if (STRIP && (y < P.row0 || y >= P.row1)) {
-            *P.oob_flag = 1;
-#pragma unroll
-            for (int c = 0; c < BMFR_BUFFER_COUNT - 1; ++c) a[s][c] = 0.f;
-            continue;
+        for (int i = 0; i < QR_SLOTS; ++i) {
+            mbar_init(&sh.full[i], QR_COMPUTE_THREADS);
+            mbar_init(&sh.empty[i], 32);
         }
-        const unsigned int lp = pix_index(P, x, y);
-        const f3 n = load_f3(P.cur_normals, lp);
-        const f3 p = load_f3(P.cur_positions, lp);
-        const f3 col = load_f3(P.cur_noisy_acc, lp);
-        const float px = scrub_nan(p.x), py = scrub_nan(p.y), pz = scrub_nan(p.z);
-        a[s][0] = scrub_nan(n.x); a[s][1] = scrub_nan(n.y); a[s][2] = scrub_nan(n.z);
-        a[s][3] = px; a[s][4] = py; a[s][5] = pz;
-        a[s][6] = px * px; a[s][7] = py * py; a[s][8] = pz * pz;
-        a[s][9] = scrub_nan(col.x); a[s][10] = scrub_nan(col.y); a[s][11] = scrub_nan(col.z);
-    }
-
-    // (i) block min / max of the six scaled features, bmfr.cl:511-535 (exact, so order-free)
-#pragma unroll
-    for (int f = 0; f < NSC; ++f) {
-        const int c = NNS - 1 + f;
-        float lo = a[0][c], hi = a[0][c];
-#pragma unroll
-        for (int s = 1; s < ROWS; ++s) {
-            lo = fminf(lo, a[s][c]);
-            hi = fmaxf(hi, a[s][c]);
-        }
-        const float wlo = warp_min(lo), whi = warp_max(hi);
-        if (lane == 0) {
-            sh.minmax[warp][2 * f] = wlo;
-            sh.minmax[warp][2 * f + 1] = whi;
-        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (tid < NSC) {  // one thread per scaled feature finishes the reduction and inverts the range once
-        float lo = sh.minmax[0][2 * tid], hi = sh.minmax[0][2 * tid + 1];
+
+    if (warp == QR_COMPUTE_WARPS) {
+        // ---------------- solver warp ----------------
+        for (int it = 0; it < iters; ++it) {
+            const int local = first + it * stride, slot = it % QR_SLOTS;
+            const int group = P.by0 * P.blocks_x + local;
+            mbar_wait(&sh.full[slot], (it / QR_SLOTS) & 1);
+            // level 2: the 40 stacked rows (row (w,k) = S_kj / sqrt(S_kk) for j >= k, zero left of the
+            // diagonal), two per lane
+            constexpr int NS2 = 2;
+            float b[NS2][BMFR_BUFFER_COUNT];
 #pragma unroll
-        for (int w = 1; w < QR_WARPS; ++w) {
-            lo = fminf(lo, sh.minmax[w][2 * tid]);
-            hi = fmaxf(hi, sh.minmax[w][2 * tid + 1]);
+            for (int s = 0; s < NS2; ++s) {
+                const int row = lane + 32 * s;
+                const bool live = row < QR_COMPUTE_WARPS * BMFR_FEATURES;
+                const int k = row % BMFR_FEATURES;
+                const float* src = &sh.tri[slot][0][0] + (live ? row : 0) * BMFR_BUFFER_COUNT;
+                const float scale = live ? rsqrt_approx(src[k]) : 0.f;
+#pragma unroll
+                for (int c = 0; c < BMFR_BUFFER_COUNT; ++c) b[s][c] = (live && c >= k) ? src[c] * scale : 0.f;
+            }
+            mbar_arrive(&sh.empty[slot]);  // the triangles are in registers: the slot may be refilled
+            QrLoopFull<NS2, 0>::run(b, &sh.red[QR_COMPUTE_WARPS][0][0], sh.coef[QR_COMPUTE_WARPS], sh.fin, lane);
+            __syncwarp();
+            // (iii) back-substitution, bmfr.cl:659-692.  Row i of R is S_ij / sqrt(S_ii); the square
+            // root cancels in R x = rhs, so the unnormalised rows are solved directly.
+            const int r = lane < BMFR_FEATURES ? lane : 0;
+            float row[BMFR_BUFFER_COUNT];
+#pragma unroll
+            for (int c = 0; c < BMFR_BUFFER_COUNT; ++c) row[c] = sh.fin[r * BMFR_BUFFER_COUNT + c];
+            float rhs[3] = {row[10], row[11], row[12]};
+            float xs[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+            for (int i = BMFR_FEATURES - 1; i >= 0; --i) {
+                const float dinv = rcp_approx(__shfl_sync(0xffffffffu, row[i], i));
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float xi = __shfl_sync(0xffffffffu, rhs[c], i) * dinv;
+                    if (lane == i) xs[c] = xi;
+                    if (lane < i) rhs[c] = fmaf(-row[i], xi, rhs[c]);
+                }
+            }
+            if (lane < BMFR_FEATURES) {  // bmfr.cl:694-699
+                float* wout = P.weights + ((size_t)group * BMFR_FEATURES + lane) * 3;
+                wout[0] = xs[0];
+                wout[1] = xs[1];
+                wout[2] = xs[2];
+            }
+            __syncwarp();  // sh.fin / red / coef are reused by the next block
         }
-        const float inv = scale_factor(lo, hi);
-        sh.scale[tid] = lo;
-        sh.scale[NSC + tid] = inv;
-        P.mins_maxs[(size_t)group * 2 * NSC + 2 * tid] = lo;
-        P.mins_maxs[(size_t)group * 2 * NSC + 2 * tid + 1] = hi;
-        P.mins_inv[(size_t)group * 2 * NSC + 2 * tid] = lo;
-        P.mins_inv[(size_t)group * 2 * NSC + 2 * tid + 1] = inv;
-    }
-    __syncthreads();
-    float mn[NSC], inv[NSC];
-#pragma unroll
-    for (int f = 0; f < NSC; ++f) {
-        mn[f] = sh.scale[f];
-        inv[f] = sh.scale[NSC + f];
+        return;
     }
 
-    // scale (bmfr.cl:538-541), then the first-touch noise on columns 1..9 (bmfr.cl:623-627).  The
-    // reference adds a double (NOISE_AMOUNT is a double literal); the tile holds that double rounded
-    // to fp32, which changes a sum by at most one ulp in rare ties — below the fit's own rounding.
-#pragma unroll
-    for (int s = 0; s < ROWS; ++s) {
-#pragma unroll
-        for (int f = 0; f < NSC; ++f) a[s][NNS - 1 + f] = scale_feature(a[s][NNS - 1 + f], mn[f], inv[f]);
-#pragma unroll
-        for (int c = 1; c < BMFR_FEATURES; ++c)
-            a[s][c - 1] += __ldg(&P.noise_f[(c - 1) * BMFR_BLOCK_PIXELS + (warp * ROWS + s) * 32 + lane]);
-    }
+    // ---------------- compute warps ----------------
+    qr_prefetch<STRIP>(P, sh, first % P.blocks_x, P.by0 + first / P.blocks_x, tid);
+    for (int it = 0; it < iters; ++it) {
+        const int local = first + it * stride, slot = it % QR_SLOTS;
+        const int group = P.by0 * P.blocks_x + local;
 
-    // (ii) level 1 of the TSQR: this warp's 256 rows -> one 10x13 triangle in shared memory
-    QrLoop<ROWS, 0>::run(a, &sh.red[warp][0][0], sh.coef[warp], sh.tri[warp], lane);
-
-    // The last warp of the block to get here finishes the block; the others are done (their
-    // registers return to the SM while level 2 runs).
-    __threadfence_block();
-    __syncwarp();
-    int last = 0;
-    if (lane == 0) last = (atomicAdd(&sh.arrived, 1) == QR_WARPS - 1);
-    last = __shfl_sync(0xffffffffu, last, 0);
-    if (!last) return;
-    __threadfence_block();
-
-    // level 2: the 40 stacked rows (row (w,k) = S_kj / sqrt(S_kk) for j >= k, zero left of the
-    // diagonal), two per lane
-    constexpr int NS2 = 2;
-    float b[NS2][BMFR_BUFFER_COUNT];
+        // a[s][c-1] = column c of row (x_in = lane, y_in = 8 warp + s): the 12 non-constant K1 values
+        // (bmfr.cl:448-453), NaN -> 0 (bmfr.cl:468-469)
+        float a[ROWS][BMFR_BUFFER_COUNT - 1];
+        cp_async_wait_all();
 #pragma unroll
-    for (int s = 0; s < NS2; ++s) {
-        const int row = lane + 32 * s;
-        const bool live = row < QR_WARPS * BMFR_FEATURES;
-        const int k = row % BMFR_FEATURES;
-        const float* src = &sh.tri[0][0] + (live ? row : 0) * BMFR_BUFFER_COUNT;
-        const float scale = live ? rsqrt_approx(src[k]) : 0.f;
+        for (int s = 0; s < ROWS; ++s) {
+            float v[9];
 #pragma unroll
-        for (int c = 0; c < BMFR_BUFFER_COUNT; ++c) b[s][c] = (live && c >= k) ? src[c] * scale : 0.f;
-    }
-    QrLoopFull<NS2, 0>::run(b, &sh.red[warp][0][0], sh.coef[warp], sh.fin, lane);
-    __syncwarp();
-
-    // (iii) back-substitution, bmfr.cl:659-692.  Row i of R is S_ij / sqrt(S_ii); the square root
-    // cancels in R x = rhs, so the unnormalised rows are solved directly: sum_j S_ij x_j = S_i,rhs.
-    const int r = lane < BMFR_FEATURES ? lane : 0;
-    float row[BMFR_BUFFER_COUNT];
-#pragma unroll
-    for (int c = 0; c < BMFR_BUFFER_COUNT; ++c) row[c] = sh.fin[r * BMFR_BUFFER_COUNT + c];
-    float rhs[3] = {row[10], row[11], row[12]};
-    float xs[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-    for (int i = BMFR_FEATURES - 1; i >= 0; --i) {
-        const float dinv = rcp_approx(__shfl_sync(0xffffffffu, row[i], i));
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float xi = __shfl_sync(0xffffffffu, rhs[c], i) * dinv;
-            if (lane == i) xs[c] = xi;
-            if (lane < i) rhs[c] = fmaf(-row[i], xi, rhs[c]);
+            for (int c = 0; c < 9; ++c) v[c] = scrub_nan(sh.stage[s * 9 + c][tid]);
+            a[s][0] = v[0]; a[s][1] = v[1]; a[s][2] = v[2];
+            a[s][3] = v[3]; a[s][4] = v[4]; a[s][5] = v[5];
+            a[s][6] = v[3] * v[3]; a[s][7] = v[4] * v[4]; a[s][8] = v[5] * v[5];
+            a[s][9] = v[6]; a[s][10] = v[7]; a[s][11] = v[8];
         }
-    }
-    if (lane < BMFR_FEATURES) {  // bmfr.cl:694-699
-        float* wout = P.weights + ((size_t)group * BMFR_FEATURES + lane) * 3;
-        wout[0] = xs[0];
-        wout[1] = xs[1];
-        wout[2] = xs[2];
+        if (it + 1 < iters) {  // the slots were read by this thread only: refill them right away
+            const int nl = local + stride;
+            qr_prefetch<STRIP>(P, sh, nl % P.blocks_x, P.by0 + nl / P.blocks_x, tid);
+        }
+
+        // (i) block min / max of the six scaled features, bmfr.cl:511-535 (exact, so order-free)
+#pragma unroll
+        for (int f = 0; f < NSC; ++f) {
+            const int c = NNS - 1 + f;
+            float lo = a[0][c], hi = a[0][c];
+#pragma unroll
+            for (int s = 1; s < ROWS; ++s) {
+                lo = fminf(lo, a[s][c]);
+                hi = fmaxf(hi, a[s][c]);
+            }
+            const float wlo = warp_min(lo), whi = warp_max(hi);
+            if (lane == 0) {
+                sh.minmax[warp][2 * f] = wlo;
+                sh.minmax[warp][2 * f + 1] = whi;
+            }
+        }
+        compute_barrier();
+        if (tid < NSC) {  // one thread per scaled feature finishes the reduction and inverts the range once
+            float lo = sh.minmax[0][2 * tid], hi = sh.minmax[0][2 * tid + 1];
+#pragma unroll
+            for (int w = 1; w < QR_COMPUTE_WARPS; ++w) {
+                lo = fminf(lo, sh.minmax[w][2 * tid]);
+                hi = fmaxf(hi, sh.minmax[w][2 * tid + 1]);
+            }
+            const float inv = scale_factor(lo, hi);
+            sh.scale[2 * tid] = lo;
+            sh.scale[2 * tid + 1] = inv;
+            P.mins_maxs[(size_t)group * 2 * NSC + 2 * tid] = lo;
+            P.mins_maxs[(size_t)group * 2 * NSC + 2 * tid + 1] = hi;
+            P.mins_inv[(size_t)group * 2 * NSC + 2 * tid] = lo;
+            P.mins_inv[(size_t)group * 2 * NSC + 2 * tid + 1] = inv;
+        }
+        compute_barrier();
+        float mn[NSC], inv[NSC];
+#pragma unroll
+        for (int f = 0; f < NSC; f += 2) {
+            const float4 v = *reinterpret_cast<const float4*>(&sh.scale[2 * f]);
+            mn[f] = v.x; inv[f] = v.y; mn[f + 1] = v.z; inv[f + 1] = v.w;
+        }
+
+        // scale (bmfr.cl:538-541), then the first-touch noise on columns 1..9 (bmfr.cl:623-627).  The
+        // reference adds a double (NOISE_AMOUNT is a double literal); the tile holds that double
+        // rounded to fp32, which changes a sum by at most one ulp in rare ties — below the fit's own
+        // rounding.
+#pragma unroll
+        for (int s = 0; s < ROWS; ++s) {
+#pragma unroll
+            for (int f = 0; f < NSC; ++f) a[s][NNS - 1 + f] = scale_feature(a[s][NNS - 1 + f], mn[f], inv[f]);
+#pragma unroll
+            for (int c = 1; c < BMFR_FEATURES; ++c)
+                a[s][c - 1] += __ldg(&P.noise_f[(c - 1) * BMFR_BLOCK_PIXELS + (warp * ROWS + s) * 32 + lane]);
+        }
+
+        // (ii) level 1 of the TSQR: this warp's 256 rows -> one 10x13 triangle in the ring slot
+        if (it >= QR_SLOTS) mbar_wait(&sh.empty[slot], ((it / QR_SLOTS) - 1) & 1);
+        QrLoop<ROWS, 0>::run(a, &sh.red[warp][0][0], sh.coef[warp], sh.tri[slot][warp], lane);
+        mbar_arrive(&sh.full[slot]);
     }
 }
 
@@ -387,8 +466,26 @@ cudaError_t launch_reproject(const KParams& P, cudaStream_t st) {
     return cudaGetLastError();
 }
 cudaError_t launch_fit_qr(const KParams& P, cudaStream_t st) {
-    const dim3 grid(P.blocks_x, P.by1 - P.by0);
-    if (is_strip(P)) fit_qr_kernel<true><<<grid, QR_THREADS, 0, st>>>(P);
-    else fit_qr_kernel<false><<<grid, QR_THREADS, 0, st>>>(P);
+    // persistent grid: as many CTAs as stay resident (sm_count * BMFR_QR_MIN_BLOCKS), never more than blocks
+    static int sm_counts[64] = {};  // per device; 0 = this device has not been configured yet
+    const int smem = (int)sizeof(QrShared);
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    if (sm_counts[dev] == 0) {
+        int n = 0;
+        e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fit_qr_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fit_qr_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        sm_counts[dev] = n;
+    }
+    const int nblocks = P.blocks_x * (P.by1 - P.by0);
+    int grid = sm_counts[dev] * BMFR_QR_MIN_BLOCKS;
+    if (grid > nblocks) grid = nblocks;
+    if (grid < 1) return cudaSuccess;
+    if (is_strip(P)) fit_qr_kernel<true><<<grid, QR_THREADS, smem, st>>>(P);
+    else fit_qr_kernel<false><<<grid, QR_THREADS, smem, st>>>(P);
     return cudaGetLastError();
 }

@@ -2,7 +2,7 @@
 // (bmfr.cl:703-758, 761-857, 860-974) in one pass; `filtered` and `tone_mapped` never reach HBM.
 //
 // One CTA per 32x32 tile of the frame's shifted block grid, so the block's 42 fit coefficients are
-// CTA-uniform and sit in registers.  Thread (lane, warp) owns the column strip x = x0 + lane,
+// CTA-uniform: they sit in shared memory and are read as warp-wide broadcasts.  Thread (lane, warp) owns the column strip x = x0 + lane,
 // rows y0 + 4*warp .. +3: every global access of a warp is 32 consecutive pixels of one row (the
 // interleaved-RGB stride of 12 B keeps each 32-bit load on 3-4 cache lines), and the four 3x3 TAA
 // neighbourhoods of a strip share their row minima / maxima.
@@ -37,8 +37,11 @@ __device__ __forceinline__ float fast_rcp(float v) {
 
 __device__ __forceinline__ float tone_map_fast(float v) {  // clamp(powr(max(0,v), 0.454545f), 0, 1), bmfr.cl:852-856
     v = fmaxf(0.f, v);
-    v = exp2f(0.454545f * __log2f(v));
-    return __saturatef(v);
+    float l, e;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(v));  // 0 -> -inf -> ex2 -> 0, like powr(0, y > 0)
+    l *= 0.454545f;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(l));
+    return __saturatef(e);
 }
 
 // weighted_sum for one pixel, bmfr.cl:725-750.  cf: the block's coefficients in shared memory; every
@@ -72,13 +75,14 @@ __device__ __forceinline__ f3 weighted_sum_px(f3 n, f3 p, const float* __restric
 }
 
 // accumulate_filtered_data for one pixel, bmfr.cl:778-856.  Returns the tone-mapped colour.
+// accept / pp / spp / alb are this pixel's accept mask, previous-frame position, sample count and
+// albedo, fetched by the caller together with the features (one round of independent loads).
 template <bool STRIP>
-__device__ __forceinline__ f3 accumulate_filtered_px(const KParams& P, unsigned int lp, f3 filtered, bool store) {
+__device__ __forceinline__ f3 accumulate_filtered_px(const KParams& P, unsigned int lp, f3 filtered, unsigned int accept,
+                                                     float2 pp, unsigned int spp, f3 alb, bool store) {
     f3 prev = make_f3(0.f, 0.f, 0.f);
     float alpha = 1.f;
-    const unsigned int accept = __ldg(P.accept + lp);
     if (P.frame > 0 && accept != 0) {
-        const float2 pp = __ldg(P.prev_pixels + lp);
         const int pix = __float2int_rd(pp.x), piy = __float2int_rd(pp.y);
         const float frx = pp.x - (float)pix, fry = pp.y - (float)piy;
         const float omx = 1.f - frx, omy = 1.f - fry;
@@ -100,7 +104,7 @@ __device__ __forceinline__ f3 accumulate_filtered_px(const KParams& P, unsigned 
             }
         }
         if (total > 0.f) {
-            alpha = fmaxf(fast_rcp((float)P.cur_spp[lp]), P.second_blend_alpha);  // bmfr.cl:838-839
+            alpha = fmaxf(fast_rcp((float)spp), P.second_blend_alpha);  // bmfr.cl:838-839
             const float inv = fast_rcp(total);
             prev.x *= inv;
             prev.y *= inv;
@@ -111,7 +115,6 @@ __device__ __forceinline__ f3 accumulate_filtered_px(const KParams& P, unsigned 
     const f3 accum = make_f3(fmaf(alpha, filtered.x, oma * prev.x), fmaf(alpha, filtered.y, oma * prev.y),
                              fmaf(alpha, filtered.z, oma * prev.z));
     if (store) store_f3(P.accum_cur, lp, accum);
-    const f3 alb = load_f3(P.albedo, lp);
     return make_f3(tone_map_fast(alb.x * accum.x), tone_map_fast(alb.y * accum.y), tone_map_fast(alb.z * accum.z));
 }
 
@@ -145,8 +148,12 @@ template <bool STRIP>
 __device__ __forceinline__ void phase_a_pixel(PostShared& sh, const KParams& P, const float* cf, int hx, int hy, int x, int y,
                                               bool store) {
     const unsigned int lp = pix_index(P, x, y);
-    const f3 filtered = weighted_sum_px(load_f3(P.cur_normals, lp), load_f3(P.cur_positions, lp), cf);
-    const f3 tone = accumulate_filtered_px<STRIP>(P, lp, filtered, store);
+    const f3 n = load_f3(P.cur_normals, lp), p = load_f3(P.cur_positions, lp), alb = load_f3(P.albedo, lp);
+    const unsigned int accept = __ldg(P.accept + lp);
+    const unsigned int spp = __ldg(const_cast<const unsigned char*>(P.cur_spp) + lp);
+    const float2 pp = __ldg(P.prev_pixels + lp);
+    const f3 filtered = weighted_sum_px(n, p, cf);
+    const f3 tone = accumulate_filtered_px<STRIP>(P, lp, filtered, accept, pp, spp, alb, store);
     put_ycc(sh, P, hx, hy, x, y, to_ycocg(tone));
 }
 
@@ -162,14 +169,14 @@ __global__ void __launch_bounds__(256, BMFR_POST_MIN_BLOCKS) post_kernel(const _
     const int x0 = bx * 32 - 16 + P.off_x, y0 = by * 32 - 16 + P.off_y;  // tile origin in image coordinates
     constexpr int NW = BMFR_FEATURES * 3, NM = BMFR_FEATURES_SCALED * 2;
 
-    // coefficients of the 3x3 block neighbourhood -> shared memory
-    for (int i = tid; i < 9 * (NW + NM); i += 256) {
-        const int nb = i / (NW + NM), k = i % (NW + NM);
+    // coefficients of the 3x3 block neighbourhood -> shared memory: warp w takes neighbour w (warp 0
+    // also the ninth), lanes 0..29 the weights, lanes 0..11 the (min, 1/range) pairs
+    for (int nb = warp; nb < 9; nb += 8) {
         const int gx = bx + nb % 3 - 1, gy = by + nb / 3 - 1;
         if (gx < 0 || gx >= P.blocks_x || gy < 0 || gy >= P.blocks_y) continue;
         const size_t g = (size_t)gy * P.blocks_x + gx;
-        if (k < NW) sh.coef[nb][(k / 3) * 4 + k % 3] = __ldg(P.weights + g * NW + k);
-        else sh.coef[nb][40 + k - NW] = __ldg(P.mins_inv + g * NM + k - NW);
+        if (lane < NW) sh.coef[nb][(lane / 3) * 4 + lane % 3] = __ldg(P.weights + g * NW + lane);
+        if (lane < NM) sh.coef[nb][40 + lane] = __ldg(P.mins_inv + g * NM + lane);
     }
     __syncthreads();
 
