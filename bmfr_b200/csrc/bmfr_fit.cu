@@ -115,6 +115,53 @@ __device__ __forceinline__ void warp_broadcast(float c, float* __restrict__ coef
     // store to `coefbuf` comes after the __syncwarp of its own warp_column_sums
 }
 
+#ifndef BMFR_QR_SMEM_REDUCE
+#define BMFR_QR_SMEM_REDUCE 0
+#endif
+
+// Sum over the 32 lanes of N (<= 16) per-lane values with the result of every column in every lane,
+// using shuffles only.  Stage `bit` (16, 8, 4, 2, 1) folds lane bit `bit`: while a lane still carries
+// more than one value the stage is a reduce-scatter step (the lane keeps one half of its values, sends
+// the other half to its partner and adds what it receives), afterwards a plain butterfly step.  One
+// indexed shuffle per column then broadcasts the totals.  16+N shuffles for N > 8 (9+N, 6+N for the
+// narrow reflectors) instead of 5N for a butterfly on every value — and no shared-memory round trip
+// and no warp barrier on the critical path of a reflector.
+//   own : the total of the column this lane ended up holding, column index lane / (32 / W0).
+template <int N>
+struct AllSum {
+    static constexpr int W0 = (N > 8) ? 16 : (N > 4) ? 8 : 4;
+    static constexpr int LANES_PER_COLUMN = 32 / W0;
+};
+template <int N>
+__device__ __forceinline__ void warp_allsum(float (&v)[16], int lane, float& own) {
+    constexpr int W0 = AllSum<N>::W0;
+    float w[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) w[i] = (i < N) ? v[i] : 0.f;
+    int width = W0;
+#pragma unroll
+    for (int bit = 16; bit >= 1; bit >>= 1) {
+        if (width > 1) {
+            const int half = width / 2;
+            const bool hi = (lane & bit) != 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (i < half) {
+                    const float send = hi ? w[i] : w[i + half];
+                    const float keep = hi ? w[i + half] : w[i];
+                    w[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+                }
+            }
+            width = half;
+        } else {
+            w[0] += __shfl_xor_sync(0xffffffffu, w[0], bit);
+        }
+    }
+    own = w[0];
+#pragma unroll
+    for (int j = 0; j < N; ++j) v[j] = __shfl_sync(0xffffffffu, w[0], j * AllSum<N>::LANES_PER_COLUMN);
+}
+
 // One reflector against a virtual zero pivot row (see bmfr_device.cuh "The fit"): with S_j = a_k.a_j,
 //   R_kj = S_j / sqrt(S_k),   a_j -= a_k * S_j / S_k   (j > k).
 // `a` holds columns 1..12 (column 0 is the constant 1 and lives in no register); srow receives
@@ -142,12 +189,24 @@ __device__ __forceinline__ void qr_step(float (&a)[ROWS][BMFR_BUFFER_COUNT - 1],
             part[j] = acc;
         }
     }
+    float cj[16];
+#if BMFR_QR_SMEM_REDUCE
     float sk;
     const float t = warp_column_sums<N>(part, red, lane, sk);
     if (lane < N) srow[K + lane] = t;
     const float c = t * rcp_approx(sk);  // 2 * dot / u_length_squared of bmfr.cl:650
-    float cj[16];
     warp_broadcast<N>(c, coefbuf, lane, cj);
+#else
+    float own;
+#pragma unroll
+    for (int j = 0; j < N; ++j) cj[j] = part[j];
+    warp_allsum<N>(cj, lane, own);
+    constexpr int LPC = AllSum<N>::LANES_PER_COLUMN;
+    if (lane % LPC == 0 && lane / LPC < N) srow[K + lane / LPC] = own;
+    const float rk = rcp_approx(cj[0]);  // 1 / S_k
+#pragma unroll
+    for (int j = 1; j < N; ++j) cj[j] *= rk;  // 2 * dot / u_length_squared of bmfr.cl:650
+#endif
 #pragma unroll
     for (int j = 1; j < N; ++j) {
 #pragma unroll
@@ -186,12 +245,24 @@ __device__ __forceinline__ void qr_step_full(float (&b)[ROWS][BMFR_BUFFER_COUNT]
         for (int s = 1; s < ROWS; ++s) acc = fmaf(b[s][K], b[s][K + j], acc);
         part[j] = acc;
     }
+    float cj[16];
+#if BMFR_QR_SMEM_REDUCE
     float sk;
     const float t = warp_column_sums<N>(part, red, lane, sk);
     if (lane < N) srow[K + lane] = t;
     const float c = t * rcp_approx(sk);
-    float cj[16];
     warp_broadcast<N>(c, coefbuf, lane, cj);
+#else
+    float own;
+#pragma unroll
+    for (int j = 0; j < N; ++j) cj[j] = part[j];
+    warp_allsum<N>(cj, lane, own);
+    constexpr int LPC = AllSum<N>::LANES_PER_COLUMN;
+    if (lane % LPC == 0 && lane / LPC < N) srow[K + lane / LPC] = own;
+    const float rk = rcp_approx(cj[0]);
+#pragma unroll
+    for (int j = 1; j < N; ++j) cj[j] *= rk;
+#endif
 #pragma unroll
     for (int j = 1; j < N; ++j)
 #pragma unroll
@@ -249,15 +320,33 @@ __device__ __forceinline__ void mbar_init(unsigned long long* b, int count) {
 __device__ __forceinline__ void mbar_arrive(unsigned long long* b) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned int parity) {
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* b, unsigned int parity) {
+    unsigned int ok;
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(b)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Waiting warps back off with nanosleep so that they do not take issue slots from the working warps
+// of their sub-partition.
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned int parity) {
+    // the whole poll-and-back-off loop stays inside one asm block, so the compiler sees straight-line
+    // code and keeps treating the warp as converged for the shuffles that follow
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MBAR_WAIT_LOOP:\n"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
+        "@p bra MBAR_WAIT_DONE;\n"
+        "nanosleep.u32 64;\n"
+        "bra MBAR_WAIT_LOOP;\n"
+        "MBAR_WAIT_DONE:\n"
         "}\n" ::"r"(smem_u32(b)), "r"(parity)
         : "memory");
 }
@@ -296,6 +385,21 @@ __device__ __forceinline__ void qr_prefetch(const KParams& P, QrShared& sh, int 
 #define BMFR_QR_MIN_BLOCKS 3
 #endif
 
+// Optional phase timers (-DBMFR_QR_TIMING, tuning builds only): clock64 stamps of CTA 0's first
+// compute thread and solver lane, read back with bmfr_debug_qr_timing().
+#ifdef BMFR_QR_TIMING
+__device__ long long g_qr_timing[512];
+#define QR_STAMP(base, it, k)                                                              \
+    do {                                                                                   \
+        if (blockIdx.x == 0 && lane == 0 && (it) < 8) g_qr_timing[(base) + (it) * 8 + (k)] = clock64(); \
+    } while (0)
+extern "C" int bmfr_debug_qr_timing(long long* out, int n) {
+    return (int)cudaMemcpyFromSymbol(out, g_qr_timing, sizeof(long long) * (n < 512 ? n : 512));
+}
+#else
+#define QR_STAMP(base, it, k) do { } while (0)
+#endif
+
 template <bool STRIP>
 __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(const __grid_constant__ KParams P) {
     extern __shared__ __align__(16) unsigned char qr_smem[];
@@ -322,7 +426,9 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
         for (int it = 0; it < iters; ++it) {
             const int local = first + it * stride, slot = it % QR_SLOTS;
             const int group = P.by0 * P.blocks_x + local;
+            QR_STAMP(256, it, 0);
             mbar_wait(&sh.full[slot], (it / QR_SLOTS) & 1);
+            QR_STAMP(256, it, 1);
             // level 2: the 40 stacked rows (row (w,k) = S_kj / sqrt(S_kk) for j >= k, zero left of the
             // diagonal), two per lane
             constexpr int NS2 = 2;
@@ -365,6 +471,7 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
                 wout[2] = xs[2];
             }
             __syncwarp();  // sh.fin / red / coef are reused by the next block
+            QR_STAMP(256, it, 2);
         }
         return;
     }
@@ -378,6 +485,7 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
         // a[s][c-1] = column c of row (x_in = lane, y_in = 8 warp + s): the 12 non-constant K1 values
         // (bmfr.cl:448-453), NaN -> 0 (bmfr.cl:468-469)
         float a[ROWS][BMFR_BUFFER_COUNT - 1];
+        if (warp == 0) QR_STAMP(0, it, 0);
         cp_async_wait_all();
 #pragma unroll
         for (int s = 0; s < ROWS; ++s) {
@@ -389,11 +497,13 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
             a[s][6] = v[3] * v[3]; a[s][7] = v[4] * v[4]; a[s][8] = v[5] * v[5];
             a[s][9] = v[6]; a[s][10] = v[7]; a[s][11] = v[8];
         }
+        if (warp == 0) QR_STAMP(0, it, 1);
         if (it + 1 < iters) {  // the slots were read by this thread only: refill them right away
             const int nl = local + stride;
             qr_prefetch<STRIP>(P, sh, nl % P.blocks_x, P.by0 + nl / P.blocks_x, tid);
         }
 
+        if (warp == 0) QR_STAMP(0, it, 2);
         // (i) block min / max of the six scaled features, bmfr.cl:511-535 (exact, so order-free)
 #pragma unroll
         for (int f = 0; f < NSC; ++f) {
@@ -427,6 +537,7 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
             P.mins_inv[(size_t)group * 2 * NSC + 2 * tid + 1] = inv;
         }
         compute_barrier();
+        if (warp == 0) QR_STAMP(0, it, 3);
         float mn[NSC], inv[NSC];
 #pragma unroll
         for (int f = 0; f < NSC; f += 2) {
@@ -448,9 +559,12 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
         }
 
         // (ii) level 1 of the TSQR: this warp's 256 rows -> one 10x13 triangle in the ring slot
+        if (warp == 0) QR_STAMP(0, it, 4);
         if (it >= QR_SLOTS) mbar_wait(&sh.empty[slot], ((it / QR_SLOTS) - 1) & 1);
+        if (warp == 0) QR_STAMP(0, it, 5);
         QrLoop<ROWS, 0>::run(a, &sh.red[warp][0][0], sh.coef[warp], sh.tri[slot][warp], lane);
         mbar_arrive(&sh.full[slot]);
+        if (warp == 0) QR_STAMP(0, it, 6);
     }
 }
 

@@ -1,0 +1,48 @@
+#!/usr/bin/env python
+"""Phase timers of fit_qr_kernel (tuning build with -DBMFR_QR_TIMING): runs a few 1080p frames and prints
+the clock64 deltas of CTA 0's first compute thread and of its solver lane, per block iteration."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bmfr_b200 import Denoiser, _lib, synth  # noqa: E402
+
+w, h, frames = 1920, 1080, 6
+stream = torch.cuda.Stream()
+torch.cuda.set_stream(stream)
+inputs = torch.empty((frames, 4, h, w, 3), dtype=torch.float32, device="cuda")
+for f in range(frames):
+    synth.frame_device(w, h, f, [inputs[f, k].data_ptr() for k in range(4)], stream=stream.cuda_stream)
+out = torch.empty((h, w, 3), dtype=torch.float32, device="cuda")
+d = Denoiser(w, h, mode="fused", stream=stream.cuda_stream)
+for f in range(frames):
+    cam = synth.camera(max(f - 1, 0), w, h)[0]
+    off = synth.camera(f, w, h)[1]
+    d.denoise_frame(f, *[inputs[f, k].data_ptr() for k in range(4)], cam, off, out.data_ptr())
+d.sync()
+lib = _lib.load()
+buf = (C.c_longlong * 512)()
+fn = lib.bmfr_debug_qr_timing
+fn.restype, fn.argtypes = C.c_int, [C.POINTER(C.c_longlong), C.c_int]
+assert fn(buf, 512) == 0
+t = np.array(buf[:], dtype=np.int64)
+comp = t[:64].reshape(8, 8)
+solv = t[256:320].reshape(8, 8)
+t0 = comp[0, 0]
+names = ["cp.wait+lds", "prefetch issue", "minmax+barriers", "scale+noise", "wait empty", "level-1 QR"]
+print("compute warp 0 of CTA 0 (cycles):")
+for it in range(8):
+    if comp[it, 0] == 0:
+        break
+    deltas = np.diff(comp[it, :7])
+    print(f"  block {it}: start +{comp[it, 0] - t0:7d}  " + "  ".join(f"{n} {v}" for n, v in zip(names, deltas)) + f"  total {comp[it, 6] - comp[it, 0]}")
+print("solver warp of CTA 0 (cycles):")
+for it in range(8):
+    if solv[it, 0] == 0:
+        break
+    print(f"  block {it}: start +{solv[it, 0] - t0:7d}  wait full {solv[it, 1] - solv[it, 0]}  level-2 + solve {solv[it, 2] - solv[it, 1]}")
+d.close()
