@@ -15,6 +15,11 @@
 // Compiled with --fmad=false (K1 is bit-exact against the oracle); the fit writes fmaf() explicitly.
 #include "bmfr_kernels.h"
 
+#include <cuda.h>  // CUtensorMap (the encoder is fetched through cudaGetDriverEntryPoint, no libcuda link)
+
+#include <mutex>
+#include <unordered_map>
+
 #include "bmfr_device.cuh"
 
 // --------------------------------------------------------------------------------------------
@@ -300,17 +305,26 @@ struct QrLoopFull<ROWS, BMFR_FEATURES> {
 #define QR_ROWS 8
 #define QR_TRI (BMFR_FEATURES * BMFR_BUFFER_COUNT)  // floats of one level-1 triangle, stored as a full 10x13
 #define QR_SLOTS 2
-#define QR_INPUTS (QR_ROWS * 9)                     // floats a compute thread needs per block
+#define QR_TILE_FLOATS (32 * 96)                    // one 32x32 tile of an interleaved-RGB image
+#define QR_TILE_BYTES (QR_TILE_FLOATS * 4)
 
 struct QrShared {
-    float stage[QR_INPUTS][QR_COMPUTE_THREADS];  // cp.async landing zone, [value][thread]: conflict-free both ways
+    float stage[3][32][96];                      // TMA landing zone: normals, positions, accumulated colour of the next block
+#if BMFR_QR_SMEM_REDUCE
     float red[QR_COMPUTE_WARPS + 1][BMFR_BUFFER_COUNT][QR_RED_STRIDE];
     float coef[QR_COMPUTE_WARPS + 1][16];
-    float minmax[QR_COMPUTE_WARPS][2 * BMFR_FEATURES_SCALED];
-    float scale[2 * BMFR_FEATURES_SCALED + 4];   // block min, 1/range
+#endif
+    float minmax[2][QR_COMPUTE_WARPS][2 * BMFR_FEATURES_SCALED];  // double-buffered by block parity
     float tri[QR_SLOTS][QR_COMPUTE_WARPS][QR_TRI];  // level-1 triangles (unnormalised rows S_kj)
     float fin[QR_TRI];                           // level-2 triangle
-    unsigned long long full[QR_SLOTS], empty[QR_SLOTS];
+    unsigned long long full[QR_SLOTS], empty[QR_SLOTS], data_full;
+};
+
+// The three tensor maps of a frame (2-D tensors [rows][W*3] of floats, box 96 x 32) and whether the
+// TMA path can be used at all (W % 4 == 0, 16-byte aligned bases, driver entry point found).
+struct QrMaps {
+    CUtensorMap normals, positions, colour;
+    int use_tma;
 };
 
 __device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
@@ -351,34 +365,30 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned int pa
         : "memory");
 }
 __device__ __forceinline__ void compute_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(QR_COMPUTE_THREADS) : "memory"); }
-__device__ __forceinline__ void cp_async4(float* dst_smem, const float* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, unsigned int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_tile(float* dst_smem, const CUtensorMap* map, int c0, int c1, unsigned long long* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
 
-// Issues the asynchronous copies of this compute thread's inputs of block (bx, by): normals,
-// positions and accumulated colour of its eight (mirrored, bmfr.cl:314-316) pixels.
-template <bool STRIP>
-__device__ __forceinline__ void qr_prefetch(const KParams& P, QrShared& sh, int bx, int by, int tid) {
-    const int lane = tid & 31, warp = tid >> 5;
-    const int x = mirror_index(bx * 32 + lane - 16 + P.off_x, P.W);
-#pragma unroll
-    for (int s = 0; s < QR_ROWS; ++s) {
-        const int y = mirror_index(by * 32 + warp * QR_ROWS + s - 16 + P.off_y, P.H);
-        if (STRIP && (y < P.row0 || y >= P.row1)) {
-            *P.oob_flag = 1;
-#pragma unroll
-            for (int c = 0; c < 9; ++c) sh.stage[s * 9 + c][tid] = 0.f;
-            continue;
-        }
-        const size_t o = (size_t)(pix_index(P, x, y) * 3u);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            cp_async4(&sh.stage[s * 9 + c][tid], P.cur_normals + o + c);
-            cp_async4(&sh.stage[s * 9 + 3 + c][tid], P.cur_positions + o + c);
-            cp_async4(&sh.stage[s * 9 + 6 + c][tid], P.cur_noisy_acc + o + c);
-        }
-    }
+// A block whose 32x32 pixels all lie inside the rows this context holds needs no mirroring
+// (bmfr.cl:314-316) and is fetched as three TMA tiles; the others are loaded pixel by pixel.
+__device__ __forceinline__ bool qr_block_is_interior(const KParams& P, int bx, int by) {
+    const int x0 = bx * 32 - 16 + P.off_x, y0 = by * 32 - 16 + P.off_y;
+    return x0 >= 0 && x0 + 32 <= P.W && y0 >= P.row0 && y0 + 32 <= P.row1;
+}
+// One thread: arm the barrier and start the three tile loads of block (bx, by).
+__device__ __forceinline__ void qr_prefetch(const KParams& P, const QrMaps& M, QrShared& sh, int bx, int by) {
+    const int c0 = (bx * 32 - 16 + P.off_x) * 3, c1 = by * 32 - 16 + P.off_y - P.row0;
+    mbar_expect_tx(&sh.data_full, 3 * QR_TILE_BYTES);
+    tma_load_tile(&sh.stage[0][0][0], &M.normals, c0, c1, &sh.data_full);
+    tma_load_tile(&sh.stage[1][0][0], &M.positions, c0, c1, &sh.data_full);
+    tma_load_tile(&sh.stage[2][0][0], &M.colour, c0, c1, &sh.data_full);
 }
 
 #ifndef BMFR_QR_MIN_BLOCKS
@@ -401,9 +411,10 @@ extern "C" int bmfr_debug_qr_timing(long long* out, int n) {
 #endif
 
 template <bool STRIP>
-__global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(const __grid_constant__ KParams P) {
-    extern __shared__ __align__(16) unsigned char qr_smem[];
-    QrShared& sh = *reinterpret_cast<QrShared*>(qr_smem);
+__global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(const __grid_constant__ KParams P,
+                                                                                const __grid_constant__ QrMaps M) {
+    extern __shared__ __align__(128) unsigned char qr_smem[];
+    QrShared& sh = *reinterpret_cast<QrShared*>((reinterpret_cast<uintptr_t>(qr_smem) + 127) & ~(uintptr_t)127);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NSC = BMFR_FEATURES_SCALED, NNS = BMFR_FEATURES_NOT_SCALED, ROWS = QR_ROWS;
     const int nblocks = P.blocks_x * (P.by1 - P.by0);
@@ -417,6 +428,7 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
             mbar_init(&sh.full[i], QR_COMPUTE_THREADS);
             mbar_init(&sh.empty[i], 32);
         }
+        mbar_init(&sh.data_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -444,7 +456,11 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
                 for (int c = 0; c < BMFR_BUFFER_COUNT; ++c) b[s][c] = (live && c >= k) ? src[c] * scale : 0.f;
             }
             mbar_arrive(&sh.empty[slot]);  // the triangles are in registers: the slot may be refilled
+#if BMFR_QR_SMEM_REDUCE
             QrLoopFull<NS2, 0>::run(b, &sh.red[QR_COMPUTE_WARPS][0][0], sh.coef[QR_COMPUTE_WARPS], sh.fin, lane);
+#else
+            QrLoopFull<NS2, 0>::run(b, nullptr, nullptr, sh.fin, lane);
+#endif
             __syncwarp();
             // (iii) back-substitution, bmfr.cl:659-692.  Row i of R is S_ij / sqrt(S_ii); the square
             // root cancels in R x = rhs, so the unnormalised rows are solved directly.
@@ -477,33 +493,57 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
     }
 
     // ---------------- compute warps ----------------
-    qr_prefetch<STRIP>(P, sh, first % P.blocks_x, P.by0 + first / P.blocks_x, tid);
+    unsigned int tma_parity = 0;
+    {
+        const int bx0 = first % P.blocks_x, by0 = P.by0 + first / P.blocks_x;
+        if (tid == 0 && M.use_tma && qr_block_is_interior(P, bx0, by0)) qr_prefetch(P, M, sh, bx0, by0);
+    }
     for (int it = 0; it < iters; ++it) {
         const int local = first + it * stride, slot = it % QR_SLOTS;
         const int group = P.by0 * P.blocks_x + local;
+        const int bx = local % P.blocks_x, by = P.by0 + local / P.blocks_x;
 
         // a[s][c-1] = column c of row (x_in = lane, y_in = 8 warp + s): the 12 non-constant K1 values
         // (bmfr.cl:448-453), NaN -> 0 (bmfr.cl:468-469)
         float a[ROWS][BMFR_BUFFER_COUNT - 1];
         if (warp == 0) QR_STAMP(0, it, 0);
-        cp_async_wait_all();
+        if (M.use_tma && qr_block_is_interior(P, bx, by)) {
+            mbar_wait(&sh.data_full, tma_parity);
+            tma_parity ^= 1;
 #pragma unroll
-        for (int s = 0; s < ROWS; ++s) {
-            float v[9];
+            for (int s = 0; s < ROWS; ++s) {
+                float v[9];
 #pragma unroll
-            for (int c = 0; c < 9; ++c) v[c] = scrub_nan(sh.stage[s * 9 + c][tid]);
-            a[s][0] = v[0]; a[s][1] = v[1]; a[s][2] = v[2];
-            a[s][3] = v[3]; a[s][4] = v[4]; a[s][5] = v[5];
-            a[s][6] = v[3] * v[3]; a[s][7] = v[4] * v[4]; a[s][8] = v[5] * v[5];
-            a[s][9] = v[6]; a[s][10] = v[7]; a[s][11] = v[8];
+                for (int c = 0; c < 9; ++c) v[c] = scrub_nan(sh.stage[c / 3][warp * ROWS + s][lane * 3 + c % 3]);
+                a[s][0] = v[0]; a[s][1] = v[1]; a[s][2] = v[2];
+                a[s][3] = v[3]; a[s][4] = v[4]; a[s][5] = v[5];
+                a[s][6] = v[3] * v[3]; a[s][7] = v[4] * v[4]; a[s][8] = v[5] * v[5];
+                a[s][9] = v[6]; a[s][10] = v[7]; a[s][11] = v[8];
+            }
+        } else {  // border block: mirrored pixel by pixel
+            const int x = mirror_index(bx * 32 + lane - 16 + P.off_x, P.W);
+#pragma unroll
+            for (int s = 0; s < ROWS; ++s) {
+                const int y = mirror_index(by * 32 + warp * ROWS + s - 16 + P.off_y, P.H);
+                if (STRIP && (y < P.row0 || y >= P.row1)) {
+                    *P.oob_flag = 1;
+#pragma unroll
+                    for (int c = 0; c < BMFR_BUFFER_COUNT - 1; ++c) a[s][c] = 0.f;
+                    continue;
+                }
+                const unsigned int lp = pix_index(P, x, y);
+                const f3 n = load_f3(P.cur_normals, lp);
+                const f3 p = load_f3(P.cur_positions, lp);
+                const f3 col = load_f3(P.cur_noisy_acc, lp);
+                const float px = scrub_nan(p.x), py = scrub_nan(p.y), pz = scrub_nan(p.z);
+                a[s][0] = scrub_nan(n.x); a[s][1] = scrub_nan(n.y); a[s][2] = scrub_nan(n.z);
+                a[s][3] = px; a[s][4] = py; a[s][5] = pz;
+                a[s][6] = px * px; a[s][7] = py * py; a[s][8] = pz * pz;
+                a[s][9] = scrub_nan(col.x); a[s][10] = scrub_nan(col.y); a[s][11] = scrub_nan(col.z);
+            }
         }
         if (warp == 0) QR_STAMP(0, it, 1);
-        if (it + 1 < iters) {  // the slots were read by this thread only: refill them right away
-            const int nl = local + stride;
-            qr_prefetch<STRIP>(P, sh, nl % P.blocks_x, P.by0 + nl / P.blocks_x, tid);
-        }
 
-        if (warp == 0) QR_STAMP(0, it, 2);
         // (i) block min / max of the six scaled features, bmfr.cl:511-535 (exact, so order-free)
 #pragma unroll
         for (int f = 0; f < NSC; ++f) {
@@ -516,34 +556,42 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
             }
             const float wlo = warp_min(lo), whi = warp_max(hi);
             if (lane == 0) {
-                sh.minmax[warp][2 * f] = wlo;
-                sh.minmax[warp][2 * f + 1] = whi;
+                sh.minmax[it & 1][warp][2 * f] = wlo;
+                sh.minmax[it & 1][warp][2 * f + 1] = whi;
             }
         }
-        compute_barrier();
-        if (tid < NSC) {  // one thread per scaled feature finishes the reduction and inverts the range once
-            float lo = sh.minmax[0][2 * tid], hi = sh.minmax[0][2 * tid + 1];
+        if (warp == 0) QR_STAMP(0, it, 2);
+        compute_barrier();  // the per-warp extrema are visible, and every thread is done with the stage
+        if (tid == 0 && it + 1 < iters && M.use_tma) {
+            const int nl = local + stride;
+            const int nbx = nl % P.blocks_x, nby = P.by0 + nl / P.blocks_x;
+            if (qr_block_is_interior(P, nbx, nby)) qr_prefetch(P, M, sh, nbx, nby);
+        }
+        // every warp finishes the reduction itself (lane f < 6 owns feature f) and shares the result
+        // by shuffle: one block-wide barrier per block instead of two
+        float mn[NSC], inv[NSC];
+        {
+            const int f = lane < NSC ? lane : 0;
+            float lo = sh.minmax[it & 1][0][2 * f], hi = sh.minmax[it & 1][0][2 * f + 1];
 #pragma unroll
             for (int w = 1; w < QR_COMPUTE_WARPS; ++w) {
-                lo = fminf(lo, sh.minmax[w][2 * tid]);
-                hi = fmaxf(hi, sh.minmax[w][2 * tid + 1]);
+                lo = fminf(lo, sh.minmax[it & 1][w][2 * f]);
+                hi = fmaxf(hi, sh.minmax[it & 1][w][2 * f + 1]);
             }
-            const float inv = scale_factor(lo, hi);
-            sh.scale[2 * tid] = lo;
-            sh.scale[2 * tid + 1] = inv;
-            P.mins_maxs[(size_t)group * 2 * NSC + 2 * tid] = lo;
-            P.mins_maxs[(size_t)group * 2 * NSC + 2 * tid + 1] = hi;
-            P.mins_inv[(size_t)group * 2 * NSC + 2 * tid] = lo;
-            P.mins_inv[(size_t)group * 2 * NSC + 2 * tid + 1] = inv;
-        }
-        compute_barrier();
-        if (warp == 0) QR_STAMP(0, it, 3);
-        float mn[NSC], inv[NSC];
+            const float iv = scale_factor(lo, hi);
+            if (warp == 0 && lane < NSC) {
+                P.mins_maxs[(size_t)group * 2 * NSC + 2 * lane] = lo;
+                P.mins_maxs[(size_t)group * 2 * NSC + 2 * lane + 1] = hi;
+                P.mins_inv[(size_t)group * 2 * NSC + 2 * lane] = lo;
+                P.mins_inv[(size_t)group * 2 * NSC + 2 * lane + 1] = iv;
+            }
 #pragma unroll
-        for (int f = 0; f < NSC; f += 2) {
-            const float4 v = *reinterpret_cast<const float4*>(&sh.scale[2 * f]);
-            mn[f] = v.x; inv[f] = v.y; mn[f + 1] = v.z; inv[f + 1] = v.w;
+            for (int k = 0; k < NSC; ++k) {
+                mn[k] = __shfl_sync(0xffffffffu, lo, k);
+                inv[k] = __shfl_sync(0xffffffffu, iv, k);
+            }
         }
+        if (warp == 0) QR_STAMP(0, it, 3);
 
         // scale (bmfr.cl:538-541), then the first-touch noise on columns 1..9 (bmfr.cl:623-627).  The
         // reference adds a double (NOISE_AMOUNT is a double literal); the tile holds that double
@@ -562,7 +610,11 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
         if (warp == 0) QR_STAMP(0, it, 4);
         if (it >= QR_SLOTS) mbar_wait(&sh.empty[slot], ((it / QR_SLOTS) - 1) & 1);
         if (warp == 0) QR_STAMP(0, it, 5);
+#if BMFR_QR_SMEM_REDUCE
         QrLoop<ROWS, 0>::run(a, &sh.red[warp][0][0], sh.coef[warp], sh.tri[slot][warp], lane);
+#else
+        QrLoop<ROWS, 0>::run(a, nullptr, nullptr, sh.tri[slot][warp], lane);
+#endif
         mbar_arrive(&sh.full[slot]);
         if (warp == 0) QR_STAMP(0, it, 6);
     }
@@ -579,10 +631,63 @@ cudaError_t launch_reproject(const KParams& P, cudaStream_t st) {
     else reproject_kernel<false><<<grid, block, 0, st>>>(P);
     return cudaGetLastError();
 }
+// ---- tensor maps of a frame --------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// [rows][W*3] floats, box = one 32x32-pixel tile.  Maps are cached by (pointer, W, rows): a caller
+// that cycles through a fixed set of frame buffers encodes each of them once.
+static bool tile_map(const float* base, int W, int rows, CUtensorMap* out) {
+    struct Key {
+        const void* p; int w, r;
+        bool operator==(const Key& o) const { return p == o.p && w == o.w && r == o.r; }
+    };
+    struct Hash {
+        size_t operator()(const Key& k) const { return std::hash<const void*>()(k.p) ^ ((size_t)k.w * 1315423911u) ^ ((size_t)k.r << 20); }
+    };
+    static std::unordered_map<Key, CUtensorMap, Hash> cache;
+    static std::mutex mu;
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc || (W & 3) != 0 || ((uintptr_t)base & 15) != 0 || rows < 32) return false;
+    std::lock_guard<std::mutex> lock(mu);
+    const Key key{base, W, rows};
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+        *out = it->second;
+        return true;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)W * 3, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)W * 3 * sizeof(float)};
+    const cuuint32_t box[2] = {96, 32}, elem[2] = {1, 1};
+    CUtensorMap m;
+    if (enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return false;
+    if (cache.size() > 4096) cache.clear();
+    cache.emplace(key, m);
+    *out = m;
+    return true;
+}
+
 cudaError_t launch_fit_qr(const KParams& P, cudaStream_t st) {
     // persistent grid: as many CTAs as stay resident (sm_count * BMFR_QR_MIN_BLOCKS), never more than blocks
     static int sm_counts[64] = {};  // per device; 0 = this device has not been configured yet
-    const int smem = (int)sizeof(QrShared);
+    const int smem = (int)sizeof(QrShared) + 128;
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
@@ -599,7 +704,12 @@ cudaError_t launch_fit_qr(const KParams& P, cudaStream_t st) {
     int grid = sm_counts[dev] * BMFR_QR_MIN_BLOCKS;
     if (grid > nblocks) grid = nblocks;
     if (grid < 1) return cudaSuccess;
-    if (is_strip(P)) fit_qr_kernel<true><<<grid, QR_THREADS, smem, st>>>(P);
-    else fit_qr_kernel<false><<<grid, QR_THREADS, smem, st>>>(P);
+    QrMaps M;
+    memset(&M, 0, sizeof(M));
+    const int rows = P.row1 - P.row0;
+    M.use_tma = tile_map(P.cur_normals, P.W, rows, &M.normals) && tile_map(P.cur_positions, P.W, rows, &M.positions) &&
+                tile_map(P.cur_noisy_acc, P.W, rows, &M.colour);
+    if (is_strip(P)) fit_qr_kernel<true><<<grid, QR_THREADS, smem, st>>>(P, M);
+    else fit_qr_kernel<false><<<grid, QR_THREADS, smem, st>>>(P, M);
     return cudaGetLastError();
 }
