@@ -305,11 +305,16 @@ struct QrLoopFull<ROWS, BMFR_FEATURES> {
 #define QR_ROWS 8
 #define QR_TRI (BMFR_FEATURES * BMFR_BUFFER_COUNT)  // floats of one level-1 triangle, stored as a full 10x13
 #define QR_SLOTS 2
-#define QR_TILE_FLOATS (32 * 96)                    // one 32x32 tile of an interleaved-RGB image
+// One 32x32-pixel tile of an interleaved-RGB image is 96 floats per row.  TMA wants the innermost
+// start coordinate on a 16-byte boundary; a tile starts at pixel x0 (even), i.e. at float 3*x0 = 0 or 2
+// (mod 4), so the box is 100 floats wide, starts at the aligned-down coordinate and the reader skips
+// `shift` = 0 or 2 floats.
+#define QR_TILE_W 100
+#define QR_TILE_FLOATS (32 * QR_TILE_W)
 #define QR_TILE_BYTES (QR_TILE_FLOATS * 4)
 
 struct QrShared {
-    float stage[3][32][96];                      // TMA landing zone: normals, positions, accumulated colour of the next block
+    float stage[3][32][QR_TILE_W];               // TMA landing zone: normals, positions, accumulated colour of the next block
 #if BMFR_QR_SMEM_REDUCE
     float red[QR_COMPUTE_WARPS + 1][BMFR_BUFFER_COUNT][QR_RED_STRIDE];
     float coef[QR_COMPUTE_WARPS + 1][16];
@@ -320,7 +325,7 @@ struct QrShared {
     unsigned long long full[QR_SLOTS], empty[QR_SLOTS], data_full;
 };
 
-// The three tensor maps of a frame (2-D tensors [rows][W*3] of floats, box 96 x 32) and whether the
+// The three tensor maps of a frame (2-D tensors [rows][W*3] of floats, box 100 x 32) and whether the
 // TMA path can be used at all (W % 4 == 0, 16-byte aligned bases, driver entry point found).
 struct QrMaps {
     CUtensorMap normals, positions, colour;
@@ -384,7 +389,7 @@ __device__ __forceinline__ bool qr_block_is_interior(const KParams& P, int bx, i
 }
 // One thread: arm the barrier and start the three tile loads of block (bx, by).
 __device__ __forceinline__ void qr_prefetch(const KParams& P, const QrMaps& M, QrShared& sh, int bx, int by) {
-    const int c0 = (bx * 32 - 16 + P.off_x) * 3, c1 = by * 32 - 16 + P.off_y - P.row0;
+    const int c0 = ((bx * 32 - 16 + P.off_x) * 3) & ~3, c1 = by * 32 - 16 + P.off_y - P.row0;
     mbar_expect_tx(&sh.data_full, 3 * QR_TILE_BYTES);
     tma_load_tile(&sh.stage[0][0][0], &M.normals, c0, c1, &sh.data_full);
     tma_load_tile(&sh.stage[1][0][0], &M.positions, c0, c1, &sh.data_full);
@@ -510,11 +515,12 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
         if (M.use_tma && qr_block_is_interior(P, bx, by)) {
             mbar_wait(&sh.data_full, tma_parity);
             tma_parity ^= 1;
+            const int col = (((bx * 32 - 16 + P.off_x) * 3) & 3) + lane * 3;  // shift + this lane's pixel
 #pragma unroll
             for (int s = 0; s < ROWS; ++s) {
                 float v[9];
 #pragma unroll
-                for (int c = 0; c < 9; ++c) v[c] = scrub_nan(sh.stage[c / 3][warp * ROWS + s][lane * 3 + c % 3]);
+                for (int c = 0; c < 9; ++c) v[c] = scrub_nan(sh.stage[c / 3][warp * ROWS + s][col + c % 3]);
                 a[s][0] = v[0]; a[s][1] = v[1]; a[s][2] = v[2];
                 a[s][3] = v[3]; a[s][4] = v[4]; a[s][5] = v[5];
                 a[s][6] = v[3] * v[3]; a[s][7] = v[4] * v[4]; a[s][8] = v[5] * v[5];
@@ -673,7 +679,7 @@ static bool tile_map(const float* base, int W, int rows, CUtensorMap* out) {
     }
     const cuuint64_t dims[2] = {(cuuint64_t)W * 3, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)W * 3 * sizeof(float)};
-    const cuuint32_t box[2] = {96, 32}, elem[2] = {1, 1};
+    const cuuint32_t box[2] = {QR_TILE_W, 32}, elem[2] = {1, 1};
     CUtensorMap m;
     if (enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
