@@ -68,6 +68,26 @@ __device__ __forceinline__ float rsqrt_approx(float v) {
     return r;
 }
 
+// Packed fp32 pairs (sm_100 FFMA2 / FADD2 / FMUL2): one issue slot for two IEEE-rounded operations.
+// The level-1 factorisation keeps two matrix rows per 64-bit register pair.
+__device__ __forceinline__ unsigned long long f2_bits(float2 v) { return *reinterpret_cast<unsigned long long*>(&v); }
+__device__ __forceinline__ float2 bits_f2(unsigned long long b) { return *reinterpret_cast<float2*>(&b); }
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)), "l"(f2_bits(c)));
+    return bits_f2(d);
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+    return bits_f2(d);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+    return bits_f2(d);
+}
+
 #define QR_RED_STRIDE 36  // floats per column of the transpose buffer: 16-byte aligned rows, bank-shifted
 
 // Sum over the 32 lanes of N per-lane values (one per remaining column): every lane stores its N
@@ -233,6 +253,58 @@ struct QrLoop {
 template <int ROWS>
 struct QrLoop<ROWS, BMFR_FEATURES> {
     static __device__ __forceinline__ void run(float (&)[ROWS][BMFR_BUFFER_COUNT - 1], float*, float*, float*, int) {}
+};
+
+// The same reflector on row PAIRS: a2[h][c-1] holds rows (2h, 2h+1) of column c, so the products and
+// the eliminations are FFMA2 (half the issue slots of the scalar form above).
+template <int PAIRS, int K>
+__device__ __forceinline__ void qr_step2(float2 (&a2)[PAIRS][BMFR_BUFFER_COUNT - 1], float* __restrict__ srow, int lane) {
+    constexpr int N = BMFR_BUFFER_COUNT - K;
+    float cj[16];
+    if (K == 0) {  // a_0 = 1: the products are plain column sums, S_0 = number of rows
+        cj[0] = (float)(2 * PAIRS);
+#pragma unroll
+        for (int j = 1; j < N; ++j) {
+            float2 acc = a2[0][j - 1];
+#pragma unroll
+            for (int h = 1; h < PAIRS; ++h) acc = fadd2(acc, a2[h][j - 1]);
+            cj[j] = acc.x + acc.y;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            float2 acc = fmul2(a2[0][K - 1], a2[0][K - 1 + j]);
+#pragma unroll
+            for (int h = 1; h < PAIRS; ++h) acc = ffma2(a2[h][K - 1], a2[h][K - 1 + j], acc);
+            cj[j] = acc.x + acc.y;
+        }
+    }
+    float own;
+    warp_allsum<N>(cj, lane, own);
+    constexpr int LPC = AllSum<N>::LANES_PER_COLUMN;
+    if (lane % LPC == 0 && lane / LPC < N) srow[K + lane / LPC] = own;
+    const float nrk = -rcp_approx(cj[0]);  // -1 / S_k
+#pragma unroll
+    for (int j = 1; j < N; ++j) {
+        const float c = cj[j] * nrk;  // -(2 * dot / u_length_squared) of bmfr.cl:650
+        const float2 c2 = make_float2(c, c);
+#pragma unroll
+        for (int h = 0; h < PAIRS; ++h) {
+            if (K == 0) a2[h][j - 1] = fadd2(a2[h][j - 1], c2);
+            else a2[h][K - 1 + j] = ffma2(a2[h][K - 1], c2, a2[h][K - 1 + j]);
+        }
+    }
+}
+template <int PAIRS, int K>
+struct QrLoop2 {
+    static __device__ __forceinline__ void run(float2 (&a2)[PAIRS][BMFR_BUFFER_COUNT - 1], float* srows, int lane) {
+        qr_step2<PAIRS, K>(a2, srows + K * BMFR_BUFFER_COUNT, lane);
+        QrLoop2<PAIRS, K + 1>::run(a2, srows, lane);
+    }
+};
+template <int PAIRS>
+struct QrLoop2<PAIRS, BMFR_FEATURES> {
+    static __device__ __forceinline__ void run(float2 (&)[PAIRS][BMFR_BUFFER_COUNT - 1], float*, int) {}
 };
 
 // --------------------------------------------------------------------------------------------
@@ -619,7 +691,14 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
 #if BMFR_QR_SMEM_REDUCE
         QrLoop<ROWS, 0>::run(a, &sh.red[warp][0][0], sh.coef[warp], sh.tri[slot][warp], lane);
 #else
-        QrLoop<ROWS, 0>::run(a, nullptr, nullptr, sh.tri[slot][warp], lane);
+        {
+            float2 a2[ROWS / 2][BMFR_BUFFER_COUNT - 1];
+#pragma unroll
+            for (int h = 0; h < ROWS / 2; ++h)
+#pragma unroll
+                for (int c = 0; c < BMFR_BUFFER_COUNT - 1; ++c) a2[h][c] = make_float2(a[2 * h][c], a[2 * h + 1][c]);
+            QrLoop2<ROWS / 2, 0>::run(a2, sh.tri[slot][warp], lane);
+        }
 #endif
         mbar_arrive(&sh.full[slot]);
         if (warp == 0) QR_STAMP(0, it, 6);

@@ -29,6 +29,18 @@ struct PostShared {
     float coef[9][PT_COEF];  // this block ([4]) and its eight neighbours (ring pixels), (dy+1)*3 + dx+1
 };
 
+// WIDE: every interleaved-RGB buffer of the launch is 8-byte aligned, so a pixel is moved with a
+// 64-bit + a 32-bit access (bmfr_device.cuh) instead of three 32-bit ones.
+template <bool WIDE>
+__device__ __forceinline__ f3 ldf3(const float* __restrict__ b, unsigned int i) {
+    return WIDE ? load_f3_wide(b, i) : load_f3(b, i);
+}
+template <bool WIDE>
+__device__ __forceinline__ void stf3(float* __restrict__ b, unsigned int i, f3 v) {
+    if (WIDE) store_f3_wide(b, i, v);
+    else store_f3(b, i, v);
+}
+
 __device__ __forceinline__ float fast_rcp(float v) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
@@ -77,7 +89,7 @@ __device__ __forceinline__ f3 weighted_sum_px(f3 n, f3 p, const float* __restric
 // accumulate_filtered_data for one pixel, bmfr.cl:778-856.  Returns the tone-mapped colour.
 // accept / pp / spp / alb are this pixel's accept mask, previous-frame position, sample count and
 // albedo, fetched by the caller together with the features (one round of independent loads).
-template <bool STRIP>
+template <bool STRIP, bool WIDE>
 __device__ __forceinline__ f3 accumulate_filtered_px(const KParams& P, unsigned int lp, f3 filtered, unsigned int accept,
                                                      float2 pp, unsigned int spp, f3 alb, bool store) {
     f3 prev = make_f3(0.f, 0.f, 0.f);
@@ -96,7 +108,7 @@ __device__ __forceinline__ f3 accumulate_filtered_px(const KParams& P, unsigned 
                     *P.oob_flag = 1;
                     continue;
                 }
-                const f3 pc = load_f3(P.accum_prev, pix_index(P, sx, sy));
+                const f3 pc = ldf3<WIDE>(P.accum_prev, pix_index(P, sx, sy));
                 total += w[i];
                 prev.x = fmaf(w[i], pc.x, prev.x);
                 prev.y = fmaf(w[i], pc.y, prev.y);
@@ -114,7 +126,7 @@ __device__ __forceinline__ f3 accumulate_filtered_px(const KParams& P, unsigned 
     const float oma = 1.f - alpha;
     const f3 accum = make_f3(fmaf(alpha, filtered.x, oma * prev.x), fmaf(alpha, filtered.y, oma * prev.y),
                              fmaf(alpha, filtered.z, oma * prev.z));
-    if (store) store_f3(P.accum_cur, lp, accum);
+    if (store) stf3<WIDE>(P.accum_cur, lp, accum);
     return make_f3(tone_map_fast(alb.x * accum.x), tone_map_fast(alb.y * accum.y), tone_map_fast(alb.z * accum.z));
 }
 
@@ -144,16 +156,16 @@ __device__ __forceinline__ void put_ycc(PostShared& sh, const KParams& P, int hx
 }
 
 // weighted_sum -> accumulate_filtered_data -> tone map of image pixel (x,y) into halo cell (hx,hy)
-template <bool STRIP>
+template <bool STRIP, bool WIDE>
 __device__ __forceinline__ void phase_a_pixel(PostShared& sh, const KParams& P, const float* cf, int hx, int hy, int x, int y,
                                               bool store) {
     const unsigned int lp = pix_index(P, x, y);
-    const f3 n = load_f3(P.cur_normals, lp), p = load_f3(P.cur_positions, lp), alb = load_f3(P.albedo, lp);
+    const f3 n = ldf3<WIDE>(P.cur_normals, lp), p = ldf3<WIDE>(P.cur_positions, lp), alb = ldf3<WIDE>(P.albedo, lp);
     const unsigned int accept = __ldg(P.accept + lp);
     const unsigned int spp = __ldg(const_cast<const unsigned char*>(P.cur_spp) + lp);
     const float2 pp = __ldg(P.prev_pixels + lp);
     const f3 filtered = weighted_sum_px(n, p, cf);
-    const f3 tone = accumulate_filtered_px<STRIP>(P, lp, filtered, accept, pp, spp, alb, store);
+    const f3 tone = accumulate_filtered_px<STRIP, WIDE>(P, lp, filtered, accept, pp, spp, alb, store);
     put_ycc(sh, P, hx, hy, x, y, to_ycocg(tone));
 }
 
@@ -161,7 +173,7 @@ __device__ __forceinline__ void phase_a_pixel(PostShared& sh, const KParams& P, 
 #define BMFR_POST_MIN_BLOCKS 4
 #endif
 
-template <bool STRIP>
+template <bool STRIP, bool WIDE>
 __global__ void __launch_bounds__(256, BMFR_POST_MIN_BLOCKS) post_kernel(const __grid_constant__ KParams P) {
     __shared__ __align__(16) PostShared sh;
     const int bx = blockIdx.x, by = P.by0 + blockIdx.y;
@@ -186,7 +198,7 @@ __global__ void __launch_bounds__(256, BMFR_POST_MIN_BLOCKS) post_kernel(const _
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
         const int ty = 4 * warp + s, y = y0 + ty;
-        if (col_ok && y >= P.py0 && y < P.py1) phase_a_pixel<STRIP>(sh, P, sh.coef[4], lane + 1, ty + 1, x, y, true);
+        if (col_ok && y >= P.py0 && y < P.py1) phase_a_pixel<STRIP, WIDE>(sh, P, sh.coef[4], lane + 1, ty + 1, x, y, true);
     }
     // phase A, ring: 4 * 33 = 132 pixels, coefficients of the pixel's own block
     if (tid < 4 * (PT_HALO - 1)) {
@@ -199,7 +211,7 @@ __global__ void __launch_bounds__(256, BMFR_POST_MIN_BLOCKS) post_kernel(const _
         const int rx = x0 + hx - 1, ry = y0 + hy - 1;
         if (rx >= 0 && rx < P.W && ry >= P.py0 && ry < P.py1) {
             const int nb = ((hy == 0) ? 0 : (hy == PT_HALO - 1) ? 6 : 3) + ((hx == 0) ? 0 : (hx == PT_HALO - 1) ? 2 : 1);
-            phase_a_pixel<STRIP>(sh, P, sh.coef[nb], hx, hy, rx, ry, false);
+            phase_a_pixel<STRIP, WIDE>(sh, P, sh.coef[nb], hx, hy, rx, ry, false);
         }
     }
     __syncthreads();
@@ -234,7 +246,7 @@ __global__ void __launch_bounds__(256, BMFR_POST_MIN_BLOCKS) post_kernel(const _
                     *P.oob_flag = 1;
                     continue;
                 }
-                const f3 pc = load_f3(P.result_prev, pix_index(P, pix + dx, sy));
+                const f3 pc = ldf3<WIDE>(P.result_prev, pix_index(P, pix + dx, sy));
                 prev.x = fmaf(w[i], pc.x, prev.x);
                 prev.y = fmaf(w[i], pc.y, prev.y);
                 prev.z = fmaf(w[i], pc.z, prev.z);
@@ -282,14 +294,23 @@ __global__ void __launch_bounds__(256, BMFR_POST_MIN_BLOCKS) post_kernel(const _
             const f3 pr = from_ycocg(hist[s]);
             out = make_f3(fmaf(a, out.x, oma * pr.x), fmaf(a, out.y, oma * pr.y), fmaf(a, out.z, oma * pr.z));
         }
-        store_f3(P.result_cur, lp, out);
-        if (P.user_out) store_f3(P.user_out, lp, out);
+        stf3<WIDE>(P.result_cur, lp, out);
+        if (P.user_out) stf3<WIDE>(P.user_out, lp, out);
     }
 }
 
 cudaError_t launch_post(const KParams& P, cudaStream_t st) {
     const dim3 grid(P.blocks_x, P.by1 - P.by0);
-    if (P.row0 != 0 || P.row1 != P.H) post_kernel<true><<<grid, 256, 0, st>>>(P);
-    else post_kernel<false><<<grid, 256, 0, st>>>(P);
+    const bool strip = P.row0 != 0 || P.row1 != P.H;
+    const uintptr_t bits = (uintptr_t)P.cur_normals | (uintptr_t)P.cur_positions | (uintptr_t)P.albedo | (uintptr_t)P.accum_prev |
+                           (uintptr_t)P.accum_cur | (uintptr_t)P.result_prev | (uintptr_t)P.result_cur | (uintptr_t)P.user_out;
+    const bool wide = (bits & 7) == 0;
+    if (strip) {
+        if (wide) post_kernel<true, true><<<grid, 256, 0, st>>>(P);
+        else post_kernel<true, false><<<grid, 256, 0, st>>>(P);
+    } else {
+        if (wide) post_kernel<false, true><<<grid, 256, 0, st>>>(P);
+        else post_kernel<false, false><<<grid, 256, 0, st>>>(P);
+    }
     return cudaGetLastError();
 }
