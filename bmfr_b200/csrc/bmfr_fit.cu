@@ -480,11 +480,25 @@ __device__ long long g_qr_timing[512];
     do {                                                                                   \
         if (blockIdx.x == 0 && lane == 0 && (it) < 8) g_qr_timing[(base) + (it) * 8 + (k)] = clock64(); \
     } while (0)
+__device__ long long g_qr_cta[4096];  // per CTA: start, compute end, solver end (globaltimer ns), SM id
+__device__ __forceinline__ long long qr_globaltimer() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define QR_CTA_STAMP(k)                                                                         \
+    do {                                                                                        \
+        if (lane == 0 && blockIdx.x < 1024) g_qr_cta[blockIdx.x * 4 + (k)] = qr_globaltimer(); \
+    } while (0)
 extern "C" int bmfr_debug_qr_timing(long long* out, int n) {
     return (int)cudaMemcpyFromSymbol(out, g_qr_timing, sizeof(long long) * (n < 512 ? n : 512));
 }
+extern "C" int bmfr_debug_qr_cta(long long* out, int n) {
+    return (int)cudaMemcpyFromSymbol(out, g_qr_cta, sizeof(long long) * (n < 4096 ? n : 4096));
+}
 #else
 #define QR_STAMP(base, it, k) do { } while (0)
+#define QR_CTA_STAMP(k) do { } while (0)
 #endif
 
 template <bool STRIP>
@@ -492,7 +506,11 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
                                                                                 const __grid_constant__ QrMaps M) {
     extern __shared__ __align__(128) unsigned char qr_smem[];
     QrShared& sh = *reinterpret_cast<QrShared*>((reinterpret_cast<uintptr_t>(qr_smem) + 127) & ~(uintptr_t)127);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    // broadcast from lane 0 so that the compiler knows the role dispatch below is warp-uniform (otherwise
+    // every shuffle of both roles gets a second, divergence-safe copy and the kernel outgrows the
+    // instruction cache)
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     constexpr int NSC = BMFR_FEATURES_SCALED, NNS = BMFR_FEATURES_NOT_SCALED, ROWS = QR_ROWS;
     const int nblocks = P.blocks_x * (P.by1 - P.by0);
     const int first = blockIdx.x, stride = gridDim.x;
@@ -510,6 +528,16 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
     }
     __syncthreads();
 
+    if (warp == 0) {
+        QR_CTA_STAMP(0);
+#ifdef BMFR_QR_TIMING
+        if (lane == 0 && blockIdx.x < 1024) {
+            unsigned int smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            g_qr_cta[blockIdx.x * 4 + 3] = smid;
+        }
+#endif
+    }
     if (warp == QR_COMPUTE_WARPS) {
         // ---------------- solver warp ----------------
         for (int it = 0; it < iters; ++it) {
@@ -566,6 +594,7 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
             __syncwarp();  // sh.fin / red / coef are reused by the next block
             QR_STAMP(256, it, 2);
         }
+        QR_CTA_STAMP(2);
         return;
     }
 
@@ -703,6 +732,7 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
         mbar_arrive(&sh.full[slot]);
         if (warp == 0) QR_STAMP(0, it, 6);
     }
+    if (warp == 0) QR_CTA_STAMP(1);
 }
 
 // --------------------------------------------------------------------------------------------

@@ -169,6 +169,9 @@ __device__ __forceinline__ void phase_a_pixel(PostShared& sh, const KParams& P, 
     put_ycc(sh, P, hx, hy, x, y, to_ycocg(tone));
 }
 
+#ifndef BMFR_POST_WIDE_ACCESS
+#define BMFR_POST_WIDE_ACCESS 0
+#endif
 #ifndef BMFR_POST_MIN_BLOCKS
 #define BMFR_POST_MIN_BLOCKS 4
 #endif
@@ -304,7 +307,9 @@ cudaError_t launch_post(const KParams& P, cudaStream_t st) {
     const bool strip = P.row0 != 0 || P.row1 != P.H;
     const uintptr_t bits = (uintptr_t)P.cur_normals | (uintptr_t)P.cur_positions | (uintptr_t)P.albedo | (uintptr_t)P.accum_prev |
                            (uintptr_t)P.accum_cur | (uintptr_t)P.result_prev | (uintptr_t)P.result_cur | (uintptr_t)P.user_out;
-    const bool wide = (bits & 7) == 0;
+    // measured on B200 (profiles/): the 64+32-bit form costs 38% more instructions (selects, address
+    // arithmetic) and the same number of L1 wavefronts, so it is kept only as a tuning switch
+    const bool wide = BMFR_POST_WIDE_ACCESS && (bits & 7) == 0;
     if (strip) {
         if (wide) post_kernel<true, true><<<grid, 256, 0, st>>>(P);
         else post_kernel<true, false><<<grid, 256, 0, st>>>(P);
