@@ -258,7 +258,8 @@ struct QrLoop<ROWS, BMFR_FEATURES> {
 // The same reflector on row PAIRS: a2[h][c-1] holds rows (2h, 2h+1) of column c, so the products and
 // the eliminations are FFMA2 (half the issue slots of the scalar form above).
 template <int PAIRS, int K>
-__device__ __forceinline__ void qr_step2(float2 (&a2)[PAIRS][BMFR_BUFFER_COUNT - 1], float* __restrict__ srow, int lane) {
+__device__ __forceinline__ void qr_step2(float2 (&a2)[PAIRS][BMFR_BUFFER_COUNT - 1], float* __restrict__ red,
+                                         float* __restrict__ coefbuf, float* __restrict__ srow, int lane) {
     constexpr int N = BMFR_BUFFER_COUNT - K;
     float cj[16];
     if (K == 0) {  // a_0 = 1: the products are plain column sums, S_0 = number of rows
@@ -279,14 +280,28 @@ __device__ __forceinline__ void qr_step2(float2 (&a2)[PAIRS][BMFR_BUFFER_COUNT -
             cj[j] = acc.x + acc.y;
         }
     }
+#if BMFR_QR_SMEM_REDUCE
+    {
+        float part[BMFR_BUFFER_COUNT];
+#pragma unroll
+        for (int j = 0; j < N; ++j) part[j] = cj[j];
+        float sk;
+        const float t = warp_column_sums<N>(part, red, lane, sk);
+        if (lane < N) srow[K + lane] = t;
+        warp_broadcast<N>(-t * rcp_approx(sk), coefbuf, lane, cj);  // -(2 * dot / u_length_squared) of bmfr.cl:650
+    }
+#else
     float own;
     warp_allsum<N>(cj, lane, own);
     constexpr int LPC = AllSum<N>::LANES_PER_COLUMN;
     if (lane % LPC == 0 && lane / LPC < N) srow[K + lane / LPC] = own;
     const float nrk = -rcp_approx(cj[0]);  // -1 / S_k
 #pragma unroll
+    for (int j = 1; j < N; ++j) cj[j] *= nrk;  // -(2 * dot / u_length_squared) of bmfr.cl:650
+#endif
+#pragma unroll
     for (int j = 1; j < N; ++j) {
-        const float c = cj[j] * nrk;  // -(2 * dot / u_length_squared) of bmfr.cl:650
+        const float c = cj[j];
         const float2 c2 = make_float2(c, c);
 #pragma unroll
         for (int h = 0; h < PAIRS; ++h) {
@@ -297,14 +312,15 @@ __device__ __forceinline__ void qr_step2(float2 (&a2)[PAIRS][BMFR_BUFFER_COUNT -
 }
 template <int PAIRS, int K>
 struct QrLoop2 {
-    static __device__ __forceinline__ void run(float2 (&a2)[PAIRS][BMFR_BUFFER_COUNT - 1], float* srows, int lane) {
-        qr_step2<PAIRS, K>(a2, srows + K * BMFR_BUFFER_COUNT, lane);
-        QrLoop2<PAIRS, K + 1>::run(a2, srows, lane);
+    static __device__ __forceinline__ void run(float2 (&a2)[PAIRS][BMFR_BUFFER_COUNT - 1], float* red, float* coefbuf,
+                                               float* srows, int lane) {
+        qr_step2<PAIRS, K>(a2, red, coefbuf, srows + K * BMFR_BUFFER_COUNT, lane);
+        QrLoop2<PAIRS, K + 1>::run(a2, red, coefbuf, srows, lane);
     }
 };
 template <int PAIRS>
 struct QrLoop2<PAIRS, BMFR_FEATURES> {
-    static __device__ __forceinline__ void run(float2 (&)[PAIRS][BMFR_BUFFER_COUNT - 1], float*, int) {}
+    static __device__ __forceinline__ void run(float2 (&)[PAIRS][BMFR_BUFFER_COUNT - 1], float*, float*, float*, int) {}
 };
 
 // --------------------------------------------------------------------------------------------
@@ -395,6 +411,8 @@ struct QrShared {
     float tri[QR_SLOTS][QR_COMPUTE_WARPS][QR_TRI];  // level-1 triangles (unnormalised rows S_kj)
     float fin[QR_TRI];                           // level-2 triangle
     unsigned long long full[QR_SLOTS], empty[QR_SLOTS], data_full;
+    int blk[4];                                  // ring of upcoming block indices of this CTA (dynamic schedule)
+    int slot_block[QR_SLOTS];                    // block whose triangles sit in the slot; -1 = no more blocks
 };
 
 // The three tensor maps of a frame (2-D tensors [rows][W*3] of floats, box 100 x 32) and whether the
@@ -512,10 +530,11 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
     // instruction cache)
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     constexpr int NSC = BMFR_FEATURES_SCALED, NNS = BMFR_FEATURES_NOT_SCALED, ROWS = QR_ROWS;
+    // Block schedule: the first two blocks of a CTA are static (blockIdx.x, blockIdx.x + gridDim.x), the
+    // following ones come from a global counter, so CTAs that drew cheap blocks or fast SMs take more.
     const int nblocks = P.blocks_x * (P.by1 - P.by0);
     const int first = blockIdx.x, stride = gridDim.x;
     if (first >= nblocks) return;
-    const int iters = (nblocks - first + stride - 1) / stride;
 
     if (tid == 0) {
 #pragma unroll
@@ -540,12 +559,14 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
     }
     if (warp == QR_COMPUTE_WARPS) {
         // ---------------- solver warp ----------------
-        for (int it = 0; it < iters; ++it) {
-            const int local = first + it * stride, slot = it % QR_SLOTS;
-            const int group = P.by0 * P.blocks_x + local;
+        for (int it = 0;; ++it) {
+            const int slot = it % QR_SLOTS;
             QR_STAMP(256, it, 0);
             mbar_wait(&sh.full[slot], (it / QR_SLOTS) & 1);
             QR_STAMP(256, it, 1);
+            const int local = sh.slot_block[slot];
+            if (local < 0) break;
+            const int group = P.by0 * P.blocks_x + local;
             // level 2: the 40 stacked rows (row (w,k) = S_kj / sqrt(S_kk) for j >= k, zero left of the
             // diagonal), two per lane
             constexpr int NS2 = 2;
@@ -600,12 +621,14 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
 
     // ---------------- compute warps ----------------
     unsigned int tma_parity = 0;
-    {
+    if (tid == 0) {
         const int bx0 = first % P.blocks_x, by0 = P.by0 + first / P.blocks_x;
-        if (tid == 0 && M.use_tma && qr_block_is_interior(P, bx0, by0)) qr_prefetch(P, M, sh, bx0, by0);
+        if (M.use_tma && qr_block_is_interior(P, bx0, by0)) qr_prefetch(P, M, sh, bx0, by0);
+        sh.blk[2] = 2 * stride + atomicAdd(P.block_counter, 1);  // block of iteration 2, read after barrier 0
     }
-    for (int it = 0; it < iters; ++it) {
-        const int local = first + it * stride, slot = it % QR_SLOTS;
+    int local = first, next_local = first + stride, it = 0;
+    for (; local < nblocks; ++it) {
+        const int slot = it % QR_SLOTS;
         const int group = P.by0 * P.blocks_x + local;
         const int bx = local % P.blocks_x, by = P.by0 + local / P.blocks_x;
 
@@ -669,10 +692,13 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
         }
         if (warp == 0) QR_STAMP(0, it, 2);
         compute_barrier();  // the per-warp extrema are visible, and every thread is done with the stage
-        if (tid == 0 && it + 1 < iters && M.use_tma) {
-            const int nl = local + stride;
-            const int nbx = nl % P.blocks_x, nby = P.by0 + nl / P.blocks_x;
-            if (qr_block_is_interior(P, nbx, nby)) qr_prefetch(P, M, sh, nbx, nby);
+        const int after_next = sh.blk[(it + 2) & 3];  // written by thread 0 before this barrier
+        if (tid == 0) {
+            if (next_local < nblocks && M.use_tma) {
+                const int nbx = next_local % P.blocks_x, nby = P.by0 + next_local / P.blocks_x;
+                if (qr_block_is_interior(P, nbx, nby)) qr_prefetch(P, M, sh, nbx, nby);
+            }
+            sh.blk[(it + 3) & 3] = 2 * stride + atomicAdd(P.block_counter, 1);  // read after the next barrier
         }
         // every warp finishes the reduction itself (lane f < 6 owns feature f) and shares the result
         // by shuffle: one block-wide barrier per block instead of two
@@ -717,20 +743,29 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
         if (warp == 0) QR_STAMP(0, it, 4);
         if (it >= QR_SLOTS) mbar_wait(&sh.empty[slot], ((it / QR_SLOTS) - 1) & 1);
         if (warp == 0) QR_STAMP(0, it, 5);
-#if BMFR_QR_SMEM_REDUCE
-        QrLoop<ROWS, 0>::run(a, &sh.red[warp][0][0], sh.coef[warp], sh.tri[slot][warp], lane);
-#else
         {
             float2 a2[ROWS / 2][BMFR_BUFFER_COUNT - 1];
 #pragma unroll
             for (int h = 0; h < ROWS / 2; ++h)
 #pragma unroll
                 for (int c = 0; c < BMFR_BUFFER_COUNT - 1; ++c) a2[h][c] = make_float2(a[2 * h][c], a[2 * h + 1][c]);
-            QrLoop2<ROWS / 2, 0>::run(a2, sh.tri[slot][warp], lane);
-        }
+#if BMFR_QR_SMEM_REDUCE
+            QrLoop2<ROWS / 2, 0>::run(a2, &sh.red[warp][0][0], sh.coef[warp], sh.tri[slot][warp], lane);
+#else
+            QrLoop2<ROWS / 2, 0>::run(a2, nullptr, nullptr, sh.tri[slot][warp], lane);
 #endif
+        }
+        if (tid == 0) sh.slot_block[slot] = local;
         mbar_arrive(&sh.full[slot]);
         if (warp == 0) QR_STAMP(0, it, 6);
+        local = next_local;
+        next_local = after_next;
+    }
+    {  // tell the solver that this CTA is done
+        const int slot = it % QR_SLOTS;
+        if (it >= QR_SLOTS) mbar_wait(&sh.empty[slot], ((it / QR_SLOTS) - 1) & 1);
+        if (tid == 0) sh.slot_block[slot] = -1;
+        mbar_arrive(&sh.full[slot]);
     }
     if (warp == 0) QR_CTA_STAMP(1);
 }

@@ -12,8 +12,10 @@
 // once per element per block.  Kept in fp64: NOISE_AMOUNT is a double literal in the reference
 // (bmfr.cpp:58), which makes `value + NOISE_AMOUNT * 2.f * (random - 0.5f)` an fp64 expression.
 // --------------------------------------------------------------------------------------------
-__global__ void noise_tile_kernel(double* __restrict__ noise, float* __restrict__ noise_f, double noise_amount, int frame) {
+__global__ void noise_tile_kernel(double* __restrict__ noise, float* __restrict__ noise_f, int* __restrict__ block_counter,
+                                  double noise_amount, int frame) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *block_counter = 0;  // the fit kernel of this frame draws its blocks from it
     if (i >= (BMFR_FEATURES - 1) * BMFR_BLOCK_PIXELS) return;
     // id + sub_vector*256 + feature_buffer*1024 + frame*13*1024 with feature_buffer = 1 + i/1024
     const int seed = i + BMFR_BLOCK_PIXELS + frame * BMFR_BUFFER_COUNT * BMFR_BLOCK_PIXELS;
@@ -140,9 +142,9 @@ void bmfr_host_block_offset(int frame, int* ox, int* oy) {
     *oy = h_block_offsets[i][1];
 }
 
-cudaError_t launch_noise_tile(double* d_noise, float* d_noise_f, double noise_amount, int frame, cudaStream_t st) {
+cudaError_t launch_noise_tile(double* d_noise, float* d_noise_f, int* block_counter, double noise_amount, int frame, cudaStream_t st) {
     const int n = (BMFR_FEATURES - 1) * BMFR_BLOCK_PIXELS;
-    noise_tile_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_noise, d_noise_f, noise_amount, frame);
+    noise_tile_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_noise, d_noise_f, block_counter, noise_amount, frame);
     return cudaGetLastError();
 }
 

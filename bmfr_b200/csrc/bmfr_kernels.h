@@ -50,11 +50,12 @@ struct KParams {
     float* result_cur;            // result_frame
     float* user_out;              // optional copy of result rows for the caller
     int* oob_flag;                // set when a gather needed a row outside [row0,row1)
+    int* block_counter;           // FUSED fit: dynamic block schedule, reset by the noise-tile kernel of the frame
 };
 
 
 void bmfr_host_block_offset(int frame, int* ox, int* oy);
-cudaError_t launch_noise_tile(double* d_noise, float* d_noise_f, double noise_amount, int frame, cudaStream_t st);
+cudaError_t launch_noise_tile(double* d_noise, float* d_noise_f, int* block_counter, double noise_amount, int frame, cudaStream_t st);
 cudaError_t launch_k1(const KParams& P, cudaStream_t st);
 cudaError_t launch_k2(const KParams& P, cudaStream_t st);
 cudaError_t launch_k3(const KParams& P, cudaStream_t st);

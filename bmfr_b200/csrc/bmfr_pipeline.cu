@@ -255,7 +255,7 @@ int bmfr_create(const bmfr_params* params, bmfr_ctx** out_ctx) {
     if (st == 0) st = dev_alloc(&c->mins_inv, nb * BMFR_FEATURES_SCALED * 2, "mins_inv");
     if (st == 0) st = dev_alloc(&c->noise, (size_t)(BMFR_FEATURES - 1) * BMFR_BLOCK_PIXELS, "noise");
     if (st == 0) st = dev_alloc(&c->noise_f, (size_t)(BMFR_FEATURES - 1) * BMFR_BLOCK_PIXELS, "noise_f");
-    if (st == 0) st = dev_alloc(&c->d_oob, 1, "oob flag");
+    if (st == 0) st = dev_alloc(&c->d_oob, 2, "oob flag + block counter");
     if (st == 0 && p.mode == BMFR_MODE_STAGED) {
         st = dev_alloc(&c->tmp_data, (size_t)c->tmp_block_rows * g.blocks_x * BMFR_BUFFER_COUNT * BMFR_BLOCK_PIXELS, "tmp_data");
         if (st == 0) st = dev_alloc(&c->filtered, npix * 3, "filtered");
@@ -327,7 +327,7 @@ static void fill_params(bmfr_ctx* c, KParams& P, int frame, const float* d_albed
     P.accum_prev = c->accum.previous(); P.accum_cur = c->accum.current();
     P.tone_mapped = c->tone_mapped;
     P.result_prev = c->result.previous(); P.result_cur = c->result.current();
-    P.user_out = d_out; P.oob_flag = c->d_oob;
+    P.user_out = d_out; P.oob_flag = c->d_oob; P.block_counter = c->d_oob + 1;
 }
 
 static StageEvents* prof_slot(bmfr_ctx* c, int frame) {
@@ -355,7 +355,7 @@ static StageEvents* prof_slot(bmfr_ctx* c, int frame) {
 
 static int run_frame(bmfr_ctx* c, const KParams& P, int frame) {
     StageEvents* pe = prof_slot(c, frame);
-    LAUNCH_TRY(launch_noise_tile(c->noise, c->noise_f, c->prm.noise_amount, frame, c->stream), "noise_tile_kernel");
+    LAUNCH_TRY(launch_noise_tile(c->noise, c->noise_f, c->d_oob + 1, c->prm.noise_amount, frame, c->stream), "noise_tile_kernel");
     MARK(0);
     if (c->prm.mode == BMFR_MODE_STAGED) {
         LAUNCH_TRY(launch_k1(P, c->stream), "accumulate_noisy_data");
