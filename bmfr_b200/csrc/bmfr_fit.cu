@@ -411,7 +411,7 @@ struct QrShared {
     float tri[QR_SLOTS][QR_COMPUTE_WARPS][QR_TRI];  // level-1 triangles (unnormalised rows S_kj)
     float fin[QR_TRI];                           // level-2 triangle
     unsigned long long full[QR_SLOTS], empty[QR_SLOTS], data_full;
-    int blk[4];                                  // ring of upcoming block indices of this CTA (dynamic schedule)
+    int blk[2];                                  // block index of the next iteration, by iteration parity (dynamic schedule)
     int slot_block[QR_SLOTS];                    // block whose triangles sit in the slot; -1 = no more blocks
 };
 
@@ -530,8 +530,9 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
     // instruction cache)
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     constexpr int NSC = BMFR_FEATURES_SCALED, NNS = BMFR_FEATURES_NOT_SCALED, ROWS = QR_ROWS;
-    // Block schedule: the first two blocks of a CTA are static (blockIdx.x, blockIdx.x + gridDim.x), the
-    // following ones come from a global counter, so CTAs that drew cheap blocks or fast SMs take more.
+    // Block schedule: the first block of a CTA is blockIdx.x, the following ones come from a global
+    // counter one block ahead (thread 0 draws the index, publishes it and starts the loads while the
+    // CTA factors the current block), so CTAs that drew cheap blocks or fast SMs take more.
     const int nblocks = P.blocks_x * (P.by1 - P.by0);
     const int first = blockIdx.x, stride = gridDim.x;
     if (first >= nblocks) return;
@@ -620,14 +621,19 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
     }
 
     // ---------------- compute warps ----------------
-    unsigned int tma_parity = 0;
+    // data_full completes once per iteration: thread 0 arrives on it after publishing sh.blk[it & 1],
+    // with the TMA byte count when the block is fetched as tiles, plainly otherwise.
     if (tid == 0) {
         const int bx0 = first % P.blocks_x, by0 = P.by0 + first / P.blocks_x;
+        sh.blk[0] = first;
         if (M.use_tma && qr_block_is_interior(P, bx0, by0)) qr_prefetch(P, M, sh, bx0, by0);
-        sh.blk[2] = 2 * stride + atomicAdd(P.block_counter, 1);  // block of iteration 2, read after barrier 0
+        else mbar_arrive(&sh.data_full);
     }
-    int local = first, next_local = first + stride, it = 0;
-    for (; local < nblocks; ++it) {
+    int it = 0;
+    for (;; ++it) {
+        mbar_wait(&sh.data_full, it & 1);
+        const int local = sh.blk[it & 1];
+        if (local >= nblocks) break;
         const int slot = it % QR_SLOTS;
         const int group = P.by0 * P.blocks_x + local;
         const int bx = local % P.blocks_x, by = P.by0 + local / P.blocks_x;
@@ -637,8 +643,6 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
         float a[ROWS][BMFR_BUFFER_COUNT - 1];
         if (warp == 0) QR_STAMP(0, it, 0);
         if (M.use_tma && qr_block_is_interior(P, bx, by)) {
-            mbar_wait(&sh.data_full, tma_parity);
-            tma_parity ^= 1;
             const int col = (((bx * 32 - 16 + P.off_x) * 3) & 3) + lane * 3;  // shift + this lane's pixel
 #pragma unroll
             for (int s = 0; s < ROWS; ++s) {
@@ -692,13 +696,12 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
         }
         if (warp == 0) QR_STAMP(0, it, 2);
         compute_barrier();  // the per-warp extrema are visible, and every thread is done with the stage
-        const int after_next = sh.blk[(it + 2) & 3];  // written by thread 0 before this barrier
-        if (tid == 0) {
-            if (next_local < nblocks && M.use_tma) {
-                const int nbx = next_local % P.blocks_x, nby = P.by0 + next_local / P.blocks_x;
-                if (qr_block_is_interior(P, nbx, nby)) qr_prefetch(P, M, sh, nbx, nby);
-            }
-            sh.blk[(it + 3) & 3] = 2 * stride + atomicAdd(P.block_counter, 1);  // read after the next barrier
+        if (tid == 0) {  // draw the next block, publish it, start its loads
+            const int nl = stride + atomicAdd(P.block_counter, 1);
+            sh.blk[(it + 1) & 1] = nl;
+            const int nbx = nl % P.blocks_x, nby = P.by0 + nl / P.blocks_x;
+            if (nl < nblocks && M.use_tma && qr_block_is_interior(P, nbx, nby)) qr_prefetch(P, M, sh, nbx, nby);
+            else mbar_arrive(&sh.data_full);
         }
         // every warp finishes the reduction itself (lane f < 6 owns feature f) and shares the result
         // by shuffle: one block-wide barrier per block instead of two
@@ -758,8 +761,6 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
         if (tid == 0) sh.slot_block[slot] = local;
         mbar_arrive(&sh.full[slot]);
         if (warp == 0) QR_STAMP(0, it, 6);
-        local = next_local;
-        next_local = after_next;
     }
     {  // tell the solver that this CTA is done
         const int slot = it % QR_SLOTS;

@@ -54,10 +54,6 @@ g0 = c[:, 0].min()
 start, cend, send, sm = c[:, 0] - g0, c[:, 1] - g0, c[:, 2] - g0, c[:, 3]
 print(f"per CTA (ns from first start): start  min {start.min()} max {start.max()};  compute end  min {cend.min()} median {int(np.median(cend))} max {cend.max()};"
       f"  solver end  min {send.min()} median {int(np.median(send))} max {send.max()}")
-nblk = np.full(444, 5)
-for k in (4, 5):
-    m = nblk == k
-    print(f"  CTAs with {k} blocks: n={m.sum()} compute end median {int(np.median(cend[m]))} max {cend[m].max()}, solver end median {int(np.median(send[m]))} max {send[m].max()}")
 order = np.argsort(send)[-5:]
 print("  slowest CTAs:", [(int(i), int(sm[i]), int(start[i]), int(cend[i]), int(send[i])) for i in order], "(cta, sm, start, compute end, solver end)")
 per_sm = {}
