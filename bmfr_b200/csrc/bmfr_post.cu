@@ -155,18 +155,58 @@ __device__ __forceinline__ void put_ycc(PostShared& sh, const KParams& P, int hx
     if (okx && oky) put_cell(sh, hx + ex, hy + ey, v);
 }
 
-// weighted_sum -> accumulate_filtered_data -> tone map of image pixel (x,y) into halo cell (hx,hy)
+// Bilinear sample of the previous TAA result at pp in YCoCg (bmfr.cl:922-965); false when the pixel
+// takes the copy-through path of bmfr.cl:884-890.  It depends on pp only, so it is issued in phase A
+// next to the accumulation taps: one round of gathers per pixel instead of two.
 template <bool STRIP, bool WIDE>
-__device__ __forceinline__ void phase_a_pixel(PostShared& sh, const KParams& P, const float* cf, int hx, int hy, int x, int y,
-                                              bool store) {
+__device__ __forceinline__ bool history_sample(const KParams& P, float2 pp, f3& hist) {
+    hist = make_f3(0.f, 0.f, 0.f);
+    if (P.frame == 0) return false;
+    const int pix = __float2int_rd(pp.x), piy = __float2int_rd(pp.y);
+    if (pix < -1 || piy < -1 || pix >= P.W || piy >= P.H) return false;  // bmfr.cl:884-890
+    const float frx = pp.x - (float)pix, fry = pp.y - (float)piy;
+    const float omx = 1.f - frx, omy = 1.f - fry;
+    const float w[4] = {omx * omy, frx * omy, omx * fry, frx * fry};
+    f3 prev = make_f3(0.f, 0.f, 0.f);
+    float total = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {  // bmfr.cl:929-960
+        const int dx = i & 1, dy = i >> 1;
+        const bool ok_y = dy ? (piy < P.H - 1) : (piy >= 0);
+        const bool ok_x = dx ? (pix < P.W - 1) : (pix >= 0);
+        if (ok_x && ok_y) {
+            const int sy = piy + dy;
+            if (STRIP && (sy < P.row0 || sy >= P.row1)) {
+                *P.oob_flag = 1;
+                continue;
+            }
+            const f3 pc = ldf3<WIDE>(P.result_prev, pix_index(P, pix + dx, sy));
+            prev.x = fmaf(w[i], pc.x, prev.x);
+            prev.y = fmaf(w[i], pc.y, prev.y);
+            prev.z = fmaf(w[i], pc.z, prev.z);
+            total += w[i];
+        }
+    }
+    const float inv = fast_rcp(total);  // 0 * inf = NaN on the image edge like the 0/0 of bmfr.cl:962
+    hist = to_ycocg(make_f3(prev.x * inv, prev.y * inv, prev.z * inv));
+    return true;
+}
+
+// weighted_sum -> accumulate_filtered_data -> tone map of image pixel (x,y) into halo cell (hx,hy);
+// with `own` also the pixel's TAA history sample (returns whether it takes the temporal path)
+template <bool STRIP, bool WIDE>
+__device__ __forceinline__ bool phase_a_pixel(PostShared& sh, const KParams& P, const float* cf, int hx, int hy, int x, int y,
+                                              bool store, bool own, f3& hist) {
     const unsigned int lp = pix_index(P, x, y);
     const f3 n = ldf3<WIDE>(P.cur_normals, lp), p = ldf3<WIDE>(P.cur_positions, lp), alb = ldf3<WIDE>(P.albedo, lp);
     const unsigned int accept = __ldg(P.accept + lp);
     const unsigned int spp = __ldg(const_cast<const unsigned char*>(P.cur_spp) + lp);
     const float2 pp = __ldg(P.prev_pixels + lp);
     const f3 filtered = weighted_sum_px(n, p, cf);
+    const bool temporal = own && history_sample<STRIP, WIDE>(P, pp, hist);
     const f3 tone = accumulate_filtered_px<STRIP, WIDE>(P, lp, filtered, accept, pp, spp, alb, store);
     put_ycc(sh, P, hx, hy, x, y, to_ycocg(tone));
+    return temporal;
 }
 
 #ifndef BMFR_POST_WIDE_ACCESS
@@ -198,10 +238,18 @@ __global__ void __launch_bounds__(256, BMFR_POST_MIN_BLOCKS) post_kernel(const _
     const int x = x0 + lane;
     const bool col_ok = x >= 0 && x < P.W;
     // phase A, interior: column strip x, rows 4*warp .. 4*warp+3
+    f3 hist[4];
+    unsigned int live = 0;  // bit s: pixel s is written; bit 4+s: it takes the temporal path
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
         const int ty = 4 * warp + s, y = y0 + ty;
-        if (col_ok && y >= P.py0 && y < P.py1) phase_a_pixel<STRIP, WIDE>(sh, P, sh.coef[4], lane + 1, ty + 1, x, y, true);
+        hist[s] = make_f3(0.f, 0.f, 0.f);
+        if (col_ok && y >= P.py0 && y < P.py1) {
+            const bool own = y >= P.own_y0 && y < P.own_y1;
+            const bool temporal = phase_a_pixel<STRIP, WIDE>(sh, P, sh.coef[4], lane + 1, ty + 1, x, y, true, own, hist[s]);
+            live |= (own ? 1u : 0u) << s;
+            live |= (temporal ? 16u : 0u) << s;
+        }
     }
     // phase A, ring: 4 * 33 = 132 pixels, coefficients of the pixel's own block
     if (tid < 4 * (PT_HALO - 1)) {
@@ -214,52 +262,13 @@ __global__ void __launch_bounds__(256, BMFR_POST_MIN_BLOCKS) post_kernel(const _
         const int rx = x0 + hx - 1, ry = y0 + hy - 1;
         if (rx >= 0 && rx < P.W && ry >= P.py0 && ry < P.py1) {
             const int nb = ((hy == 0) ? 0 : (hy == PT_HALO - 1) ? 6 : 3) + ((hx == 0) ? 0 : (hx == PT_HALO - 1) ? 2 : 1);
-            phase_a_pixel<STRIP, WIDE>(sh, P, sh.coef[nb], hx, hy, rx, ry, false);
+            f3 unused;
+            phase_a_pixel<STRIP, WIDE>(sh, P, sh.coef[nb], hx, hy, rx, ry, false, false, unused);
         }
     }
     __syncthreads();
 
-    // phase B, step 1: history sample of each of the strip's pixels in YCoCg (bmfr.cl:922-965)
-    f3 hist[4];
-    unsigned int live = 0;  // bit s: pixel s is written; bit 4+s: it takes the temporal path
-#pragma unroll
-    for (int s = 0; s < 4; ++s) {
-        const int y = y0 + 4 * warp + s;
-        hist[s] = make_f3(0.f, 0.f, 0.f);
-        if (!(col_ok && y >= P.py0 && y < P.py1 && y >= P.own_y0 && y < P.own_y1)) continue;
-        live |= 1u << s;
-        if (P.frame == 0) continue;
-        const float2 pp = __ldg(P.prev_pixels + pix_index(P, x, y));
-        const int pix = __float2int_rd(pp.x), piy = __float2int_rd(pp.y);
-        if (pix < -1 || piy < -1 || pix >= P.W || piy >= P.H) continue;  // bmfr.cl:884-890
-        live |= 16u << s;
-        const float frx = pp.x - (float)pix, fry = pp.y - (float)piy;
-        const float omx = 1.f - frx, omy = 1.f - fry;
-        const float w[4] = {omx * omy, frx * omy, omx * fry, frx * fry};
-        f3 prev = make_f3(0.f, 0.f, 0.f);
-        float total = 0.f;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {  // bmfr.cl:929-960
-            const int dx = i & 1, dy = i >> 1;
-            const bool ok_y = dy ? (piy < P.H - 1) : (piy >= 0);
-            const bool ok_x = dx ? (pix < P.W - 1) : (pix >= 0);
-            if (ok_x && ok_y) {
-                const int sy = piy + dy;
-                if (STRIP && (sy < P.row0 || sy >= P.row1)) {
-                    *P.oob_flag = 1;
-                    continue;
-                }
-                const f3 pc = ldf3<WIDE>(P.result_prev, pix_index(P, pix + dx, sy));
-                prev.x = fmaf(w[i], pc.x, prev.x);
-                prev.y = fmaf(w[i], pc.y, prev.y);
-                prev.z = fmaf(w[i], pc.z, prev.z);
-                total += w[i];
-            }
-        }
-        const float inv = fast_rcp(total);  // 0 * inf = NaN on the image edge like the 0/0 of bmfr.cl:962
-        hist[s] = to_ycocg(make_f3(prev.x * inv, prev.y * inv, prev.z * inv));
-    }
-    // step 2: clamp to the neighbourhood box, plane by plane (bmfr.cl:893-920, 967-969).  Halo rows
+    // phase B: clamp the history samples to the neighbourhood box, plane by plane (bmfr.cl:893-920, 967-969).  Halo rows
     // 4*warp .. 4*warp+5 cover the 3x3 neighbourhoods of the strip; this thread's column is lane+1.
     f3 mine[4];
 #pragma unroll
