@@ -213,7 +213,7 @@ __device__ __forceinline__ bool phase_a_pixel(PostShared& sh, const KParams& P, 
 #define BMFR_POST_WIDE_ACCESS 0
 #endif
 #ifndef BMFR_POST_MIN_BLOCKS
-#define BMFR_POST_MIN_BLOCKS 4
+#define BMFR_POST_MIN_BLOCKS 5
 #endif
 
 template <bool STRIP, bool WIDE>
