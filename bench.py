@@ -72,20 +72,59 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md)."""
+    """SM clock and throttle reasons while the timed region runs (B200_PROFILING.md), polled through NVML
+    every 2 ms from a helper thread (nvidia-smi -lms 100 as the fallback when NVML is not importable)."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index=0):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.stop, self.thread, self.source = index, [], None, False, None, None
+
+    def _nvml_loop(self, nv, handle):
+        bits = [(getattr(nv, n, 0), name) for n, name in (
+            ("nvmlClocksEventReasonHwSlowdown", "hw_slowdown"), ("nvmlClocksEventReasonHwThermalSlowdown", "hw_thermal_slowdown"),
+            ("nvmlClocksEventReasonSwThermalSlowdown", "sw_thermal_slowdown"), ("nvmlClocksEventReasonSwPowerCap", "sw_power_cap"))]
+        if not any(b for b, _ in bits):  # older binding names
+            bits = [(getattr(nv, n, 0), name) for n, name in (
+                ("nvmlClocksThrottleReasonHwSlowdown", "hw_slowdown"), ("nvmlClocksThrottleReasonHwThermalSlowdown", "hw_thermal_slowdown"),
+                ("nvmlClocksThrottleReasonSwThermalSlowdown", "sw_thermal_slowdown"), ("nvmlClocksThrottleReasonSwPowerCap", "sw_power_cap"))]
+        mx = nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM)
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)
+                r = get_reasons(handle)
+                self.rows.append([str(sm), str(mx)] + ["Active" if (b and (r & b)) else "Not Active" for b, _ in bits])
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def __enter__(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            idx = self.index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.index])
+                except Exception:
+                    pass
+            handle = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, handle), daemon=True)
+            self.thread.start()
+            self.source = "nvml, 2 ms"
+            return self
+        except Exception:
+            self.thread = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            self.source = "nvidia-smi -lms 100"
         except Exception:
             self.proc = None
         return self
@@ -95,6 +134,9 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def __exit__(self, *a):
+        self.stop = True
+        if self.thread:
+            self.thread.join(timeout=1)
         if self.proc:
             time.sleep(0.15)
             self.proc.terminate()
@@ -105,17 +147,16 @@ class ClockSampler:
 
     def summary(self):
         sm, mx, reasons = [], 0.0, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             try:
                 sm.append(float(r[0])); mx = max(mx, float(r[1]))
-                for n, v in zip(names, r[2:6]):
+                for n, v in zip(self.NAMES, r[2:6]):
                     if v.lower().startswith("active"):
                         reasons.add(n)
             except Exception:
                 continue
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": self.source}
 
 
 def host_cores():
@@ -268,8 +309,17 @@ def run_single_gpu(args):
         dp.close()
     own = [k for k in kernels if not k.startswith("total_") and (k in FUSED_KERNELS) == (args.mode == "fused")]
     dom = max(own, key=lambda k: kernels[k]["ms"])
+    # DRAM traffic of the same kernel from the committed ncu --set full capture (profiles/), per launch
+    traffic, traffic_src = None, None
+    try:
+        cap = json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text())
+        if args.mode == "fused" and (w, h) == SINGLE_GPU_WORKLOAD and dom in cap["kernels"]:
+            k = cap["kernels"][dom]
+            traffic, traffic_src = k["dram_bytes_read"] + k["dram_bytes_write"], cap["capture"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                "frac": kernels[dom]["frac"], "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": kernels[dom]["algorithmic_bytes"], "ms_per_launch": kernels[dom]["ms"]}
 
     # end to end through the host-pointer entry of the C ABI: pinned-host inputs, uploads and the
