@@ -87,6 +87,27 @@ __device__ __forceinline__ f3 weighted_sum_px(f3 n, f3 p, const float* __restric
 }
 
 // accumulate_filtered_data for one pixel, bmfr.cl:778-856.  Returns the tone-mapped colour.
+// The same for two pixels of a strip: every coefficient is fetched once and used twice, which halves
+// the shared-memory wavefronts of the weighted sum (a warp-wide 128-bit broadcast is four wavefronts).
+__device__ __forceinline__ void weighted_sum_px2(f3 n0, f3 p0, f3 n1, f3 p1, const float* __restrict__ cf, f3& out0, f3& out1) {
+    const float4* c4 = reinterpret_cast<const float4*>(cf);
+    const float4 m0 = c4[10], m1 = c4[11], m2 = c4[12];
+    const float f0[BMFR_FEATURES - 1] = {n0.x, n0.y, n0.z, (p0.x - m0.x) * m0.y, (p0.y - m0.z) * m0.w, (p0.z - m1.x) * m1.y,
+                                         (p0.x * p0.x - m1.z) * m1.w, (p0.y * p0.y - m2.x) * m2.y, (p0.z * p0.z - m2.z) * m2.w};
+    const float f1[BMFR_FEATURES - 1] = {n1.x, n1.y, n1.z, (p1.x - m0.x) * m0.y, (p1.y - m0.z) * m0.w, (p1.z - m1.x) * m1.y,
+                                         (p1.x * p1.x - m1.z) * m1.w, (p1.y * p1.y - m2.x) * m2.y, (p1.z * p1.z - m2.z) * m2.w};
+    const float4 w0 = c4[0];
+    f3 a = make_f3(w0.x, w0.y, w0.z), b = a;
+#pragma unroll
+    for (int f = 1; f < BMFR_FEATURES; ++f) {
+        const float4 w = c4[f];
+        a.x = fmaf(w.x, f0[f - 1], a.x); a.y = fmaf(w.y, f0[f - 1], a.y); a.z = fmaf(w.z, f0[f - 1], a.z);
+        b.x = fmaf(w.x, f1[f - 1], b.x); b.y = fmaf(w.y, f1[f - 1], b.y); b.z = fmaf(w.z, f1[f - 1], b.z);
+    }
+    out0 = make_f3(a.x < 0.f ? 0.f : a.x, a.y < 0.f ? 0.f : a.y, a.z < 0.f ? 0.f : a.z);  // keeps NaN, bmfr.cl:750
+    out1 = make_f3(b.x < 0.f ? 0.f : b.x, b.y < 0.f ? 0.f : b.y, b.z < 0.f ? 0.f : b.z);
+}
+
 // accept / pp / spp / alb are this pixel's accept mask, previous-frame position, sample count and
 // albedo, fetched by the caller together with the features (one round of independent loads).
 template <bool STRIP, bool WIDE>
@@ -194,19 +215,36 @@ __device__ __forceinline__ bool history_sample(const KParams& P, float2 pp, f3& 
 
 // weighted_sum -> accumulate_filtered_data -> tone map of image pixel (x,y) into halo cell (hx,hy);
 // with `own` also the pixel's TAA history sample (returns whether it takes the temporal path)
+struct PixelIn {  // everything phase A reads at the pixel itself: one round of independent loads
+    f3 n, p, alb;
+    float2 pp;
+    unsigned int lp, accept, spp;
+};
+template <bool WIDE>
+__device__ __forceinline__ PixelIn load_pixel(const KParams& P, int x, int y) {
+    PixelIn in;
+    in.lp = pix_index(P, x, y);
+    in.n = ldf3<WIDE>(P.cur_normals, in.lp);
+    in.p = ldf3<WIDE>(P.cur_positions, in.lp);
+    in.alb = ldf3<WIDE>(P.albedo, in.lp);
+    in.accept = __ldg(P.accept + in.lp);
+    in.spp = __ldg(const_cast<const unsigned char*>(P.cur_spp) + in.lp);
+    in.pp = __ldg(P.prev_pixels + in.lp);
+    return in;
+}
+template <bool STRIP, bool WIDE>
+__device__ __forceinline__ bool finish_pixel(PostShared& sh, const KParams& P, const PixelIn& in, f3 filtered, int hx, int hy, int x,
+                                             int y, bool store, bool own, f3& hist) {
+    const bool temporal = own && history_sample<STRIP, WIDE>(P, in.pp, hist);
+    const f3 tone = accumulate_filtered_px<STRIP, WIDE>(P, in.lp, filtered, in.accept, in.pp, in.spp, in.alb, store);
+    put_ycc(sh, P, hx, hy, x, y, to_ycocg(tone));
+    return temporal;
+}
 template <bool STRIP, bool WIDE>
 __device__ __forceinline__ bool phase_a_pixel(PostShared& sh, const KParams& P, const float* cf, int hx, int hy, int x, int y,
                                               bool store, bool own, f3& hist) {
-    const unsigned int lp = pix_index(P, x, y);
-    const f3 n = ldf3<WIDE>(P.cur_normals, lp), p = ldf3<WIDE>(P.cur_positions, lp), alb = ldf3<WIDE>(P.albedo, lp);
-    const unsigned int accept = __ldg(P.accept + lp);
-    const unsigned int spp = __ldg(const_cast<const unsigned char*>(P.cur_spp) + lp);
-    const float2 pp = __ldg(P.prev_pixels + lp);
-    const f3 filtered = weighted_sum_px(n, p, cf);
-    const bool temporal = own && history_sample<STRIP, WIDE>(P, pp, hist);
-    const f3 tone = accumulate_filtered_px<STRIP, WIDE>(P, lp, filtered, accept, pp, spp, alb, store);
-    put_ycc(sh, P, hx, hy, x, y, to_ycocg(tone));
-    return temporal;
+    const PixelIn in = load_pixel<WIDE>(P, x, y);
+    return finish_pixel<STRIP, WIDE>(sh, P, in, weighted_sum_px(in.n, in.p, cf), hx, hy, x, y, store, own, hist);
 }
 
 #ifndef BMFR_POST_WIDE_ACCESS
@@ -241,14 +279,27 @@ __global__ void __launch_bounds__(256, BMFR_POST_MIN_BLOCKS) post_kernel(const _
     f3 hist[4];
     unsigned int live = 0;  // bit s: pixel s is written; bit 4+s: it takes the temporal path
 #pragma unroll
-    for (int s = 0; s < 4; ++s) {
+    for (int s = 0; s < 4; s += 2) {  // two pixels at a time: they share the coefficient loads
         const int ty = 4 * warp + s, y = y0 + ty;
-        hist[s] = make_f3(0.f, 0.f, 0.f);
-        if (col_ok && y >= P.py0 && y < P.py1) {
+        hist[s] = hist[s + 1] = make_f3(0.f, 0.f, 0.f);
+        const bool v0 = col_ok && y >= P.py0 && y < P.py1, v1 = col_ok && y + 1 >= P.py0 && y + 1 < P.py1;
+        if (v0 && v1) {
+            const PixelIn i0 = load_pixel<WIDE>(P, x, y), i1 = load_pixel<WIDE>(P, x, y + 1);
+            f3 fl0, fl1;
+            weighted_sum_px2(i0.n, i0.p, i1.n, i1.p, sh.coef[4], fl0, fl1);
+            const bool own0 = y >= P.own_y0 && y < P.own_y1, own1 = y + 1 >= P.own_y0 && y + 1 < P.own_y1;
+            const bool t0 = finish_pixel<STRIP, WIDE>(sh, P, i0, fl0, lane + 1, ty + 1, x, y, true, own0, hist[s]);
+            const bool t1 = finish_pixel<STRIP, WIDE>(sh, P, i1, fl1, lane + 1, ty + 2, x, y + 1, true, own1, hist[s + 1]);
+            live |= ((own0 ? 1u : 0u) | (t0 ? 16u : 0u)) << s;
+            live |= ((own1 ? 1u : 0u) | (t1 ? 16u : 0u)) << (s + 1);
+        } else if (v0) {  // a strip or image edge cuts the pair
             const bool own = y >= P.own_y0 && y < P.own_y1;
-            const bool temporal = phase_a_pixel<STRIP, WIDE>(sh, P, sh.coef[4], lane + 1, ty + 1, x, y, true, own, hist[s]);
-            live |= (own ? 1u : 0u) << s;
-            live |= (temporal ? 16u : 0u) << s;
+            const bool t = phase_a_pixel<STRIP, WIDE>(sh, P, sh.coef[4], lane + 1, ty + 1, x, y, true, own, hist[s]);
+            live |= ((own ? 1u : 0u) | (t ? 16u : 0u)) << s;
+        } else if (v1) {
+            const bool own = y + 1 >= P.own_y0 && y + 1 < P.own_y1;
+            const bool t = phase_a_pixel<STRIP, WIDE>(sh, P, sh.coef[4], lane + 1, ty + 2, x, y + 1, true, own, hist[s + 1]);
+            live |= ((own ? 1u : 0u) | (t ? 16u : 0u)) << (s + 1);
         }
     }
     // phase A, ring: 4 * 33 = 132 pixels, coefficients of the pixel's own block
