@@ -35,6 +35,7 @@ template <bool WIDE>
 __device__ __forceinline__ f3 ldf3(const float* __restrict__ b, unsigned int i) {
     return WIDE ? load_f3_wide(b, i) : load_f3(b, i);
 }
+
 template <bool WIDE>
 __device__ __forceinline__ void stf3(float* __restrict__ b, unsigned int i, f3 v) {
     if (WIDE) store_f3_wide(b, i, v);
