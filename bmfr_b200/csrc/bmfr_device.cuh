@@ -51,6 +51,35 @@ __device__ __forceinline__ void store_f3_wide(float* __restrict__ b, unsigned in
 __device__ __forceinline__ float dot3(f3 a, f3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
 __device__ __forceinline__ f3 sub3(f3 a, f3 b) { return f3{a.x - b.x, a.y - b.y, a.z - b.z}; }
 
+// Packed fp32 pairs (sm_100 FFMA2 / FADD2 / FMUL2): one issue slot for two IEEE-rounded operations.  Each
+// half is the same round-to-nearest operation as the scalar instruction.  CAUTION for code that must
+// match the oracle bit for bit: ptxas 12.9 contracts mul.rn.f32x2 followed by add/sub.rn.f32x2 into
+// FFMA2 even with --fmad=false (it honours .rn only for scalars; checked with cuobjdump), so a product
+// that feeds a sum must be a scalar __fmul_rn; packed sums of scalar products are not contracted.
+__device__ __forceinline__ unsigned long long f2_bits(float2 v) { return *reinterpret_cast<unsigned long long*>(&v); }
+__device__ __forceinline__ float2 bits_f2(unsigned long long b) { return *reinterpret_cast<float2*>(&b); }
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)), "l"(f2_bits(c)));
+    return bits_f2(d);
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+    return bits_f2(d);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+    return bits_f2(d);
+}
+__device__ __forceinline__ float2 fsub2(float2 a, float2 b) {
+    unsigned long long d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+    return bits_f2(d);
+}
+__device__ __forceinline__ float2 dup2(float v) { return make_float2(v, v); }
+
 __device__ __forceinline__ unsigned int pix_index(const KParams& P, int x, int y) {
     return (unsigned int)((y - P.row0) * P.W + x);
 }
@@ -108,21 +137,25 @@ __device__ __forceinline__ K1Pixel k1_pixel(const KParams& P, int x, int y) {
 
     if (P.frame > 0) {
         const float* M = P.cam;
-        // dot(M.s048c, (p,1)) etc., left to right; bmfr.cl:343-349
-        float cx = ((M[0] * wp.x + M[4] * wp.y) + M[8] * wp.z) + M[12] * 1.f;
-        float cy = ((M[1] * wp.x + M[5] * wp.y) + M[9] * wp.z) + M[13] * 1.f;
+        // dot(M.s048c, (p,1)) etc., left to right; bmfr.cl:343-349.  The sums of x and y share packed
+        // additions; the products stay scalar (see the caution above): every operation is the IEEE
+        // operation of the reference expression, in the same order.
+        float2 cxy = fadd2(make_float2(__fmul_rn(M[0], wp.x), __fmul_rn(M[1], wp.x)),
+                           make_float2(__fmul_rn(M[4], wp.y), __fmul_rn(M[5], wp.y)));
+        cxy = fadd2(cxy, make_float2(__fmul_rn(M[8], wp.z), __fmul_rn(M[9], wp.z)));
+        cxy = fadd2(cxy, make_float2(M[12], M[13]));  // M * 1.f
         const float cw = ((M[3] * wp.x + M[7] * wp.y) + M[11] * wp.z) + M[15] * 1.f;
-        cx = cx / cw;
-        cy = cy / cw;
-        cx = (cx + 1.f) / 2.f;
-        cy = (cy + 1.f) / 2.f;
-        pfx = cx * (float)P.W - P.poff_x;  // bmfr.cl:352-355
-        pfy = cy * (float)P.H - P.poff_y1;
+        cxy = make_float2(cxy.x / cw, cxy.y / cw);
+        cxy = fmul2(fadd2(cxy, dup2(1.f)), dup2(0.5f));  // (c + 1) / 2: a division by 2 is the exact product with 0.5
+        const float2 pf = fsub2(make_float2(__fmul_rn(cxy.x, (float)P.W), __fmul_rn(cxy.y, (float)P.H)),
+                                make_float2(P.poff_x, P.poff_y1));  // bmfr.cl:352-355
+        pfx = pf.x;
+        pfy = pf.y;
         const int pix = __float2int_rd(pfx);  // convert_int2_rtn, bmfr.cl:356
         const int piy = __float2int_rd(pfy);
-        const float frx = pfx - (float)pix, fry = pfy - (float)piy;
-        const float omx = 1.f - frx, omy = 1.f - fry;
-        const float w[4] = {omx * omy, frx * omy, omx * fry, frx * fry};  // bmfr.cl:367-370
+        const float2 fr = fsub2(pf, make_float2((float)pix, (float)piy));
+        const float2 om = fsub2(dup2(1.f), fr);
+        const float w[4] = {om.x * om.y, fr.x * om.y, om.x * fr.y, fr.x * fr.y};  // bmfr.cl:367-370
         float total = 0.f;
         // The four taps are fetched unconditionally from clamped addresses (one round of independent
         // loads instead of three dependent ones) and the reference's nested tests (bmfr.cl:380-404)
@@ -147,20 +180,28 @@ __device__ __forceinline__ K1Pixel k1_pixel(const KParams& P, int x, int y) {
             tc[i] = load_f3(P.prev_noisy_acc, ls);
             ts[i] = (float)__ldg(P.prev_spp + ls);
         }
+        // position and normal differences ride in the two halves of a pair (bmfr.cl:388-404);
+        // (sample_spp, prev.x) and (prev.y, prev.z) are accumulated as pairs (bmfr.cl:407-415)
+        const float2 refx = make_float2(wp.x, n.x), refy = make_float2(wp.y, n.y), refz = make_float2(wp.z, n.z);
+        float2 acc_sx = make_float2(0.f, 0.f), acc_yz = make_float2(0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const f3 pd = sub3(tp[i], wp);
-            const f3 nd = sub3(tn[i], n);
-            const bool ok = valid[i] && (dot3(pd, pd) < P.pos_limit) && (dot3(nd, nd) < P.nrm_limit);  // bmfr.cl:388-404
+            const float2 dx = fsub2(make_float2(tp[i].x, tn[i].x), refx);
+            const float2 dy = fsub2(make_float2(tp[i].y, tn[i].y), refy);
+            const float2 dz = fsub2(make_float2(tp[i].z, tn[i].z), refz);
+            const float2 d2 = fadd2(fadd2(make_float2(__fmul_rn(dx.x, dx.x), __fmul_rn(dx.y, dx.y)),
+                                          make_float2(__fmul_rn(dy.x, dy.x), __fmul_rn(dy.y, dy.y))),
+                                    make_float2(__fmul_rn(dz.x, dz.x), __fmul_rn(dz.y, dz.y)));  // (|dp|^2, |dn|^2), dot left to right
+            const bool ok = valid[i] && (d2.x < P.pos_limit) && (d2.y < P.nrm_limit);
             if (ok) {
                 accept |= 1u << i;
-                sample_spp = sample_spp + w[i] * ts[i];
-                prev.x = prev.x + w[i] * tc[i].x;
-                prev.y = prev.y + w[i] * tc[i].y;
-                prev.z = prev.z + w[i] * tc[i].z;
+                acc_sx = fadd2(acc_sx, make_float2(__fmul_rn(w[i], ts[i]), __fmul_rn(w[i], tc[i].x)));
+                acc_yz = fadd2(acc_yz, make_float2(__fmul_rn(w[i], tc[i].y), __fmul_rn(w[i], tc[i].z)));
                 total = total + w[i];
             }
         }
+        sample_spp = acc_sx.x;
+        prev = make_f3(acc_sx.y, acc_yz.x, acc_yz.y);
         if (total > 0.f) {  // bmfr.cl:421-429
             prev.x = prev.x / total;
             prev.y = prev.y / total;
@@ -181,8 +222,9 @@ __device__ __forceinline__ K1Pixel k1_pixel(const KParams& P, int x, int y) {
         }
     }
     const float oma = 1.f - blend_alpha;
-    r.new_color = make_f3(blend_alpha * cur.x + oma * prev.x, blend_alpha * cur.y + oma * prev.y,
-                          blend_alpha * cur.z + oma * prev.z);  // bmfr.cl:444-445
+    const float2 nxy = fadd2(make_float2(__fmul_rn(blend_alpha, cur.x), __fmul_rn(blend_alpha, cur.y)),
+                             make_float2(__fmul_rn(oma, prev.x), __fmul_rn(oma, prev.y)));
+    r.new_color = make_f3(nxy.x, nxy.y, blend_alpha * cur.z + oma * prev.z);  // bmfr.cl:444-445
     r.normal = n;
     r.position = wp;
     r.prev_x = pfx;

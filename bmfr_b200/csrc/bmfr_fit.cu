@@ -68,26 +68,6 @@ __device__ __forceinline__ float rsqrt_approx(float v) {
     return r;
 }
 
-// Packed fp32 pairs (sm_100 FFMA2 / FADD2 / FMUL2): one issue slot for two IEEE-rounded operations.
-// The level-1 factorisation keeps two matrix rows per 64-bit register pair.
-__device__ __forceinline__ unsigned long long f2_bits(float2 v) { return *reinterpret_cast<unsigned long long*>(&v); }
-__device__ __forceinline__ float2 bits_f2(unsigned long long b) { return *reinterpret_cast<float2*>(&b); }
-__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
-    unsigned long long d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)), "l"(f2_bits(c)));
-    return bits_f2(d);
-}
-__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
-    unsigned long long d;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)));
-    return bits_f2(d);
-}
-__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
-    unsigned long long d;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)));
-    return bits_f2(d);
-}
-
 #define QR_RED_STRIDE 36  // floats per column of the transpose buffer: 16-byte aligned rows, bank-shifted
 
 // Sum over the 32 lanes of N per-lane values (one per remaining column): every lane stores its N
