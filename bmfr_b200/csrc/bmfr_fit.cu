@@ -27,10 +27,17 @@
 // (bmfr.cl:314-325) and store nothing per pixel (bmfr.cl:478), so the image pixels are the whole
 // job; the fit re-derives margin rows from these outputs.
 // --------------------------------------------------------------------------------------------
+#ifndef BMFR_REPROJECT_MIN_BLOCKS
+#define BMFR_REPROJECT_MIN_BLOCKS 4
+#endif
+#ifndef BMFR_REPROJECT_BX
+#define BMFR_REPROJECT_BX 32  // CTA = BX x (256 / BX) pixels
+#endif
+#define BMFR_REPROJECT_BY (256 / BMFR_REPROJECT_BX)
 template <bool STRIP>
-__global__ void __launch_bounds__(256, 4) reproject_kernel(const __grid_constant__ KParams P) {
-    const int x = blockIdx.x * 32 + threadIdx.x;
-    const int y = P.k1_y0 + blockIdx.y * 8 + threadIdx.y;
+__global__ void __launch_bounds__(256, BMFR_REPROJECT_MIN_BLOCKS) reproject_kernel(const __grid_constant__ KParams P) {
+    const int x = blockIdx.x * BMFR_REPROJECT_BX + threadIdx.x;
+    const int y = P.k1_y0 + blockIdx.y * BMFR_REPROJECT_BY + threadIdx.y;
     if (x >= P.W || y >= P.k1_y1) return;
     if (STRIP && (y < P.row0 || y >= P.row1)) {
         *P.oob_flag = 1;
@@ -757,7 +764,8 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
 static bool is_strip(const KParams& P) { return P.row0 != 0 || P.row1 != P.H; }
 
 cudaError_t launch_reproject(const KParams& P, cudaStream_t st) {
-    const dim3 grid((P.W + 31) / 32, (P.k1_y1 - P.k1_y0 + 7) / 8), block(32, 8);
+    const dim3 grid((P.W + BMFR_REPROJECT_BX - 1) / BMFR_REPROJECT_BX, (P.k1_y1 - P.k1_y0 + BMFR_REPROJECT_BY - 1) / BMFR_REPROJECT_BY),
+        block(BMFR_REPROJECT_BX, BMFR_REPROJECT_BY);
     if (is_strip(P)) reproject_kernel<true><<<grid, block, 0, st>>>(P);
     else reproject_kernel<false><<<grid, block, 0, st>>>(P);
     return cudaGetLastError();

@@ -187,6 +187,17 @@ int bmfr_create(const bmfr_params* params, bmfr_ctx** out_ctx) {
     if (p.width < BMFR_BLOCK_EDGE || p.height < BMFR_BLOCK_EDGE)
         return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_create: image %dx%d smaller than one 32x32 block",
                               p.width, p.height);
+    // mirror() "works only if index is less than one size out of bounds" (bmfr.cl:207-208): the margin grid
+    // reaches WORKSET + 29 pixels, which must still mirror into the image.  The reference reads out of
+    // bounds for such sizes; this library refuses them.
+    {
+        const int ww = BMFR_BLOCK_EDGE * ((p.width + BMFR_BLOCK_EDGE - 1) / BMFR_BLOCK_EDGE);
+        const int hw = BMFR_BLOCK_EDGE * ((p.height + BMFR_BLOCK_EDGE - 1) / BMFR_BLOCK_EDGE);
+        if (ww + 29 > 2 * p.width - 1 || hw + 29 > 2 * p.height - 1)
+            return bmfr_set_error(BMFR_ERR_UNSUPPORTED,
+                                  "bmfr_create: image %dx%d: the 32-pixel margin of the block grid cannot be mirrored into the "
+                                  "image (needs 2*size - 1 >= workset + 29, bmfr.cl:207-216)", p.width, p.height);
+    }
     if (p.mode != BMFR_MODE_STAGED && p.mode != BMFR_MODE_FUSED)
         return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_create: unknown mode %d", p.mode);
     if (p.tmp_half != 0)

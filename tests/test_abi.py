@@ -71,3 +71,15 @@ def test_invalid_arguments(lib):
     p.tmp_half = 1
     assert lib.bmfr_create(C.byref(p), C.byref(h)) in (-5, -2)
     assert lib.bmfr_sync(None) == -1
+
+
+def test_unmirrorable_geometry_is_refused(lib):
+    """mirror() only folds indices less than one image size out of bounds (bmfr.cl:207-208); sizes whose
+    32-pixel block margin reaches further (e.g. 33x40: workset 64x64) make the reference read out of bounds
+    and are refused here before any device is touched."""
+    for w, h in ((33, 40), (40, 100), (100, 40)):
+        p = _lib.Params()
+        lib.bmfr_default_params(C.byref(p), w, h)
+        hnd = C.c_void_p()
+        assert lib.bmfr_create(C.byref(p), C.byref(hnd)) == -5, (w, h)
+        assert b"mirrored" in lib.bmfr_last_error()

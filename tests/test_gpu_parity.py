@@ -41,6 +41,45 @@ def test_sequence_matches_oracle(mode, size):
     print(f"{mode} {w}x{h}: worst rel {worst['rel']:.2e}, worst PSNR {worst['psnr']:.1f} dB")
 
 
+@pytest.mark.parametrize("size", [(32, 32), (48, 47), (64, 64), (97, 75), (98, 70), (132, 100)])
+def test_fused_edge_geometries(size):
+    """One-block images, odd widths, widths that are not multiples of 4 (the TMA tile path of the fit needs
+    W % 4 == 0 and falls back to per-pixel loads otherwise) — every block offset of the 16-entry table."""
+    w, h = size
+    ref = util.run_oracle("port", w, h, 17, keep=KEEP_FUSED)
+    cuda = util.run_cuda(w, h, 17, mode="fused", keep=KEEP_FUSED)
+    _check_frames(cuda, ref, False)
+
+
+def test_nan_and_far_inputs_follow_the_oracle():
+    """NaN normals / positions are scrubbed before the fit (bmfr.cl:468-469) but not in the weighted sum
+    (bmfr.cl:725-750): the NaN pattern of every colour buffer must be the oracle's."""
+    w, h, frames = 160, 96, 4
+    seq = list(util.sequence(w, h, frames))
+    rng = np.random.default_rng(7)
+    ys, xs = rng.integers(0, h, 40), rng.integers(0, w, 40)
+    for k, (f, a, n, p, c, cam, off) in enumerate(seq):
+        n, p = n.copy(), p.copy()
+        n[ys[:20], xs[:20], 0] = np.nan
+        p[ys[20:], xs[20:], 1] = np.nan
+        seq[k] = (f, a, n, p, c, cam, off)
+    from bmfr_b200 import Denoiser, synth
+    from oracle.oracle import Oracle
+    pl, nl = synth.limits()
+    o = Oracle("port", w, h, position_limit_squared=pl, normal_limit_squared=nl, keep_tmp=0)
+    with Denoiser(w, h, mode="fused") as d:
+        for fr in seq:
+            o.frame(*fr)
+            d.denoise_frame_host(*fr)
+            for k in util.INTEGER_BUFFERS:
+                assert util.bits_equal(d.read(k), o.buffer(k)), k
+            r_c, r_o = d.read("result"), o.buffer("result")
+            assert np.array_equal(np.isnan(r_c), np.isnan(r_o)), f"frame {fr[0]}: NaN pattern of result differs"
+            m = ~np.isnan(r_o)
+            util.assert_colour_close(np.where(m, r_c, 0), np.where(m, r_o, 0), f"frame {fr[0]} result")
+    o.close()
+
+
 def test_jittered_offsets_match_oracle():
     ref = util.run_oracle("port", 200, 120, 8, keep=KEEP_FUSED, jitter=True)
     cuda = util.run_cuda(200, 120, 8, mode="fused", keep=KEEP_FUSED, jitter=True)
