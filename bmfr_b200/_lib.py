@@ -64,6 +64,9 @@ SYMBOLS = {
     "bmfr_get_fused_kernel_ms": (_I, [_P, _I, _F]),
     "bmfr_kernel_launches": (C.c_longlong, [_P]),
     "bmfr_get_halo_plan": (_I, [_P, _I, C.POINTER(HaloPlan)]),
+    "bmfr_halo_export": (_I, [_P, _P, C.c_size_t]),
+    "bmfr_halo_connect": (_I, [_P, _I, _P, C.c_size_t]),
+    "bmfr_halo_connect_local": (_I, [_P, _I, _P]),
     "bmfr_synth_camera": (None, [_I, _I, _I, _I, _F, _F]),
     "bmfr_synth_limits": (None, [_F, _F]),
     "bmfr_synth_frame_host": (_I, [_I, _I, _I, _I, _I, C.c_uint, _P, _P, _P, _P]),

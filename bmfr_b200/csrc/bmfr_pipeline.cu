@@ -4,6 +4,7 @@
 // and the per-kernel event timers (:386-397,488-506).  The arithmetic lives in bmfr_kernels.cu.
 #include <cuda_runtime.h>
 #include <stdarg.h>
+#include <stdint.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -100,6 +101,19 @@ struct bmfr_ctx {
     bool host_ready = false;
 
     std::vector<StageEvents> prof;
+
+    // peer-to-peer halo exchange (sharded contexts): the neighbour above (side 0) / below (side 1)
+    struct Peer {
+        bool connected = false, ipc = false;
+        int row0 = 0, row1 = 0, own_y0 = 0, own_y1 = 0;    // the neighbour's geometry
+        float* noisy_acc[2] = {nullptr, nullptr};          // its state buffers (peer-mapped), by physical index
+        unsigned char* spp[2] = {nullptr, nullptr};
+        float* accum[2] = {nullptr, nullptr};
+        float* result[2] = {nullptr, nullptr};
+        unsigned int* flags = nullptr;                     // its flag pair; this context signals flags[1 - side]
+    } peer[2];
+    unsigned int* d_flags = nullptr;   // [0]: frames completed by the neighbour above, [1]: below; [2]: wait timed out
+    long long seq = 0;                 // frames submitted on this context
 };
 
 static size_t rows_of(const bmfr_ctx* c) { return (size_t)(c->geo.row1 - c->geo.row0); }
@@ -135,6 +149,17 @@ static void free_ctx(bmfr_ctx* c) {
     cudaFree(c->noise);
     cudaFree(c->noise_f);
     cudaFree(c->d_oob);
+    for (int side = 0; side < 2; ++side) {
+        bmfr_ctx::Peer& pr = c->peer[side];
+        if (pr.connected && pr.ipc) {
+            for (int i = 0; i < 2; ++i) {
+                cudaIpcCloseMemHandle(pr.noisy_acc[i]); cudaIpcCloseMemHandle(pr.spp[i]);
+                cudaIpcCloseMemHandle(pr.accum[i]); cudaIpcCloseMemHandle(pr.result[i]);
+            }
+            cudaIpcCloseMemHandle(pr.flags);
+        }
+    }
+    cudaFree(c->d_flags);
     for (int k = 0; k < 4; ++k)
         for (int s = 0; s < kHostSlots; ++s) cudaFree(c->up[k][s]);
     for (int s = 0; s < kHostSlots; ++s) {
@@ -267,6 +292,7 @@ int bmfr_create(const bmfr_params* params, bmfr_ctx** out_ctx) {
     if (st == 0) st = dev_alloc(&c->noise, (size_t)(BMFR_FEATURES - 1) * BMFR_BLOCK_PIXELS, "noise");
     if (st == 0) st = dev_alloc(&c->noise_f, (size_t)(BMFR_FEATURES - 1) * BMFR_BLOCK_PIXELS, "noise_f");
     if (st == 0) st = dev_alloc(&c->d_oob, 2, "oob flag + block counter");
+    if (st == 0) st = dev_alloc(&c->d_flags, 4, "halo flags");
     if (st == 0 && p.mode == BMFR_MODE_STAGED) {
         st = dev_alloc(&c->tmp_data, (size_t)c->tmp_block_rows * g.blocks_x * BMFR_BUFFER_COUNT * BMFR_BLOCK_PIXELS, "tmp_data");
         if (st == 0) st = dev_alloc(&c->filtered, npix * 3, "filtered");
@@ -274,6 +300,7 @@ int bmfr_create(const bmfr_params* params, bmfr_ctx** out_ctx) {
     }
     if (st != 0) return fail(st);
     if ((st = bmfr_check_cuda(cudaMemsetAsync(c->d_oob, 0, sizeof(int), c->stream), "memset")) != 0) return fail(st);
+    if ((st = bmfr_check_cuda(cudaMemsetAsync(c->d_flags, 0, 4 * sizeof(unsigned int), c->stream), "memset")) != 0) return fail(st);
     // weights of blocks a strip never fits stay defined
     if ((st = bmfr_check_cuda(cudaMemsetAsync(c->weights, 0, nb * BMFR_FEATURES * 3 * sizeof(float), c->stream), "memset")) != 0) return fail(st);
     if ((st = bmfr_check_cuda(cudaMemsetAsync(c->mins_maxs, 0, nb * BMFR_FEATURES_SCALED * 2 * sizeof(float), c->stream), "memset")) != 0) return fail(st);
@@ -390,6 +417,119 @@ static int run_frame(bmfr_ctx* c, const KParams& P, int frame) {
     return BMFR_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Peer-to-peer halo exchange (option A).  After its kernels of frame s a context copies the
+// boundary rows it owns of the four state buffers it has just written straight into the neighbours'
+// halo rows (peer memory, NVLink) and then raises the neighbours' flag to s; before the kernels of
+// frame s+1 it waits for its own two flags to reach s.  The flag protocol also orders the
+// write-after-read hazard: a neighbour can push frame s+1 only after it has run frame s+1, which it
+// starts only after this context's flag for frame s — i.e. after this context is done with frame s.
+// ------------------------------------------------------------------------------------------------
+struct HaloSegment {
+    const unsigned char* src;
+    unsigned char* dst;
+    unsigned long long bytes;
+};
+struct HaloCopy {
+    HaloSegment seg[8];
+    int count;
+};
+
+__global__ void halo_push_kernel(const __grid_constant__ HaloCopy hc) {
+    const HaloSegment s = hc.seg[blockIdx.y];
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((((uintptr_t)s.src | (uintptr_t)s.dst | s.bytes) & 15) == 0) {
+        const uint4* a = reinterpret_cast<const uint4*>(s.src);
+        uint4* b = reinterpret_cast<uint4*>(s.dst);
+        for (unsigned long long i = tid; i < s.bytes / 16; i += stride) b[i] = a[i];
+    } else if ((((uintptr_t)s.src | (uintptr_t)s.dst | s.bytes) & 3) == 0) {
+        const unsigned int* a = reinterpret_cast<const unsigned int*>(s.src);
+        unsigned int* b = reinterpret_cast<unsigned int*>(s.dst);
+        for (unsigned long long i = tid; i < s.bytes / 4; i += stride) b[i] = a[i];
+    } else {
+        for (unsigned long long i = tid; i < s.bytes; i += stride) s.dst[i] = s.src[i];
+    }
+}
+
+__global__ void halo_signal_kernel(unsigned int* flag_a, unsigned int* flag_b, unsigned int value) {
+    __threadfence_system();
+    if (flag_a) *reinterpret_cast<volatile unsigned int*>(flag_a) = value;
+    if (flag_b) *reinterpret_cast<volatile unsigned int*>(flag_b) = value;
+    __threadfence_system();
+}
+
+// One thread polls this context's flags (written by the neighbours' GPUs).  Bounded: a neighbour that
+// never arrives sets flags[2] instead of hanging the device (reported by bmfr_sync).
+__global__ void halo_wait_kernel(unsigned int* flags, int need_a, int need_b, unsigned int value) {
+    const long long t0 = clock64();
+    const long long limit = 4000000000ll;  // ~2 s at 2 GHz
+    for (;;) {
+        const unsigned int a = *reinterpret_cast<volatile unsigned int*>(flags);
+        const unsigned int b = *reinterpret_cast<volatile unsigned int*>(flags + 1);
+        if ((!need_a || a >= value) && (!need_b || b >= value)) break;
+        if (clock64() - t0 > limit) {
+            flags[2] = 1;
+            break;
+        }
+        __nanosleep(200);
+    }
+    __threadfence_system();
+}
+
+static int halo_wait(bmfr_ctx* c) {
+    if (!(c->peer[0].connected || c->peer[1].connected) || c->seq == 0) return BMFR_OK;
+    halo_wait_kernel<<<1, 1, 0, c->stream>>>(c->d_flags, c->peer[0].connected, c->peer[1].connected, (unsigned int)c->seq);
+    int st = bmfr_check_cuda(cudaGetLastError(), "halo_wait_kernel");
+    if (st == 0) ++c->launches;
+    return st;
+}
+
+static int halo_push(bmfr_ctx* c) {
+    if (!(c->peer[0].connected || c->peer[1].connected)) return BMFR_OK;
+    const bmfr_geometry& g = c->geo;
+    const size_t W = (size_t)g.width;
+    const int cur = c->noisy_acc.swapped ? 0 : 1;  // physical index of the buffers this frame wrote (all four swap together)
+    HaloCopy hc;
+    memset(&hc, 0, sizeof(hc));
+    for (int side = 0; side < 2; ++side) {
+        const bmfr_ctx::Peer& pr = c->peer[side];
+        if (!pr.connected) continue;
+        // owned rows of this strip that the neighbour stores as halo
+        int y0, y1;
+        if (side == 0) { y0 = g.own_y0; y1 = pr.row1 < g.own_y1 ? pr.row1 : g.own_y1; }
+        else { y0 = pr.row0 > g.own_y0 ? pr.row0 : g.own_y0; y1 = g.own_y1; }
+        if (y0 >= y1) continue;
+        const size_t so = (size_t)(y0 - g.row0) * W, dof = (size_t)(y0 - pr.row0) * W, n = (size_t)(y1 - y0) * W;
+        const float* src_f[3] = {c->noisy_acc.buf[cur], c->accum.buf[cur], c->result.buf[cur]};
+        float* dst_f[3] = {pr.noisy_acc[cur], pr.accum[cur], pr.result[cur]};
+        for (int k = 0; k < 3; ++k)
+            hc.seg[hc.count++] = HaloSegment{(const unsigned char*)(src_f[k] + so * 3), (unsigned char*)(dst_f[k] + dof * 3), n * 12};
+        hc.seg[hc.count++] = HaloSegment{c->spp.buf[cur] + so, pr.spp[cur] + dof, n};
+    }
+    if (hc.count > 0) {
+        halo_push_kernel<<<dim3(64, hc.count), 256, 0, c->stream>>>(hc);
+        int st = bmfr_check_cuda(cudaGetLastError(), "halo_push_kernel");
+        if (st != 0) return st;
+        ++c->launches;
+    }
+    // the neighbour above sees this context as its "below" neighbour (flag 1) and vice versa
+    unsigned int* fa = c->peer[0].connected ? c->peer[0].flags + 1 : nullptr;
+    unsigned int* fb = c->peer[1].connected ? c->peer[1].flags + 0 : nullptr;
+    halo_signal_kernel<<<1, 1, 0, c->stream>>>(fa, fb, (unsigned int)(c->seq + 1));
+    int st = bmfr_check_cuda(cudaGetLastError(), "halo_signal_kernel");
+    if (st == 0) ++c->launches;
+    return st;
+}
+
+struct HaloBlob {  // what a neighbour needs to address this context's state: geometry + IPC handles
+    unsigned int magic;
+    int device, width, height, row0, row1, own_y0, own_y1, swapped;
+    long long seq;
+    cudaIpcMemHandle_t noisy_acc[2], spp[2], accum[2], result[2], flags;
+};
+static const unsigned int kHaloMagic = 0x424d4648u;  // "BMFH"
+
 extern "C" {
 
 int bmfr_denoise_frame(bmfr_ctx* c, int frame, const float* d_albedo, const float* d_normal, const float* d_position,
@@ -403,8 +543,13 @@ int bmfr_denoise_frame(bmfr_ctx* c, int frame, const float* d_albedo, const floa
     BMFR_CUDA_TRY(cudaSetDevice(c->prm.device));
     KParams P;
     fill_params(c, P, frame, d_albedo, d_normal, d_position, d_noisy, cam_prev, pixel_offset, d_out);
-    int st = run_frame(c, P, frame);
+    int st = halo_wait(c);  // the neighbours' rows of the previous frame's state have arrived
     if (st != 0) return st;
+    st = run_frame(c, P, frame);
+    if (st != 0) return st;
+    st = halo_push(c);      // this frame's boundary rows -> the neighbours' halo rows, then their flags
+    if (st != 0) return st;
+    ++c->seq;
     // swap all double buffers, bmfr.cpp:483-484
     c->noisy_acc.swap(); c->spp.swap(); c->accum.swap(); c->result.swap();
     c->prev_normals = d_normal;
@@ -479,6 +624,13 @@ int bmfr_sync(bmfr_ctx* c) {
     if (c->h2d_stream) BMFR_CUDA_TRY(cudaStreamSynchronize(c->h2d_stream));
     BMFR_CUDA_TRY(cudaStreamSynchronize(c->stream));
     if (c->d2h_stream) BMFR_CUDA_TRY(cudaStreamSynchronize(c->d2h_stream));
+    unsigned int timed_out = 0;
+    BMFR_CUDA_TRY(cudaMemcpy(&timed_out, c->d_flags + 2, sizeof(unsigned int), cudaMemcpyDeviceToHost));
+    if (timed_out) {
+        cudaMemset(c->d_flags + 2, 0, sizeof(unsigned int));
+        return bmfr_set_error(BMFR_ERR_SEQUENCE, "bmfr_sync: a neighbouring strip did not deliver its halo rows within 2 s "
+                                                 "(the contexts must submit the same frames)");
+    }
     int oob = 0;
     BMFR_CUDA_TRY(cudaMemcpy(&oob, c->d_oob, sizeof(int), cudaMemcpyDeviceToHost));
     if (oob) {
@@ -560,6 +712,91 @@ int bmfr_get_fused_kernel_ms(bmfr_ctx* c, int frame, float ms[BMFR_FUSED_KERNEL_
     if (!s.created || s.frame != frame) return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_get_fused_kernel_ms: frame %d not recorded", frame);
     BMFR_CUDA_TRY(cudaEventSynchronize(s.ev[BMFR_FUSED_KERNEL_COUNT]));
     for (int i = 0; i < BMFR_FUSED_KERNEL_COUNT; ++i) BMFR_CUDA_TRY(cudaEventElapsedTime(&ms[i], s.ev[i], s.ev[i + 1]));
+    return BMFR_OK;
+}
+
+static int halo_check_neighbour(const bmfr_ctx* c, int side, int n_w, int n_h, int n_own_y0, int n_own_y1, int n_row0, int n_row1,
+                                int n_swapped, long long n_seq) {
+    const bmfr_geometry& g = c->geo;
+    if (side != 0 && side != 1) return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "halo connect: side must be 0 (above) or 1 (below)");
+    if (n_w != g.width || n_h != g.height) return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "halo connect: the neighbour denoises another image size");
+    if ((side == 0 && n_own_y1 != g.own_y0) || (side == 1 && n_own_y0 != g.own_y1))
+        return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "halo connect: strips [%d,%d) and [%d,%d) are not adjacent on side %d", g.own_y0,
+                              g.own_y1, n_own_y0, n_own_y1, side);
+    // every halo row must belong to the immediate neighbour
+    if ((side == 0 && g.row0 < n_own_y0) || (side == 1 && g.row1 > n_own_y1) || (side == 0 && n_row1 > g.own_y1) ||
+        (side == 1 && n_row0 < g.own_y0))
+        return bmfr_set_error(BMFR_ERR_UNSUPPORTED, "halo connect: halo_rows exceed the neighbouring strip (strips must be at least halo_rows tall)");
+    if (n_swapped != (c->noisy_acc.swapped ? 1 : 0) || n_seq != c->seq)
+        return bmfr_set_error(BMFR_ERR_SEQUENCE, "halo connect: the two contexts have not submitted the same frames");
+    return BMFR_OK;
+}
+
+int bmfr_halo_export(bmfr_ctx* c, void* blob, size_t blob_bytes) {
+    if (!c || !blob || blob_bytes < sizeof(HaloBlob)) return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_halo_export: need %zu bytes", sizeof(HaloBlob));
+    BMFR_CUDA_TRY(cudaSetDevice(c->prm.device));
+    HaloBlob b;
+    memset(&b, 0, sizeof(b));
+    b.magic = kHaloMagic; b.device = c->prm.device; b.width = c->geo.width; b.height = c->geo.height;
+    b.row0 = c->geo.row0; b.row1 = c->geo.row1; b.own_y0 = c->geo.own_y0; b.own_y1 = c->geo.own_y1;
+    b.swapped = c->noisy_acc.swapped ? 1 : 0; b.seq = c->seq;
+    for (int i = 0; i < 2; ++i) {
+        BMFR_CUDA_TRY(cudaIpcGetMemHandle(&b.noisy_acc[i], c->noisy_acc.buf[i]));
+        BMFR_CUDA_TRY(cudaIpcGetMemHandle(&b.spp[i], c->spp.buf[i]));
+        BMFR_CUDA_TRY(cudaIpcGetMemHandle(&b.accum[i], c->accum.buf[i]));
+        BMFR_CUDA_TRY(cudaIpcGetMemHandle(&b.result[i], c->result.buf[i]));
+    }
+    BMFR_CUDA_TRY(cudaIpcGetMemHandle(&b.flags, c->d_flags));
+    memcpy(blob, &b, sizeof(b));
+    return BMFR_OK;
+}
+
+int bmfr_halo_connect(bmfr_ctx* c, int side, const void* neighbour_blob, size_t blob_bytes) {
+    if (!c || !neighbour_blob || blob_bytes < sizeof(HaloBlob)) return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_halo_connect: bad blob");
+    HaloBlob b;
+    memcpy(&b, neighbour_blob, sizeof(b));
+    if (b.magic != kHaloMagic) return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_halo_connect: not a bmfr_halo_export blob");
+    int st = halo_check_neighbour(c, side, b.width, b.height, b.own_y0, b.own_y1, b.row0, b.row1, b.swapped, b.seq);
+    if (st != 0) return st;
+    BMFR_CUDA_TRY(cudaSetDevice(c->prm.device));
+    bmfr_ctx::Peer& pr = c->peer[side];
+    const unsigned int fl = cudaIpcMemLazyEnablePeerAccess;
+    for (int i = 0; i < 2; ++i) {
+        BMFR_CUDA_TRY(cudaIpcOpenMemHandle((void**)&pr.noisy_acc[i], b.noisy_acc[i], fl));
+        BMFR_CUDA_TRY(cudaIpcOpenMemHandle((void**)&pr.spp[i], b.spp[i], fl));
+        BMFR_CUDA_TRY(cudaIpcOpenMemHandle((void**)&pr.accum[i], b.accum[i], fl));
+        BMFR_CUDA_TRY(cudaIpcOpenMemHandle((void**)&pr.result[i], b.result[i], fl));
+    }
+    BMFR_CUDA_TRY(cudaIpcOpenMemHandle((void**)&pr.flags, b.flags, fl));
+    pr.row0 = b.row0; pr.row1 = b.row1; pr.own_y0 = b.own_y0; pr.own_y1 = b.own_y1;
+    pr.ipc = true;
+    pr.connected = true;
+    return BMFR_OK;
+}
+
+int bmfr_halo_connect_local(bmfr_ctx* c, int side, bmfr_ctx* n) {
+    if (!c || !n || c == n) return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_halo_connect_local: bad context");
+    int st = halo_check_neighbour(c, side, n->geo.width, n->geo.height, n->geo.own_y0, n->geo.own_y1, n->geo.row0, n->geo.row1,
+                                  n->noisy_acc.swapped ? 1 : 0, n->seq);
+    if (st != 0) return st;
+    if (n->prm.device != c->prm.device) {
+        BMFR_CUDA_TRY(cudaSetDevice(c->prm.device));
+        int can = 0;
+        BMFR_CUDA_TRY(cudaDeviceCanAccessPeer(&can, c->prm.device, n->prm.device));
+        if (!can) return bmfr_set_error(BMFR_ERR_UNSUPPORTED, "bmfr_halo_connect_local: device %d cannot access device %d", c->prm.device, n->prm.device);
+        cudaError_t e = cudaDeviceEnablePeerAccess(n->prm.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return bmfr_check_cuda(e, "cudaDeviceEnablePeerAccess");
+        cudaGetLastError();
+    }
+    bmfr_ctx::Peer& pr = c->peer[side];
+    for (int i = 0; i < 2; ++i) {
+        pr.noisy_acc[i] = n->noisy_acc.buf[i]; pr.spp[i] = n->spp.buf[i];
+        pr.accum[i] = n->accum.buf[i]; pr.result[i] = n->result.buf[i];
+    }
+    pr.flags = n->d_flags;
+    pr.row0 = n->geo.row0; pr.row1 = n->geo.row1; pr.own_y0 = n->geo.own_y0; pr.own_y1 = n->geo.own_y1;
+    pr.ipc = false;
+    pr.connected = true;
     return BMFR_OK;
 }
 

@@ -143,6 +143,21 @@ class Denoiser:
     def kernel_launches(self):
         return int(self.lib.bmfr_kernel_launches(self._h))
 
+    # -- peer-to-peer halo exchange of sharded contexts -------------------------------------------
+    def halo_export(self) -> bytes:
+        """Opaque blob (CUDA IPC handles + geometry) a neighbouring rank passes to halo_connect()."""
+        buf = C.create_string_buffer(1024)
+        _lib.check(self.lib.bmfr_halo_export(self._h, buf, len(buf)))
+        return buf.raw
+
+    def halo_connect(self, side, blob: bytes):
+        """side 0: the strip above, 1: below.  From then on every frame pushes / waits for halo rows itself."""
+        buf = C.create_string_buffer(blob, len(blob))
+        _lib.check(self.lib.bmfr_halo_connect(self._h, side, buf, len(blob)))
+
+    def halo_connect_local(self, side, other: "Denoiser"):
+        _lib.check(self.lib.bmfr_halo_connect_local(self._h, side, other._h))
+
     def halo_plan(self, side):
         hp = HaloPlan()
         _lib.check(self.lib.bmfr_get_halo_plan(self._h, side, C.byref(hp)))

@@ -9,7 +9,12 @@ Rank r owns a contiguous band of image rows (a whole number of 32-row block rows
      bits and no coefficient exchange is needed;
   2. the four temporal state buffers (accumulated noisy colour, spp, accumulated filtered colour,
      TAA result) have their halo rows refreshed from the owning neighbour — the only communication,
-     neighbour-to-neighbour, no collective reduction.
+     neighbour-to-neighbour, no collective reduction.  Two transports:
+       "p2p"  (default): the contexts are connected once (CUDA IPC handles exchanged through
+              torch.distributed); from then on every bmfr_denoise_frame call pushes its boundary rows
+              straight into the neighbours' halo rows over NVLink and waits for theirs on the device
+              (csrc/bmfr_pipeline.cu, "Peer-to-peer halo exchange") — no host work per frame;
+       "nccl" : batched torch.distributed isend/irecv of the same rows after every frame.
 
 Ownership is fixed, so the sharded output equals the single-GPU output bit for bit as long as
 `halo_rows >= 34 + max vertical reprojection distance`; a gather that leaves strip + halo raises
@@ -113,9 +118,9 @@ class LocalStripSet:
     how the strip logic is verified bit for bit on a single-GPU box (ranks emulated over all ranks'
     data, as B200_PROFILING.md prescribes when there are fewer GPUs than ranks)."""
 
-    def __init__(self, width, height, n, halo=DEFAULT_HALO, device=0, mode="fused", **kw):
+    def __init__(self, width, height, n, halo=DEFAULT_HALO, device=0, mode="fused", exchange="p2p", **kw):
         import torch
-        self.W, self.H, self.n = width, height, n
+        self.W, self.H, self.n, self.exchange = width, height, n, exchange
         self.strips = partition(height, n)
         check_partition(self.strips, height, halo)
         # one explicit stream for all strips and for the halo copies (torch's default stream has
@@ -125,15 +130,20 @@ class LocalStripSet:
         self.stream = self._stream.cuda_stream
         self.ctx = [StripContext(width, height, s, halo, device, self.stream, mode, **kw) for s in self.strips]
         self.msgs = halo_messages(self.strips, height, halo)
+        if exchange == "p2p":  # the library pushes / waits for halo rows itself from now on
+            for r in range(n - 1):
+                self.ctx[r].d.halo_connect_local(1, self.ctx[r + 1].d)
+                self.ctx[r + 1].d.halo_connect_local(0, self.ctx[r].d)
 
     def denoise_frame(self, frame, full_inputs, cam_prev, pixel_offset, out_full):
         """full_inputs: four torch CUDA tensors [H, W, 3]; out_full: [H, W, 3] receives owned rows."""
         for c in self.ctx:
             ptrs = [t[c.row0:c.row1].data_ptr() for t in full_inputs]
             c.d.denoise_frame(frame, *ptrs, cam_prev, pixel_offset, out_full[c.row0:c.row1].data_ptr())
-        for name in STATE_BUFFERS:
-            for src, dst, y0, y1 in self.msgs:
-                self.ctx[dst].rows_view(name, y0, y1).copy_(self.ctx[src].rows_view(name, y0, y1))
+        if self.exchange != "p2p":
+            for name in STATE_BUFFERS:
+                for src, dst, y0, y1 in self.msgs:
+                    self.ctx[dst].rows_view(name, y0, y1).copy_(self.ctx[src].rows_view(name, y0, y1))
 
     def sync(self):
         for c in self.ctx:
@@ -180,6 +190,15 @@ def bench_sharded(args, workload, frames):
     torch.cuda.set_stream(stream)
     sp = stream.cuda_stream
     ctx = StripContext(w, h, strips[rank], halo, local, sp, args.mode)
+    exchange = getattr(args, "exchange", "p2p")
+    if exchange == "p2p":  # one-time exchange of IPC handles; afterwards no host-side communication per frame
+        blobs = [None] * world
+        dist.all_gather_object(blobs, ctx.d.halo_export())
+        if rank > 0:
+            ctx.d.halo_connect(0, blobs[rank - 1])
+        if rank < world - 1:
+            ctx.d.halo_connect(1, blobs[rank + 1])
+        dist.barrier()
     rows = ctx.row1 - ctx.row0
     inputs = torch.empty((frames, 4, rows, w, 3), dtype=torch.float32, device="cuda")
     for f in range(frames):
@@ -192,7 +211,8 @@ def bench_sharded(args, workload, frames):
         for f in range(frames):
             ctx.d.denoise_frame(f, inputs[f, 0].data_ptr(), inputs[f, 1].data_ptr(), inputs[f, 2].data_ptr(),
                                 inputs[f, 3].data_ptr(), cams[f], offs[f], out.data_ptr())
-            exchange_distributed(ctx.rows_view, msgs, rank)
+            if exchange != "p2p":
+                exchange_distributed(ctx.rows_view, msgs, rank)
 
     for _ in range(args.warmup):
         run_sequence()
@@ -215,14 +235,21 @@ def bench_sharded(args, workload, frames):
     launches = ctx.d.kernel_launches - l0
     halo_bytes = sum((y1 - y0) * w * sum(_BYTES_PER_PIXEL.values()) for s, d_, y0, y1 in msgs if d_ == rank)
     if rank == 0:
-        fps = frames * args.steps / (total_ms * 1e-3)
+        native = frames * args.steps / (total_ms * 1e-3)
+        norm = (w * h) / float(1920 * 1080)
+        weak = not (args.width or args.height)
         line = {
-            "metric": "frames/sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "metric": "frames/sec", "value": native * norm, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "ms_per_frame": total_ms / args.steps / frames,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak" if weak else "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "frames_per_s_native": native,
             "config": {"workload": f"{w}x{h} x{frames} frames synth-v1 strip-sharded over {world} GPUs along block rows",
+                       "value_unit": "1080p-equivalent frames/s = native frames/s x (W*H)/(1920*1080); every rank owns "
+                                     "a 3840x540 strip in the default (weak-scaling) series",
                        "mode": args.mode, "strips": strips, "halo_rows": halo,
-                       "parallelism": f"strips{world}", "exchange": "NCCL send/recv of state halo rows, neighbours only",
+                       "parallelism": f"strips{world}",
+                       "exchange": ("peer-to-peer pushes of state halo rows over NVLink from the library (CUDA IPC), device-side flags"
+                                    if exchange == "p2p" else "NCCL send/recv of state halo rows, neighbours only"),
                        "l2": "inputs larger than L2; no explicit flush"},
             "halo_bytes_per_frame_rank0": halo_bytes, "gpu_launches": int(launches), "roofline": None,
             "cpu_baseline": None, "e2e": None,

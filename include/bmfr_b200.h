@@ -186,6 +186,20 @@ typedef struct bmfr_halo_plan {
 } bmfr_halo_plan;
 int bmfr_get_halo_plan(const bmfr_ctx* ctx, int side, bmfr_halo_plan* out);
 
+/* Peer-to-peer halo exchange (option A; no counterpart in the single-device reference).  Once
+ * a sharded context is connected to the contexts that own the strips above (side 0) and below (side 1),
+ * every bmfr_denoise_frame call copies its boundary rows of the four state buffers straight into the
+ * neighbours' halo rows (peer memory over NVLink) after its kernels and waits for the neighbours' rows
+ * before the kernels of the next frame — no host round trip, no collective.  All contexts must submit
+ * the same frame sequence.
+ *   bmfr_halo_export / bmfr_halo_connect : contexts in different processes (one rank per GPU): export an
+ *       opaque blob (CUDA IPC handles + geometry), ship it to the neighbour with any transport, connect.
+ *   bmfr_halo_connect_local              : both contexts live in this process. */
+#define BMFR_HALO_BLOB_BYTES 1024
+int bmfr_halo_export(bmfr_ctx* ctx, void* blob, size_t blob_bytes);
+int bmfr_halo_connect(bmfr_ctx* ctx, int side, const void* neighbour_blob, size_t blob_bytes);
+int bmfr_halo_connect_local(bmfr_ctx* ctx, int side, bmfr_ctx* neighbour);
+
 /* ---- synthetic inputs ("synth-v1"): stands in for the dataset of bmfr.cpp:44-53 ---- */
 void bmfr_synth_camera(int frame, int width, int height, int jitter, float cam_matrix[16], float pixel_offset[2]);
 void bmfr_synth_limits(float* position_limit_squared, float* normal_limit_squared);

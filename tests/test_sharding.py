@@ -100,10 +100,12 @@ def test_halo_exchange_gloo_world2():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("exchange", ["p2p", "copy"])
 @pytest.mark.parametrize("n", [2, 3])
-def test_sharded_equals_single_gpu_bitwise(n):
-    """All ranks' strips in one process on one GPU (halo refresh by device copies): owned rows of every
-    state buffer and the output are bit-identical to the whole-image run, frame after frame."""
+def test_sharded_equals_single_gpu_bitwise(n, exchange):
+    """All ranks' strips in one process on one GPU: owned rows of every state buffer and the output are
+    bit-identical to the whole-image run, frame after frame.  "p2p": the library's own halo pushes and
+    device-side flags between locally connected contexts; "copy": halo rows refreshed by the test."""
     import torch
     from bmfr_b200 import Denoiser, synth
     w, h, frames, halo = 320, 384, 7, 40
@@ -117,7 +119,7 @@ def test_sharded_equals_single_gpu_bitwise(n):
     torch.cuda.synchronize()
 
     whole = Denoiser(w, h, mode="fused")
-    ss = sharding.LocalStripSet(w, h, n, halo=halo)
+    ss = sharding.LocalStripSet(w, h, n, halo=halo, exchange=exchange)
     out_s = torch.zeros((h, w, 3), dtype=torch.float32, device=dev)
     out_w = torch.zeros((h, w, 3), dtype=torch.float32, device=dev)
     for f in range(frames):
