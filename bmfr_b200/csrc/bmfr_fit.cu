@@ -36,6 +36,23 @@
 #define BMFR_REPROJECT_BY (256 / BMFR_REPROJECT_BX)
 template <bool STRIP>
 __global__ void __launch_bounds__(256, BMFR_REPROJECT_MIN_BLOCKS) reproject_kernel(const __grid_constant__ KParams P) {
+    // The first CTAs also produce this frame's add_random() tile (bmfr.cl:173-182; one 9x1024 tile per
+    // frame shared by all blocks, fp64 like the reference's double literal plus its fp32 rounding for the
+    // fit) and reset the fit's block counter: the fit starts only after this kernel has completed.
+    {
+        const int cta = blockIdx.y * gridDim.x + blockIdx.x, ncta = gridDim.x * gridDim.y;
+        const int workers = ncta < 36 ? ncta : 36;
+        if (cta < workers) {
+            const int n = (BMFR_FEATURES - 1) * BMFR_BLOCK_PIXELS;
+            for (int i = cta * 256 + threadIdx.y * BMFR_REPROJECT_BX + threadIdx.x; i < n; i += workers * 256) {
+                const int seed = i + BMFR_BLOCK_PIXELS + P.frame * BMFR_BUFFER_COUNT * BMFR_BLOCK_PIXELS;
+                const double d = (P.noise_amount * 2.0) * (double)(bmfr_random((unsigned int)seed) - 0.5f);
+                P.noise_out[i] = d;
+                P.noise_f_out[i] = (float)d;
+            }
+            if (cta == 0 && threadIdx.x == 0 && threadIdx.y == 0) *P.block_counter = 0;
+        }
+    }
     const int x = blockIdx.x * BMFR_REPROJECT_BX + threadIdx.x;
     const int y = P.k1_y0 + blockIdx.y * BMFR_REPROJECT_BY + threadIdx.y;
     if (x >= P.W || y >= P.k1_y1) return;
@@ -446,6 +463,21 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned int pa
         "}\n" ::"r"(smem_u32(b)), "r"(parity)
         : "memory");
 }
+// The same without the back-off, for waits that are on the critical path of every compute warp (the
+// block's input tiles): try_wait already suspends the thread for a hardware-defined interval, and a
+// sleeping warp can oversleep the arrival by microseconds.
+__device__ __forceinline__ void mbar_wait_hot(unsigned long long* b, unsigned int parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MBAR_HOT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MBAR_HOT_DONE;\n"
+        "bra MBAR_HOT_LOOP;\n"
+        "MBAR_HOT_DONE:\n"
+        "}\n" ::"r"(smem_u32(b)), "r"(parity)
+        : "memory");
+}
 __device__ __forceinline__ void compute_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(QR_COMPUTE_THREADS) : "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, unsigned int bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
@@ -618,7 +650,7 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
     }
     int it = 0;
     for (;; ++it) {
-        mbar_wait(&sh.data_full, it & 1);
+        mbar_wait_hot(&sh.data_full, it & 1);
         const int local = sh.blk[it & 1];
         if (local >= nblocks) break;
         const int slot = it % QR_SLOTS;

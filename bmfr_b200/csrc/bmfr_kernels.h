@@ -41,6 +41,9 @@ struct KParams {
     float* mins_inv;              // (min, 1/range or 1) per block and scaled feature, see scale_factor()
     const double* noise;          // [9][1024] add_random() increments of this frame
     const float* noise_f;         // the same tile rounded to fp32 (FUSED fit)
+    double* noise_out;            // FUSED: the reproject kernel writes both tiles itself
+    float* noise_f_out;
+    double noise_amount;          // NOISE_AMOUNT (a double literal in the reference, bmfr.cpp:58)
     const float* albedo;
     float* filtered;              // STAGED only
     const float* accum_prev;      // accumulated_prev_frame

@@ -360,7 +360,7 @@ static void fill_params(bmfr_ctx* c, KParams& P, int frame, const float* d_albed
     P.prev_spp = c->spp.previous(); P.cur_spp = c->spp.current();
     P.prev_pixels = c->prev_pixels; P.accept = c->accept;
     P.tmp_data = c->tmp_data; P.weights = c->weights; P.mins_maxs = c->mins_maxs; P.mins_inv = c->mins_inv; P.noise = c->noise;
-    P.noise_f = c->noise_f;
+    P.noise_f = c->noise_f; P.noise_out = c->noise; P.noise_f_out = c->noise_f; P.noise_amount = c->prm.noise_amount;
     P.albedo = d_albedo; P.filtered = c->filtered;
     P.accum_prev = c->accum.previous(); P.accum_cur = c->accum.current();
     P.tone_mapped = c->tone_mapped;
@@ -393,7 +393,8 @@ static StageEvents* prof_slot(bmfr_ctx* c, int frame) {
 
 static int run_frame(bmfr_ctx* c, const KParams& P, int frame) {
     StageEvents* pe = prof_slot(c, frame);
-    LAUNCH_TRY(launch_noise_tile(c->noise, c->noise_f, c->d_oob + 1, c->prm.noise_amount, frame, c->stream), "noise_tile_kernel");
+    if (c->prm.mode == BMFR_MODE_STAGED)  // FUSED: the reproject kernel produces the tile itself
+        LAUNCH_TRY(launch_noise_tile(c->noise, c->noise_f, c->d_oob + 1, c->prm.noise_amount, frame, c->stream), "noise_tile_kernel");
     MARK(0);
     if (c->prm.mode == BMFR_MODE_STAGED) {
         LAUNCH_TRY(launch_k1(P, c->stream), "accumulate_noisy_data");
