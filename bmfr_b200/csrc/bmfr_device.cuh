@@ -122,11 +122,13 @@ struct K1Pixel {
 };
 
 // STRIP = the context holds only a band of rows: gathers are checked against it (oob_flag).
+// wp: the pixel's world position, already loaded (callers that walk over several pixels fetch the next
+// pixel's position before they start this one, so that the two dependent memory round trips of a pixel
+// — position -> reprojection -> taps — overlap across pixels).
 template <bool STRIP>
-__device__ __forceinline__ K1Pixel k1_pixel(const KParams& P, int x, int y) {
+__device__ __forceinline__ K1Pixel k1_pixel(const KParams& P, int x, int y, f3 wp) {
     K1Pixel r;
     const unsigned int lp = pix_index(P, x, y);
-    const f3 wp = load_f3(P.cur_positions, lp);
     const f3 n = load_f3(P.cur_normals, lp);
     const f3 cur = load_f3(P.cur_noisy, lp);
     float pfx = (float)x, pfy = (float)y;  // bmfr.cl:325
@@ -252,6 +254,11 @@ __device__ __forceinline__ void k1_features(const K1Pixel& r, float* f) {
     f[10] = scrub_nan(r.new_color.x);
     f[11] = scrub_nan(r.new_color.y);
     f[12] = scrub_nan(r.new_color.z);
+}
+
+template <bool STRIP>
+__device__ __forceinline__ K1Pixel k1_pixel(const KParams& P, int x, int y) {
+    return k1_pixel<STRIP>(P, x, y, load_f3(P.cur_positions, pix_index(P, x, y)));
 }
 
 // ---------------------------------------------------------------------------------------------

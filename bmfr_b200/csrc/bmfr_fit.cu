@@ -34,6 +34,9 @@
 #define BMFR_REPROJECT_BX 32  // CTA = BX x (256 / BX) pixels
 #endif
 #define BMFR_REPROJECT_BY (256 / BMFR_REPROJECT_BX)
+#ifndef BMFR_REPROJECT_PIXELS
+#define BMFR_REPROJECT_PIXELS 4  // pixels per thread (rows BY apart); the next pixel's position is fetched one pixel ahead
+#endif
 template <bool STRIP>
 __global__ void __launch_bounds__(256, BMFR_REPROJECT_MIN_BLOCKS) reproject_kernel(const __grid_constant__ KParams P) {
     // The first CTAs also produce this frame's add_random() tile (bmfr.cl:173-182; one 9x1024 tile per
@@ -54,18 +57,33 @@ __global__ void __launch_bounds__(256, BMFR_REPROJECT_MIN_BLOCKS) reproject_kern
         }
     }
     const int x = blockIdx.x * BMFR_REPROJECT_BX + threadIdx.x;
-    const int y = P.k1_y0 + blockIdx.y * BMFR_REPROJECT_BY + threadIdx.y;
-    if (x >= P.W || y >= P.k1_y1) return;
-    if (STRIP && (y < P.row0 || y >= P.row1)) {
-        *P.oob_flag = 1;
-        return;
+    const int ybase = P.k1_y0 + blockIdx.y * (BMFR_REPROJECT_BY * BMFR_REPROJECT_PIXELS) + threadIdx.y;
+    if (x >= P.W) return;
+    int ylo = P.k1_y0, yhi = P.k1_y1;
+    if (STRIP) {  // rows outside the strip + halo cannot be reprojected here: flag and skip them
+        if (ylo < P.row0 || yhi > P.row1) *P.oob_flag = 1;
+        ylo = max(ylo, P.row0);
+        yhi = min(yhi, P.row1);
     }
-    const K1Pixel r = k1_pixel<STRIP>(P, x, y);
-    const unsigned int lp = pix_index(P, x, y);
-    store_f3(P.cur_noisy_acc, lp, r.new_color);
-    P.cur_spp[lp] = r.spp;
-    P.prev_pixels[lp] = make_float2(r.prev_x, r.prev_y);
-    P.accept[lp] = r.accept;
+    // software pipeline over the thread's pixels: position of pixel k+1 in flight while pixel k runs its
+    // reprojection -> tap gather chain
+    f3 wp_next = make_f3(0.f, 0.f, 0.f);
+    if (ybase >= ylo && ybase < yhi) wp_next = load_f3(P.cur_positions, pix_index(P, x, ybase));
+#pragma unroll 1
+    for (int k = 0; k < BMFR_REPROJECT_PIXELS; ++k) {
+        const int y = ybase + k * BMFR_REPROJECT_BY;
+        if (y >= yhi) break;
+        const f3 wp = wp_next;
+        const int yn = y + BMFR_REPROJECT_BY;
+        if (k + 1 < BMFR_REPROJECT_PIXELS && yn >= ylo && yn < yhi) wp_next = load_f3(P.cur_positions, pix_index(P, x, yn));
+        if (y < ylo) continue;
+        const K1Pixel r = k1_pixel<STRIP>(P, x, y, wp);
+        const unsigned int lp = pix_index(P, x, y);
+        store_f3(P.cur_noisy_acc, lp, r.new_color);
+        P.cur_spp[lp] = r.spp;
+        P.prev_pixels[lp] = make_float2(r.prev_x, r.prev_y);
+        P.accept[lp] = r.accept;
+    }
 }
 
 // --------------------------------------------------------------------------------------------
@@ -796,7 +814,8 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
 static bool is_strip(const KParams& P) { return P.row0 != 0 || P.row1 != P.H; }
 
 cudaError_t launch_reproject(const KParams& P, cudaStream_t st) {
-    const dim3 grid((P.W + BMFR_REPROJECT_BX - 1) / BMFR_REPROJECT_BX, (P.k1_y1 - P.k1_y0 + BMFR_REPROJECT_BY - 1) / BMFR_REPROJECT_BY),
+    const int rows_per_cta = BMFR_REPROJECT_BY * BMFR_REPROJECT_PIXELS;
+    const dim3 grid((P.W + BMFR_REPROJECT_BX - 1) / BMFR_REPROJECT_BX, (P.k1_y1 - P.k1_y0 + rows_per_cta - 1) / rows_per_cta),
         block(BMFR_REPROJECT_BX, BMFR_REPROJECT_BY);
     if (is_strip(P)) reproject_kernel<true><<<grid, block, 0, st>>>(P);
     else reproject_kernel<false><<<grid, block, 0, st>>>(P);
