@@ -182,7 +182,9 @@ def bench_sharded(args, workload, frames):
     w, h = args.width or workload[0], args.height or workload[1]
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-    halo = DEFAULT_HALO
+    # 34 rows (one straddling block + the TAA ring) + the vertical reprojection distance, which grows with
+    # the image height in the synthetic sequence (a few pixels per frame at 1080 rows)
+    halo = 34 + 14 * ((h + 1079) // 1080)
     strips = partition(h, world)
     check_partition(strips, h, halo)
     msgs = halo_messages(strips, h, halo)

@@ -15,8 +15,11 @@ except Exception as e:
     print(sys.argv[2], "FAILED", e)
 PY
 }
+WHAT=${2:-all}
 run weak_p2p ""
 run weak_nccl "--exchange nccl"
-run strong4k_p2p "--width 3840 --height 2160"
-[ "$N" = "8" ] && run strong8k_p2p "--width 7680 --height 4320"
-tail -3 $OUT/*.err | grep -iE "error|Traceback" | head
+if [ "$WHAT" = "all" ]; then
+  run strong4k_p2p "--width 3840 --height 2160"
+  [ "$N" = "8" ] && run strong8k_p2p "--width 7680 --height 4320"
+fi
+grep -hiE "BmfrError|Error:" $OUT/*.err | head -5
