@@ -320,7 +320,7 @@ __device__ __forceinline__ void k4_pixel(const KParams& P, unsigned int lp, f3 f
         for (int i = 0; i < 4; ++i) {
             if (accept & (1u << i)) {  // taps are trusted, not re-checked: bmfr.cl:801-832
                 const int sx = pix + (i & 1), sy = piy + (i >> 1);
-                if (sy < P.row0 || sy >= P.row1) {
+                if (sy < P.state2_row0 || sy >= P.state2_row1) {
                     *P.oob_flag = 1;
                     continue;
                 }
@@ -392,7 +392,7 @@ __device__ __forceinline__ f3 taa_resolve(const KParams& P, f3 my_new, const Taa
         const bool ok_x = dx ? (pix < P.W - 1) : (pix >= 0);
         if (ok_x && ok_y) {
             const int sy = piy + dy;
-            if (sy < P.row0 || sy >= P.row1) {
+            if (sy < P.state2_row0 || sy >= P.state2_row1) {
                 *P.oob_flag = 1;
                 continue;
             }

@@ -19,6 +19,7 @@ struct KParams {
     int py0, py1;        // image rows the per-pixel stages (K3,K4) cover; K5 covers own_y0..own_y1
     int own_y0, own_y1;
     int k1_y0, k1_y1;    // image rows reproject_kernel covers: every row a block of by0..by1 reads
+    int state2_row0, state2_row1;  // rows of accum / result that are valid on this strip (own rows + refreshed halo)
     float cam[16];       // prev_frame_camera_matrix
     float poff_x;        // pixel_offset.x
     float poff_y1;       // 1 - pixel_offset.y  (bmfr.cl:353-355)

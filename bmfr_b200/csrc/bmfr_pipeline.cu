@@ -112,6 +112,8 @@ struct bmfr_ctx {
         float* result[2] = {nullptr, nullptr};
         unsigned int* flags = nullptr;                     // its flag pair; this context signals flags[1 - side]
     } peer[2];
+    cudaStream_t halo_stream = nullptr;               // early push (accumulated colour + spp) overlaps fit and post
+    cudaEvent_t halo_ready = nullptr, halo_pushed = nullptr;
     unsigned int* d_flags = nullptr;   // [0]: frames completed by the neighbour above, [1]: below; [2]: wait timed out
     long long seq = 0;                 // frames submitted on this context
 };
@@ -160,6 +162,9 @@ static void free_ctx(bmfr_ctx* c) {
         }
     }
     cudaFree(c->d_flags);
+    if (c->halo_stream) { cudaStreamSynchronize(c->halo_stream); cudaStreamDestroy(c->halo_stream); }
+    if (c->halo_ready) cudaEventDestroy(c->halo_ready);
+    if (c->halo_pushed) cudaEventDestroy(c->halo_pushed);
     for (int k = 0; k < 4; ++k)
         for (int s = 0; s < kHostSlots; ++s) cudaFree(c->up[k][s]);
     for (int s = 0; s < kHostSlots; ++s) {
@@ -342,6 +347,12 @@ static void fill_params(bmfr_ctx* c, KParams& P, int frame, const float* d_albed
         P.by0 = (P.py0 + 16 - P.off_y) >> 5;
         P.by1 = ((P.py1 - 1 + 16 - P.off_y) >> 5) + 1;
     }
+    // rows of the accumulated filtered colour / TAA result a neighbour keeps fresh (see halo_rows_for)
+    {
+        const int h2 = c->prm.halo_rows > 32 ? c->prm.halo_rows - 32 : 0;
+        P.state2_row0 = whole ? 0 : (g.own_y0 - h2 > g.row0 ? g.own_y0 - h2 : g.row0);
+        P.state2_row1 = whole ? g.height : (g.own_y1 + h2 < g.row1 ? g.own_y1 + h2 : g.row1);
+    }
     // rows the blocks by0..by1 cover (mirrored margin rows fold back into the first / last block row)
     P.k1_y0 = P.by0 * 32 - 16 + P.off_y; if (P.k1_y0 < 0) P.k1_y0 = 0;
     P.k1_y1 = P.by1 * 32 - 16 + P.off_y; if (P.k1_y1 > g.height) P.k1_y1 = g.height;
@@ -391,6 +402,8 @@ static StageEvents* prof_slot(bmfr_ctx* c, int frame) {
         if (pe) BMFR_CUDA_TRY(cudaEventRecord(pe->ev[i], c->stream)); \
     } while (0)
 
+static int halo_push_early(bmfr_ctx* c);
+
 static int run_frame(bmfr_ctx* c, const KParams& P, int frame) {
     StageEvents* pe = prof_slot(c, frame);
     if (c->prm.mode == BMFR_MODE_STAGED)  // FUSED: the reproject kernel produces the tile itself
@@ -399,6 +412,7 @@ static int run_frame(bmfr_ctx* c, const KParams& P, int frame) {
     if (c->prm.mode == BMFR_MODE_STAGED) {
         LAUNCH_TRY(launch_k1(P, c->stream), "accumulate_noisy_data");
         MARK(1);
+        { int hs = halo_push_early(c); if (hs != 0) return hs; }
         LAUNCH_TRY(launch_k2(P, c->stream), "fitter");
         MARK(2);
         LAUNCH_TRY(launch_k3(P, c->stream), "weighted_sum");
@@ -410,6 +424,7 @@ static int run_frame(bmfr_ctx* c, const KParams& P, int frame) {
     } else {
         LAUNCH_TRY(launch_reproject(P, c->stream), "reproject_kernel");
         MARK(1);
+        { int hs = halo_push_early(c); if (hs != 0) return hs; }
         LAUNCH_TRY(launch_fit_qr(P, c->stream), "fit_qr_kernel");
         MARK(2);
         LAUNCH_TRY(launch_post(P, c->stream), "post_kernel");
@@ -486,39 +501,81 @@ static int halo_wait(bmfr_ctx* c) {
     return st;
 }
 
-static int halo_push(bmfr_ctx* c) {
-    if (!(c->peer[0].connected || c->peer[1].connected)) return BMFR_OK;
+// Rows of a neighbour's halo this context must refresh, per state buffer.  The accumulated noisy colour and
+// spp are gathered by the reprojection of every row a straddling block covers (halo_rows = 34 + motion);
+// the accumulated filtered colour and the TAA result are gathered only from the owned rows +- 1, so their
+// halo needs halo_rows - 32 rows (KParams::state2_row0/1 make a gather beyond that fail loudly).
+static bool halo_rows_for(const bmfr_ctx* c, int side, bool late, int* y0, int* y1) {
+    const bmfr_geometry& g = c->geo;
+    const bmfr_ctx::Peer& pr = c->peer[side];
+    int lo = pr.row0, hi = pr.row1;  // rows the neighbour stores
+    if (late) {
+        const int h2 = c->prm.halo_rows > 32 ? c->prm.halo_rows - 32 : 0;
+        lo = pr.own_y0 - h2 > lo ? pr.own_y0 - h2 : lo;
+        hi = pr.own_y1 + h2 < hi ? pr.own_y1 + h2 : hi;
+    }
+    if (side == 0) { *y0 = g.own_y0; *y1 = hi < g.own_y1 ? hi : g.own_y1; }
+    else { *y0 = lo > g.own_y0 ? lo : g.own_y0; *y1 = g.own_y1; }
+    return *y0 < *y1;
+}
+
+// late = false: accumulated noisy colour + spp (available after the first kernel of the frame);
+// late = true : accumulated filtered colour + TAA result (after the last kernel).
+static int halo_push_part(bmfr_ctx* c, bool late, cudaStream_t st) {
     const bmfr_geometry& g = c->geo;
     const size_t W = (size_t)g.width;
-    const int cur = c->noisy_acc.swapped ? 0 : 1;  // physical index of the buffers this frame wrote (all four swap together)
+    const int cur = c->noisy_acc.swapped ? 0 : 1;  // physical index of the buffers this frame writes (all four swap together)
     HaloCopy hc;
     memset(&hc, 0, sizeof(hc));
     for (int side = 0; side < 2; ++side) {
         const bmfr_ctx::Peer& pr = c->peer[side];
-        if (!pr.connected) continue;
-        // owned rows of this strip that the neighbour stores as halo
         int y0, y1;
-        if (side == 0) { y0 = g.own_y0; y1 = pr.row1 < g.own_y1 ? pr.row1 : g.own_y1; }
-        else { y0 = pr.row0 > g.own_y0 ? pr.row0 : g.own_y0; y1 = g.own_y1; }
-        if (y0 >= y1) continue;
+        if (!pr.connected || !halo_rows_for(c, side, late, &y0, &y1)) continue;
         const size_t so = (size_t)(y0 - g.row0) * W, dof = (size_t)(y0 - pr.row0) * W, n = (size_t)(y1 - y0) * W;
-        const float* src_f[3] = {c->noisy_acc.buf[cur], c->accum.buf[cur], c->result.buf[cur]};
-        float* dst_f[3] = {pr.noisy_acc[cur], pr.accum[cur], pr.result[cur]};
-        for (int k = 0; k < 3; ++k)
-            hc.seg[hc.count++] = HaloSegment{(const unsigned char*)(src_f[k] + so * 3), (unsigned char*)(dst_f[k] + dof * 3), n * 12};
-        hc.seg[hc.count++] = HaloSegment{c->spp.buf[cur] + so, pr.spp[cur] + dof, n};
+        if (late) {
+            hc.seg[hc.count++] = HaloSegment{(const unsigned char*)(c->accum.buf[cur] + so * 3), (unsigned char*)(pr.accum[cur] + dof * 3), n * 12};
+            hc.seg[hc.count++] = HaloSegment{(const unsigned char*)(c->result.buf[cur] + so * 3), (unsigned char*)(pr.result[cur] + dof * 3), n * 12};
+        } else {
+            hc.seg[hc.count++] = HaloSegment{(const unsigned char*)(c->noisy_acc.buf[cur] + so * 3), (unsigned char*)(pr.noisy_acc[cur] + dof * 3), n * 12};
+            hc.seg[hc.count++] = HaloSegment{c->spp.buf[cur] + so, pr.spp[cur] + dof, n};
+        }
     }
-    if (hc.count > 0) {
-        halo_push_kernel<<<dim3(64, hc.count), 256, 0, c->stream>>>(hc);
-        int st = bmfr_check_cuda(cudaGetLastError(), "halo_push_kernel");
-        if (st != 0) return st;
-        ++c->launches;
+    if (hc.count == 0) return BMFR_OK;
+    halo_push_kernel<<<dim3(48, hc.count), 256, 0, st>>>(hc);
+    int rc = bmfr_check_cuda(cudaGetLastError(), "halo_push_kernel");
+    if (rc == 0) ++c->launches;
+    return rc;
+}
+
+static bool halo_active(const bmfr_ctx* c) { return c->peer[0].connected || c->peer[1].connected; }
+
+// after the kernel that produced the accumulated noisy colour and spp: push them on the side stream
+static int halo_push_early(bmfr_ctx* c) {
+    if (!halo_active(c)) return BMFR_OK;
+    if (!c->halo_stream) {
+        BMFR_CUDA_TRY(cudaStreamCreateWithFlags(&c->halo_stream, cudaStreamNonBlocking));
+        BMFR_CUDA_TRY(cudaEventCreateWithFlags(&c->halo_ready, cudaEventDisableTiming));
+        BMFR_CUDA_TRY(cudaEventCreateWithFlags(&c->halo_pushed, cudaEventDisableTiming));
     }
+    BMFR_CUDA_TRY(cudaEventRecord(c->halo_ready, c->stream));
+    BMFR_CUDA_TRY(cudaStreamWaitEvent(c->halo_stream, c->halo_ready, 0));
+    int st = halo_push_part(c, false, c->halo_stream);
+    if (st != 0) return st;
+    BMFR_CUDA_TRY(cudaEventRecord(c->halo_pushed, c->halo_stream));
+    return BMFR_OK;
+}
+
+// after the last kernel: push the rest, then raise the neighbours' flags
+static int halo_push_late(bmfr_ctx* c) {
+    if (!halo_active(c)) return BMFR_OK;
+    int st = halo_push_part(c, true, c->stream);
+    if (st != 0) return st;
+    BMFR_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->halo_pushed, 0));
     // the neighbour above sees this context as its "below" neighbour (flag 1) and vice versa
     unsigned int* fa = c->peer[0].connected ? c->peer[0].flags + 1 : nullptr;
     unsigned int* fb = c->peer[1].connected ? c->peer[1].flags + 0 : nullptr;
     halo_signal_kernel<<<1, 1, 0, c->stream>>>(fa, fb, (unsigned int)(c->seq + 1));
-    int st = bmfr_check_cuda(cudaGetLastError(), "halo_signal_kernel");
+    st = bmfr_check_cuda(cudaGetLastError(), "halo_signal_kernel");
     if (st == 0) ++c->launches;
     return st;
 }
@@ -548,7 +605,7 @@ int bmfr_denoise_frame(bmfr_ctx* c, int frame, const float* d_albedo, const floa
     if (st != 0) return st;
     st = run_frame(c, P, frame);
     if (st != 0) return st;
-    st = halo_push(c);      // this frame's boundary rows -> the neighbours' halo rows, then their flags
+    st = halo_push_late(c);  // the rest of this frame's boundary rows -> the neighbours' halo rows, then their flags
     if (st != 0) return st;
     ++c->seq;
     // swap all double buffers, bmfr.cpp:483-484

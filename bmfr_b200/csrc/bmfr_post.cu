@@ -126,7 +126,7 @@ __device__ __forceinline__ f3 accumulate_filtered_px(const KParams& P, unsigned 
         for (int i = 0; i < 4; ++i) {
             if (accept & (1u << i)) {  // taps are trusted, not re-checked: bmfr.cl:801-832
                 const int sx = pix + (i & 1), sy = piy + (i >> 1);
-                if (STRIP && (sy < P.row0 || sy >= P.row1)) {
+                if (STRIP && (sy < P.state2_row0 || sy >= P.state2_row1)) {
                     *P.oob_flag = 1;
                     continue;
                 }
@@ -198,7 +198,7 @@ __device__ __forceinline__ bool history_sample(const KParams& P, float2 pp, f3& 
         const bool ok_x = dx ? (pix < P.W - 1) : (pix >= 0);
         if (ok_x && ok_y) {
             const int sy = piy + dy;
-            if (STRIP && (sy < P.row0 || sy >= P.row1)) {
+            if (STRIP && (sy < P.state2_row0 || sy >= P.state2_row1)) {
                 *P.oob_flag = 1;
                 continue;
             }
