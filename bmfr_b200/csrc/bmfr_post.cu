@@ -248,6 +248,31 @@ __device__ __forceinline__ bool phase_a_pixel(PostShared& sh, const KParams& P, 
     return finish_pixel<STRIP, WIDE>(sh, P, in, weighted_sum_px(in.n, in.p, cf), hx, hy, x, y, store, own, hist);
 }
 
+#ifndef BMFR_POST_PREFETCH
+#define BMFR_POST_PREFETCH 1
+#endif
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// Starts the DRAM -> L2 fetch of everything phase A reads at pixel (x,y) (no registers are tied up); the
+// loads that follow one or two pixels later then see L2 latency instead of DRAM latency.
+__device__ __forceinline__ void prefetch_pixel(const KParams& P, int x, int y) {
+    const unsigned int lp = pix_index(P, x, y);
+    prefetch_l2(P.cur_normals + (size_t)(lp * 3u));
+    prefetch_l2(P.cur_positions + (size_t)(lp * 3u));
+    prefetch_l2(P.albedo + (size_t)(lp * 3u));
+    prefetch_l2(P.prev_pixels + lp);
+}
+// The same for the two gathers of a pixel whose previous-frame position is already known.
+__device__ __forceinline__ void prefetch_taps(const KParams& P, float2 pp) {
+    const int pix = min(max(__float2int_rd(pp.x), 0), P.W - 1);
+    const int piy = __float2int_rd(pp.y);
+    const int ya = min(max(piy, P.row0), P.row1 - 1), yb = min(max(piy + 1, P.row0), P.row1 - 1);
+    const unsigned int la = pix_index(P, pix, ya), lb = pix_index(P, pix, yb);
+    prefetch_l2(P.accum_prev + (size_t)(la * 3u));
+    prefetch_l2(P.accum_prev + (size_t)(lb * 3u));
+    prefetch_l2(P.result_prev + (size_t)(la * 3u));
+    prefetch_l2(P.result_prev + (size_t)(lb * 3u));
+}
+
 #ifndef BMFR_POST_WIDE_ACCESS
 #define BMFR_POST_WIDE_ACCESS 0
 #endif
@@ -262,6 +287,21 @@ __global__ void __launch_bounds__(256, BMFR_POST_MIN_BLOCKS) post_kernel(const _
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int x0 = bx * 32 - 16 + P.off_x, y0 = by * 32 - 16 + P.off_y;  // tile origin in image coordinates
     constexpr int NW = BMFR_FEATURES * 3, NM = BMFR_FEATURES_SCALED * 2;
+
+#if BMFR_POST_PREFETCH
+    // DRAM -> L2 prefetch of the strip's four pixels and of this thread's ring pixel, issued before the
+    // coefficient staging so that its latency overlaps with it
+    {
+        const int px = x0 + lane;
+        if (px >= 0 && px < P.W) {
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                const int py = y0 + 4 * warp + s;
+                if (py >= P.py0 && py < P.py1) prefetch_pixel(P, px, py);
+            }
+        }
+    }
+#endif
 
     // coefficients of the 3x3 block neighbourhood -> shared memory: warp w takes neighbour w (warp 0
     // also the ninth), lanes 0..29 the weights, lanes 0..11 the (min, 1/range) pairs
@@ -286,6 +326,15 @@ __global__ void __launch_bounds__(256, BMFR_POST_MIN_BLOCKS) post_kernel(const _
         const bool v0 = col_ok && y >= P.py0 && y < P.py1, v1 = col_ok && y + 1 >= P.py0 && y + 1 < P.py1;
         if (v0 && v1) {
             const PixelIn i0 = load_pixel<WIDE>(P, x, y), i1 = load_pixel<WIDE>(P, x, y + 1);
+#if BMFR_POST_PREFETCH
+            if (s == 0 && P.frame > 0) {  // while this pair is processed, pull the next pair's gather targets into L2
+                const int yn = y + 2;
+                if (yn >= P.py0 && yn + 1 < P.py1) {
+                    prefetch_taps(P, __ldg(P.prev_pixels + pix_index(P, x, yn)));
+                    prefetch_taps(P, __ldg(P.prev_pixels + pix_index(P, x, yn + 1)));
+                }
+            }
+#endif
             f3 fl0, fl1;
             weighted_sum_px2(i0.n, i0.p, i1.n, i1.p, sh.coef[4], fl0, fl1);
             const bool own0 = y >= P.own_y0 && y < P.own_y1, own1 = y + 1 >= P.own_y0 && y + 1 < P.own_y1;
