@@ -1,13 +1,15 @@
 // FUSED mode, first half of the frame: accumulate_noisy_data + fitter (bmfr.cl:290-485, 490-700)
 // as two sm_100a kernels sized for what each phase is bound by:
 //
-//   reproject_kernel  : K1 for every image pixel, one thread per pixel at full occupancy (gather
-//                       latency bound).  Writes the four per-pixel outputs of bmfr.cl:478-484.
-//                       The block-planar tmp_data of the reference is never written.
+//   reproject_kernel  : K1 for every image pixel, four pixels per thread with the next pixel's world
+//                       position fetched one pixel ahead (gather-latency bound).  Writes the four
+//                       per-pixel outputs of bmfr.cl:478-484 and, in its first CTAs, the frame's noise
+//                       tile.  The block-planar tmp_data of the reference is never written.
 //   fit_qr_kernel     : persistent warp-specialised CTAs walking over the 32x32 blocks.  Four
 //                       compute warps rebuild the block's 1024x13 matrix in registers from the
-//                       per-pixel buffers (mirrored margins included, bmfr.cl:314-316; prefetched
-//                       with cp.async one block ahead), block min/max + scaling + noise
+//                       per-pixel buffers (mirrored margins included, bmfr.cl:314-316; the three
+//                       32x32-pixel input tiles of the next block arrive by TMA while the current
+//                       block is factored), block min/max + scaling + noise
 //                       (bmfr.cl:511-542, 623-627), then each factors its own 256 rows (level 1 of a
 //                       TSQR) without a block barrier.  A fifth warp factors the four stacked
 //                       triangles (level 2) and back-substitutes (bmfr.cl:659-699) concurrently.
@@ -398,13 +400,14 @@ struct QrLoopFull<ROWS, BMFR_FEATURES> {
 // --------------------------------------------------------------------------------------------
 // fit_qr_kernel: persistent, warp-specialised.
 //
-// A CTA is four compute warps and one solver warp and walks over blocks  b = blockIdx.x + i*gridDim.x.
-//   compute warp w, lane l : rows (x_in = l, y_in = 8w .. 8w+7) of the block, eight rows per thread, so
-//       one warp-wide reduction serves 256 matrix rows.  Each thread prefetches its own 72 input
-//       floats of the NEXT block with cp.async into a private shared-memory slot while it factors
-//       the current one (no load phase, no barrier for the data).  Per block: block min/max through
-//       two 128-thread named barriers, scaling + noise, level 1 of the TSQR (this warp's 256 rows ->
-//       one 10x13 triangle) written to a two-slot shared-memory ring.
+// A CTA is four compute warps and one solver warp and walks over blocks: its first block is
+// blockIdx.x, the following ones are drawn from a global counter one block ahead.
+//   compute warp w, lane l : rows (x_in = l, y_in = 8w .. 8w+7) of the block, eight rows per thread (as
+//       four packed fp32 pairs), so one warp-wide reduction serves 256 matrix rows.  Thread 0 draws the
+//       next block, publishes its index and starts the TMA loads of its three input tiles while the
+//       current block is factored (border blocks, which need mirroring, are loaded pixel by pixel).  Per
+//       block: block min/max through one 128-thread named barrier, scaling + noise, level 1 of the TSQR
+//       (this warp's 256 rows -> one 10x13 triangle) written to a two-slot shared-memory ring.
 //   solver warp            : waits for the four triangles of a block (mbarrier), factors the 40
 //       stacked rows (level 2), back-substitutes (bmfr.cl:659-699) and writes the weights, while the
 //       compute warps are already on the next block.
