@@ -14,6 +14,31 @@
 #include "../../include/bmfr_b200.h"
 #include "bmfr_kernels.h"
 
+// Programmatic dependent launch (the FUSED kernels are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization): a kernel may start while its predecessor in the
+// stream is still draining; pdl_wait() blocks until the predecessor has completed and its writes are
+// visible, pdl_trigger() lets the successor's CTAs be scheduled as soon as SM resources free up.  Both
+// are no-ops for a normal launch.  Every kernel of the chain calls pdl_wait() before it completes, so
+// "predecessor complete" is transitive along the frame loop.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// Launch with programmatic stream serialization (host side, all three FUSED kernels).
+template <class... KArgs, class... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 struct f3 {
     float x, y, z;
 };

@@ -41,6 +41,7 @@
 #endif
 template <bool STRIP>
 __global__ void __launch_bounds__(256, BMFR_REPROJECT_MIN_BLOCKS) reproject_kernel(const __grid_constant__ KParams P) {
+    pdl_trigger();  // the fit's CTAs may take SM slots as this grid drains (all they do before their wait is barrier set-up)
     // The first CTAs also produce this frame's add_random() tile (bmfr.cl:173-182; one 9x1024 tile per
     // frame shared by all blocks, fp64 like the reference's double literal plus its fp32 rounding for the
     // fit) and reset the fit's block counter: the fit starts only after this kernel has completed.
@@ -49,6 +50,7 @@ __global__ void __launch_bounds__(256, BMFR_REPROJECT_MIN_BLOCKS) reproject_kern
         const int workers = ncta < 36 ? ncta : 36;
         if (cta < workers) {
             const int n = (BMFR_FEATURES - 1) * BMFR_BLOCK_PIXELS;
+            pdl_wait();  // (the previous frame's kernels are complete: nothing reads the tile or the counter any more)
             for (int i = cta * 256 + threadIdx.y * BMFR_REPROJECT_BX + threadIdx.x; i < n; i += workers * 256) {
                 const int seed = i + BMFR_BLOCK_PIXELS + P.frame * BMFR_BUFFER_COUNT * BMFR_BLOCK_PIXELS;
                 const double d = (P.noise_amount * 2.0) * (double)(bmfr_random((unsigned int)seed) - 0.5f);
@@ -80,6 +82,9 @@ __global__ void __launch_bounds__(256, BMFR_REPROJECT_MIN_BLOCKS) reproject_kern
         if (k + 1 < BMFR_REPROJECT_PIXELS && yn >= ylo && yn < yhi) wp_next = load_f3(P.cur_positions, pix_index(P, x, yn));
         if (y < ylo) continue;
         const K1Pixel r = k1_pixel<STRIP>(P, x, y, wp);
+        // everything above only reads buffers that no kernel in flight writes; prev_pixels / accept are
+        // still being read by the previous frame's post pass until it completes
+        pdl_wait();
         const unsigned int lp = pix_index(P, x, y);
         store_f3(P.cur_noisy_acc, lp, r.new_color);
         P.cur_spp[lp] = r.spp;
@@ -587,6 +592,8 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    pdl_wait();     // the reprojection of this frame is complete (accumulated colour, noise tile, block counter)
+    pdl_trigger();  // after the wait, so that completion of everything before this grid is transitive for the post pass
 
     if (warp == 0) {
         QR_CTA_STAMP(0);
@@ -820,9 +827,8 @@ cudaError_t launch_reproject(const KParams& P, cudaStream_t st) {
     const int rows_per_cta = BMFR_REPROJECT_BY * BMFR_REPROJECT_PIXELS;
     const dim3 grid((P.W + BMFR_REPROJECT_BX - 1) / BMFR_REPROJECT_BX, (P.k1_y1 - P.k1_y0 + rows_per_cta - 1) / rows_per_cta),
         block(BMFR_REPROJECT_BX, BMFR_REPROJECT_BY);
-    if (is_strip(P)) reproject_kernel<true><<<grid, block, 0, st>>>(P);
-    else reproject_kernel<false><<<grid, block, 0, st>>>(P);
-    return cudaGetLastError();
+    if (is_strip(P)) return launch_pdl(reproject_kernel<true>, grid, block, 0, st, P);
+    return launch_pdl(reproject_kernel<false>, grid, block, 0, st, P);
 }
 // ---- tensor maps of a frame --------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -902,7 +908,6 @@ cudaError_t launch_fit_qr(const KParams& P, cudaStream_t st) {
     const int rows = P.row1 - P.row0;
     M.use_tma = tile_map(P.cur_normals, P.W, rows, &M.normals) && tile_map(P.cur_positions, P.W, rows, &M.positions) &&
                 tile_map(P.cur_noisy_acc, P.W, rows, &M.colour);
-    if (is_strip(P)) fit_qr_kernel<true><<<grid, QR_THREADS, smem, st>>>(P, M);
-    else fit_qr_kernel<false><<<grid, QR_THREADS, smem, st>>>(P, M);
-    return cudaGetLastError();
+    if (is_strip(P)) return launch_pdl(fit_qr_kernel<true>, dim3(grid), dim3(QR_THREADS), (size_t)smem, st, P, M);
+    return launch_pdl(fit_qr_kernel<false>, dim3(grid), dim3(QR_THREADS), (size_t)smem, st, P, M);
 }

@@ -287,6 +287,11 @@ __global__ void __launch_bounds__(256, BMFR_POST_MIN_BLOCKS) post_kernel(const _
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int x0 = bx * 32 - 16 + P.off_x, y0 = by * 32 - 16 + P.off_y;  // tile origin in image coordinates
     constexpr int NW = BMFR_FEATURES * 3, NM = BMFR_FEATURES_SCALED * 2;
+    pdl_wait();     // the fit of this frame is complete (weights, min/max)
+    // Only now: a successor (the next frame's reprojection) starts once every CTA of this grid has passed
+    // this point, so "this frame's fit and reprojection are complete" holds for it too — it reads their
+    // outputs before its own wait, and only its stores to prev_pixels / accept wait for this grid.
+    pdl_trigger();
 
 #if BMFR_POST_PREFETCH
     // DRAM -> L2 prefetch of the strip's four pixels and of this thread's ring pixel, issued before the
@@ -421,11 +426,9 @@ cudaError_t launch_post(const KParams& P, cudaStream_t st) {
     // arithmetic) and the same number of L1 wavefronts, so it is kept only as a tuning switch
     const bool wide = BMFR_POST_WIDE_ACCESS && (bits & 7) == 0;
     if (strip) {
-        if (wide) post_kernel<true, true><<<grid, 256, 0, st>>>(P);
-        else post_kernel<true, false><<<grid, 256, 0, st>>>(P);
-    } else {
-        if (wide) post_kernel<false, true><<<grid, 256, 0, st>>>(P);
-        else post_kernel<false, false><<<grid, 256, 0, st>>>(P);
+        if (wide) return launch_pdl(post_kernel<true, true>, grid, dim3(256), 0, st, P);
+        return launch_pdl(post_kernel<true, false>, grid, dim3(256), 0, st, P);
     }
-    return cudaGetLastError();
+    if (wide) return launch_pdl(post_kernel<false, true>, grid, dim3(256), 0, st, P);
+    return launch_pdl(post_kernel<false, false>, grid, dim3(256), 0, st, P);
 }
