@@ -522,13 +522,17 @@ __device__ __forceinline__ bool qr_block_is_interior(const KParams& P, int bx, i
     const int x0 = bx * 32 - 16 + P.off_x, y0 = by * 32 - 16 + P.off_y;
     return x0 >= 0 && x0 + 32 <= P.W && y0 >= P.row0 && y0 + 32 <= P.row1;
 }
-// One thread: arm the barrier and start the three tile loads of block (bx, by).
-__device__ __forceinline__ void qr_prefetch(const KParams& P, const QrMaps& M, QrShared& sh, int bx, int by) {
+// One thread: arm the barrier and start the three tile loads of block (bx, by).  part 0: everything;
+// part 1: the caller's inputs only (normals, positions — they do not depend on this frame's
+// reprojection and can be requested before the grid dependency is resolved); part 2: the colour tile.
+__device__ __forceinline__ void qr_prefetch(const KParams& P, const QrMaps& M, QrShared& sh, int bx, int by, int part = 0) {
     const int c0 = ((bx * 32 - 16 + P.off_x) * 3) & ~3, c1 = by * 32 - 16 + P.off_y - P.row0;
-    mbar_expect_tx(&sh.data_full, 3 * QR_TILE_BYTES);
-    tma_load_tile(&sh.stage[0][0][0], &M.normals, c0, c1, &sh.data_full);
-    tma_load_tile(&sh.stage[1][0][0], &M.positions, c0, c1, &sh.data_full);
-    tma_load_tile(&sh.stage[2][0][0], &M.colour, c0, c1, &sh.data_full);
+    if (part != 2) {
+        mbar_expect_tx(&sh.data_full, 3 * QR_TILE_BYTES);
+        tma_load_tile(&sh.stage[0][0][0], &M.normals, c0, c1, &sh.data_full);
+        tma_load_tile(&sh.stage[1][0][0], &M.positions, c0, c1, &sh.data_full);
+    }
+    if (part != 1) tma_load_tile(&sh.stage[2][0][0], &M.colour, c0, c1, &sh.data_full);
 }
 
 #ifndef BMFR_QR_MIN_BLOCKS
@@ -592,6 +596,9 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    // before the grid dependency: the first block's normals / positions tiles (the caller's inputs)
+    const bool first_by_tma = M.use_tma && qr_block_is_interior(P, first % P.blocks_x, P.by0 + first / P.blocks_x);
+    if (tid == 0 && first_by_tma) qr_prefetch(P, M, sh, first % P.blocks_x, P.by0 + first / P.blocks_x, 1);
     pdl_wait();     // the reprojection of this frame is complete (accumulated colour, noise tile, block counter)
     pdl_trigger();  // after the wait, so that completion of everything before this grid is transitive for the post pass
 
@@ -673,7 +680,7 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
     if (tid == 0) {
         const int bx0 = first % P.blocks_x, by0 = P.by0 + first / P.blocks_x;
         sh.blk[0] = first;
-        if (M.use_tma && qr_block_is_interior(P, bx0, by0)) qr_prefetch(P, M, sh, bx0, by0);
+        if (first_by_tma) qr_prefetch(P, M, sh, bx0, by0, 2);
         else mbar_arrive(&sh.data_full);
     }
     int it = 0;

@@ -248,8 +248,11 @@ __device__ __forceinline__ bool phase_a_pixel(PostShared& sh, const KParams& P, 
     return finish_pixel<STRIP, WIDE>(sh, P, in, weighted_sum_px(in.n, in.p, cf), hx, hy, x, y, store, own, hist);
 }
 
+#ifndef BMFR_POST_PREFETCH_TAPS
+#define BMFR_POST_PREFETCH_TAPS 0  // measured: no effect
+#endif
 #ifndef BMFR_POST_PREFETCH
-#define BMFR_POST_PREFETCH 0  // measured on B200: no effect (68.4 vs 67.7 us), kept as a tuning switch
+#define BMFR_POST_PREFETCH 1  // L2 prefetch of the pixel inputs before the wait for the fit (see the kernel)
 #endif
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // Starts the DRAM -> L2 fetch of everything phase A reads at pixel (x,y) (no registers are tied up); the
@@ -287,15 +290,9 @@ __global__ void __launch_bounds__(256, BMFR_POST_MIN_BLOCKS) post_kernel(const _
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int x0 = bx * 32 - 16 + P.off_x, y0 = by * 32 - 16 + P.off_y;  // tile origin in image coordinates
     constexpr int NW = BMFR_FEATURES * 3, NM = BMFR_FEATURES_SCALED * 2;
-    pdl_wait();     // the fit of this frame is complete (weights, min/max)
-    // Only now: a successor (the next frame's reprojection) starts once every CTA of this grid has passed
-    // this point, so "this frame's fit and reprojection are complete" holds for it too — it reads their
-    // outputs before its own wait, and only its stores to prev_pixels / accept wait for this grid.
-    pdl_trigger();
-
 #if BMFR_POST_PREFETCH
     // DRAM -> L2 prefetch of the strip's four pixels and of this thread's ring pixel, issued before the
-    // coefficient staging so that its latency overlaps with it
+    // wait for the fit: CTAs that became resident while the fit drains warm the L2 for their pixels
     {
         const int px = x0 + lane;
         if (px >= 0 && px < P.W) {
@@ -307,6 +304,12 @@ __global__ void __launch_bounds__(256, BMFR_POST_MIN_BLOCKS) post_kernel(const _
         }
     }
 #endif
+    pdl_wait();     // the fit of this frame is complete (weights, min/max)
+    // Only now: a successor (the next frame's reprojection) starts once every CTA of this grid has passed
+    // this point, so "this frame's fit and reprojection are complete" holds for it too — it reads their
+    // outputs before its own wait, and only its stores to prev_pixels / accept wait for this grid.
+    pdl_trigger();
+
 
     // coefficients of the 3x3 block neighbourhood -> shared memory: warp w takes neighbour w (warp 0
     // also the ninth), lanes 0..29 the weights, lanes 0..11 the (min, 1/range) pairs
@@ -331,7 +334,7 @@ __global__ void __launch_bounds__(256, BMFR_POST_MIN_BLOCKS) post_kernel(const _
         const bool v0 = col_ok && y >= P.py0 && y < P.py1, v1 = col_ok && y + 1 >= P.py0 && y + 1 < P.py1;
         if (v0 && v1) {
             const PixelIn i0 = load_pixel<WIDE>(P, x, y), i1 = load_pixel<WIDE>(P, x, y + 1);
-#if BMFR_POST_PREFETCH
+#if BMFR_POST_PREFETCH_TAPS
             if (s == 0 && P.frame > 0) {  // while this pair is processed, pull the next pair's gather targets into L2
                 const int yn = y + 2;
                 if (yn >= P.py0 && yn + 1 < P.py1) {
