@@ -17,7 +17,7 @@ CSRC = ROOT / "bmfr_b200" / "csrc"
 LIB = ROOT / "bmfr_b200" / "libbmfr_b200.so"
 BUILD_DIR = ROOT / "bmfr_b200" / "_build"
 
-CUDA_SOURCES = ["bmfr_kernels.cu", "bmfr_fit.cu", "bmfr_post.cu", "bmfr_pipeline.cu", "synth.cu"]
+CUDA_SOURCES = ["bmfr_kernels.cu", "bmfr_reforder.cu", "bmfr_fit.cu", "bmfr_post.cu", "bmfr_pipeline.cu", "synth.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

@@ -2,6 +2,8 @@
 //   STAGED : the reference's five kernels (bmfr.cl:290,490,703,761,860), one launch each
 //   FUSED  : bmfr_fit.cu (reproject + fit) and bmfr_post.cu (weighted sum + accumulation + taa)
 // Compiled with --fmad=false; see bmfr_device.cuh for the arithmetic convention.
+#include <cuda_fp16.h>
+
 #include "bmfr_kernels.h"
 
 #include "bmfr_device.cuh"
@@ -28,7 +30,8 @@ __global__ void noise_tile_kernel(double* __restrict__ noise, float* __restrict_
 // --------------------------------------------------------------------------------------------
 // STAGED K1: one thread per work-item of the margin-extended domain (bmfr.cl:310-484).
 // --------------------------------------------------------------------------------------------
-template <bool STRIP>
+// HALF: USE_HALF_PRECISION_IN_TMP_DATA = 1 — clamp to the fp16 range, store rounded to fp16 (bmfr.cl:471-473)
+template <bool STRIP, bool HALF>
 __global__ void __launch_bounds__(256) k1_accumulate_noisy_kernel(const __grid_constant__ KParams P) {
     const int gx = blockIdx.x * 32 + threadIdx.x;
     const int gy = P.by0 * 32 + blockIdx.y * 8 + threadIdx.y;
@@ -42,10 +45,15 @@ __global__ void __launch_bounds__(256) k1_accumulate_noisy_kernel(const __grid_c
     float f[BMFR_BUFFER_COUNT];
     k1_features(r, f);
     const int bx = gx >> 5, by = gy >> 5;
-    float* t = P.tmp_data + ((size_t)((by - P.by0) * P.blocks_x + bx) * BMFR_BUFFER_COUNT) * BMFR_BLOCK_PIXELS +
-               (gy & 31) * 32 + (gx & 31);
+    const size_t t0 = ((size_t)((by - P.by0) * P.blocks_x + bx) * BMFR_BUFFER_COUNT) * BMFR_BLOCK_PIXELS + (gy & 31) * 32 + (gx & 31);
 #pragma unroll
-    for (int i = 0; i < BMFR_BUFFER_COUNT; ++i) t[(size_t)i * BMFR_BLOCK_PIXELS] = f[i];
+    for (int i = 0; i < BMFR_BUFFER_COUNT; ++i) {
+        if (HALF)
+            reinterpret_cast<__half*>(P.tmp_data)[t0 + (size_t)i * BMFR_BLOCK_PIXELS] =
+                __float2half_rn(fmaxf(fminf(f[i], 65504.f), -65504.f));
+        else
+            P.tmp_data[t0 + (size_t)i * BMFR_BLOCK_PIXELS] = f[i];
+    }
     if (ux >= 0 && ux < P.W && uy >= 0 && uy < P.H) {  // bmfr.cl:478-484
         const size_t lp = pix_index(P, x, y);
         store_f3(P.cur_noisy_acc, lp, r.new_color);
@@ -154,8 +162,13 @@ static dim3 pixel_grid(const KParams& P, int y0, int y1) { return dim3((P.W + 31
 
 cudaError_t launch_k1(const KParams& P, cudaStream_t st) {
     dim3 grid(P.blocks_x, (P.by1 - P.by0) * 4), block(32, 8);
-    if (is_strip(P)) k1_accumulate_noisy_kernel<true><<<grid, block, 0, st>>>(P);
-    else k1_accumulate_noisy_kernel<false><<<grid, block, 0, st>>>(P);
+    if (P.tmp_half) {
+        if (is_strip(P)) k1_accumulate_noisy_kernel<true, true><<<grid, block, 0, st>>>(P);
+        else k1_accumulate_noisy_kernel<false, true><<<grid, block, 0, st>>>(P);
+    } else {
+        if (is_strip(P)) k1_accumulate_noisy_kernel<true, false><<<grid, block, 0, st>>>(P);
+        else k1_accumulate_noisy_kernel<false, false><<<grid, block, 0, st>>>(P);
+    }
     return cudaGetLastError();
 }
 cudaError_t launch_k2(const KParams& P, cudaStream_t st) {

@@ -36,7 +36,8 @@ struct KParams {
     unsigned char* cur_spp;
     float2* prev_pixels;          // out_prev_frame_pixel / in_prev_frame_pixel
     unsigned char* accept;        // accept_bools
-    float* tmp_data;              // STAGED only
+    float* tmp_data;              // STAGED only (fp16 elements when tmp_half)
+    int tmp_half, reference_order;
     float* weights;
     float* mins_maxs;
     float* mins_inv;              // (min, 1/range or 1) per block and scaled feature, see scale_factor()
@@ -62,6 +63,8 @@ void bmfr_host_block_offset(int frame, int* ox, int* oy);
 cudaError_t launch_noise_tile(double* d_noise, float* d_noise_f, int* block_counter, double noise_amount, int frame, cudaStream_t st);
 cudaError_t launch_k1(const KParams& P, cudaStream_t st);
 cudaError_t launch_k2(const KParams& P, cudaStream_t st);
+cudaError_t launch_k2_reference_order(const KParams& P, bool half, cudaStream_t st);
+cudaError_t launch_k3_reference_order(const KParams& P, cudaStream_t st);
 cudaError_t launch_k3(const KParams& P, cudaStream_t st);
 cudaError_t launch_k4(const KParams& P, cudaStream_t st);
 cudaError_t launch_k5(const KParams& P, cudaStream_t st);

@@ -230,9 +230,10 @@ int bmfr_create(const bmfr_params* params, bmfr_ctx** out_ctx) {
     }
     if (p.mode != BMFR_MODE_STAGED && p.mode != BMFR_MODE_FUSED)
         return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_create: unknown mode %d", p.mode);
-    if (p.tmp_half != 0)
+    if ((p.tmp_half != 0 || p.reference_order != 0) && p.mode != BMFR_MODE_STAGED)
         return bmfr_set_error(BMFR_ERR_UNSUPPORTED,
-                              "bmfr_create: USE_HALF_PRECISION_IN_TMP_DATA=1 is not built (fp32 fitter only)");
+                              "bmfr_create: tmp_half / reference_order are the STAGED compatibility path (the FUSED fit is fp32 and "
+                              "keeps tmp_data in registers)");
     const bool whole = (p.strip_y0 == 0 && p.strip_y1 == 0);
     if (!whole && (p.strip_y0 < 0 || p.strip_y1 > p.height || p.strip_y0 >= p.strip_y1 || p.halo_rows < 0))
         return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_create: bad strip [%d,%d) halo %d", p.strip_y0,
@@ -250,6 +251,7 @@ int bmfr_create(const bmfr_params* params, bmfr_ctx** out_ctx) {
     bmfr_ctx* c = new (std::nothrow) bmfr_ctx();
     if (!c) return bmfr_set_error(BMFR_ERR_OUT_OF_MEMORY, "bmfr_create: host allocation failed");
     c->prm = p;
+    if (c->prm.tmp_half) c->prm.reference_order = 1;  // fp16 rounding of every tmp_data store only exists in the reference's schedule
     bmfr_geometry& g = c->geo;
     g.width = p.width;
     g.height = p.height;
@@ -370,6 +372,7 @@ static void fill_params(bmfr_ctx* c, KParams& P, int frame, const float* d_albed
     P.prev_noisy_acc = c->noisy_acc.previous(); P.cur_noisy_acc = c->noisy_acc.current();
     P.prev_spp = c->spp.previous(); P.cur_spp = c->spp.current();
     P.prev_pixels = c->prev_pixels; P.accept = c->accept;
+    P.tmp_half = c->prm.tmp_half; P.reference_order = c->prm.reference_order;
     P.tmp_data = c->tmp_data; P.weights = c->weights; P.mins_maxs = c->mins_maxs; P.mins_inv = c->mins_inv; P.noise = c->noise;
     P.noise_f = c->noise_f; P.noise_out = c->noise; P.noise_f_out = c->noise_f; P.noise_amount = c->prm.noise_amount;
     P.albedo = d_albedo; P.filtered = c->filtered;
@@ -413,9 +416,11 @@ static int run_frame(bmfr_ctx* c, const KParams& P, int frame) {
         LAUNCH_TRY(launch_k1(P, c->stream), "accumulate_noisy_data");
         MARK(1);
         { int hs = halo_push_early(c); if (hs != 0) return hs; }
-        LAUNCH_TRY(launch_k2(P, c->stream), "fitter");
+        if (c->prm.reference_order) LAUNCH_TRY(launch_k2_reference_order(P, c->prm.tmp_half != 0, c->stream), "fitter (reference order)");
+        else LAUNCH_TRY(launch_k2(P, c->stream), "fitter");
         MARK(2);
-        LAUNCH_TRY(launch_k3(P, c->stream), "weighted_sum");
+        if (c->prm.reference_order) LAUNCH_TRY(launch_k3_reference_order(P, c->stream), "weighted_sum (reference order)");
+        else LAUNCH_TRY(launch_k3(P, c->stream), "weighted_sum");
         MARK(3);
         LAUNCH_TRY(launch_k4(P, c->stream), "accumulate_filtered_data");
         MARK(4);

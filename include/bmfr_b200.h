@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define BMFR_B200_ABI_VERSION 1
+#define BMFR_B200_ABI_VERSION 2
 
 /* Compile-time constants of the reference that are not tunable (bmfr.cpp:102-118). */
 #define BMFR_BLOCK_EDGE 32          /* BLOCK_EDGE_LENGTH, bmfr.cpp:104 */
@@ -65,7 +65,8 @@ typedef struct bmfr_params {
     float taa_blend_alpha;        /* TAA_BLEND_ALPHA,    bmfr.cpp:62 */
     float position_limit_squared; /* POSITION_LIMIT_SQUARED, bmfr.cpp:226 */
     float normal_limit_squared;   /* NORMAL_LIMIT_SQUARED,   bmfr.cpp:227 */
-    int tmp_half;                 /* USE_HALF_PRECISION_IN_TMP_DATA, bmfr.cpp:88; only 0 (fp32) is built */
+    int tmp_half;                 /* USE_HALF_PRECISION_IN_TMP_DATA, bmfr.cpp:88 (the reference ships 1; the default here
+                                     is 0 = fp32 fitter).  1 needs mode = STAGED and implies reference_order = 1 */
     int profile;                  /* 1: record per-stage CUDA-event times (bmfr.cpp:386-397) */
     /* Strip sharding (no counterpart in the reference, which is single-device).  The context owns
      * image rows [strip_y0, strip_y1) and stores rows [strip_y0 - halo_rows, strip_y1 + halo_rows)
@@ -74,6 +75,11 @@ typedef struct bmfr_params {
     int strip_y1;
     int halo_rows;
     void* stream;                 /* cudaStream_t to enqueue on; NULL: the context creates one */
+    /* STAGED only.  1: the fitter and the weighted sum run in the reference's own operation order
+     * (256-thread groups, the reduction trees of bmfr.cl:26-87, 13 Householder columns, division in
+     * scale()), which makes EVERY buffer of the loop bit-identical to the reference kernels' arithmetic
+     * — the compatibility mode; slower than the default fitter. */
+    int reference_order;
 } bmfr_params;
 
 typedef struct bmfr_ctx bmfr_ctx;

@@ -80,6 +80,25 @@ def test_nan_and_far_inputs_follow_the_oracle():
     o.close()
 
 
+@pytest.mark.parametrize("half", [0, 1], ids=["fp32_tmp", "fp16_tmp"])
+@pytest.mark.parametrize("size", [(160, 96), (200, 120)])
+def test_reference_order_mode_is_bit_identical(size, half):
+    """STAGED with reference_order=1 evaluates the fitter and the weighted sum in the reference's own
+    operation order: every buffer up to the accumulated colour — the fit coefficients included — is
+    bit-identical to the oracle, for the fp32 tmp_data of the north star and for the reference's shipped
+    default USE_HALF_PRECISION_IN_TMP_DATA=1 (bmfr.cpp:88).  Only the tone map (powr: 16 ulp in OpenCL,
+    different libm implementations) keeps tone_mapped / result within tolerance."""
+    w, h = size
+    keep = ("noisy_acc", "spp", "prev_pixels", "accept", "weights", "mins_maxs", "filtered", "accum", "tone_mapped", "result")
+    ref = util.run_oracle("port", w, h, 18, keep=keep, tmp_half=half)
+    cuda = util.run_cuda(w, h, 18, mode="staged", keep=keep, tmp_half=half, reference_order=1)
+    for f, (c, r) in enumerate(zip(cuda, ref)):
+        for k in ("noisy_acc", "spp", "prev_pixels", "accept", "mins_maxs", "weights", "filtered", "accum"):
+            assert util.bits_equal(c[k], r[k]), f"frame {f}: {k} differs in {(c[k] != r[k]).sum()} elements"
+        for k in ("tone_mapped", "result"):
+            util.assert_colour_close(c[k], r[k], f"frame {f} {k}")
+
+
 def test_jittered_offsets_match_oracle():
     ref = util.run_oracle("port", 200, 120, 8, keep=KEEP_FUSED, jitter=True)
     cuda = util.run_cuda(200, 120, 8, mode="fused", keep=KEEP_FUSED, jitter=True)
