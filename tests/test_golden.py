@@ -66,3 +66,18 @@ def test_cuda_matches_golden(backend):
             for k in ("accum", "result"):
                 util.assert_colour_close(r.get(k), GOLD[f"f{f}_{k}"], f"frame {f} {k}")
     r.close()
+
+
+@pytest.mark.gpu
+def test_reference_order_mode_reproduces_the_reference_kernels_bits():
+    """STAGED + reference_order against the SHA-256 of the buffers the reference's own kernels produced
+    (tests/golden/make_golden.py): the fit coefficients, the weighted sum and the accumulated colour are
+    the reference's bits, not just the reprojection outputs."""
+    from bmfr_b200 import Denoiser
+    d = Denoiser(META["width"], META["height"], mode="staged", reference_order=1,
+                 position_limit_squared=META["position_limit_squared"], normal_limit_squared=META["normal_limit_squared"])
+    for f, *arrs in frames():
+        d.denoise_frame_host(f, *arrs)
+        for k in ("spp", "accept", "noisy_acc", "prev_pixels", "mins_maxs", "weights", "filtered", "accum"):
+            assert sha(d.read(k)) == META["buffer_sha256"][f][k], f"frame {f}: {k}"
+    d.close()
