@@ -39,6 +39,10 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
     return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
+#ifndef BMFR_STREAM_LOADS
+#define BMFR_STREAM_LOADS 0
+#endif
+
 struct f3 {
     float x, y, z;
 };
@@ -48,6 +52,21 @@ __device__ __forceinline__ f3 make_f3(float x, float y, float z) { return f3{x, 
 __device__ __forceinline__ f3 load_f3(const float* __restrict__ b, unsigned int i) {
     const float* p = b + (size_t)(i * 3u);
     return f3{__ldg(p), __ldg(p + 1), __ldg(p + 2)};
+}
+// Read-once (streaming) data: do not allocate the line in L1, so that the L1 keeps the lines the 4-tap
+// gathers share between neighbouring pixels.
+__device__ __forceinline__ float ldg_stream(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ f3 load_f3_stream(const float* __restrict__ b, unsigned int i) {
+#if BMFR_STREAM_LOADS
+    const float* p = b + (size_t)(i * 3u);
+    return f3{ldg_stream(p), ldg_stream(p + 1), ldg_stream(p + 2)};
+#else
+    return load_f3(b, i);
+#endif
 }
 __device__ __forceinline__ void store_f3(float* __restrict__ b, unsigned int i, f3 v) {
     float* p = b + (size_t)(i * 3u);
@@ -154,8 +173,8 @@ template <bool STRIP>
 __device__ __forceinline__ K1Pixel k1_pixel(const KParams& P, int x, int y, f3 wp) {
     K1Pixel r;
     const unsigned int lp = pix_index(P, x, y);
-    const f3 n = load_f3(P.cur_normals, lp);
-    const f3 cur = load_f3(P.cur_noisy, lp);
+    const f3 n = load_f3_stream(P.cur_normals, lp);
+    const f3 cur = load_f3_stream(P.cur_noisy, lp);
     float pfx = (float)x, pfy = (float)y;  // bmfr.cl:325
     unsigned int accept = 0;
     float blend_alpha = 1.f;

@@ -72,14 +72,14 @@ __global__ void __launch_bounds__(256, BMFR_REPROJECT_MIN_BLOCKS) reproject_kern
     // software pipeline over the thread's pixels: position of pixel k+1 in flight while pixel k runs its
     // reprojection -> tap gather chain
     f3 wp_next = make_f3(0.f, 0.f, 0.f);
-    if (ybase >= ylo && ybase < yhi) wp_next = load_f3(P.cur_positions, pix_index(P, x, ybase));
+    if (ybase >= ylo && ybase < yhi) wp_next = load_f3_stream(P.cur_positions, pix_index(P, x, ybase));
 #pragma unroll 1
     for (int k = 0; k < BMFR_REPROJECT_PIXELS; ++k) {
         const int y = ybase + k * BMFR_REPROJECT_BY;
         if (y >= yhi) break;
         const f3 wp = wp_next;
         const int yn = y + BMFR_REPROJECT_BY;
-        if (k + 1 < BMFR_REPROJECT_PIXELS && yn >= ylo && yn < yhi) wp_next = load_f3(P.cur_positions, pix_index(P, x, yn));
+        if (k + 1 < BMFR_REPROJECT_PIXELS && yn >= ylo && yn < yhi) wp_next = load_f3_stream(P.cur_positions, pix_index(P, x, yn));
         if (y < ylo) continue;
         const K1Pixel r = k1_pixel<STRIP>(P, x, y, wp);
         // everything above only reads buffers that no kernel in flight writes; prev_pixels / accept are

@@ -225,9 +225,9 @@ template <bool WIDE>
 __device__ __forceinline__ PixelIn load_pixel(const KParams& P, int x, int y) {
     PixelIn in;
     in.lp = pix_index(P, x, y);
-    in.n = ldf3<WIDE>(P.cur_normals, in.lp);
-    in.p = ldf3<WIDE>(P.cur_positions, in.lp);
-    in.alb = ldf3<WIDE>(P.albedo, in.lp);
+    in.n = WIDE ? load_f3_wide(P.cur_normals, in.lp) : load_f3_stream(P.cur_normals, in.lp);
+    in.p = WIDE ? load_f3_wide(P.cur_positions, in.lp) : load_f3_stream(P.cur_positions, in.lp);
+    in.alb = WIDE ? load_f3_wide(P.albedo, in.lp) : load_f3_stream(P.albedo, in.lp);
     in.accept = __ldg(P.accept + in.lp);
     in.spp = __ldg(const_cast<const unsigned char*>(P.cur_spp) + in.lp);
     in.pp = __ldg(P.prev_pixels + in.lp);
