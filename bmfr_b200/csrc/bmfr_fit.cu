@@ -535,24 +535,6 @@ __device__ __forceinline__ void qr_prefetch(const KParams& P, const QrMaps& M, Q
     if (part != 1) tma_load_tile(&sh.stage[2][0][0], &M.colour, c0, c1, &sh.data_full);
 }
 
-// The 12 non-constant K1 values of one matrix row (bmfr.cl:448-453) from the pixel's normal, position
-// and accumulated colour, NaN -> 0 (bmfr.cl:468-469).  NaNs are rare: one sum detects "any NaN in the
-// nine inputs" (an inf - inf false positive only takes the exact path too).
-__device__ __forceinline__ void qr_row(const float (&v)[9], float (&row)[BMFR_BUFFER_COUNT - 1]) {
-    float w[9];
-#pragma unroll
-    for (int c = 0; c < 9; ++c) w[c] = v[c];
-    const float probe = (((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]))) + v[8];
-    if (probe != probe) {
-#pragma unroll
-        for (int c = 0; c < 9; ++c) w[c] = scrub_nan(v[c]);
-    }
-    row[0] = w[0]; row[1] = w[1]; row[2] = w[2];
-    row[3] = w[3]; row[4] = w[4]; row[5] = w[5];
-    row[6] = w[3] * w[3]; row[7] = w[4] * w[4]; row[8] = w[5] * w[5];
-    row[9] = w[6]; row[10] = w[7]; row[11] = w[8];
-}
-
 #ifndef BMFR_QR_MIN_BLOCKS
 #define BMFR_QR_MIN_BLOCKS 3
 #endif
@@ -720,8 +702,11 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
             for (int s = 0; s < ROWS; ++s) {
                 float v[9];
 #pragma unroll
-                for (int c = 0; c < 9; ++c) v[c] = sh.stage[c / 3][warp * ROWS + s][col + c % 3];
-                qr_row(v, a[s]);
+                for (int c = 0; c < 9; ++c) v[c] = scrub_nan(sh.stage[c / 3][warp * ROWS + s][col + c % 3]);
+                a[s][0] = v[0]; a[s][1] = v[1]; a[s][2] = v[2];
+                a[s][3] = v[3]; a[s][4] = v[4]; a[s][5] = v[5];
+                a[s][6] = v[3] * v[3]; a[s][7] = v[4] * v[4]; a[s][8] = v[5] * v[5];
+                a[s][9] = v[6]; a[s][10] = v[7]; a[s][11] = v[8];
             }
         } else {  // border block: mirrored pixel by pixel
             const int x = mirror_index(bx * 32 + lane - 16 + P.off_x, P.W);
@@ -738,8 +723,11 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
                 const f3 n = load_f3(P.cur_normals, lp);
                 const f3 p = load_f3(P.cur_positions, lp);
                 const f3 col = load_f3(P.cur_noisy_acc, lp);
-                const float v[9] = {n.x, n.y, n.z, p.x, p.y, p.z, col.x, col.y, col.z};
-                qr_row(v, a[s]);
+                const float px = scrub_nan(p.x), py = scrub_nan(p.y), pz = scrub_nan(p.z);
+                a[s][0] = scrub_nan(n.x); a[s][1] = scrub_nan(n.y); a[s][2] = scrub_nan(n.z);
+                a[s][3] = px; a[s][4] = py; a[s][5] = pz;
+                a[s][6] = px * px; a[s][7] = py * py; a[s][8] = pz * pz;
+                a[s][9] = scrub_nan(col.x); a[s][10] = scrub_nan(col.y); a[s][11] = scrub_nan(col.z);
             }
         }
         if (warp == 0) QR_STAMP(0, it, 1);
@@ -799,31 +787,31 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
         // reference adds a double (NOISE_AMOUNT is a double literal); the tile holds that double
         // rounded to fp32, which changes a sum by at most one ulp in rare ties — below the fit's own
         // rounding.
-        // Row pairs from here on (rows 2h, 2h+1 in one 64-bit register pair): packed subtract, multiply, add.
-        float2 a2[ROWS / 2][BMFR_BUFFER_COUNT - 1];
 #pragma unroll
-        for (int h = 0; h < ROWS / 2; ++h) {
+        for (int s = 0; s < ROWS; ++s) {
 #pragma unroll
-            for (int c = 0; c < BMFR_BUFFER_COUNT - 1; ++c) a2[h][c] = make_float2(a[2 * h][c], a[2 * h + 1][c]);
+            for (int f = 0; f < NSC; ++f) a[s][NNS - 1 + f] = scale_feature(a[s][NNS - 1 + f], mn[f], inv[f]);
 #pragma unroll
-            for (int f = 0; f < NSC; ++f)
-                a2[h][NNS - 1 + f] = fmul2(fsub2(a2[h][NNS - 1 + f], dup2(mn[f])), dup2(inv[f]));  // (v - min) * 1/range
-#pragma unroll
-            for (int c = 1; c < BMFR_FEATURES; ++c) {
-                const float* nz = &P.noise_f[(c - 1) * BMFR_BLOCK_PIXELS + (warp * ROWS + 2 * h) * 32 + lane];
-                a2[h][c - 1] = fadd2(a2[h][c - 1], make_float2(__ldg(nz), __ldg(nz + 32)));
-            }
+            for (int c = 1; c < BMFR_FEATURES; ++c)
+                a[s][c - 1] += __ldg(&P.noise_f[(c - 1) * BMFR_BLOCK_PIXELS + (warp * ROWS + s) * 32 + lane]);
         }
 
         // (ii) level 1 of the TSQR: this warp's 256 rows -> one 10x13 triangle in the ring slot
         if (warp == 0) QR_STAMP(0, it, 4);
         if (it >= QR_SLOTS) mbar_wait(&sh.empty[slot], ((it / QR_SLOTS) - 1) & 1);
         if (warp == 0) QR_STAMP(0, it, 5);
+        {
+            float2 a2[ROWS / 2][BMFR_BUFFER_COUNT - 1];
+#pragma unroll
+            for (int h = 0; h < ROWS / 2; ++h)
+#pragma unroll
+                for (int c = 0; c < BMFR_BUFFER_COUNT - 1; ++c) a2[h][c] = make_float2(a[2 * h][c], a[2 * h + 1][c]);
 #if BMFR_QR_SMEM_REDUCE
-        QrLoop2<ROWS / 2, 0>::run(a2, &sh.red[warp][0][0], sh.coef[warp], sh.tri[slot][warp], lane);
+            QrLoop2<ROWS / 2, 0>::run(a2, &sh.red[warp][0][0], sh.coef[warp], sh.tri[slot][warp], lane);
 #else
-        QrLoop2<ROWS / 2, 0>::run(a2, nullptr, nullptr, sh.tri[slot][warp], lane);
+            QrLoop2<ROWS / 2, 0>::run(a2, nullptr, nullptr, sh.tri[slot][warp], lane);
 #endif
+        }
         if (tid == 0) sh.slot_block[slot] = local;
         mbar_arrive(&sh.full[slot]);
         if (warp == 0) QR_STAMP(0, it, 6);
