@@ -280,16 +280,11 @@ __device__ __forceinline__ void prefetch_taps(const KParams& P, float2 pp) {
 #define BMFR_POST_WIDE_ACCESS 0
 #endif
 #ifndef BMFR_POST_MIN_BLOCKS
-#define BMFR_POST_MIN_BLOCKS 4
+#define BMFR_POST_MIN_BLOCKS 5
 #endif
-// Eight interior warps (one 32x4 strip set each) + two ring warps: the 132 ring pixels run beside the
-// interior instead of after it, which shortens a CTA's phase A from three dependent pixel rounds to two.
-#define PT_INTERIOR_WARPS 8
-#define PT_RING_WARPS 2
-#define PT_THREADS ((PT_INTERIOR_WARPS + PT_RING_WARPS) * 32)
 
 template <bool STRIP, bool WIDE>
-__global__ void __launch_bounds__(PT_THREADS, BMFR_POST_MIN_BLOCKS) post_kernel(const __grid_constant__ KParams P) {
+__global__ void __launch_bounds__(256, BMFR_POST_MIN_BLOCKS) post_kernel(const __grid_constant__ KParams P) {
     __shared__ __align__(16) PostShared sh;
     const int bx = blockIdx.x, by = P.by0 + blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -300,7 +295,7 @@ __global__ void __launch_bounds__(PT_THREADS, BMFR_POST_MIN_BLOCKS) post_kernel(
     // wait for the fit: CTAs that became resident while the fit drains warm the L2 for their pixels
     {
         const int px = x0 + lane;
-        if (warp < PT_INTERIOR_WARPS && px >= 0 && px < P.W) {
+        if (px >= 0 && px < P.W) {
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
                 const int py = y0 + 4 * warp + s;
@@ -318,7 +313,7 @@ __global__ void __launch_bounds__(PT_THREADS, BMFR_POST_MIN_BLOCKS) post_kernel(
 
     // coefficients of the 3x3 block neighbourhood -> shared memory: warp w takes neighbour w (warp 0
     // also the ninth), lanes 0..29 the weights, lanes 0..11 the (min, 1/range) pairs
-    for (int nb = warp; nb < 9; nb += PT_INTERIOR_WARPS + PT_RING_WARPS) {
+    for (int nb = warp; nb < 9; nb += 8) {
         const int gx = bx + nb % 3 - 1, gy = by + nb / 3 - 1;
         if (gx < 0 || gx >= P.blocks_x || gy < 0 || gy >= P.blocks_y) continue;
         const size_t g = (size_t)gy * P.blocks_x + gx;
@@ -332,7 +327,6 @@ __global__ void __launch_bounds__(PT_THREADS, BMFR_POST_MIN_BLOCKS) post_kernel(
     // phase A, interior: column strip x, rows 4*warp .. 4*warp+3
     f3 hist[4];
     unsigned int live = 0;  // bit s: pixel s is written; bit 4+s: it takes the temporal path
-    if (warp < PT_INTERIOR_WARPS) {
 #pragma unroll
     for (int s = 0; s < 4; s += 2) {  // two pixels at a time: they share the coefficient loads
         const int ty = 4 * warp + s, y = y0 + ty;
@@ -366,11 +360,9 @@ __global__ void __launch_bounds__(PT_THREADS, BMFR_POST_MIN_BLOCKS) post_kernel(
             live |= ((own ? 1u : 0u) | (t ? 16u : 0u)) << (s + 1);
         }
     }
-    } else {
-    // phase A, ring: 4 * 33 = 132 pixels on the two ring warps, coefficients of the pixel's own block
-#pragma unroll 1
-    for (int rid = tid - PT_INTERIOR_WARPS * 32; rid < 4 * (PT_HALO - 1); rid += PT_RING_WARPS * 32) {
-        const int side = rid / (PT_HALO - 1), k = rid % (PT_HALO - 1);
+    // phase A, ring: 4 * 33 = 132 pixels, coefficients of the pixel's own block
+    if (tid < 4 * (PT_HALO - 1)) {
+        const int side = tid / (PT_HALO - 1), k = tid % (PT_HALO - 1);
         int hx, hy;
         if (side == 0) { hx = k; hy = 0; }
         else if (side == 1) { hx = PT_HALO - 1; hy = k; }
@@ -383,9 +375,7 @@ __global__ void __launch_bounds__(PT_THREADS, BMFR_POST_MIN_BLOCKS) post_kernel(
             phase_a_pixel<STRIP, WIDE>(sh, P, sh.coef[nb], hx, hy, rx, ry, false, false, unused);
         }
     }
-    }
     __syncthreads();
-    if (warp >= PT_INTERIOR_WARPS) return;  // the ring warps are done
 
     // phase B: clamp the history samples to the neighbourhood box, plane by plane (bmfr.cl:893-920, 967-969).  Halo rows
     // 4*warp .. 4*warp+5 cover the 3x3 neighbourhoods of the strip; this thread's column is lane+1.
@@ -439,9 +429,9 @@ cudaError_t launch_post(const KParams& P, cudaStream_t st) {
     // arithmetic) and the same number of L1 wavefronts, so it is kept only as a tuning switch
     const bool wide = BMFR_POST_WIDE_ACCESS && (bits & 7) == 0;
     if (strip) {
-        if (wide) return launch_pdl(post_kernel<true, true>, grid, dim3(PT_THREADS), 0, st, P);
-        return launch_pdl(post_kernel<true, false>, grid, dim3(PT_THREADS), 0, st, P);
+        if (wide) return launch_pdl(post_kernel<true, true>, grid, dim3(256), 0, st, P);
+        return launch_pdl(post_kernel<true, false>, grid, dim3(256), 0, st, P);
     }
-    if (wide) return launch_pdl(post_kernel<false, true>, grid, dim3(PT_THREADS), 0, st, P);
-    return launch_pdl(post_kernel<false, false>, grid, dim3(PT_THREADS), 0, st, P);
+    if (wide) return launch_pdl(post_kernel<false, true>, grid, dim3(256), 0, st, P);
+    return launch_pdl(post_kernel<false, false>, grid, dim3(256), 0, st, P);
 }
