@@ -406,8 +406,6 @@ static StageEvents* prof_slot(bmfr_ctx* c, int frame) {
     } while (0)
 
 static int halo_push_early(bmfr_ctx* c);
-static int halo_push_late(bmfr_ctx* c);
-static bool halo_active(const bmfr_ctx* c);
 
 static int run_frame(bmfr_ctx* c, const KParams& P, int frame) {
     StageEvents* pe = prof_slot(c, frame);
@@ -428,39 +426,13 @@ static int run_frame(bmfr_ctx* c, const KParams& P, int frame) {
         MARK(4);
         LAUNCH_TRY(launch_k5(P, c->stream), "taa");
         MARK(5);
-        { int hs = halo_push_late(c); if (hs != 0) return hs; }
     } else {
         LAUNCH_TRY(launch_reproject(P, c->stream), "reproject_kernel");
         MARK(1);
         { int hs = halo_push_early(c); if (hs != 0) return hs; }
         LAUNCH_TRY(launch_fit_qr(P, c->stream), "fit_qr_kernel");
         MARK(2);
-        // Sharded with connected neighbours: the tile rows that hold the rows a neighbour keeps as halo go
-        // first, their push runs on the side stream beside the remaining tile rows.
-        bool split = false;
-        if (halo_active(c)) {
-            const bmfr_geometry& g = c->geo;
-            const int h2 = c->prm.halo_rows > 32 ? c->prm.halo_rows - 32 : 0;
-            int top1 = P.by0, bot0 = P.by1;  // [by0, top1) and [bot0, by1) are the boundary tile rows
-            if (c->peer[0].connected) top1 = ((g.own_y0 + h2 - 1 + 16 - P.off_y) >> 5) + 1;
-            if (c->peer[1].connected) bot0 = (g.own_y1 - h2 + 16 - P.off_y) >> 5;
-            if (top1 < P.by0) top1 = P.by0;
-            if (bot0 > P.by1) bot0 = P.by1;
-            if (h2 > 0 && top1 < bot0) {
-                split = true;
-                KParams Q = P;
-                if (top1 > P.by0) { Q.by0 = P.by0; Q.by1 = top1; LAUNCH_TRY(launch_post(Q, c->stream), "post_kernel (top boundary)"); }
-                if (bot0 < P.by1) { Q.by0 = bot0; Q.by1 = P.by1; LAUNCH_TRY(launch_post(Q, c->stream), "post_kernel (bottom boundary)"); }
-                { int hs = halo_push_late(c); if (hs != 0) return hs; }
-                Q.by0 = top1; Q.by1 = bot0;
-                LAUNCH_TRY(launch_post(Q, c->stream), "post_kernel");
-            }
-        }
-        if (!split) {
-            LAUNCH_TRY(launch_post(P, c->stream), "post_kernel");
-            int hs = halo_push_late(c);
-            if (hs != 0) return hs;
-        }
+        LAUNCH_TRY(launch_post(P, c->stream), "post_kernel");
         MARK(3);
     }
     return BMFR_OK;
@@ -598,22 +570,11 @@ static int halo_push_early(bmfr_ctx* c) {
     return BMFR_OK;
 }
 
-// once the kernels that produce the boundary rows of the accumulated filtered colour and of the TAA result
-// are enqueued: push those rows on the side stream (the rest of the post pass runs beside the copy)
+// after the last kernel: push the rest, then raise the neighbours' flags
 static int halo_push_late(bmfr_ctx* c) {
     if (!halo_active(c)) return BMFR_OK;
-    BMFR_CUDA_TRY(cudaEventRecord(c->halo_ready, c->stream));
-    BMFR_CUDA_TRY(cudaStreamWaitEvent(c->halo_stream, c->halo_ready, 0));
-    int st = halo_push_part(c, true, c->halo_stream);
+    int st = halo_push_part(c, true, c->stream);
     if (st != 0) return st;
-    BMFR_CUDA_TRY(cudaEventRecord(c->halo_pushed, c->halo_stream));
-    return BMFR_OK;
-}
-
-// after the last kernel of the frame: both pushes are done -> raise the neighbours' flags
-static int halo_signal(bmfr_ctx* c) {
-    if (!halo_active(c)) return BMFR_OK;
-    int st;
     BMFR_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->halo_pushed, 0));
     // the neighbour above sees this context as its "below" neighbour (flag 1) and vice versa
     unsigned int* fa = c->peer[0].connected ? c->peer[0].flags + 1 : nullptr;
@@ -649,7 +610,7 @@ int bmfr_denoise_frame(bmfr_ctx* c, int frame, const float* d_albedo, const floa
     if (st != 0) return st;
     st = run_frame(c, P, frame);
     if (st != 0) return st;
-    st = halo_signal(c);  // every boundary row of this frame is in the neighbours' halos: raise their flags
+    st = halo_push_late(c);  // the rest of this frame's boundary rows -> the neighbours' halo rows, then their flags
     if (st != 0) return st;
     ++c->seq;
     // swap all double buffers, bmfr.cpp:483-484
