@@ -2,19 +2,22 @@
 // (bmfr.cl:703-758, 761-857, 860-974) in one pass; `filtered` and `tone_mapped` never reach HBM.
 //
 // One CTA per 32x32 tile of the frame's shifted block grid, so the block's 42 fit coefficients are
-// CTA-uniform: they sit in shared memory and are read as warp-wide broadcasts.  Thread (lane, warp) owns the column strip x = x0 + lane,
-// rows y0 + 4*warp .. +3: every global access of a warp is 32 consecutive pixels of one row (the
-// interleaved-RGB stride of 12 B keeps each 32-bit load on 3-4 cache lines), and the four 3x3 TAA
-// neighbourhoods of a strip share their row minima / maxima.
+// CTA-uniform: they sit in shared memory (with those of the eight neighbouring blocks, for the ring) and
+// are read as warp-wide broadcasts, one read serving a pair of pixels.  Thread (lane, warp) owns the
+// column strip x = x0 + lane, rows y0 + 4*warp .. +3: every global access of a warp is 32 consecutive
+// pixels of one row (the interleaved-RGB stride of 12 B keeps each 32-bit load on 3-4 cache lines), and
+// the four 3x3 TAA neighbourhoods of a strip share their row minima / maxima.
 //   phase A : filtered -> accumulated -> tone-mapped for the tile and a one-pixel ring (ring pixels
-//             use their own block's coefficients), written to shared memory as YCoCg planes;
-//             neighbours outside the image are filled with the nearest in-image pixel, which leaves
-//             the min / max over the in-image neighbours unchanged (bmfr.cl:900-920) and removes
-//             every per-neighbour test.
-//   phase B : taa for the tile interior from shared memory.
+//             use their own block's coefficients), written to shared memory as YCoCg planes; the TAA
+//             history gather of a pixel is issued here too, next to the accumulation gather (both
+//             depend only on the stored previous-pixel position: one dependent gather round per
+//             pixel).  Neighbours outside the image are filled with the nearest in-image pixel, which
+//             leaves the min / max over the in-image neighbours unchanged (bmfr.cl:900-920) and
+//             removes every per-neighbour test.
+//   phase B : clamp of the history sample to the neighbourhood box from shared memory, blend, store.
 // Nothing here is compared bitwise with the reference (the inputs already carry the fit's
 // rounding), so this translation unit is compiled with FMA contraction and uses the fast
-// reciprocal; tests/test_gpu_parity.py holds it to the 1e-3 / 60 dB colour tolerance.
+// reciprocal / lg2 / ex2; tests/test_gpu_parity.py holds it to the 1e-3 / 60 dB colour tolerance.
 #include "bmfr_kernels.h"
 
 #include "bmfr_device.cuh"
