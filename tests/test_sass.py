@@ -1,0 +1,62 @@
+"""Static checks on the built sm_100a code (cuobjdump, no GPU needed).
+
+* The reprojection must stay bit-exact against the oracle: ptxas 12.9 contracts `mul.rn.f32x2` followed by
+  `add/sub.rn.f32x2` into FFMA2 even with --fmad=false, so K1 keeps its products scalar and only packs sums
+  (csrc/bmfr_device.cuh).  A fused multiply-add in the K1 kernels would silently break parity.
+* The FUSED fit is the TMA-fed, FFMA2 kernel DESIGN.md describes: its SASS must show it.
+"""
+import re
+import shutil
+import subprocess
+
+import pytest
+
+from bmfr_b200 import _lib
+
+
+def _sass_by_function():
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    _lib.load()
+    out = subprocess.run([exe, "-sass", str(_lib.LIB_PATH)], capture_output=True, text=True, check=True).stdout
+    funcs, cur = {}, None
+    for line in out.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            funcs[cur] = []
+        elif cur and re.match(r"\s+/\*[0-9a-f]{4,}\*/\s", line):
+            funcs[cur].append(line)
+    return funcs
+
+
+@pytest.fixture(scope="module")
+def sass():
+    if not (shutil.which("cuobjdump") or shutil.os.path.exists("/usr/local/cuda/bin/cuobjdump")):
+        pytest.skip("cuobjdump not available")
+    return _sass_by_function()
+
+
+def _ops(lines):
+    return [re.sub(r"^\s+/\*[0-9a-f]+\*/\s+(@!?U?P\w+\s+)?", "", l).split()[0].split(".")[0] for l in lines]
+
+
+def test_reprojection_has_no_fused_multiply_add_pairs(sass):
+    k1 = {n: l for n, l in sass.items() if "reproject_kernel" in n or "k1_accumulate_noisy_kernel" in n}
+    assert len(k1) >= 4, list(sass)
+    for name, lines in k1.items():
+        ops = _ops(lines)
+        assert "FFMA2" not in ops, f"{name}: a packed multiply-add was contracted — K1 is no longer bit-exact"
+        assert "FADD2" in ops, f"{name}: the packed sums are gone"
+        # scalar FFMA only inside the IEEE division / sqrt sequences (they come with MUFU.RCP + FCHK)
+        assert ops.count("FFMA") <= 12 * ops.count("FCHK") + 8, f"{name}: unexpected scalar FFMA count {ops.count('FFMA')}"
+
+
+def test_fit_kernel_uses_tma_and_packed_fma(sass):
+    fit = [l for n, l in sass.items() if "fit_qr_kernel" in n]
+    assert fit
+    for lines in fit:
+        ops = _ops(lines)
+        assert "UTMALDG" in ops, "the TMA tile loads of the fit are gone"
+        assert ops.count("FFMA2") > 300, "the level-1 factorisation is no longer on packed pairs"
+        assert "SYNCS" in ops, "mbarrier hand-off missing"
+        assert len(lines) * 16 < 96 * 1024, f"fit kernel grew to {len(lines) * 16 // 1024} KB of SASS (I-cache)"
