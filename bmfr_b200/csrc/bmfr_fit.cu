@@ -417,12 +417,21 @@ struct QrLoopFull<ROWS, BMFR_FEATURES> {
 //       stacked rows (level 2), back-substitutes (bmfr.cl:659-699) and writes the weights, while the
 //       compute warps are already on the next block.
 // --------------------------------------------------------------------------------------------
+#ifndef BMFR_QR_TAIL_SOLVE
+#define BMFR_QR_TAIL_SOLVE 1  // 1: no solver warp; level 2 runs from global memory once a CTA has no blocks left (see below)
+#endif
 #define QR_COMPUTE_WARPS 4
 #define QR_COMPUTE_THREADS (QR_COMPUTE_WARPS * 32)
+#if BMFR_QR_TAIL_SOLVE
+#define QR_THREADS QR_COMPUTE_THREADS
+#else
 #define QR_THREADS (QR_COMPUTE_THREADS + 32)
+#endif
 #define QR_ROWS 8
 #define QR_TRI (BMFR_FEATURES * BMFR_BUFFER_COUNT)  // floats of one level-1 triangle, stored as a full 10x13
 #define QR_SLOTS 2
+#define QR_MINE 64    // tail-solve build: blocks a CTA collects before it runs level 2 on them
+#define QR_TRI_G 136  // floats per triangle in global memory: four of them are a whole number of 128-byte lines
 // One 32x32-pixel tile of an interleaved-RGB image is 96 floats per row.  TMA wants the innermost
 // start coordinate on a 16-byte boundary; a tile starts at pixel x0 (even), i.e. at float 3*x0 = 0 or 2
 // (mod 4), so the box is 100 floats wide, starts at the aligned-down coordinate and the reader skips
@@ -438,11 +447,19 @@ struct QrShared {
     float coef[QR_COMPUTE_WARPS + 1][16];
 #endif
     float minmax[2][QR_COMPUTE_WARPS][2 * BMFR_FEATURES_SCALED];  // double-buffered by block parity
+#if BMFR_QR_TAIL_SOLVE
+    float fin[QR_COMPUTE_WARPS][2 * QR_TRI];     // level-2 triangles: two blocks per solving warp
+    int mine[QR_MINE];                           // blocks this CTA has factored and not yet solved
+#else
     float tri[QR_SLOTS][QR_COMPUTE_WARPS][QR_TRI];  // level-1 triangles (unnormalised rows S_kj)
-    float fin[QR_TRI];                           // level-2 triangle
-    unsigned long long full[QR_SLOTS], empty[QR_SLOTS], data_full;
+    float fin[1][QR_TRI];                        // level-2 triangle
+#endif
+    unsigned long long data_full;
     int blk[2];                                  // block index of the next iteration, by iteration parity (dynamic schedule)
+#if !BMFR_QR_TAIL_SOLVE
+    unsigned long long full[QR_SLOTS], empty[QR_SLOTS];
     int slot_block[QR_SLOTS];                    // block whose triangles sit in the slot; -1 = no more blocks
+#endif
 };
 
 // The three tensor maps of a frame (2-D tensors [rows][W*3] of floats, box 100 x 32) and whether the
@@ -535,9 +552,147 @@ __device__ __forceinline__ void qr_prefetch(const KParams& P, const QrMaps& M, Q
     if (part != 1) tma_load_tile(&sh.stage[2][0][0], &M.colour, c0, c1, &sh.data_full);
 }
 
+__device__ __forceinline__ int qr_block_of_draw(int i, int nblocks, int blocks_x);
+// One thread: draw the block of iteration it + 1 (sh.blk holds the block index, or >= nblocks when the
+// frame is exhausted), start its tile loads or arrive plainly.
+__device__ __forceinline__ void qr_draw_next(const KParams& P, const QrMaps& M, QrShared& sh, int it, int nblocks, int stride) {
+    const int draw = stride + atomicAdd(P.block_counter, 1);
+    const int nl = draw < nblocks ? qr_block_of_draw(draw, nblocks, P.blocks_x) : nblocks;
+    sh.blk[(it + 1) & 1] = nl;
+    const int nbx = nl % P.blocks_x, nby = P.by0 + nl / P.blocks_x;
+    if (nl < nblocks && M.use_tma && qr_block_is_interior(P, nbx, nby)) qr_prefetch(P, M, sh, nbx, nby);
+    else mbar_arrive(&sh.data_full);
+}
+
 #ifndef BMFR_QR_MIN_BLOCKS
-#define BMFR_QR_MIN_BLOCKS 3
+#define BMFR_QR_MIN_BLOCKS (BMFR_QR_TAIL_SOLVE ? 4 : 3)
 #endif
+
+// Level 2 of the TSQR and the back-substitution for TWO blocks by one warp (tail-solve build), written
+// for code size: this runs once per block, so its instructions are fetched cold, and a fully unrolled
+// reflector chain (tens of KB) is bound by instruction fetch, not by arithmetic.
+//   Half-warp h = lane >> 4 works on block blk (negative: none); its lane j < 13 owns COLUMN j of the 40
+//   stacked level-1 rows (row (w,k) = S_kj / sqrt(S_kk) for j >= k, zero left of the diagonal).  A
+//   reflector is then: broadcast column k (40 indexed shuffles), one in-lane dot product per column, one
+//   in-lane update — no reduction across lanes, and the k loop stays rolled because only the shuffle
+//   source lane depends on k.
+//   tri = the block's four level-1 triangles in global memory (written by this CTA), fin = 130 floats of
+//   shared memory for this half-warp.
+__device__ __forceinline__ void qr_solve_columns(const KParams& P, const float* __restrict__ tri, float* __restrict__ fin, int blk,
+                                                 int lane) {
+    constexpr int NROWS = QR_COMPUTE_WARPS * BMFR_FEATURES;
+    const int j = lane & 15, hb = lane & 16;
+    const bool owner = blk >= 0 && j < BMFR_BUFFER_COUNT;
+    float col[NROWS];
+#pragma unroll
+    for (int r = 0; r < NROWS; ++r) {
+        const int w = r / BMFR_FEATURES, k = r % BMFR_FEATURES;
+        const float v = owner ? __ldcg(tri + w * QR_TRI_G + k * BMFR_BUFFER_COUNT + j) : 0.f;
+        const float diag = __shfl_sync(0xffffffffu, v, hb + k);  // S_kk of this row
+        col[r] = (owner && j >= k) ? v * rsqrt_approx(diag) : 0.f;  // (entries left of the diagonal were never written)
+    }
+#pragma unroll 1
+    for (int k = 0; k < BMFR_FEATURES; ++k) {
+        float ck[NROWS];
+#pragma unroll
+        for (int r = 0; r < NROWS; ++r) ck[r] = __shfl_sync(0xffffffffu, col[r], hb + k);
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int r = 0; r < NROWS; ++r) acc[r & 3] = fmaf(ck[r], col[r], acc[r & 3]);
+        const float S = (acc[0] + acc[1]) + (acc[2] + acc[3]);  // S_j = a_k . a_j
+        const float Sk = __shfl_sync(0xffffffffu, S, hb + k);
+        if (owner && j >= k) fin[k * BMFR_BUFFER_COUNT + j] = S;  // unnormalised row k of R
+        const float c = (j > k) ? -S * rcp_approx(Sk) : 0.f;     // columns <= k are finished
+#pragma unroll
+        for (int r = 0; r < NROWS; ++r) col[r] = fmaf(ck[r], c, col[r]);
+    }
+    __syncwarp();
+    // back-substitution, bmfr.cl:659-692, one colour channel per lane (j < 3), R read as shared-memory
+    // broadcasts.  Row i of R is S_ij / sqrt(S_ii); the square root cancels in R x = rhs.
+    if (blk >= 0 && j < 3) {
+        float x[BMFR_FEATURES];
+#pragma unroll
+        for (int i = BMFR_FEATURES - 1; i >= 0; --i) {
+            float a = fin[i * BMFR_BUFFER_COUNT + BMFR_FEATURES + j];
+#pragma unroll
+            for (int jj = i + 1; jj < BMFR_FEATURES; ++jj) a = fmaf(-fin[i * BMFR_BUFFER_COUNT + jj], x[jj], a);
+            x[i] = a * rcp_approx(fin[i * BMFR_BUFFER_COUNT + i]);
+        }
+        float* wout = P.weights + (size_t)(P.by0 * P.blocks_x + blk) * BMFR_FEATURES * 3 + j;  // bmfr.cl:694-699
+#pragma unroll
+        for (int i = 0; i < BMFR_FEATURES; ++i) wout[i * 3] = x[i];
+    }
+    __syncwarp();  // fin is reused by this half-warp's next block
+}
+
+// Tail-solve build: level 2 for the `count` blocks listed in sh.mine, whose triangles this CTA wrote to
+// global memory.  Entry e goes to half-warp (e / 4) % 2 of warp e % 4, so a short list still spreads over
+// all four warps.  Nothing crosses CTAs: two CTA barriers are all the synchronisation there is.
+__device__ __noinline__ void qr_solve_mine(const KParams& P, QrShared& sh, int count, int warp, int lane) {
+    __syncthreads();  // the triangles (global stores of this CTA) and the list are complete
+    for (int t = 0; t * 8 + warp < count; ++t) {
+        const int e = t * 8 + (lane >> 4) * 4 + warp;
+        const int blk = e < count ? sh.mine[e] : -1;
+        qr_solve_columns(P, P.tri + (size_t)(blk >= 0 ? blk : 0) * QR_COMPUTE_WARPS * QR_TRI_G, &sh.fin[warp][0] + (lane >> 4) * QR_TRI,
+                         blk, lane);
+    }
+    __syncthreads();  // the list may be refilled
+}
+
+// Level 2 of the TSQR and the back-substitution for one block, by one warp.  `tri` holds the four
+// level-1 triangles (row k of triangle w at tri[w * TRI_STRIDE + k * 13], entries left of the diagonal
+// undefined); GLOBAL = they live in global memory and were written by other SMs (L2 loads).
+template <bool GLOBAL, int TRI_STRIDE>
+__device__ __forceinline__ void qr_solve_block(const KParams& P, const float* __restrict__ tri, float* __restrict__ fin, int group,
+                                               int lane, unsigned long long* release) {
+    // the 40 stacked rows (row (w,k) = S_kj / sqrt(S_kk) for j >= k, zero left of the diagonal), two per lane
+    constexpr int NS2 = 2;
+    float b[NS2][BMFR_BUFFER_COUNT];
+#pragma unroll
+    for (int s = 0; s < NS2; ++s) {
+        const int row = lane + 32 * s;
+        const bool live = row < QR_COMPUTE_WARPS * BMFR_FEATURES;
+        const int k = row % BMFR_FEATURES;
+        const float* src = tri + (live ? (row / BMFR_FEATURES) * TRI_STRIDE + k * BMFR_BUFFER_COUNT : 0);
+        float v[BMFR_BUFFER_COUNT];
+#pragma unroll
+        for (int c = 0; c < BMFR_BUFFER_COUNT; ++c) v[c] = GLOBAL ? __ldcg(src + c) : src[c];
+        float diag = v[0];
+#pragma unroll
+        for (int c = 1; c < BMFR_FEATURES; ++c) diag = (c == k) ? v[c] : diag;
+        const float scale = live ? rsqrt_approx(diag) : 0.f;
+#pragma unroll
+        for (int c = 0; c < BMFR_BUFFER_COUNT; ++c) b[s][c] = (live && c >= k) ? v[c] * scale : 0.f;
+    }
+    if (!GLOBAL) mbar_arrive(release);  // the triangles are in registers: the ring slot may be refilled
+    QrLoopFull<NS2, 0>::run(b, nullptr, nullptr, fin, lane);
+    __syncwarp();
+    // back-substitution, bmfr.cl:659-692.  Row i of R is S_ij / sqrt(S_ii); the square root cancels in
+    // R x = rhs, so the unnormalised rows are solved directly.
+    const int r = lane < BMFR_FEATURES ? lane : 0;
+    float row[BMFR_BUFFER_COUNT];
+#pragma unroll
+    for (int c = 0; c < BMFR_BUFFER_COUNT; ++c) row[c] = fin[r * BMFR_BUFFER_COUNT + c];
+    float rhs[3] = {row[10], row[11], row[12]};
+    float xs[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = BMFR_FEATURES - 1; i >= 0; --i) {
+        const float dinv = rcp_approx(__shfl_sync(0xffffffffu, row[i], i));
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float xi = __shfl_sync(0xffffffffu, rhs[c], i) * dinv;
+            if (lane == i) xs[c] = xi;
+            if (lane < i) rhs[c] = fmaf(-row[i], xi, rhs[c]);
+        }
+    }
+    if (lane < BMFR_FEATURES) {  // bmfr.cl:694-699
+        float* wout = P.weights + ((size_t)group * BMFR_FEATURES + lane) * 3;
+        wout[0] = xs[0];
+        wout[1] = xs[1];
+        wout[2] = xs[2];
+    }
+    __syncwarp();  // fin is reused by this warp's next block
+}
 
 // Optional phase timers (-DBMFR_QR_TIMING, tuning builds only): clock64 stamps of CTA 0's first
 // compute thread and solver lane, read back with bmfr_debug_qr_timing().
@@ -568,6 +723,15 @@ extern "C" int bmfr_debug_qr_cta(long long* out, int n) {
 #define QR_CTA_STAMP(k) do { } while (0)
 #endif
 
+// Draw order -> block: the last block row first (with the first row right after it: on a full frame
+// both need mirroring and take longer), so that the blocks drawn last are cheap interior ones.
+__device__ __forceinline__ int qr_block_of_draw(int i, int nblocks, int blocks_x) {
+    return i < blocks_x ? nblocks - blocks_x + i : i - blocks_x;
+}
+#ifndef BMFR_QR_LAZY_DIV
+#define BMFR_QR_LAZY_DIV 1  // draws become late once fewer than gridDim.x / LAZY_DIV blocks are left (0: never)
+#endif
+
 template <bool STRIP>
 __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(const __grid_constant__ KParams P,
                                                                                 const __grid_constant__ QrMaps M) {
@@ -583,15 +747,18 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
     // counter one block ahead (thread 0 draws the index, publishes it and starts the loads while the
     // CTA factors the current block), so CTAs that drew cheap blocks or fast SMs take more.
     const int nblocks = P.blocks_x * (P.by1 - P.by0);
-    const int first = blockIdx.x, stride = gridDim.x;
-    if (first >= nblocks) return;
+    const int stride = gridDim.x;
+    if ((int)blockIdx.x >= nblocks) return;
+    const int first = qr_block_of_draw(blockIdx.x, nblocks, P.blocks_x);
 
     if (tid == 0) {
+#if !BMFR_QR_TAIL_SOLVE
 #pragma unroll
         for (int i = 0; i < QR_SLOTS; ++i) {
             mbar_init(&sh.full[i], QR_COMPUTE_THREADS);
             mbar_init(&sh.empty[i], 32);
         }
+#endif
         mbar_init(&sh.data_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -612,6 +779,7 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
         }
 #endif
     }
+#if !BMFR_QR_TAIL_SOLVE
     if (warp == QR_COMPUTE_WARPS) {
         // ---------------- solver warp ----------------
         for (int it = 0;; ++it) {
@@ -621,58 +789,14 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
             QR_STAMP(256, it, 1);
             const int local = sh.slot_block[slot];
             if (local < 0) break;
-            const int group = P.by0 * P.blocks_x + local;
-            // level 2: the 40 stacked rows (row (w,k) = S_kj / sqrt(S_kk) for j >= k, zero left of the
-            // diagonal), two per lane
-            constexpr int NS2 = 2;
-            float b[NS2][BMFR_BUFFER_COUNT];
-#pragma unroll
-            for (int s = 0; s < NS2; ++s) {
-                const int row = lane + 32 * s;
-                const bool live = row < QR_COMPUTE_WARPS * BMFR_FEATURES;
-                const int k = row % BMFR_FEATURES;
-                const float* src = &sh.tri[slot][0][0] + (live ? row : 0) * BMFR_BUFFER_COUNT;
-                const float scale = live ? rsqrt_approx(src[k]) : 0.f;
-#pragma unroll
-                for (int c = 0; c < BMFR_BUFFER_COUNT; ++c) b[s][c] = (live && c >= k) ? src[c] * scale : 0.f;
-            }
-            mbar_arrive(&sh.empty[slot]);  // the triangles are in registers: the slot may be refilled
-#if BMFR_QR_SMEM_REDUCE
-            QrLoopFull<NS2, 0>::run(b, &sh.red[QR_COMPUTE_WARPS][0][0], sh.coef[QR_COMPUTE_WARPS], sh.fin, lane);
-#else
-            QrLoopFull<NS2, 0>::run(b, nullptr, nullptr, sh.fin, lane);
-#endif
-            __syncwarp();
-            // (iii) back-substitution, bmfr.cl:659-692.  Row i of R is S_ij / sqrt(S_ii); the square
-            // root cancels in R x = rhs, so the unnormalised rows are solved directly.
-            const int r = lane < BMFR_FEATURES ? lane : 0;
-            float row[BMFR_BUFFER_COUNT];
-#pragma unroll
-            for (int c = 0; c < BMFR_BUFFER_COUNT; ++c) row[c] = sh.fin[r * BMFR_BUFFER_COUNT + c];
-            float rhs[3] = {row[10], row[11], row[12]};
-            float xs[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-            for (int i = BMFR_FEATURES - 1; i >= 0; --i) {
-                const float dinv = rcp_approx(__shfl_sync(0xffffffffu, row[i], i));
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const float xi = __shfl_sync(0xffffffffu, rhs[c], i) * dinv;
-                    if (lane == i) xs[c] = xi;
-                    if (lane < i) rhs[c] = fmaf(-row[i], xi, rhs[c]);
-                }
-            }
-            if (lane < BMFR_FEATURES) {  // bmfr.cl:694-699
-                float* wout = P.weights + ((size_t)group * BMFR_FEATURES + lane) * 3;
-                wout[0] = xs[0];
-                wout[1] = xs[1];
-                wout[2] = xs[2];
-            }
-            __syncwarp();  // sh.fin / red / coef are reused by the next block
+            // the slot is released inside: after the triangles are in registers
+            qr_solve_block<false, QR_TRI>(P, &sh.tri[slot][0][0], sh.fin[0], P.by0 * P.blocks_x + local, lane, &sh.empty[slot]);
             QR_STAMP(256, it, 2);
         }
         QR_CTA_STAMP(2);
         return;
     }
+#endif
 
     // ---------------- compute warps ----------------
     // data_full completes once per iteration: thread 0 arrives on it after publishing sh.blk[it & 1],
@@ -684,11 +808,15 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
         else mbar_arrive(&sh.data_full);
     }
     int it = 0;
+#if BMFR_QR_TAIL_SOLVE
+    int mine = 0;  // blocks of this CTA whose triangles wait in global memory for level 2
+#endif
     for (;; ++it) {
         mbar_wait_hot(&sh.data_full, it & 1);
         const int local = sh.blk[it & 1];
         if (local >= nblocks) break;
         const int slot = it % QR_SLOTS;
+        (void)slot;
         const int group = P.by0 * P.blocks_x + local;
         const int bx = local % P.blocks_x, by = P.by0 + local / P.blocks_x;
 
@@ -750,12 +878,18 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
         }
         if (warp == 0) QR_STAMP(0, it, 2);
         compute_barrier();  // the per-warp extrema are visible, and every thread is done with the stage
-        if (tid == 0) {  // draw the next block, publish it, start its loads
-            const int nl = stride + atomicAdd(P.block_counter, 1);
-            sh.blk[(it + 1) & 1] = nl;
-            const int nbx = nl % P.blocks_x, nby = P.by0 + nl / P.blocks_x;
-            if (nl < nblocks && M.use_tma && qr_block_is_interior(P, nbx, nby)) qr_prefetch(P, M, sh, nbx, nby);
-            else mbar_arrive(&sh.data_full);
+        // Thread 0 draws the next block, publishes it and starts its loads: right here, a whole block
+        // ahead, while many blocks are left; but once less than a round is left an early draw would park a
+        // block behind this CTA's current one while other CTAs run dry, so the draw moves to the end of
+        // the iteration (the last blocks go to whoever is free first, at the price of an exposed load).
+        bool late_draw = false;
+        if (tid == 0) {
+#if BMFR_QR_TAIL_SOLVE
+            sh.mine[mine] = local;
+#endif
+            if (BMFR_QR_LAZY_DIV > 0)
+                late_draw = nblocks - stride - *(volatile int*)P.block_counter < stride / (BMFR_QR_LAZY_DIV > 0 ? BMFR_QR_LAZY_DIV : 1);
+            if (!late_draw) qr_draw_next(P, M, sh, it, nblocks, stride);
         }
         // every warp finishes the reduction itself (lane f < 6 owns feature f) and shares the result
         // by shuffle: one block-wide barrier per block instead of two
@@ -798,7 +932,12 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
 
         // (ii) level 1 of the TSQR: this warp's 256 rows -> one 10x13 triangle in the ring slot
         if (warp == 0) QR_STAMP(0, it, 4);
+#if BMFR_QR_TAIL_SOLVE
+        float* const tri_out = P.tri + ((size_t)local * QR_COMPUTE_WARPS + warp) * QR_TRI_G;
+#else
         if (it >= QR_SLOTS) mbar_wait(&sh.empty[slot], ((it / QR_SLOTS) - 1) & 1);
+        float* const tri_out = sh.tri[slot][warp];
+#endif
         if (warp == 0) QR_STAMP(0, it, 5);
         {
             float2 a2[ROWS / 2][BMFR_BUFFER_COUNT - 1];
@@ -807,22 +946,39 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
 #pragma unroll
                 for (int c = 0; c < BMFR_BUFFER_COUNT - 1; ++c) a2[h][c] = make_float2(a[2 * h][c], a[2 * h + 1][c]);
 #if BMFR_QR_SMEM_REDUCE
-            QrLoop2<ROWS / 2, 0>::run(a2, &sh.red[warp][0][0], sh.coef[warp], sh.tri[slot][warp], lane);
+            QrLoop2<ROWS / 2, 0>::run(a2, &sh.red[warp][0][0], sh.coef[warp], tri_out, lane);
 #else
-            QrLoop2<ROWS / 2, 0>::run(a2, nullptr, nullptr, sh.tri[slot][warp], lane);
+            QrLoop2<ROWS / 2, 0>::run(a2, nullptr, nullptr, tri_out, lane);
 #endif
         }
+#if BMFR_QR_TAIL_SOLVE
+        if (++mine == QR_MINE) {  // (only frames with more than 64 blocks per CTA get here)
+            qr_solve_mine(P, sh, mine, warp, lane);
+            mine = 0;
+        }
+#else
         if (tid == 0) sh.slot_block[slot] = local;
         mbar_arrive(&sh.full[slot]);
+#endif
+        if (tid == 0 && late_draw) qr_draw_next(P, M, sh, it, nblocks, stride);
         if (warp == 0) QR_STAMP(0, it, 6);
     }
+    if (warp == 0) QR_CTA_STAMP(1);
+#if BMFR_QR_TAIL_SOLVE
+    // ---------------- tail: level 2 + back-substitution of this CTA's blocks ----------------
+#ifdef BMFR_QR_NO_SOLVE  // TIMING EXPERIMENT ONLY: no weights are produced
+    if (tid >= 0) return;
+#endif
+    qr_solve_mine(P, sh, mine, warp, lane);
+    if (warp == 0) QR_CTA_STAMP(2);
+#else
     {  // tell the solver that this CTA is done
         const int slot = it % QR_SLOTS;
         if (it >= QR_SLOTS) mbar_wait(&sh.empty[slot], ((it / QR_SLOTS) - 1) & 1);
         if (tid == 0) sh.slot_block[slot] = -1;
         mbar_arrive(&sh.full[slot]);
     }
-    if (warp == 0) QR_CTA_STAMP(1);
+#endif
 }
 
 // --------------------------------------------------------------------------------------------
@@ -892,7 +1048,7 @@ static bool tile_map(const float* base, int W, int rows, CUtensorMap* out) {
 
 cudaError_t launch_fit_qr(const KParams& P, cudaStream_t st) {
     // persistent grid: as many CTAs as stay resident (sm_count * BMFR_QR_MIN_BLOCKS), never more than blocks
-    static int sm_counts[64] = {};  // per device; 0 = this device has not been configured yet
+    static int sm_counts[64] = {};  // resident CTAs per device; 0 = this device has not been configured yet
     const int smem = (int)sizeof(QrShared) + 128;
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -903,11 +1059,16 @@ cudaError_t launch_fit_qr(const KParams& P, cudaStream_t st) {
         e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fit_qr_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fit_qr_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        // persistent grid: sized from what the device really keeps resident, not from the launch bounds
+        int per_sm = 0;
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fit_qr_kernel<true>, QR_THREADS, (size_t)smem);
         if (e != cudaSuccess) return e;
-        sm_counts[dev] = n;
+        if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+        if (per_sm > BMFR_QR_MIN_BLOCKS) per_sm = BMFR_QR_MIN_BLOCKS;
+        sm_counts[dev] = n * per_sm;
     }
     const int nblocks = P.blocks_x * (P.by1 - P.by0);
-    int grid = sm_counts[dev] * BMFR_QR_MIN_BLOCKS;
+    int grid = sm_counts[dev];
     if (grid > nblocks) grid = nblocks;
     if (grid < 1) return cudaSuccess;
     QrMaps M;

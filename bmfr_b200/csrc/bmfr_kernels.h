@@ -55,7 +55,8 @@ struct KParams {
     float* result_cur;            // result_frame
     float* user_out;              // optional copy of result rows for the caller
     int* oob_flag;                // set when a gather needed a row outside [row0,row1)
-    int* block_counter;           // FUSED fit: dynamic block schedule, reset by the noise-tile kernel of the frame
+    int* block_counter;           // FUSED fit: dynamic block schedule, reset by the reprojection (STAGED: noise-tile kernel) of the frame
+    float* tri;                   // FUSED fit: level-1 triangles between the two levels of the TSQR, blocks x 4 x 136 floats
 };
 
 

@@ -84,7 +84,8 @@ struct bmfr_ctx {
     float* mins_inv = nullptr;              // (min, 1/range) twin of mins_maxs used by the weighted sum
     double* noise = nullptr;
     float* noise_f = nullptr;               // the tile rounded to fp32 (FUSED fit)
-    int* d_oob = nullptr;
+    int* d_oob = nullptr;  // [0] out-of-strip flag, [1] fit block draw
+    float* tri = nullptr;  // FUSED: level-1 triangles of the fit
     int tmp_block_rows = 0;
 
     const float* prev_normals = nullptr;    // normals_buffer.previous(): the caller's pointer of the last call
@@ -151,6 +152,7 @@ static void free_ctx(bmfr_ctx* c) {
     cudaFree(c->noise);
     cudaFree(c->noise_f);
     cudaFree(c->d_oob);
+    cudaFree(c->tri);
     for (int side = 0; side < 2; ++side) {
         bmfr_ctx::Peer& pr = c->peer[side];
         if (pr.connected && pr.ipc) {
@@ -299,6 +301,7 @@ int bmfr_create(const bmfr_params* params, bmfr_ctx** out_ctx) {
     if (st == 0) st = dev_alloc(&c->noise, (size_t)(BMFR_FEATURES - 1) * BMFR_BLOCK_PIXELS, "noise");
     if (st == 0) st = dev_alloc(&c->noise_f, (size_t)(BMFR_FEATURES - 1) * BMFR_BLOCK_PIXELS, "noise_f");
     if (st == 0) st = dev_alloc(&c->d_oob, 2, "oob flag + block counter");
+    if (st == 0 && p.mode == BMFR_MODE_FUSED) st = dev_alloc(&c->tri, nb * 4 * 136, "level-1 triangles");
     if (st == 0) st = dev_alloc(&c->d_flags, 4, "halo flags");
     if (st == 0 && p.mode == BMFR_MODE_STAGED) {
         st = dev_alloc(&c->tmp_data, (size_t)c->tmp_block_rows * g.blocks_x * BMFR_BUFFER_COUNT * BMFR_BLOCK_PIXELS, "tmp_data");
@@ -306,7 +309,7 @@ int bmfr_create(const bmfr_params* params, bmfr_ctx** out_ctx) {
         if (st == 0) st = dev_alloc(&c->tone_mapped, npix * 3, "tone_mapped");
     }
     if (st != 0) return fail(st);
-    if ((st = bmfr_check_cuda(cudaMemsetAsync(c->d_oob, 0, sizeof(int), c->stream), "memset")) != 0) return fail(st);
+    if ((st = bmfr_check_cuda(cudaMemsetAsync(c->d_oob, 0, 2 * sizeof(int), c->stream), "memset")) != 0) return fail(st);
     if ((st = bmfr_check_cuda(cudaMemsetAsync(c->d_flags, 0, 4 * sizeof(unsigned int), c->stream), "memset")) != 0) return fail(st);
     // weights of blocks a strip never fits stay defined
     if ((st = bmfr_check_cuda(cudaMemsetAsync(c->weights, 0, nb * BMFR_FEATURES * 3 * sizeof(float), c->stream), "memset")) != 0) return fail(st);
@@ -380,6 +383,7 @@ static void fill_params(bmfr_ctx* c, KParams& P, int frame, const float* d_albed
     P.tone_mapped = c->tone_mapped;
     P.result_prev = c->result.previous(); P.result_cur = c->result.current();
     P.user_out = d_out; P.oob_flag = c->d_oob; P.block_counter = c->d_oob + 1;
+    P.tri = c->tri;
 }
 
 static StageEvents* prof_slot(bmfr_ctx* c, int frame) {

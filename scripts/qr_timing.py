@@ -49,15 +49,19 @@ cta = (C.c_longlong * 4096)()
 fn2 = lib.bmfr_debug_qr_cta
 fn2.restype, fn2.argtypes = C.c_int, [C.POINTER(C.c_longlong), C.c_int]
 assert fn2(cta, 4096) == 0
-c = np.array(cta[:], dtype=np.int64).reshape(1024, 4)[:444]
+c = np.array(cta[:], dtype=np.int64).reshape(1024, 4)
+ncta = int((c[:, 0] != 0).sum())
+c = c[:ncta]
 g0 = c[:, 0].min()
 start, cend, send, sm = c[:, 0] - g0, c[:, 1] - g0, c[:, 2] - g0, c[:, 3]
-print(f"per CTA (ns from first start): start  min {start.min()} max {start.max()};  compute end  min {cend.min()} median {int(np.median(cend))} max {cend.max()};"
+print(f"{ncta} CTAs; per CTA (ns from first start): start  min {start.min()} max {start.max()};  compute end  min {cend.min()} median {int(np.median(cend))} max {cend.max()};"
       f"  solver end  min {send.min()} median {int(np.median(send))} max {send.max()}")
+print("  compute end histogram (2 us bins from 28):", np.histogram(cend, bins=np.arange(28000, 60000, 2000))[0].tolist())
+print("  solver  end histogram (2 us bins from 28):", np.histogram(send, bins=np.arange(28000, 60000, 2000))[0].tolist())
 order = np.argsort(send)[-5:]
 print("  slowest CTAs:", [(int(i), int(sm[i]), int(start[i]), int(cend[i]), int(send[i])) for i in order], "(cta, sm, start, compute end, solver end)")
 per_sm = {}
-for i in range(444):
+for i in range(ncta):
     per_sm.setdefault(int(sm[i]), []).append(int(send[i]))
 ends = np.array([max(v) for v in per_sm.values()])
 print(f"  SMs used {len(per_sm)}, CTAs per SM {sorted(set(len(v) for v in per_sm.values()))}, per-SM last end: min {ends.min()} median {int(np.median(ends))} max {ends.max()}")
