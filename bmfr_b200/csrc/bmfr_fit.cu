@@ -39,6 +39,13 @@
 #ifndef BMFR_REPROJECT_PIXELS
 #define BMFR_REPROJECT_PIXELS 4  // pixels per thread (rows BY apart); the next pixel's position is fetched one pixel ahead
 #endif
+// Layout of the fp32 copy of the noise tile (read only by fit_qr_kernel): feature c (0..8 = columns
+// 1..9), pixel (x, y) of the block.  The fit's thread (warp = y / 8, lane = x) owns rows y = 8 warp .. +7
+// and reads them as two float4 per feature, consecutive lanes 16 bytes apart.
+__device__ __forceinline__ int noise_f_index(int c, int y, int x) {
+    return (((((y >> 3) * (BMFR_FEATURES - 1) + c) * 2 + ((y & 7) >> 2)) * 32 + x) << 2) + (y & 3);
+}
+
 template <bool STRIP>
 __global__ void __launch_bounds__(256, BMFR_REPROJECT_MIN_BLOCKS) reproject_kernel(const __grid_constant__ KParams P) {
     pdl_trigger();  // the fit's CTAs may take SM slots as this grid drains (all they do before their wait is barrier set-up)
@@ -55,7 +62,7 @@ __global__ void __launch_bounds__(256, BMFR_REPROJECT_MIN_BLOCKS) reproject_kern
                 const int seed = i + BMFR_BLOCK_PIXELS + P.frame * BMFR_BUFFER_COUNT * BMFR_BLOCK_PIXELS;
                 const double d = (P.noise_amount * 2.0) * (double)(bmfr_random((unsigned int)seed) - 0.5f);
                 P.noise_out[i] = d;
-                P.noise_f_out[i] = (float)d;
+                P.noise_f_out[noise_f_index(i / BMFR_BLOCK_PIXELS, (i % BMFR_BLOCK_PIXELS) / 32, i % 32)] = (float)d;
             }
             if (cta == 0 && threadIdx.x == 0 && threadIdx.y == 0) *P.block_counter = 0;
         }
@@ -921,13 +928,28 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
         // reference adds a double (NOISE_AMOUNT is a double literal); the tile holds that double
         // rounded to fp32, which changes a sum by at most one ulp in rare ties — below the fit's own
         // rounding.
+        float2 a2[ROWS / 2][BMFR_BUFFER_COUNT - 1];  // rows (2h, 2h+1) packed: FADD2 / FMUL2 / FFMA2 from here on
 #pragma unroll
-        for (int s = 0; s < ROWS; ++s) {
+        for (int h = 0; h < ROWS / 2; ++h)
 #pragma unroll
-            for (int f = 0; f < NSC; ++f) a[s][NNS - 1 + f] = scale_feature(a[s][NNS - 1 + f], mn[f], inv[f]);
+            for (int c = 0; c < BMFR_BUFFER_COUNT - 1; ++c) a2[h][c] = make_float2(a[2 * h][c], a[2 * h + 1][c]);
 #pragma unroll
-            for (int c = 1; c < BMFR_FEATURES; ++c)
-                a[s][c - 1] += __ldg(&P.noise_f[(c - 1) * BMFR_BLOCK_PIXELS + (warp * ROWS + s) * 32 + lane]);
+        for (int f = 0; f < NSC; ++f) {
+            const float2 mn2 = dup2(mn[f]), inv2 = dup2(inv[f]);
+#pragma unroll
+            for (int h = 0; h < ROWS / 2; ++h) a2[h][NNS - 1 + f] = fmul2(fsub2(a2[h][NNS - 1 + f], mn2), inv2);
+        }
+        {
+            const float4* nz4 = reinterpret_cast<const float4*>(P.noise_f) + (size_t)warp * (BMFR_FEATURES - 1) * 2 * 32 + lane;
+#pragma unroll
+            for (int c = 0; c < BMFR_FEATURES - 1; ++c) {
+#pragma unroll
+                for (int q = 0; q < ROWS / 4; ++q) {
+                    const float4 nz = __ldg(nz4 + (c * 2 + q) * 32);
+                    a2[2 * q][c] = fadd2(a2[2 * q][c], make_float2(nz.x, nz.y));
+                    a2[2 * q + 1][c] = fadd2(a2[2 * q + 1][c], make_float2(nz.z, nz.w));
+                }
+            }
         }
 
         // (ii) level 1 of the TSQR: this warp's 256 rows -> one 10x13 triangle in the ring slot
@@ -940,11 +962,6 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
 #endif
         if (warp == 0) QR_STAMP(0, it, 5);
         {
-            float2 a2[ROWS / 2][BMFR_BUFFER_COUNT - 1];
-#pragma unroll
-            for (int h = 0; h < ROWS / 2; ++h)
-#pragma unroll
-                for (int c = 0; c < BMFR_BUFFER_COUNT - 1; ++c) a2[h][c] = make_float2(a[2 * h][c], a[2 * h + 1][c]);
 #if BMFR_QR_SMEM_REDUCE
             QrLoop2<ROWS / 2, 0>::run(a2, &sh.red[warp][0][0], sh.coef[warp], tri_out, lane);
 #else
