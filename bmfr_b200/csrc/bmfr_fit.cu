@@ -833,15 +833,28 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
         if (warp == 0) QR_STAMP(0, it, 0);
         if (M.use_tma && qr_block_is_interior(P, bx, by)) {
             const int col = (((bx * 32 - 16 + P.off_x) * 3) & 3) + lane * 3;  // shift + this lane's pixel
+            // NaN -> 0 costs two instructions per value; NaNs are rare, so the values are only probed
+            // (one predicate-accumulating compare each) and scrubbed in a cold path if any lane saw one
+            // (a squared NaN is a NaN and scrubs to 0 = the square of the scrubbed value).
+            bool bad = false;
 #pragma unroll
             for (int s = 0; s < ROWS; ++s) {
                 float v[9];
 #pragma unroll
-                for (int c = 0; c < 9; ++c) v[c] = scrub_nan(sh.stage[c / 3][warp * ROWS + s][col + c % 3]);
+                for (int c = 0; c < 9; ++c) {
+                    v[c] = sh.stage[c / 3][warp * ROWS + s][col + c % 3];
+                    bad = bad || (v[c] != v[c]);
+                }
                 a[s][0] = v[0]; a[s][1] = v[1]; a[s][2] = v[2];
                 a[s][3] = v[3]; a[s][4] = v[4]; a[s][5] = v[5];
                 a[s][6] = v[3] * v[3]; a[s][7] = v[4] * v[4]; a[s][8] = v[5] * v[5];
                 a[s][9] = v[6]; a[s][10] = v[7]; a[s][11] = v[8];
+            }
+            if (__any_sync(0xffffffffu, bad)) {
+#pragma unroll
+                for (int s = 0; s < ROWS; ++s)
+#pragma unroll
+                    for (int c = 0; c < BMFR_BUFFER_COUNT - 1; ++c) a[s][c] = scrub_nan(a[s][c]);
             }
         } else {  // border block: mirrored pixel by pixel
             const int x = mirror_index(bx * 32 + lane - 16 + P.off_x, P.W);
