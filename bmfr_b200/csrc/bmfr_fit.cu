@@ -5,14 +5,14 @@
 //                       position fetched one pixel ahead (gather-latency bound).  Writes the four
 //                       per-pixel outputs of bmfr.cl:478-484 and, in its first CTAs, the frame's noise
 //                       tile.  The block-planar tmp_data of the reference is never written.
-//   fit_qr_kernel     : persistent warp-specialised CTAs walking over the 32x32 blocks.  Four
-//                       compute warps rebuild the block's 1024x13 matrix in registers from the
-//                       per-pixel buffers (mirrored margins included, bmfr.cl:314-316; the three
-//                       32x32-pixel input tiles of the next block arrive by TMA while the current
-//                       block is factored), block min/max + scaling + noise
-//                       (bmfr.cl:511-542, 623-627), then each factors its own 256 rows (level 1 of a
-//                       TSQR) without a block barrier.  A fifth warp factors the four stacked
-//                       triangles (level 2) and back-substitutes (bmfr.cl:659-699) concurrently.
+//   fit_qr_kernel     : persistent four-warp CTAs (four per SM) walking over the 32x32 blocks.  The
+//                       warps rebuild the block's 1024x13 matrix in registers from the per-pixel
+//                       buffers (mirrored margins included, bmfr.cl:314-316; the three 32x32-pixel
+//                       input tiles of the next block arrive by TMA while the current block is
+//                       factored), block min/max + scaling + noise (bmfr.cl:511-542, 623-627), then
+//                       each factors its own 256 rows (level 1 of a TSQR) without a block barrier.
+//                       After its last block the CTA factors the four stacked triangles of each of
+//                       its blocks (level 2) and back-substitutes (bmfr.cl:659-699).
 //
 // Compiled with --fmad=false (K1 is bit-exact against the oracle); the fit writes fmaf() explicitly.
 #include "bmfr_kernels.h"
@@ -124,62 +124,6 @@ __device__ __forceinline__ float rsqrt_approx(float v) {
     return r;
 }
 
-#define QR_RED_STRIDE 36  // floats per column of the transpose buffer: 16-byte aligned rows, bank-shifted
-
-// Sum over the 32 lanes of N per-lane values (one per remaining column): every lane stores its N
-// partials column-major, then PARTS lanes share one column's 32 partials (128-bit loads + a short
-// add tree + log2(PARTS) shuffles).  Returns in lane j < N the total of column j, and in all lanes
-// the total of column 0.
-template <int N>
-__device__ __forceinline__ float warp_column_sums(const float (&part)[BMFR_BUFFER_COUNT], float* __restrict__ red, int lane,
-                                                  float& total0) {
-    constexpr int PARTS = (N > 8) ? 2 : (N > 4) ? 4 : 8;
-    constexpr int VALS = 32 / PARTS;  // columns handled per pass: 16, 8 or 4
-    constexpr int LEN = 32 / PARTS;   // partial sums per lane
-#pragma unroll
-    for (int j = 0; j < N; ++j) red[j * QR_RED_STRIDE + lane] = part[j];
-    __syncwarp();
-    const int jj = lane % VALS, q = lane / VALS;
-    float t = 0.f;
-    if (jj < N) {
-        const float4* src = reinterpret_cast<const float4*>(red + jj * QR_RED_STRIDE + q * LEN);
-        const float4 v0 = src[0];
-        float t0 = (v0.x + v0.y) + (v0.z + v0.w);
-        if (LEN >= 8) {
-            const float4 v1 = src[1];
-            t0 += (v1.x + v1.y) + (v1.z + v1.w);
-        }
-        if (LEN == 16) {
-            const float4 v2 = src[2], v3 = src[3];
-            const float t1 = ((v2.x + v2.y) + (v2.z + v2.w)) + ((v3.x + v3.y) + (v3.z + v3.w));
-            t0 += t1;
-        }
-        t = t0;
-    }
-#pragma unroll
-    for (int m = VALS; m < 32; m <<= 1) t += __shfl_xor_sync(0xffffffffu, t, m);
-    total0 = __shfl_sync(0xffffffffu, t, 0);
-    return t;
-}
-
-// Broadcast of the N elimination coefficients to every lane through shared memory.
-template <int N>
-__device__ __forceinline__ void warp_broadcast(float c, float* __restrict__ coefbuf, int lane, float (&cj)[16]) {
-    if (lane < N) coefbuf[lane] = c;
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < (N + 3) / 4; ++i) {
-        const float4 v = reinterpret_cast<const float4*>(coefbuf)[i];
-        cj[4 * i] = v.x; cj[4 * i + 1] = v.y; cj[4 * i + 2] = v.z; cj[4 * i + 3] = v.w;
-    }
-    // no trailing barrier: the next reflector's stores to `red` come after this __syncwarp, and its
-    // store to `coefbuf` comes after the __syncwarp of its own warp_column_sums
-}
-
-#ifndef BMFR_QR_SMEM_REDUCE
-#define BMFR_QR_SMEM_REDUCE 0
-#endif
-
 // Sum over the 32 lanes of N (<= 16) per-lane values with the result of every column in every lane,
 // using shuffles only.  Stage `bit` (16, 8, 4, 2, 1) folds lane bit `bit`: while a lane still carries
 // more than one value the stage is a reduce-scatter step (the lane keeps one half of its values, sends
@@ -223,79 +167,12 @@ __device__ __forceinline__ void warp_allsum(float (&v)[16], int lane, float& own
     for (int j = 0; j < N; ++j) v[j] = __shfl_sync(0xffffffffu, w[0], j * AllSum<N>::LANES_PER_COLUMN);
 }
 
-// One reflector against a virtual zero pivot row (see bmfr_device.cuh "The fit"): with S_j = a_k.a_j,
-//   R_kj = S_j / sqrt(S_k),   a_j -= a_k * S_j / S_k   (j > k).
-// `a` holds columns 1..12 (column 0 is the constant 1 and lives in no register); srow receives
-// S_k..S_12, the unnormalised row k of R.  ROWS rows per lane.
-template <int ROWS, int K>
-__device__ __forceinline__ void qr_step(float (&a)[ROWS][BMFR_BUFFER_COUNT - 1], float* __restrict__ red,
-                                        float* __restrict__ coefbuf, float* __restrict__ srow, int lane) {
-    constexpr int N = BMFR_BUFFER_COUNT - K;
-    float part[BMFR_BUFFER_COUNT];
-    if (K == 0) {  // a_0 = 1: the products are plain column sums, S_0 = number of rows
-        part[0] = (float)ROWS;
-#pragma unroll
-        for (int j = 1; j < N; ++j) {
-            float acc = a[0][j - 1];
-#pragma unroll
-            for (int s = 1; s < ROWS; ++s) acc += a[s][j - 1];
-            part[j] = acc;
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < N; ++j) {
-            float acc = a[0][K - 1] * a[0][K - 1 + j];
-#pragma unroll
-            for (int s = 1; s < ROWS; ++s) acc = fmaf(a[s][K - 1], a[s][K - 1 + j], acc);
-            part[j] = acc;
-        }
-    }
-    float cj[16];
-#if BMFR_QR_SMEM_REDUCE
-    float sk;
-    const float t = warp_column_sums<N>(part, red, lane, sk);
-    if (lane < N) srow[K + lane] = t;
-    const float c = t * rcp_approx(sk);  // 2 * dot / u_length_squared of bmfr.cl:650
-    warp_broadcast<N>(c, coefbuf, lane, cj);
-#else
-    float own;
-#pragma unroll
-    for (int j = 0; j < N; ++j) cj[j] = part[j];
-    warp_allsum<N>(cj, lane, own);
-    constexpr int LPC = AllSum<N>::LANES_PER_COLUMN;
-    if (lane % LPC == 0 && lane / LPC < N) srow[K + lane / LPC] = own;
-    const float rk = rcp_approx(cj[0]);  // 1 / S_k
-#pragma unroll
-    for (int j = 1; j < N; ++j) cj[j] *= rk;  // 2 * dot / u_length_squared of bmfr.cl:650
-#endif
-#pragma unroll
-    for (int j = 1; j < N; ++j) {
-#pragma unroll
-        for (int s = 0; s < ROWS; ++s) {
-            if (K == 0) a[s][j - 1] -= cj[j];
-            else a[s][K - 1 + j] = fmaf(-a[s][K - 1], cj[j], a[s][K - 1 + j]);
-        }
-    }
-}
-
-template <int ROWS, int K>
-struct QrLoop {
-    static __device__ __forceinline__ void run(float (&a)[ROWS][BMFR_BUFFER_COUNT - 1], float* red, float* coefbuf,
-                                               float* srows, int lane) {
-        qr_step<ROWS, K>(a, red, coefbuf, srows + K * BMFR_BUFFER_COUNT, lane);
-        QrLoop<ROWS, K + 1>::run(a, red, coefbuf, srows, lane);
-    }
-};
-template <int ROWS>
-struct QrLoop<ROWS, BMFR_FEATURES> {
-    static __device__ __forceinline__ void run(float (&)[ROWS][BMFR_BUFFER_COUNT - 1], float*, float*, float*, int) {}
-};
-
-// The same reflector on row PAIRS: a2[h][c-1] holds rows (2h, 2h+1) of column c, so the products and
-// the eliminations are FFMA2 (half the issue slots of the scalar form above).
+// One reflector of level 1 against a virtual zero pivot row (see bmfr_device.cuh "The fit"): with
+// S_j = a_k.a_j,   R_kj = S_j / sqrt(S_k),   a_j -= a_k * S_j / S_k   (j > k).
+// a2[h][c-1] holds rows (2h, 2h+1) of column c (column 0 is the constant 1 and lives in no register),
+// so the products and the eliminations are FFMA2; srow receives S_k..S_12, the unnormalised row k of R.
 template <int PAIRS, int K>
-__device__ __forceinline__ void qr_step2(float2 (&a2)[PAIRS][BMFR_BUFFER_COUNT - 1], float* __restrict__ red,
-                                         float* __restrict__ coefbuf, float* __restrict__ srow, int lane) {
+__device__ __forceinline__ void qr_step2(float2 (&a2)[PAIRS][BMFR_BUFFER_COUNT - 1], float* __restrict__ srow, int lane) {
     constexpr int N = BMFR_BUFFER_COUNT - K;
     float cj[16];
     if (K == 0) {  // a_0 = 1: the products are plain column sums, S_0 = number of rows
@@ -316,17 +193,6 @@ __device__ __forceinline__ void qr_step2(float2 (&a2)[PAIRS][BMFR_BUFFER_COUNT -
             cj[j] = acc.x + acc.y;
         }
     }
-#if BMFR_QR_SMEM_REDUCE
-    {
-        float part[BMFR_BUFFER_COUNT];
-#pragma unroll
-        for (int j = 0; j < N; ++j) part[j] = cj[j];
-        float sk;
-        const float t = warp_column_sums<N>(part, red, lane, sk);
-        if (lane < N) srow[K + lane] = t;
-        warp_broadcast<N>(-t * rcp_approx(sk), coefbuf, lane, cj);  // -(2 * dot / u_length_squared) of bmfr.cl:650
-    }
-#else
     float own;
     warp_allsum<N>(cj, lane, own);
     constexpr int LPC = AllSum<N>::LANES_PER_COLUMN;
@@ -334,7 +200,6 @@ __device__ __forceinline__ void qr_step2(float2 (&a2)[PAIRS][BMFR_BUFFER_COUNT -
     const float nrk = -rcp_approx(cj[0]);  // -1 / S_k
 #pragma unroll
     for (int j = 1; j < N; ++j) cj[j] *= nrk;  // -(2 * dot / u_length_squared) of bmfr.cl:650
-#endif
 #pragma unroll
     for (int j = 1; j < N; ++j) {
         const float c = cj[j];
@@ -348,97 +213,42 @@ __device__ __forceinline__ void qr_step2(float2 (&a2)[PAIRS][BMFR_BUFFER_COUNT -
 }
 template <int PAIRS, int K>
 struct QrLoop2 {
-    static __device__ __forceinline__ void run(float2 (&a2)[PAIRS][BMFR_BUFFER_COUNT - 1], float* red, float* coefbuf,
-                                               float* srows, int lane) {
-        qr_step2<PAIRS, K>(a2, red, coefbuf, srows + K * BMFR_BUFFER_COUNT, lane);
-        QrLoop2<PAIRS, K + 1>::run(a2, red, coefbuf, srows, lane);
+    static __device__ __forceinline__ void run(float2 (&a2)[PAIRS][BMFR_BUFFER_COUNT - 1], float* srows, int lane) {
+        qr_step2<PAIRS, K>(a2, srows + K * BMFR_BUFFER_COUNT, lane);
+        QrLoop2<PAIRS, K + 1>::run(a2, srows, lane);
     }
 };
 template <int PAIRS>
 struct QrLoop2<PAIRS, BMFR_FEATURES> {
-    static __device__ __forceinline__ void run(float2 (&)[PAIRS][BMFR_BUFFER_COUNT - 1], float*, float*, float*, int) {}
+    static __device__ __forceinline__ void run(float2 (&)[PAIRS][BMFR_BUFFER_COUNT - 1], float*, int) {}
 };
 
-// --------------------------------------------------------------------------------------------
-// General reflector on a matrix with all 13 columns in registers (level 2: column 0 is no longer 1).
-// --------------------------------------------------------------------------------------------
-template <int ROWS, int K>
-__device__ __forceinline__ void qr_step_full(float (&b)[ROWS][BMFR_BUFFER_COUNT], float* __restrict__ red,
-                                             float* __restrict__ coefbuf, float* __restrict__ srow, int lane) {
-    constexpr int N = BMFR_BUFFER_COUNT - K;
-    float part[BMFR_BUFFER_COUNT];
-#pragma unroll
-    for (int j = 0; j < N; ++j) {
-        float acc = b[0][K] * b[0][K + j];
-#pragma unroll
-        for (int s = 1; s < ROWS; ++s) acc = fmaf(b[s][K], b[s][K + j], acc);
-        part[j] = acc;
-    }
-    float cj[16];
-#if BMFR_QR_SMEM_REDUCE
-    float sk;
-    const float t = warp_column_sums<N>(part, red, lane, sk);
-    if (lane < N) srow[K + lane] = t;
-    const float c = t * rcp_approx(sk);
-    warp_broadcast<N>(c, coefbuf, lane, cj);
-#else
-    float own;
-#pragma unroll
-    for (int j = 0; j < N; ++j) cj[j] = part[j];
-    warp_allsum<N>(cj, lane, own);
-    constexpr int LPC = AllSum<N>::LANES_PER_COLUMN;
-    if (lane % LPC == 0 && lane / LPC < N) srow[K + lane / LPC] = own;
-    const float rk = rcp_approx(cj[0]);
-#pragma unroll
-    for (int j = 1; j < N; ++j) cj[j] *= rk;
-#endif
-#pragma unroll
-    for (int j = 1; j < N; ++j)
-#pragma unroll
-        for (int s = 0; s < ROWS; ++s) b[s][K + j] = fmaf(-b[s][K], cj[j], b[s][K + j]);
-}
-template <int ROWS, int K>
-struct QrLoopFull {
-    static __device__ __forceinline__ void run(float (&b)[ROWS][BMFR_BUFFER_COUNT], float* red, float* coefbuf, float* srows, int lane) {
-        qr_step_full<ROWS, K>(b, red, coefbuf, srows + K * BMFR_BUFFER_COUNT, lane);
-        QrLoopFull<ROWS, K + 1>::run(b, red, coefbuf, srows, lane);
-    }
-};
-template <int ROWS>
-struct QrLoopFull<ROWS, BMFR_FEATURES> {
-    static __device__ __forceinline__ void run(float (&)[ROWS][BMFR_BUFFER_COUNT], float*, float*, float*, int) {}
-};
 
 // --------------------------------------------------------------------------------------------
-// fit_qr_kernel: persistent, warp-specialised.
+// fit_qr_kernel: persistent CTAs of four warps, four CTAs per SM.
 //
-// A CTA is four compute warps and one solver warp and walks over blocks: its first block is
-// blockIdx.x, the following ones are drawn from a global counter one block ahead.
-//   compute warp w, lane l : rows (x_in = l, y_in = 8w .. 8w+7) of the block, eight rows per thread (as
-//       four packed fp32 pairs), so one warp-wide reduction serves 256 matrix rows.  Thread 0 draws the
-//       next block, publishes its index and starts the TMA loads of its three input tiles while the
-//       current block is factored (border blocks, which need mirroring, are loaded pixel by pixel).  Per
-//       block: block min/max through one 128-thread named barrier, scaling + noise, level 1 of the TSQR
-//       (this warp's 256 rows -> one 10x13 triangle) written to a two-slot shared-memory ring.
-//   solver warp            : waits for the four triangles of a block (mbarrier), factors the 40
-//       stacked rows (level 2), back-substitutes (bmfr.cl:659-699) and writes the weights, while the
-//       compute warps are already on the next block.
+// A CTA walks over blocks: its first block is blockIdx.x, the following ones are drawn from a global
+// counter (a block ahead while many are left, at the last moment near the end).
+//   warp w, lane l : rows (x_in = l, y_in = 8w .. 8w+7) of the block, eight rows per thread (as four
+//       packed fp32 pairs), so one warp-wide reduction serves 256 matrix rows.  Thread 0 draws the next
+//       block, publishes its index and starts the TMA loads of its three input tiles while the current
+//       block is factored (border blocks, which need mirroring, are loaded pixel by pixel).  Per block:
+//       block min/max through one CTA barrier, scaling + noise, level 1 of the TSQR (this warp's 256
+//       rows -> one 10x13 triangle), written to global memory (it stays in L2).
+//   after its last block the CTA runs level 2 for the blocks it factored: 40 stacked rows -> R, back-
+//       substitution (bmfr.cl:659-699), weights.  Nothing crosses CTAs.  Level 2 used to live in a fifth,
+//       concurrent "solver" warp fed through a shared-memory ring: its unrolled code competed with level 1
+//       for the instruction cache (`no_instruction` was the top stall) and for issue slots, and the 160-
+//       thread CTAs fit only three to an SM.
 // --------------------------------------------------------------------------------------------
-#ifndef BMFR_QR_TAIL_SOLVE
-#define BMFR_QR_TAIL_SOLVE 1  // 1: no solver warp; level 2 runs from global memory once a CTA has no blocks left (see below)
-#endif
 #define QR_COMPUTE_WARPS 4
-#define QR_COMPUTE_THREADS (QR_COMPUTE_WARPS * 32)
-#if BMFR_QR_TAIL_SOLVE
-#define QR_THREADS QR_COMPUTE_THREADS
-#else
-#define QR_THREADS (QR_COMPUTE_THREADS + 32)
-#endif
+#define QR_THREADS (QR_COMPUTE_WARPS * 32)
 #define QR_ROWS 8
-#define QR_TRI (BMFR_FEATURES * BMFR_BUFFER_COUNT)  // floats of one level-1 triangle, stored as a full 10x13
-#define QR_SLOTS 2
-#define QR_MINE 64    // tail-solve build: blocks a CTA collects before it runs level 2 on them
-#define QR_TRI_G 136  // floats per triangle in global memory: four of them are a whole number of 128-byte lines
+#define QR_TRI (BMFR_FEATURES * BMFR_BUFFER_COUNT)  // floats of one triangle, stored as a full 10x13
+#ifndef QR_MINE
+#define QR_MINE 64  // blocks a CTA collects before it runs level 2 on them (normally: all its blocks, once, at the end)
+#endif
+#define QR_TRI_G 136  // floats per level-1 triangle in global memory: four of them are a whole number of 128-byte lines
 // One 32x32-pixel tile of an interleaved-RGB image is 96 floats per row.  TMA wants the innermost
 // start coordinate on a 16-byte boundary; a tile starts at pixel x0 (even), i.e. at float 3*x0 = 0 or 2
 // (mod 4), so the box is 100 floats wide, starts at the aligned-down coordinate and the reader skips
@@ -449,24 +259,11 @@ struct QrLoopFull<ROWS, BMFR_FEATURES> {
 
 struct QrShared {
     float stage[3][32][QR_TILE_W];               // TMA landing zone: normals, positions, accumulated colour of the next block
-#if BMFR_QR_SMEM_REDUCE
-    float red[QR_COMPUTE_WARPS + 1][BMFR_BUFFER_COUNT][QR_RED_STRIDE];
-    float coef[QR_COMPUTE_WARPS + 1][16];
-#endif
     float minmax[2][QR_COMPUTE_WARPS][2 * BMFR_FEATURES_SCALED];  // double-buffered by block parity
-#if BMFR_QR_TAIL_SOLVE
     float fin[QR_COMPUTE_WARPS][2 * QR_TRI];     // level-2 triangles: two blocks per solving warp
     int mine[QR_MINE];                           // blocks this CTA has factored and not yet solved
-#else
-    float tri[QR_SLOTS][QR_COMPUTE_WARPS][QR_TRI];  // level-1 triangles (unnormalised rows S_kj)
-    float fin[1][QR_TRI];                        // level-2 triangle
-#endif
-    unsigned long long data_full;
+    unsigned long long data_full;                // mbarrier: the tiles of the next block have landed / its index is published
     int blk[2];                                  // block index of the next iteration, by iteration parity (dynamic schedule)
-#if !BMFR_QR_TAIL_SOLVE
-    unsigned long long full[QR_SLOTS], empty[QR_SLOTS];
-    int slot_block[QR_SLOTS];                    // block whose triangles sit in the slot; -1 = no more blocks
-#endif
 };
 
 // The three tensor maps of a frame (2-D tensors [rows][W*3] of floats, box 100 x 32) and whether the
@@ -483,39 +280,11 @@ __device__ __forceinline__ void mbar_init(unsigned long long* b, int count) {
 __device__ __forceinline__ void mbar_arrive(unsigned long long* b) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(unsigned long long* b, unsigned int parity) {
-    unsigned int ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(b)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// Waiting warps back off with nanosleep so that they do not take issue slots from the working warps
-// of their sub-partition.
-__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned int parity) {
-    // the whole poll-and-back-off loop stays inside one asm block, so the compiler sees straight-line
-    // code and keeps treating the warp as converged for the shuffles that follow
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "MBAR_WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra MBAR_WAIT_DONE;\n"
-        "nanosleep.u32 64;\n"
-        "bra MBAR_WAIT_LOOP;\n"
-        "MBAR_WAIT_DONE:\n"
-        "}\n" ::"r"(smem_u32(b)), "r"(parity)
-        : "memory");
-}
-// The same without the back-off, for waits that are on the critical path of every compute warp (the
-// block's input tiles): try_wait already suspends the thread for a hardware-defined interval, and a
-// sleeping warp can oversleep the arrival by microseconds.
+// Spin on an mbarrier phase.  No nanosleep back-off: the wait (the block's input tiles) is on the
+// critical path of every warp, try_wait already suspends the thread for a hardware-defined interval,
+// and a sleeping warp can oversleep the arrival by microseconds.  The loop stays inside one asm block so
+// that the compiler sees straight-line code and keeps treating the warp as converged for the shuffles
+// that follow.
 __device__ __forceinline__ void mbar_wait_hot(unsigned long long* b, unsigned int parity) {
     asm volatile(
         "{\n"
@@ -528,7 +297,6 @@ __device__ __forceinline__ void mbar_wait_hot(unsigned long long* b, unsigned in
         "}\n" ::"r"(smem_u32(b)), "r"(parity)
         : "memory");
 }
-__device__ __forceinline__ void compute_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(QR_COMPUTE_THREADS) : "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, unsigned int bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
 }
@@ -572,10 +340,10 @@ __device__ __forceinline__ void qr_draw_next(const KParams& P, const QrMaps& M, 
 }
 
 #ifndef BMFR_QR_MIN_BLOCKS
-#define BMFR_QR_MIN_BLOCKS (BMFR_QR_TAIL_SOLVE ? 4 : 3)
+#define BMFR_QR_MIN_BLOCKS 4
 #endif
 
-// Level 2 of the TSQR and the back-substitution for TWO blocks by one warp (tail-solve build), written
+// Level 2 of the TSQR and the back-substitution for TWO blocks by one warp, written
 // for code size: this runs once per block, so its instructions are fetched cold, and a fully unrolled
 // reflector chain (tens of KB) is bound by instruction fetch, not by arithmetic.
 //   Half-warp h = lane >> 4 works on block blk (negative: none); its lane j < 13 owns COLUMN j of the 40
@@ -632,7 +400,7 @@ __device__ __forceinline__ void qr_solve_columns(const KParams& P, const float* 
     __syncwarp();  // fin is reused by this half-warp's next block
 }
 
-// Tail-solve build: level 2 for the `count` blocks listed in sh.mine, whose triangles this CTA wrote to
+// Level 2 for the `count` blocks listed in sh.mine, whose triangles this CTA wrote to
 // global memory.  Entry e goes to half-warp (e / 4) % 2 of warp e % 4, so a short list still spreads over
 // all four warps.  Nothing crosses CTAs: two CTA barriers are all the synchronisation there is.
 __device__ __noinline__ void qr_solve_mine(const KParams& P, QrShared& sh, int count, int warp, int lane) {
@@ -646,70 +414,15 @@ __device__ __noinline__ void qr_solve_mine(const KParams& P, QrShared& sh, int c
     __syncthreads();  // the list may be refilled
 }
 
-// Level 2 of the TSQR and the back-substitution for one block, by one warp.  `tri` holds the four
-// level-1 triangles (row k of triangle w at tri[w * TRI_STRIDE + k * 13], entries left of the diagonal
-// undefined); GLOBAL = they live in global memory and were written by other SMs (L2 loads).
-template <bool GLOBAL, int TRI_STRIDE>
-__device__ __forceinline__ void qr_solve_block(const KParams& P, const float* __restrict__ tri, float* __restrict__ fin, int group,
-                                               int lane, unsigned long long* release) {
-    // the 40 stacked rows (row (w,k) = S_kj / sqrt(S_kk) for j >= k, zero left of the diagonal), two per lane
-    constexpr int NS2 = 2;
-    float b[NS2][BMFR_BUFFER_COUNT];
-#pragma unroll
-    for (int s = 0; s < NS2; ++s) {
-        const int row = lane + 32 * s;
-        const bool live = row < QR_COMPUTE_WARPS * BMFR_FEATURES;
-        const int k = row % BMFR_FEATURES;
-        const float* src = tri + (live ? (row / BMFR_FEATURES) * TRI_STRIDE + k * BMFR_BUFFER_COUNT : 0);
-        float v[BMFR_BUFFER_COUNT];
-#pragma unroll
-        for (int c = 0; c < BMFR_BUFFER_COUNT; ++c) v[c] = GLOBAL ? __ldcg(src + c) : src[c];
-        float diag = v[0];
-#pragma unroll
-        for (int c = 1; c < BMFR_FEATURES; ++c) diag = (c == k) ? v[c] : diag;
-        const float scale = live ? rsqrt_approx(diag) : 0.f;
-#pragma unroll
-        for (int c = 0; c < BMFR_BUFFER_COUNT; ++c) b[s][c] = (live && c >= k) ? v[c] * scale : 0.f;
-    }
-    if (!GLOBAL) mbar_arrive(release);  // the triangles are in registers: the ring slot may be refilled
-    QrLoopFull<NS2, 0>::run(b, nullptr, nullptr, fin, lane);
-    __syncwarp();
-    // back-substitution, bmfr.cl:659-692.  Row i of R is S_ij / sqrt(S_ii); the square root cancels in
-    // R x = rhs, so the unnormalised rows are solved directly.
-    const int r = lane < BMFR_FEATURES ? lane : 0;
-    float row[BMFR_BUFFER_COUNT];
-#pragma unroll
-    for (int c = 0; c < BMFR_BUFFER_COUNT; ++c) row[c] = fin[r * BMFR_BUFFER_COUNT + c];
-    float rhs[3] = {row[10], row[11], row[12]};
-    float xs[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-    for (int i = BMFR_FEATURES - 1; i >= 0; --i) {
-        const float dinv = rcp_approx(__shfl_sync(0xffffffffu, row[i], i));
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float xi = __shfl_sync(0xffffffffu, rhs[c], i) * dinv;
-            if (lane == i) xs[c] = xi;
-            if (lane < i) rhs[c] = fmaf(-row[i], xi, rhs[c]);
-        }
-    }
-    if (lane < BMFR_FEATURES) {  // bmfr.cl:694-699
-        float* wout = P.weights + ((size_t)group * BMFR_FEATURES + lane) * 3;
-        wout[0] = xs[0];
-        wout[1] = xs[1];
-        wout[2] = xs[2];
-    }
-    __syncwarp();  // fin is reused by this warp's next block
-}
-
 // Optional phase timers (-DBMFR_QR_TIMING, tuning builds only): clock64 stamps of CTA 0's first
-// compute thread and solver lane, read back with bmfr_debug_qr_timing().
+// thread, read back with bmfr_debug_qr_timing(); per CTA start / end of level 1 / end of level 2.
 #ifdef BMFR_QR_TIMING
 __device__ long long g_qr_timing[512];
 #define QR_STAMP(base, it, k)                                                              \
     do {                                                                                   \
         if (blockIdx.x == 0 && lane == 0 && (it) < 8) g_qr_timing[(base) + (it) * 8 + (k)] = clock64(); \
     } while (0)
-__device__ long long g_qr_cta[4096];  // per CTA: start, compute end, solver end (globaltimer ns), SM id
+__device__ long long g_qr_cta[4096];  // per CTA: start, end of level 1, end of level 2 (globaltimer ns), SM id
 __device__ __forceinline__ long long qr_globaltimer() {
     long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -745,9 +458,9 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
     extern __shared__ __align__(128) unsigned char qr_smem[];
     QrShared& sh = *reinterpret_cast<QrShared*>((reinterpret_cast<uintptr_t>(qr_smem) + 127) & ~(uintptr_t)127);
     const int tid = threadIdx.x, lane = tid & 31;
-    // broadcast from lane 0 so that the compiler knows the role dispatch below is warp-uniform (otherwise
-    // every shuffle of both roles gets a second, divergence-safe copy and the kernel outgrows the
-    // instruction cache)
+    // broadcast from lane 0 so that the compiler knows that branches on `warp` are warp-uniform (otherwise
+    // the shuffles behind them get a second, divergence-safe copy and the kernel outgrows the instruction
+    // cache)
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     constexpr int NSC = BMFR_FEATURES_SCALED, NNS = BMFR_FEATURES_NOT_SCALED, ROWS = QR_ROWS;
     // Block schedule: the first block of a CTA is blockIdx.x, the following ones come from a global
@@ -759,13 +472,6 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
     const int first = qr_block_of_draw(blockIdx.x, nblocks, P.blocks_x);
 
     if (tid == 0) {
-#if !BMFR_QR_TAIL_SOLVE
-#pragma unroll
-        for (int i = 0; i < QR_SLOTS; ++i) {
-            mbar_init(&sh.full[i], QR_COMPUTE_THREADS);
-            mbar_init(&sh.empty[i], 32);
-        }
-#endif
         mbar_init(&sh.data_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -786,26 +492,7 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
         }
 #endif
     }
-#if !BMFR_QR_TAIL_SOLVE
-    if (warp == QR_COMPUTE_WARPS) {
-        // ---------------- solver warp ----------------
-        for (int it = 0;; ++it) {
-            const int slot = it % QR_SLOTS;
-            QR_STAMP(256, it, 0);
-            mbar_wait(&sh.full[slot], (it / QR_SLOTS) & 1);
-            QR_STAMP(256, it, 1);
-            const int local = sh.slot_block[slot];
-            if (local < 0) break;
-            // the slot is released inside: after the triangles are in registers
-            qr_solve_block<false, QR_TRI>(P, &sh.tri[slot][0][0], sh.fin[0], P.by0 * P.blocks_x + local, lane, &sh.empty[slot]);
-            QR_STAMP(256, it, 2);
-        }
-        QR_CTA_STAMP(2);
-        return;
-    }
-#endif
-
-    // ---------------- compute warps ----------------
+    // ---------------- level 1, block after block ----------------
     // data_full completes once per iteration: thread 0 arrives on it after publishing sh.blk[it & 1],
     // with the TMA byte count when the block is fetched as tiles, plainly otherwise.
     if (tid == 0) {
@@ -815,15 +502,11 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
         else mbar_arrive(&sh.data_full);
     }
     int it = 0;
-#if BMFR_QR_TAIL_SOLVE
     int mine = 0;  // blocks of this CTA whose triangles wait in global memory for level 2
-#endif
     for (;; ++it) {
         mbar_wait_hot(&sh.data_full, it & 1);
         const int local = sh.blk[it & 1];
         if (local >= nblocks) break;
-        const int slot = it % QR_SLOTS;
-        (void)slot;
         const int group = P.by0 * P.blocks_x + local;
         const int bx = local % P.blocks_x, by = P.by0 + local / P.blocks_x;
 
@@ -897,16 +580,14 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
             }
         }
         if (warp == 0) QR_STAMP(0, it, 2);
-        compute_barrier();  // the per-warp extrema are visible, and every thread is done with the stage
+        __syncthreads();  // the per-warp extrema are visible, and every thread is done with the stage
         // Thread 0 draws the next block, publishes it and starts its loads: right here, a whole block
         // ahead, while many blocks are left; but once less than a round is left an early draw would park a
         // block behind this CTA's current one while other CTAs run dry, so the draw moves to the end of
         // the iteration (the last blocks go to whoever is free first, at the price of an exposed load).
         bool late_draw = false;
         if (tid == 0) {
-#if BMFR_QR_TAIL_SOLVE
             sh.mine[mine] = local;
-#endif
             if (BMFR_QR_LAZY_DIV > 0)
                 late_draw = nblocks - stride - *(volatile int*)P.block_counter < stride / (BMFR_QR_LAZY_DIV > 0 ? BMFR_QR_LAZY_DIV : 1);
             if (!late_draw) qr_draw_next(P, M, sh, it, nblocks, stride);
@@ -965,50 +646,21 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
             }
         }
 
-        // (ii) level 1 of the TSQR: this warp's 256 rows -> one 10x13 triangle in the ring slot
+        // (ii) level 1 of the TSQR: this warp's 256 rows -> one 10x13 triangle (global memory, stays in L2)
         if (warp == 0) QR_STAMP(0, it, 4);
-#if BMFR_QR_TAIL_SOLVE
-        float* const tri_out = P.tri + ((size_t)local * QR_COMPUTE_WARPS + warp) * QR_TRI_G;
-#else
-        if (it >= QR_SLOTS) mbar_wait(&sh.empty[slot], ((it / QR_SLOTS) - 1) & 1);
-        float* const tri_out = sh.tri[slot][warp];
-#endif
         if (warp == 0) QR_STAMP(0, it, 5);
-        {
-#if BMFR_QR_SMEM_REDUCE
-            QrLoop2<ROWS / 2, 0>::run(a2, &sh.red[warp][0][0], sh.coef[warp], tri_out, lane);
-#else
-            QrLoop2<ROWS / 2, 0>::run(a2, nullptr, nullptr, tri_out, lane);
-#endif
-        }
-#if BMFR_QR_TAIL_SOLVE
-        if (++mine == QR_MINE) {  // (only frames with more than 64 blocks per CTA get here)
+        QrLoop2<ROWS / 2, 0>::run(a2, P.tri + ((size_t)local * QR_COMPUTE_WARPS + warp) * QR_TRI_G, lane);
+        if (++mine == QR_MINE) {  // the list is full (more than 64 blocks per CTA: no frame up to 8K on a B200 gets here)
             qr_solve_mine(P, sh, mine, warp, lane);
             mine = 0;
         }
-#else
-        if (tid == 0) sh.slot_block[slot] = local;
-        mbar_arrive(&sh.full[slot]);
-#endif
         if (tid == 0 && late_draw) qr_draw_next(P, M, sh, it, nblocks, stride);
         if (warp == 0) QR_STAMP(0, it, 6);
     }
     if (warp == 0) QR_CTA_STAMP(1);
-#if BMFR_QR_TAIL_SOLVE
-    // ---------------- tail: level 2 + back-substitution of this CTA's blocks ----------------
-#ifdef BMFR_QR_NO_SOLVE  // TIMING EXPERIMENT ONLY: no weights are produced
-    if (tid >= 0) return;
-#endif
+    // ---------------- level 2 + back-substitution of this CTA's blocks ----------------
     qr_solve_mine(P, sh, mine, warp, lane);
     if (warp == 0) QR_CTA_STAMP(2);
-#else
-    {  // tell the solver that this CTA is done
-        const int slot = it % QR_SLOTS;
-        if (it >= QR_SLOTS) mbar_wait(&sh.empty[slot], ((it / QR_SLOTS) - 1) & 1);
-        if (tid == 0) sh.slot_block[slot] = -1;
-        mbar_arrive(&sh.full[slot]);
-    }
-#endif
 }
 
 // --------------------------------------------------------------------------------------------

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Phase timers of fit_qr_kernel (tuning build with -DBMFR_QR_TIMING): runs a few 1080p frames and prints
-the clock64 deltas of CTA 0's first compute thread and of its solver lane, per block iteration."""
+the clock64 deltas of CTA 0's first thread per block iteration, and per CTA the end of level 1 (its last
+block) and of level 2 (the solves of its blocks)."""
 import ctypes as C
 import os
 import sys
@@ -31,20 +32,14 @@ fn.restype, fn.argtypes = C.c_int, [C.POINTER(C.c_longlong), C.c_int]
 assert fn(buf, 512) == 0
 t = np.array(buf[:], dtype=np.int64)
 comp = t[:64].reshape(8, 8)
-solv = t[256:320].reshape(8, 8)
 t0 = comp[0, 0]
-names = ["cp.wait+lds", "prefetch issue", "minmax+barriers", "scale+noise", "wait empty", "level-1 QR"]
+names = ["lds", "minmax", "barrier+draw+finish", "scale+noise", "-", "level-1 QR"]
 print("compute warp 0 of CTA 0 (cycles):")
 for it in range(8):
     if comp[it, 0] == 0:
         break
     deltas = np.diff(comp[it, :7])
     print(f"  block {it}: start +{comp[it, 0] - t0:7d}  " + "  ".join(f"{n} {v}" for n, v in zip(names, deltas)) + f"  total {comp[it, 6] - comp[it, 0]}")
-print("solver warp of CTA 0 (cycles):")
-for it in range(8):
-    if solv[it, 0] == 0:
-        break
-    print(f"  block {it}: start +{solv[it, 0] - t0:7d}  wait full {solv[it, 1] - solv[it, 0]}  level-2 + solve {solv[it, 2] - solv[it, 1]}")
 cta = (C.c_longlong * 4096)()
 fn2 = lib.bmfr_debug_qr_cta
 fn2.restype, fn2.argtypes = C.c_int, [C.POINTER(C.c_longlong), C.c_int]
@@ -54,12 +49,12 @@ ncta = int((c[:, 0] != 0).sum())
 c = c[:ncta]
 g0 = c[:, 0].min()
 start, cend, send, sm = c[:, 0] - g0, c[:, 1] - g0, c[:, 2] - g0, c[:, 3]
-print(f"{ncta} CTAs; per CTA (ns from first start): start  min {start.min()} max {start.max()};  compute end  min {cend.min()} median {int(np.median(cend))} max {cend.max()};"
-      f"  solver end  min {send.min()} median {int(np.median(send))} max {send.max()}")
-print("  compute end histogram (2 us bins from 28):", np.histogram(cend, bins=np.arange(28000, 60000, 2000))[0].tolist())
-print("  solver  end histogram (2 us bins from 28):", np.histogram(send, bins=np.arange(28000, 60000, 2000))[0].tolist())
+print(f"{ncta} CTAs; per CTA (ns from first start): start  min {start.min()} max {start.max()};  level-1 end  min {cend.min()} median {int(np.median(cend))} max {cend.max()};"
+      f"  level-2 end  min {send.min()} median {int(np.median(send))} max {send.max()}")
+print("  level-1 end histogram (2 us bins from 28):", np.histogram(cend, bins=np.arange(28000, 60000, 2000))[0].tolist())
+print("  level-2 end histogram (2 us bins from 28):", np.histogram(send, bins=np.arange(28000, 60000, 2000))[0].tolist())
 order = np.argsort(send)[-5:]
-print("  slowest CTAs:", [(int(i), int(sm[i]), int(start[i]), int(cend[i]), int(send[i])) for i in order], "(cta, sm, start, compute end, solver end)")
+print("  slowest CTAs:", [(int(i), int(sm[i]), int(start[i]), int(cend[i]), int(send[i])) for i in order], "(cta, sm, start, level-1 end, level-2 end)")
 per_sm = {}
 for i in range(ncta):
     per_sm.setdefault(int(sm[i]), []).append(int(send[i]))
