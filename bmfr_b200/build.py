@@ -83,13 +83,26 @@ def build_library(force: bool = False, verbose: bool = False, extra_flags=(), ou
     return LIB
 
 
+IO_LIB = ROOT / "bmfr_b200" / "libbmfr_io.so"
+
+
+def build_io(force: bool = False) -> Path:
+    """libbmfr_io.so: EXR reader, camera_matrices.h parser, PNG writer (include/bmfr_io.h); host only, no CUDA."""
+    src, hdr = CSRC / "bmfr_io.cpp", ROOT / "include" / "bmfr_io.h"
+    if not force and IO_LIB.exists() and IO_LIB.stat().st_mtime > max(src.stat().st_mtime, hdr.stat().st_mtime):
+        return IO_LIB
+    subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-shared", "-fPIC", str(src), "-o", str(IO_LIB), "-lz"], check=True)
+    return IO_LIB
+
+
 def build_driver(force: bool = False) -> Path:
     """bmfr_run: the reference's driver program (tasks(), bmfr.cpp:179-556) on top of the C ABI."""
-    exe, src = ROOT / "bmfr_b200" / "bmfr_run", CSRC / "bmfr_main.cpp"
+    exe, srcs = ROOT / "bmfr_b200" / "bmfr_run", [CSRC / "bmfr_main.cpp", CSRC / "bmfr_io.cpp"]
     build_library()
-    if not force and exe.exists() and exe.stat().st_mtime > max(src.stat().st_mtime, LIB.stat().st_mtime):
+    newest = max([s.stat().st_mtime for s in srcs] + [LIB.stat().st_mtime, (ROOT / "include" / "bmfr_io.h").stat().st_mtime])
+    if not force and exe.exists() and exe.stat().st_mtime > newest:
         return exe
-    subprocess.run(["g++", "-std=c++17", "-O2", str(src), "-o", str(exe), f"-L{LIB.parent}", "-lbmfr_b200",
+    subprocess.run(["g++", "-std=c++17", "-O2", "-fopenmp", *map(str, srcs), "-o", str(exe), f"-L{LIB.parent}", "-lbmfr_b200", "-lz",
                     f"-Wl,-rpath,{LIB.parent}", "-Wl,-rpath,$ORIGIN"], check=True)
     return exe
 
@@ -114,4 +127,5 @@ def _build_variant(out: Path, extra_flags, verbose):
 
 if __name__ == "__main__":
     print(build_library(force="--force" in sys.argv, verbose=True))
+    print(build_io(force="--force" in sys.argv))
     print(build_driver(force="--force" in sys.argv))

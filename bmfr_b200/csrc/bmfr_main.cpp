@@ -6,7 +6,12 @@
 // clutils::ProfilingInfo::print (CLUtils.hpp:313-332) with the reference's frame-0 exclusion rules
 // (bmfr.cpp:392-397,488-506): K1 / K4 / K5 / total over frames 1..N-1, K2 / K3 over frames 0..N-1.
 //
-//   bmfr_run [width height frames staged|fused]
+//   bmfr_run [width height frames staged|fused]                      synthetic sequence (synth-v1)
+//   bmfr_run --data DIR [--frames N] [--out DIR] [staged|fused]     a dataset in the reference's format:
+//       DIR/{color,shading_normal,world_position,albedo}N.exr + DIR/camera_matrices.h (bmfr.cpp:43-52),
+//       image size taken from color0.exr (the reference's TODO at bmfr.cpp:37), position / normal
+//       limits and the per-frame matrices / pixel offsets parsed from the header; with --out the
+//       frames are written as DIR/outputN.png (bmfr.cpp:52,520-539).
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -18,6 +23,7 @@
 #include <vector>
 
 #include "../../include/bmfr_b200.h"
+#include "../../include/bmfr_io.h"
 
 struct Table {  // same numbers and layout as ProfilingInfo (Mean / Min / Max / Total, 3 decimals)
     std::string label;
@@ -42,14 +48,56 @@ struct Table {  // same numbers and layout as ProfilingInfo (Mean / Min / Max / 
         }                                                             \
     } while (0)
 
+#define CHECK_IO(call)                                                \
+    do {                                                              \
+        int _st = (call);                                             \
+        if (_st != BMFR_IO_OK) {                                      \
+            printf("Error %d: %s\n", _st, bmfr_io_last_error());      \
+            return 1;                                                 \
+        }                                                             \
+    } while (0)
+
 int main(int argc, char** argv) {
-    const int W = argc > 2 ? atoi(argv[1]) : 1280, H = argc > 2 ? atoi(argv[2]) : 720;  // bmfr.cpp:39-40
-    const int frames = argc > 3 ? atoi(argv[3]) : 60;                                     // bmfr.cpp:42
-    const bool staged = !(argc > 4 && strcmp(argv[4], "fused") == 0);
+    int W = 1280, H = 720, frames = 60;  // bmfr.cpp:39-42
+    bool staged = true;
+    std::string data_dir, out_dir;
+    std::vector<std::string> pos;
+    for (int i = 1; i < argc; ++i) {
+        const std::string a = argv[i];
+        if (a == "--data" && i + 1 < argc) data_dir = argv[++i];
+        else if (a == "--out" && i + 1 < argc) out_dir = argv[++i];
+        else if (a == "--frames" && i + 1 < argc) frames = atoi(argv[++i]);
+        else if (a == "fused") staged = false;
+        else if (a == "staged") staged = true;
+        else pos.push_back(a);
+    }
+    if (data_dir.empty() && pos.size() >= 2) {
+        W = atoi(pos[0].c_str());
+        H = atoi(pos[1].c_str());
+        if (pos.size() >= 3) frames = atoi(pos[2].c_str());
+    }
+    if (frames < 1) {
+        printf("Error: no frames\n");
+        return 1;
+    }
 
     printf("Initialize.\n");
     bmfr_params prm;
-    bmfr_default_params(&prm, W, H);
+    std::vector<float> matrices((size_t)frames * 16), offsets((size_t)frames * 2);
+    if (!data_dir.empty()) {
+        int channels = 0;
+        CHECK_IO(bmfr_io_exr_info((data_dir + "/color0.exr").c_str(), &W, &H, &channels));
+        bmfr_default_params(&prm, W, H);
+        int nm = 0, no = 0;
+        CHECK_IO(bmfr_io_parse_camera_header((data_dir + "/camera_matrices.h").c_str(), frames, matrices.data(), offsets.data(), &nm,
+                                             &no, &prm.position_limit_squared, &prm.normal_limit_squared));
+        if (nm < frames || no < frames) {
+            printf("Error: camera_matrices.h holds %d matrices and %d pixel offsets, %d frames were asked for\n", nm, no, frames);
+            return 1;
+        }
+    } else {
+        bmfr_default_params(&prm, W, H);
+    }
     prm.mode = staged ? BMFR_MODE_STAGED : BMFR_MODE_FUSED;
     prm.profile = 1;
     bmfr_ctx* ctx = nullptr;
@@ -58,19 +106,43 @@ int main(int argc, char** argv) {
     printf("Loading input data.\n");
     const size_t n = (size_t)W * H * 3;
     std::vector<std::vector<float>> albedo(frames), normal(frames), position(frames), noisy(frames), out(frames);
-    for (int f = 0; f < frames; ++f) {
-        albedo[f].resize(n); normal[f].resize(n); position[f].resize(n); noisy[f].resize(n); out[f].resize(n);
-        CHECK(bmfr_synth_frame_host(W, H, 0, H, f, 0x424D4652u, albedo[f].data(), normal[f].data(), position[f].data(),
-                                    noisy[f].data()));
+    if (!data_dir.empty()) {  // bmfr.cpp:259-312
+        bool error = false;
+#pragma omp parallel for
+        for (int f = 0; f < frames; ++f) {
+            if (error) continue;
+            albedo[f].resize(n); normal[f].resize(n); position[f].resize(n); noisy[f].resize(n); out[f].resize(n);
+            const struct { const char* stem; float* dst; const char* what; } files[4] = {
+                {"albedo", albedo[f].data(), "Albedo"}, {"shading_normal", normal[f].data(), "Normal"},
+                {"world_position", position[f].data(), "Position"}, {"color", noisy[f].data(), "Noisy"}};
+            for (const auto& file : files) {
+                const std::string path = data_dir + "/" + file.stem + std::to_string(f) + ".exr";
+                if (bmfr_io_read_exr_rgb(path.c_str(), W, H, file.dst) != BMFR_IO_OK) {
+                    error = true;
+                    printf("%s buffer loading failed, reason: %s\n", file.what, bmfr_io_last_error());
+                    break;
+                }
+            }
+        }
+        if (error) {
+            printf("One or more errors occurred during buffer loading\n");
+            return 1;
+        }
+    } else {
+        for (int f = 0; f < frames; ++f) {
+            albedo[f].resize(n); normal[f].resize(n); position[f].resize(n); noisy[f].resize(n); out[f].resize(n);
+            CHECK(bmfr_synth_frame_host(W, H, 0, H, f, 0x424D4652u, albedo[f].data(), normal[f].data(), position[f].data(),
+                                        noisy[f].data()));
+            bmfr_synth_camera(f, W, H, 0, &matrices[(size_t)f * 16], &offsets[(size_t)f * 2]);
+        }
     }
 
     printf("Run and profile kernels.\n");
     for (int f = 0; f < frames; ++f) {
-        float cam[16], off[2], unused[16];
-        bmfr_synth_camera(f == 0 ? 0 : f - 1, W, H, 0, cam, unused);  // camera_matrices[matrix_index], bmfr.cpp:440-442
-        bmfr_synth_camera(f, W, H, 0, unused, off);                   // pixel_offsets[frame], bmfr.cpp:443-444
-        CHECK(bmfr_denoise_frame_host(ctx, f, albedo[f].data(), normal[f].data(), position[f].data(), noisy[f].data(), cam,
-                                      off, out[f].data()));
+        const int matrix_index = f == 0 ? 0 : f - 1;  // camera_matrices[matrix_index], bmfr.cpp:440-442
+        CHECK(bmfr_denoise_frame_host(ctx, f, albedo[f].data(), normal[f].data(), position[f].data(), noisy[f].data(),
+                                      &matrices[(size_t)matrix_index * 16], &offsets[(size_t)f * 2],  // pixel_offsets[frame], :443-444
+                                      out[f].data()));
     }
     CHECK(bmfr_sync(ctx));
 
@@ -106,5 +178,22 @@ int main(int argc, char** argv) {
     printf("checksum of the last frame: %.6f (%d x %d, %d frames, %lld kernel launches)\n", cs, W, H, frames,
            bmfr_kernel_launches(ctx));
     bmfr_destroy(ctx);
+
+    if (!out_dir.empty()) {  // "Store results", bmfr.cpp:519-553
+        bool error = false;
+#pragma omp parallel for
+        for (int f = 0; f < frames; ++f) {
+            if (error) continue;
+            const std::string path = out_dir + "/output" + std::to_string(f) + ".png";
+            if (bmfr_io_write_png_rgb(path.c_str(), W, H, out[f].data(), (size_t)W * 3) != BMFR_IO_OK) {
+                printf("Can't create image file on disk to location %s\n", path.c_str());
+                error = true;
+            }
+        }
+        if (error) {
+            printf("One or more errors occurred during image saving\n");
+            return 1;
+        }
+    }
     return 0;
 }
