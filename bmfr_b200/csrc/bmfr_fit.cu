@@ -455,8 +455,11 @@ __device__ __forceinline__ int qr_block_of_draw(int i, int nblocks, int blocks_x
 template <bool STRIP>
 __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(const __grid_constant__ KParams P,
                                                                                 const __grid_constant__ QrMaps M) {
+    // (the 128-byte alignment the TMA destination needs comes from the declaration: rounding the address
+    // up through an integer would hide the address space from the compiler, and every access to `sh`
+    // would become a generic LD / ST instead of LDS / STS)
     extern __shared__ __align__(128) unsigned char qr_smem[];
-    QrShared& sh = *reinterpret_cast<QrShared*>((reinterpret_cast<uintptr_t>(qr_smem) + 127) & ~(uintptr_t)127);
+    QrShared& sh = *reinterpret_cast<QrShared*>(qr_smem);
     const int tid = threadIdx.x, lane = tid & 31;
     // broadcast from lane 0 so that the compiler knows that branches on `warp` are warp-uniform (otherwise
     // the shuffles behind them get a second, divergence-safe copy and the kernel outgrows the instruction
@@ -731,7 +734,7 @@ static bool tile_map(const float* base, int W, int rows, CUtensorMap* out) {
 cudaError_t launch_fit_qr(const KParams& P, cudaStream_t st) {
     // persistent grid: as many CTAs as stay resident (sm_count * BMFR_QR_MIN_BLOCKS), never more than blocks
     static int sm_counts[64] = {};  // resident CTAs per device; 0 = this device has not been configured yet
-    const int smem = (int)sizeof(QrShared) + 128;
+    const int smem = (int)sizeof(QrShared);
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
