@@ -59,8 +59,9 @@ struct ExrHeader {
     int compression = -1, line_order = 0;
     int xmin = 0, ymin = 0, xmax = -1, ymax = -1;
     size_t table = 0;  // file offset of the chunk offset table
-    int width() const { return xmax - xmin + 1; }
-    int height() const { return ymax - ymin + 1; }
+    // (64-bit: the four corners are arbitrary 32-bit values in a damaged file)
+    long long width() const { return (long long)xmax - xmin + 1; }
+    long long height() const { return (long long)ymax - ymin + 1; }
 };
 
 struct Cursor {
@@ -297,8 +298,8 @@ int bmfr_io_exr_info(const char* path, int* width, int* height, int* channels) {
     ExrHeader h;
     const int st = parse_header(file, path, h);
     if (st != BMFR_IO_OK) return st;
-    *width = h.width();
-    *height = h.height();
+    *width = (int)h.width();
+    *height = (int)h.height();
     *channels = (int)h.channels.size();
     return BMFR_IO_OK;
 }
@@ -311,8 +312,8 @@ int bmfr_io_read_exr_rgb(const char* path, int width, int height, float* rgb) {
     int st = parse_header(file, path, h);
     if (st != BMFR_IO_OK) return st;
     if (h.width() != width || h.height() != height || h.channels.size() != 3)  // bmfr.cpp:150-155
-        return fail(BMFR_IO_ERR_MISMATCH, "%s: %d x %d with %d channels, expected %d x %d with 3 (wrong type)", path, h.width(),
-                    h.height(), (int)h.channels.size(), width, height);
+        return fail(BMFR_IO_ERR_MISMATCH, "%s: %d x %d with %d channels, expected %d x %d with 3 (wrong type)", path, (int)h.width(),
+                    (int)h.height(), (int)h.channels.size(), width, height);
     if (h.compression > COMP_ZIP)
         return fail(BMFR_IO_ERR_UNSUPPORTED, "%s: compression %d is not covered (NONE, RLE, ZIPS, ZIP are)", path, h.compression);
     size_t line_bytes = 0;
@@ -336,15 +337,16 @@ int bmfr_io_read_exr_rgb(const char* path, int width, int height, float* rgb) {
     for (int k = 0; k < chunks; ++k) {
         uint64_t off = 0;
         for (int b = 0; b < 8; ++b) off |= (uint64_t)file[h.table + (size_t)k * 8 + b] << (8 * b);
-        if (off + 8 > file.size()) return fail(BMFR_IO_ERR_FORMAT, "%s: chunk %d lies outside the file", path, k);
+        if (file.size() < 8 || off > file.size() - 8) return fail(BMFR_IO_ERR_FORMAT, "%s: chunk %d lies outside the file", path, k);
         Cursor c{file.data(), file.size(), (size_t)off};
         int32_t y = 0, size = 0;
         c.i32(y);
         c.i32(size);
         if (size < 0 || !c.has((size_t)size)) return fail(BMFR_IO_ERR_FORMAT, "%s: chunk %d is truncated", path, k);
-        const int y0 = y - h.ymin;
-        if (y0 < 0 || y0 >= height || y0 % lines_per_chunk != 0)
+        const long long row = (long long)y - h.ymin;
+        if (row < 0 || row >= height || row % lines_per_chunk != 0)
             return fail(BMFR_IO_ERR_FORMAT, "%s: chunk %d starts at scanline %d", path, k, y);
+        const int y0 = (int)row;
         const int lines = std::min(lines_per_chunk, height - y0);
         const size_t expect = line_bytes * (size_t)lines;
         const unsigned char* src = file.data() + c.at;

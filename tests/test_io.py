@@ -130,6 +130,13 @@ def test_exr_errors_follow_the_reference(io, tmp_path):
         t = tmp_path / f"cut{cut}.exr"
         t.write_bytes(blob[:cut])
         assert _read(io, t, w, h)[0] == ERR_FORMAT, cut
+    # a data window whose corners overflow 32-bit arithmetic (found by scripts/fuzz_io.cpp)
+    blob_w = bytearray(blob)
+    at = blob_w.index(b"dataWindow\0box2i\0") + len(b"dataWindow\0box2i\0") + 4
+    blob_w[at:at + 4] = (-2**31).to_bytes(4, "little", signed=True)
+    t = tmp_path / "window.exr"
+    t.write_bytes(bytes(blob_w))
+    assert _read(io, t, w, h)[0] == ERR_FORMAT
     junk = tmp_path / "junk.exr"
     junk.write_bytes(b"not an exr file at all")
     assert _read(io, junk, w, h)[0] == ERR_FORMAT
