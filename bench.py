@@ -273,7 +273,8 @@ def run_single_gpu(args):
             d.denoise_frame(f, inputs[f, 0].data_ptr(), inputs[f, 1].data_ptr(), inputs[f, 2].data_ptr(),
                             inputs[f, 3].data_ptr(), cams[f], offs[f], None)
 
-    d = Denoiser(w, h, mode=args.mode, stream=sp)
+    overlap = int(args.overlap and args.mode == "fused")
+    d = Denoiser(w, h, mode=args.mode, stream=sp, overlap_frames=overlap)
     for _ in range(args.warmup):
         run_sequence(d)
     torch.cuda.synchronize()
@@ -284,6 +285,7 @@ def run_single_gpu(args):
         e0.record(stream)
         for _ in range(args.steps):
             run_sequence(d)
+        d.join()  # overlapped frames run on the context's internal streams: order the closing event after them
         e1.record(stream)
         torch.cuda.synchronize()
     d.sync()
@@ -343,7 +345,7 @@ def run_single_gpu(args):
         host_out = torch.empty((2, h, w, 3), dtype=torch.float32, pin_memory=True)
         torch.cuda.synchronize()
         hin, hout = host_in.numpy(), host_out.numpy()
-        dh = Denoiser(w, h, mode=args.mode)
+        dh = Denoiser(w, h, mode=args.mode, overlap_frames=overlap)
 
         def run_host_sequence():
             for f in range(FRAMES):
@@ -376,7 +378,8 @@ def run_single_gpu(args):
         "ms_per_step": ms_per_step, "ms_per_frame": ms_per_step / FRAMES, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{w}x{h} x{FRAMES} frames synth-v1, 32x32 blocks, 10 features, fp32 tmp_data",
-                   "mode": args.mode, "l2": "inputs (5.97 GB/sequence at 1080p) larger than L2; no explicit flush",
+                   "mode": args.mode, "overlap_frames": overlap,
+                   "l2": "inputs (5.97 GB/sequence at 1080p) larger than L2; no explicit flush",
                    "parallelism": "single GPU"},
         "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
         "clocks": clocks.summary(),
@@ -397,6 +400,9 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=8, help="frames of the workload the cpu_baseline runs")
     ap.add_argument("--ref-frames", type=int, default=6, help="frames per pass of --impl reference")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="halo transport of the sharded run (N > 1)")
+    ap.add_argument("--overlap", type=int, default=1, choices=[0, 1],
+                    help="bmfr_params.overlap_frames of the timed contexts: 1 = consecutive frames overlap on the device "
+                         "(three event-linked streams), 0 = one in-order stream")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

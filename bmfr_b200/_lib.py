@@ -33,7 +33,7 @@ class Params(C.Structure):
                 ("taa_blend_alpha", C.c_float), ("position_limit_squared", C.c_float),
                 ("normal_limit_squared", C.c_float), ("tmp_half", C.c_int), ("profile", C.c_int),
                 ("strip_y0", C.c_int), ("strip_y1", C.c_int), ("halo_rows", C.c_int), ("stream", C.c_void_p),
-                ("reference_order", C.c_int)]
+                ("reference_order", C.c_int), ("overlap_frames", C.c_int)]
 
 
 class Geometry(C.Structure):
@@ -59,6 +59,7 @@ SYMBOLS = {
     "bmfr_denoise_frame": (_I, [_P, _I, _P, _P, _P, _P, _F, _F, _P]),
     "bmfr_denoise_frame_host": (_I, [_P, _I, _P, _P, _P, _P, _F, _F, _P]),
     "bmfr_sync": (_I, [_P]),
+    "bmfr_join": (_I, [_P]),
     "bmfr_get_buffer": (_I, [_P, _I, C.POINTER(_P), C.POINTER(C.c_size_t)]),
     "bmfr_read_buffer": (_I, [_P, _I, _P, C.c_size_t]),
     "bmfr_get_stage_ms": (_I, [_P, _I, _F]),

@@ -675,8 +675,8 @@ cudaError_t launch_reproject(const KParams& P, cudaStream_t st) {
     const int rows_per_cta = BMFR_REPROJECT_BY * BMFR_REPROJECT_PIXELS;
     const dim3 grid((P.W + BMFR_REPROJECT_BX - 1) / BMFR_REPROJECT_BX, (P.k1_y1 - P.k1_y0 + rows_per_cta - 1) / rows_per_cta),
         block(BMFR_REPROJECT_BX, BMFR_REPROJECT_BY);
-    if (is_strip(P)) return launch_pdl(reproject_kernel<true>, grid, block, 0, st, P);
-    return launch_pdl(reproject_kernel<false>, grid, block, 0, st, P);
+    if (is_strip(P)) return launch_pdl(!P.plain_launch, reproject_kernel<true>, grid, block, 0, st, P);
+    return launch_pdl(!P.plain_launch, reproject_kernel<false>, grid, block, 0, st, P);
 }
 // ---- tensor maps of a frame --------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -761,6 +761,6 @@ cudaError_t launch_fit_qr(const KParams& P, cudaStream_t st) {
     const int rows = P.row1 - P.row0;
     M.use_tma = tile_map(P.cur_normals, P.W, rows, &M.normals) && tile_map(P.cur_positions, P.W, rows, &M.positions) &&
                 tile_map(P.cur_noisy_acc, P.W, rows, &M.colour);
-    if (is_strip(P)) return launch_pdl(fit_qr_kernel<true>, dim3(grid), dim3(QR_THREADS), (size_t)smem, st, P, M);
-    return launch_pdl(fit_qr_kernel<false>, dim3(grid), dim3(QR_THREADS), (size_t)smem, st, P, M);
+    if (is_strip(P)) return launch_pdl(!P.plain_launch, fit_qr_kernel<true>, dim3(grid), dim3(QR_THREADS), (size_t)smem, st, P, M);
+    return launch_pdl(!P.plain_launch, fit_qr_kernel<false>, dim3(grid), dim3(QR_THREADS), (size_t)smem, st, P, M);
 }

@@ -117,6 +117,24 @@ struct bmfr_ctx {
     cudaEvent_t halo_ready = nullptr, halo_pushed = nullptr;
     unsigned int* d_flags = nullptr;   // [0]: frames completed by the neighbour above, [1]: below; [2]: wait timed out
     long long seq = 0;                 // frames submitted on this context
+
+    // Overlapped frames (params.overlap_frames, FUSED whole-frame contexts): reprojection, fit and post pass
+    // each have their own stream; events order them within a frame (R -> F -> P) and across frames (R(f)
+    // after P(f-2): everything a frame hands from one kernel to the next exists twice, indexed by frame
+    // parity, so frame f+1 can start while frame f is still in its fit / post pass).
+    struct Overlap {
+        bool on = false;
+        cudaStream_t s_r = nullptr, s_f = nullptr, s_p = nullptr;
+        cudaEvent_t e_in[2] = {}, e_r[2] = {}, e_f[2] = {}, e_p[2] = {};
+        // the second copy (odd frames) of the per-frame temporaries; even frames use the context's own
+        float2* prev_pixels = nullptr;
+        unsigned char* accept = nullptr;
+        float *weights = nullptr, *mins_maxs = nullptr, *mins_inv = nullptr, *noise_f = nullptr;
+        double* noise = nullptr;
+        int* counter = nullptr;
+    } ov;
+    int parity() const { return ov.on ? (int)(seq & 1) : 0; }            // of the frame being submitted
+    int last_parity() const { return ov.on ? (int)((seq + 1) & 1) : 0; }  // of the last submitted frame
 };
 
 static size_t rows_of(const bmfr_ctx* c) { return (size_t)(c->geo.row1 - c->geo.row0); }
@@ -153,6 +171,16 @@ static void free_ctx(bmfr_ctx* c) {
     cudaFree(c->noise_f);
     cudaFree(c->d_oob);
     cudaFree(c->tri);
+    {
+        bmfr_ctx::Overlap& o = c->ov;
+        for (cudaStream_t st : {o.s_r, o.s_f, o.s_p})
+            if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+        for (int i = 0; i < 2; ++i)
+            for (cudaEvent_t e : {o.e_in[i], o.e_r[i], o.e_f[i], o.e_p[i]})
+                if (e) cudaEventDestroy(e);
+        cudaFree(o.prev_pixels); cudaFree(o.accept); cudaFree(o.weights); cudaFree(o.mins_maxs); cudaFree(o.mins_inv);
+        cudaFree(o.noise); cudaFree(o.noise_f); cudaFree(o.counter);
+    }
     for (int side = 0; side < 2; ++side) {
         bmfr_ctx::Peer& pr = c->peer[side];
         if (pr.connected && pr.ipc) {
@@ -316,6 +344,25 @@ int bmfr_create(const bmfr_params* params, bmfr_ctx** out_ctx) {
     if ((st = bmfr_check_cuda(cudaMemsetAsync(c->mins_maxs, 0, nb * BMFR_FEATURES_SCALED * 2 * sizeof(float), c->stream), "memset")) != 0) return fail(st);
     if ((st = bmfr_check_cuda(cudaMemsetAsync(c->mins_inv, 0, nb * BMFR_FEATURES_SCALED * 2 * sizeof(float), c->stream), "memset")) != 0) return fail(st);
     if (p.profile) c->prof.resize(kProfileSlots);
+    if (p.overlap_frames && p.mode == BMFR_MODE_FUSED && !p.profile && g.own_y0 == 0 && g.own_y1 == g.height && g.row0 == 0 &&
+        g.row1 == g.height) {
+        bmfr_ctx::Overlap& o = c->ov;
+        if (st == 0) st = dev_alloc(&o.prev_pixels, npix, "prev_pixels (odd frames)");
+        if (st == 0) st = dev_alloc(&o.accept, npix, "accept (odd frames)");
+        if (st == 0) st = dev_alloc(&o.weights, nb * BMFR_FEATURES * 3, "weights (odd frames)");
+        if (st == 0) st = dev_alloc(&o.mins_maxs, nb * BMFR_FEATURES_SCALED * 2, "mins_maxs (odd frames)");
+        if (st == 0) st = dev_alloc(&o.mins_inv, nb * BMFR_FEATURES_SCALED * 2, "mins_inv (odd frames)");
+        if (st == 0) st = dev_alloc(&o.noise, (size_t)(BMFR_FEATURES - 1) * BMFR_BLOCK_PIXELS, "noise (odd frames)");
+        if (st == 0) st = dev_alloc(&o.noise_f, (size_t)(BMFR_FEATURES - 1) * BMFR_BLOCK_PIXELS, "noise_f (odd frames)");
+        if (st == 0) st = dev_alloc(&o.counter, 1, "block counter (odd frames)");
+        for (cudaStream_t* ps : {&o.s_r, &o.s_f, &o.s_p})
+            if (st == 0) st = bmfr_check_cuda(cudaStreamCreateWithFlags(ps, cudaStreamNonBlocking), "cudaStreamCreate");
+        for (int i = 0; i < 2; ++i)
+            for (cudaEvent_t* pe : {&o.e_in[i], &o.e_r[i], &o.e_f[i], &o.e_p[i]})
+                if (st == 0) st = bmfr_check_cuda(cudaEventCreateWithFlags(pe, cudaEventDisableTiming), "cudaEventCreate");
+        if (st != 0) return fail(st);
+        o.on = true;
+    }
     if ((st = bmfr_check_cuda(cudaStreamSynchronize(c->stream), "create sync")) != 0) return fail(st);
     *out_ctx = c;
     return BMFR_OK;
@@ -374,15 +421,22 @@ static void fill_params(bmfr_ctx* c, KParams& P, int frame, const float* d_albed
     P.cur_noisy = d_noisy;
     P.prev_noisy_acc = c->noisy_acc.previous(); P.cur_noisy_acc = c->noisy_acc.current();
     P.prev_spp = c->spp.previous(); P.cur_spp = c->spp.current();
-    P.prev_pixels = c->prev_pixels; P.accept = c->accept;
+    const bool odd = c->parity() == 1;
+    P.prev_pixels = odd ? c->ov.prev_pixels : c->prev_pixels; P.accept = odd ? c->ov.accept : c->accept;
     P.tmp_half = c->prm.tmp_half; P.reference_order = c->prm.reference_order;
-    P.tmp_data = c->tmp_data; P.weights = c->weights; P.mins_maxs = c->mins_maxs; P.mins_inv = c->mins_inv; P.noise = c->noise;
-    P.noise_f = c->noise_f; P.noise_out = c->noise; P.noise_f_out = c->noise_f; P.noise_amount = c->prm.noise_amount;
+    P.tmp_data = c->tmp_data;
+    P.weights = odd ? c->ov.weights : c->weights;
+    P.mins_maxs = odd ? c->ov.mins_maxs : c->mins_maxs;
+    P.mins_inv = odd ? c->ov.mins_inv : c->mins_inv;
+    P.noise = odd ? c->ov.noise : c->noise;
+    P.noise_f = odd ? c->ov.noise_f : c->noise_f;
+    P.noise_out = const_cast<double*>(P.noise); P.noise_f_out = const_cast<float*>(P.noise_f); P.noise_amount = c->prm.noise_amount;
     P.albedo = d_albedo; P.filtered = c->filtered;
     P.accum_prev = c->accum.previous(); P.accum_cur = c->accum.current();
     P.tone_mapped = c->tone_mapped;
     P.result_prev = c->result.previous(); P.result_cur = c->result.current();
-    P.user_out = d_out; P.oob_flag = c->d_oob; P.block_counter = c->d_oob + 1;
+    P.user_out = d_out; P.oob_flag = c->d_oob; P.block_counter = odd ? c->ov.counter : c->d_oob + 1;
+    P.plain_launch = c->ov.on ? 1 : 0;
     P.tri = c->tri;
 }
 
@@ -430,6 +484,25 @@ static int run_frame(bmfr_ctx* c, const KParams& P, int frame) {
         MARK(4);
         LAUNCH_TRY(launch_k5(P, c->stream), "taa");
         MARK(5);
+    } else if (c->ov.on) {
+        // R(f) | F(f) | P(f) on three streams.  R(f) follows the caller's work on the context's stream and
+        // P(f-2): the buffers of this parity (accumulated colour + spp as "current", prev_pixels, accept,
+        // noise tile, block counter, weights, min/max) were last read by frame f-2.  R(f-1) precedes R(f) on
+        // the same stream (temporal state), as F(f-1) precedes F(f) (triangle scratch) and P(f-1) P(f)
+        // (accumulated filtered colour, TAA history).
+        bmfr_ctx::Overlap& o = c->ov;
+        const int q = c->parity();
+        BMFR_CUDA_TRY(cudaEventRecord(o.e_in[q], c->stream));
+        BMFR_CUDA_TRY(cudaStreamWaitEvent(o.s_r, o.e_in[q], 0));
+        if (c->seq >= 2) BMFR_CUDA_TRY(cudaStreamWaitEvent(o.s_r, o.e_p[q], 0));
+        LAUNCH_TRY(launch_reproject(P, o.s_r), "reproject_kernel");
+        BMFR_CUDA_TRY(cudaEventRecord(o.e_r[q], o.s_r));
+        BMFR_CUDA_TRY(cudaStreamWaitEvent(o.s_f, o.e_r[q], 0));
+        LAUNCH_TRY(launch_fit_qr(P, o.s_f), "fit_qr_kernel");
+        BMFR_CUDA_TRY(cudaEventRecord(o.e_f[q], o.s_f));
+        BMFR_CUDA_TRY(cudaStreamWaitEvent(o.s_p, o.e_f[q], 0));
+        LAUNCH_TRY(launch_post(P, o.s_p), "post_kernel");
+        BMFR_CUDA_TRY(cudaEventRecord(o.e_p[q], o.s_p));
     } else {
         LAUNCH_TRY(launch_reproject(P, c->stream), "reproject_kernel");
         MARK(1);
@@ -663,16 +736,19 @@ int bmfr_denoise_frame_host(bmfr_ctx* c, int frame, const float* h_albedo, const
     BMFR_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->up_done[slot], 0));
     // result.current() of this frame was last read by the D2H of two frames ago
     const int rslot = (int)(c->host_frames & 1);
-    if (c->host_frames >= 2) BMFR_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->d2h_done[rslot], 0));
+    // (overlapped frames: the post pass, which writes it, runs on its own stream; that stream also carries
+    // "the kernels of this frame are done")
+    cudaStream_t done_stream = c->ov.on ? c->ov.s_p : c->stream;
+    if (c->host_frames >= 2) BMFR_CUDA_TRY(cudaStreamWaitEvent(done_stream, c->d2h_done[rslot], 0));
     float* d_result = c->result.current();
     st = bmfr_denoise_frame(c, frame, c->up[0][slot], c->up[1][slot], c->up[2][slot], c->up[3][slot], cam_prev,
                             pixel_offset, nullptr);
     if (st != 0) return st;
     // the previous frame's slot is released once this frame's kernels (which read it as "previous") are done
-    BMFR_CUDA_TRY(cudaEventRecord(c->frame_done[slot], c->stream));
+    BMFR_CUDA_TRY(cudaEventRecord(c->frame_done[slot], done_stream));
     if (c->host_frames >= 1) {
         const int pslot = (int)((c->host_frames - 1) % kHostSlots);
-        BMFR_CUDA_TRY(cudaEventRecord(c->frame_done[pslot], c->stream));
+        BMFR_CUDA_TRY(cudaEventRecord(c->frame_done[pslot], done_stream));
     }
     if (h_out) {  // bmfr.cpp:479-480
         BMFR_CUDA_TRY(cudaStreamWaitEvent(c->d2h_stream, c->frame_done[slot], 0));
@@ -685,11 +761,22 @@ int bmfr_denoise_frame_host(bmfr_ctx* c, int frame, const float* h_albedo, const
     return BMFR_OK;
 }
 
+int bmfr_join(bmfr_ctx* c) {
+    if (!c) return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_join: null context");
+    if (!c->ov.on || c->seq == 0) return BMFR_OK;
+    BMFR_CUDA_TRY(cudaSetDevice(c->prm.device));
+    // P(f) is the last kernel of frame f, and the post passes run in order on one stream
+    BMFR_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ov.e_p[c->last_parity()], 0));
+    return BMFR_OK;
+}
+
 int bmfr_sync(bmfr_ctx* c) {
     if (!c) return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_sync: null context");
     BMFR_CUDA_TRY(cudaSetDevice(c->prm.device));
     if (c->h2d_stream) BMFR_CUDA_TRY(cudaStreamSynchronize(c->h2d_stream));
     BMFR_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    for (cudaStream_t st : {c->ov.s_r, c->ov.s_f, c->ov.s_p})
+        if (st) BMFR_CUDA_TRY(cudaStreamSynchronize(st));
     if (c->d2h_stream) BMFR_CUDA_TRY(cudaStreamSynchronize(c->d2h_stream));
     unsigned int timed_out = 0;
     BMFR_CUDA_TRY(cudaMemcpy(&timed_out, c->d_flags + 2, sizeof(unsigned int), cudaMemcpyDeviceToHost));
@@ -715,20 +802,21 @@ int bmfr_get_buffer(bmfr_ctx* c, int buffer, void** d_ptr, size_t* bytes) {
     const size_t nb = (size_t)c->geo.blocks_x * c->geo.blocks_y;
     void* p = nullptr;
     size_t n = 0;
+    const bool last_odd = c->last_parity() == 1;  // overlapped frames: which copy the last frame wrote
     // after the swap at the end of a frame the buffers that frame wrote are the "previous" halves
     switch (buffer) {
         case BMFR_BUF_NOISY_ACC: p = c->noisy_acc.previous(); n = npix * 12; break;
         case BMFR_BUF_SPP: p = c->spp.previous(); n = npix; break;
-        case BMFR_BUF_PREV_PIXELS: p = c->prev_pixels; n = npix * 8; break;
-        case BMFR_BUF_ACCEPT: p = c->accept; n = npix; break;
+        case BMFR_BUF_PREV_PIXELS: p = last_odd ? c->ov.prev_pixels : c->prev_pixels; n = npix * 8; break;
+        case BMFR_BUF_ACCEPT: p = last_odd ? c->ov.accept : c->accept; n = npix; break;
         case BMFR_BUF_TMP_DATA: p = c->tmp_data; n = (size_t)c->tmp_block_rows * c->geo.blocks_x * BMFR_BUFFER_COUNT * BMFR_BLOCK_PIXELS * 4; break;
-        case BMFR_BUF_WEIGHTS: p = c->weights; n = nb * BMFR_FEATURES * 3 * 4; break;
-        case BMFR_BUF_MINS_MAXS: p = c->mins_maxs; n = nb * BMFR_FEATURES_SCALED * 2 * 4; break;
+        case BMFR_BUF_WEIGHTS: p = last_odd ? c->ov.weights : c->weights; n = nb * BMFR_FEATURES * 3 * 4; break;
+        case BMFR_BUF_MINS_MAXS: p = last_odd ? c->ov.mins_maxs : c->mins_maxs; n = nb * BMFR_FEATURES_SCALED * 2 * 4; break;
         case BMFR_BUF_FILTERED: p = c->filtered; n = npix * 12; break;
         case BMFR_BUF_ACCUM: p = c->accum.previous(); n = npix * 12; break;
         case BMFR_BUF_TONE_MAPPED: p = c->tone_mapped; n = npix * 12; break;
         case BMFR_BUF_RESULT: p = c->result.previous(); n = npix * 12; break;
-        case BMFR_BUF_NOISE_TILE: p = c->noise; n = (size_t)(BMFR_FEATURES - 1) * BMFR_BLOCK_PIXELS * 8; break;
+        case BMFR_BUF_NOISE_TILE: p = last_odd ? c->ov.noise : c->noise; n = (size_t)(BMFR_FEATURES - 1) * BMFR_BLOCK_PIXELS * 8; break;
         default: return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_get_buffer: unknown buffer %d", buffer);
     }
     if (!p)

@@ -432,9 +432,9 @@ cudaError_t launch_post(const KParams& P, cudaStream_t st) {
     // arithmetic) and the same number of L1 wavefronts, so it is kept only as a tuning switch
     const bool wide = BMFR_POST_WIDE_ACCESS && (bits & 7) == 0;
     if (strip) {
-        if (wide) return launch_pdl(post_kernel<true, true>, grid, dim3(256), 0, st, P);
-        return launch_pdl(post_kernel<true, false>, grid, dim3(256), 0, st, P);
+        if (wide) return launch_pdl(!P.plain_launch, post_kernel<true, true>, grid, dim3(256), 0, st, P);
+        return launch_pdl(!P.plain_launch, post_kernel<true, false>, grid, dim3(256), 0, st, P);
     }
-    if (wide) return launch_pdl(post_kernel<false, true>, grid, dim3(256), 0, st, P);
-    return launch_pdl(post_kernel<false, false>, grid, dim3(256), 0, st, P);
+    if (wide) return launch_pdl(!P.plain_launch, post_kernel<false, true>, grid, dim3(256), 0, st, P);
+    return launch_pdl(!P.plain_launch, post_kernel<false, false>, grid, dim3(256), 0, st, P);
 }

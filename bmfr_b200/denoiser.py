@@ -35,7 +35,7 @@ def block_offset(frame: int):
 class Denoiser:
     def __init__(self, width, height, *, mode="fused", device=0, profile=False, stream=0, strip=None, halo_rows=0,
                  position_limit_squared=None, normal_limit_squared=None, noise_amount=None, blend_alpha=None,
-                 second_blend_alpha=None, taa_blend_alpha=None, tmp_half=0, reference_order=0):
+                 second_blend_alpha=None, taa_blend_alpha=None, tmp_half=0, reference_order=0, overlap_frames=0):
         self.lib = _lib.load()
         p = Params()
         self.lib.bmfr_default_params(C.byref(p), width, height)
@@ -43,6 +43,7 @@ class Denoiser:
         p.mode = {"staged": MODE_STAGED, "fused": MODE_FUSED}[mode]
         p.profile = int(profile)
         p.tmp_half, p.reference_order = int(tmp_half), int(reference_order)
+        p.overlap_frames = int(overlap_frames)
         p.stream = C.c_void_p(stream or None)
         if strip is not None:
             p.strip_y0, p.strip_y1, p.halo_rows = int(strip[0]), int(strip[1]), int(halo_rows)
@@ -101,6 +102,10 @@ class Denoiser:
 
     def sync(self):
         _lib.check(self.lib.bmfr_sync(self._h))
+
+    def join(self):
+        """Orders the context's stream after all submitted frames (contexts with overlap_frames; else a no-op)."""
+        _lib.check(self.lib.bmfr_join(self._h))
 
     # -- inspection -----------------------------------------------------------------------------
     def buffer_ptr(self, name):

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define BMFR_B200_ABI_VERSION 2
+#define BMFR_B200_ABI_VERSION 3
 
 /* Compile-time constants of the reference that are not tunable (bmfr.cpp:102-118). */
 #define BMFR_BLOCK_EDGE 32          /* BLOCK_EDGE_LENGTH, bmfr.cpp:104 */
@@ -80,6 +80,15 @@ typedef struct bmfr_params {
      * scale()), which makes EVERY buffer of the loop bit-identical to the reference kernels' arithmetic
      * — the compatibility mode; slower than the default fitter. */
     int reference_order;
+    /* FUSED, whole-frame contexts without profiling only (ignored otherwise).  1: consecutive frames may
+     * overlap on the device.  The reprojection of frame f+1 does not depend on the fit and the post pass of
+     * frame f, so the three kernels are enqueued on three internal streams linked by events (per-frame
+     * temporaries double-buffered) and the tail of one kernel is filled by the next frame's work.  The
+     * context's stream is then ordered BEFORE a frame's kernels (the caller's producers of the inputs) but
+     * not after them: the output (d_out, bmfr_get_buffer) is valid, and the input buffers of the last two
+     * frames may be overwritten, only after bmfr_sync() or, on the stream, after bmfr_join().  bmfr_denoise_frame_host handles that ordering
+     * itself.  0 (default): one in-order stream, the reference's queue semantics (bmfr.cpp:191). */
+    int overlap_frames;
 } bmfr_params;
 
 typedef struct bmfr_ctx bmfr_ctx;
@@ -166,6 +175,12 @@ int bmfr_denoise_frame_host(bmfr_ctx* ctx, int frame, const float* h_albedo, con
 
 /* queue.finish(), bmfr.cpp:486.  Also reports BMFR_ERR_HALO_TOO_SMALL for sharded contexts. */
 int bmfr_sync(bmfr_ctx* ctx);
+
+/* Orders the context's stream after every frame submitted so far, without blocking the host: what follows
+ * on that stream (an event record, a copy of d_out, the producer of the next inputs) sees the frames
+ * complete.  Only contexts with overlap_frames = 1 need it (their kernels run on internal streams); on
+ * the others it does nothing, the stream already is in order. */
+int bmfr_join(bmfr_ctx* ctx);
 
 /* Device pointer + size of one of the loop's buffers as of the last submitted frame. */
 int bmfr_get_buffer(bmfr_ctx* ctx, int buffer, void** d_ptr, size_t* bytes);

@@ -5,6 +5,7 @@ must be bit-exact; fitted / accumulated colour must be within the north star's t
 import numpy as np
 import pytest
 
+from bmfr_b200 import Denoiser
 from tests import util
 
 pytestmark = pytest.mark.gpu
@@ -123,3 +124,43 @@ def test_staged_and_fused_agree():
     assert util.floats_equal_mod_zero_sign(a["mins_maxs"], b["mins_maxs"])
     for k in util.COLOUR_BUFFERS:
         util.assert_colour_close(b[k], a[k], k)
+
+
+@pytest.mark.parametrize("size", [(256, 160), (1920, 1080)])
+def test_overlapped_frames_are_bit_identical(size):
+    """params.overlap_frames: the three kernels on three event-linked streams, per-frame temporaries double-
+    buffered.  Same kernels on the same inputs: every output frame and every buffer must equal the in-order
+    run bit for bit, through the host entry (upload ring, read-back) and through the device-pointer entry with
+    all frames resident (nothing between the frames but the events)."""
+    import torch
+
+    w, h = size
+    frames = 9
+    seq = list(util.sequence(w, h, frames))
+
+    def run_host(overlap):
+        outs = [np.empty((h, w, 3), dtype=np.float32) for _ in range(frames)]
+        with Denoiser(w, h, mode="fused", overlap_frames=overlap) as d:
+            for (f, a, n, p, c, cam, off), out in zip(seq, outs):
+                d.denoise_frame_host(f, a, n, p, c, cam, off, out)
+            d.sync()
+            return outs, {k: d.read(k) for k in KEEP_FUSED}
+
+    def run_device(overlap):
+        dev = [[torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in (a, n, p, c)] for (_, a, n, p, c, _, _) in seq]
+        outs = [torch.empty((h, w, 3), dtype=torch.float32, device="cuda") for _ in range(frames)]
+        torch.cuda.synchronize()
+        with Denoiser(w, h, mode="fused", overlap_frames=overlap) as d:
+            for (f, _, _, _, _, cam, off), t, out in zip(seq, dev, outs):
+                d.denoise_frame(f, *[x.data_ptr() for x in t], cam, off, out.data_ptr())
+            d.sync()
+            return [o.cpu().numpy() for o in outs], {k: d.read(k) for k in KEEP_FUSED}
+
+    for run in (run_host, run_device):
+        ref_outs, ref_bufs = run(0)
+        for rep in range(2):
+            outs, bufs = run(1)
+            for f in range(frames):
+                assert util.bits_equal(outs[f], ref_outs[f]), f"{run.__name__}: output of frame {f} differs (pass {rep})"
+            for k in KEEP_FUSED:
+                assert util.bits_equal(bufs[k], ref_bufs[k]), f"{run.__name__}: {k} differs (pass {rep})"
