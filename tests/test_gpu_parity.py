@@ -156,6 +156,28 @@ def test_overlapped_frames_are_bit_identical(size):
             d.sync()
             return [o.cpu().numpy() for o in outs], {k: d.read(k) for k in KEEP_FUSED}
 
+    def run_joined():
+        """bmfr_join: work on the context's stream after it sees the frames complete, with no host synchronisation."""
+        stream = torch.cuda.Stream()
+        dev = [[torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in (a, n, p, c)] for (_, a, n, p, c, _, _) in seq]
+        outs = [torch.empty((h, w, 3), dtype=torch.float32, device="cuda") for _ in range(frames)]
+        torch.cuda.synchronize()
+        with Denoiser(w, h, mode="fused", overlap_frames=1, stream=stream.cuda_stream) as d:
+            for (f, _, _, _, _, cam, off), t, out in zip(seq, dev, outs):
+                d.denoise_frame(f, *[x.data_ptr() for x in t], cam, off, out.data_ptr())
+            d.join()
+            with torch.cuda.stream(stream):
+                snap = [o.clone() for o in outs]  # stream-ordered after the join
+            stream.synchronize()  # the context's stream only: the internal streams are not waited for by the host
+            got = [x.cpu().numpy() for x in snap]
+            d.sync()
+        return got
+
+    joined = run_joined()
+    ref_outs, _ = run_device(0)
+    for f in range(frames):
+        assert util.bits_equal(joined[f], ref_outs[f]), f"bmfr_join: frame {f} was copied before it was complete"
+
     for run in (run_host, run_device):
         ref_outs, ref_bufs = run(0)
         for rep in range(2):
