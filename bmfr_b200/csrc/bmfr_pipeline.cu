@@ -115,7 +115,10 @@ struct bmfr_ctx {
     } peer[2];
     cudaStream_t halo_stream = nullptr;               // early push (accumulated colour + spp) overlaps fit and post
     cudaEvent_t halo_ready = nullptr, halo_pushed = nullptr;
-    unsigned int* d_flags = nullptr;   // [0]: frames completed by the neighbour above, [1]: below; [2]: wait timed out
+    // [0]: frames completed by the neighbour above, [1]: below; [2]: a wait timed out.  Overlapped frames split the
+    // signal: [0], [1] = frames whose accumulated noisy colour + spp rows have arrived (after the neighbour's
+    // reprojection), [4], [5] = frames whose accumulated filtered colour + TAA rows have arrived (after its post pass)
+    unsigned int* d_flags = nullptr;
     long long seq = 0;                 // frames submitted on this context
 
     // Overlapped frames (params.overlap_frames, FUSED whole-frame contexts): reprojection, fit and post pass
@@ -125,7 +128,7 @@ struct bmfr_ctx {
     struct Overlap {
         bool on = false;
         cudaStream_t s_r = nullptr, s_f = nullptr, s_p = nullptr;
-        cudaEvent_t e_in[2] = {}, e_r[2] = {}, e_f[2] = {}, e_p[2] = {};
+        cudaEvent_t e_in[2] = {}, e_r[2] = {}, e_f[2] = {}, e_p[2] = {}, e_e[2] = {};  // e_e: early halo push done
         // the second copy (odd frames) of the per-frame temporaries; even frames use the context's own
         float2* prev_pixels = nullptr;
         unsigned char* accept = nullptr;
@@ -176,7 +179,7 @@ static void free_ctx(bmfr_ctx* c) {
         for (cudaStream_t st : {o.s_r, o.s_f, o.s_p})
             if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
         for (int i = 0; i < 2; ++i)
-            for (cudaEvent_t e : {o.e_in[i], o.e_r[i], o.e_f[i], o.e_p[i]})
+            for (cudaEvent_t e : {o.e_in[i], o.e_r[i], o.e_f[i], o.e_p[i], o.e_e[i]})
                 if (e) cudaEventDestroy(e);
         cudaFree(o.prev_pixels); cudaFree(o.accept); cudaFree(o.weights); cudaFree(o.mins_maxs); cudaFree(o.mins_inv);
         cudaFree(o.noise); cudaFree(o.noise_f); cudaFree(o.counter);
@@ -330,7 +333,7 @@ int bmfr_create(const bmfr_params* params, bmfr_ctx** out_ctx) {
     if (st == 0) st = dev_alloc(&c->noise_f, (size_t)(BMFR_FEATURES - 1) * BMFR_BLOCK_PIXELS, "noise_f");
     if (st == 0) st = dev_alloc(&c->d_oob, 2, "oob flag + block counter");
     if (st == 0 && p.mode == BMFR_MODE_FUSED) st = dev_alloc(&c->tri, nb * 4 * 136, "level-1 triangles");
-    if (st == 0) st = dev_alloc(&c->d_flags, 4, "halo flags");
+    if (st == 0) st = dev_alloc(&c->d_flags, 8, "halo flags");
     if (st == 0 && p.mode == BMFR_MODE_STAGED) {
         st = dev_alloc(&c->tmp_data, (size_t)c->tmp_block_rows * g.blocks_x * BMFR_BUFFER_COUNT * BMFR_BLOCK_PIXELS, "tmp_data");
         if (st == 0) st = dev_alloc(&c->filtered, npix * 3, "filtered");
@@ -338,14 +341,13 @@ int bmfr_create(const bmfr_params* params, bmfr_ctx** out_ctx) {
     }
     if (st != 0) return fail(st);
     if ((st = bmfr_check_cuda(cudaMemsetAsync(c->d_oob, 0, 2 * sizeof(int), c->stream), "memset")) != 0) return fail(st);
-    if ((st = bmfr_check_cuda(cudaMemsetAsync(c->d_flags, 0, 4 * sizeof(unsigned int), c->stream), "memset")) != 0) return fail(st);
+    if ((st = bmfr_check_cuda(cudaMemsetAsync(c->d_flags, 0, 8 * sizeof(unsigned int), c->stream), "memset")) != 0) return fail(st);
     // weights of blocks a strip never fits stay defined
     if ((st = bmfr_check_cuda(cudaMemsetAsync(c->weights, 0, nb * BMFR_FEATURES * 3 * sizeof(float), c->stream), "memset")) != 0) return fail(st);
     if ((st = bmfr_check_cuda(cudaMemsetAsync(c->mins_maxs, 0, nb * BMFR_FEATURES_SCALED * 2 * sizeof(float), c->stream), "memset")) != 0) return fail(st);
     if ((st = bmfr_check_cuda(cudaMemsetAsync(c->mins_inv, 0, nb * BMFR_FEATURES_SCALED * 2 * sizeof(float), c->stream), "memset")) != 0) return fail(st);
     if (p.profile) c->prof.resize(kProfileSlots);
-    if (p.overlap_frames && p.mode == BMFR_MODE_FUSED && !p.profile && g.own_y0 == 0 && g.own_y1 == g.height && g.row0 == 0 &&
-        g.row1 == g.height) {
+    if (p.overlap_frames && p.mode == BMFR_MODE_FUSED && !p.profile) {
         bmfr_ctx::Overlap& o = c->ov;
         if (st == 0) st = dev_alloc(&o.prev_pixels, npix, "prev_pixels (odd frames)");
         if (st == 0) st = dev_alloc(&o.accept, npix, "accept (odd frames)");
@@ -358,7 +360,7 @@ int bmfr_create(const bmfr_params* params, bmfr_ctx** out_ctx) {
         for (cudaStream_t* ps : {&o.s_r, &o.s_f, &o.s_p})
             if (st == 0) st = bmfr_check_cuda(cudaStreamCreateWithFlags(ps, cudaStreamNonBlocking), "cudaStreamCreate");
         for (int i = 0; i < 2; ++i)
-            for (cudaEvent_t* pe : {&o.e_in[i], &o.e_r[i], &o.e_f[i], &o.e_p[i]})
+            for (cudaEvent_t* pe : {&o.e_in[i], &o.e_r[i], &o.e_f[i], &o.e_p[i], &o.e_e[i]})
                 if (st == 0) st = bmfr_check_cuda(cudaEventCreateWithFlags(pe, cudaEventDisableTiming), "cudaEventCreate");
         if (st != 0) return fail(st);
         o.on = true;
@@ -464,6 +466,11 @@ static StageEvents* prof_slot(bmfr_ctx* c, int frame) {
     } while (0)
 
 static int halo_push_early(bmfr_ctx* c);
+static bool halo_active(const bmfr_ctx* c);
+static int halo_ensure_stream(bmfr_ctx* c);
+static int halo_push_part(bmfr_ctx* c, bool late, cudaStream_t st);
+static int halo_wait_split(bmfr_ctx* c, cudaStream_t st, unsigned int early_value, unsigned int late_value);
+static int halo_signal_split(bmfr_ctx* c, cudaStream_t st, bool late);
 
 static int run_frame(bmfr_ctx* c, const KParams& P, int frame) {
     StageEvents* pe = prof_slot(c, frame);
@@ -490,18 +497,50 @@ static int run_frame(bmfr_ctx* c, const KParams& P, int frame) {
         // noise tile, block counter, weights, min/max) were last read by frame f-2.  R(f-1) precedes R(f) on
         // the same stream (temporal state), as F(f-1) precedes F(f) (triangle scratch) and P(f-1) P(f)
         // (accumulated filtered colour, TAA history).
+        //
+        // Strips (connected neighbours) add the halo exchange, with the in-order protocol's single "frame done"
+        // flag split in two so that it does not serialise the frames again:
+        //   early (after R(f)) : push accumulated noisy colour + spp rows, raise the neighbours' early flag to f+1
+        //   late  (after P(f)) : push accumulated filtered colour + TAA rows, raise their late flag to f+1
+        //   R(f) waits for early >= f (the rows it gathers from; also: the neighbours' R(f-1) no longer reads the
+        //        halo rows this context's early push of frame f overwrites) and late >= f-1 (their F/P(f-2), which
+        //        read the same physical buffers as "current", are done);
+        //   P(f) waits for late >= f (the history rows it gathers from; also: their P(f-1) no longer reads what
+        //        this context's late push of frame f overwrites).
+        // Every wait refers to frames submitted earlier on both sides, so the order of submission is a schedule
+        // that never blocks.
         bmfr_ctx::Overlap& o = c->ov;
         const int q = c->parity();
+        const bool halo = halo_active(c);
+        const unsigned int f = (unsigned int)c->seq;
+        if (halo) { int hs = halo_ensure_stream(c); if (hs != 0) return hs; }
         BMFR_CUDA_TRY(cudaEventRecord(o.e_in[q], c->stream));
         BMFR_CUDA_TRY(cudaStreamWaitEvent(o.s_r, o.e_in[q], 0));
-        if (c->seq >= 2) BMFR_CUDA_TRY(cudaStreamWaitEvent(o.s_r, o.e_p[q], 0));
+        if (c->seq >= 2) {
+            BMFR_CUDA_TRY(cudaStreamWaitEvent(o.s_r, o.e_p[q], 0));
+            if (halo) BMFR_CUDA_TRY(cudaStreamWaitEvent(o.s_r, o.e_e[q], 0));  // the early push of frame f-2 has read its rows
+        }
+        if (halo && f >= 1) { int hs = halo_wait_split(c, o.s_r, f, f - 1); if (hs != 0) return hs; }
         LAUNCH_TRY(launch_reproject(P, o.s_r), "reproject_kernel");
         BMFR_CUDA_TRY(cudaEventRecord(o.e_r[q], o.s_r));
+        if (halo) {
+            BMFR_CUDA_TRY(cudaStreamWaitEvent(c->halo_stream, o.e_r[q], 0));
+            int hs = halo_push_part(c, false, c->halo_stream);
+            if (hs == 0) hs = halo_signal_split(c, c->halo_stream, false);
+            if (hs != 0) return hs;
+            BMFR_CUDA_TRY(cudaEventRecord(o.e_e[q], c->halo_stream));
+        }
         BMFR_CUDA_TRY(cudaStreamWaitEvent(o.s_f, o.e_r[q], 0));
         LAUNCH_TRY(launch_fit_qr(P, o.s_f), "fit_qr_kernel");
         BMFR_CUDA_TRY(cudaEventRecord(o.e_f[q], o.s_f));
         BMFR_CUDA_TRY(cudaStreamWaitEvent(o.s_p, o.e_f[q], 0));
+        if (halo && f >= 1) { int hs = halo_wait_split(c, o.s_p, 0, f); if (hs != 0) return hs; }
         LAUNCH_TRY(launch_post(P, o.s_p), "post_kernel");
+        if (halo) {
+            int hs = halo_push_part(c, true, o.s_p);
+            if (hs == 0) hs = halo_signal_split(c, o.s_p, true);
+            if (hs != 0) return hs;
+        }
         BMFR_CUDA_TRY(cudaEventRecord(o.e_p[q], o.s_p));
     } else {
         LAUNCH_TRY(launch_reproject(P, c->stream), "reproject_kernel");
@@ -576,11 +615,38 @@ __global__ void halo_wait_kernel(unsigned int* flags, int need_a, int need_b, un
 }
 
 static int halo_wait(bmfr_ctx* c) {
-    if (!(c->peer[0].connected || c->peer[1].connected) || c->seq == 0) return BMFR_OK;
+    if (!(c->peer[0].connected || c->peer[1].connected) || c->seq == 0 || c->ov.on) return BMFR_OK;
     halo_wait_kernel<<<1, 1, 0, c->stream>>>(c->d_flags, c->peer[0].connected, c->peer[1].connected, (unsigned int)c->seq);
     int st = bmfr_check_cuda(cudaGetLastError(), "halo_wait_kernel");
     if (st == 0) ++c->launches;
     return st;
+}
+
+// Overlapped frames: wait for the early flags (index 0, 1) to reach early_value and the late flags (4, 5) to reach
+// late_value; 0 = do not wait for that kind.
+__global__ void halo_wait_split_kernel(unsigned int* flags, int need_a, int need_b, unsigned int early_value, unsigned int late_value) {
+    const long long t0 = clock64();
+    const long long limit = 4000000000ll;  // ~2 s at 2 GHz
+    for (;;) {
+        volatile unsigned int* f = flags;
+        const bool a = !need_a || (f[0] >= early_value && f[4] >= late_value);
+        const bool b = !need_b || (f[1] >= early_value && f[5] >= late_value);
+        if (a && b) break;
+        if (clock64() - t0 > limit) {
+            flags[2] = 1;
+            break;
+        }
+        __nanosleep(200);
+    }
+    __threadfence_system();
+}
+
+static int halo_wait_split(bmfr_ctx* c, cudaStream_t st, unsigned int early_value, unsigned int late_value) {
+    if (early_value == 0 && late_value == 0) return BMFR_OK;
+    halo_wait_split_kernel<<<1, 1, 0, st>>>(c->d_flags, c->peer[0].connected, c->peer[1].connected, early_value, late_value);
+    int rc = bmfr_check_cuda(cudaGetLastError(), "halo_wait_split_kernel");
+    if (rc == 0) ++c->launches;
+    return rc;
 }
 
 // Rows of a neighbour's halo this context must refresh, per state buffer.  The accumulated noisy colour and
@@ -631,14 +697,31 @@ static int halo_push_part(bmfr_ctx* c, bool late, cudaStream_t st) {
 
 static bool halo_active(const bmfr_ctx* c) { return c->peer[0].connected || c->peer[1].connected; }
 
-// after the kernel that produced the accumulated noisy colour and spp: push them on the side stream
-static int halo_push_early(bmfr_ctx* c) {
-    if (!halo_active(c)) return BMFR_OK;
+static int halo_ensure_stream(bmfr_ctx* c) {
     if (!c->halo_stream) {
         BMFR_CUDA_TRY(cudaStreamCreateWithFlags(&c->halo_stream, cudaStreamNonBlocking));
         BMFR_CUDA_TRY(cudaEventCreateWithFlags(&c->halo_ready, cudaEventDisableTiming));
         BMFR_CUDA_TRY(cudaEventCreateWithFlags(&c->halo_pushed, cudaEventDisableTiming));
     }
+    return BMFR_OK;
+}
+
+// Overlapped frames: raise the neighbours' early (late = false) or late flag to "frames completed" = seq + 1.
+static int halo_signal_split(bmfr_ctx* c, cudaStream_t st, bool late) {
+    const int k = late ? 4 : 0;
+    // the neighbour above sees this context as its "below" neighbour (flag 1) and vice versa
+    unsigned int* fa = c->peer[0].connected ? c->peer[0].flags + k + 1 : nullptr;
+    unsigned int* fb = c->peer[1].connected ? c->peer[1].flags + k + 0 : nullptr;
+    halo_signal_kernel<<<1, 1, 0, st>>>(fa, fb, (unsigned int)(c->seq + 1));
+    int rc = bmfr_check_cuda(cudaGetLastError(), "halo_signal_kernel");
+    if (rc == 0) ++c->launches;
+    return rc;
+}
+
+// after the kernel that produced the accumulated noisy colour and spp: push them on the side stream
+static int halo_push_early(bmfr_ctx* c) {
+    if (!halo_active(c) || c->ov.on) return BMFR_OK;
+    { int hs = halo_ensure_stream(c); if (hs != 0) return hs; }
     BMFR_CUDA_TRY(cudaEventRecord(c->halo_ready, c->stream));
     BMFR_CUDA_TRY(cudaStreamWaitEvent(c->halo_stream, c->halo_ready, 0));
     int st = halo_push_part(c, false, c->halo_stream);
@@ -649,7 +732,7 @@ static int halo_push_early(bmfr_ctx* c) {
 
 // after the last kernel: push the rest, then raise the neighbours' flags
 static int halo_push_late(bmfr_ctx* c) {
-    if (!halo_active(c)) return BMFR_OK;
+    if (!halo_active(c) || c->ov.on) return BMFR_OK;  // (overlapped frames: run_frame does the exchange)
     int st = halo_push_part(c, true, c->stream);
     if (st != 0) return st;
     BMFR_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->halo_pushed, 0));
@@ -665,6 +748,7 @@ static int halo_push_late(bmfr_ctx* c) {
 struct HaloBlob {  // what a neighbour needs to address this context's state: geometry + IPC handles
     unsigned int magic;
     int device, width, height, row0, row1, own_y0, own_y1, swapped;
+    int overlap;  // the two sides must speak the same flag protocol (in-order: one flag per frame; overlapped: two)
     long long seq;
     cudaIpcMemHandle_t noisy_acc[2], spp[2], accum[2], result[2], flags;
 };
@@ -767,6 +851,7 @@ int bmfr_join(bmfr_ctx* c) {
     BMFR_CUDA_TRY(cudaSetDevice(c->prm.device));
     // P(f) is the last kernel of frame f, and the post passes run in order on one stream
     BMFR_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ov.e_p[c->last_parity()], 0));
+    if (halo_active(c)) BMFR_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ov.e_e[c->last_parity()], 0));
     return BMFR_OK;
 }
 
@@ -775,7 +860,7 @@ int bmfr_sync(bmfr_ctx* c) {
     BMFR_CUDA_TRY(cudaSetDevice(c->prm.device));
     if (c->h2d_stream) BMFR_CUDA_TRY(cudaStreamSynchronize(c->h2d_stream));
     BMFR_CUDA_TRY(cudaStreamSynchronize(c->stream));
-    for (cudaStream_t st : {c->ov.s_r, c->ov.s_f, c->ov.s_p})
+    for (cudaStream_t st : {c->ov.s_r, c->ov.s_f, c->ov.s_p, c->ov.on ? c->halo_stream : (cudaStream_t) nullptr})
         if (st) BMFR_CUDA_TRY(cudaStreamSynchronize(st));
     if (c->d2h_stream) BMFR_CUDA_TRY(cudaStreamSynchronize(c->d2h_stream));
     unsigned int timed_out = 0;
@@ -894,7 +979,7 @@ int bmfr_halo_export(bmfr_ctx* c, void* blob, size_t blob_bytes) {
     memset(&b, 0, sizeof(b));
     b.magic = kHaloMagic; b.device = c->prm.device; b.width = c->geo.width; b.height = c->geo.height;
     b.row0 = c->geo.row0; b.row1 = c->geo.row1; b.own_y0 = c->geo.own_y0; b.own_y1 = c->geo.own_y1;
-    b.swapped = c->noisy_acc.swapped ? 1 : 0; b.seq = c->seq;
+    b.swapped = c->noisy_acc.swapped ? 1 : 0; b.seq = c->seq; b.overlap = c->ov.on ? 1 : 0;
     for (int i = 0; i < 2; ++i) {
         BMFR_CUDA_TRY(cudaIpcGetMemHandle(&b.noisy_acc[i], c->noisy_acc.buf[i]));
         BMFR_CUDA_TRY(cudaIpcGetMemHandle(&b.spp[i], c->spp.buf[i]));
@@ -913,6 +998,9 @@ int bmfr_halo_connect(bmfr_ctx* c, int side, const void* neighbour_blob, size_t 
     if (b.magic != kHaloMagic) return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_halo_connect: not a bmfr_halo_export blob");
     int st = halo_check_neighbour(c, side, b.width, b.height, b.own_y0, b.own_y1, b.row0, b.row1, b.swapped, b.seq);
     if (st != 0) return st;
+    if ((b.overlap != 0) != c->ov.on)
+        return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_halo_connect: the neighbour was created with overlap_frames = %d, this "
+                                                         "context with %d", b.overlap, c->ov.on ? 1 : 0);
     BMFR_CUDA_TRY(cudaSetDevice(c->prm.device));
     bmfr_ctx::Peer& pr = c->peer[side];
     const unsigned int fl = cudaIpcMemLazyEnablePeerAccess;
@@ -934,6 +1022,8 @@ int bmfr_halo_connect_local(bmfr_ctx* c, int side, bmfr_ctx* n) {
     int st = halo_check_neighbour(c, side, n->geo.width, n->geo.height, n->geo.own_y0, n->geo.own_y1, n->geo.row0, n->geo.row1,
                                   n->noisy_acc.swapped ? 1 : 0, n->seq);
     if (st != 0) return st;
+    if (n->ov.on != c->ov.on)
+        return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_halo_connect_local: the two contexts differ in overlap_frames");
     if (n->prm.device != c->prm.device) {
         BMFR_CUDA_TRY(cudaSetDevice(c->prm.device));
         int can = 0;

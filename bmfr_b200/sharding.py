@@ -191,8 +191,11 @@ def bench_sharded(args, workload, frames):
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     sp = stream.cuda_stream
-    ctx = StripContext(w, h, strips[rank], halo, local, sp, args.mode)
     exchange = getattr(args, "exchange", "p2p")
+    # overlapped frames need the library's own halo exchange (the split-flag protocol); the host-driven NCCL
+    # exchange works on the context's stream between frames and keeps the in-order mode
+    overlap = int(bool(getattr(args, "overlap", 1)) and exchange == "p2p" and args.mode == "fused")
+    ctx = StripContext(w, h, strips[rank], halo, local, sp, args.mode, overlap_frames=overlap)
     if exchange == "p2p":  # one-time exchange of IPC handles; afterwards no host-side communication per frame
         blobs = [None] * world
         dist.all_gather_object(blobs, ctx.d.halo_export())
@@ -227,6 +230,7 @@ def bench_sharded(args, workload, frames):
     e0.record(stream)
     for _ in range(args.steps):
         run_sequence()
+    ctx.d.join()  # overlapped frames: order the closing event after the frames on the internal streams
     e1.record(stream)
     torch.cuda.synchronize()
     dist.barrier()
@@ -283,7 +287,7 @@ def bench_sharded(args, workload, frames):
             "config": {"workload": f"{w}x{h} x{frames} frames synth-v1 strip-sharded over {world} GPUs along block rows",
                        "value_unit": "1080p-equivalent frames/s = native frames/s x (W*H)/(1920*1080); every rank owns "
                                      "a 3840x540 strip in the default (weak-scaling) series",
-                       "mode": args.mode, "strips": strips, "halo_rows": halo,
+                       "mode": args.mode, "overlap_frames": overlap, "strips": strips, "halo_rows": halo,
                        "parallelism": f"strips{world}",
                        "exchange": ("peer-to-peer pushes of state halo rows over NVLink from the library (CUDA IPC), device-side flags"
                                     if exchange == "p2p" else "NCCL send/recv of state halo rows, neighbours only"),
