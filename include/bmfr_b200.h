@@ -80,14 +80,17 @@ typedef struct bmfr_params {
      * scale()), which makes EVERY buffer of the loop bit-identical to the reference kernels' arithmetic
      * — the compatibility mode; slower than the default fitter. */
     int reference_order;
-    /* FUSED, whole-frame contexts without profiling only (ignored otherwise).  1: consecutive frames may
-     * overlap on the device.  The reprojection of frame f+1 does not depend on the fit and the post pass of
+    /* FUSED contexts without profiling only (ignored otherwise).  1: consecutive frames may overlap on the
+     * device.  The reprojection of frame f+1 does not depend on the fit and the post pass of
      * frame f, so the three kernels are enqueued on three internal streams linked by events (per-frame
      * temporaries double-buffered) and the tail of one kernel is filled by the next frame's work.  The
      * context's stream is then ordered BEFORE a frame's kernels (the caller's producers of the inputs) but
      * not after them: the output (d_out, bmfr_get_buffer) is valid, and the input buffers of the last two
      * frames may be overwritten, only after bmfr_sync() or, on the stream, after bmfr_join().  bmfr_denoise_frame_host handles that ordering
-     * itself.  0 (default): one in-order stream, the reference's queue semantics (bmfr.cpp:191). */
+     * itself.  Strip contexts: the library's own halo exchange (bmfr_halo_connect*) switches to a two-flag
+     * protocol, so all connected contexts must agree on this field, and a caller-driven exchange of the
+     * state rows (which needs the in-order stream) cannot be combined with it.
+     * 0 (default): one in-order stream, the reference's queue semantics (bmfr.cpp:191). */
     int overlap_frames;
 } bmfr_params;
 
