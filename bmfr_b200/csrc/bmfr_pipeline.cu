@@ -121,7 +121,7 @@ struct bmfr_ctx {
     unsigned int* d_flags = nullptr;
     long long seq = 0;                 // frames submitted on this context
 
-    // Overlapped frames (params.overlap_frames, FUSED whole-frame contexts): reprojection, fit and post pass
+    // Overlapped frames (params.overlap_frames, FUSED contexts, strips included): reprojection, fit and post pass
     // each have their own stream; events order them within a frame (R -> F -> P) and across frames (R(f)
     // after P(f-2): everything a frame hands from one kernel to the next exists twice, indexed by frame
     // parity, so frame f+1 can start while frame f is still in its fit / post pass).

@@ -71,6 +71,10 @@ def test_invalid_arguments(lib):
     p.tmp_half = 1
     assert lib.bmfr_create(C.byref(p), C.byref(h)) in (-5, -2)
     assert lib.bmfr_sync(None) == -1
+    assert lib.bmfr_join(None) == -1
+    # the defaults keep the reference's in-order queue semantics
+    lib.bmfr_default_params(C.byref(p), 64, 64)
+    assert p.overlap_frames == 0 and p.reference_order == 0 and p.tmp_half == 0
 
 
 def test_unmirrorable_geometry_is_refused(lib):
