@@ -48,7 +48,7 @@ bool read_file(const char* path, std::vector<unsigned char>& out) {
 
 // ---- OpenEXR ---------------------------------------------------------------------------------
 enum { PIXEL_UINT = 0, PIXEL_HALF = 1, PIXEL_FLOAT = 2 };
-enum { COMP_NONE = 0, COMP_RLE = 1, COMP_ZIPS = 2, COMP_ZIP = 3 };
+enum { COMP_NONE = 0, COMP_RLE = 1, COMP_ZIPS = 2, COMP_ZIP = 3, COMP_PIZ = 4 };
 
 struct Channel {
     std::string name;
@@ -194,6 +194,224 @@ bool rle_decode(const unsigned char* src, size_t n, std::vector<unsigned char>& 
     return out.size() == expect;
 }
 
+// ---- PIZ: 16-bit value range compaction (bitmap + LUT), 2-D Haar-like wavelet, Huffman ----------
+// Decoder for OpenEXR's PIZ chunks, written from the format: the chunk holds the range of used 16-bit
+// values as a bitmap, then a canonical-Huffman stream (6-bit packed code lengths with zero runs, one
+// run-length symbol) of the wavelet-transformed, channel-planar 16-bit planes (a FLOAT channel = two
+// interleaved planes).
+struct BitReader {
+    const unsigned char* p;
+    const unsigned char* end;
+    uint64_t c = 0;
+    int lc = 0;
+    bool ok = true;
+    uint32_t get(int n) {  // MSB first
+        while (lc < n) {
+            if (p >= end) {
+                ok = false;
+                return 0;
+            }
+            c = (c << 8) | *p++;
+            lc += 8;
+        }
+        lc -= n;
+        return (uint32_t)((c >> lc) & ((1ull << n) - 1));
+    }
+};
+
+constexpr int kHufEncSize = (1 << 16) + 1;  // symbols 0..65535 and the run-length symbol
+
+bool huf_uncompress(const unsigned char* in, size_t n_in, uint16_t* out, size_t n_out) {
+    if (n_in < 20) return n_out == 0;
+    auto u32 = [&](size_t at) { return (uint32_t)in[at] | ((uint32_t)in[at + 1] << 8) | ((uint32_t)in[at + 2] << 16) | ((uint32_t)in[at + 3] << 24); };
+    const uint32_t im = u32(0), iM = u32(4), n_bits = u32(12);
+    if (im >= (uint32_t)kHufEncSize || iM >= (uint32_t)kHufEncSize || im > iM) return false;
+    // code lengths im..iM: 6 bits each; 59..62 = run of 2..5 zeros, 63 = run of 6 + next 8 bits zeros
+    std::vector<unsigned char> len((size_t)kHufEncSize, 0);
+    BitReader br{in + 20, in + n_in};
+    for (uint32_t i = im; i <= iM; ++i) {
+        const uint32_t l = br.get(6);
+        if (!br.ok) return false;
+        if (l == 63) {
+            uint32_t run = br.get(8) + 6;
+            if (!br.ok || i + run > iM + 1) return false;
+            i += run - 1;
+        } else if (l >= 59) {
+            const uint32_t run = l - 59 + 2;
+            if (i + run > iM + 1) return false;
+            i += run - 1;
+        } else {
+            len[i] = (unsigned char)l;
+        }
+    }
+    // canonical codes: within a length codes grow with the symbol, longer lengths take the numerically
+    // smaller prefixes (first[l] = (first[l+1] + count[l+1]) >> 1)
+    uint64_t count[59] = {0}, first[60] = {0};
+    for (uint32_t i = im; i <= iM; ++i) count[len[i]]++;
+    {
+        uint64_t c = 0;
+        for (int l = 58; l >= 1; --l) {
+            const uint64_t nc = (c + count[l]) >> 1;
+            first[l] = c;
+            c = nc;
+        }
+    }
+    size_t offset[60] = {0};
+    for (int l = 1; l < 59; ++l) offset[l + 1] = offset[l] + (size_t)count[l];
+    std::vector<uint32_t> syms(offset[59]);
+    {
+        size_t fill[60];
+        memcpy(fill, offset, sizeof(fill));
+        for (uint32_t i = im; i <= iM; ++i)
+            if (len[i]) syms[fill[len[i]]++] = i;
+    }
+    // the data starts at the next byte boundary after the table
+    const unsigned char* data = br.p;  // bytes consumed so far (partial byte bits are discarded)
+    BitReader dr{data, in + n_in};
+    uint64_t left = n_bits;
+    size_t o = 0;
+    while (left > 0) {
+        uint64_t code = 0;
+        int l = 0;
+        uint32_t sym = 0;
+        for (;;) {
+            if (left == 0 || l >= 58) return false;
+            code = (code << 1) | dr.get(1);
+            if (!dr.ok) return false;
+            --left;
+            ++l;
+            if (count[l] && code >= first[l] && code - first[l] < count[l]) {
+                sym = syms[offset[l] + (size_t)(code - first[l])];
+                break;
+            }
+        }
+        if (sym == iM) {  // run-length symbol: repeat the previous value
+            if (left < 8 || o == 0) return false;
+            const uint32_t run = dr.get(8);
+            if (!dr.ok) return false;
+            left -= 8;
+            if (o + run > n_out) return false;
+            for (uint32_t r = 0; r < run; ++r, ++o) out[o] = out[o - 1];
+        } else {
+            if (o >= n_out) return false;
+            out[o++] = (uint16_t)sym;
+        }
+    }
+    return o == n_out;
+}
+
+inline void wdec14(uint16_t l, uint16_t h, uint16_t& a, uint16_t& b) {
+    const int ls = (int16_t)l, hs = (int16_t)h;
+    const int ai = ls + (hs & 1) + (hs >> 1);
+    a = (uint16_t)(int16_t)ai;
+    b = (uint16_t)(int16_t)(ai - hs);
+}
+inline void wdec16(uint16_t l, uint16_t h, uint16_t& a, uint16_t& b) {
+    const int m = l, d = h;
+    const int bb = (m - (d >> 1)) & 0xffff;
+    const int aa = (d + bb - (1 << 15)) & 0xffff;
+    b = (uint16_t)bb;
+    a = (uint16_t)aa;
+}
+// in: nx x ny values with strides ox, oy (in uint16 units); mx = largest value after the LUT
+void wav2_decode(uint16_t* in, int nx, int ox, int ny, int oy, uint16_t mx) {
+    const bool w14 = mx < (1 << 14);
+    const int n = nx > ny ? ny : nx;
+    int p = 1, p2;
+    while (p <= n) p <<= 1;
+    p >>= 1;
+    p2 = p;
+    p >>= 1;
+    auto dec = [&](uint16_t l, uint16_t h, uint16_t& a, uint16_t& b) {
+        if (w14) wdec14(l, h, a, b);
+        else wdec16(l, h, a, b);
+    };
+    while (p >= 1) {
+        uint16_t* py = in;
+        uint16_t* ey = in + (ptrdiff_t)oy * (ny - p2);
+        const ptrdiff_t oy1 = (ptrdiff_t)oy * p, oy2 = (ptrdiff_t)oy * p2, ox1 = (ptrdiff_t)ox * p, ox2 = (ptrdiff_t)ox * p2;
+        uint16_t i00, i01, i10, i11;
+        for (; py <= ey; py += oy2) {
+            uint16_t* px = py;
+            uint16_t* ex = py + (ptrdiff_t)ox * (nx - p2);
+            for (; px <= ex; px += ox2) {
+                uint16_t* p01 = px + ox1;
+                uint16_t* p10 = px + oy1;
+                uint16_t* p11 = p10 + ox1;
+                dec(*px, *p10, i00, i10);
+                dec(*p01, *p11, i01, i11);
+                dec(i00, i01, *px, *p01);
+                dec(i10, i11, *p10, *p11);
+            }
+            if (nx & p) {
+                uint16_t* p10 = px + oy1;
+                dec(*px, *p10, i00, *p10);
+                *px = i00;
+            }
+        }
+        if (ny & p) {
+            uint16_t* px = py;
+            uint16_t* ex = py + (ptrdiff_t)ox * (nx - p2);
+            for (; px <= ex; px += ox2) {
+                uint16_t* p01 = px + ox1;
+                dec(*px, *p01, i00, *p01);
+                *px = i00;
+            }
+        }
+        p2 = p;
+        p >>= 1;
+    }
+}
+
+// One PIZ chunk -> `lines` scanlines in the raw layout (per scanline: channel after channel).
+bool piz_decode(const unsigned char* src, size_t n, const std::vector<Channel>& ch, int width, int lines, std::vector<unsigned char>& raw) {
+    if (n < 4) return false;
+    const uint32_t min_nz = src[0] | (src[1] << 8), max_nz = src[2] | (src[3] << 8);
+    size_t at = 4;
+    std::vector<unsigned char> bitmap(8192, 0);
+    if (max_nz >= 8192) return false;
+    if (min_nz <= max_nz) {
+        const size_t nb = max_nz - min_nz + 1;
+        if (at + nb > n) return false;
+        memcpy(bitmap.data() + min_nz, src + at, nb);
+        at += nb;
+    }
+    std::vector<uint16_t> lut(65536, 0);
+    uint32_t k = 0;
+    for (uint32_t i = 0; i < 65536; ++i)
+        if (i == 0 || (bitmap[i >> 3] & (1 << (i & 7)))) lut[k++] = (uint16_t)i;
+    const uint16_t max_value = (uint16_t)(k - 1);
+    if (at + 4 > n) return false;
+    const uint32_t hlen = (uint32_t)src[at] | ((uint32_t)src[at + 1] << 8) | ((uint32_t)src[at + 2] << 16) | ((uint32_t)src[at + 3] << 24);
+    at += 4;
+    if (hlen > n - at) return false;
+    size_t total = 0;  // uint16 values of the chunk
+    for (const Channel& c : ch) total += (size_t)width * lines * (c.type == PIXEL_HALF ? 1 : 2);
+    std::vector<uint16_t> planar(total);
+    if (!huf_uncompress(src + at, hlen, planar.data(), total)) return false;
+    size_t start = 0;
+    std::vector<size_t> starts;
+    for (const Channel& c : ch) {
+        const int size = c.type == PIXEL_HALF ? 1 : 2;
+        starts.push_back(start);
+        for (int j = 0; j < size; ++j) wav2_decode(planar.data() + start + j, width, size, lines, width * size, max_value);
+        start += (size_t)width * lines * size;
+    }
+    for (uint16_t& v : planar) v = lut[v];
+    raw.resize(total * 2);
+    unsigned char* out = raw.data();
+    for (int y = 0; y < lines; ++y)
+        for (size_t i = 0; i < ch.size(); ++i) {
+            const size_t nvals = (size_t)width * (ch[i].type == PIXEL_HALF ? 1 : 2);
+            const uint16_t* row = planar.data() + starts[i] + (size_t)y * nvals;
+            for (size_t v = 0; v < nvals; ++v) {  // little-endian, whatever the host is
+                *out++ = (unsigned char)(row[v] & 0xff);
+                *out++ = (unsigned char)(row[v] >> 8);
+            }
+        }
+    return true;
+}
+
 // Which file channel feeds output component 0, 1, 2.
 bool pick_rgb(const std::vector<Channel>& ch, int order[3]) {
     auto base = [](const std::string& s) {
@@ -314,8 +532,8 @@ int bmfr_io_read_exr_rgb(const char* path, int width, int height, float* rgb) {
     if (h.width() != width || h.height() != height || h.channels.size() != 3)  // bmfr.cpp:150-155
         return fail(BMFR_IO_ERR_MISMATCH, "%s: %d x %d with %d channels, expected %d x %d with 3 (wrong type)", path, (int)h.width(),
                     (int)h.height(), (int)h.channels.size(), width, height);
-    if (h.compression > COMP_ZIP)
-        return fail(BMFR_IO_ERR_UNSUPPORTED, "%s: compression %d is not covered (NONE, RLE, ZIPS, ZIP are)", path, h.compression);
+    if (h.compression > COMP_PIZ)
+        return fail(BMFR_IO_ERR_UNSUPPORTED, "%s: compression %d is not covered (NONE, RLE, ZIPS, ZIP, PIZ are)", path, h.compression);
     size_t line_bytes = 0;
     std::vector<size_t> ch_offset(h.channels.size());
     for (size_t i = 0; i < h.channels.size(); ++i) {
@@ -329,7 +547,7 @@ int bmfr_io_read_exr_rgb(const char* path, int width, int height, float* rgb) {
     int order[3];
     pick_rgb(h.channels, order);
 
-    const int lines_per_chunk = h.compression == COMP_ZIP ? 16 : 1;
+    const int lines_per_chunk = h.compression == COMP_ZIP ? 16 : h.compression == COMP_PIZ ? 32 : 1;
     const int chunks = (height + lines_per_chunk - 1) / lines_per_chunk;
     if (h.table + (size_t)chunks * 8 > file.size()) return fail(BMFR_IO_ERR_FORMAT, "%s: truncated offset table", path);
     std::vector<unsigned char> raw, tmp;
@@ -354,6 +572,9 @@ int bmfr_io_read_exr_rgb(const char* path, int width, int height, float* rgb) {
             raw.assign(src, src + expect);
         } else if (h.compression == COMP_NONE) {
             return fail(BMFR_IO_ERR_FORMAT, "%s: chunk %d has %d bytes, expected %zu", path, k, size, expect);
+        } else if (h.compression == COMP_PIZ) {
+            if (!piz_decode(src, (size_t)size, h.channels, width, lines, raw) || raw.size() != expect)
+                return fail(BMFR_IO_ERR_FORMAT, "%s: corrupt PIZ chunk %d", path, k);
         } else {
             if (h.compression == COMP_RLE) {
                 if (!rle_decode(src, (size_t)size, raw, expect)) return fail(BMFR_IO_ERR_FORMAT, "%s: corrupt RLE chunk %d", path, k);

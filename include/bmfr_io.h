@@ -19,7 +19,7 @@ enum {
     BMFR_IO_ERR_ARGUMENT = -1,
     BMFR_IO_ERR_OPEN = -2,        /* file missing / unreadable / not writable */
     BMFR_IO_ERR_FORMAT = -3,      /* not an OpenEXR scanline file, truncated, corrupt chunk */
-    BMFR_IO_ERR_UNSUPPORTED = -4, /* valid file this reader does not cover (tiled, deep, multi-part, PIZ/B44/DWA ...) */
+    BMFR_IO_ERR_UNSUPPORTED = -4, /* valid file this reader does not cover (tiled, deep, multi-part, PXR24/B44/DWA ...) */
     BMFR_IO_ERR_MISMATCH = -5     /* size or channel count differs from what the caller asked for */
 };
 
@@ -32,7 +32,8 @@ int bmfr_io_exr_info(const char* path, int* width, int* height, int* channels);
  * are widened to fp32 (bmfr.cpp:159-161).  rgb receives width*height*3 tightly packed interleaved floats,
  * top row first.  Channels are delivered in R,G,B order when they are named so (as OpenImageIO does), X,Y,Z
  * likewise, otherwise in the file's (alphabetical) order.
- * Covered: single-part scanline files, compression NONE / RLE / ZIPS / ZIP, HALF and FLOAT channels. */
+ * Covered: single-part scanline files, compression NONE / RLE / ZIPS / ZIP / PIZ (the lossless ones), HALF and
+ * FLOAT channels. */
 int bmfr_io_read_exr_rgb(const char* path, int width, int height, float* rgb);
 
 /* The dataset's camera_matrices.h (bmfr.cpp:46-47), parsed instead of compiled in: the initialisers of

@@ -83,9 +83,13 @@ def write_exr(path, planes, types, compression, xmin=0, ymin=0, decreasing=False
 
 # ---- the image of tests/golden/exr/*.exr (written by tests/golden/make_exr_fixtures.py with the OpenEXR library) ----
 FIXTURE_W, FIXTURE_H, FIXTURE_SEED = 24, 19, 20261018
+FIXTURE_TALL_W, FIXTURE_TALL_H = 21, 70
 
 
-def fixture_image():
-    img = np.random.default_rng(FIXTURE_SEED).normal(0, 2, (FIXTURE_H, FIXTURE_W, 3)).astype(np.float32)
-    img[: FIXTURE_H // 2] = np.linspace(0, 4, FIXTURE_W, dtype=np.float32)[None, :, None] * np.array([1, -1, 0.5], dtype=np.float32)
+def fixture_image(tall=False):
+    w, h = (FIXTURE_TALL_W, FIXTURE_TALL_H) if tall else (FIXTURE_W, FIXTURE_H)
+    img = np.random.default_rng(FIXTURE_SEED + int(tall)).normal(0, 2, (h, w, 3)).astype(np.float32)
+    img[: h // 2] = np.linspace(0, 4, w, dtype=np.float32)[None, :, None] * np.array([1, -1, 0.5], dtype=np.float32)
+    if tall:
+        img[h // 2: h // 2 + 8] = 0.75  # constant rows: the Huffman run-length symbol
     return img

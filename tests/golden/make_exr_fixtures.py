@@ -21,13 +21,21 @@ VARIANTS = {
     "rle_f16": (cv2.IMWRITE_EXR_TYPE_HALF, cv2.IMWRITE_EXR_COMPRESSION_RLE),
     "zips_f16": (cv2.IMWRITE_EXR_TYPE_HALF, cv2.IMWRITE_EXR_COMPRESSION_ZIPS),
     "zip_f32": (cv2.IMWRITE_EXR_TYPE_FLOAT, cv2.IMWRITE_EXR_COMPRESSION_ZIP),
-    "piz_f32": (cv2.IMWRITE_EXR_TYPE_FLOAT, cv2.IMWRITE_EXR_COMPRESSION_PIZ),  # not covered: must be refused
+    "piz_f32": (cv2.IMWRITE_EXR_TYPE_FLOAT, cv2.IMWRITE_EXR_COMPRESSION_PIZ),
+    "piz_f16": (cv2.IMWRITE_EXR_TYPE_HALF, cv2.IMWRITE_EXR_COMPRESSION_PIZ),
+    "pxr24_f32": (cv2.IMWRITE_EXR_TYPE_FLOAT, cv2.IMWRITE_EXR_COMPRESSION_PXR24),  # not covered: must be refused
+}
+# a second, taller image for the 32-scanline PIZ chunks: three chunks, the last one ragged
+TALL = {
+    "piz_f32_tall": (cv2.IMWRITE_EXR_TYPE_FLOAT, cv2.IMWRITE_EXR_COMPRESSION_PIZ),
+    "zip_f16_tall": (cv2.IMWRITE_EXR_TYPE_HALF, cv2.IMWRITE_EXR_COMPRESSION_ZIP),
 }
 
 if __name__ == "__main__":
     out = Path(__file__).resolve().parent / "exr"
     out.mkdir(exist_ok=True)
-    bgr = np.ascontiguousarray(fixture_image()[..., ::-1])  # OpenCV's channel order
-    for name, (typ, comp) in VARIANTS.items():
-        assert cv2.imwrite(str(out / f"{name}.exr"), bgr, [cv2.IMWRITE_EXR_TYPE, typ, cv2.IMWRITE_EXR_COMPRESSION, comp])
-        print(name, (out / f"{name}.exr").stat().st_size, "bytes")
+    for variants, img in ((VARIANTS, fixture_image()), (TALL, fixture_image(tall=True))):
+        bgr = np.ascontiguousarray(img[..., ::-1])  # OpenCV's channel order
+        for name, (typ, comp) in variants.items():
+            assert cv2.imwrite(str(out / f"{name}.exr"), bgr, [cv2.IMWRITE_EXR_TYPE, typ, cv2.IMWRITE_EXR_COMPRESSION, comp])
+            print(name, (out / f"{name}.exr").stat().st_size, "bytes")

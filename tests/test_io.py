@@ -9,7 +9,7 @@ import pytest
 
 from bmfr_b200 import build
 
-from .exr_util import FIXTURE_H, FIXTURE_W, FLOAT, HALF, NONE, PIZ, RLE, ZIP, ZIPS, fixture_image, write_exr
+from .exr_util import FLOAT, HALF, NONE, RLE, ZIP, ZIPS, fixture_image, write_exr
 
 OK, ERR_OPEN, ERR_FORMAT, ERR_UNSUPPORTED, ERR_MISMATCH = 0, -2, -3, -4, -5
 
@@ -58,20 +58,23 @@ def test_exr_round_trip(io, tmp_path, compression, pixel_type):
     assert np.array_equal(out.view(np.uint32), want.view(np.uint32))  # bit for bit, -0 and inf included
 
 
-@pytest.mark.parametrize("name", ["none_f32", "rle_f16", "zips_f16", "zip_f32", "piz_f32"])
+@pytest.mark.parametrize("name", ["none_f32", "rle_f16", "zips_f16", "zip_f32", "piz_f32", "piz_f16", "pxr24_f32",
+                                  "piz_f32_tall", "zip_f16_tall"])
 def test_exr_files_written_by_the_openexr_library(io, name):
     """tests/golden/exr/*.exr were written by OpenCV's bundled OpenEXR (tests/golden/make_exr_fixtures.py)."""
     from pathlib import Path
 
     golden = Path(__file__).resolve().parent / "golden"
-    img, w, h = fixture_image(), FIXTURE_W, FIXTURE_H
+    tall = name.endswith("_tall")
+    img = fixture_image(tall=tall)
+    h, w = img.shape[:2]
     st, out = _read(io, golden / "exr" / f"{name}.exr", w, h)
-    if name.startswith("piz"):
+    if name.startswith("pxr24"):
         assert st == ERR_UNSUPPORTED and b"not covered" in io.bmfr_io_last_error()
         return
     assert st == OK, io.bmfr_io_last_error()
     with np.errstate(over="ignore"):
-        want = img.astype(np.float16).astype(np.float32) if name.endswith("f16") else img
+        want = img.astype(np.float16).astype(np.float32) if "f16" in name else img
     assert np.array_equal(out.view(np.uint32), want.view(np.uint32))
 
 
@@ -119,7 +122,7 @@ def test_exr_errors_follow_the_reference(io, tmp_path):
     write_exr(piz, rgb, f3, NONE)
     data = bytearray(piz.read_bytes())
     at = data.index(b"compression\0compression\0") + len(b"compression\0compression\0") + 4
-    data[at] = PIZ
+    data[at] = 6  # B44
     piz.write_bytes(bytes(data))
     assert _read(io, piz, w, h)[0] == ERR_UNSUPPORTED
     tiled = tmp_path / "tiled.exr"
