@@ -7,6 +7,7 @@
 #include "../../include/bmfr_io.h"
 
 #include <ctype.h>
+#include <math.h>
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -631,6 +632,67 @@ int bmfr_io_parse_camera_header(const char* path, int max_frames, float* matrice
     if (position_limit_squared && initialiser_values(text, "position_limit_squared", v) && !v.empty()) *position_limit_squared = v[0];
     if (normal_limit_squared && initialiser_values(text, "normal_limit_squared", v) && !v.empty()) *normal_limit_squared = v[0];
     return BMFR_IO_OK;
+}
+
+int bmfr_io_psnr(const float* a, const float* b, size_t n, float peak, double* psnr_db) {
+    if (!a || !b || !psnr_db || n == 0 || !(peak > 0.f)) return fail(BMFR_IO_ERR_ARGUMENT, "bmfr_io_psnr: bad argument");
+    double se = 0.0;
+    for (size_t i = 0; i < n; ++i) {
+        const double d = (double)a[i] - (double)b[i];
+        if (d != d) return fail(BMFR_IO_ERR_FORMAT, "bmfr_io_psnr: NaN at element %zu", i);
+        se += d * d;
+    }
+    const double mse = se / (double)n;
+    *psnr_db = mse == 0.0 ? HUGE_VAL : 10.0 * log10((double)peak * peak / mse);
+    return BMFR_IO_OK;
+}
+
+int bmfr_io_ssim_rgb(const float* a, const float* b, int width, int height, float peak, double* ssim) {
+    constexpr int R = 5, WIN = 2 * R + 1;
+    if (!a || !b || !ssim || width < WIN || height < WIN || !(peak > 0.f))
+        return fail(BMFR_IO_ERR_ARGUMENT, "bmfr_io_ssim_rgb: bad argument (images must be at least 11 x 11)");
+    double g[WIN], gs = 0.0;
+    for (int i = 0; i < WIN; ++i) gs += g[i] = exp(-(double)((i - R) * (i - R)) / (2.0 * 1.5 * 1.5));
+    for (int i = 0; i < WIN; ++i) g[i] /= gs;
+    const double c1 = (0.01 * peak) * (0.01 * peak), c2 = (0.03 * peak) * (0.03 * peak);
+    const int ow = width - 2 * R, oh = height - 2 * R;
+    // separable Gaussian moments: five planes (a, b, a^2, b^2, ab), filtered along x then along y
+    std::vector<double> tmp((size_t)5 * ow * height), row(5);
+    double total = 0.0;
+    for (int ch = 0; ch < 3; ++ch) {
+        for (int y = 0; y < height; ++y)
+            for (int x = 0; x < ow; ++x) {
+                double m[5] = {0, 0, 0, 0, 0};
+                for (int k = 0; k < WIN; ++k) {
+                    const size_t at = ((size_t)y * width + x + k) * 3 + ch;
+                    const double va = a[at], vb = b[at];
+                    if (va != va || vb != vb) return fail(BMFR_IO_ERR_FORMAT, "bmfr_io_ssim_rgb: NaN at pixel (%d, %d)", x + k, y);
+                    m[0] += g[k] * va; m[1] += g[k] * vb; m[2] += g[k] * va * va; m[3] += g[k] * vb * vb; m[4] += g[k] * va * vb;
+                }
+                for (int q = 0; q < 5; ++q) tmp[((size_t)q * height + y) * ow + x] = m[q];
+            }
+        double sum = 0.0;
+        for (int y = 0; y < oh; ++y)
+            for (int x = 0; x < ow; ++x) {
+                double m[5] = {0, 0, 0, 0, 0};
+                for (int k = 0; k < WIN; ++k)
+                    for (int q = 0; q < 5; ++q) m[q] += g[k] * tmp[((size_t)q * height + y + k) * ow + x];
+                const double va = m[2] - m[0] * m[0], vb = m[3] - m[1] * m[1], cov = m[4] - m[0] * m[1];
+                sum += ((2.0 * m[0] * m[1] + c1) * (2.0 * cov + c2)) / ((m[0] * m[0] + m[1] * m[1] + c1) * (va + vb + c2));
+            }
+        total += sum / ((double)ow * oh);
+    }
+    *ssim = total / 3.0;
+    return BMFR_IO_OK;
+}
+
+void bmfr_io_tone_map(float* rgb, size_t n) {
+    if (!rgb) return;
+    for (size_t i = 0; i < n; ++i) {
+        float v = rgb[i] > 0.f ? rgb[i] : 0.f;  // max(0, v); NaN -> 0
+        v = powf(v, 0.454545f);
+        rgb[i] = v < 1.f ? v : 1.f;
+    }
 }
 
 int bmfr_io_write_png_rgb(const char* path, int width, int height, const float* rgb, size_t row_stride_floats) {

@@ -11,7 +11,9 @@
 //       DIR/{color,shading_normal,world_position,albedo}N.exr + DIR/camera_matrices.h (bmfr.cpp:43-52),
 //       image size taken from color0.exr (the reference's TODO at bmfr.cpp:37), position / normal
 //       limits and the per-frame matrices / pixel offsets parsed from the header; with --out the
-//       frames are written as DIR/outputN.png (bmfr.cpp:52,520-539).
+//       frames are written as DIR/outputN.png (bmfr.cpp:52,520-539); with --truth PREFIX every output
+//       frame is compared with the linear ground-truth image PREFIX + N + ".exr" after the display
+//       transform of bmfr.cl:852-856 (PSNR and SSIM per frame and their means).
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -60,12 +62,13 @@ struct Table {  // same numbers and layout as ProfilingInfo (Mean / Min / Max / 
 int main(int argc, char** argv) {
     int W = 1280, H = 720, frames = 60;  // bmfr.cpp:39-42
     bool staged = true;
-    std::string data_dir, out_dir;
+    std::string data_dir, out_dir, truth_prefix;
     std::vector<std::string> pos;
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
         if (a == "--data" && i + 1 < argc) data_dir = argv[++i];
         else if (a == "--out" && i + 1 < argc) out_dir = argv[++i];
+        else if (a == "--truth" && i + 1 < argc) truth_prefix = argv[++i];
         else if (a == "--frames" && i + 1 < argc) frames = atoi(argv[++i]);
         else if (a == "fused") staged = false;
         else if (a == "staged") staged = true;
@@ -178,6 +181,37 @@ int main(int argc, char** argv) {
     printf("checksum of the last frame: %.6f (%d x %d, %d frames, %lld kernel launches)\n", cs, W, H, frames,
            bmfr_kernel_launches(ctx));
     bmfr_destroy(ctx);
+
+    if (!truth_prefix.empty()) {
+        std::vector<double> psnr(frames, 0.0), ssim(frames, 0.0);
+        bool error = false;
+#pragma omp parallel for
+        for (int f = 0; f < frames; ++f) {
+            if (error) continue;
+            std::vector<float> truth(n);
+            const std::string path = truth_prefix + std::to_string(f) + ".exr";
+            if (bmfr_io_read_exr_rgb(path.c_str(), W, H, truth.data()) != BMFR_IO_OK) {
+                printf("Ground truth loading failed, reason: %s\n", bmfr_io_last_error());
+                error = true;
+                continue;
+            }
+            bmfr_io_tone_map(truth.data(), n);
+            if (bmfr_io_psnr(out[f].data(), truth.data(), n, 1.f, &psnr[f]) != BMFR_IO_OK ||
+                bmfr_io_ssim_rgb(out[f].data(), truth.data(), W, H, 1.f, &ssim[f]) != BMFR_IO_OK) {
+                printf("Quality metrics failed for frame %d, reason: %s\n", f, bmfr_io_last_error());
+                error = true;
+            }
+        }
+        if (error) return 1;
+        double mp = 0, ms = 0;
+        printf("\n Quality against %sN.exr (tone-mapped)\n", truth_prefix.c_str());
+        for (int f = 0; f < frames; ++f) {
+            printf("   frame %3d : PSNR %7.3f dB   SSIM %.5f\n", f, psnr[f], ssim[f]);
+            mp += psnr[f];
+            ms += ssim[f];
+        }
+        printf("   mean      : PSNR %7.3f dB   SSIM %.5f\n\n", mp / frames, ms / frames);
+    }
 
     if (!out_dir.empty()) {  // "Store results", bmfr.cpp:519-553
         bool error = false;

@@ -50,6 +50,17 @@ int bmfr_io_parse_camera_header(const char* path, int max_frames, float* matrice
  * (NaN -> 0).  The values are the tone-mapped result of the taa kernel, no further transfer curve. */
 int bmfr_io_write_png_rgb(const char* path, int width, int height, const float* rgb, size_t row_stride_floats);
 
+/* Image-quality metrics of the paper's evaluation, for comparing output frames with ground truth:
+ *   PSNR = 10 log10(peak^2 / mean squared error) over n values (+inf for identical inputs), NaNs are an error;
+ *   SSIM = mean structural similarity (Wang et al. 2004: 11x11 Gaussian window, sigma 1.5, K1 = 0.01, K2 = 0.03,
+ *          dynamic range `peak`, valid windows only), per channel of an interleaved width x height x 3 image, averaged.
+ * tone_map applies the display transform of the accumulate_filtered_data kernel to linear radiance in place:
+ * clamp(pow(max(0, v), 0.454545), 0, 1) (bmfr.cl:852-856), so that a linear ground-truth image can be compared with
+ * the denoiser's tone-mapped output. */
+int bmfr_io_psnr(const float* a, const float* b, size_t n, float peak, double* psnr_db);
+int bmfr_io_ssim_rgb(const float* a, const float* b, int width, int height, float peak, double* ssim);
+void bmfr_io_tone_map(float* rgb, size_t n);
+
 const char* bmfr_io_last_error(void);
 
 #ifdef __cplusplus

@@ -1,6 +1,7 @@
 """bmfr_run, the reference's driver program on the C ABI: a dataset in the reference's
 format (EXR frames + camera_matrices.h, bmfr.cpp:43-52) goes in, the reference's profiling tables and PNG
 frames come out; the frames must be the ones the library produces for the same inputs."""
+import re
 import subprocess
 
 import numpy as np
@@ -51,9 +52,12 @@ def test_driver_runs_a_dataset_in_the_reference_format(tmp_path, mode):
     data.mkdir()
     out.mkdir()
     frames = _write_dataset(data)
-    r = subprocess.run([str(exe), "--data", str(data), "--frames", str(FRAMES), "--out", str(out), mode], capture_output=True, text=True,
-                       timeout=300)
+    # --truth: the noisy input stands in for a ground-truth sequence (same file format: linear radiance)
+    r = subprocess.run([str(exe), "--data", str(data), "--frames", str(FRAMES), "--out", str(out), "--truth", str(data / "color"), mode],
+                       capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
+    reported = [tuple(float(x) for x in m) for m in re.findall(r"frame +\d+ : PSNR +([0-9.]+) dB +SSIM ([0-9.]+)", r.stdout)]
+    assert len(reported) == FRAMES, r.stdout
     for line in ("Initialize.", "Loading input data.", "Run and profile kernels.", "Total time in all kernels"):  # bmfr.cpp:181,252,387
         assert line in r.stdout
     # the same frames through the library
@@ -65,6 +69,10 @@ def test_driver_runs_a_dataset_in_the_reference_format(tmp_path, mode):
             d.denoise_frame_host(f, a, n, p, c, cam_prev, off, res)
             d.sync()
             want = np.floor(np.clip(np.nan_to_num(res, nan=0.0), 0, 1) * np.float32(255) + np.float32(0.5)).astype(np.uint8)
+            truth = np.clip(np.power(np.maximum(np.asarray(c, dtype=np.float32).reshape(H, W, 3), 0), np.float32(0.454545)), 0, 1)
+            mse = np.mean((res.astype(np.float64) - truth.astype(np.float64)) ** 2)
+            assert abs(reported[f][0] - 10 * np.log10(1.0 / mse)) < 2e-3, (f, reported[f], 10 * np.log10(1.0 / mse))
+            assert 0.0 < reported[f][1] <= 1.0
             got = np.asarray(Image.open(out / f"output{f}.png"))
             assert got.shape == (H, W, 3)
             assert np.array_equal(got, want), f"frame {f}: {np.abs(got.astype(int) - want.astype(int)).max()} levels off"

@@ -23,6 +23,10 @@ def io():
     lib.bmfr_io_parse_camera_header.argtypes = [C.c_char_p, C.c_int, fp, fp, ip, ip, fp, fp]
     lib.bmfr_io_write_png_rgb.argtypes = [C.c_char_p, C.c_int, C.c_int, fp, C.c_size_t]
     lib.bmfr_io_last_error.restype = C.c_char_p
+    lib.bmfr_io_psnr.argtypes = [fp, fp, C.c_size_t, C.c_float, C.POINTER(C.c_double)]
+    lib.bmfr_io_ssim_rgb.argtypes = [fp, fp, C.c_int, C.c_int, C.c_float, C.POINTER(C.c_double)]
+    lib.bmfr_io_tone_map.argtypes = [fp, C.c_size_t]
+    lib.bmfr_io_tone_map.restype = None
     return lib
 
 
@@ -238,6 +242,53 @@ def test_io_library_exports_every_declared_symbol(io):
 
     header = (Path(__file__).resolve().parent.parent / "include" / "bmfr_io.h").read_text()
     names = sorted(set(re.findall(r"\b(bmfr_io_\w+)\s*\(", header)))
-    assert len(names) == 5, names
+    assert len(names) == 8, names
     for n in names:
         assert hasattr(io, n), n
+
+
+def _ssim_reference(a, b, peak):
+    """Wang et al. 2004 as usually implemented (11x11 Gaussian, sigma 1.5, valid windows), in float64 with scipy."""
+    from scipy.signal import convolve2d
+
+    g = np.exp(-((np.arange(11) - 5.0) ** 2) / (2 * 1.5 ** 2))
+    g /= g.sum()
+    win = np.outer(g, g)
+    c1, c2 = (0.01 * peak) ** 2, (0.03 * peak) ** 2
+    vals = []
+    for ch in range(3):
+        x, y = a[..., ch].astype(np.float64), b[..., ch].astype(np.float64)
+        f = lambda im: convolve2d(im, win, mode="valid")  # noqa: E731 (the window is symmetric)
+        mx, my = f(x), f(y)
+        vx, vy, cxy = f(x * x) - mx * mx, f(y * y) - my * my, f(x * y) - mx * my
+        vals.append((((2 * mx * my + c1) * (2 * cxy + c2)) / ((mx * mx + my * my + c1) * (vx + vy + c2))).mean())
+    return float(np.mean(vals))
+
+
+def test_quality_metrics(io):
+    fp = C.POINTER(C.c_float)
+    rng = np.random.default_rng(4)
+    h, w = 37, 52
+    a = rng.uniform(0, 1, (h, w, 3)).astype(np.float32)
+    a[:, : w // 2] = np.linspace(0, 1, w // 2, dtype=np.float32)[None, :, None]  # structure, not only noise
+    b = np.clip(a + rng.normal(0, 0.05, a.shape), 0, 1).astype(np.float32)
+    v = C.c_double()
+    assert io.bmfr_io_psnr(a.ctypes.data_as(fp), b.ctypes.data_as(fp), a.size, 1.0, C.byref(v)) == OK
+    mse = np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2)
+    assert abs(v.value - 10 * np.log10(1.0 / mse)) < 1e-9
+    assert io.bmfr_io_psnr(a.ctypes.data_as(fp), a.ctypes.data_as(fp), a.size, 1.0, C.byref(v)) == OK and v.value == np.inf
+    for x, y, peak in ((a, b, 1.0), (a, a, 1.0), (a, 1 - a, 1.0), (2 * a, 2 * b, 2.0)):
+        assert io.bmfr_io_ssim_rgb(x.ctypes.data_as(fp), y.ctypes.data_as(fp), w, h, peak, C.byref(v)) == OK
+        assert abs(v.value - _ssim_reference(x, y, peak)) < 1e-9, (v.value, _ssim_reference(x, y, peak))
+    assert io.bmfr_io_ssim_rgb(a.ctypes.data_as(fp), a.ctypes.data_as(fp), w, h, 1.0, C.byref(v)) == OK and abs(v.value - 1) < 1e-12
+    bad = a.copy()
+    bad[3, 4, 1] = np.nan
+    assert io.bmfr_io_psnr(a.ctypes.data_as(fp), bad.ctypes.data_as(fp), a.size, 1.0, C.byref(v)) == ERR_FORMAT
+    assert io.bmfr_io_ssim_rgb(a.ctypes.data_as(fp), bad.ctypes.data_as(fp), w, h, 1.0, C.byref(v)) == ERR_FORMAT
+    assert io.bmfr_io_ssim_rgb(a.ctypes.data_as(fp), b.ctypes.data_as(fp), 10, 10, 1.0, C.byref(v)) == -1
+    # the display transform of bmfr.cl:852-856
+    lin = np.array([-1.0, 0.0, 0.18, 1.0, 7.5, np.nan, np.inf], dtype=np.float32)
+    t = lin.copy()
+    io.bmfr_io_tone_map(t.ctypes.data_as(fp), t.size)
+    want = np.clip(np.power(np.maximum(np.nan_to_num(lin, nan=0.0), 0), np.float32(0.454545)), 0, 1).astype(np.float32)
+    assert np.allclose(t, want, rtol=1e-6, atol=0) and t[0] == 0 and t[3] == 1 and t[5] == 0 and t[6] == 1
