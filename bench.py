@@ -175,8 +175,9 @@ def host_cores():
 # ------------------------------------------------------------------------------------------------
 # CPU arms (the only places bench.py touches oracle/)
 # ------------------------------------------------------------------------------------------------
-def time_oracle(kind, w, h, nframes, inputs=None):
-    """frames/s of `kind` ("port" | "reference") over the first `nframes` frames of the workload."""
+def time_oracle(kind, w, h, nframes, inputs=None, min_seconds=0.0):
+    """frames/s of `kind` ("port" | "reference") over the first `nframes` frames of the workload; the pass is
+    repeated (restarting at frame 0) until `min_seconds` of CPU work have been timed.  -> (fps, seconds, stage ms, passes)"""
     from bmfr_b200 import synth
     from oracle.oracle import Oracle
     pl, nl = synth.limits()
@@ -188,13 +189,18 @@ def time_oracle(kind, w, h, nframes, inputs=None):
         _, off = synth.camera(f, w, h)
         frames.append((f, a, n, p, c, cam, off))
     stage = np.zeros(6)
+    passes = 0
     t0 = time.perf_counter()
-    for fr in frames:
-        o.frame(*fr)
-        stage += np.array(o.stage_ms())
-    dt = time.perf_counter() - t0
+    while True:
+        for fr in frames:
+            o.frame(*fr)
+            stage += np.array(o.stage_ms())
+        passes += 1
+        dt = time.perf_counter() - t0
+        if dt >= min_seconds:
+            break
     o.close()
-    return nframes / dt, dt, (stage / nframes).tolist()
+    return nframes * passes / dt, dt, (stage / (nframes * passes)).tolist(), passes
 
 
 def run_reference_arm(args):
@@ -215,7 +221,7 @@ def run_reference_arm(args):
         for _ in range(args.warmup if args.warmup < 1 else 1):
             time_oracle(kind, w, h, 1)
         for _ in range(max(1, min(args.steps, 3))):
-            fps, dt, stage = time_oracle(kind, w, h, sample)
+            fps, dt, stage, _ = time_oracle(kind, w, h, sample)
             vals.append((fps, dt, stage))
         best = max(vals, key=lambda v: v[0])
         results[kind] = dict(fps=best[0], seconds=best[1], stage_ms=best[2])
@@ -368,9 +374,11 @@ def run_single_gpu(args):
     if not args.no_cpu:
         nfr = args.cpu_frames
         hin_small = inputs[:nfr].cpu().numpy()
-        fps_cpu, dt_cpu, stage = time_oracle("port", w, h, nfr, inputs=lambda f: [hin_small[f, k] for k in range(4)])
+        fps_cpu, dt_cpu, stage, passes = time_oracle("port", w, h, nfr, inputs=lambda f: [hin_small[f, k] for k in range(4)],
+                                                     min_seconds=args.cpu_seconds)
         cpu = {"value": fps_cpu, "unit": "frames/s", "cores": host_cores(), "kind": "port",
-               "sample": f"first {nfr} frames of the workload ({dt_cpu:.1f} s), oracle/bmfr_oracle.c with OpenMP",
+               "sample": f"first {nfr} frames of the workload, {passes} passes ({dt_cpu:.1f} s of CPU work), "
+                         "oracle/bmfr_oracle.c with OpenMP",
                "stage_ms": stage}
 
     line = {
@@ -398,6 +406,7 @@ def main():
     ap.add_argument("--width", type=int, default=0)
     ap.add_argument("--height", type=int, default=0)
     ap.add_argument("--cpu-frames", type=int, default=8, help="frames of the workload the cpu_baseline runs")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="the cpu_baseline repeats its frames until this much CPU work is timed")
     ap.add_argument("--ref-frames", type=int, default=6, help="frames per pass of --impl reference")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="halo transport of the sharded run (N > 1)")
     ap.add_argument("--overlap", type=int, default=1, choices=[0, 1],
