@@ -1,26 +1,33 @@
 #!/bin/bash
-# One gpurun call: parity tests, bench, then (only if both exited 0) ncu launch list + full captures.
-# usage: gpurun --timeout 1500 -- 'bash scripts/gpu_round.sh [tag]'
-TAG=${1:-r01}
+# parity tests, bench (fused + staged per-kernel), launch list, ncu --set full of the four FUSED kernels
+TAG=${1:-r02a}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
-{
-  echo "== host"; nproc; free -g | head -2; nvidia-smi --query-gpu=name,driver_version,memory.total --format=csv
-  echo "== opencl probe"; ls /etc/OpenCL/vendors 2>&1; find / -name 'libnvidia-opencl*' 2>/dev/null | head; find / -iname '*pocl*' 2>/dev/null | head -3
-} > $OUT/probe.log 2>&1
-python -m pytest tests -m gpu -x -q -s > $OUT/pytest.log 2>&1
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/smi.log 2>&1
+if [ -z "$NCU_ONLY" ]; then
+timeout 600 python -m pytest tests -m gpu -x -q > $OUT/pytest.log 2>&1
 PT=$?
 echo "pytest exit $PT"; tail -15 $OUT/pytest.log
-[ $PT -ne 0 ] && exit $PT
-python bench.py --steps 3 --warmup 3 --all-modes > $OUT/bench.json 2> $OUT/bench.err
+[ $PT -ne 0 ] && [ -z "$KEEP_GOING" ] && exit $PT
+timeout 600 python bench.py --steps 3 --warmup 3 ${BENCH_ARGS:---all-modes} > $OUT/bench.json 2> $OUT/bench.err
 BE=$?
-echo "bench exit $BE"; cat $OUT/bench.json | cut -c1-3000; tail -5 $OUT/bench.err
+echo "bench exit $BE"; python scripts/show_bench.py $OUT/bench.json; tail -5 $OUT/bench.err
 [ $BE -ne 0 ] && exit $BE
-python bench.py --impl reference --steps 1 --warmup 0 > $OUT/bench_reference.json 2>> $OUT/bench.err
-cat $OUT/bench_reference.json | cut -c1-1200
-SHORT="python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu"
-$SHORT > $OUT/plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv $SHORT > $OUT/ncu_launches.log 2>&1
-$SHORT > $OUT/plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:'fit_kernel|post_kernel' -s 40 -c 4 -f -o $OUT/prof $SHORT > $OUT/ncu_full.log 2>&1
-ls -la $OUT
+for V in bmfr_b200/libbmfr_b200_*.so; do
+  [ -f "$V" ] || continue
+  N=$(basename $V .so)
+  BMFR_B200_LIB=$PWD/$V timeout 300 python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu > $OUT/bench_$N.json 2>> $OUT/bench.err
+  echo "== variant $N"; python scripts/show_bench.py $OUT/bench_$N.json
+done
+fi
+[ -n "$NO_NCU" ] && exit 0
+# one ncu pass per call, each after the same command has exited 0 without ncu: NCU_MODE=launches (default) or full
+SHORT="timeout 300 python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu"
+if [ "${NCU_MODE:-launches}" = "launches" ]; then
+  $SHORT > $OUT/plain.log 2>&1 &&
+  ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'reproject_kernel|fit_qr_kernel|post_kernel|noise_tile' -s 160 -c 80 --csv --log-file $OUT/launches.csv $SHORT > $OUT/ncu_launches.log 2>&1
+else
+  $SHORT > $OUT/plain2.log 2>&1 &&
+  ncu --set full --clock-control none --import-source on -k regex:'reproject_kernel|fit_qr_kernel|post_kernel' -s 60 -c 3 -f -o $OUT/prof $SHORT > $OUT/ncu_full.log 2>&1
+fi
+ls $OUT
