@@ -4,16 +4,18 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
 
 A "step" is one pass of the hot path over one batch = the 60-frame synthetic sequence (synth-v1) of
-the workload.  N=1: 1920x1080 (the headline single-GPU config).  N>1 (torchrun, one rank per GPU):
-3840x2160 strip-sharded along block rows with NCCL halo exchange.
+the workload.  N=1: 1920x1080 (the headline single-GPU config).  N>1 (torchrun, one rank per GPU): the
+multi-GPU configs of BASELINE.json, strip-sharded along block rows with peer-to-peer halo pushes over
+NVLink: N=2 and N=4 -> 3840x2160, N=8 -> 7680x4320.
 
   value  : frames/s, inputs resident in HBM, device-timed (CUDA events on the launching stream)
   e2e    : frames/s through the C ABI's host-pointer entry: pinned-host uploads + read-back inside
   roofline / kernels : per-kernel algorithmic bytes / measured launch duration
   cpu_baseline : the CPU oracle on the box's host cores, bounded sample (reported, not a target)
 
-`--impl reference` times the reference's CPU implementation of the path (the reference's own bmfr.cl
-through oracle/_ref when present, and the plain-C port of it) on the host cores.
+`--impl reference` times the reference's CPU implementation of the path on the host cores (the plain-C port
+of bmfr.cl, pinned bit for bit against the reference's own kernels; --ref-shim also times those through the
+OpenCL-C shim of oracle/_ref), all host threads, every step a bounded sample of the same workload.
 """
 from __future__ import annotations
 
@@ -38,10 +40,18 @@ SINGLE_GPU_WORKLOAD = (1920, 1080)
 
 
 def sharded_workload(n_gpus):
-    """Weak scaling: every rank owns a 3840x540 strip (the pixel count of one 1080p frame), so N = 4 is
-    BASELINE.json's 3840x2160 config; N = 2 is 3840x1080 and N = 8 is 3840x4320.  The strong-scaling
-    configs of BASELINE.json (4K over 2/4/8, 8K over 8) are run with --width/--height."""
-    return (3840, 540 * n_gpus)
+    """BASELINE.json's multi-GPU configs: 3840x2160 over 2 and 4 GPUs, 7680x4320 over 8 (other N: a 3840x540 strip
+    per rank).  `value` stays in 1080p-equivalent frames/s so that the series is comparable across N; other
+    pairings (4K over 8, the old 3840x(540 N) weak series) run with --width/--height."""
+    return {2: (3840, 2160), 4: (3840, 2160), 8: (7680, 4320)}.get(n_gpus, (3840, 540 * n_gpus))
+
+
+def workload_config(w, h, n_gpus):
+    """The `config` object of the JSON line — identical for the B200 arm and the reference arm."""
+    return {"workload": f"{w}x{h} x{FRAMES} frames synth-v1, 32x32 blocks, 10 features, fp32 tmp_data",
+            "value_unit": "1080p-equivalent frames/s = native frames/s x (W*H)/(1920*1080) (= frames/s at 1920x1080)",
+            "l2": "inputs of a sequence (5.97 GB at 1080p) are larger than L2; no explicit flush",
+            "parallelism": "single GPU" if n_gpus == 1 else f"strips{n_gpus} (block rows)"}
 
 
 def geometry(w, h):
@@ -165,6 +175,21 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "source": self.source}
 
 
+def reference_gpu(w, h):
+    """The reference's unmodified bmfr.cl on the B200 through NVIDIA's OpenCL ICD: the committed measurement of
+    scripts/opencl_reference.py for this workload (profiles/), or None.  A reported baseline, never part of `value`."""
+    for name in sorted((ROOT / "profiles").glob("r*_reference_opencl_b200*.json"), reverse=True):
+        try:
+            m = json.loads(name.read_text())
+            if m.get("opencl") == "ok" and m.get("workload", "").startswith(f"{w}x{h} "):
+                return {"frames_per_s": m["frames_per_s_from_total"], "kernel_sum_ms": m["kernel_sum_ms"], "device": m["device"],
+                        "tmp_half": m["tmp_half"], "stages_ms": {k: v["mean_ms"] for k, v in m["stages"].items()},
+                        "source": f"profiles/{name.name}"}
+        except Exception:
+            continue
+    return None
+
+
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -175,13 +200,13 @@ def host_cores():
 # ------------------------------------------------------------------------------------------------
 # CPU arms (the only places bench.py touches oracle/)
 # ------------------------------------------------------------------------------------------------
-def time_oracle(kind, w, h, nframes, inputs=None, min_seconds=0.0):
+def time_oracle(kind, w, h, nframes, inputs=None, min_seconds=0.0, threads=0):
     """frames/s of `kind` ("port" | "reference") over the first `nframes` frames of the workload; the pass is
     repeated (restarting at frame 0) until `min_seconds` of CPU work have been timed.  -> (fps, seconds, stage ms, passes)"""
     from bmfr_b200 import synth
     from oracle.oracle import Oracle
     pl, nl = synth.limits()
-    o = Oracle(kind, w, h, position_limit_squared=pl, normal_limit_squared=nl)
+    o = Oracle(kind, w, h, position_limit_squared=pl, normal_limit_squared=nl, threads=threads or host_cores())
     frames = []
     for f in range(nframes):
         a, n, p, c = inputs(f) if inputs else synth.frame_host(w, h, f)
@@ -203,7 +228,38 @@ def time_oracle(kind, w, h, nframes, inputs=None, min_seconds=0.0):
     return nframes * passes / dt, dt, (stage / (nframes * passes)).tolist(), passes
 
 
+class OracleSequence:
+    """The reference's frame loop on the host cores as one continuing run: frame numbers walk through the 60-frame
+    sequence and wrap (frame 0, the only frame without a temporal path, comes up once per 60 frames as in the full
+    workload).  Inputs are generated outside the timed calls."""
+
+    def __init__(self, kind, w, h, threads):
+        from bmfr_b200 import synth
+        from oracle.oracle import Oracle
+        self.synth, self.w, self.h, self.f = synth, w, h, 0
+        pl, nl = synth.limits()
+        self.o = Oracle(kind, w, h, position_limit_squared=pl, normal_limit_squared=nl, threads=threads)
+
+    def run(self, nframes):
+        """Processes the next `nframes` frames; returns the seconds spent inside the oracle (inputs excluded)."""
+        spent = 0.0
+        for _ in range(nframes):
+            f = self.f % FRAMES
+            a, n, p, c = self.synth.frame_host(self.w, self.h, f)
+            cam, _ = self.synth.camera(max(f - 1, 0), self.w, self.h)
+            _, off = self.synth.camera(f, self.w, self.h)
+            t0 = time.perf_counter()
+            self.o.frame(f, a, n, p, c, cam, off)
+            spent += time.perf_counter() - t0
+            self.f += 1
+        return spent
+
+
 def run_reference_arm(args):
+    """Rank 0 only (the other ranks exit 0 without work).  Each of the `steps` steps is a bounded sample of the
+    workload — F consecutive frames of the continuing sequence — with F calibrated on one untimed frame so that
+    warm-up + steps take about --ref-budget seconds (default 60) at any size; `steps`, `ms_per_step` and
+    `frames_per_step` are what was actually run."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -212,35 +268,40 @@ def run_reference_arm(args):
     w, h = args.width or w, args.height or h
     norm = (w * h) / float(SINGLE_GPU_WORKLOAD[0] * SINGLE_GPU_WORKLOAD[1])  # 1080p-equivalent frames per frame
     cores = host_cores()
-    sample = args.ref_frames
+    kinds = ["port"] + (["reference"] if args.ref_shim and orc.available("reference") else [])
     results = {}
-    for kind in ("port", "reference"):
-        if not orc.available(kind) and kind == "reference":
-            continue
-        vals = []
-        for _ in range(args.warmup if args.warmup < 1 else 1):
-            time_oracle(kind, w, h, 1)
-        for _ in range(max(1, min(args.steps, 3))):
-            fps, dt, stage, _ = time_oracle(kind, w, h, sample)
-            vals.append((fps, dt, stage))
-        best = max(vals, key=lambda v: v[0])
-        results[kind] = dict(fps=best[0], seconds=best[1], stage_ms=best[2])
-    # the reference's CPU implementation at the best speed available here: its own kernels through the
-    # CL shim pay a fiber switch per work-item per barrier, the plain-C port of them does not
+    for kind in kinds:
+        seq = OracleSequence(kind, w, h, cores)
+        t_cal = seq.run(1) + seq.run(1)        # calibration (untimed for the result): frames 0 and 1
+        per_frame = max(t_cal / 2.0, 1e-4)
+        nsteps = max(1, args.steps)
+        if args.ref_frames > 0:
+            fps_step = args.ref_frames
+        else:
+            fps_step = int(args.ref_budget / per_frame / (nsteps + max(0, args.warmup)))
+            fps_step = max(1, min(FRAMES, fps_step))
+        for _ in range(max(0, args.warmup)):
+            seq.run(fps_step)
+        step_s = [seq.run(fps_step) for _ in range(nsteps)]
+        total = float(sum(step_s))
+        results[kind] = dict(fps=fps_step * nsteps / total, seconds=total, frames_per_step=fps_step,
+                             ms_per_step=1e3 * total / nsteps)
+        seq.o.close()
     kind = max(results, key=lambda k: results[k]["fps"])
-    native = results[kind]["fps"]
+    r = results[kind]
+    native = r["fps"]
     v = native * norm  # same unit as the B200 arm: 1080p-equivalent frames/s (identical to frames/s at N = 1)
     line = {
         "impl": "reference", "metric": "frames/sec", "value": v, "unit": "frames/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * FRAMES / native, "higher_is_better": True,
+        "steps": max(1, args.steps), "warmup": max(0, args.warmup), "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "frames_per_s_native": native,
-        "config": {"workload": f"{w}x{h} x{FRAMES} frames synth-v1, 32x32 blocks, 10 features, fp32 tmp_data",
-                   "value_unit": "1080p-equivalent frames/s = native frames/s x (W*H)/(1920*1080)"},
+        "frames_per_s_native": native, "frames_per_step": r["frames_per_step"],
+        "config": workload_config(w, h, args.gpus),
         "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": kind,
-                         "sample": f"first {sample} frames of the workload, best of {max(1, min(args.steps, 3))} passes, "
-                                   f"OpenMP on {cores} host threads",
-                         "all": {k: {"frames_per_s": r["fps"], "stage_ms": r["stage_ms"]} for k, r in results.items()}},
+                         "sample": f"every step = {r['frames_per_step']} consecutive frames of the continuing 60-frame sequence "
+                                   f"({r['seconds']:.1f} s of CPU work in the {max(1, args.steps)} timed steps), oracle/bmfr_oracle.c, "
+                                   f"OpenMP on {cores} host threads (set explicitly: torchrun exports OMP_NUM_THREADS=1)",
+                         "all": {k: {"frames_per_s": x["fps"], "frames_per_step": x["frames_per_step"]} for k, x in results.items()}},
         "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -280,26 +341,47 @@ def run_single_gpu(args):
                             inputs[f, 3].data_ptr(), cams[f], offs[f], None)
 
     overlap = int(args.overlap and args.mode == "fused")
-    d = Denoiser(w, h, mode=args.mode, stream=sp, overlap_frames=overlap)
-    for _ in range(args.warmup):
-        run_sequence(d)
-    torch.cuda.synchronize()
-    launches0 = d.kernel_launches
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(0) as clocks:
+
+    def timed(overlap_frames, steps, warmup, sample_clocks=False):
+        """-> (total ms of `steps` steps, kernel launches, clock summary): CUDA events on the context's stream."""
+        d = Denoiser(w, h, mode=args.mode, stream=sp, overlap_frames=overlap_frames)
+        for _ in range(warmup):
+            run_sequence(d)
+        torch.cuda.synchronize()
+        l0 = d.kernel_launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler = ClockSampler(0) if sample_clocks else None
+        if sampler:
+            sampler.__enter__()
         torch.cuda.synchronize()
         e0.record(stream)
-        for _ in range(args.steps):
+        for _ in range(steps):
             run_sequence(d)
         d.join()  # overlapped frames run on the context's internal streams: order the closing event after them
         e1.record(stream)
         torch.cuda.synchronize()
-    d.sync()
-    total_ms = e0.elapsed_time(e1)
-    launches = d.kernel_launches - launches0
+        if sampler:
+            sampler.__exit__()
+        d.sync()
+        ms, n = e0.elapsed_time(e1), d.kernel_launches - l0
+        d.close()
+        return ms, n, (sampler.summary() if sampler else None)
+
+    total_ms, launches, clock_summary = timed(overlap, args.steps, args.warmup, sample_clocks=True)
     ms_per_step = total_ms / args.steps
     fps = FRAMES * args.steps / (total_ms * 1e-3)
-    d.close()
+    # the same K steps on the drop-in in-order stream (the reference's queue semantics, bmfr.cpp:191)
+    in_order = None
+    if overlap:
+        ms_io, _, _ = timed(0, args.steps, args.warmup)
+        in_order = {"value": FRAMES * args.steps / (ms_io * 1e-3), "unit": "frames/s", "ms_per_frame": ms_io / args.steps / FRAMES,
+                    "what": "overlap_frames = 0: one in-order stream, three kernels per frame chained with programmatic dependent launch"}
+    # a longer timed region of the same mode, so that one DVFS wobble cannot move the figure
+    sustained = None
+    if args.sustain_seconds > 0:
+        k = max(args.steps, int(np.ceil(args.sustain_seconds * 1e3 / ms_per_step)))
+        ms_s, _, clk_s = timed(overlap, k, 1, sample_clocks=True)
+        sustained = {"value": FRAMES * k / (ms_s * 1e-3), "unit": "frames/s", "steps": k, "seconds": ms_s * 1e-3, "clocks": clk_s}
 
     # per-kernel durations: same sequence with event pairs around every launch (separate pass, so the
     # events do not perturb the headline number)
@@ -358,7 +440,7 @@ def run_single_gpu(args):
                 dh.denoise_frame_host(f, hin[f, 0], hin[f, 1], hin[f, 2], hin[f, 3], cams[f], offs[f], hout[f & 1])
         run_host_sequence()
         dh.sync()
-        steps = max(1, min(args.steps, 3))
+        steps = max(1, min(args.steps, 10))
         t0 = time.perf_counter()
         for _ in range(steps):
             run_host_sequence()
@@ -375,7 +457,7 @@ def run_single_gpu(args):
         nfr = args.cpu_frames
         hin_small = inputs[:nfr].cpu().numpy()
         fps_cpu, dt_cpu, stage, passes = time_oracle("port", w, h, nfr, inputs=lambda f: [hin_small[f, k] for k in range(4)],
-                                                     min_seconds=args.cpu_seconds)
+                                                     min_seconds=args.cpu_seconds, threads=host_cores())
         cpu = {"value": fps_cpu, "unit": "frames/s", "cores": host_cores(), "kind": "port",
                "sample": f"first {nfr} frames of the workload, {passes} passes ({dt_cpu:.1f} s of CPU work), "
                          "oracle/bmfr_oracle.c with OpenMP",
@@ -385,12 +467,11 @@ def run_single_gpu(args):
         "metric": "frames/sec", "value": fps, "unit": "frames/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "ms_per_frame": ms_per_step / FRAMES, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{w}x{h} x{FRAMES} frames synth-v1, 32x32 blocks, 10 features, fp32 tmp_data",
-                   "mode": args.mode, "overlap_frames": overlap,
-                   "l2": "inputs (5.97 GB/sequence at 1080p) larger than L2; no explicit flush",
-                   "parallelism": "single GPU"},
+        "config": workload_config(w, h, 1),
+        "run": {"mode": args.mode, "overlap_frames": overlap},
         "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-        "clocks": clocks.summary(),
+        "in_order": in_order, "sustained": sustained, "reference_gpu": reference_gpu(w, h),
+        "clocks": clock_summary,
     }
     print(json.dumps(line))
 
@@ -398,7 +479,7 @@ def run_single_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=150, help="timed steps (150 x 60 frames at 1080p is a 1.2 s timed region)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default="fused", choices=["fused", "staged"])
@@ -407,7 +488,11 @@ def main():
     ap.add_argument("--height", type=int, default=0)
     ap.add_argument("--cpu-frames", type=int, default=8, help="frames of the workload the cpu_baseline runs")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="the cpu_baseline repeats its frames until this much CPU work is timed")
-    ap.add_argument("--ref-frames", type=int, default=6, help="frames per pass of --impl reference")
+    ap.add_argument("--ref-frames", type=int, default=0, help="--impl reference: frames per step (0 = calibrated to --ref-budget)")
+    ap.add_argument("--ref-budget", type=float, default=60.0, help="--impl reference: seconds of CPU work for warm-up + steps")
+    ap.add_argument("--ref-shim", action="store_true", help="--impl reference: also time the reference's own kernels through the CL shim")
+    ap.add_argument("--parity-frames", type=int, default=3, help="N > 1: frames compared bit for bit with a whole-image run (outside the timed region)")
+    ap.add_argument("--sustain-seconds", type=float, default=1.0, help="length of the extra long timed region reported as `sustained`")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="halo transport of the sharded run (N > 1)")
     ap.add_argument("--overlap", type=int, default=1, choices=[0, 1],
                     help="bmfr_params.overlap_frames of the timed contexts: 1 = consecutive frames overlap on the device "

@@ -48,7 +48,14 @@ __device__ __forceinline__ int noise_f_index(int c, int y, int x) {
 
 template <bool STRIP>
 __global__ void __launch_bounds__(256, BMFR_REPROJECT_MIN_BLOCKS) reproject_kernel(const __grid_constant__ KParams P) {
-    pdl_trigger();  // the fit's CTAs may take SM slots as this grid drains (all they do before their wait is barrier set-up)
+    // Everything below reads the caller's inputs.  Their producer may be the kernel right before this one on the
+    // context's stream — then it is this grid's programmatic-launch primary, and if it triggers its dependents early
+    // its writes are only guaranteed visible after the wait.  So the wait comes first; what the programmatic launch
+    // still buys is that this grid's CTAs are resident when the previous frame's post pass retires.
+    pdl_wait();
+    // after the wait, so that "everything before this grid is complete" is transitive: the fit requests its first
+    // normals / positions tiles (the caller's inputs) before its own wait
+    pdl_trigger();  // the fit's CTAs may take SM slots as this grid drains
     // The first CTAs also produce this frame's add_random() tile (bmfr.cl:173-182; one 9x1024 tile per
     // frame shared by all blocks, fp64 like the reference's double literal plus its fp32 rounding for the
     // fit) and reset the fit's block counter: the fit starts only after this kernel has completed.
@@ -57,7 +64,6 @@ __global__ void __launch_bounds__(256, BMFR_REPROJECT_MIN_BLOCKS) reproject_kern
         const int workers = ncta < 36 ? ncta : 36;
         if (cta < workers) {
             const int n = (BMFR_FEATURES - 1) * BMFR_BLOCK_PIXELS;
-            pdl_wait();  // (the previous frame's kernels are complete: nothing reads the tile or the counter any more)
             for (int i = cta * 256 + threadIdx.y * BMFR_REPROJECT_BX + threadIdx.x; i < n; i += workers * 256) {
                 const int seed = i + BMFR_BLOCK_PIXELS + P.frame * BMFR_BUFFER_COUNT * BMFR_BLOCK_PIXELS;
                 const double d = (P.noise_amount * 2.0) * (double)(bmfr_random((unsigned int)seed) - 0.5f);
@@ -89,9 +95,6 @@ __global__ void __launch_bounds__(256, BMFR_REPROJECT_MIN_BLOCKS) reproject_kern
         if (k + 1 < BMFR_REPROJECT_PIXELS && yn >= ylo && yn < yhi) wp_next = load_f3_stream(P.cur_positions, pix_index(P, x, yn));
         if (y < ylo) continue;
         const K1Pixel r = k1_pixel<STRIP>(P, x, y, wp);
-        // everything above only reads buffers that no kernel in flight writes; prev_pixels / accept are
-        // still being read by the previous frame's post pass until it completes
-        pdl_wait();
         const unsigned int lp = pix_index(P, x, y);
         store_f3(P.cur_noisy_acc, lp, r.new_color);
         P.cur_spp[lp] = r.spp;

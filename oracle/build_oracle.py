@@ -119,7 +119,54 @@ def build_reference(force=False):
     return REF_LIB
 
 
+CLGPU_LIB = REF_DIR / "libbmfr_clgpu.so"
+
+
+def _opencl_header(cl_text: bytes, cpp_text: str) -> str:
+    """bmfr.cl as a byte array + the feature-list build options of bmfr.cpp:63-77,195-202 — the unmodified
+    kernel source is what the OpenCL driver on the GPU box compiles."""
+    defs = dict(re.findall(r"^#define (\w+) (.*)$", _defines_from_bmfr_cpp(cpp_text), re.M))
+    out = ["// generated from /root/reference/opencl/{bmfr.cl,bmfr.cpp} by oracle/build_oracle.py — do not commit",
+           f"#define BMFR_CL_FEATURE_OPTIONS \"{defs['FEATURE_BUFFERS']}\""]
+    for name in ("BUFFER_COUNT", "FEATURES_NOT_SCALED", "FEATURES_SCALED", "LOCAL_WIDTH", "LOCAL_HEIGHT", "LOCAL_SIZE",
+                 "COMPRESSED_R", "CACHE_TMP_DATA", "ADD_REQD_WG_SIZE"):
+        out.append(f"#define BMFR_CL_{name} {defs[name]}")
+    out.append(f"static const unsigned long kBmfrClSourceLen = {len(cl_text)};")
+    out.append("static const unsigned char kBmfrClSource[] = {")
+    for i in range(0, len(cl_text), 32):
+        out.append(",".join(str(b) for b in cl_text[i:i + 32]) + ",")
+    out.append("0};")
+    return "\n".join(out) + "\n"
+
+
+def build_opencl_host(force=False):
+    """oracle/_ref/libbmfr_clgpu.so: the reference's unmodified bmfr.cl + a host that drives it through the box's
+    OpenCL ICD (oracle/cl_gpu/cl_gpu_host.c).  Needs no OpenCL at build time (the API is resolved with dlopen)."""
+    cl, cpp = REFERENCE / "bmfr.cl", REFERENCE / "bmfr.cpp"
+    host = HERE / "cl_gpu" / "cl_gpu_host.c"
+    if not cl.exists() or not cpp.exists():
+        return CLGPU_LIB if CLGPU_LIB.exists() else None   # GPU box: use what travelled
+    digest = _stamp([cl, cpp, host, HERE / "bmfr_oracle.h", Path(__file__)])
+    stamp = REF_DIR / "clgpu.sha256"
+    if not force and CLGPU_LIB.exists() and stamp.exists() and stamp.read_text() == digest:
+        return CLGPU_LIB
+    work = REF_DIR / "gen_clgpu"
+    work.mkdir(parents=True, exist_ok=True)
+    try:
+        (work / "bmfr_cl_source.gen.h").write_text(_opencl_header(cl.read_bytes(), cpp.read_text()))
+        cmd = ["gcc", "-std=gnu11", "-O2", "-fPIC", "-shared", "-Wall", "-I", str(work), "-o", str(CLGPU_LIB), str(host), "-ldl"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("gcc failed on the OpenCL host")
+        stamp.write_text(digest)
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+    return CLGPU_LIB
+
+
 if __name__ == "__main__":
     force = "--force" in sys.argv
     print("port     :", build_port(force))
     print("reference:", build_reference(force))
+    print("opencl   :", build_opencl_host(force))

@@ -1,7 +1,9 @@
-"""TEST INFRASTRUCTURE — ctypes front end of the two CPU checkers (oracle/bmfr_oracle.h).
+"""TEST INFRASTRUCTURE — ctypes front end of the checkers (oracle/bmfr_oracle.h).
 
     Oracle("port")       oracle/libbmfr_oracle.so      plain-C restatement of bmfr.cl
-    Oracle("reference")  oracle/_ref/libbmfr_clref.so  the reference's own bmfr.cl through the CL shim
+    Oracle("reference")  oracle/_ref/libbmfr_clref.so  the reference's own bmfr.cl through the CL shim (CPU)
+    Oracle("opencl")     oracle/_ref/libbmfr_clgpu.so  the reference's unmodified bmfr.cl on the box's OpenCL
+                                                       device (the B200 through NVIDIA's ICD); needs a GPU box
 """
 from __future__ import annotations
 
@@ -27,7 +29,8 @@ class OracleParams(C.Structure):
 
 
 def lib_path(kind: str) -> Path:
-    return HERE / "libbmfr_oracle.so" if kind == "port" else HERE / "_ref" / "libbmfr_clref.so"
+    return {"port": HERE / "libbmfr_oracle.so", "reference": HERE / "_ref" / "libbmfr_clref.so",
+            "opencl": HERE / "_ref" / "libbmfr_clgpu.so"}[kind]
 
 
 def available(kind: str) -> bool:
@@ -38,7 +41,7 @@ def _load(kind: str):
     path = lib_path(kind)
     if not path.exists():
         from . import build_oracle
-        (build_oracle.build_port if kind == "port" else build_oracle.build_reference)()
+        dict(port=build_oracle.build_port, reference=build_oracle.build_reference, opencl=build_oracle.build_opencl_host)[kind]()
     if not path.exists():
         raise FileNotFoundError(f"{path} is missing (kind={kind})")
     lib = C.CDLL(str(path))
@@ -54,6 +57,10 @@ def _load(kind: str):
     lib.oracle_random.restype = C.c_float
     lib.oracle_random.argtypes = [C.c_uint]
     assert lib.oracle_kind().decode() == kind
+    if kind == "opencl":
+        lib.oracle_last_error.restype = C.c_char_p
+        lib.oracle_device_name.restype = C.c_char_p
+        lib.oracle_device_name.argtypes = [C.c_void_p]
     return lib
 
 
@@ -79,7 +86,8 @@ class Oracle:
                                    threads)
         self.h = self.lib.oracle_create(C.byref(self.params))
         if not self.h:
-            raise RuntimeError("oracle_create failed")
+            why = self.lib.oracle_last_error().decode(errors="replace") if kind == "opencl" else ""
+            raise RuntimeError(f"oracle_create({kind}) failed{': ' + why if why else ''}")
 
     def close(self):
         if getattr(self, "h", None):
@@ -116,6 +124,10 @@ class Oracle:
         elif name == "noise_tile":
             a = a.reshape(9, 1024)
         return a
+
+    @property
+    def device_name(self):
+        return self.lib.oracle_device_name(self.h).decode(errors="replace") if self.kind == "opencl" else "host CPU"
 
     def stage_ms(self):
         ms = (C.c_double * 6)()

@@ -14,3 +14,8 @@ if d.get("e2e"):
     print("  e2e", round(d["e2e"]["value"], 1), d["e2e"]["unit"])
 if d.get("cpu_baseline"):
     print("  cpu", round(d["cpu_baseline"]["value"], 2), d["cpu_baseline"]["kind"], d["cpu_baseline"]["cores"], "cores")
+for k in ("in_order", "sustained"):
+    if d.get(k):
+        print(f"  {k}", round(d[k]["value"], 1), d[k].get("unit"), {a: b for a, b in d[k].items() if a in ("steps", "seconds", "ms_per_frame")})
+if d.get("parity"):
+    print("  parity", d["parity"])
