@@ -17,12 +17,8 @@
 // Compiled with --fmad=false (K1 is bit-exact against the oracle); the fit writes fmaf() explicitly.
 #include "bmfr_kernels.h"
 
-#include <cuda.h>  // CUtensorMap (the encoder is fetched through cudaGetDriverEntryPoint, no libcuda link)
-
-#include <mutex>
-#include <unordered_map>
-
 #include "bmfr_device.cuh"
+#include "bmfr_tma.cuh"
 
 // --------------------------------------------------------------------------------------------
 // K1 per image pixel.  Mirrored margin work-items of the reference recompute an in-image pixel
@@ -276,41 +272,6 @@ struct QrMaps {
     int use_tma;
 };
 
-__device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* b, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long* b) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
-}
-// Spin on an mbarrier phase.  No nanosleep back-off: the wait (the block's input tiles) is on the
-// critical path of every warp, try_wait already suspends the thread for a hardware-defined interval,
-// and a sleeping warp can oversleep the arrival by microseconds.  The loop stays inside one asm block so
-// that the compiler sees straight-line code and keeps treating the warp as converged for the shuffles
-// that follow.
-__device__ __forceinline__ void mbar_wait_hot(unsigned long long* b, unsigned int parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "MBAR_HOT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra MBAR_HOT_DONE;\n"
-        "bra MBAR_HOT_LOOP;\n"
-        "MBAR_HOT_DONE:\n"
-        "}\n" ::"r"(smem_u32(b)), "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, unsigned int bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load_tile(float* dst_smem, const CUtensorMap* map, int c0, int c1, unsigned long long* bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-            smem_u32(dst_smem)),
-        "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
-        : "memory");
-}
-
 // A block whose 32x32 pixels all lie inside the rows this context holds needs no mirroring
 // (bmfr.cl:314-316) and is fetched as three TMA tiles; the others are loaded pixel by pixel.
 __device__ __forceinline__ bool qr_block_is_interior(const KParams& P, int bx, int by) {
@@ -479,7 +440,7 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
 
     if (tid == 0) {
         mbar_init(&sh.data_full, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_fence_init();
     }
     __syncthreads();
     // before the grid dependency: the first block's normals / positions tiles (the caller's inputs)
@@ -681,57 +642,10 @@ cudaError_t launch_reproject(const KParams& P, cudaStream_t st) {
     if (is_strip(P)) return launch_pdl(!P.plain_launch, reproject_kernel<true>, grid, block, 0, st, P);
     return launch_pdl(!P.plain_launch, reproject_kernel<false>, grid, block, 0, st, P);
 }
-// ---- tensor maps of a frame --------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_tiled_fn() {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = (EncodeTiledFn)p;
-    }
-    return fn;
-}
-
-// [rows][W*3] floats, box = one 32x32-pixel tile.  Maps are cached by (pointer, W, rows): a caller
-// that cycles through a fixed set of frame buffers encodes each of them once.
+// ---- tensor maps of a frame: [rows][W*3] floats, box = one 32x32-pixel tile (bmfr_tma.cuh) ----------------
 static bool tile_map(const float* base, int W, int rows, CUtensorMap* out) {
-    struct Key {
-        const void* p; int w, r;
-        bool operator==(const Key& o) const { return p == o.p && w == o.w && r == o.r; }
-    };
-    struct Hash {
-        size_t operator()(const Key& k) const { return std::hash<const void*>()(k.p) ^ ((size_t)k.w * 1315423911u) ^ ((size_t)k.r << 20); }
-    };
-    static std::unordered_map<Key, CUtensorMap, Hash> cache;
-    static std::mutex mu;
-    EncodeTiledFn enc = encode_tiled_fn();
-    if (!enc || (W & 3) != 0 || ((uintptr_t)base & 15) != 0 || rows < 32) return false;
-    std::lock_guard<std::mutex> lock(mu);
-    const Key key{base, W, rows};
-    auto it = cache.find(key);
-    if (it != cache.end()) {
-        *out = it->second;
-        return true;
-    }
-    const cuuint64_t dims[2] = {(cuuint64_t)W * 3, (cuuint64_t)rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)W * 3 * sizeof(float)};
-    const cuuint32_t box[2] = {QR_TILE_W, 32}, elem[2] = {1, 1};
-    CUtensorMap m;
-    if (enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-        return false;
-    if (cache.size() > 4096) cache.clear();
-    cache.emplace(key, m);
-    *out = m;
-    return true;
+    if ((W & 3) != 0 || rows < 32) return false;
+    return bmfr_tensor_map_2d(base, 4, (long long)W * 3, rows, QR_TILE_W, 32, out);
 }
 
 cudaError_t launch_fit_qr(const KParams& P, cudaStream_t st) {

@@ -21,6 +21,7 @@
 #include "bmfr_kernels.h"
 
 #include "bmfr_device.cuh"
+#include "bmfr_tma.cuh"
 
 #define PT_TILE 32
 #define PT_HALO (PT_TILE + 2)
@@ -423,9 +424,383 @@ __global__ void __launch_bounds__(256, BMFR_POST_MIN_BLOCKS) post_kernel(const _
     }
 }
 
+
+// ================================================================================================
+// TMA-staged variant (the default wherever the tensor maps can be built: W % 16 == 0, at least 34 rows).
+//
+// The read-once inputs of a tile — normals, positions, albedo, previous-pixel positions, accept masks and sample
+// counts of the 34x34 pixels around it (tile + ring) — arrive as six bulk tensor copies (cp.async.bulk.tensor,
+// one elected thread, one mbarrier) instead of ~2000 L1 wavefronts of per-thread loads: an interleaved-RGB
+// image read component by component touches 3-4 cache lines per 32-bit warp load, and the ring columns one line
+// per pixel.  The copies are requested before the wait for the fit (everything they read is complete by then,
+// see the kernel), so with three CTAs per SM a tile's inputs land while its neighbours compute.  From shared
+// memory a warp reads the same values at a stride of three words, which is bank-conflict free.
+//   * Each pixel's tone-mapped YCoCg value is written over its own albedo cell (only that pixel's thread ever
+//     reads the cell), so the neighbourhood planes of phase B need no memory of their own.
+//   * What still goes through the L1 are the two 4-tap gathers.  A thread's vertically adjacent pixels share
+//     their middle tap row whenever the reprojection is locally uniform (the common case; checked per pair), so
+//     a pair loads three tap rows instead of four; all taps come from clamped addresses in one round of
+//     independent loads, issued before the weighted sum so that its arithmetic overlaps their latency.
+// Arithmetic and operation order per pixel are those of the per-thread-load variant above.
+// ================================================================================================
+#define PT_RGB_W 108  // floats per staged row of an interleaved-RGB image: 34 pixels + up to 3 floats of alignment shift
+#define PT_PP_W 72    // floats per staged row of prev_pixels: 34 float2 + 2 floats of shift
+#define PT_U8_W 64    // bytes per staged row of accept / spp: 34 + up to 15 bytes of shift
+
+struct __align__(128) PostStage {  // every TMA destination starts on a 128-byte boundary
+    float nrm[PT_HALO][PT_RGB_W]; char pad0[32];
+    float pos[PT_HALO][PT_RGB_W]; char pad1[32];
+    float alb[PT_HALO][PT_RGB_W]; char pad2[32];  // albedo, then (cell by cell) the tone-mapped colour as YCoCg
+    float pp[PT_HALO][PT_PP_W];   char pad3[64];
+    unsigned char acc[PT_HALO][PT_U8_W];
+    unsigned char spp[PT_HALO][PT_U8_W];
+    float coef[9][PT_COEF];
+    unsigned long long bar;
+};
+static_assert(sizeof(float[PT_HALO][PT_RGB_W]) % 128 == 96 && sizeof(float[PT_HALO][PT_PP_W]) % 128 == 64, "TMA destinations must stay 128-byte aligned");
+#define PT_STAGE_TX (3 * PT_HALO * PT_RGB_W * 4 + PT_HALO * PT_PP_W * 4 + 2 * PT_HALO * PT_U8_W)
+
+struct PostMaps {
+    CUtensorMap normals, positions, albedo, pp, accept, spp;
+};
+
+struct TileGeom {
+    int x0, y0;              // image coordinates of the tile's first pixel
+    int sh_rgb, sh_pp, sh_u8;  // offset of halo column 0 inside a staged row (alignment of the box start)
+};
+
+__device__ __forceinline__ f3 cell_f3(const float (*buf)[PT_RGB_W], const TileGeom& G, int hx, int hy) {
+    const float* p = &buf[hy][G.sh_rgb + 3 * hx];
+    return make_f3(p[0], p[1], p[2]);
+}
+__device__ __forceinline__ void put_cell_i(PostStage& sh, const TileGeom& G, int hx, int hy, f3 v) {
+    float* p = &sh.alb[hy][G.sh_rgb + 3 * hx];
+    p[0] = v.x; p[1] = v.y; p[2] = v.z;
+}
+// put_ycc() for the interleaved cells: the value of image pixel (x,y) also fills the out-of-image cells whose
+// nearest in-image pixel it is (nobody reads an albedo there).
+__device__ __forceinline__ void put_ycc_i(PostStage& sh, const KParams& P, const TileGeom& G, int hx, int hy, int x, int y, f3 v) {
+    put_cell_i(sh, G, hx, hy, v);
+    const int ex = (x == 0) ? -1 : (x == P.W - 1) ? 1 : 0;
+    const int ey = (y == 0) ? -1 : (y == P.H - 1) ? 1 : 0;
+    if ((ex | ey) == 0) return;
+    const bool okx = ex != 0 && (unsigned)(hx + ex) < PT_HALO, oky = ey != 0 && (unsigned)(hy + ey) < PT_HALO;
+    if (okx) put_cell_i(sh, G, hx + ex, hy, v);
+    if (oky) put_cell_i(sh, G, hx, hy + ey, v);
+    if (okx && oky) put_cell_i(sh, G, hx + ex, hy + ey, v);
+}
+__device__ __forceinline__ PixelIn load_pixel_staged(const PostStage& sh, const KParams& P, const TileGeom& G, int hx, int hy, int x, int y) {
+    PixelIn in;
+    in.lp = pix_index(P, x, y);
+    in.n = cell_f3(sh.nrm, G, hx, hy);
+    in.p = cell_f3(sh.pos, G, hx, hy);
+    in.alb = cell_f3(sh.alb, G, hx, hy);
+    in.pp = *reinterpret_cast<const float2*>(&sh.pp[hy][G.sh_pp + 2 * hx]);
+    in.accept = sh.acc[hy][G.sh_u8 + hx];
+    in.spp = sh.spp[hy][G.sh_u8 + hx];
+    return in;
+}
+// One pixel whose inputs are staged: ring pixels, and the pixels of a pair cut by a strip or image edge.
+template <bool STRIP>
+__device__ __forceinline__ bool staged_pixel(PostStage& sh, const KParams& P, const TileGeom& G, const float* cf, int hx, int hy, int x, int y,
+                                             bool store, bool own, f3& hist) {
+    const PixelIn in = load_pixel_staged(sh, P, G, hx, hy, x, y);
+    const f3 filtered = weighted_sum_px(in.n, in.p, cf);
+    const bool temporal = own && history_sample<STRIP, false>(P, in.pp, hist);
+    const f3 tone = accumulate_filtered_px<STRIP, false>(P, in.lp, filtered, in.accept, in.pp, in.spp, in.alb, store);
+    put_ycc_i(sh, P, G, hx, hy, x, y, to_ycocg(tone));
+    return temporal;
+}
+
+struct TapGeom {  // the 2x2 bilinear footprint of one pixel in the previous frame
+    int pix, piy;
+    float w[4];
+};
+__device__ __forceinline__ TapGeom tap_geom(float2 pp) {
+    TapGeom t;
+    t.pix = __float2int_rd(pp.x);
+    t.piy = __float2int_rd(pp.y);
+    const float frx = pp.x - (float)t.pix, fry = pp.y - (float)t.piy;
+    const float omx = 1.f - frx, omy = 1.f - fry;
+    t.w[0] = omx * omy; t.w[1] = frx * omy; t.w[2] = omx * fry; t.w[3] = frx * fry;
+    return t;
+}
+// accumulate_filtered_data (bmfr.cl:778-849) and the TAA history sample (bmfr.cl:884-965) of one pixel from taps that
+// are already in registers: a0 / r0 = the footprint's upper row (dx = 0, 1) of accumulated colour / TAA history, a1 / r1
+// its lower row.  Same operation order as accumulate_filtered_px() / history_sample().
+template <bool STRIP>
+__device__ __forceinline__ bool resolve_pixel(PostStage& sh, const KParams& P, const TileGeom& G, const PixelIn& in, const TapGeom& t, f3 filtered,
+                                              const f3 (&a0)[2], const f3 (&a1)[2], const f3 (&r0)[2], const f3 (&r1)[2], int hx, int hy, int x, int y,
+                                              bool own, f3& hist) {
+    f3 prev = make_f3(0.f, 0.f, 0.f);
+    float alpha = 1.f;
+    if (in.accept != 0) {
+        float total = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (in.accept & (1u << i)) {  // taps are trusted, not re-checked: bmfr.cl:801-832
+                const int sy = t.piy + (i >> 1);
+                if (STRIP && (sy < P.state2_row0 || sy >= P.state2_row1)) {
+                    *P.oob_flag = 1;
+                    continue;
+                }
+                const f3 pc = (i >> 1) ? a1[i & 1] : a0[i & 1];
+                total += t.w[i];
+                prev.x = fmaf(t.w[i], pc.x, prev.x);
+                prev.y = fmaf(t.w[i], pc.y, prev.y);
+                prev.z = fmaf(t.w[i], pc.z, prev.z);
+            }
+        }
+        if (total > 0.f) {
+            alpha = fmaxf(fast_rcp((float)in.spp), P.second_blend_alpha);  // bmfr.cl:838-839
+            const float inv = fast_rcp(total);
+            prev.x *= inv; prev.y *= inv; prev.z *= inv;
+        }
+    }
+    const float oma = 1.f - alpha;
+    const f3 accum = make_f3(fmaf(alpha, filtered.x, oma * prev.x), fmaf(alpha, filtered.y, oma * prev.y), fmaf(alpha, filtered.z, oma * prev.z));
+    store_f3(P.accum_cur, in.lp, accum);
+    const f3 tone = make_f3(tone_map_fast(in.alb.x * accum.x), tone_map_fast(in.alb.y * accum.y), tone_map_fast(in.alb.z * accum.z));
+    put_ycc_i(sh, P, G, hx, hy, x, y, to_ycocg(tone));
+
+    hist = make_f3(0.f, 0.f, 0.f);
+    if (!own || t.pix < -1 || t.piy < -1 || t.pix >= P.W || t.piy >= P.H) return false;  // bmfr.cl:884-890
+    f3 hp = make_f3(0.f, 0.f, 0.f);
+    float total = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {  // bmfr.cl:929-960
+        const int dx = i & 1, dy = i >> 1;
+        const bool ok_y = dy ? (t.piy < P.H - 1) : (t.piy >= 0);
+        const bool ok_x = dx ? (t.pix < P.W - 1) : (t.pix >= 0);
+        if (ok_x && ok_y) {
+            const int sy = t.piy + dy;
+            if (STRIP && (sy < P.state2_row0 || sy >= P.state2_row1)) {
+                *P.oob_flag = 1;
+                continue;
+            }
+            const f3 pc = dy ? r1[dx] : r0[dx];
+            hp.x = fmaf(t.w[i], pc.x, hp.x);
+            hp.y = fmaf(t.w[i], pc.y, hp.y);
+            hp.z = fmaf(t.w[i], pc.z, hp.z);
+            total += t.w[i];
+        }
+    }
+    const float inv = fast_rcp(total);  // 0 * inf = NaN on the image edge like the 0/0 of bmfr.cl:962
+    hist = to_ycocg(make_f3(hp.x * inv, hp.y * inv, hp.z * inv));
+    return true;
+}
+
+#ifndef BMFR_POST_TMA_MIN_BLOCKS
+#define BMFR_POST_TMA_MIN_BLOCKS 3
+#endif
+
+template <bool STRIP>
+__global__ void __launch_bounds__(256, BMFR_POST_TMA_MIN_BLOCKS) post_tma_kernel(const __grid_constant__ KParams P, const __grid_constant__ PostMaps M) {
+    extern __shared__ __align__(128) unsigned char post_smem[];
+    PostStage& sh = *reinterpret_cast<PostStage*>(post_smem);
+    const int bx = blockIdx.x, by = P.by0 + blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    TileGeom G;
+    G.x0 = bx * 32 - 16 + P.off_x;
+    G.y0 = by * 32 - 16 + P.off_y;
+    const int f_rgb = 3 * (G.x0 - 1), f_pp = 2 * (G.x0 - 1), b_u8 = G.x0 - 1;
+    const int c_rgb = f_rgb & ~3, c_pp = f_pp & ~3, c_u8 = b_u8 & ~15;  // 16-byte aligned box starts (floor, also for negatives)
+    G.sh_rgb = f_rgb - c_rgb; G.sh_pp = f_pp - c_pp; G.sh_u8 = b_u8 - c_u8;
+    constexpr int NW = BMFR_FEATURES * 3, NM = BMFR_FEATURES_SCALED * 2;
+
+    if (tid == 0) {
+        mbar_init(&sh.bar, 1);
+        mbar_fence_init();
+        // Requested before the grid dependency is resolved: the caller's inputs and the reprojection's outputs are
+        // complete by now — in the in-order stream this grid's CTAs start only after every CTA of the fit has passed
+        // its own wait for the reprojection (which waited for the caller's producer), in the overlapped mode the fit's
+        // event already orders this launch.  Rows / columns outside the image (or the strip) arrive as zeros.
+        const int c1 = G.y0 - 1 - P.row0;
+        mbar_expect_tx(&sh.bar, PT_STAGE_TX);
+        tma_load_tile(&sh.pp[0][0], &M.pp, c_pp, c1, &sh.bar);
+        tma_load_tile(&sh.acc[0][0], &M.accept, c_u8, c1, &sh.bar);
+        tma_load_tile(&sh.spp[0][0], &M.spp, c_u8, c1, &sh.bar);
+        tma_load_tile(&sh.nrm[0][0], &M.normals, c_rgb, c1, &sh.bar);
+        tma_load_tile(&sh.pos[0][0], &M.positions, c_rgb, c1, &sh.bar);
+        tma_load_tile(&sh.alb[0][0], &M.albedo, c_rgb, c1, &sh.bar);
+    }
+    pdl_wait();     // the fit of this frame is complete (weights, min/max)
+    pdl_trigger();  // only now, so that "this frame's fit and reprojection are complete" also holds for the successor
+
+    // coefficients of the 3x3 block neighbourhood -> shared memory (as in post_kernel)
+    for (int nb = warp; nb < 9; nb += 8) {
+        const int gx = bx + nb % 3 - 1, gy = by + nb / 3 - 1;
+        if (gx < 0 || gx >= P.blocks_x || gy < 0 || gy >= P.blocks_y) continue;
+        const size_t g = (size_t)gy * P.blocks_x + gx;
+        if (lane < NW) sh.coef[nb][(lane / 3) * 4 + lane % 3] = __ldg(P.weights + g * NW + lane);
+        if (lane < NM) sh.coef[nb][40 + lane] = __ldg(P.mins_inv + g * NM + lane);
+    }
+    __syncthreads();  // the coefficients and the barrier's initialisation are visible
+    mbar_wait_hot(&sh.bar, 0);
+
+    const int x = G.x0 + lane;
+    const bool col_ok = x >= 0 && x < P.W;
+    const int rlo = STRIP ? P.state2_row0 : 0, rhi = (STRIP ? P.state2_row1 : P.H) - 1;
+    // phase A, interior: column strip x, rows 4*warp .. 4*warp+3, two vertically adjacent pixels at a time
+    f3 hist[4];
+    unsigned int live = 0;  // bit s: pixel s is written; bit 4+s: it takes the temporal path
+#pragma unroll
+    for (int s = 0; s < 4; s += 2) {
+        const int ty = 4 * warp + s, y = G.y0 + ty;
+        hist[s] = hist[s + 1] = make_f3(0.f, 0.f, 0.f);
+        const bool v0 = col_ok && y >= P.py0 && y < P.py1, v1 = col_ok && y + 1 >= P.py0 && y + 1 < P.py1;
+        const bool own0 = y >= P.own_y0 && y < P.own_y1, own1 = y + 1 >= P.own_y0 && y + 1 < P.own_y1;
+        if (v0 && v1) {
+            const PixelIn i0 = load_pixel_staged(sh, P, G, lane + 1, ty + 1, x, y), i1 = load_pixel_staged(sh, P, G, lane + 1, ty + 2, x, y + 1);
+            bool t0 = false, t1 = false;
+            if (P.frame > 0) {
+                const TapGeom g0 = tap_geom(i0.pp), g1 = tap_geom(i1.pp);
+                // one round of independent loads from clamped addresses: tap rows R0, R1 of the upper pixel, R2 of the lower;
+                // the lower pixel's upper row is R1 when the two footprints are stacked (checked below)
+                const int cx0[2] = {min(max(g0.pix, 0), P.W - 1), min(max(g0.pix + 1, 0), P.W - 1)};
+                const int cx1[2] = {min(max(g1.pix, 0), P.W - 1), min(max(g1.pix + 1, 0), P.W - 1)};
+                const int ry0[2] = {min(max(g0.piy, rlo), rhi), min(max(g0.piy + 1, rlo), rhi)};
+                const int ry1[2] = {min(max(g1.piy, rlo), rhi), min(max(g1.piy + 1, rlo), rhi)};
+                f3 A[3][2], R[3][2];
+#pragma unroll
+                for (int dx = 0; dx < 2; ++dx) {
+                    const unsigned int l0 = pix_index(P, cx0[dx], ry0[0]), l1 = pix_index(P, cx0[dx], ry0[1]), l2 = pix_index(P, cx1[dx], ry1[1]);
+                    A[0][dx] = load_f3(P.accum_prev, l0); A[1][dx] = load_f3(P.accum_prev, l1); A[2][dx] = load_f3(P.accum_prev, l2);
+                    R[0][dx] = load_f3(P.result_prev, l0); R[1][dx] = load_f3(P.result_prev, l1); R[2][dx] = load_f3(P.result_prev, l2);
+                }
+                f3 fl0, fl1;
+                weighted_sum_px2(i0.n, i0.p, i1.n, i1.p, sh.coef[4], fl0, fl1);  // its arithmetic overlaps the gathers
+                t0 = resolve_pixel<STRIP>(sh, P, G, i0, g0, fl0, A[0], A[1], R[0], R[1], lane + 1, ty + 1, x, y, own0, hist[s]);
+                if (!(cx1[0] == cx0[0] && cx1[1] == cx0[1] && ry1[0] == ry0[1])) {  // footprints not stacked (rare): fetch the row
+#pragma unroll
+                    for (int dx = 0; dx < 2; ++dx) {
+                        const unsigned int l = pix_index(P, cx1[dx], ry1[0]);
+                        A[1][dx] = load_f3(P.accum_prev, l);
+                        R[1][dx] = load_f3(P.result_prev, l);
+                    }
+                }
+                t1 = resolve_pixel<STRIP>(sh, P, G, i1, g1, fl1, A[1], A[2], R[1], R[2], lane + 1, ty + 2, x, y + 1, own1, hist[s + 1]);
+            } else {  // frame 0: no temporal path, alpha = 1 (bmfr.cl:784, 884)
+                f3 fl0, fl1;
+                weighted_sum_px2(i0.n, i0.p, i1.n, i1.p, sh.coef[4], fl0, fl1);
+                store_f3(P.accum_cur, i0.lp, fl0);
+                store_f3(P.accum_cur, i1.lp, fl1);
+                put_ycc_i(sh, P, G, lane + 1, ty + 1, x, y,
+                          to_ycocg(make_f3(tone_map_fast(i0.alb.x * fl0.x), tone_map_fast(i0.alb.y * fl0.y), tone_map_fast(i0.alb.z * fl0.z))));
+                put_ycc_i(sh, P, G, lane + 1, ty + 2, x, y + 1,
+                          to_ycocg(make_f3(tone_map_fast(i1.alb.x * fl1.x), tone_map_fast(i1.alb.y * fl1.y), tone_map_fast(i1.alb.z * fl1.z))));
+            }
+            live |= ((own0 ? 1u : 0u) | (t0 ? 16u : 0u)) << s;
+            live |= ((own1 ? 1u : 0u) | (t1 ? 16u : 0u)) << (s + 1);
+        } else if (v0) {  // a strip or image edge cuts the pair
+            const bool t = staged_pixel<STRIP>(sh, P, G, sh.coef[4], lane + 1, ty + 1, x, y, true, own0, hist[s]);
+            live |= ((own0 ? 1u : 0u) | (t ? 16u : 0u)) << s;
+        } else if (v1) {
+            const bool t = staged_pixel<STRIP>(sh, P, G, sh.coef[4], lane + 1, ty + 2, x, y + 1, true, own1, hist[s + 1]);
+            live |= ((own1 ? 1u : 0u) | (t ? 16u : 0u)) << (s + 1);
+        }
+    }
+    // phase A, ring: 4 * 33 = 132 pixels, coefficients of the pixel's own block
+    if (tid < 4 * (PT_HALO - 1)) {
+        const int side = tid / (PT_HALO - 1), k = tid % (PT_HALO - 1);
+        int hx, hy;
+        if (side == 0) { hx = k; hy = 0; }
+        else if (side == 1) { hx = PT_HALO - 1; hy = k; }
+        else if (side == 2) { hx = PT_HALO - 1 - k; hy = PT_HALO - 1; }
+        else { hx = 0; hy = PT_HALO - 1 - k; }
+        const int rx = G.x0 + hx - 1, ry = G.y0 + hy - 1;
+        if (rx >= 0 && rx < P.W && ry >= P.py0 && ry < P.py1) {
+            const int nb = ((hy == 0) ? 0 : (hy == PT_HALO - 1) ? 6 : 3) + ((hx == 0) ? 0 : (hx == PT_HALO - 1) ? 2 : 1);
+            f3 unused;
+            staged_pixel<STRIP>(sh, P, G, sh.coef[nb], hx, hy, rx, ry, false, false, unused);
+        }
+    }
+    __syncthreads();
+
+    // phase B: clamp the history samples to the neighbourhood box, component by component (bmfr.cl:893-920, 967-969).  Halo
+    // rows 4*warp .. 4*warp+5 cover the 3x3 neighbourhoods of the strip; this thread's column is lane+1.
+    f3 mine[4];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float ctr[6], rmin[6], rmax[6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            const float* row = &sh.alb[4 * warp + r][G.sh_rgb + c];
+            const float l = row[3 * lane], m = row[3 * lane + 3], rr = row[3 * lane + 6];
+            ctr[r] = m;
+            rmin[r] = fminf(fminf(l, m), rr);
+            rmax[r] = fmaxf(fmaxf(l, m), rr);
+        }
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const float min_box = fminf(fminf(rmin[s], rmin[s + 1]), rmin[s + 2]);
+            const float max_box = fmaxf(fmaxf(rmax[s], rmax[s + 1]), rmax[s + 2]);
+            const float min_cross = fminf(fminf(ctr[s], rmin[s + 1]), ctr[s + 2]);
+            const float max_cross = fmaxf(fmaxf(ctr[s], rmax[s + 1]), ctr[s + 2]);
+            const float lo = (min_box + min_cross) * 0.5f, hi = (max_box + max_cross) * 0.5f;
+            float& h = (c == 0) ? hist[s].x : (c == 1) ? hist[s].y : hist[s].z;
+            h = fminf(fmaxf(h, lo), hi);
+            float& m = (c == 0) ? mine[s].x : (c == 1) ? mine[s].y : mine[s].z;
+            m = ctr[s + 1];
+        }
+    }
+    // blend and store (bmfr.cl:971-973)
+    const float a = P.taa_blend_alpha, oma = 1.f - P.taa_blend_alpha;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        if (!(live & (1u << s))) continue;
+        const unsigned int lp = pix_index(P, x, G.y0 + 4 * warp + s);
+        f3 out = from_ycocg(mine[s]);  // this pixel's tone-mapped colour
+        if (live & (16u << s)) {
+            const f3 pr = from_ycocg(hist[s]);
+            out = make_f3(fmaf(a, out.x, oma * pr.x), fmaf(a, out.y, oma * pr.y), fmaf(a, out.z, oma * pr.z));
+        }
+        store_f3(P.result_cur, lp, out);
+        if (P.user_out) store_f3(P.user_out, lp, out);
+    }
+}
+
+#ifndef BMFR_POST_TMA
+#define BMFR_POST_TMA 1
+#endif
+
+// Tensor maps of the frame's six read-once inputs, or false when the TMA path cannot be used (then post_kernel runs).
+static bool post_maps(const KParams& P, PostMaps* M) {
+    const int rows = P.row1 - P.row0;
+    if (!BMFR_POST_TMA || (P.W & 15) != 0 || rows < PT_HALO || P.W * 3 < PT_RGB_W) return false;
+    return bmfr_tensor_map_2d(P.cur_normals, 4, (long long)P.W * 3, rows, PT_RGB_W, PT_HALO, &M->normals) &&
+           bmfr_tensor_map_2d(P.cur_positions, 4, (long long)P.W * 3, rows, PT_RGB_W, PT_HALO, &M->positions) &&
+           bmfr_tensor_map_2d(P.albedo, 4, (long long)P.W * 3, rows, PT_RGB_W, PT_HALO, &M->albedo) &&
+           bmfr_tensor_map_2d(P.prev_pixels, 4, (long long)P.W * 2, rows, PT_PP_W, PT_HALO, &M->pp) &&
+           bmfr_tensor_map_2d(P.accept, 1, (long long)P.W, rows, PT_U8_W, PT_HALO, &M->accept) &&
+           bmfr_tensor_map_2d(P.cur_spp, 1, (long long)P.W, rows, PT_U8_W, PT_HALO, &M->spp);
+}
+
+static cudaError_t post_tma_configure() {
+    static bool done[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    if (!done[dev]) {
+        e = cudaFuncSetAttribute(post_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PostStage));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(post_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PostStage));
+        if (e != cudaSuccess) return e;
+        done[dev] = true;
+    }
+    return cudaSuccess;
+}
+
 cudaError_t launch_post(const KParams& P, cudaStream_t st) {
     const dim3 grid(P.blocks_x, P.by1 - P.by0);
     const bool strip = P.row0 != 0 || P.row1 != P.H;
+    PostMaps M;
+    if (post_maps(P, &M)) {
+        cudaError_t e = post_tma_configure();
+        if (e != cudaSuccess) return e;
+        if (strip) return launch_pdl(!P.plain_launch, post_tma_kernel<true>, grid, dim3(256), sizeof(PostStage), st, P, M);
+        return launch_pdl(!P.plain_launch, post_tma_kernel<false>, grid, dim3(256), sizeof(PostStage), st, P, M);
+    }
     const uintptr_t bits = (uintptr_t)P.cur_normals | (uintptr_t)P.cur_positions | (uintptr_t)P.albedo | (uintptr_t)P.accum_prev |
                            (uintptr_t)P.accum_cur | (uintptr_t)P.result_prev | (uintptr_t)P.result_cur | (uintptr_t)P.user_out;
     // measured on B200 (profiles/): the 64+32-bit form costs 38% more instructions (selects, address

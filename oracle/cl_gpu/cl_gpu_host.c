@@ -231,9 +231,16 @@ oracle_state* oracle_create(const oracle_params* p) {
                  p->noise_amount, (double)p->blend_alpha, (double)p->second_blend_alpha, (double)p->taa_blend_alpha,
                  (double)p->position_limit_squared, (double)p->normal_limit_squared, BMFR_CL_COMPRESSED_R, BMFR_CL_CACHE_TMP_DATA,
                  BMFR_CL_ADD_REQD_WG_SIZE, BMFR_CL_LOCAL_SIZE, p->tmp_half ? 1 : 0);
-        const char* src = (const char*)kBmfrClSource;
-        const size_t len = kBmfrClSourceLen;
-        s->prog = cl.CreateProgramWithSource(s->ctx, 1, &src, &len, &err);
+        /* BMFR_OPENCL_STRICT_FP=1: the same source under the arithmetic convention of the CPU checkers (no FMA
+         * contraction, correctly rounded division and square root) — a pragma in front of the unmodified file and one
+         * standard build option; the default is the vendor compiler's own latitude, like a stock run of the reference. */
+        const char* strict = getenv("BMFR_OPENCL_STRICT_FP");
+        const int strict_fp = strict && strict[0] == '1';
+        const char* pragma = "#pragma OPENCL FP_CONTRACT OFF\n";
+        const char* srcs[2] = {pragma, (const char*)kBmfrClSource};
+        const size_t lens[2] = {strlen(pragma), kBmfrClSourceLen};
+        if (strict_fp) strncat(opts, " -cl-fp32-correctly-rounded-divide-sqrt", sizeof(opts) - strlen(opts) - 1);
+        s->prog = cl.CreateProgramWithSource(s->ctx, strict_fp ? 2 : 1, strict_fp ? srcs : srcs + 1, strict_fp ? lens : lens + 1, &err);
         CL_TRY(err, "clCreateProgramWithSource");
         err = cl.BuildProgram(s->prog, 1, &s->dev, opts, NULL, NULL);
         if (err != CL_SUCCESS) {

@@ -1,0 +1,66 @@
+"""The reference's UNMODIFIED bmfr.cl, compiled by the box's own OpenCL driver and run on the B200
+(oracle/_ref/libbmfr_clgpu.so, built from /root/reference by oracle/build_oracle.py), as a second, independent pin:
+
+  * against the CPU port oracle under the same arithmetic convention (FP_CONTRACT OFF, correctly rounded division):
+    the integer / exact buffers must be bit-identical — the restatement and the vendor-compiled original agree;
+  * against the CUDA path in the vendor compiler's default mode (FMA contraction allowed by OpenCL C): colour within
+    the north star's tolerance, integer buffers within a handful of pixels (last-bit differences of prev_pixels).
+Skipped where no OpenCL platform can be opened (this container; a box without the NVIDIA ICD)."""
+import os
+
+import numpy as np
+import pytest
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _opencl(w, h, strict):
+    from bmfr_b200 import synth
+    from oracle import oracle as orc
+    if not orc.available("opencl"):
+        pytest.skip("oracle/_ref/libbmfr_clgpu.so was not built (needs /root/reference at build time)")
+    os.environ["BMFR_OPENCL_STRICT_FP"] = "1" if strict else "0"
+    pl, nl = synth.limits()
+    try:
+        return orc.Oracle("opencl", w, h, position_limit_squared=pl, normal_limit_squared=nl)
+    except RuntimeError as e:
+        pytest.skip(f"no usable OpenCL platform here: {e}")
+
+
+def test_vendor_compiled_reference_kernels_match_the_port_bitwise_under_the_same_fp_convention():
+    from bmfr_b200 import synth
+    from oracle.oracle import Oracle
+    w, h, frames = 416, 250, 10
+    cl = _opencl(w, h, strict=True)
+    pl, nl = synth.limits()
+    port = Oracle("port", w, h, position_limit_squared=pl, normal_limit_squared=nl)
+    for fr in util.sequence(w, h, frames):
+        cl.frame(*fr)
+        port.frame(*fr)
+        for k in ("spp", "accept", "prev_pixels", "noisy_acc", "mins_maxs"):
+            a, b = cl.buffer(k), port.buffer(k)
+            assert util.bits_equal(a, b), f"frame {fr[0]}: {k} of the OpenCL run differs from the port in {(a != b).sum()} elements"
+        for k in ("filtered", "accum", "result"):
+            util.assert_colour_close(cl.buffer(k), port.buffer(k), f"frame {fr[0]} {k}")
+    cl.close(); port.close()
+
+
+def test_cuda_path_matches_the_reference_kernels_on_the_same_gpu():
+    from bmfr_b200 import Denoiser
+    w, h, frames = 1280, 720, 12
+    cl = _opencl(w, h, strict=False)
+    with Denoiser(w, h, mode="fused") as d:
+        for fr in util.sequence(w, h, frames):
+            cl.frame(*fr)
+            d.denoise_frame_host(*fr)
+            for k in ("spp", "accept"):
+                bad = int((cl.buffer(k) != d.read(k)).sum())
+                assert bad <= 1e-4 * w * h, f"frame {fr[0]}: {k} differs in {bad} pixels"
+            assert util.floats_equal_mod_zero_sign(cl.buffer("mins_maxs"), d.read("mins_maxs"))
+            dp = np.abs(cl.buffer("prev_pixels") - d.read("prev_pixels"))
+            assert float(dp.max()) <= 1e-3, f"frame {fr[0]}: prev_pixels differ by {dp.max()} pixels"
+            for k in ("accum", "result"):
+                util.assert_colour_close(d.read(k), cl.buffer(k), f"frame {fr[0]} {k}")
+    cl.close()
