@@ -35,7 +35,7 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 FRAMES = 60
-FUSED_KERNELS = ("reproject_kernel", "fit_qr_kernel", "post_kernel")
+FUSED_KERNELS = ("reproject_kernel", "fit_gram_kernel", "post_tma_kernel")  # replaced by the context's own list at run time
 SINGLE_GPU_WORKLOAD = (1920, 1080)
 
 
@@ -73,7 +73,9 @@ def algorithmic_bytes(w, h):
         # FUSED: tmp_data / filtered / tone_mapped never reach HBM
         "reproject_kernel": 95 * P,                        # K1 per image pixel: 73 B in, 22 B out
         "fit_qr_kernel": 36 * P + 216 * NB,                # normals, positions, accumulated colour once; weights + min/max out
+        "fit_gram_kernel": 36 * P + 216 * NB,
         "post_kernel": 94 * P + 168 * NB,                  # K3+K4+K5
+        "post_tma_kernel": 94 * P + 168 * NB,
     }
 
 
@@ -344,7 +346,7 @@ def run_single_gpu(args):
 
     def timed(overlap_frames, steps, warmup, sample_clocks=False):
         """-> (total ms of `steps` steps, kernel launches, clock summary): CUDA events on the context's stream."""
-        d = Denoiser(w, h, mode=args.mode, stream=sp, overlap_frames=overlap_frames)
+        d = Denoiser(w, h, mode=args.mode, stream=sp, overlap_frames=overlap_frames, fit=args.fit)
         for _ in range(warmup):
             run_sequence(d)
         torch.cuda.synchronize()
@@ -389,7 +391,7 @@ def run_single_gpu(args):
     alg = algorithmic_bytes(w, h)
     kernels = {}
     for mode in ([args.mode] if not args.all_modes else ["fused", "staged"]):
-        dp = Denoiser(w, h, mode=mode, stream=sp, profile=True)
+        dp = Denoiser(w, h, mode=mode, stream=sp, profile=True, fit=args.fit)
         run_sequence(dp)
         run_sequence(dp)
         dp.sync()
@@ -398,8 +400,8 @@ def run_single_gpu(args):
             ms = np.array([[dp.stage_ms(f)[k] for k in ("accum_noisy", "fitter", "weighted_sum", "accum_filtered", "taa", "total")]
                            for f in range(1, FRAMES)])  # frame 0 excluded like bmfr.cpp:392-397
         else:
-            names = list(FUSED_KERNELS)
-            ms = np.array([[dp.fused_kernel_ms(f)[k] for k in FUSED_KERNELS] + [0.0, 0.0, dp.stage_ms(f)["total"]]
+            names = list(dp.fused_kernels)
+            ms = np.array([[dp.fused_kernel_ms(f)[k] for k in names] + [0.0, 0.0, dp.stage_ms(f)["total"]]
                            for f in range(1, FRAMES)])
         mean = ms.mean(axis=0)
         for i, name in enumerate(names):
@@ -409,7 +411,8 @@ def run_single_gpu(args):
                                  "algorithmic_bytes": alg[name], "achieved_gbs": gbs, "frac": gbs / peak}
         kernels[f"total_{mode}"] = {"ms": float(mean[5])}
         dp.close()
-    own = [k for k in kernels if not k.startswith("total_") and (k in FUSED_KERNELS) == (args.mode == "fused")]
+    staged_names = ("accumulate_noisy_data", "fitter", "weighted_sum", "accumulate_filtered_data", "taa")
+    own = [k for k in kernels if not k.startswith("total_") and (k not in staged_names) == (args.mode == "fused")]
     dom = max(own, key=lambda k: kernels[k]["ms"])
     # DRAM traffic of the same kernel from the committed ncu --set full capture (profiles/), per launch
     traffic, traffic_src = None, None
@@ -433,7 +436,7 @@ def run_single_gpu(args):
         host_out = torch.empty((2, h, w, 3), dtype=torch.float32, pin_memory=True)
         torch.cuda.synchronize()
         hin, hout = host_in.numpy(), host_out.numpy()
-        dh = Denoiser(w, h, mode=args.mode, overlap_frames=overlap)
+        dh = Denoiser(w, h, mode=args.mode, overlap_frames=overlap, fit=args.fit)
 
         def run_host_sequence():
             for f in range(FRAMES):
@@ -468,7 +471,7 @@ def run_single_gpu(args):
         "ms_per_step": ms_per_step, "ms_per_frame": ms_per_step / FRAMES, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(w, h, 1),
-        "run": {"mode": args.mode, "overlap_frames": overlap},
+        "run": {"mode": args.mode, "overlap_frames": overlap, "fit_method": args.fit},
         "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
         "in_order": in_order, "sustained": sustained, "reference_gpu": reference_gpu(w, h),
         "clocks": clock_summary,
@@ -497,6 +500,7 @@ def main():
     ap.add_argument("--overlap", type=int, default=1, choices=[0, 1],
                     help="bmfr_params.overlap_frames of the timed contexts: 1 = consecutive frames overlap on the device "
                          "(three event-linked streams), 0 = one in-order stream")
+    ap.add_argument("--fit", default="gram", choices=["gram", "tsqr"], help="bmfr_params.fit_method of the FUSED contexts")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

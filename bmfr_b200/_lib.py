@@ -33,7 +33,8 @@ class Params(C.Structure):
                 ("taa_blend_alpha", C.c_float), ("position_limit_squared", C.c_float),
                 ("normal_limit_squared", C.c_float), ("tmp_half", C.c_int), ("profile", C.c_int),
                 ("strip_y0", C.c_int), ("strip_y1", C.c_int), ("halo_rows", C.c_int), ("stream", C.c_void_p),
-                ("reference_order", C.c_int), ("overlap_frames", C.c_int)]
+                ("reference_order", C.c_int), ("overlap_frames", C.c_int), ("fit_method", C.c_int),
+                ("halo_timeout_ms", C.c_int)]
 
 
 class Geometry(C.Structure):

@@ -245,7 +245,7 @@ struct QrLoop2<PAIRS, BMFR_FEATURES> {
 #define QR_ROWS 8
 #define QR_TRI (BMFR_FEATURES * BMFR_BUFFER_COUNT)  // floats of one triangle, stored as a full 10x13
 #ifndef QR_MINE
-#define QR_MINE 64  // blocks a CTA collects before it runs level 2 on them (normally: all its blocks, once, at the end)
+#define QR_MINE 128  // blocks a CTA collects before it runs level 2 on them (normally: all its blocks, once, at the end)
 #endif
 #define QR_TRI_G 136  // floats per level-1 triangle in global memory: four of them are a whole number of 128-byte lines
 // One 32x32-pixel tile of an interleaved-RGB image is 96 floats per row.  TMA wants the innermost
@@ -281,7 +281,8 @@ __device__ __forceinline__ bool qr_block_is_interior(const KParams& P, int bx, i
 // One thread: arm the barrier and start the three tile loads of block (bx, by).  part 0: everything;
 // part 1: the caller's inputs only (normals, positions — they do not depend on this frame's
 // reprojection and can be requested before the grid dependency is resolved); part 2: the colour tile.
-__device__ __forceinline__ void qr_prefetch(const KParams& P, const QrMaps& M, QrShared& sh, int bx, int by, int part = 0) {
+template <class SH>
+__device__ __forceinline__ void qr_prefetch(const KParams& P, const QrMaps& M, SH& sh, int bx, int by, int part = 0) {
     const int c0 = ((bx * 32 - 16 + P.off_x) * 3) & ~3, c1 = by * 32 - 16 + P.off_y - P.row0;
     if (part != 2) {
         mbar_expect_tx(&sh.data_full, 3 * QR_TILE_BYTES);
@@ -294,7 +295,8 @@ __device__ __forceinline__ void qr_prefetch(const KParams& P, const QrMaps& M, Q
 __device__ __forceinline__ int qr_block_of_draw(int i, int nblocks, int blocks_x);
 // One thread: draw the block of iteration it + 1 (sh.blk holds the block index, or >= nblocks when the
 // frame is exhausted), start its tile loads or arrive plainly.
-__device__ __forceinline__ void qr_draw_next(const KParams& P, const QrMaps& M, QrShared& sh, int it, int nblocks, int stride) {
+template <class SH>
+__device__ __forceinline__ void qr_draw_next(const KParams& P, const QrMaps& M, SH& sh, int it, int nblocks, int stride) {
     const int draw = stride + atomicAdd(P.block_counter, 1);
     const int nl = draw < nblocks ? qr_block_of_draw(draw, nblocks, P.blocks_x) : nblocks;
     sh.blk[(it + 1) & 1] = nl;
@@ -617,7 +619,7 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
         if (warp == 0) QR_STAMP(0, it, 4);
         if (warp == 0) QR_STAMP(0, it, 5);
         QrLoop2<ROWS / 2, 0>::run(a2, P.tri + ((size_t)local * QR_COMPUTE_WARPS + warp) * QR_TRI_G, lane);
-        if (++mine == QR_MINE) {  // the list is full (more than 64 blocks per CTA: no frame up to 8K on a B200 gets here)
+        if (++mine == QR_MINE) {  // the list is full (more than 128 blocks per CTA: no frame up to 8K on a B200 gets here)
             qr_solve_mine(P, sh, mine, warp, lane);
             mine = 0;
         }
@@ -628,6 +630,375 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
     // ---------------- level 2 + back-substitution of this CTA's blocks ----------------
     qr_solve_mine(P, sh, mine, warp, lane);
     if (warp == 0) QR_CTA_STAMP(2);
+}
+
+
+// ================================================================================================
+// fit_gram_kernel: the fit through the block's Gram matrix (the default; fit_qr_kernel above stays selectable with
+// bmfr_params.fit_method = BMFR_FIT_TSQR).
+//
+// The two-level QR above spends a third of its issue slots on ten DEPENDENT warp all-reductions per block (one per
+// reflector) and another third on the eliminations; profiles/r01_v7_ncu_full.md has it issue-bound.  The least-squares
+// solution only needs R^T R = A^T A and A^T y, i.e. the 13x13 Gram matrix G of [1 | features | colour]: 90 independent
+// dot products per thread (FFMA2 on packed row pairs, no dependence between them), ONE reduction over the warp for all
+// of them (a shared-memory transpose: 90 stores, 24 128-bit loads and a pairwise add tree per lane), the four warps'
+// totals and the Cholesky factorisation + substitutions in fp64 by half a warp per block after the CTA's last block.
+//
+// Accuracy: the normal equations square the condition number (about 500 here: planar geometry makes positions and
+// their squares collinear up to the 1e-2 regularisation noise, bmfr.cl:623-627), so the columns are first centred on
+// the block means (the constant column stays in G, so centring by a rounded mean is still exact algebra; the
+// intercept is recovered after the solve).  Measured on synth-v1 blocks against an fp64 least-squares fit, worst
+// relative error of the fitted colour: reference-order fp32 Householder 1.3e-5, this scheme 1.9e-5, uncentred fp32
+// normal equations 3e-4 (scripts/gram_accuracy.py); parity tests hold the frame to 1e-3 / 60 dB as before.
+// ================================================================================================
+#define GR_ENTRIES 90   // upper triangle of the 13x13 Gram matrix without G_00 (= 1024): row 0 first (12 column sums), then rows 1..12
+#define GR_STRIDE 104   // floats per (block, warp) in the scratch: 90 Gram entries, 12 block means (warp 0), padding; <= QR_TRI_G
+#define GR_RED_W 36     // floats per row of the transpose buffer: 16-byte aligned rows, conflict-free 128-bit reads
+
+struct GramShared {
+    float stage[3][32][QR_TILE_W];                  // TMA landing zone (as QrShared)
+    float red[QR_COMPUTE_WARPS][32][GR_RED_W];      // per-warp transpose buffer: [entry of the chunk][lane]; between blocks the solver's fp64 workspace
+    float part[2][QR_COMPUTE_WARPS][24];            // per warp: min (6), max (6), column sums (12); double-buffered by block parity
+    int mine[QR_MINE];
+    unsigned long long data_full;
+    int blk[2];
+};
+static_assert(GR_STRIDE <= QR_TRI_G, "the Gram scratch reuses the triangle scratch allocation");
+static_assert(2 * BMFR_BUFFER_COUNT * BMFR_FEATURES * sizeof(double) <= 32 * GR_RED_W * sizeof(float), "solver workspace fits the transpose buffer");
+
+// Sum of the 32 floats of one row of the transpose buffer (eight 128-bit loads, pairwise tree).
+__device__ __forceinline__ float gram_row_sum(const float* __restrict__ row) {
+    const float4* r4 = reinterpret_cast<const float4*>(row);
+    float t[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float4 v = r4[i];
+        t[i] = (v.x + v.y) + (v.z + v.w);
+    }
+    return ((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7]));
+}
+
+__device__ __forceinline__ double shfl_f64(double v, int src) {
+    const int lo = __shfl_sync(0xffffffffu, __double2loint(v), src), hi = __shfl_sync(0xffffffffu, __double2hiint(v), src);
+    return __hiloint2double(hi, lo);
+}
+// 1 / sqrt(d) and 1 / d in fp64 from the fp32 approximation and two Newton steps (no DSQRT / DDIV sequences: this code
+// runs once per block and is fetched cold, so it is written for size)
+__device__ __forceinline__ double rsqrt_f64(double d) {
+    double r = (double)rsqrt_approx((float)d);
+    r = r * (1.5 - 0.5 * d * r * r);
+    r = r * (1.5 - 0.5 * d * r * r);
+    return r;
+}
+__device__ __forceinline__ double rcp_f64(double d) {
+    double r = (double)rcp_approx((float)d);
+    r = r * (2.0 - d * r);
+    r = r * (2.0 - d * r);
+    return r;
+}
+// index of G_ij (i <= j, (i, j) != (0, 0)) in the scratch order
+__device__ __forceinline__ int gram_index(int i, int j) {
+    return i == 0 ? j - 1 : 12 + (i - 1) * 12 - ((i - 1) * (i - 2)) / 2 + (j - i);
+}
+
+// Cholesky + substitutions for the block `blk` by half a warp (hb = lane & 16): lane i < 13 owns row i of G.
+__device__ __forceinline__ void gram_solve(const KParams& P, double* __restrict__ fin, int blk, int lane) {
+    constexpr int NC = BMFR_BUFFER_COUNT, NF = BMFR_FEATURES;
+    const int i = lane & 15, hb = lane & 16;
+    const bool owner = blk >= 0 && i < NC;
+    const float* sc = P.tri + (size_t)(blk >= 0 ? blk : 0) * QR_COMPUTE_WARPS * QR_TRI_G;
+    double g[NC];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+        double v = 0.0;
+        if (owner && (i | j) != 0) {
+            const int e = gram_index(i < j ? i : j, i < j ? j : i);
+#pragma unroll
+            for (int w = 0; w < QR_COMPUTE_WARPS; ++w) v += (double)__ldcg(sc + w * QR_TRI_G + e);  // the four warps, in fp64, fixed order
+        }
+        g[j] = v;
+    }
+    if (i == 0) g[0] = (double)BMFR_BLOCK_PIXELS;
+    if (!owner) {  // idle lanes: an identity row keeps every operation below finite
+#pragma unroll
+        for (int j = 0; j < NC; ++j) g[j] = (j == i) ? 1.0 : 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < NF; ++k) {  // right-looking Cholesky on the first ten pivots; rows 10..12 become L^-1 [A^T y]
+        const double dk = shfl_f64(g[k], hb + k);
+        const double lik = g[k] * rsqrt_f64(dk);  // L_ik (lane k: sqrt(G_kk))
+        g[k] = lik;
+#pragma unroll
+        for (int j = k + 1; j < NC; ++j) g[j] -= lik * shfl_f64(lik, hb + j);
+    }
+    // L (rows 0..9) and z (rows 10..12) -> shared memory, then one colour channel per lane solves L^T x = z (bmfr.cl:659-692)
+    if (owner) {
+#pragma unroll
+        for (int k = 0; k < NF; ++k) fin[i * NF + k] = g[k];
+    }
+    __syncwarp();
+    if (blk >= 0 && i < 3) {
+        double x[NF];
+#pragma unroll
+        for (int r = NF - 1; r >= 0; --r) {
+            double a = fin[(NF + i) * NF + r];
+#pragma unroll
+            for (int jj = r + 1; jj < NF; ++jj) a -= fin[jj * NF + r] * x[jj];
+            x[r] = a * rcp_f64(fin[r * NF + r]);
+        }
+        // the columns were centred: y - m_y = x_0 + sum_j x_j (a_j - m_j)  ->  intercept of the uncentred model
+        const float* mean = sc + GR_ENTRIES;  // block means of columns 1..12, written by warp 0
+        double w0 = x[0] + (double)__ldcg(mean + (NF - 1) + i);
+#pragma unroll
+        for (int jj = 1; jj < NF; ++jj) w0 -= x[jj] * (double)__ldcg(mean + jj - 1);
+        float* wout = P.weights + (size_t)(P.by0 * P.blocks_x + blk) * NF * 3 + i;  // bmfr.cl:694-699
+        wout[0] = (float)w0;
+#pragma unroll
+        for (int r = 1; r < NF; ++r) wout[r * 3] = (float)x[r];
+    }
+    __syncwarp();  // fin is reused by this half-warp's next block
+}
+
+template <class SH>
+__device__ __noinline__ void gram_solve_mine(const KParams& P, SH& sh, int count, int warp, int lane) {
+    __syncthreads();  // this CTA's scratch stores and the list are complete
+    // fp64 workspace of the two half-warps: this warp's own transpose buffer (idle between blocks)
+    double* fin = reinterpret_cast<double*>(&sh.red[warp][0][0]) + (size_t)(lane >> 4) * (BMFR_BUFFER_COUNT * BMFR_FEATURES);
+    for (int t = 0; t * 8 + warp < count; ++t) {
+        const int e = t * 8 + (lane >> 4) * 4 + warp;
+        gram_solve(P, fin, e < count ? sh.mine[e] : -1, lane);
+    }
+    __syncthreads();
+}
+
+#ifndef BMFR_GRAM_MIN_BLOCKS
+#define BMFR_GRAM_MIN_BLOCKS 3
+#endif
+
+template <bool STRIP>
+__global__ void __launch_bounds__(QR_THREADS, BMFR_GRAM_MIN_BLOCKS) fit_gram_kernel(const __grid_constant__ KParams P,
+                                                                                    const __grid_constant__ QrMaps M) {
+    extern __shared__ __align__(128) unsigned char qr_smem[];
+    GramShared& sh = *reinterpret_cast<GramShared*>(qr_smem);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform (see fit_qr_kernel)
+    constexpr int NSC = BMFR_FEATURES_SCALED, NNS = BMFR_FEATURES_NOT_SCALED, ROWS = QR_ROWS, NCOL = BMFR_BUFFER_COUNT - 1;
+    const int nblocks = P.blocks_x * (P.by1 - P.by0);
+    const int stride = gridDim.x;
+    if ((int)blockIdx.x >= nblocks) return;
+    const int first = qr_block_of_draw(blockIdx.x, nblocks, P.blocks_x);
+
+    if (tid == 0) {
+        mbar_init(&sh.data_full, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const bool first_by_tma = M.use_tma && qr_block_is_interior(P, first % P.blocks_x, P.by0 + first / P.blocks_x);
+    if (tid == 0 && first_by_tma) qr_prefetch(P, M, sh, first % P.blocks_x, P.by0 + first / P.blocks_x, 1);
+    pdl_wait();     // the reprojection of this frame is complete (accumulated colour, noise tile, block counter)
+    pdl_trigger();  // after the wait, so that completion of everything before this grid is transitive for the post pass
+    if (tid == 0) {
+        sh.blk[0] = first;
+        if (first_by_tma) qr_prefetch(P, M, sh, first % P.blocks_x, P.by0 + first / P.blocks_x, 2);
+        else mbar_arrive(&sh.data_full);
+    }
+    float* const red = &sh.red[warp][0][0];
+    int mine = 0;
+    for (int it = 0;; ++it) {
+        mbar_wait_hot(&sh.data_full, it & 1);
+        const int local = sh.blk[it & 1];
+        if (local >= nblocks) break;
+        const int group = P.by0 * P.blocks_x + local;
+        const int bx = local % P.blocks_x, by = P.by0 + local / P.blocks_x;
+
+        // a[s][c-1] = column c of row (x_in = lane, y_in = 8 warp + s): the 12 non-constant K1 values (bmfr.cl:448-453), NaN -> 0
+        float a[ROWS][NCOL];
+        if (M.use_tma && qr_block_is_interior(P, bx, by)) {
+            const int col = (((bx * 32 - 16 + P.off_x) * 3) & 3) + lane * 3;
+            bool bad = false;
+#pragma unroll
+            for (int s = 0; s < ROWS; ++s) {
+                float v[9];
+#pragma unroll
+                for (int c = 0; c < 9; ++c) {
+                    v[c] = sh.stage[c / 3][warp * ROWS + s][col + c % 3];
+                    bad = bad || (v[c] != v[c]);
+                }
+                a[s][0] = v[0]; a[s][1] = v[1]; a[s][2] = v[2];
+                a[s][3] = v[3]; a[s][4] = v[4]; a[s][5] = v[5];
+                a[s][6] = v[3] * v[3]; a[s][7] = v[4] * v[4]; a[s][8] = v[5] * v[5];
+                a[s][9] = v[6]; a[s][10] = v[7]; a[s][11] = v[8];
+            }
+            if (__any_sync(0xffffffffu, bad)) {
+#pragma unroll
+                for (int s = 0; s < ROWS; ++s)
+#pragma unroll
+                    for (int c = 0; c < NCOL; ++c) a[s][c] = scrub_nan(a[s][c]);
+            }
+        } else {  // border block: mirrored pixel by pixel
+            const int x = mirror_index(bx * 32 + lane - 16 + P.off_x, P.W);
+#pragma unroll
+            for (int s = 0; s < ROWS; ++s) {
+                const int y = mirror_index(by * 32 + warp * ROWS + s - 16 + P.off_y, P.H);
+                if (STRIP && (y < P.row0 || y >= P.row1)) {
+                    *P.oob_flag = 1;
+#pragma unroll
+                    for (int c = 0; c < NCOL; ++c) a[s][c] = 0.f;
+                    continue;
+                }
+                const unsigned int lp = pix_index(P, x, y);
+                const f3 n = load_f3(P.cur_normals, lp);
+                const f3 p = load_f3(P.cur_positions, lp);
+                const f3 col = load_f3(P.cur_noisy_acc, lp);
+                const float px = scrub_nan(p.x), py = scrub_nan(p.y), pz = scrub_nan(p.z);
+                a[s][0] = scrub_nan(n.x); a[s][1] = scrub_nan(n.y); a[s][2] = scrub_nan(n.z);
+                a[s][3] = px; a[s][4] = py; a[s][5] = pz;
+                a[s][6] = px * px; a[s][7] = py * py; a[s][8] = pz * pz;
+                a[s][9] = scrub_nan(col.x); a[s][10] = scrub_nan(col.y); a[s][11] = scrub_nan(col.z);
+            }
+        }
+
+        // (i) block min / max of the six scaled features (bmfr.cl:511-535; exact, order-free) and, for the centring, the
+        // sums of all twelve columns: per thread, then over the warp (redux for the extrema, the transpose buffer for the sums)
+        float* part = &sh.part[it & 1][warp][0];
+#pragma unroll
+        for (int f = 0; f < NSC; ++f) {
+            const int c = NNS - 1 + f;
+            float lo = a[0][c], hi = a[0][c];
+#pragma unroll
+            for (int s = 1; s < ROWS; ++s) {
+                lo = fminf(lo, a[s][c]);
+                hi = fmaxf(hi, a[s][c]);
+            }
+            const float wlo = warp_min(lo), whi = warp_max(hi);
+            if (lane == 0) {
+                part[f] = wlo;
+                part[NSC + f] = whi;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < NCOL; ++c) {
+            float t = (a[0][c] + a[1][c]) + (a[2][c] + a[3][c]);
+            t += (a[4][c] + a[5][c]) + (a[6][c] + a[7][c]);
+            red[c * GR_RED_W + lane] = t;
+        }
+        __syncwarp();
+        if (lane < NCOL) part[2 * NSC + lane] = gram_row_sum(red + lane * GR_RED_W);
+        __syncthreads();  // the per-warp extrema and sums are visible, and every thread is done with the stage
+        bool late_draw = false;
+        if (tid == 0) {
+            sh.mine[mine] = local;
+            if (BMFR_QR_LAZY_DIV > 0)
+                late_draw = nblocks - stride - *(volatile int*)P.block_counter < stride / (BMFR_QR_LAZY_DIV > 0 ? BMFR_QR_LAZY_DIV : 1);
+            if (!late_draw) qr_draw_next(P, M, sh, it, nblocks, stride);
+        }
+        // every warp finishes the reductions itself: lane f < 6 owns scaled feature f, lane c < 12 the mean of column c + 1
+        float mn[NSC], inv[NSC], mean[NCOL];
+        {
+            const int f = lane < NSC ? lane : 0, c = lane < NCOL ? lane : 0;
+            float lo = sh.part[it & 1][0][f], hi = sh.part[it & 1][0][NSC + f], sum = sh.part[it & 1][0][2 * NSC + c];
+#pragma unroll
+            for (int w = 1; w < QR_COMPUTE_WARPS; ++w) {
+                lo = fminf(lo, sh.part[it & 1][w][f]);
+                hi = fmaxf(hi, sh.part[it & 1][w][NSC + f]);
+                sum += sh.part[it & 1][w][2 * NSC + c];
+            }
+            const float iv = scale_factor(lo, hi);
+            if (warp == 0 && lane < NSC) {
+                P.mins_maxs[(size_t)group * 2 * NSC + 2 * lane] = lo;
+                P.mins_maxs[(size_t)group * 2 * NSC + 2 * lane + 1] = hi;
+                P.mins_inv[(size_t)group * 2 * NSC + 2 * lane] = lo;
+                P.mins_inv[(size_t)group * 2 * NSC + 2 * lane + 1] = iv;
+            }
+            const float m_raw = sum * (1.0f / BMFR_BLOCK_PIXELS);
+#pragma unroll
+            for (int k = 0; k < NSC; ++k) {
+                mn[k] = __shfl_sync(0xffffffffu, lo, k);
+                inv[k] = __shfl_sync(0xffffffffu, iv, k);
+            }
+#pragma unroll
+            for (int k = 0; k < NCOL; ++k) mean[k] = __shfl_sync(0xffffffffu, m_raw, k);
+#pragma unroll
+            for (int k = 0; k < NSC; ++k) mean[NNS - 1 + k] = (mean[NNS - 1 + k] - mn[k]) * inv[k];  // mean of the scaled column (the noise averages to ~0)
+        }
+        // the solver needs the means to recover the intercept: one per lane, in the scratch of warp 0
+        if (warp == 0) {
+            float mv = 0.f;
+#pragma unroll
+            for (int k = 0; k < NCOL; ++k) mv = (lane == k) ? mean[k] : mv;
+            if (lane < NCOL) P.tri[((size_t)local * QR_COMPUTE_WARPS) * QR_TRI_G + GR_ENTRIES + lane] = mv;
+        }
+
+        // scale (bmfr.cl:538-541), first-touch noise on columns 1..9 (bmfr.cl:623-627; from the tile's fp32 rounding as in
+        // fit_qr_kernel), centre.  a2[h][c]: rows (2h, 2h+1) packed.
+        float2 a2[ROWS / 2][NCOL];
+#pragma unroll
+        for (int h = 0; h < ROWS / 2; ++h)
+#pragma unroll
+            for (int c = 0; c < NCOL; ++c) a2[h][c] = make_float2(a[2 * h][c], a[2 * h + 1][c]);
+#pragma unroll
+        for (int f = 0; f < NSC; ++f) {
+            const float2 mn2 = dup2(mn[f]), inv2 = dup2(inv[f]);
+#pragma unroll
+            for (int h = 0; h < ROWS / 2; ++h) a2[h][NNS - 1 + f] = fmul2(fsub2(a2[h][NNS - 1 + f], mn2), inv2);
+        }
+        {
+            const float4* nz4 = reinterpret_cast<const float4*>(P.noise_f) + (size_t)warp * (BMFR_FEATURES - 1) * 2 * 32 + lane;
+#pragma unroll
+            for (int c = 0; c < BMFR_FEATURES - 1; ++c) {
+                const float2 m2 = dup2(mean[c]);
+#pragma unroll
+                for (int q = 0; q < ROWS / 4; ++q) {
+                    const float4 nz = __ldg(nz4 + (c * 2 + q) * 32);
+                    a2[2 * q][c] = fsub2(fadd2(a2[2 * q][c], make_float2(nz.x, nz.y)), m2);
+                    a2[2 * q + 1][c] = fsub2(fadd2(a2[2 * q + 1][c], make_float2(nz.z, nz.w)), m2);
+                }
+            }
+#pragma unroll
+            for (int c = BMFR_FEATURES - 1; c < NCOL; ++c) {
+                const float2 m2 = dup2(mean[c]);
+#pragma unroll
+                for (int h = 0; h < ROWS / 2; ++h) a2[h][c] = fsub2(a2[h][c], m2);
+            }
+        }
+
+        // (ii) this thread's share of the 90 Gram entries, reduced over the warp 32 entries at a time through the transpose
+        // buffer; the warp's totals go to the scratch (global memory, stays in L2) for the solver
+        float* const out = P.tri + ((size_t)local * QR_COMPUTE_WARPS + warp) * QR_TRI_G;
+        auto flush = [&](int chunk, int count) {
+            __syncwarp();
+            if (lane < count) out[chunk * 32 + lane] = gram_row_sum(red + lane * GR_RED_W);
+            __syncwarp();
+        };
+        int e = 0;  // compile-time after unrolling
+#pragma unroll
+        for (int j = 0; j < NCOL; ++j) {  // row 0: column sums
+            float2 acc = a2[0][j];
+#pragma unroll
+            for (int h = 1; h < ROWS / 2; ++h) acc = fadd2(acc, a2[h][j]);
+            red[(e & 31) * GR_RED_W + lane] = acc.x + acc.y;
+            if ((++e & 31) == 0) flush(e / 32 - 1, 32);
+        }
+#pragma unroll
+        for (int i = 0; i < NCOL; ++i) {
+#pragma unroll
+            for (int j = i; j < NCOL; ++j) {
+                float2 acc = fmul2(a2[0][i], a2[0][j]);
+#pragma unroll
+                for (int h = 1; h < ROWS / 2; ++h) acc = ffma2(a2[h][i], a2[h][j], acc);
+                red[(e & 31) * GR_RED_W + lane] = acc.x + acc.y;
+                if ((++e & 31) == 0) flush(e / 32 - 1, 32);
+            }
+        }
+        flush(GR_ENTRIES / 32, GR_ENTRIES % 32);
+
+        if (++mine == QR_MINE) {
+            gram_solve_mine(P, sh, mine, warp, lane);
+            mine = 0;
+        }
+        if (tid == 0 && late_draw) qr_draw_next(P, M, sh, it, nblocks, stride);
+    }
+    gram_solve_mine(P, sh, mine, warp, lane);
 }
 
 // --------------------------------------------------------------------------------------------
@@ -648,10 +1019,9 @@ static bool tile_map(const float* base, int W, int rows, CUtensorMap* out) {
     return bmfr_tensor_map_2d(base, 4, (long long)W * 3, rows, QR_TILE_W, 32, out);
 }
 
-cudaError_t launch_fit_qr(const KParams& P, cudaStream_t st) {
-    // persistent grid: as many CTAs as stay resident (sm_count * BMFR_QR_MIN_BLOCKS), never more than blocks
-    static int sm_counts[64] = {};  // resident CTAs per device; 0 = this device has not been configured yet
-    const int smem = (int)sizeof(QrShared);
+// Persistent grid of a fit kernel: as many CTAs as stay resident (never more than blocks), configured once per device.
+template <class K0, class K1>
+static cudaError_t fit_grid(K0 k_plain, K1 k_strip, int smem, int max_per_sm, int* sm_counts, int* grid_out) {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
@@ -659,18 +1029,29 @@ cudaError_t launch_fit_qr(const KParams& P, cudaStream_t st) {
     if (sm_counts[dev] == 0) {
         int n = 0;
         e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(fit_qr_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(fit_qr_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        // persistent grid: sized from what the device really keeps resident, not from the launch bounds
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_plain, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_strip, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        // sized from what the device really keeps resident, not from the launch bounds
         int per_sm = 0;
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fit_qr_kernel<true>, QR_THREADS, (size_t)smem);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_strip, QR_THREADS, (size_t)smem);
         if (e != cudaSuccess) return e;
         if (per_sm < 1) return cudaErrorLaunchOutOfResources;
-        if (per_sm > BMFR_QR_MIN_BLOCKS) per_sm = BMFR_QR_MIN_BLOCKS;
+        if (per_sm > max_per_sm) per_sm = max_per_sm;
         sm_counts[dev] = n * per_sm;
     }
+    *grid_out = sm_counts[dev];
+    return cudaSuccess;
+}
+
+cudaError_t launch_fit_qr(const KParams& P, cudaStream_t st) {
+    static int counts_qr[64] = {}, counts_gram[64] = {};  // resident CTAs per device; 0 = not configured yet
+    const bool gram = P.fit_method == BMFR_FIT_GRAM;
+    const int smem = gram ? (int)sizeof(GramShared) : (int)sizeof(QrShared);
+    int grid = 0;
+    cudaError_t e = gram ? fit_grid(fit_gram_kernel<false>, fit_gram_kernel<true>, smem, BMFR_GRAM_MIN_BLOCKS, counts_gram, &grid)
+                         : fit_grid(fit_qr_kernel<false>, fit_qr_kernel<true>, smem, BMFR_QR_MIN_BLOCKS, counts_qr, &grid);
+    if (e != cudaSuccess) return e;
     const int nblocks = P.blocks_x * (P.by1 - P.by0);
-    int grid = sm_counts[dev];
     if (grid > nblocks) grid = nblocks;
     if (grid < 1) return cudaSuccess;
     QrMaps M;
@@ -678,6 +1059,10 @@ cudaError_t launch_fit_qr(const KParams& P, cudaStream_t st) {
     const int rows = P.row1 - P.row0;
     M.use_tma = tile_map(P.cur_normals, P.W, rows, &M.normals) && tile_map(P.cur_positions, P.W, rows, &M.positions) &&
                 tile_map(P.cur_noisy_acc, P.W, rows, &M.colour);
+    if (gram) {
+        if (is_strip(P)) return launch_pdl(!P.plain_launch, fit_gram_kernel<true>, dim3(grid), dim3(QR_THREADS), (size_t)smem, st, P, M);
+        return launch_pdl(!P.plain_launch, fit_gram_kernel<false>, dim3(grid), dim3(QR_THREADS), (size_t)smem, st, P, M);
+    }
     if (is_strip(P)) return launch_pdl(!P.plain_launch, fit_qr_kernel<true>, dim3(grid), dim3(QR_THREADS), (size_t)smem, st, P, M);
     return launch_pdl(!P.plain_launch, fit_qr_kernel<false>, dim3(grid), dim3(QR_THREADS), (size_t)smem, st, P, M);
 }

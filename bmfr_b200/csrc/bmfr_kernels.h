@@ -57,6 +57,7 @@ struct KParams {
     int* oob_flag;                // set when a gather needed a row outside [row0,row1)
     int* block_counter;           // FUSED fit: dynamic block schedule, reset by the reprojection (STAGED: noise-tile kernel) of the frame
     float* tri;                   // FUSED fit: level-1 triangles between the two levels of the TSQR, blocks x 4 x 136 floats
+    int fit_method;               // host side only: BMFR_FIT_GRAM / BMFR_FIT_TSQR (which FUSED fit kernel launch_fit_qr starts)
     int plain_launch;             // host side only: launch the FUSED kernels without programmatic stream serialization
 };
 

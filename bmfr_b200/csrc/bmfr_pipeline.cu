@@ -263,6 +263,9 @@ int bmfr_create(const bmfr_params* params, bmfr_ctx** out_ctx) {
     }
     if (p.mode != BMFR_MODE_STAGED && p.mode != BMFR_MODE_FUSED)
         return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_create: unknown mode %d", p.mode);
+    if (p.fit_method != BMFR_FIT_GRAM && p.fit_method != BMFR_FIT_TSQR)
+        return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_create: unknown fit_method %d", p.fit_method);
+    if (p.halo_timeout_ms < 0) return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_create: negative halo_timeout_ms");
     if ((p.tmp_half != 0 || p.reference_order != 0) && p.mode != BMFR_MODE_STAGED)
         return bmfr_set_error(BMFR_ERR_UNSUPPORTED,
                               "bmfr_create: tmp_half / reference_order are the STAGED compatibility path (the FUSED fit is fp32 and "
@@ -439,6 +442,7 @@ static void fill_params(bmfr_ctx* c, KParams& P, int frame, const float* d_albed
     P.result_prev = c->result.previous(); P.result_cur = c->result.current();
     P.user_out = d_out; P.oob_flag = c->d_oob; P.block_counter = odd ? c->ov.counter : c->d_oob + 1;
     P.plain_launch = c->ov.on ? 1 : 0;
+    P.fit_method = c->prm.fit_method;
     P.tri = c->tri;
 }
 

@@ -14,7 +14,14 @@ import numpy as np
 from . import _lib
 from ._lib import BUF, MODE_FUSED, MODE_STAGED, STAGES, BmfrError, Geometry, HaloPlan, Params
 
-FUSED_KERNELS = ("reproject_kernel", "fit_qr_kernel", "post_kernel")
+FUSED_KERNELS = ("reproject_kernel", "fit_gram_kernel", "post_tma_kernel")  # the default FUSED path, in launch order
+
+
+def fused_kernel_names(width, fit="gram"):
+    """The three kernels a FUSED frame launches: the fit by bmfr_params.fit_method, the post pass by whether its tensor
+    maps can be built for this width (csrc/bmfr_post.cu: W % 16 == 0)."""
+    return ("reproject_kernel", "fit_gram_kernel" if fit == "gram" else "fit_qr_kernel",
+            "post_tma_kernel" if width % 16 == 0 else "post_kernel")
 
 _BUF_DTYPE = dict(noisy_acc=np.float32, spp=np.uint8, prev_pixels=np.float32, accept=np.uint8, tmp_data=np.float32,
                   weights=np.float32, mins_maxs=np.float32, filtered=np.float32, accum=np.float32,
@@ -35,7 +42,8 @@ def block_offset(frame: int):
 class Denoiser:
     def __init__(self, width, height, *, mode="fused", device=0, profile=False, stream=0, strip=None, halo_rows=0,
                  position_limit_squared=None, normal_limit_squared=None, noise_amount=None, blend_alpha=None,
-                 second_blend_alpha=None, taa_blend_alpha=None, tmp_half=0, reference_order=0, overlap_frames=0):
+                 second_blend_alpha=None, taa_blend_alpha=None, tmp_half=0, reference_order=0, overlap_frames=0, fit="gram",
+                 halo_timeout_ms=0):
         self.lib = _lib.load()
         p = Params()
         self.lib.bmfr_default_params(C.byref(p), width, height)
@@ -44,6 +52,8 @@ class Denoiser:
         p.profile = int(profile)
         p.tmp_half, p.reference_order = int(tmp_half), int(reference_order)
         p.overlap_frames = int(overlap_frames)
+        p.fit_method = {"gram": 0, "tsqr": 1}[fit]
+        p.halo_timeout_ms = int(halo_timeout_ms)
         p.stream = C.c_void_p(stream or None)
         if strip is not None:
             p.strip_y0, p.strip_y1, p.halo_rows = int(strip[0]), int(strip[1]), int(halo_rows)
@@ -53,6 +63,7 @@ class Denoiser:
             if v is not None:
                 setattr(p, k, v)
         self.params, self.mode = p, mode
+        self.fused_kernels = fused_kernel_names(width, fit)
         self._h = C.c_void_p()
         _lib.check(self.lib.bmfr_create(C.byref(p), C.byref(self._h)))
         g = Geometry()
@@ -143,7 +154,7 @@ class Denoiser:
         """Device time of reproject / fit_qr / post for one frame (FUSED, profile=True)."""
         ms = (C.c_float * 3)()
         _lib.check(self.lib.bmfr_get_fused_kernel_ms(self._h, frame, ms))
-        return dict(zip(FUSED_KERNELS, ms))
+        return dict(zip(self.fused_kernels, ms))
 
     @property
     def kernel_launches(self):

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define BMFR_B200_ABI_VERSION 3
+#define BMFR_B200_ABI_VERSION 4
 
 /* Compile-time constants of the reference that are not tunable (bmfr.cpp:102-118). */
 #define BMFR_BLOCK_EDGE 32          /* BLOCK_EDGE_LENGTH, bmfr.cpp:104 */
@@ -92,7 +92,19 @@ typedef struct bmfr_params {
      * state rows (which needs the in-order stream) cannot be combined with it.
      * 0 (default): one in-order stream, the reference's queue semantics (bmfr.cpp:191). */
     int overlap_frames;
+    /* FUSED only: how the per-block least-squares problem of the fitter (bmfr.cl:546-699) is solved.
+     *   BMFR_FIT_GRAM (0, default): centred normal equations — one 13x13 Gram matrix per block accumulated in fp32,
+     *       reduced once, Cholesky + substitutions in fp64;
+     *   BMFR_FIT_TSQR (1): two-level Householder/MGS QR in fp32 registers (the round-1 kernel; ten dependent warp
+     *       reductions per block).
+     * Both are held to the same colour tolerance against the reference's Householder QR. */
+    int fit_method;
+    /* Strip contexts with a connected neighbour: how long a kernel waits on the device for the neighbour's halo rows
+     * before it gives up (the context then fails: every later call returns BMFR_ERR_SEQUENCE).  0 = 10000 ms. */
+    int halo_timeout_ms;
 } bmfr_params;
+
+enum { BMFR_FIT_GRAM = 0, BMFR_FIT_TSQR = 1 };
 
 typedef struct bmfr_ctx bmfr_ctx;
 

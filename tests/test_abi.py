@@ -23,7 +23,7 @@ def test_header_symbols_are_exported(lib):
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/bmfr_b200.h but not exported"
     assert set(names) == set(_lib.SYMBOLS), "ctypes table and header disagree"
-    assert lib.bmfr_abi_version() == 3
+    assert lib.bmfr_abi_version() == 4
 
 
 def test_block_offsets_table():

@@ -113,6 +113,13 @@ def test_720p_matches_oracle():
     _check_frames(cuda, ref, False)
 
 
+def test_tsqr_fit_still_matches_oracle():
+    """bmfr_params.fit_method = BMFR_FIT_TSQR: the round-1 two-level QR fit stays selectable and in tolerance."""
+    ref = util.run_oracle("port", 416, 250, 8, keep=KEEP_FUSED)
+    cuda = util.run_cuda(416, 250, 8, mode="fused", keep=KEEP_FUSED, fit="tsqr")
+    _check_frames(cuda, ref, False)
+
+
 def test_staged_and_fused_agree():
     """The two kernel structures share the reprojection code (bit-identical K1 outputs, block min/max
     and noise tile); the fit and the post-fit passes are separate implementations held to the colour

@@ -1,8 +1,10 @@
 """The reference's UNMODIFIED bmfr.cl, compiled by the box's own OpenCL driver and run on the B200
 (oracle/_ref/libbmfr_clgpu.so, built from /root/reference by oracle/build_oracle.py), as a second, independent pin:
 
-  * against the CPU port oracle under the same arithmetic convention (FP_CONTRACT OFF, correctly rounded division):
-    the integer / exact buffers must be bit-identical — the restatement and the vendor-compiled original agree;
+  * against the CPU port oracle with FP_CONTRACT OFF and correctly rounded division: frame 0 and the block min/max bit
+    for bit; from frame 1 on within last-bit differences of prev_pixels — the vendor's dot() built-in (the camera
+    projection, bmfr.cl:343-347) is fused whatever the pragma says, which OpenCL C allows — hence integer buffers equal
+    up to 1e-4 of the pixels and colour within the north star's tolerance;
   * against the CUDA path in the vendor compiler's default mode (FMA contraction allowed by OpenCL C): colour within
     the north star's tolerance, integer buffers within a handful of pixels (last-bit differences of prev_pixels).
 Skipped where no OpenCL platform can be opened (this container; a box without the NVIDIA ICD)."""
@@ -29,7 +31,7 @@ def _opencl(w, h, strict):
         pytest.skip(f"no usable OpenCL platform here: {e}")
 
 
-def test_vendor_compiled_reference_kernels_match_the_port_bitwise_under_the_same_fp_convention():
+def test_vendor_compiled_reference_kernels_match_the_port():
     from bmfr_b200 import synth
     from oracle.oracle import Oracle
     w, h, frames = 416, 250, 10
@@ -39,10 +41,16 @@ def test_vendor_compiled_reference_kernels_match_the_port_bitwise_under_the_same
     for fr in util.sequence(w, h, frames):
         cl.frame(*fr)
         port.frame(*fr)
-        for k in ("spp", "accept", "prev_pixels", "noisy_acc", "mins_maxs"):
-            a, b = cl.buffer(k), port.buffer(k)
-            assert util.bits_equal(a, b), f"frame {fr[0]}: {k} of the OpenCL run differs from the port in {(a != b).sum()} elements"
-        for k in ("filtered", "accum", "result"):
+        assert util.bits_equal(cl.buffer("mins_maxs"), port.buffer("mins_maxs")), f"frame {fr[0]}: mins_maxs"
+        if fr[0] == 0:  # no reprojection yet: everything up to the fit's inputs is exact arithmetic
+            for k in ("spp", "accept", "prev_pixels", "noisy_acc"):
+                assert util.bits_equal(cl.buffer(k), port.buffer(k)), f"frame 0: {k} of the OpenCL run differs from the port"
+        for k in ("spp", "accept"):
+            bad = int((cl.buffer(k) != port.buffer(k)).sum())
+            assert bad <= 1e-4 * w * h, f"frame {fr[0]}: {k} differs in {bad} pixels"
+        dp = np.abs(cl.buffer("prev_pixels") - port.buffer("prev_pixels"))
+        assert float(dp.max()) <= 1e-3, f"frame {fr[0]}: prev_pixels differ by {dp.max()} pixels"
+        for k in ("noisy_acc", "filtered", "accum", "result"):
             util.assert_colour_close(cl.buffer(k), port.buffer(k), f"frame {fr[0]} {k}")
     cl.close(); port.close()
 
