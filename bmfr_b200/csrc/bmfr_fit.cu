@@ -272,18 +272,30 @@ struct QrMaps {
     int use_tma;
 };
 
-// A block whose 32x32 pixels all lie inside the rows this context holds needs no mirroring
-// (bmfr.cl:314-316) and is fetched as three TMA tiles; the others are loaded pixel by pixel.
-__device__ __forceinline__ bool qr_block_is_interior(const KParams& P, int bx, int by) {
-    const int x0 = bx * 32 - 16 + P.off_x, y0 = by * 32 - 16 + P.off_y;
-    return x0 >= 0 && x0 + 32 <= P.W && y0 >= P.row0 && y0 + 32 <= P.row1;
+// The 32 source indices mirror(x0 .. x0 + 31) of a block edge (bmfr.cl:209-216, 314-316) always lie within 32 consecutive
+// pixels: a block inside the image is its own source, a block that straddles or lies beyond a border folds back onto
+// the 32 pixels next to that border.  Returns the first pixel of that 32-pixel window (inside [0, size - 32]).
+__device__ __forceinline__ int qr_box_origin(int x0, int size) {
+    int lo;
+    if (x0 >= 0 && x0 + 32 <= size) lo = x0;
+    else if (x0 < 0) lo = (x0 + 31 >= 0) ? 0 : -x0 - 32;
+    else lo = (x0 < size) ? min(x0, 2 * size - x0 - 32) : 2 * size - x0 - 32;
+    return min(max(lo, 0), size - 32);
+}
+// Every block is therefore fetched as three 32x32-pixel TMA tiles at (ox, oy) and read with mirrored indices — as
+// long as this context holds the window's rows; otherwise (a strip edge) the block is loaded pixel by pixel, which
+// also reports rows the strip does not hold.
+__device__ __forceinline__ bool qr_block_box(const KParams& P, int bx, int by, int& ox, int& oy) {
+    ox = qr_box_origin(bx * 32 - 16 + P.off_x, P.W);
+    oy = qr_box_origin(by * 32 - 16 + P.off_y, P.H);
+    return oy >= P.row0 && oy + 32 <= P.row1;
 }
 // One thread: arm the barrier and start the three tile loads of block (bx, by).  part 0: everything;
 // part 1: the caller's inputs only (normals, positions — they do not depend on this frame's
 // reprojection and can be requested before the grid dependency is resolved); part 2: the colour tile.
 template <class SH>
-__device__ __forceinline__ void qr_prefetch(const KParams& P, const QrMaps& M, SH& sh, int bx, int by, int part = 0) {
-    const int c0 = ((bx * 32 - 16 + P.off_x) * 3) & ~3, c1 = by * 32 - 16 + P.off_y - P.row0;
+__device__ __forceinline__ void qr_prefetch(const KParams& P, const QrMaps& M, SH& sh, int ox, int oy, int part = 0) {
+    const int c0 = (ox * 3) & ~3, c1 = oy - P.row0;
     if (part != 2) {
         mbar_expect_tx(&sh.data_full, 3 * QR_TILE_BYTES);
         tma_load_tile(&sh.stage[0][0][0], &M.normals, c0, c1, &sh.data_full);
@@ -300,8 +312,8 @@ __device__ __forceinline__ void qr_draw_next(const KParams& P, const QrMaps& M, 
     const int draw = stride + atomicAdd(P.block_counter, 1);
     const int nl = draw < nblocks ? qr_block_of_draw(draw, nblocks, P.blocks_x) : nblocks;
     sh.blk[(it + 1) & 1] = nl;
-    const int nbx = nl % P.blocks_x, nby = P.by0 + nl / P.blocks_x;
-    if (nl < nblocks && M.use_tma && qr_block_is_interior(P, nbx, nby)) qr_prefetch(P, M, sh, nbx, nby);
+    int ox, oy;
+    if (nl < nblocks && qr_block_box(P, nl % P.blocks_x, P.by0 + nl / P.blocks_x, ox, oy) && M.use_tma) qr_prefetch(P, M, sh, ox, oy);
     else mbar_arrive(&sh.data_full);
 }
 
@@ -446,8 +458,9 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
     }
     __syncthreads();
     // before the grid dependency: the first block's normals / positions tiles (the caller's inputs)
-    const bool first_by_tma = M.use_tma && qr_block_is_interior(P, first % P.blocks_x, P.by0 + first / P.blocks_x);
-    if (tid == 0 && first_by_tma) qr_prefetch(P, M, sh, first % P.blocks_x, P.by0 + first / P.blocks_x, 1);
+    int fox, foy;
+    const bool first_by_tma = qr_block_box(P, first % P.blocks_x, P.by0 + first / P.blocks_x, fox, foy) && M.use_tma;
+    if (tid == 0 && first_by_tma) qr_prefetch(P, M, sh, fox, foy, 1);
     pdl_wait();     // the reprojection of this frame is complete (accumulated colour, noise tile, block counter)
     pdl_trigger();  // after the wait, so that completion of everything before this grid is transitive for the post pass
 
@@ -465,9 +478,8 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
     // data_full completes once per iteration: thread 0 arrives on it after publishing sh.blk[it & 1],
     // with the TMA byte count when the block is fetched as tiles, plainly otherwise.
     if (tid == 0) {
-        const int bx0 = first % P.blocks_x, by0 = P.by0 + first / P.blocks_x;
         sh.blk[0] = first;
-        if (first_by_tma) qr_prefetch(P, M, sh, bx0, by0, 2);
+        if (first_by_tma) qr_prefetch(P, M, sh, fox, foy, 2);
         else mbar_arrive(&sh.data_full);
     }
     int it = 0;
@@ -483,8 +495,11 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
         // (bmfr.cl:448-453), NaN -> 0 (bmfr.cl:468-469)
         float a[ROWS][BMFR_BUFFER_COUNT - 1];
         if (warp == 0) QR_STAMP(0, it, 0);
-        if (M.use_tma && qr_block_is_interior(P, bx, by)) {
-            const int col = (((bx * 32 - 16 + P.off_x) * 3) & 3) + lane * 3;  // shift + this lane's pixel
+        int ox, oy;
+        if (qr_block_box(P, bx, by, ox, oy) && M.use_tma) {
+            // this lane's pixel column and this thread's eight rows inside the 32x32 window, mirrored like bmfr.cl:314-316
+            const int col = ((ox * 3) & 3) + 3 * (mirror_index(bx * 32 + lane - 16 + P.off_x, P.W) - ox);
+            const int y_in = by * 32 + warp * ROWS - 16 + P.off_y;  // shift + this lane's pixel
             // NaN -> 0 costs two instructions per value; NaNs are rare, so the values are only probed
             // (one predicate-accumulating compare each) and scrubbed in a cold path if any lane saw one
             // (a squared NaN is a NaN and scrubs to 0 = the square of the scrubbed value).
@@ -494,7 +509,7 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
                 float v[9];
 #pragma unroll
                 for (int c = 0; c < 9; ++c) {
-                    v[c] = sh.stage[c / 3][warp * ROWS + s][col + c % 3];
+                    v[c] = sh.stage[c / 3][mirror_index(y_in + s, P.H) - oy][col + c % 3];
                     bad = bad || (v[c] != v[c]);
                 }
                 a[s][0] = v[0]; a[s][1] = v[1]; a[s][2] = v[2];
@@ -508,7 +523,7 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
 #pragma unroll
                     for (int c = 0; c < BMFR_BUFFER_COUNT - 1; ++c) a[s][c] = scrub_nan(a[s][c]);
             }
-        } else {  // border block: mirrored pixel by pixel
+        } else {  // the window leaves the rows this strip holds (or no tensor maps): pixel by pixel
             const int x = mirror_index(bx * 32 + lane - 16 + P.off_x, P.W);
 #pragma unroll
             for (int s = 0; s < ROWS; ++s) {
@@ -793,13 +808,14 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_GRAM_MIN_BLOCKS) fit_gram_ker
         mbar_fence_init();
     }
     __syncthreads();
-    const bool first_by_tma = M.use_tma && qr_block_is_interior(P, first % P.blocks_x, P.by0 + first / P.blocks_x);
-    if (tid == 0 && first_by_tma) qr_prefetch(P, M, sh, first % P.blocks_x, P.by0 + first / P.blocks_x, 1);
+    int fox, foy;
+    const bool first_by_tma = qr_block_box(P, first % P.blocks_x, P.by0 + first / P.blocks_x, fox, foy) && M.use_tma;
+    if (tid == 0 && first_by_tma) qr_prefetch(P, M, sh, fox, foy, 1);
     pdl_wait();     // the reprojection of this frame is complete (accumulated colour, noise tile, block counter)
     pdl_trigger();  // after the wait, so that completion of everything before this grid is transitive for the post pass
     if (tid == 0) {
         sh.blk[0] = first;
-        if (first_by_tma) qr_prefetch(P, M, sh, first % P.blocks_x, P.by0 + first / P.blocks_x, 2);
+        if (first_by_tma) qr_prefetch(P, M, sh, fox, foy, 2);
         else mbar_arrive(&sh.data_full);
     }
     float* const red = &sh.red[warp][0][0];
@@ -813,15 +829,18 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_GRAM_MIN_BLOCKS) fit_gram_ker
 
         // a[s][c-1] = column c of row (x_in = lane, y_in = 8 warp + s): the 12 non-constant K1 values (bmfr.cl:448-453), NaN -> 0
         float a[ROWS][NCOL];
-        if (M.use_tma && qr_block_is_interior(P, bx, by)) {
-            const int col = (((bx * 32 - 16 + P.off_x) * 3) & 3) + lane * 3;
+        int ox, oy;
+        if (qr_block_box(P, bx, by, ox, oy) && M.use_tma) {
+            // this lane's pixel column and this thread's eight rows inside the 32x32 window, mirrored like bmfr.cl:314-316
+            const int col = ((ox * 3) & 3) + 3 * (mirror_index(bx * 32 + lane - 16 + P.off_x, P.W) - ox);
+            const int y_in = by * 32 + warp * ROWS - 16 + P.off_y;
             bool bad = false;
 #pragma unroll
             for (int s = 0; s < ROWS; ++s) {
                 float v[9];
 #pragma unroll
                 for (int c = 0; c < 9; ++c) {
-                    v[c] = sh.stage[c / 3][warp * ROWS + s][col + c % 3];
+                    v[c] = sh.stage[c / 3][mirror_index(y_in + s, P.H) - oy][col + c % 3];
                     bad = bad || (v[c] != v[c]);
                 }
                 a[s][0] = v[0]; a[s][1] = v[1]; a[s][2] = v[2];
@@ -835,7 +854,7 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_GRAM_MIN_BLOCKS) fit_gram_ker
 #pragma unroll
                     for (int c = 0; c < NCOL; ++c) a[s][c] = scrub_nan(a[s][c]);
             }
-        } else {  // border block: mirrored pixel by pixel
+        } else {  // the window leaves the rows this strip holds (or no tensor maps): pixel by pixel
             const int x = mirror_index(bx * 32 + lane - 16 + P.off_x, P.W);
 #pragma unroll
             for (int s = 0; s < ROWS; ++s) {

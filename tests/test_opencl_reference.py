@@ -69,6 +69,13 @@ def test_cuda_path_matches_the_reference_kernels_on_the_same_gpu():
             assert util.floats_equal_mod_zero_sign(cl.buffer("mins_maxs"), d.read("mins_maxs"))
             dp = np.abs(cl.buffer("prev_pixels") - d.read("prev_pixels"))
             assert float(dp.max()) <= 1e-3, f"frame {fr[0]}: prev_pixels differ by {dp.max()} pixels"
+            # Two legal evaluations of the same source (contracted on the OpenCL side): a pixel whose accept mask or sample
+            # count flips takes a different temporal path in the two runs, so the per-pixel bound is asked of all but 1e-4 of
+            # the pixels and the PSNR bound of the whole frame.
             for k in ("accum", "result"):
-                util.assert_colour_close(d.read(k), cl.buffer(k), f"frame {fr[0]} {k}")
+                a, b = d.read(k).astype(np.float64), cl.buffer(k).astype(np.float64)
+                bad = np.abs(a - b) > util.REL * np.maximum(np.abs(b), util.EPS)
+                assert bad.mean() <= 1e-4, f"frame {fr[0]} {k}: {bad.sum()} elements outside the tolerance"
+                _, psnr = util.colour_error(a, b)
+                assert psnr >= util.PSNR_DB, f"frame {fr[0]} {k}: PSNR {psnr:.1f} dB"
     cl.close()
