@@ -669,17 +669,26 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
 #define GR_ENTRIES 90   // upper triangle of the 13x13 Gram matrix without G_00 (= 1024): row 0 first (12 column sums), then rows 1..12
 #define GR_STRIDE 104   // floats per (block, warp) in the scratch: 90 Gram entries, 12 block means (warp 0), padding; <= QR_TRI_G
 #define GR_RED_W 36     // floats per row of the transpose buffer: 16-byte aligned rows, conflict-free 128-bit reads
+#ifndef BMFR_GRAM_MIN_BLOCKS
+#define BMFR_GRAM_MIN_BLOCKS 4
+#endif
+// Gram entries reduced per round trip through the transpose buffer.  32 uses every lane for the row sums; 16 halves the
+// buffer (2.3 KB per warp), which is what lets a fourth CTA fit on an SM next to the 38 KB landing zones.
+#ifndef GR_CHUNK
+#define GR_CHUNK (BMFR_GRAM_MIN_BLOCKS >= 4 ? 16 : 32)
+#endif
 
 struct GramShared {
     float stage[3][32][QR_TILE_W];                  // TMA landing zone (as QrShared)
-    float red[QR_COMPUTE_WARPS][32][GR_RED_W];      // per-warp transpose buffer: [entry of the chunk][lane]; between blocks the solver's fp64 workspace
+    float red[QR_COMPUTE_WARPS][GR_CHUNK][GR_RED_W];  // per-warp transpose buffer: [entry of the chunk][lane]; between blocks the solver's fp64 workspace
     float part[2][QR_COMPUTE_WARPS][24];            // per warp: min (6), max (6), column sums (12); double-buffered by block parity
     int mine[QR_MINE];
     unsigned long long data_full;
     int blk[2];
 };
 static_assert(GR_STRIDE <= QR_TRI_G, "the Gram scratch reuses the triangle scratch allocation");
-static_assert(2 * BMFR_BUFFER_COUNT * BMFR_FEATURES * sizeof(double) <= 32 * GR_RED_W * sizeof(float), "solver workspace fits the transpose buffer");
+static_assert(2 * BMFR_BUFFER_COUNT * BMFR_FEATURES * sizeof(double) <= GR_CHUNK * GR_RED_W * sizeof(float), "solver workspace fits the transpose buffer");
+static_assert(GR_CHUNK >= BMFR_BUFFER_COUNT - 1 && GR_CHUNK <= 32, "the column sums of a block go through the buffer in one round");
 
 // Sum of the 32 floats of one row of the transpose buffer (eight 128-bit loads, pairwise tree).
 __device__ __forceinline__ float gram_row_sum(const float* __restrict__ row) {
@@ -785,10 +794,6 @@ __device__ __noinline__ void gram_solve_mine(const KParams& P, SH& sh, int count
     }
     __syncthreads();
 }
-
-#ifndef BMFR_GRAM_MIN_BLOCKS
-#define BMFR_GRAM_MIN_BLOCKS 3
-#endif
 
 template <bool STRIP>
 __global__ void __launch_bounds__(QR_THREADS, BMFR_GRAM_MIN_BLOCKS) fit_gram_kernel(const __grid_constant__ KParams P,
@@ -986,7 +991,7 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_GRAM_MIN_BLOCKS) fit_gram_ker
         float* const out = P.tri + ((size_t)local * QR_COMPUTE_WARPS + warp) * QR_TRI_G;
         auto flush = [&](int chunk, int count) {
             __syncwarp();
-            if (lane < count) out[chunk * 32 + lane] = gram_row_sum(red + lane * GR_RED_W);
+            if (lane < count) out[chunk * GR_CHUNK + lane] = gram_row_sum(red + lane * GR_RED_W);
             __syncwarp();
         };
         int e = 0;  // compile-time after unrolling
@@ -995,8 +1000,8 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_GRAM_MIN_BLOCKS) fit_gram_ker
             float2 acc = a2[0][j];
 #pragma unroll
             for (int h = 1; h < ROWS / 2; ++h) acc = fadd2(acc, a2[h][j]);
-            red[(e & 31) * GR_RED_W + lane] = acc.x + acc.y;
-            if ((++e & 31) == 0) flush(e / 32 - 1, 32);
+            red[(e % GR_CHUNK) * GR_RED_W + lane] = acc.x + acc.y;
+            if (++e % GR_CHUNK == 0) flush(e / GR_CHUNK - 1, GR_CHUNK);
         }
 #pragma unroll
         for (int i = 0; i < NCOL; ++i) {
@@ -1005,11 +1010,11 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_GRAM_MIN_BLOCKS) fit_gram_ker
                 float2 acc = fmul2(a2[0][i], a2[0][j]);
 #pragma unroll
                 for (int h = 1; h < ROWS / 2; ++h) acc = ffma2(a2[h][i], a2[h][j], acc);
-                red[(e & 31) * GR_RED_W + lane] = acc.x + acc.y;
-                if ((++e & 31) == 0) flush(e / 32 - 1, 32);
+                red[(e % GR_CHUNK) * GR_RED_W + lane] = acc.x + acc.y;
+                if (++e % GR_CHUNK == 0) flush(e / GR_CHUNK - 1, GR_CHUNK);
             }
         }
-        flush(GR_ENTRIES / 32, GR_ENTRIES % 32);
+        if (GR_ENTRIES % GR_CHUNK != 0) flush(GR_ENTRIES / GR_CHUNK, GR_ENTRIES % GR_CHUNK);
 
         if (++mine == QR_MINE) {
             gram_solve_mine(P, sh, mine, warp, lane);

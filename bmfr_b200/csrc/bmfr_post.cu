@@ -113,6 +113,34 @@ __device__ __forceinline__ void weighted_sum_px2(f3 n0, f3 p0, f3 n1, f3 p1, con
     out1 = make_f3(b.x < 0.f ? 0.f : b.x, b.y < 0.f ? 0.f : b.y, b.z < 0.f ? 0.f : b.z);
 }
 
+// The same for the four pixels of a thread's column strip: every coefficient is fetched once and used four times.
+__device__ __forceinline__ void weighted_sum_px4(const f3 (&n)[4], const f3 (&p)[4], const float* __restrict__ cf, f3 (&out)[4]) {
+    const float4* c4 = reinterpret_cast<const float4*>(cf);
+    const float4 m0 = c4[10], m1 = c4[11], m2 = c4[12];
+    float ft[4][BMFR_FEATURES - 1];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        ft[k][0] = n[k].x; ft[k][1] = n[k].y; ft[k][2] = n[k].z;
+        ft[k][3] = (p[k].x - m0.x) * m0.y; ft[k][4] = (p[k].y - m0.z) * m0.w; ft[k][5] = (p[k].z - m1.x) * m1.y;
+        ft[k][6] = (p[k].x * p[k].x - m1.z) * m1.w; ft[k][7] = (p[k].y * p[k].y - m2.x) * m2.y; ft[k][8] = (p[k].z * p[k].z - m2.z) * m2.w;
+    }
+    const float4 w0 = c4[0];
+    f3 acc[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[k] = make_f3(w0.x, w0.y, w0.z);
+#pragma unroll
+    for (int f = 1; f < BMFR_FEATURES; ++f) {
+        const float4 w = c4[f];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            acc[k].x = fmaf(w.x, ft[k][f - 1], acc[k].x); acc[k].y = fmaf(w.y, ft[k][f - 1], acc[k].y); acc[k].z = fmaf(w.z, ft[k][f - 1], acc[k].z);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)  // keeps NaN, bmfr.cl:750
+        out[k] = make_f3(acc[k].x < 0.f ? 0.f : acc[k].x, acc[k].y < 0.f ? 0.f : acc[k].y, acc[k].z < 0.f ? 0.f : acc[k].z);
+}
+
 // accept / pp / spp / alb are this pixel's accept mask, previous-frame position, sample count and
 // albedo, fetched by the caller together with the features (one round of independent loads).
 template <bool STRIP, bool WIDE>
@@ -455,9 +483,10 @@ struct __align__(128) PostStage {  // every TMA destination starts on a 128-byte
     unsigned char acc[PT_HALO][PT_U8_W];
     unsigned char spp[PT_HALO][PT_U8_W];
     float coef[9][PT_COEF];
-    unsigned long long bar[3];
+    unsigned long long bar;
 };
 static_assert(sizeof(float[PT_HALO][PT_RGB_W]) % 128 == 96 && sizeof(float[PT_HALO][PT_PP_W]) % 128 == 64, "TMA destinations must stay 128-byte aligned");
+#define PT_STAGE_TX (3 * PT_HALO * PT_RGB_W * 4 + PT_HALO * PT_PP_W * 4 + 2 * PT_HALO * PT_U8_W)
 
 struct PostMaps {
     CUtensorMap normals, positions, albedo, pp, accept, spp;
@@ -592,15 +621,9 @@ __device__ __forceinline__ bool resolve_pixel(PostStage& sh, const KParams& P, c
 #ifndef BMFR_POST_TMA_MIN_BLOCKS
 #define BMFR_POST_TMA_MIN_BLOCKS 3
 #endif
-
-// What a thread carries from one step of a pixel pair to the next.
-struct PairState {
-    PixelIn i0, i1;
-    TapGeom g0, g1;
-    f3 A[3][2], R[3][2];  // tap rows R0, R1 of the upper pixel, R2 of the lower (accumulated colour / TAA history)
-    bool stacked;         // the lower pixel's upper tap row is R1
-    int cx1[2], ry10;     // where to fetch that row otherwise
-};
+#ifndef BMFR_POST_WS4
+#define BMFR_POST_WS4 0
+#endif
 
 template <bool STRIP>
 __global__ void __launch_bounds__(256, BMFR_POST_TMA_MIN_BLOCKS) post_tma_kernel(const __grid_constant__ KParams P, const __grid_constant__ PostMaps M) {
@@ -617,45 +640,34 @@ __global__ void __launch_bounds__(256, BMFR_POST_TMA_MIN_BLOCKS) post_tma_kernel
     constexpr int NW = BMFR_FEATURES * 3, NM = BMFR_FEATURES_SCALED * 2;
 
     if (tid == 0) {
-        mbar_init(&sh.bar[0], 1);
-        mbar_init(&sh.bar[1], 1);
-        mbar_init(&sh.bar[2], 1);
+        mbar_init(&sh.bar, 1);
         mbar_fence_init();
         // Requested before the grid dependency is resolved: the caller's inputs and the reprojection's outputs are
         // complete by now — in the in-order stream this grid's CTAs start only after every CTA of the fit has passed
         // its own wait for the reprojection (which waited for the caller's producer), in the overlapped mode the fit's
         // event already orders this launch.  Rows / columns outside the image (or the strip) arrive as zeros.
-        // Three barriers in the order the data is needed: what the gather addresses depend on first (so that the gathers
-        // are in flight while the rest still lands), then the features of the weighted sum, then the albedo.
         const int c1 = G.y0 - 1 - P.row0;
-        mbar_expect_tx(&sh.bar[0], PT_HALO * PT_PP_W * 4 + 2 * PT_HALO * PT_U8_W);
-        tma_load_tile(&sh.pp[0][0], &M.pp, c_pp, c1, &sh.bar[0]);
-        tma_load_tile(&sh.acc[0][0], &M.accept, c_u8, c1, &sh.bar[0]);
-        tma_load_tile(&sh.spp[0][0], &M.spp, c_u8, c1, &sh.bar[0]);
-        mbar_expect_tx(&sh.bar[1], 2 * PT_HALO * PT_RGB_W * 4);
-        tma_load_tile(&sh.nrm[0][0], &M.normals, c_rgb, c1, &sh.bar[1]);
-        tma_load_tile(&sh.pos[0][0], &M.positions, c_rgb, c1, &sh.bar[1]);
-        mbar_expect_tx(&sh.bar[2], PT_HALO * PT_RGB_W * 4);
-        tma_load_tile(&sh.alb[0][0], &M.albedo, c_rgb, c1, &sh.bar[2]);
+        mbar_expect_tx(&sh.bar, PT_STAGE_TX);
+        tma_load_tile(&sh.pp[0][0], &M.pp, c_pp, c1, &sh.bar);
+        tma_load_tile(&sh.acc[0][0], &M.accept, c_u8, c1, &sh.bar);
+        tma_load_tile(&sh.spp[0][0], &M.spp, c_u8, c1, &sh.bar);
+        tma_load_tile(&sh.nrm[0][0], &M.normals, c_rgb, c1, &sh.bar);
+        tma_load_tile(&sh.pos[0][0], &M.positions, c_rgb, c1, &sh.bar);
+        tma_load_tile(&sh.alb[0][0], &M.albedo, c_rgb, c1, &sh.bar);
     }
     pdl_wait();     // the fit of this frame is complete (weights, min/max)
     pdl_trigger();  // only now, so that "this frame's fit and reprojection are complete" also holds for the successor
 
-    // coefficients of the 3x3 block neighbourhood: warp w fetches neighbour w (warp 0 also the ninth) into registers now
-    // and stores them to shared memory once its first gathers are in flight
-    float cw[2] = {0.f, 0.f}, cm[2] = {0.f, 0.f};
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-        const int nb = warp + 8 * k;
+    // coefficients of the 3x3 block neighbourhood -> shared memory (as in post_kernel)
+    for (int nb = warp; nb < 9; nb += 8) {
         const int gx = bx + nb % 3 - 1, gy = by + nb / 3 - 1;
-        if (nb < 9 && gx >= 0 && gx < P.blocks_x && gy >= 0 && gy < P.blocks_y) {
-            const size_t g = (size_t)gy * P.blocks_x + gx;
-            if (lane < NW) cw[k] = __ldg(P.weights + g * NW + lane);
-            if (lane < NM) cm[k] = __ldg(P.mins_inv + g * NM + lane);
-        }
+        if (gx < 0 || gx >= P.blocks_x || gy < 0 || gy >= P.blocks_y) continue;
+        const size_t g = (size_t)gy * P.blocks_x + gx;
+        if (lane < NW) sh.coef[nb][(lane / 3) * 4 + lane % 3] = __ldg(P.weights + g * NW + lane);
+        if (lane < NM) sh.coef[nb][40 + lane] = __ldg(P.mins_inv + g * NM + lane);
     }
-    __syncthreads();  // the barriers' initialisation is visible
-    mbar_wait_hot(&sh.bar[0], 0);
+    __syncthreads();  // the coefficients and the barrier's initialisation are visible
+    mbar_wait_hot(&sh.bar, 0);
 
     const int x = G.x0 + lane;
     const bool col_ok = x >= 0 && x < P.W;
@@ -663,81 +675,74 @@ __global__ void __launch_bounds__(256, BMFR_POST_TMA_MIN_BLOCKS) post_tma_kernel
     // phase A, interior: column strip x, rows 4*warp .. 4*warp+3, two vertically adjacent pixels at a time
     f3 hist[4];
     unsigned int live = 0;  // bit s: pixel s is written; bit 4+s: it takes the temporal path
+#if BMFR_POST_WS4
+    // the weighted sum of the whole strip first (shared-memory operands only), so that the coefficients are read once for
+    // four pixels; strips cut by an edge take the pair path below
+    f3 fl4[4];
+    const bool strip_whole = col_ok && G.y0 + 4 * warp >= P.py0 && G.y0 + 4 * warp + 3 < P.py1;
+    if (strip_whole) {
+        f3 n4[4], p4[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            n4[k] = cell_f3(sh.nrm, G, lane + 1, 4 * warp + k + 1);
+            p4[k] = cell_f3(sh.pos, G, lane + 1, 4 * warp + k + 1);
+        }
+        weighted_sum_px4(n4, p4, sh.coef[4], fl4);
+    }
+#endif
 #pragma unroll
     for (int s = 0; s < 4; s += 2) {
         const int ty = 4 * warp + s, y = G.y0 + ty;
         hist[s] = hist[s + 1] = make_f3(0.f, 0.f, 0.f);
         const bool v0 = col_ok && y >= P.py0 && y < P.py1, v1 = col_ok && y + 1 >= P.py0 && y + 1 < P.py1;
         const bool own0 = y >= P.own_y0 && y < P.own_y1, own1 = y + 1 >= P.own_y0 && y + 1 < P.own_y1;
-        const bool fast = v0 && v1;
-        PairState st;
-        // step 1: previous-pixel positions -> tap addresses -> one round of independent loads from clamped addresses
-        if (fast) {
-            const int hx = lane + 1, hy = ty + 1;
-            st.i0.lp = pix_index(P, x, y); st.i1.lp = pix_index(P, x, y + 1);
-            st.i0.pp = *reinterpret_cast<const float2*>(&sh.pp[hy][G.sh_pp + 2 * hx]);
-            st.i1.pp = *reinterpret_cast<const float2*>(&sh.pp[hy + 1][G.sh_pp + 2 * hx]);
-            st.i0.accept = sh.acc[hy][G.sh_u8 + hx]; st.i1.accept = sh.acc[hy + 1][G.sh_u8 + hx];
-            st.i0.spp = sh.spp[hy][G.sh_u8 + hx]; st.i1.spp = sh.spp[hy + 1][G.sh_u8 + hx];
-            if (P.frame > 0) {
-                st.g0 = tap_geom(st.i0.pp); st.g1 = tap_geom(st.i1.pp);
-                const int cx0[2] = {min(max(st.g0.pix, 0), P.W - 1), min(max(st.g0.pix + 1, 0), P.W - 1)};
-                const int ry0[2] = {min(max(st.g0.piy, rlo), rhi), min(max(st.g0.piy + 1, rlo), rhi)};
-                const int ry11 = min(max(st.g1.piy + 1, rlo), rhi);
-                st.cx1[0] = min(max(st.g1.pix, 0), P.W - 1); st.cx1[1] = min(max(st.g1.pix + 1, 0), P.W - 1);
-                st.ry10 = min(max(st.g1.piy, rlo), rhi);
-                st.stacked = st.cx1[0] == cx0[0] && st.cx1[1] == cx0[1] && st.ry10 == ry0[1];
-#pragma unroll
-                for (int dx = 0; dx < 2; ++dx) {
-                    const unsigned int l0 = pix_index(P, cx0[dx], ry0[0]), l1 = pix_index(P, cx0[dx], ry0[1]), l2 = pix_index(P, st.cx1[dx], ry11);
-                    st.A[0][dx] = load_f3(P.accum_prev, l0); st.A[1][dx] = load_f3(P.accum_prev, l1); st.A[2][dx] = load_f3(P.accum_prev, l2);
-                    st.R[0][dx] = load_f3(P.result_prev, l0); st.R[1][dx] = load_f3(P.result_prev, l1); st.R[2][dx] = load_f3(P.result_prev, l2);
-                }
-            }
-        }
-        if (s == 0) {  // (uniform) the coefficients, while the first gathers are in flight
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                const int nb = warp + 8 * k;
-                if (nb < 9) {
-                    if (lane < NW) sh.coef[nb][(lane / 3) * 4 + lane % 3] = cw[k];
-                    if (lane < NM) sh.coef[nb][40 + lane] = cm[k];
-                }
-            }
-            __syncthreads();
-            mbar_wait_hot(&sh.bar[1], 0);
-        }
-        // step 2: the weighted sum of the pair (shared-memory operands only: its arithmetic overlaps the gathers)
-        f3 fl0 = make_f3(0.f, 0.f, 0.f), fl1 = fl0;
-        if (fast) {
-            st.i0.n = cell_f3(sh.nrm, G, lane + 1, ty + 1); st.i0.p = cell_f3(sh.pos, G, lane + 1, ty + 1);
-            st.i1.n = cell_f3(sh.nrm, G, lane + 1, ty + 2); st.i1.p = cell_f3(sh.pos, G, lane + 1, ty + 2);
-            weighted_sum_px2(st.i0.n, st.i0.p, st.i1.n, st.i1.p, sh.coef[4], fl0, fl1);
-        }
-        if (s == 0) mbar_wait_hot(&sh.bar[2], 0);
-        // step 3: accumulate, tone map, YCoCg cell, TAA history sample
-        if (fast) {
-            st.i0.alb = cell_f3(sh.alb, G, lane + 1, ty + 1);
-            st.i1.alb = cell_f3(sh.alb, G, lane + 1, ty + 2);
+        if (v0 && v1) {
+            const PixelIn i0 = load_pixel_staged(sh, P, G, lane + 1, ty + 1, x, y), i1 = load_pixel_staged(sh, P, G, lane + 1, ty + 2, x, y + 1);
             bool t0 = false, t1 = false;
             if (P.frame > 0) {
-                t0 = resolve_pixel<STRIP>(sh, P, G, st.i0, st.g0, fl0, st.A[0], st.A[1], st.R[0], st.R[1], lane + 1, ty + 1, x, y, own0, hist[s]);
-                if (!st.stacked) {  // footprints not stacked (rare): fetch the lower pixel's upper tap row
+                const TapGeom g0 = tap_geom(i0.pp), g1 = tap_geom(i1.pp);
+                // one round of independent loads from clamped addresses: tap rows R0, R1 of the upper pixel, R2 of the lower;
+                // the lower pixel's upper row is R1 when the two footprints are stacked (checked below)
+                const int cx0[2] = {min(max(g0.pix, 0), P.W - 1), min(max(g0.pix + 1, 0), P.W - 1)};
+                const int cx1[2] = {min(max(g1.pix, 0), P.W - 1), min(max(g1.pix + 1, 0), P.W - 1)};
+                const int ry0[2] = {min(max(g0.piy, rlo), rhi), min(max(g0.piy + 1, rlo), rhi)};
+                const int ry1[2] = {min(max(g1.piy, rlo), rhi), min(max(g1.piy + 1, rlo), rhi)};
+                f3 A[3][2], R[3][2];
+#pragma unroll
+                for (int dx = 0; dx < 2; ++dx) {
+                    const unsigned int l0 = pix_index(P, cx0[dx], ry0[0]), l1 = pix_index(P, cx0[dx], ry0[1]), l2 = pix_index(P, cx1[dx], ry1[1]);
+                    A[0][dx] = load_f3(P.accum_prev, l0); A[1][dx] = load_f3(P.accum_prev, l1); A[2][dx] = load_f3(P.accum_prev, l2);
+                    R[0][dx] = load_f3(P.result_prev, l0); R[1][dx] = load_f3(P.result_prev, l1); R[2][dx] = load_f3(P.result_prev, l2);
+                }
+                f3 fl0, fl1;
+#if BMFR_POST_WS4
+                if (strip_whole) { fl0 = fl4[s]; fl1 = fl4[s + 1]; }
+                else
+#endif
+                weighted_sum_px2(i0.n, i0.p, i1.n, i1.p, sh.coef[4], fl0, fl1);  // its arithmetic overlaps the gathers
+                t0 = resolve_pixel<STRIP>(sh, P, G, i0, g0, fl0, A[0], A[1], R[0], R[1], lane + 1, ty + 1, x, y, own0, hist[s]);
+                if (!(cx1[0] == cx0[0] && cx1[1] == cx0[1] && ry1[0] == ry0[1])) {  // footprints not stacked (rare): fetch the row
 #pragma unroll
                     for (int dx = 0; dx < 2; ++dx) {
-                        const unsigned int l = pix_index(P, st.cx1[dx], st.ry10);
-                        st.A[1][dx] = load_f3(P.accum_prev, l);
-                        st.R[1][dx] = load_f3(P.result_prev, l);
+                        const unsigned int l = pix_index(P, cx1[dx], ry1[0]);
+                        A[1][dx] = load_f3(P.accum_prev, l);
+                        R[1][dx] = load_f3(P.result_prev, l);
                     }
                 }
-                t1 = resolve_pixel<STRIP>(sh, P, G, st.i1, st.g1, fl1, st.A[1], st.A[2], st.R[1], st.R[2], lane + 1, ty + 2, x, y + 1, own1, hist[s + 1]);
+                t1 = resolve_pixel<STRIP>(sh, P, G, i1, g1, fl1, A[1], A[2], R[1], R[2], lane + 1, ty + 2, x, y + 1, own1, hist[s + 1]);
             } else {  // frame 0: no temporal path, alpha = 1 (bmfr.cl:784, 884)
-                store_f3(P.accum_cur, st.i0.lp, fl0);
-                store_f3(P.accum_cur, st.i1.lp, fl1);
+                f3 fl0, fl1;
+#if BMFR_POST_WS4
+                if (strip_whole) { fl0 = fl4[s]; fl1 = fl4[s + 1]; }
+                else
+#endif
+                weighted_sum_px2(i0.n, i0.p, i1.n, i1.p, sh.coef[4], fl0, fl1);
+                store_f3(P.accum_cur, i0.lp, fl0);
+                store_f3(P.accum_cur, i1.lp, fl1);
                 put_ycc_i(sh, P, G, lane + 1, ty + 1, x, y,
-                          to_ycocg(make_f3(tone_map_fast(st.i0.alb.x * fl0.x), tone_map_fast(st.i0.alb.y * fl0.y), tone_map_fast(st.i0.alb.z * fl0.z))));
+                          to_ycocg(make_f3(tone_map_fast(i0.alb.x * fl0.x), tone_map_fast(i0.alb.y * fl0.y), tone_map_fast(i0.alb.z * fl0.z))));
                 put_ycc_i(sh, P, G, lane + 1, ty + 2, x, y + 1,
-                          to_ycocg(make_f3(tone_map_fast(st.i1.alb.x * fl1.x), tone_map_fast(st.i1.alb.y * fl1.y), tone_map_fast(st.i1.alb.z * fl1.z))));
+                          to_ycocg(make_f3(tone_map_fast(i1.alb.x * fl1.x), tone_map_fast(i1.alb.y * fl1.y), tone_map_fast(i1.alb.z * fl1.z))));
             }
             live |= ((own0 ? 1u : 0u) | (t0 ? 16u : 0u)) << s;
             live |= ((own1 ? 1u : 0u) | (t1 ? 16u : 0u)) << (s + 1);
