@@ -35,7 +35,7 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 FRAMES = 60
-FUSED_KERNELS = ("reproject_kernel", "fit_gram_kernel", "post_tma_kernel")  # replaced by the context's own list at run time
+FUSED_KERNELS = ("reproject_tma_kernel", "fit_gram_kernel", "post_tma_kernel")  # replaced by the context's own list at run time
 SINGLE_GPU_WORKLOAD = (1920, 1080)
 
 
@@ -72,6 +72,7 @@ def algorithmic_bytes(w, h):
         "taa": 32 * P + 12 * P,
         # FUSED: tmp_data / filtered / tone_mapped never reach HBM
         "reproject_kernel": 95 * P,                        # K1 per image pixel: 73 B in, 22 B out
+        "reproject_tma_kernel": 95 * P,
         "fit_qr_kernel": 36 * P + 216 * NB,                # normals, positions, accumulated colour once; weights + min/max out
         "fit_gram_kernel": 36 * P + 216 * NB,
         "post_kernel": 94 * P + 168 * NB,                  # K3+K4+K5

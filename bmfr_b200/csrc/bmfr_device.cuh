@@ -172,12 +172,10 @@ struct K1Pixel {
 // wp: the pixel's world position, already loaded (callers that walk over several pixels fetch the next
 // pixel's position before they start this one, so that the two dependent memory round trips of a pixel
 // — position -> reprojection -> taps — overlap across pixels).
+// n, cur: the pixel's shading normal and this frame's noisy colour, already loaded too.
 template <bool STRIP>
-__device__ __forceinline__ K1Pixel k1_pixel(const KParams& P, int x, int y, f3 wp) {
+__device__ __forceinline__ K1Pixel k1_pixel_core(const KParams& P, int x, int y, f3 wp, f3 n, f3 cur) {
     K1Pixel r;
-    const unsigned int lp = pix_index(P, x, y);
-    const f3 n = load_f3_stream(P.cur_normals, lp);
-    const f3 cur = load_f3_stream(P.cur_noisy, lp);
     float pfx = (float)x, pfy = (float)y;  // bmfr.cl:325
     unsigned int accept = 0;
     float blend_alpha = 1.f;
@@ -303,6 +301,11 @@ __device__ __forceinline__ void k1_features(const K1Pixel& r, float* f) {
     f[12] = scrub_nan(r.new_color.z);
 }
 
+template <bool STRIP>
+__device__ __forceinline__ K1Pixel k1_pixel(const KParams& P, int x, int y, f3 wp) {
+    const unsigned int lp = pix_index(P, x, y);
+    return k1_pixel_core<STRIP>(P, x, y, wp, load_f3_stream(P.cur_normals, lp), load_f3_stream(P.cur_noisy, lp));
+}
 template <bool STRIP>
 __device__ __forceinline__ K1Pixel k1_pixel(const KParams& P, int x, int y) {
     return k1_pixel<STRIP>(P, x, y, load_f3(P.cur_positions, pix_index(P, x, y)));

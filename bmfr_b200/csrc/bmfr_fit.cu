@@ -42,6 +42,24 @@ __device__ __forceinline__ int noise_f_index(int c, int y, int x) {
     return (((((y >> 3) * (BMFR_FEATURES - 1) + c) * 2 + ((y & 7) >> 2)) * 32 + x) << 2) + (y & 3);
 }
 
+// The first CTAs of the reprojection also produce this frame's add_random() tile (bmfr.cl:173-182; one 9x1024 tile per
+// frame shared by all blocks, fp64 like the reference's double literal plus its fp32 rounding for the fit) and reset the
+// fit's block counter: the fit starts only after the reprojection has completed.
+__device__ __forceinline__ void reproject_noise_tile(const KParams& P, int tid) {
+    const int cta = blockIdx.y * gridDim.x + blockIdx.x, ncta = gridDim.x * gridDim.y;
+    const int workers = ncta < 36 ? ncta : 36;
+    if (cta < workers) {
+        const int n = (BMFR_FEATURES - 1) * BMFR_BLOCK_PIXELS;
+        for (int i = cta * 256 + tid; i < n; i += workers * 256) {
+            const int seed = i + BMFR_BLOCK_PIXELS + P.frame * BMFR_BUFFER_COUNT * BMFR_BLOCK_PIXELS;
+            const double d = (P.noise_amount * 2.0) * (double)(bmfr_random((unsigned int)seed) - 0.5f);
+            P.noise_out[i] = d;
+            P.noise_f_out[noise_f_index(i / BMFR_BLOCK_PIXELS, (i % BMFR_BLOCK_PIXELS) / 32, i % 32)] = (float)d;
+        }
+        if (cta == 0 && tid == 0) *P.block_counter = 0;
+    }
+}
+
 template <bool STRIP>
 __global__ void __launch_bounds__(256, BMFR_REPROJECT_MIN_BLOCKS) reproject_kernel(const __grid_constant__ KParams P) {
     // Everything below reads the caller's inputs.  Their producer may be the kernel right before this one on the
@@ -52,23 +70,7 @@ __global__ void __launch_bounds__(256, BMFR_REPROJECT_MIN_BLOCKS) reproject_kern
     // after the wait, so that "everything before this grid is complete" is transitive: the fit requests its first
     // normals / positions tiles (the caller's inputs) before its own wait
     pdl_trigger();  // the fit's CTAs may take SM slots as this grid drains
-    // The first CTAs also produce this frame's add_random() tile (bmfr.cl:173-182; one 9x1024 tile per
-    // frame shared by all blocks, fp64 like the reference's double literal plus its fp32 rounding for the
-    // fit) and reset the fit's block counter: the fit starts only after this kernel has completed.
-    {
-        const int cta = blockIdx.y * gridDim.x + blockIdx.x, ncta = gridDim.x * gridDim.y;
-        const int workers = ncta < 36 ? ncta : 36;
-        if (cta < workers) {
-            const int n = (BMFR_FEATURES - 1) * BMFR_BLOCK_PIXELS;
-            for (int i = cta * 256 + threadIdx.y * BMFR_REPROJECT_BX + threadIdx.x; i < n; i += workers * 256) {
-                const int seed = i + BMFR_BLOCK_PIXELS + P.frame * BMFR_BUFFER_COUNT * BMFR_BLOCK_PIXELS;
-                const double d = (P.noise_amount * 2.0) * (double)(bmfr_random((unsigned int)seed) - 0.5f);
-                P.noise_out[i] = d;
-                P.noise_f_out[noise_f_index(i / BMFR_BLOCK_PIXELS, (i % BMFR_BLOCK_PIXELS) / 32, i % 32)] = (float)d;
-            }
-            if (cta == 0 && threadIdx.x == 0 && threadIdx.y == 0) *P.block_counter = 0;
-        }
-    }
+    reproject_noise_tile(P, threadIdx.y * BMFR_REPROJECT_BX + threadIdx.x);
     const int x = blockIdx.x * BMFR_REPROJECT_BX + threadIdx.x;
     const int ybase = P.k1_y0 + blockIdx.y * (BMFR_REPROJECT_BY * BMFR_REPROJECT_PIXELS) + threadIdx.y;
     if (x >= P.W) return;
@@ -96,6 +98,70 @@ __global__ void __launch_bounds__(256, BMFR_REPROJECT_MIN_BLOCKS) reproject_kern
         P.cur_spp[lp] = r.spp;
         P.prev_pixels[lp] = make_float2(r.prev_x, r.prev_y);
         P.accept[lp] = r.accept;
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+// reproject_tma_kernel: the same per-pixel arithmetic (k1_pixel_core), but a CTA's 32x32 pixels of the three
+// current-frame inputs (world position, normal, noisy colour) arrive as three bulk tensor copies.  That takes the first
+// of the two dependent memory round trips of a pixel (position -> reprojection -> 40 tap loads) off the critical path of
+// every thread — the taps of a thread's first pixel are issued as soon as the tiles have landed — and leaves the load /
+// store unit to the gathers.  Used when the tensor maps can be built (W % 4 == 0, at least 32 rows).
+// --------------------------------------------------------------------------------------------
+#define RP_TILE_W 96
+struct ReprojectShared {
+    float pos[32][RP_TILE_W];
+    float nrm[32][RP_TILE_W];
+    float col[32][RP_TILE_W];
+    unsigned long long bar;
+};
+struct ReprojectMaps {
+    CUtensorMap positions, normals, noisy;
+};
+
+template <bool STRIP>
+__global__ void __launch_bounds__(256, BMFR_REPROJECT_MIN_BLOCKS) reproject_tma_kernel(const __grid_constant__ KParams P,
+                                                                                       const __grid_constant__ ReprojectMaps M) {
+    __shared__ __align__(128) ReprojectShared sh;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int x0 = blockIdx.x * 32, y0 = P.k1_y0 + blockIdx.y * 32;
+    if (threadIdx.x == 0) {
+        mbar_init(&sh.bar, 1);
+        mbar_fence_init();
+    }
+    pdl_wait();     // the caller's inputs are complete (see reproject_kernel)
+    pdl_trigger();
+    if (threadIdx.x == 0) {  // rows below the image / the strip arrive as zeros and are never used
+        mbar_expect_tx(&sh.bar, 3 * 32 * RP_TILE_W * 4);
+        tma_load_tile(&sh.pos[0][0], &M.positions, x0 * 3, y0 - P.row0, &sh.bar);
+        tma_load_tile(&sh.nrm[0][0], &M.normals, x0 * 3, y0 - P.row0, &sh.bar);
+        tma_load_tile(&sh.col[0][0], &M.noisy, x0 * 3, y0 - P.row0, &sh.bar);
+    }
+    reproject_noise_tile(P, threadIdx.x);
+    __syncthreads();  // the barrier's initialisation is visible
+    int ylo = P.k1_y0, yhi = P.k1_y1;
+    if (STRIP) {  // rows outside the strip + halo cannot be reprojected here: flag and skip them
+        if (ylo < P.row0 || yhi > P.row1) *P.oob_flag = 1;
+        ylo = max(ylo, P.row0);
+        yhi = min(yhi, P.row1);
+    }
+    mbar_wait_hot(&sh.bar, 0);
+    const int x = x0 + tx;
+    if (x >= P.W) return;
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) {
+        const int r = ty + 8 * k, y = y0 + r;
+        if (y >= yhi) break;
+        if (y < ylo) continue;
+        const f3 wp = make_f3(sh.pos[r][3 * tx], sh.pos[r][3 * tx + 1], sh.pos[r][3 * tx + 2]);
+        const f3 n = make_f3(sh.nrm[r][3 * tx], sh.nrm[r][3 * tx + 1], sh.nrm[r][3 * tx + 2]);
+        const f3 cur = make_f3(sh.col[r][3 * tx], sh.col[r][3 * tx + 1], sh.col[r][3 * tx + 2]);
+        const K1Pixel px = k1_pixel_core<STRIP>(P, x, y, wp, n, cur);
+        const unsigned int lp = pix_index(P, x, y);
+        store_f3(P.cur_noisy_acc, lp, px.new_color);
+        P.cur_spp[lp] = px.spp;
+        P.prev_pixels[lp] = make_float2(px.prev_x, px.prev_y);
+        P.accept[lp] = px.accept;
     }
 }
 
@@ -669,8 +735,11 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
 #define GR_ENTRIES 90   // upper triangle of the 13x13 Gram matrix without G_00 (= 1024): row 0 first (12 column sums), then rows 1..12
 #define GR_STRIDE 104   // floats per (block, warp) in the scratch: 90 Gram entries, 12 block means (warp 0), padding; <= QR_TRI_G
 #define GR_RED_W 36     // floats per row of the transpose buffer: 16-byte aligned rows, conflict-free 128-bit reads
+// CTAs per SM.  Measured at 1080p (profiles/r02_f_*): 3 -> 35.2 us, 4 (with 16-entry reduction rounds, 128 registers) ->
+// 45.3 us: a CTA's first block is its most expensive one (cold landing zone, cold instruction cache) and a fourth CTA
+// takes the L1 away, so fewer, longer-lived CTAs win.
 #ifndef BMFR_GRAM_MIN_BLOCKS
-#define BMFR_GRAM_MIN_BLOCKS 4
+#define BMFR_GRAM_MIN_BLOCKS 3
 #endif
 // Gram entries reduced per round trip through the transpose buffer.  32 uses every lane for the row sums; 16 halves the
 // buffer (2.3 KB per warp), which is what lets a fourth CTA fit on an SM next to the 38 KB landing zones.
@@ -1030,7 +1099,20 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_GRAM_MIN_BLOCKS) fit_gram_ker
 // --------------------------------------------------------------------------------------------
 static bool is_strip(const KParams& P) { return P.row0 != 0 || P.row1 != P.H; }
 
+#ifndef BMFR_REPROJECT_TMA
+#define BMFR_REPROJECT_TMA 1
+#endif
 cudaError_t launch_reproject(const KParams& P, cudaStream_t st) {
+    const int rows = P.row1 - P.row0;
+    ReprojectMaps M;
+    if (BMFR_REPROJECT_TMA && (P.W & 3) == 0 && rows >= 32 && P.W >= 32 &&
+        bmfr_tensor_map_2d(P.cur_positions, 4, (long long)P.W * 3, rows, RP_TILE_W, 32, &M.positions) &&
+        bmfr_tensor_map_2d(P.cur_normals, 4, (long long)P.W * 3, rows, RP_TILE_W, 32, &M.normals) &&
+        bmfr_tensor_map_2d(P.cur_noisy, 4, (long long)P.W * 3, rows, RP_TILE_W, 32, &M.noisy)) {
+        const dim3 grid((P.W + 31) / 32, (P.k1_y1 - P.k1_y0 + 31) / 32);
+        if (is_strip(P)) return launch_pdl(!P.plain_launch, reproject_tma_kernel<true>, grid, dim3(256), 0, st, P, M);
+        return launch_pdl(!P.plain_launch, reproject_tma_kernel<false>, grid, dim3(256), 0, st, P, M);
+    }
     const int rows_per_cta = BMFR_REPROJECT_BY * BMFR_REPROJECT_PIXELS;
     const dim3 grid((P.W + BMFR_REPROJECT_BX - 1) / BMFR_REPROJECT_BX, (P.k1_y1 - P.k1_y0 + rows_per_cta - 1) / rows_per_cta),
         block(BMFR_REPROJECT_BX, BMFR_REPROJECT_BY);
