@@ -42,6 +42,59 @@ static inline cudaError_t launch_pdl(bool pdl, void (*kernel)(KArgs...), dim3 gr
     return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
+// ---------------------------------------------------------------------------------------------
+// In-kernel halo exchange of strip contexts (HaloK in bmfr_kernels.h).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Does the CTA that covers image rows [ya, yb) belong to the zone?
+__device__ __forceinline__ bool halo_in_zone(const HaloK& h, int ya, int yb) { return h.active && (ya < h.zone_y[0] || yb > h.zone_y[1]); }
+// Prologue of a zone CTA (all threads call it): wait for the neighbours' rows.  Bounded: after timeout_ns the context is
+// marked failed (flags[2], sticky) and the kernel goes on with whatever it finds; a failed context never signals.
+__device__ __forceinline__ void halo_poll(const HaloK& h) {
+    if (threadIdx.x == 0 && threadIdx.y == 0 && (h.wait_early | h.wait_late) != 0) {
+        volatile unsigned int* f = h.flags;
+        const unsigned long long t0 = globaltimer_ns();
+        for (;;) {
+            const bool a = !h.side_on[0] || (f[0] >= h.wait_early && f[4] >= h.wait_late);
+            const bool b = !h.side_on[1] || (f[1] >= h.wait_early && f[5] >= h.wait_late);
+            if (a && b) break;
+            if (globaltimer_ns() - t0 > h.timeout_ns) {
+                f[2] = 1;
+                break;
+            }
+            __nanosleep(100);
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+}
+// Epilogue of a zone CTA (all threads call it, after their last store): the last zone CTA of the launch raises the flags.
+__device__ __forceinline__ void halo_finish(const HaloK& h) {
+    __threadfence_system();  // this thread's peer stores are visible system-wide before the flag can be
+    __syncthreads();
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        const unsigned int done = atomicAdd(h.done_counter, 1u);
+        if (done + 1 == h.zone_ctas) {
+            *h.done_counter = 0;  // for the next launch (ordered after this one by the stream)
+            __threadfence_system();
+            if (*(volatile unsigned int*)(h.flags + 2) == 0) {
+#pragma unroll
+                for (int s = 0; s < 2; ++s)
+                    if (h.side_on[s]) *(volatile unsigned int*)h.peer_flag[s] = h.signal_value;
+                __threadfence_system();
+            }
+        }
+    }
+}
+// Index of image pixel (x, y) in the neighbour's buffers on side s, or -1 when the row is not mirrored there.
+__device__ __forceinline__ long long halo_peer_index(const HaloK& h, const KParams& P, int s, int x, int y) {
+    return (h.side_on[s] && y >= h.push_y0[s] && y < h.push_y1[s]) ? (long long)(y - h.peer_row0[s]) * P.W + x : -1;
+}
+
 #ifndef BMFR_STREAM_LOADS
 #define BMFR_STREAM_LOADS 0
 #endif

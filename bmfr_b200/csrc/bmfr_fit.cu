@@ -60,6 +60,28 @@ __device__ __forceinline__ void reproject_noise_tile(const KParams& P, int tid) 
     }
 }
 
+// The four per-pixel outputs of bmfr.cl:478-484; in the zone of a strip the accumulated colour and the sample count of a
+// row a neighbour mirrors go to its halo as well (peer memory over NVLink).
+template <bool STRIP>
+__device__ __forceinline__ void reproject_store(const KParams& P, int x, int y, const K1Pixel& r, bool zone) {
+    const unsigned int lp = pix_index(P, x, y);
+    store_f3(P.cur_noisy_acc, lp, r.new_color);
+    P.cur_spp[lp] = r.spp;
+    P.prev_pixels[lp] = make_float2(r.prev_x, r.prev_y);
+    P.accept[lp] = r.accept;
+    if (STRIP && zone) {
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const long long pi = halo_peer_index(P.halo_r, P, s, x, y);
+            if (pi >= 0) {
+                float* pa = P.halo_r.peer_a[s] + pi * 3;
+                pa[0] = r.new_color.x; pa[1] = r.new_color.y; pa[2] = r.new_color.z;
+                P.halo_r.peer_c[s][pi] = r.spp;
+            }
+        }
+    }
+}
+
 template <bool STRIP>
 __global__ void __launch_bounds__(256, BMFR_REPROJECT_MIN_BLOCKS) reproject_kernel(const __grid_constant__ KParams P) {
     // Everything below reads the caller's inputs.  Their producer may be the kernel right before this one on the
@@ -72,33 +94,35 @@ __global__ void __launch_bounds__(256, BMFR_REPROJECT_MIN_BLOCKS) reproject_kern
     pdl_trigger();  // the fit's CTAs may take SM slots as this grid drains
     reproject_noise_tile(P, threadIdx.y * BMFR_REPROJECT_BX + threadIdx.x);
     const int x = blockIdx.x * BMFR_REPROJECT_BX + threadIdx.x;
-    const int ybase = P.k1_y0 + blockIdx.y * (BMFR_REPROJECT_BY * BMFR_REPROJECT_PIXELS) + threadIdx.y;
-    if (x >= P.W) return;
+    const int cta_y0 = P.k1_y0 + blockIdx.y * (BMFR_REPROJECT_BY * BMFR_REPROJECT_PIXELS);
+    const int ybase = cta_y0 + threadIdx.y;
+    // strips: a CTA near a strip edge waits for the neighbours' rows of the previous frame before it gathers from them
+    const bool zone = STRIP && halo_in_zone(P.halo_r, cta_y0, cta_y0 + BMFR_REPROJECT_BY * BMFR_REPROJECT_PIXELS);
+    if (zone) halo_poll(P.halo_r);
     int ylo = P.k1_y0, yhi = P.k1_y1;
     if (STRIP) {  // rows outside the strip + halo cannot be reprojected here: flag and skip them
         if (ylo < P.row0 || yhi > P.row1) *P.oob_flag = 1;
         ylo = max(ylo, P.row0);
         yhi = min(yhi, P.row1);
     }
-    // software pipeline over the thread's pixels: position of pixel k+1 in flight while pixel k runs its
-    // reprojection -> tap gather chain
-    f3 wp_next = make_f3(0.f, 0.f, 0.f);
-    if (ybase >= ylo && ybase < yhi) wp_next = load_f3_stream(P.cur_positions, pix_index(P, x, ybase));
+    if (x < P.W) {
+        // software pipeline over the thread's pixels: position of pixel k+1 in flight while pixel k runs its
+        // reprojection -> tap gather chain
+        f3 wp_next = make_f3(0.f, 0.f, 0.f);
+        if (ybase >= ylo && ybase < yhi) wp_next = load_f3_stream(P.cur_positions, pix_index(P, x, ybase));
 #pragma unroll 1
-    for (int k = 0; k < BMFR_REPROJECT_PIXELS; ++k) {
-        const int y = ybase + k * BMFR_REPROJECT_BY;
-        if (y >= yhi) break;
-        const f3 wp = wp_next;
-        const int yn = y + BMFR_REPROJECT_BY;
-        if (k + 1 < BMFR_REPROJECT_PIXELS && yn >= ylo && yn < yhi) wp_next = load_f3_stream(P.cur_positions, pix_index(P, x, yn));
-        if (y < ylo) continue;
-        const K1Pixel r = k1_pixel<STRIP>(P, x, y, wp);
-        const unsigned int lp = pix_index(P, x, y);
-        store_f3(P.cur_noisy_acc, lp, r.new_color);
-        P.cur_spp[lp] = r.spp;
-        P.prev_pixels[lp] = make_float2(r.prev_x, r.prev_y);
-        P.accept[lp] = r.accept;
+        for (int k = 0; k < BMFR_REPROJECT_PIXELS; ++k) {
+            const int y = ybase + k * BMFR_REPROJECT_BY;
+            if (y >= yhi) break;
+            const f3 wp = wp_next;
+            const int yn = y + BMFR_REPROJECT_BY;
+            if (k + 1 < BMFR_REPROJECT_PIXELS && yn >= ylo && yn < yhi) wp_next = load_f3_stream(P.cur_positions, pix_index(P, x, yn));
+            if (y < ylo) continue;
+            const K1Pixel r = k1_pixel<STRIP>(P, x, y, wp);
+            reproject_store<STRIP>(P, x, y, r, zone);
+        }
     }
+    if (zone) halo_finish(P.halo_r);
 }
 
 // --------------------------------------------------------------------------------------------
@@ -139,6 +163,8 @@ __global__ void __launch_bounds__(256, BMFR_REPROJECT_MIN_BLOCKS) reproject_tma_
     }
     reproject_noise_tile(P, threadIdx.x);
     __syncthreads();  // the barrier's initialisation is visible
+    const bool zone = STRIP && halo_in_zone(P.halo_r, y0, y0 + 32);
+    if (zone) halo_poll(P.halo_r);
     int ylo = P.k1_y0, yhi = P.k1_y1;
     if (STRIP) {  // rows outside the strip + halo cannot be reprojected here: flag and skip them
         if (ylo < P.row0 || yhi > P.row1) *P.oob_flag = 1;
@@ -147,22 +173,19 @@ __global__ void __launch_bounds__(256, BMFR_REPROJECT_MIN_BLOCKS) reproject_tma_
     }
     mbar_wait_hot(&sh.bar, 0);
     const int x = x0 + tx;
-    if (x >= P.W) return;
+    if (x < P.W) {
 #pragma unroll 1
-    for (int k = 0; k < 4; ++k) {
-        const int r = ty + 8 * k, y = y0 + r;
-        if (y >= yhi) break;
-        if (y < ylo) continue;
-        const f3 wp = make_f3(sh.pos[r][3 * tx], sh.pos[r][3 * tx + 1], sh.pos[r][3 * tx + 2]);
-        const f3 n = make_f3(sh.nrm[r][3 * tx], sh.nrm[r][3 * tx + 1], sh.nrm[r][3 * tx + 2]);
-        const f3 cur = make_f3(sh.col[r][3 * tx], sh.col[r][3 * tx + 1], sh.col[r][3 * tx + 2]);
-        const K1Pixel px = k1_pixel_core<STRIP>(P, x, y, wp, n, cur);
-        const unsigned int lp = pix_index(P, x, y);
-        store_f3(P.cur_noisy_acc, lp, px.new_color);
-        P.cur_spp[lp] = px.spp;
-        P.prev_pixels[lp] = make_float2(px.prev_x, px.prev_y);
-        P.accept[lp] = px.accept;
+        for (int k = 0; k < 4; ++k) {
+            const int r = ty + 8 * k, y = y0 + r;
+            if (y >= yhi) break;
+            if (y < ylo) continue;
+            const f3 wp = make_f3(sh.pos[r][3 * tx], sh.pos[r][3 * tx + 1], sh.pos[r][3 * tx + 2]);
+            const f3 n = make_f3(sh.nrm[r][3 * tx], sh.nrm[r][3 * tx + 1], sh.nrm[r][3 * tx + 2]);
+            const f3 cur = make_f3(sh.col[r][3 * tx], sh.col[r][3 * tx + 1], sh.col[r][3 * tx + 2]);
+            reproject_store<STRIP>(P, x, y, k1_pixel_core<STRIP>(P, x, y, wp, n, cur), zone);
+        }
     }
+    if (zone) halo_finish(P.halo_r);
 }
 
 // --------------------------------------------------------------------------------------------
@@ -1099,8 +1122,11 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_GRAM_MIN_BLOCKS) fit_gram_ker
 // --------------------------------------------------------------------------------------------
 static bool is_strip(const KParams& P) { return P.row0 != 0 || P.row1 != P.H; }
 
+// Measured at 1080p (profiles/r02_h_*): 51.8 us with the tiles staged by TMA, 51.6 us with per-thread loads — the
+// reprojection is bound by its 430 instructions and 40 tap loads per pixel, not by the first round trip.  Kept as a
+// build option, off.
 #ifndef BMFR_REPROJECT_TMA
-#define BMFR_REPROJECT_TMA 1
+#define BMFR_REPROJECT_TMA 0
 #endif
 cudaError_t launch_reproject(const KParams& P, cudaStream_t st) {
     const int rows = P.row1 - P.row0;

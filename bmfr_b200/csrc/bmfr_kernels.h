@@ -7,6 +7,32 @@
 #define BMFR_FIT_THREADS 256  // LOCAL_SIZE, bmfr.cpp:116
 #define BMFR_ROWS_PER_THREAD 4
 
+// Strip contexts with connected neighbours: what one kernel of a frame (the reprojection, or the post pass) does for the
+// halo exchange itself (option A: peer stores from inside the kernels).  Only the CTAs of the "zone" — those
+// that cover rows within halo_rows of a strip edge with a neighbour — take part: they are the only ones whose gathers can
+// reach halo rows and the only ones that own rows a neighbour mirrors.
+//   prologue : one thread polls this context's flags until the neighbours' rows of the frames named below have arrived
+//              (and the neighbours are done reading what this kernel's pushes overwrite);
+//   body     : every store to a row of push_y0..push_y1 is repeated into the neighbour's halo (peer-mapped memory);
+//   epilogue : the last zone CTA to finish raises the neighbours' flag to signal_value.
+struct HaloK {
+    unsigned int* flags;            // this context's flags: [0],[1] early from above / below, [4],[5] late, [2] a wait timed out
+    unsigned int wait_early, wait_late;  // poll until early >= wait_early and late >= wait_late on every connected side (0: none)
+    int side_on[2];                 // neighbour connected above / below
+    int zone_y[2];                  // rows y < zone_y[0] or y >= zone_y[1] belong to the zone
+    int push_y0[2], push_y1[2];     // image rows of this context stored a second time into the neighbour on that side
+    float* peer_a[2];               // reprojection: the neighbour's accumulated noisy colour; post: its accumulated filtered colour
+    float* peer_b[2];               // post: the neighbour's TAA result
+    unsigned char* peer_c[2];       // reprojection: the neighbour's spp
+    int peer_row0[2];               // first image row the neighbour's buffers hold
+    unsigned int* peer_flag[2];     // the flag of the neighbour this kernel raises
+    unsigned int signal_value;
+    unsigned int* done_counter;     // zone CTAs of this launch that have finished (reset by the last one)
+    unsigned int zone_ctas;
+    unsigned long long timeout_ns;
+    int active;                     // 0: no neighbour, nothing of the above happens
+};
+
 // Everything a kernel of one frame needs; passed by value as a __grid_constant__.
 struct KParams {
     int W, H;            // IMAGE_WIDTH / IMAGE_HEIGHT (full image)
@@ -57,6 +83,7 @@ struct KParams {
     int* oob_flag;                // set when a gather needed a row outside [row0,row1)
     int* block_counter;           // FUSED fit: dynamic block schedule, reset by the reprojection (STAGED: noise-tile kernel) of the frame
     float* tri;                   // FUSED fit: level-1 triangles between the two levels of the TSQR, blocks x 4 x 136 floats
+    HaloK halo_r, halo_p;         // halo exchange duties of the reprojection / the post pass (FUSED strips)
     int fit_method;               // host side only: BMFR_FIT_GRAM / BMFR_FIT_TSQR (which FUSED fit kernel launch_fit_qr starts)
     int plain_launch;             // host side only: launch the FUSED kernels without programmatic stream serialization
 };

@@ -105,7 +105,7 @@ struct bmfr_ctx {
 
     // peer-to-peer halo exchange (sharded contexts): the neighbour above (side 0) / below (side 1)
     struct Peer {
-        bool connected = false, ipc = false;
+        bool connected = false, ipc = false, same_device = false;
         int row0 = 0, row1 = 0, own_y0 = 0, own_y1 = 0;    // the neighbour's geometry
         float* noisy_acc[2] = {nullptr, nullptr};          // its state buffers (peer-mapped), by physical index
         unsigned char* spp[2] = {nullptr, nullptr};
@@ -113,12 +113,12 @@ struct bmfr_ctx {
         float* result[2] = {nullptr, nullptr};
         unsigned int* flags = nullptr;                     // its flag pair; this context signals flags[1 - side]
     } peer[2];
-    cudaStream_t halo_stream = nullptr;               // early push (accumulated colour + spp) overlaps fit and post
-    cudaEvent_t halo_ready = nullptr, halo_pushed = nullptr;
-    // [0]: frames completed by the neighbour above, [1]: below; [2]: a wait timed out.  Overlapped frames split the
-    // signal: [0], [1] = frames whose accumulated noisy colour + spp rows have arrived (after the neighbour's
-    // reprojection), [4], [5] = frames whose accumulated filtered colour + TAA rows have arrived (after its post pass)
+    // Written by the neighbours' GPUs: [0], [1] = frames whose accumulated noisy colour + spp rows have arrived from the
+    // neighbour above / below (raised by its reprojection), [4], [5] = frames whose accumulated filtered colour + TAA
+    // rows have arrived (raised by its post pass).  Local: [2] a wait timed out (sticky), [8], [9] zone-CTA counters of
+    // the reprojection / the post pass.
     unsigned int* d_flags = nullptr;
+    bool failed = false;               // a halo wait timed out: the temporal state is no longer trustworthy
     long long seq = 0;                 // frames submitted on this context
 
     // Overlapped frames (params.overlap_frames, FUSED contexts, strips included): reprojection, fit and post pass
@@ -128,7 +128,7 @@ struct bmfr_ctx {
     struct Overlap {
         bool on = false;
         cudaStream_t s_r = nullptr, s_f = nullptr, s_p = nullptr;
-        cudaEvent_t e_in[2] = {}, e_r[2] = {}, e_f[2] = {}, e_p[2] = {}, e_e[2] = {};  // e_e: early halo push done
+        cudaEvent_t e_in[2] = {}, e_r[2] = {}, e_f[2] = {}, e_p[2] = {};
         // the second copy (odd frames) of the per-frame temporaries; even frames use the context's own
         float2* prev_pixels = nullptr;
         unsigned char* accept = nullptr;
@@ -179,7 +179,7 @@ static void free_ctx(bmfr_ctx* c) {
         for (cudaStream_t st : {o.s_r, o.s_f, o.s_p})
             if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
         for (int i = 0; i < 2; ++i)
-            for (cudaEvent_t e : {o.e_in[i], o.e_r[i], o.e_f[i], o.e_p[i], o.e_e[i]})
+            for (cudaEvent_t e : {o.e_in[i], o.e_r[i], o.e_f[i], o.e_p[i]})
                 if (e) cudaEventDestroy(e);
         cudaFree(o.prev_pixels); cudaFree(o.accept); cudaFree(o.weights); cudaFree(o.mins_maxs); cudaFree(o.mins_inv);
         cudaFree(o.noise); cudaFree(o.noise_f); cudaFree(o.counter);
@@ -195,9 +195,6 @@ static void free_ctx(bmfr_ctx* c) {
         }
     }
     cudaFree(c->d_flags);
-    if (c->halo_stream) { cudaStreamSynchronize(c->halo_stream); cudaStreamDestroy(c->halo_stream); }
-    if (c->halo_ready) cudaEventDestroy(c->halo_ready);
-    if (c->halo_pushed) cudaEventDestroy(c->halo_pushed);
     for (int k = 0; k < 4; ++k)
         for (int s = 0; s < kHostSlots; ++s) cudaFree(c->up[k][s]);
     for (int s = 0; s < kHostSlots; ++s) {
@@ -336,7 +333,7 @@ int bmfr_create(const bmfr_params* params, bmfr_ctx** out_ctx) {
     if (st == 0) st = dev_alloc(&c->noise_f, (size_t)(BMFR_FEATURES - 1) * BMFR_BLOCK_PIXELS, "noise_f");
     if (st == 0) st = dev_alloc(&c->d_oob, 2, "oob flag + block counter");
     if (st == 0 && p.mode == BMFR_MODE_FUSED) st = dev_alloc(&c->tri, nb * 4 * 136, "level-1 triangles");
-    if (st == 0) st = dev_alloc(&c->d_flags, 8, "halo flags");
+    if (st == 0) st = dev_alloc(&c->d_flags, 16, "halo flags");
     if (st == 0 && p.mode == BMFR_MODE_STAGED) {
         st = dev_alloc(&c->tmp_data, (size_t)c->tmp_block_rows * g.blocks_x * BMFR_BUFFER_COUNT * BMFR_BLOCK_PIXELS, "tmp_data");
         if (st == 0) st = dev_alloc(&c->filtered, npix * 3, "filtered");
@@ -344,7 +341,7 @@ int bmfr_create(const bmfr_params* params, bmfr_ctx** out_ctx) {
     }
     if (st != 0) return fail(st);
     if ((st = bmfr_check_cuda(cudaMemsetAsync(c->d_oob, 0, 2 * sizeof(int), c->stream), "memset")) != 0) return fail(st);
-    if ((st = bmfr_check_cuda(cudaMemsetAsync(c->d_flags, 0, 8 * sizeof(unsigned int), c->stream), "memset")) != 0) return fail(st);
+    if ((st = bmfr_check_cuda(cudaMemsetAsync(c->d_flags, 0, 16 * sizeof(unsigned int), c->stream), "memset")) != 0) return fail(st);
     // weights of blocks a strip never fits stay defined
     if ((st = bmfr_check_cuda(cudaMemsetAsync(c->weights, 0, nb * BMFR_FEATURES * 3 * sizeof(float), c->stream), "memset")) != 0) return fail(st);
     if ((st = bmfr_check_cuda(cudaMemsetAsync(c->mins_maxs, 0, nb * BMFR_FEATURES_SCALED * 2 * sizeof(float), c->stream), "memset")) != 0) return fail(st);
@@ -363,7 +360,7 @@ int bmfr_create(const bmfr_params* params, bmfr_ctx** out_ctx) {
         for (cudaStream_t* ps : {&o.s_r, &o.s_f, &o.s_p})
             if (st == 0) st = bmfr_check_cuda(cudaStreamCreateWithFlags(ps, cudaStreamNonBlocking), "cudaStreamCreate");
         for (int i = 0; i < 2; ++i)
-            for (cudaEvent_t* pe : {&o.e_in[i], &o.e_r[i], &o.e_f[i], &o.e_p[i], &o.e_e[i]})
+            for (cudaEvent_t* pe : {&o.e_in[i], &o.e_r[i], &o.e_f[i], &o.e_p[i]})
                 if (st == 0) st = bmfr_check_cuda(cudaEventCreateWithFlags(pe, cudaEventDisableTiming), "cudaEventCreate");
         if (st != 0) return fail(st);
         o.on = true;
@@ -384,6 +381,66 @@ int bmfr_get_geometry(const bmfr_ctx* ctx, bmfr_geometry* out) {
 long long bmfr_kernel_launches(const bmfr_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 }  // extern "C"
+
+static bool halo_active(const bmfr_ctx* c) { return c->peer[0].connected || c->peer[1].connected; }
+static bool halo_rows_for(const bmfr_ctx* c, int side, bool late, int* y0, int* y1);
+
+// The halo-exchange duties of this frame's reprojection (early: accumulated noisy colour + spp) and post pass (late:
+// accumulated filtered colour + TAA result); see HaloK in bmfr_kernels.h and DESIGN.md 5 for the protocol:
+//   R(f) waits for early >= f (the rows it gathers from have arrived; and the neighbours' R(f-1) zone no longer reads the
+//        halo rows this frame's pushes overwrite — same physical buffer, two frames apart) and late >= f-1 (their fit /
+//        post pass of frame f-2, which read that buffer as "current", are done); raises early to f+1;
+//   P(f) waits for late >= f (history rows arrived; their P(f-1) zone no longer reads what this frame's pushes
+//        overwrite); raises late to f+1.
+// Every wait refers to frames submitted earlier on both sides, so the order of submission is a schedule that never
+// blocks — in order (one stream) as well as with overlapped frames (three streams).
+static void fill_halo(bmfr_ctx* c, KParams& P) {
+    if (!halo_active(c) || c->prm.mode != BMFR_MODE_FUSED) return;
+    const bmfr_geometry& g = c->geo;
+    const unsigned int f = (unsigned int)c->seq;
+    const int cur = c->noisy_acc.swapped ? 0 : 1;  // physical index of the buffers this frame writes (all four swap together)
+    const unsigned long long timeout_ns = (unsigned long long)(c->prm.halo_timeout_ms > 0 ? c->prm.halo_timeout_ms : 10000) * 1000000ull;
+    for (int late = 0; late < 2; ++late) {
+        HaloK& h = late ? P.halo_p : P.halo_r;
+        h.active = 1;
+        h.flags = c->d_flags;
+        h.wait_early = late ? 0u : f;
+        h.wait_late = late ? f : (f >= 1 ? f - 1 : 0u);
+        h.signal_value = f + 1;
+        h.done_counter = c->d_flags + 8 + late;
+        h.timeout_ns = timeout_ns;
+        h.zone_y[0] = c->peer[0].connected ? g.own_y0 + c->prm.halo_rows : -(1 << 30);
+        h.zone_y[1] = c->peer[1].connected ? g.own_y1 - c->prm.halo_rows : (1 << 30);
+        for (int s = 0; s < 2; ++s) {
+            const bmfr_ctx::Peer& pr = c->peer[s];
+            h.side_on[s] = pr.connected ? 1 : 0;
+            h.push_y0[s] = h.push_y1[s] = 0;
+            if (!pr.connected) continue;
+            int y0, y1;
+            if (halo_rows_for(c, s, late != 0, &y0, &y1)) { h.push_y0[s] = y0; h.push_y1[s] = y1; }
+            h.peer_row0[s] = pr.row0;
+            h.peer_a[s] = late ? pr.accum[cur] : pr.noisy_acc[cur];
+            h.peer_b[s] = late ? pr.result[cur] : nullptr;
+            h.peer_c[s] = late ? nullptr : pr.spp[cur];
+            // the neighbour above sees this context as its "below" neighbour (flag 1) and vice versa
+            h.peer_flag[s] = pr.flags + (late ? 4 : 0) + (s == 0 ? 1 : 0);
+        }
+        // zone CTAs of the launch, counted the way the kernels decide it (halo_in_zone)
+        auto in_zone = [&](int ya, int yb) { return ya < h.zone_y[0] || yb > h.zone_y[1]; };
+        unsigned int n = 0;
+        if (!late) {
+            for (int ya = P.k1_y0; ya < P.k1_y1; ya += 32) n += in_zone(ya, ya + 32) ? 1u : 0u;
+            n *= (unsigned int)((g.width + 31) / 32);
+        } else {
+            for (int by = P.by0; by < P.by1; ++by) {
+                const int y0 = by * 32 - 16 + P.off_y;
+                n += in_zone(y0 - 1, y0 + 33) ? 1u : 0u;
+            }
+            n *= (unsigned int)P.blocks_x;
+        }
+        h.zone_ctas = n;
+    }
+}
 
 // Per-frame argument binding, bmfr.cpp:429-474.
 static void fill_params(bmfr_ctx* c, KParams& P, int frame, const float* d_albedo, const float* d_normal,
@@ -469,12 +526,7 @@ static StageEvents* prof_slot(bmfr_ctx* c, int frame) {
         if (pe) BMFR_CUDA_TRY(cudaEventRecord(pe->ev[i], c->stream)); \
     } while (0)
 
-static int halo_push_early(bmfr_ctx* c);
-static bool halo_active(const bmfr_ctx* c);
-static int halo_ensure_stream(bmfr_ctx* c);
-static int halo_push_part(bmfr_ctx* c, bool late, cudaStream_t st);
-static int halo_wait_split(bmfr_ctx* c, cudaStream_t st, unsigned int early_value, unsigned int late_value);
-static int halo_signal_split(bmfr_ctx* c, cudaStream_t st, bool late);
+static int halo_wait_same_device(bmfr_ctx* c, cudaStream_t st, unsigned int early_value, unsigned int late_value);
 
 static int run_frame(bmfr_ctx* c, const KParams& P, int frame) {
     StageEvents* pe = prof_slot(c, frame);
@@ -484,7 +536,6 @@ static int run_frame(bmfr_ctx* c, const KParams& P, int frame) {
     if (c->prm.mode == BMFR_MODE_STAGED) {
         LAUNCH_TRY(launch_k1(P, c->stream), "accumulate_noisy_data");
         MARK(1);
-        { int hs = halo_push_early(c); if (hs != 0) return hs; }
         if (c->prm.reference_order) LAUNCH_TRY(launch_k2_reference_order(P, c->prm.tmp_half != 0, c->stream), "fitter (reference order)");
         else LAUNCH_TRY(launch_k2(P, c->stream), "fitter");
         MARK(2);
@@ -499,59 +550,30 @@ static int run_frame(bmfr_ctx* c, const KParams& P, int frame) {
         // R(f) | F(f) | P(f) on three streams.  R(f) follows the caller's work on the context's stream and
         // P(f-2): the buffers of this parity (accumulated colour + spp as "current", prev_pixels, accept,
         // noise tile, block counter, weights, min/max) were last read by frame f-2.  R(f-1) precedes R(f) on
-        // the same stream (temporal state), as F(f-1) precedes F(f) (triangle scratch) and P(f-1) P(f)
-        // (accumulated filtered colour, TAA history).
-        //
-        // Strips (connected neighbours) add the halo exchange, with the in-order protocol's single "frame done"
-        // flag split in two so that it does not serialise the frames again:
-        //   early (after R(f)) : push accumulated noisy colour + spp rows, raise the neighbours' early flag to f+1
-        //   late  (after P(f)) : push accumulated filtered colour + TAA rows, raise their late flag to f+1
-        //   R(f) waits for early >= f (the rows it gathers from; also: the neighbours' R(f-1) no longer reads the
-        //        halo rows this context's early push of frame f overwrites) and late >= f-1 (their F/P(f-2), which
-        //        read the same physical buffers as "current", are done);
-        //   P(f) waits for late >= f (the history rows it gathers from; also: their P(f-1) no longer reads what
-        //        this context's late push of frame f overwrites).
-        // Every wait refers to frames submitted earlier on both sides, so the order of submission is a schedule
-        // that never blocks.
+        // the same stream (temporal state), as F(f-1) precedes F(f) (scratch of the fit) and P(f-1) P(f)
+        // (accumulated filtered colour, TAA history).  Strips: the halo exchange happens inside R and P (fill_halo).
         bmfr_ctx::Overlap& o = c->ov;
         const int q = c->parity();
-        const bool halo = halo_active(c);
-        const unsigned int f = (unsigned int)c->seq;
-        if (halo) { int hs = halo_ensure_stream(c); if (hs != 0) return hs; }
         BMFR_CUDA_TRY(cudaEventRecord(o.e_in[q], c->stream));
         BMFR_CUDA_TRY(cudaStreamWaitEvent(o.s_r, o.e_in[q], 0));
-        if (c->seq >= 2) {
-            BMFR_CUDA_TRY(cudaStreamWaitEvent(o.s_r, o.e_p[q], 0));
-            if (halo) BMFR_CUDA_TRY(cudaStreamWaitEvent(o.s_r, o.e_e[q], 0));  // the early push of frame f-2 has read its rows
-        }
-        if (halo && f >= 1) { int hs = halo_wait_split(c, o.s_r, f, f - 1); if (hs != 0) return hs; }
+        if (c->seq >= 2) BMFR_CUDA_TRY(cudaStreamWaitEvent(o.s_r, o.e_p[q], 0));
+        { int hs = halo_wait_same_device(c, o.s_r, P.halo_r.wait_early, P.halo_r.wait_late); if (hs != 0) return hs; }
         LAUNCH_TRY(launch_reproject(P, o.s_r), "reproject_kernel");
         BMFR_CUDA_TRY(cudaEventRecord(o.e_r[q], o.s_r));
-        if (halo) {
-            BMFR_CUDA_TRY(cudaStreamWaitEvent(c->halo_stream, o.e_r[q], 0));
-            int hs = halo_push_part(c, false, c->halo_stream);
-            if (hs == 0) hs = halo_signal_split(c, c->halo_stream, false);
-            if (hs != 0) return hs;
-            BMFR_CUDA_TRY(cudaEventRecord(o.e_e[q], c->halo_stream));
-        }
         BMFR_CUDA_TRY(cudaStreamWaitEvent(o.s_f, o.e_r[q], 0));
-        LAUNCH_TRY(launch_fit_qr(P, o.s_f), "fit_qr_kernel");
+        LAUNCH_TRY(launch_fit_qr(P, o.s_f), "fit kernel");
         BMFR_CUDA_TRY(cudaEventRecord(o.e_f[q], o.s_f));
         BMFR_CUDA_TRY(cudaStreamWaitEvent(o.s_p, o.e_f[q], 0));
-        if (halo && f >= 1) { int hs = halo_wait_split(c, o.s_p, 0, f); if (hs != 0) return hs; }
+        { int hs = halo_wait_same_device(c, o.s_p, 0, P.halo_p.wait_late); if (hs != 0) return hs; }
         LAUNCH_TRY(launch_post(P, o.s_p), "post_kernel");
-        if (halo) {
-            int hs = halo_push_part(c, true, o.s_p);
-            if (hs == 0) hs = halo_signal_split(c, o.s_p, true);
-            if (hs != 0) return hs;
-        }
         BMFR_CUDA_TRY(cudaEventRecord(o.e_p[q], o.s_p));
     } else {
+        { int hs = halo_wait_same_device(c, c->stream, P.halo_r.wait_early, P.halo_r.wait_late); if (hs != 0) return hs; }
         LAUNCH_TRY(launch_reproject(P, c->stream), "reproject_kernel");
         MARK(1);
-        { int hs = halo_push_early(c); if (hs != 0) return hs; }
-        LAUNCH_TRY(launch_fit_qr(P, c->stream), "fit_qr_kernel");
+        LAUNCH_TRY(launch_fit_qr(P, c->stream), "fit kernel");
         MARK(2);
+        { int hs = halo_wait_same_device(c, c->stream, 0, P.halo_p.wait_late); if (hs != 0) return hs; }
         LAUNCH_TRY(launch_post(P, c->stream), "post_kernel");
         MARK(3);
     }
@@ -559,85 +581,29 @@ static int run_frame(bmfr_ctx* c, const KParams& P, int frame) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Peer-to-peer halo exchange (option A).  After its kernels of frame s a context copies the
-// boundary rows it owns of the four state buffers it has just written straight into the neighbours'
-// halo rows (peer memory, NVLink) and then raises the neighbours' flag to s; before the kernels of
-// frame s+1 it waits for its own two flags to reach s.  The flag protocol also orders the
-// write-after-read hazard: a neighbour can push frame s+1 only after it has run frame s+1, which it
-// starts only after this context's flag for frame s — i.e. after this context is done with frame s.
+// Peer-to-peer halo exchange (option A).  The exchange itself lives in the kernels (HaloK, fill_halo):
+// zone CTAs of the reprojection / the post pass poll this context's flags in their prologue, store the rows a
+// neighbour mirrors a second time into its memory (peer-mapped, NVLink) and the last of them raises the neighbour's
+// flag — no copy, signal or wait launches.
+//
+// One exception.  Contexts connected INSIDE one process on ONE device (how the strip logic is tested on a single-GPU
+// box) must not spin inside a full-size grid: the kernel they wait for may not be resident yet, and nothing guarantees
+// that two grids of one device run at the same time (B200_PROFILING.md).  For such neighbours a one-thread kernel does
+// the waiting in front of the launch — it occupies one CTA slot only — and the in-kernel poll then passes at once.
 // ------------------------------------------------------------------------------------------------
-struct HaloSegment {
-    const unsigned char* src;
-    unsigned char* dst;
-    unsigned long long bytes;
-};
-struct HaloCopy {
-    HaloSegment seg[8];
-    int count;
-};
-
-__global__ void halo_push_kernel(const __grid_constant__ HaloCopy hc) {
-    const HaloSegment s = hc.seg[blockIdx.y];
-    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if ((((uintptr_t)s.src | (uintptr_t)s.dst | s.bytes) & 15) == 0) {
-        const uint4* a = reinterpret_cast<const uint4*>(s.src);
-        uint4* b = reinterpret_cast<uint4*>(s.dst);
-        for (unsigned long long i = tid; i < s.bytes / 16; i += stride) b[i] = a[i];
-    } else if ((((uintptr_t)s.src | (uintptr_t)s.dst | s.bytes) & 3) == 0) {
-        const unsigned int* a = reinterpret_cast<const unsigned int*>(s.src);
-        unsigned int* b = reinterpret_cast<unsigned int*>(s.dst);
-        for (unsigned long long i = tid; i < s.bytes / 4; i += stride) b[i] = a[i];
-    } else {
-        for (unsigned long long i = tid; i < s.bytes; i += stride) s.dst[i] = s.src[i];
-    }
-}
-
-__global__ void halo_signal_kernel(unsigned int* flag_a, unsigned int* flag_b, unsigned int value) {
-    __threadfence_system();
-    if (flag_a) *reinterpret_cast<volatile unsigned int*>(flag_a) = value;
-    if (flag_b) *reinterpret_cast<volatile unsigned int*>(flag_b) = value;
-    __threadfence_system();
-}
-
-// One thread polls this context's flags (written by the neighbours' GPUs).  Bounded: a neighbour that
-// never arrives sets flags[2] instead of hanging the device (reported by bmfr_sync).
-__global__ void halo_wait_kernel(unsigned int* flags, int need_a, int need_b, unsigned int value) {
-    const long long t0 = clock64();
-    const long long limit = 4000000000ll;  // ~2 s at 2 GHz
-    for (;;) {
-        const unsigned int a = *reinterpret_cast<volatile unsigned int*>(flags);
-        const unsigned int b = *reinterpret_cast<volatile unsigned int*>(flags + 1);
-        if ((!need_a || a >= value) && (!need_b || b >= value)) break;
-        if (clock64() - t0 > limit) {
-            flags[2] = 1;
-            break;
-        }
-        __nanosleep(200);
-    }
-    __threadfence_system();
-}
-
-static int halo_wait(bmfr_ctx* c) {
-    if (!(c->peer[0].connected || c->peer[1].connected) || c->seq == 0 || c->ov.on) return BMFR_OK;
-    halo_wait_kernel<<<1, 1, 0, c->stream>>>(c->d_flags, c->peer[0].connected, c->peer[1].connected, (unsigned int)c->seq);
-    int st = bmfr_check_cuda(cudaGetLastError(), "halo_wait_kernel");
-    if (st == 0) ++c->launches;
-    return st;
-}
-
-// Overlapped frames: wait for the early flags (index 0, 1) to reach early_value and the late flags (4, 5) to reach
-// late_value; 0 = do not wait for that kind.
-__global__ void halo_wait_split_kernel(unsigned int* flags, int need_a, int need_b, unsigned int early_value, unsigned int late_value) {
-    const long long t0 = clock64();
-    const long long limit = 4000000000ll;  // ~2 s at 2 GHz
+__global__ void halo_wait_split_kernel(unsigned int* flags, int need_a, int need_b, unsigned int early_value, unsigned int late_value,
+                                       unsigned long long timeout_ns) {
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     for (;;) {
         volatile unsigned int* f = flags;
         const bool a = !need_a || (f[0] >= early_value && f[4] >= late_value);
         const bool b = !need_b || (f[1] >= early_value && f[5] >= late_value);
         if (a && b) break;
-        if (clock64() - t0 > limit) {
-            flags[2] = 1;
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t - t0 > timeout_ns) {
+            flags[2] = 1;  // sticky: the context has failed
             break;
         }
         __nanosleep(200);
@@ -645,9 +611,12 @@ __global__ void halo_wait_split_kernel(unsigned int* flags, int need_a, int need
     __threadfence_system();
 }
 
-static int halo_wait_split(bmfr_ctx* c, cudaStream_t st, unsigned int early_value, unsigned int late_value) {
+static int halo_wait_same_device(bmfr_ctx* c, cudaStream_t st, unsigned int early_value, unsigned int late_value) {
     if (early_value == 0 && late_value == 0) return BMFR_OK;
-    halo_wait_split_kernel<<<1, 1, 0, st>>>(c->d_flags, c->peer[0].connected, c->peer[1].connected, early_value, late_value);
+    const int need_a = c->peer[0].connected && c->peer[0].same_device, need_b = c->peer[1].connected && c->peer[1].same_device;
+    if (!need_a && !need_b) return BMFR_OK;
+    const unsigned long long timeout_ns = (unsigned long long)(c->prm.halo_timeout_ms > 0 ? c->prm.halo_timeout_ms : 10000) * 1000000ull;
+    halo_wait_split_kernel<<<1, 1, 0, st>>>(c->d_flags, need_a, need_b, early_value, late_value, timeout_ns);
     int rc = bmfr_check_cuda(cudaGetLastError(), "halo_wait_split_kernel");
     if (rc == 0) ++c->launches;
     return rc;
@@ -671,88 +640,11 @@ static bool halo_rows_for(const bmfr_ctx* c, int side, bool late, int* y0, int* 
     return *y0 < *y1;
 }
 
-// late = false: accumulated noisy colour + spp (available after the first kernel of the frame);
-// late = true : accumulated filtered colour + TAA result (after the last kernel).
-static int halo_push_part(bmfr_ctx* c, bool late, cudaStream_t st) {
-    const bmfr_geometry& g = c->geo;
-    const size_t W = (size_t)g.width;
-    const int cur = c->noisy_acc.swapped ? 0 : 1;  // physical index of the buffers this frame writes (all four swap together)
-    HaloCopy hc;
-    memset(&hc, 0, sizeof(hc));
-    for (int side = 0; side < 2; ++side) {
-        const bmfr_ctx::Peer& pr = c->peer[side];
-        int y0, y1;
-        if (!pr.connected || !halo_rows_for(c, side, late, &y0, &y1)) continue;
-        const size_t so = (size_t)(y0 - g.row0) * W, dof = (size_t)(y0 - pr.row0) * W, n = (size_t)(y1 - y0) * W;
-        if (late) {
-            hc.seg[hc.count++] = HaloSegment{(const unsigned char*)(c->accum.buf[cur] + so * 3), (unsigned char*)(pr.accum[cur] + dof * 3), n * 12};
-            hc.seg[hc.count++] = HaloSegment{(const unsigned char*)(c->result.buf[cur] + so * 3), (unsigned char*)(pr.result[cur] + dof * 3), n * 12};
-        } else {
-            hc.seg[hc.count++] = HaloSegment{(const unsigned char*)(c->noisy_acc.buf[cur] + so * 3), (unsigned char*)(pr.noisy_acc[cur] + dof * 3), n * 12};
-            hc.seg[hc.count++] = HaloSegment{c->spp.buf[cur] + so, pr.spp[cur] + dof, n};
-        }
-    }
-    if (hc.count == 0) return BMFR_OK;
-    halo_push_kernel<<<dim3(48, hc.count), 256, 0, st>>>(hc);
-    int rc = bmfr_check_cuda(cudaGetLastError(), "halo_push_kernel");
-    if (rc == 0) ++c->launches;
-    return rc;
-}
-
-static bool halo_active(const bmfr_ctx* c) { return c->peer[0].connected || c->peer[1].connected; }
-
-static int halo_ensure_stream(bmfr_ctx* c) {
-    if (!c->halo_stream) {
-        BMFR_CUDA_TRY(cudaStreamCreateWithFlags(&c->halo_stream, cudaStreamNonBlocking));
-        BMFR_CUDA_TRY(cudaEventCreateWithFlags(&c->halo_ready, cudaEventDisableTiming));
-        BMFR_CUDA_TRY(cudaEventCreateWithFlags(&c->halo_pushed, cudaEventDisableTiming));
-    }
-    return BMFR_OK;
-}
-
-// Overlapped frames: raise the neighbours' early (late = false) or late flag to "frames completed" = seq + 1.
-static int halo_signal_split(bmfr_ctx* c, cudaStream_t st, bool late) {
-    const int k = late ? 4 : 0;
-    // the neighbour above sees this context as its "below" neighbour (flag 1) and vice versa
-    unsigned int* fa = c->peer[0].connected ? c->peer[0].flags + k + 1 : nullptr;
-    unsigned int* fb = c->peer[1].connected ? c->peer[1].flags + k + 0 : nullptr;
-    halo_signal_kernel<<<1, 1, 0, st>>>(fa, fb, (unsigned int)(c->seq + 1));
-    int rc = bmfr_check_cuda(cudaGetLastError(), "halo_signal_kernel");
-    if (rc == 0) ++c->launches;
-    return rc;
-}
-
-// after the kernel that produced the accumulated noisy colour and spp: push them on the side stream
-static int halo_push_early(bmfr_ctx* c) {
-    if (!halo_active(c) || c->ov.on) return BMFR_OK;
-    { int hs = halo_ensure_stream(c); if (hs != 0) return hs; }
-    BMFR_CUDA_TRY(cudaEventRecord(c->halo_ready, c->stream));
-    BMFR_CUDA_TRY(cudaStreamWaitEvent(c->halo_stream, c->halo_ready, 0));
-    int st = halo_push_part(c, false, c->halo_stream);
-    if (st != 0) return st;
-    BMFR_CUDA_TRY(cudaEventRecord(c->halo_pushed, c->halo_stream));
-    return BMFR_OK;
-}
-
-// after the last kernel: push the rest, then raise the neighbours' flags
-static int halo_push_late(bmfr_ctx* c) {
-    if (!halo_active(c) || c->ov.on) return BMFR_OK;  // (overlapped frames: run_frame does the exchange)
-    int st = halo_push_part(c, true, c->stream);
-    if (st != 0) return st;
-    BMFR_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->halo_pushed, 0));
-    // the neighbour above sees this context as its "below" neighbour (flag 1) and vice versa
-    unsigned int* fa = c->peer[0].connected ? c->peer[0].flags + 1 : nullptr;
-    unsigned int* fb = c->peer[1].connected ? c->peer[1].flags + 0 : nullptr;
-    halo_signal_kernel<<<1, 1, 0, c->stream>>>(fa, fb, (unsigned int)(c->seq + 1));
-    st = bmfr_check_cuda(cudaGetLastError(), "halo_signal_kernel");
-    if (st == 0) ++c->launches;
-    return st;
-}
-
 struct HaloBlob {  // what a neighbour needs to address this context's state: geometry + IPC handles
     unsigned int magic;
     int device, width, height, row0, row1, own_y0, own_y1, swapped;
-    int overlap;  // the two sides must speak the same flag protocol (in-order: one flag per frame; overlapped: two)
+    int mode;
+    unsigned char uuid[16];  // of the device: a neighbour on the SAME device is waited for by a one-thread kernel, not in-kernel
     long long seq;
     cudaIpcMemHandle_t noisy_acc[2], spp[2], accum[2], result[2], flags;
 };
@@ -769,13 +661,12 @@ int bmfr_denoise_frame(bmfr_ctx* c, int frame, const float* d_albedo, const floa
     if (frame > 0 && !c->has_prev)
         return bmfr_set_error(BMFR_ERR_SEQUENCE, "bmfr_denoise_frame: frame %d submitted before any frame 0", frame);
     BMFR_CUDA_TRY(cudaSetDevice(c->prm.device));
+    if (c->failed)
+        return bmfr_set_error(BMFR_ERR_SEQUENCE, "bmfr_denoise_frame: a halo wait of this context timed out earlier; its temporal state is "
+                                                 "not valid any more (destroy it and start the strips again)");
     KParams P;
     fill_params(c, P, frame, d_albedo, d_normal, d_position, d_noisy, cam_prev, pixel_offset, d_out);
-    int st = halo_wait(c);  // the neighbours' rows of the previous frame's state have arrived
-    if (st != 0) return st;
-    st = run_frame(c, P, frame);
-    if (st != 0) return st;
-    st = halo_push_late(c);  // the rest of this frame's boundary rows -> the neighbours' halo rows, then their flags
+    int st = run_frame(c, P, frame);
     if (st != 0) return st;
     ++c->seq;
     // swap all double buffers, bmfr.cpp:483-484
@@ -855,7 +746,6 @@ int bmfr_join(bmfr_ctx* c) {
     BMFR_CUDA_TRY(cudaSetDevice(c->prm.device));
     // P(f) is the last kernel of frame f, and the post passes run in order on one stream
     BMFR_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ov.e_p[c->last_parity()], 0));
-    if (halo_active(c)) BMFR_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ov.e_e[c->last_parity()], 0));
     return BMFR_OK;
 }
 
@@ -864,15 +754,16 @@ int bmfr_sync(bmfr_ctx* c) {
     BMFR_CUDA_TRY(cudaSetDevice(c->prm.device));
     if (c->h2d_stream) BMFR_CUDA_TRY(cudaStreamSynchronize(c->h2d_stream));
     BMFR_CUDA_TRY(cudaStreamSynchronize(c->stream));
-    for (cudaStream_t st : {c->ov.s_r, c->ov.s_f, c->ov.s_p, c->ov.on ? c->halo_stream : (cudaStream_t) nullptr})
+    for (cudaStream_t st : {c->ov.s_r, c->ov.s_f, c->ov.s_p})
         if (st) BMFR_CUDA_TRY(cudaStreamSynchronize(st));
     if (c->d2h_stream) BMFR_CUDA_TRY(cudaStreamSynchronize(c->d2h_stream));
     unsigned int timed_out = 0;
     BMFR_CUDA_TRY(cudaMemcpy(&timed_out, c->d_flags + 2, sizeof(unsigned int), cudaMemcpyDeviceToHost));
-    if (timed_out) {
-        cudaMemset(c->d_flags + 2, 0, sizeof(unsigned int));
-        return bmfr_set_error(BMFR_ERR_SEQUENCE, "bmfr_sync: a neighbouring strip did not deliver its halo rows within 2 s "
-                                                 "(the contexts must submit the same frames)");
+    if (timed_out || c->failed) {  // sticky: the frame ran on stale halo rows and nothing was signalled to the neighbours
+        c->failed = true;
+        return bmfr_set_error(BMFR_ERR_SEQUENCE, "bmfr_sync: a neighbouring strip did not deliver its halo rows within %d ms (the contexts "
+                                                 "must submit the same frames); this context has failed and refuses further frames",
+                              c->prm.halo_timeout_ms > 0 ? c->prm.halo_timeout_ms : 10000);
     }
     int oob = 0;
     BMFR_CUDA_TRY(cudaMemcpy(&oob, c->d_oob, sizeof(int), cudaMemcpyDeviceToHost));
@@ -971,8 +862,12 @@ static int halo_check_neighbour(const bmfr_ctx* c, int side, int n_w, int n_h, i
     if ((side == 0 && g.row0 < n_own_y0) || (side == 1 && g.row1 > n_own_y1) || (side == 0 && n_row1 > g.own_y1) ||
         (side == 1 && n_row0 < g.own_y0))
         return bmfr_set_error(BMFR_ERR_UNSUPPORTED, "halo connect: halo_rows exceed the neighbouring strip (strips must be at least halo_rows tall)");
-    if (n_swapped != (c->noisy_acc.swapped ? 1 : 0) || n_seq != c->seq)
-        return bmfr_set_error(BMFR_ERR_SEQUENCE, "halo connect: the two contexts have not submitted the same frames");
+    if (c->prm.mode != BMFR_MODE_FUSED)
+        return bmfr_set_error(BMFR_ERR_UNSUPPORTED, "halo connect: the in-library halo exchange lives in the FUSED kernels (STAGED strips: "
+                                                    "refresh the state rows yourself, bmfr_get_halo_plan)");
+    // the flags count frames from zero and the halo rows of frames submitted earlier were never exchanged
+    if (c->seq != 0 || n_seq != 0 || n_swapped != (c->noisy_acc.swapped ? 1 : 0))
+        return bmfr_set_error(BMFR_ERR_SEQUENCE, "halo connect: contexts must be connected before their first frame");
     return BMFR_OK;
 }
 
@@ -983,7 +878,12 @@ int bmfr_halo_export(bmfr_ctx* c, void* blob, size_t blob_bytes) {
     memset(&b, 0, sizeof(b));
     b.magic = kHaloMagic; b.device = c->prm.device; b.width = c->geo.width; b.height = c->geo.height;
     b.row0 = c->geo.row0; b.row1 = c->geo.row1; b.own_y0 = c->geo.own_y0; b.own_y1 = c->geo.own_y1;
-    b.swapped = c->noisy_acc.swapped ? 1 : 0; b.seq = c->seq; b.overlap = c->ov.on ? 1 : 0;
+    b.swapped = c->noisy_acc.swapped ? 1 : 0; b.seq = c->seq; b.mode = c->prm.mode;
+    {
+        cudaDeviceProp prop;
+        BMFR_CUDA_TRY(cudaGetDeviceProperties(&prop, c->prm.device));
+        memcpy(b.uuid, &prop.uuid, 16);
+    }
     for (int i = 0; i < 2; ++i) {
         BMFR_CUDA_TRY(cudaIpcGetMemHandle(&b.noisy_acc[i], c->noisy_acc.buf[i]));
         BMFR_CUDA_TRY(cudaIpcGetMemHandle(&b.spp[i], c->spp.buf[i]));
@@ -1002,9 +902,7 @@ int bmfr_halo_connect(bmfr_ctx* c, int side, const void* neighbour_blob, size_t 
     if (b.magic != kHaloMagic) return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_halo_connect: not a bmfr_halo_export blob");
     int st = halo_check_neighbour(c, side, b.width, b.height, b.own_y0, b.own_y1, b.row0, b.row1, b.swapped, b.seq);
     if (st != 0) return st;
-    if ((b.overlap != 0) != c->ov.on)
-        return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_halo_connect: the neighbour was created with overlap_frames = %d, this "
-                                                         "context with %d", b.overlap, c->ov.on ? 1 : 0);
+    if (b.mode != BMFR_MODE_FUSED) return bmfr_set_error(BMFR_ERR_UNSUPPORTED, "bmfr_halo_connect: the neighbour is not a FUSED context");
     BMFR_CUDA_TRY(cudaSetDevice(c->prm.device));
     bmfr_ctx::Peer& pr = c->peer[side];
     const unsigned int fl = cudaIpcMemLazyEnablePeerAccess;
@@ -1017,6 +915,11 @@ int bmfr_halo_connect(bmfr_ctx* c, int side, const void* neighbour_blob, size_t 
     BMFR_CUDA_TRY(cudaIpcOpenMemHandle((void**)&pr.flags, b.flags, fl));
     pr.row0 = b.row0; pr.row1 = b.row1; pr.own_y0 = b.own_y0; pr.own_y1 = b.own_y1;
     pr.ipc = true;
+    {
+        cudaDeviceProp prop;
+        BMFR_CUDA_TRY(cudaGetDeviceProperties(&prop, c->prm.device));
+        pr.same_device = memcmp(b.uuid, &prop.uuid, 16) == 0;
+    }
     pr.connected = true;
     return BMFR_OK;
 }
@@ -1026,8 +929,7 @@ int bmfr_halo_connect_local(bmfr_ctx* c, int side, bmfr_ctx* n) {
     int st = halo_check_neighbour(c, side, n->geo.width, n->geo.height, n->geo.own_y0, n->geo.own_y1, n->geo.row0, n->geo.row1,
                                   n->noisy_acc.swapped ? 1 : 0, n->seq);
     if (st != 0) return st;
-    if (n->ov.on != c->ov.on)
-        return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_halo_connect_local: the two contexts differ in overlap_frames");
+    if (n->prm.mode != BMFR_MODE_FUSED) return bmfr_set_error(BMFR_ERR_UNSUPPORTED, "bmfr_halo_connect_local: the neighbour is not a FUSED context");
     if (n->prm.device != c->prm.device) {
         BMFR_CUDA_TRY(cudaSetDevice(c->prm.device));
         int can = 0;
@@ -1045,6 +947,7 @@ int bmfr_halo_connect_local(bmfr_ctx* c, int side, bmfr_ctx* n) {
     pr.flags = n->d_flags;
     pr.row0 = n->geo.row0; pr.row1 = n->geo.row1; pr.own_y0 = n->geo.own_y0; pr.own_y1 = n->geo.own_y1;
     pr.ipc = false;
+    pr.same_device = n->prm.device == c->prm.device;
     pr.connected = true;
     return BMFR_OK;
 }

@@ -46,6 +46,21 @@ __device__ __forceinline__ void stf3(float* __restrict__ b, unsigned int i, f3 v
     else store_f3(b, i, v);
 }
 
+// Strips: a row a neighbour mirrors is stored a second time, into the neighbour's halo (peer memory over NVLink).
+// which = 0: accumulated filtered colour, 1: TAA result.
+template <bool STRIP>
+__device__ __forceinline__ void post_push(const KParams& P, int which, int x, int y, f3 v) {
+    if (!STRIP || !P.halo_p.active) return;
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const long long pi = halo_peer_index(P.halo_p, P, s, x, y);
+        if (pi >= 0) {
+            float* dst = (which ? P.halo_p.peer_b[s] : P.halo_p.peer_a[s]) + pi * 3;
+            dst[0] = v.x; dst[1] = v.y; dst[2] = v.z;
+        }
+    }
+}
+
 __device__ __forceinline__ float fast_rcp(float v) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
@@ -145,7 +160,7 @@ __device__ __forceinline__ void weighted_sum_px4(const f3 (&n)[4], const f3 (&p)
 // albedo, fetched by the caller together with the features (one round of independent loads).
 template <bool STRIP, bool WIDE>
 __device__ __forceinline__ f3 accumulate_filtered_px(const KParams& P, unsigned int lp, f3 filtered, unsigned int accept,
-                                                     float2 pp, unsigned int spp, f3 alb, bool store) {
+                                                     float2 pp, unsigned int spp, f3 alb, bool store, int x, int y) {
     f3 prev = make_f3(0.f, 0.f, 0.f);
     float alpha = 1.f;
     if (P.frame > 0 && accept != 0) {
@@ -180,7 +195,10 @@ __device__ __forceinline__ f3 accumulate_filtered_px(const KParams& P, unsigned 
     const float oma = 1.f - alpha;
     const f3 accum = make_f3(fmaf(alpha, filtered.x, oma * prev.x), fmaf(alpha, filtered.y, oma * prev.y),
                              fmaf(alpha, filtered.z, oma * prev.z));
-    if (store) stf3<WIDE>(P.accum_cur, lp, accum);
+    if (store) {
+        stf3<WIDE>(P.accum_cur, lp, accum);
+        post_push<STRIP>(P, 0, x, y, accum);
+    }
     return make_f3(tone_map_fast(alb.x * accum.x), tone_map_fast(alb.y * accum.y), tone_map_fast(alb.z * accum.z));
 }
 
@@ -269,7 +287,7 @@ template <bool STRIP, bool WIDE>
 __device__ __forceinline__ bool finish_pixel(PostShared& sh, const KParams& P, const PixelIn& in, f3 filtered, int hx, int hy, int x,
                                              int y, bool store, bool own, f3& hist) {
     const bool temporal = own && history_sample<STRIP, WIDE>(P, in.pp, hist);
-    const f3 tone = accumulate_filtered_px<STRIP, WIDE>(P, in.lp, filtered, in.accept, in.pp, in.spp, in.alb, store);
+    const f3 tone = accumulate_filtered_px<STRIP, WIDE>(P, in.lp, filtered, in.accept, in.pp, in.spp, in.alb, store, x, y);
     put_ycc(sh, P, hx, hy, x, y, to_ycocg(tone));
     return temporal;
 }
@@ -338,9 +356,11 @@ __global__ void __launch_bounds__(256, BMFR_POST_MIN_BLOCKS) post_kernel(const _
 #endif
     pdl_wait();     // the fit of this frame is complete (weights, min/max)
     // Only now: a successor (the next frame's reprojection) starts once every CTA of this grid has passed
-    // this point, so "this frame's fit and reprojection are complete" holds for it too — it reads their
-    // outputs before its own wait, and only its stores to prev_pixels / accept wait for this grid.
+    // this point, so "this frame's fit and reprojection are complete" holds for it too.
     pdl_trigger();
+    // strips: a CTA near a strip edge waits for the neighbours' accumulated colour / TAA rows of the previous frame
+    const bool zone = STRIP && halo_in_zone(P.halo_p, y0 - 1, y0 + 33);
+    if (zone) halo_poll(P.halo_p);
 
 
     // coefficients of the 3x3 block neighbourhood -> shared memory: warp w takes neighbour w (warp 0
@@ -449,7 +469,9 @@ __global__ void __launch_bounds__(256, BMFR_POST_MIN_BLOCKS) post_kernel(const _
         }
         stf3<WIDE>(P.result_cur, lp, out);
         if (P.user_out) stf3<WIDE>(P.user_out, lp, out);
+        post_push<STRIP>(P, 1, x, y0 + 4 * warp + s, out);
     }
+    if (zone) halo_finish(P.halo_p);
 }
 
 
@@ -535,7 +557,7 @@ __device__ __forceinline__ bool staged_pixel(PostStage& sh, const KParams& P, co
     const PixelIn in = load_pixel_staged(sh, P, G, hx, hy, x, y);
     const f3 filtered = weighted_sum_px(in.n, in.p, cf);
     const bool temporal = own && history_sample<STRIP, false>(P, in.pp, hist);
-    const f3 tone = accumulate_filtered_px<STRIP, false>(P, in.lp, filtered, in.accept, in.pp, in.spp, in.alb, store);
+    const f3 tone = accumulate_filtered_px<STRIP, false>(P, in.lp, filtered, in.accept, in.pp, in.spp, in.alb, store, x, y);
     put_ycc_i(sh, P, G, hx, hy, x, y, to_ycocg(tone));
     return temporal;
 }
@@ -588,6 +610,7 @@ __device__ __forceinline__ bool resolve_pixel(PostStage& sh, const KParams& P, c
     const float oma = 1.f - alpha;
     const f3 accum = make_f3(fmaf(alpha, filtered.x, oma * prev.x), fmaf(alpha, filtered.y, oma * prev.y), fmaf(alpha, filtered.z, oma * prev.z));
     store_f3(P.accum_cur, in.lp, accum);
+    post_push<STRIP>(P, 0, x, y, accum);
     const f3 tone = make_f3(tone_map_fast(in.alb.x * accum.x), tone_map_fast(in.alb.y * accum.y), tone_map_fast(in.alb.z * accum.z));
     put_ycc_i(sh, P, G, hx, hy, x, y, to_ycocg(tone));
 
@@ -657,6 +680,9 @@ __global__ void __launch_bounds__(256, BMFR_POST_TMA_MIN_BLOCKS) post_tma_kernel
     }
     pdl_wait();     // the fit of this frame is complete (weights, min/max)
     pdl_trigger();  // only now, so that "this frame's fit and reprojection are complete" also holds for the successor
+    // strips: a CTA near a strip edge waits for the neighbours' accumulated colour / TAA rows of the previous frame
+    const bool zone = STRIP && halo_in_zone(P.halo_p, G.y0 - 1, G.y0 + 33);
+    if (zone) halo_poll(P.halo_p);
 
     // coefficients of the 3x3 block neighbourhood -> shared memory (as in post_kernel)
     for (int nb = warp; nb < 9; nb += 8) {
@@ -739,6 +765,8 @@ __global__ void __launch_bounds__(256, BMFR_POST_TMA_MIN_BLOCKS) post_tma_kernel
                 weighted_sum_px2(i0.n, i0.p, i1.n, i1.p, sh.coef[4], fl0, fl1);
                 store_f3(P.accum_cur, i0.lp, fl0);
                 store_f3(P.accum_cur, i1.lp, fl1);
+                post_push<STRIP>(P, 0, x, y, fl0);
+                post_push<STRIP>(P, 0, x, y + 1, fl1);
                 put_ycc_i(sh, P, G, lane + 1, ty + 1, x, y,
                           to_ycocg(make_f3(tone_map_fast(i0.alb.x * fl0.x), tone_map_fast(i0.alb.y * fl0.y), tone_map_fast(i0.alb.z * fl0.z))));
                 put_ycc_i(sh, P, G, lane + 1, ty + 2, x, y + 1,
@@ -811,7 +839,9 @@ __global__ void __launch_bounds__(256, BMFR_POST_TMA_MIN_BLOCKS) post_tma_kernel
         }
         store_f3(P.result_cur, lp, out);
         if (P.user_out) store_f3(P.user_out, lp, out);
+        post_push<STRIP>(P, 1, x, G.y0 + 4 * warp + s, out);
     }
+    if (zone) halo_finish(P.halo_p);
 }
 
 #ifndef BMFR_POST_TMA

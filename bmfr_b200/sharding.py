@@ -171,11 +171,31 @@ def exchange_distributed(views_by_name, msgs, rank):
 
 
 # ------------------------------------------------------------------------------------------------
-# bench.py --gpus N (N > 1): 3840x2160 strip-sharded, one rank per GPU
+# bench.py --gpus N (N > 1): BASELINE.json's multi-GPU configs strip-sharded, one rank per GPU
 # ------------------------------------------------------------------------------------------------
+def _connect(ctx, rank, world, dist):
+    """One-time exchange of IPC handles between neighbouring ranks; afterwards no host-side communication per frame."""
+    blobs = [None] * world
+    dist.all_gather_object(blobs, ctx.d.halo_export())
+    if rank > 0:
+        ctx.d.halo_connect(0, blobs[rank - 1])
+    if rank < world - 1:
+        ctx.d.halo_connect(1, blobs[rank + 1])
+    dist.barrier()
+
+
+def strip_algorithmic_bytes(w, strip):
+    """Algorithmic bytes per frame of the three FUSED kernels for the rows a rank OWNS (SURVEY.md 8d's per-pixel figures;
+    the redundant rows of straddling blocks and the halo traffic are not credited)."""
+    P = w * (strip[1] - strip[0])
+    NB = ((w + 31) // 32 + 1) * ((strip[1] - strip[0] + 31) // 32)
+    return {"reproject": 95 * P, "fit": 36 * P + 216 * NB, "post": 94 * P + 168 * NB}
+
+
 def bench_sharded(args, workload, frames):
     import torch
     import torch.distributed as dist
+    from bench import ClockSampler, measured_peak, workload_config
 
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -192,55 +212,132 @@ def bench_sharded(args, workload, frames):
     torch.cuda.set_stream(stream)
     sp = stream.cuda_stream
     exchange = getattr(args, "exchange", "p2p")
-    # overlapped frames need the library's own halo exchange (the split-flag protocol); the host-driven NCCL
-    # exchange works on the context's stream between frames and keeps the in-order mode
+    fit = getattr(args, "fit", "gram")
+    # the host-driven NCCL exchange works on the context's stream between frames and needs the in-order mode
     overlap = int(bool(getattr(args, "overlap", 1)) and exchange == "p2p" and args.mode == "fused")
-    ctx = StripContext(w, h, strips[rank], halo, local, sp, args.mode, overlap_frames=overlap)
-    if exchange == "p2p":  # one-time exchange of IPC handles; afterwards no host-side communication per frame
-        blobs = [None] * world
-        dist.all_gather_object(blobs, ctx.d.halo_export())
-        if rank > 0:
-            ctx.d.halo_connect(0, blobs[rank - 1])
-        if rank < world - 1:
-            ctx.d.halo_connect(1, blobs[rank + 1])
+
+    def make_ctx(**kw):
+        c = StripContext(w, h, strips[rank], halo, local, sp, args.mode, fit=fit, **kw)
+        if exchange == "p2p":
+            _connect(c, rank, world, dist)
+        return c
+
+    def replace_ctx(old, **kw):
+        """A neighbour may still be storing into this context's memory until every rank is done with the frames."""
+        old.d.sync()
+        torch.cuda.synchronize()
         dist.barrier()
+        old.close()
+        return make_ctx(**kw)
+
+    ctx = make_ctx(overlap_frames=overlap)
     rows = ctx.row1 - ctx.row0
     inputs = torch.empty((frames, 4, rows, w, 3), dtype=torch.float32, device="cuda")
     for f in range(frames):
         synth.frame_device(w, h, f, [inputs[f, k].data_ptr() for k in range(4)], y0=ctx.row0, y1=ctx.row1, stream=sp)
     cams = [synth.camera(max(f - 1, 0), w, h)[0] for f in range(frames)]
     offs = [synth.camera(f, w, h)[1] for f in range(frames)]
-    out = torch.empty((rows, w, 3), dtype=torch.float32, device="cuda")
 
-    def run_sequence():
-        for f in range(frames):
+    def run_sequence(c, out_ptr=None, nframes=frames):
+        for f in range(nframes):
             # like the single-GPU arm, the device-timed run leaves the result in the context's buffer
-            ctx.d.denoise_frame(f, inputs[f, 0].data_ptr(), inputs[f, 1].data_ptr(), inputs[f, 2].data_ptr(),
-                                inputs[f, 3].data_ptr(), cams[f], offs[f], None)
+            c.d.denoise_frame(f, inputs[f, 0].data_ptr(), inputs[f, 1].data_ptr(), inputs[f, 2].data_ptr(),
+                              inputs[f, 3].data_ptr(), cams[f], offs[f], out_ptr(f) if out_ptr else None)
             if exchange != "p2p":
-                exchange_distributed(ctx.rows_view, msgs, rank)
+                exchange_distributed(c.rows_view, msgs, rank)
 
-    for _ in range(args.warmup):
-        run_sequence()
-    torch.cuda.synchronize()
-    dist.barrier()
-    torch.cuda.synchronize()
-    l0 = ctx.d.kernel_launches
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
-        run_sequence()
-    ctx.d.join()  # overlapped frames: order the closing event after the frames on the internal streams
-    e1.record(stream)
-    torch.cuda.synchronize()
-    dist.barrier()
-    torch.cuda.synchronize()
-    ctx.d.sync()
-    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
-    dist.all_reduce(ms, op=dist.ReduceOp.MAX)      # max over ranks
-    total_ms = float(ms.item())
-    launches = ctx.d.kernel_launches - l0
+    def timed(c, steps, warmup, clocks=False):
+        """max over ranks of the device time of `steps` steps (CUDA events on the context's stream), launches"""
+        for _ in range(warmup):
+            run_sequence(c)
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        l0 = c.d.kernel_launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler = ClockSampler(local) if clocks else None
+        if sampler:
+            sampler.__enter__()
+        e0.record(stream)
+        for _ in range(steps):
+            run_sequence(c)
+        c.d.join()  # overlapped frames: order the closing event after the frames on the internal streams
+        e1.record(stream)
+        torch.cuda.synchronize()
+        if sampler:
+            sampler.__exit__()
+        dist.barrier()
+        torch.cuda.synchronize()
+        c.d.sync()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), c.d.kernel_launches - l0, (sampler.summary() if sampler else None)
+
+    # ---- parity, outside the timed region: the first K frames of THIS transport (IPC peer stores, device flags) against a
+    # whole-image context on the same GPU, owned rows of every output frame bit for bit
+    K = max(0, min(int(getattr(args, "parity_frames", 3)), frames))
+    parity = None
+    if K > 0:
+        y0, y1 = strips[rank]
+        out_s = torch.zeros((K, rows, w, 3), dtype=torch.float32, device="cuda")
+        run_sequence(ctx, out_ptr=lambda f: out_s[f].data_ptr(), nframes=K)
+        ctx.d.sync()
+        torch.cuda.synchronize()
+        ok = True
+        full = torch.empty((2, 4, h, w, 3), dtype=torch.float32, device="cuda")   # this frame's and the previous frame's inputs
+        out_w = torch.empty((h, w, 3), dtype=torch.float32, device="cuda")
+        with Denoiser(w, h, mode=args.mode, device=local, stream=sp, fit=fit) as whole:
+            for f in range(K):
+                synth.frame_device(w, h, f, [full[f & 1, k].data_ptr() for k in range(4)], stream=sp)
+                whole.denoise_frame(f, *[full[f & 1, k].data_ptr() for k in range(4)], cams[f], offs[f], out_w.data_ptr())
+                whole.sync()
+                ok = ok and bool(torch.equal(out_w[y0:y1], out_s[f, y0 - ctx.row0:y1 - ctx.row0]))
+        del full, out_w, out_s
+        flag = torch.tensor([1 if ok else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        parity = {"frames": K, "bit_identical": bool(flag.item() == 1),
+                  "what": "owned rows of every rank's output frames vs a whole-image context of the same library on the same GPU"}
+        # a fresh context for the timed run: frame numbers restart at 0, and so do the halo flags
+        ctx = replace_ctx(ctx, overlap_frames=overlap)
+
+    total_ms, launches, clock_summary = timed(ctx, args.steps, args.warmup, clocks=True)
     halo_bytes = sum((y1 - y0) * w * sum(_BYTES_PER_PIXEL.values()) for s, d_, y0, y1 in msgs if d_ == rank)
+    norm = (w * h) / float(1920 * 1080)
+    native = frames * args.steps / (total_ms * 1e-3)
+
+    # the same K steps on in-order streams (one stream per context, the reference's queue semantics)
+    in_order = None
+    if overlap:
+        ctx = replace_ctx(ctx, overlap_frames=0)
+        ms_io, _, _ = timed(ctx, args.steps, args.warmup)
+        in_order = {"value": frames * args.steps / (ms_io * 1e-3) * norm, "unit": "frames/s", "ms_per_frame": ms_io / args.steps / frames}
+
+    # per-kernel durations on every rank (event pairs around the launches, in-order profile contexts connected like the
+    # timed ones), roofline of rank 0's dominant kernel against the bytes of the rows it owns
+    kernels = roofline = None
+    if args.mode == "fused" and exchange == "p2p":
+        ctx = replace_ctx(ctx, profile=True)
+        run_sequence(ctx)
+        run_sequence(ctx)
+        ctx.d.sync()
+        names = list(ctx.d.fused_kernels)
+        ms = np.array([[ctx.d.fused_kernel_ms(f)[k] for k in names] for f in range(1, frames)]).mean(axis=0)
+        per_rank = torch.tensor(ms, device="cuda", dtype=torch.float64)
+        gathered = [torch.zeros_like(per_rank) for _ in range(world)]
+        dist.all_gather(gathered, per_rank)
+        peak, peak_src = measured_peak()
+        alg = strip_algorithmic_bytes(w, strips[0])
+        kernels = {}
+        for i, (name, key) in enumerate(zip(names, ("reproject", "fit", "post"))):
+            gbs = alg[key] / (float(gathered[0][i]) * 1e-3) / 1e9
+            kernels[name] = {"ms": float(gathered[0][i]), "ms_per_rank": [float(g[i]) for g in gathered], "algorithmic_bytes": alg[key],
+                             "achieved_gbs": gbs, "frac": gbs / peak}
+        dom = max(kernels, key=lambda k: kernels[k]["ms"])
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                    "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src, "rank": 0,
+                    "algorithmic_bytes_per_launch": kernels[dom]["algorithmic_bytes"], "ms_per_launch": kernels[dom]["ms"],
+                    "what": "rank 0's strip: bytes of the rows it owns / the kernel's mean launch duration on rank 0"}
+        ctx = replace_ctx(ctx, overlap_frames=overlap)
 
     # end to end: every rank uploads its strip of each frame from pinned host memory and reads its rows of the
     # result back, through the C ABI's host entry (bounded to the first frames of the sequence to bound pinned memory)
@@ -269,32 +366,29 @@ def bench_sharded(args, workload, frames):
         dt = torch.tensor([time.perf_counter() - t0], device="cuda")
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         own_rows = strips[rank][1] - strips[rank][0]
-        e2e = {"value": nf * steps_h / float(dt.item()) * (w * h) / float(1920 * 1080), "unit": "frames/s",
+        e2e = {"value": nf * steps_h / float(dt.item()) * norm, "unit": "frames/s",
                "frames_per_s_native": nf * steps_h / float(dt.item()),
                "h2d_bytes_per_step": nf * 4 * rows * w * 12, "d2h_bytes_per_step": nf * own_rows * w * 12, "steps": steps_h,
                "frames_per_step": nf, "bytes_are": "per rank (rank 0)",
                "api": "bmfr_denoise_frame_host on every rank: pinned host buffers, async upload ring + read-back, p2p halos"}
         del host_in, host_out
     if rank == 0:
-        native = frames * args.steps / (total_ms * 1e-3)
-        norm = (w * h) / float(1920 * 1080)
-        weak = not (args.width or args.height)
         line = {
             "metric": "frames/sec", "value": native * norm, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "ms_per_frame": total_ms / args.steps / frames,
-            "higher_is_better": True, "scaling": "weak" if weak else "strong", "vs_baseline": None, "dtype": "f32",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "frames_per_s_native": native,
-            "config": {"workload": f"{w}x{h} x{frames} frames synth-v1 strip-sharded over {world} GPUs along block rows",
-                       "value_unit": "1080p-equivalent frames/s = native frames/s x (W*H)/(1920*1080); every rank owns "
-                                     "a 3840x540 strip in the default (weak-scaling) series",
-                       "mode": args.mode, "overlap_frames": overlap, "strips": strips, "halo_rows": halo,
-                       "parallelism": f"strips{world}",
-                       "exchange": ("peer-to-peer pushes of state halo rows over NVLink from the library (CUDA IPC), device-side flags"
-                                    if exchange == "p2p" else "NCCL send/recv of state halo rows, neighbours only"),
-                       "l2": "inputs larger than L2; no explicit flush"},
-            "halo_bytes_per_frame_rank0": halo_bytes, "gpu_launches": int(launches), "roofline": None,
-            "cpu_baseline": None, "e2e": e2e,
+            "config": workload_config(w, h, world),
+            "run": {"mode": args.mode, "overlap_frames": overlap, "fit_method": fit, "strips": strips, "halo_rows": halo,
+                    "exchange": ("in-kernel peer stores of the state halo rows over NVLink (CUDA IPC mappings), device-side flags"
+                                 if exchange == "p2p" else "NCCL send/recv of state halo rows, neighbours only")},
+            "parity": parity, "in_order": in_order, "kernels": kernels, "roofline": roofline,
+            "halo_bytes_per_frame_rank0": halo_bytes, "gpu_launches": int(launches),
+            "cpu_baseline": None, "e2e": e2e, "clocks": clock_summary,
         }
         print(json.dumps(line))
+    ctx.d.sync()
+    torch.cuda.synchronize()
+    dist.barrier()
     ctx.close()
     dist.destroy_process_group()
