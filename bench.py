@@ -35,7 +35,7 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 FRAMES = 60
-FUSED_KERNELS = ("reproject_tma_kernel", "fit_gram_kernel", "post_tma_kernel")  # replaced by the context's own list at run time
+FUSED_KERNELS = ("reproject_kernel", "fit_gram_kernel", "post_tma_kernel")  # replaced by the context's own list at run time
 SINGLE_GPU_WORKLOAD = (1920, 1080)
 
 

@@ -501,6 +501,7 @@ static void fill_params(bmfr_ctx* c, KParams& P, int frame, const float* d_albed
     P.plain_launch = c->ov.on ? 1 : 0;
     P.fit_method = c->prm.fit_method;
     P.tri = c->tri;
+    fill_halo(c, P);
 }
 
 static StageEvents* prof_slot(bmfr_ctx* c, int frame) {

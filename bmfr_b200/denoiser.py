@@ -14,13 +14,13 @@ import numpy as np
 from . import _lib
 from ._lib import BUF, MODE_FUSED, MODE_STAGED, STAGES, BmfrError, Geometry, HaloPlan, Params
 
-FUSED_KERNELS = ("reproject_tma_kernel", "fit_gram_kernel", "post_tma_kernel")  # the default FUSED path, in launch order
+FUSED_KERNELS = ("reproject_kernel", "fit_gram_kernel", "post_tma_kernel")  # the default FUSED path, in launch order
 
 
 def fused_kernel_names(width, fit="gram"):
     """The three kernels a FUSED frame launches: the fit by bmfr_params.fit_method, the post pass by whether its tensor
-    maps can be built for this width (csrc/bmfr_post.cu: W % 16 == 0), the reprojection likewise (W % 4 == 0)."""
-    return ("reproject_tma_kernel" if width % 4 == 0 else "reproject_kernel", "fit_gram_kernel" if fit == "gram" else "fit_qr_kernel",
+    maps can be built for this width (csrc/bmfr_post.cu: W % 16 == 0)."""
+    return ("reproject_kernel", "fit_gram_kernel" if fit == "gram" else "fit_qr_kernel",
             "post_tma_kernel" if width % 16 == 0 else "post_kernel")
 
 _BUF_DTYPE = dict(noisy_acc=np.float32, spp=np.uint8, prev_pixels=np.float32, accept=np.uint8, tmp_data=np.float32,

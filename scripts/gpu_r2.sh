@@ -38,7 +38,7 @@ launches)
 full)
   SHORT="timeout 300 python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu --sustain-seconds 0"
   $SHORT > $OUT/plain2.log 2>&1 &&
-  ncu --set full --clock-control none --import-source on -k regex:"${NCU_KERNELS:-reproject_tma_kernel|fit_gram_kernel|post_tma_kernel}" -s ${NCU_SKIP:-243} -c ${NCU_COUNT:-3} -f -o $OUT/prof $SHORT > $OUT/ncu_full.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:"${NCU_KERNELS:-reproject_kernel|fit_gram_kernel|post_tma_kernel}" -s ${NCU_SKIP:-243} -c ${NCU_COUNT:-3} -f -o $OUT/prof $SHORT > $OUT/ncu_full.log 2>&1
   echo "full exit $?" ;;
 esac
 done
