@@ -50,6 +50,15 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+// Zone rows first: CTA row i of n (blockIdx.y, which the hardware hands out in ascending order) -> the row it works on.
+// The zone CTAs' peer stores then travel while the interior CTAs compute, and the neighbours see the flag early in the
+// kernel instead of at its end.  Without neighbours (rows_top = rows_bot = 0) this is the identity.
+__device__ __forceinline__ int halo_row_order(const HaloK& h, int i, int n) {
+    const int top = h.rows_top, bot = h.rows_bot;
+    if (i < top) return i;
+    if (i < top + bot) return n - bot + (i - top);
+    return top + (i - top - bot);
+}
 // Does the CTA that covers image rows [ya, yb) belong to the zone?
 __device__ __forceinline__ bool halo_in_zone(const HaloK& h, int ya, int yb) { return h.active && (ya < h.zone_y[0] || yb > h.zone_y[1]); }
 // Prologue of a zone CTA (all threads call it): wait for the neighbours' rows.  Bounded: after timeout_ns the context is
@@ -74,9 +83,9 @@ __device__ __forceinline__ void halo_poll(const HaloK& h) {
 }
 // Epilogue of a zone CTA (all threads call it, after their last store): the last zone CTA of the launch raises the flags.
 __device__ __forceinline__ void halo_finish(const HaloK& h) {
-    __threadfence_system();  // this thread's peer stores are visible system-wide before the flag can be
-    __syncthreads();
+    __syncthreads();  // every thread's peer stores precede ...
     if (threadIdx.x == 0 && threadIdx.y == 0) {
+        __threadfence_system();  // ... this fence (cumulative over what the barrier ordered before it): visible system-wide before the count
         const unsigned int done = atomicAdd(h.done_counter, 1u);
         if (done + 1 == h.zone_ctas) {
             *h.done_counter = 0;  // for the next launch (ordered after this one by the stream)

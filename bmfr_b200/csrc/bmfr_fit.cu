@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(256, BMFR_REPROJECT_MIN_BLOCKS) reproject_kern
     pdl_trigger();  // the fit's CTAs may take SM slots as this grid drains
     reproject_noise_tile(P, threadIdx.y * BMFR_REPROJECT_BX + threadIdx.x);
     const int x = blockIdx.x * BMFR_REPROJECT_BX + threadIdx.x;
-    const int cta_y0 = P.k1_y0 + blockIdx.y * (BMFR_REPROJECT_BY * BMFR_REPROJECT_PIXELS);
+    const int cta_y0 = P.k1_y0 + (STRIP ? halo_row_order(P.halo_r, blockIdx.y, gridDim.y) : (int)blockIdx.y) * (BMFR_REPROJECT_BY * BMFR_REPROJECT_PIXELS);
     const int ybase = cta_y0 + threadIdx.y;
     // strips: a CTA near a strip edge waits for the neighbours' rows of the previous frame before it gathers from them
     const bool zone = STRIP && halo_in_zone(P.halo_r, cta_y0, cta_y0 + BMFR_REPROJECT_BY * BMFR_REPROJECT_PIXELS);
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(256, BMFR_REPROJECT_MIN_BLOCKS) reproject_tma_
                                                                                        const __grid_constant__ ReprojectMaps M) {
     __shared__ __align__(128) ReprojectShared sh;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int x0 = blockIdx.x * 32, y0 = P.k1_y0 + blockIdx.y * 32;
+    const int x0 = blockIdx.x * 32, y0 = P.k1_y0 + (STRIP ? halo_row_order(P.halo_r, blockIdx.y, gridDim.y) : (int)blockIdx.y) * 32;
     if (threadIdx.x == 0) {
         mbar_init(&sh.bar, 1);
         mbar_fence_init();

@@ -29,6 +29,7 @@ struct HaloK {
     unsigned int signal_value;
     unsigned int* done_counter;     // zone CTAs of this launch that have finished (reset by the last one)
     unsigned int zone_ctas;
+    int rows_top, rows_bot;         // CTA rows of the launch that belong to the zone at its upper / lower end: they are scheduled first
     unsigned long long timeout_ns;
     int active;                     // 0: no neighbour, nothing of the above happens
 };

@@ -426,15 +426,20 @@ static void fill_halo(bmfr_ctx* c, KParams& P) {
             h.peer_flag[s] = pr.flags + (late ? 4 : 0) + (s == 0 ? 1 : 0);
         }
         // zone CTAs of the launch, counted the way the kernels decide it (halo_in_zone)
-        auto in_zone = [&](int ya, int yb) { return ya < h.zone_y[0] || yb > h.zone_y[1]; };
+        // (a CTA row inside both ends' zones — a strip shorter than two halos — counts as a top row)
         unsigned int n = 0;
+        h.rows_top = h.rows_bot = 0;
+        auto count = [&](int ya, int yb) {
+            if (ya < h.zone_y[0]) { ++h.rows_top; ++n; }
+            else if (yb > h.zone_y[1]) { ++h.rows_bot; ++n; }
+        };
         if (!late) {
-            for (int ya = P.k1_y0; ya < P.k1_y1; ya += 32) n += in_zone(ya, ya + 32) ? 1u : 0u;
+            for (int ya = P.k1_y0; ya < P.k1_y1; ya += 32) count(ya, ya + 32);
             n *= (unsigned int)((g.width + 31) / 32);
         } else {
             for (int by = P.by0; by < P.by1; ++by) {
                 const int y0 = by * 32 - 16 + P.off_y;
-                n += in_zone(y0 - 1, y0 + 33) ? 1u : 0u;
+                count(y0 - 1, y0 + 33);
             }
             n *= (unsigned int)P.blocks_x;
         }

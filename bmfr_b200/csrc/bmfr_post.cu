@@ -169,14 +169,16 @@ __device__ __forceinline__ f3 accumulate_filtered_px(const KParams& P, unsigned 
         const float omx = 1.f - frx, omy = 1.f - fry;
         const float w[4] = {omx * omy, frx * omy, omx * fry, frx * fry};
         float total = 0.f;
+        // (a strip that does not hold a tap's row reports it once, after the loop: a store inside would keep the compiler
+        // from predicating the taps)
+        bool missing = false;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            if (accept & (1u << i)) {  // taps are trusted, not re-checked: bmfr.cl:801-832
-                const int sx = pix + (i & 1), sy = piy + (i >> 1);
-                if (STRIP && (sy < P.state2_row0 || sy >= P.state2_row1)) {
-                    *P.oob_flag = 1;
-                    continue;
-                }
+            const int sx = pix + (i & 1), sy = piy + (i >> 1);
+            const bool held = !STRIP || (sy >= P.state2_row0 && sy < P.state2_row1);
+            const bool want = (accept & (1u << i)) != 0;  // taps are trusted, not re-checked: bmfr.cl:801-832
+            missing = missing || (want && !held);
+            if (want && held) {
                 const f3 pc = ldf3<WIDE>(P.accum_prev, pix_index(P, sx, sy));
                 total += w[i];
                 prev.x = fmaf(w[i], pc.x, prev.x);
@@ -184,6 +186,7 @@ __device__ __forceinline__ f3 accumulate_filtered_px(const KParams& P, unsigned 
                 prev.z = fmaf(w[i], pc.z, prev.z);
             }
         }
+        if (STRIP && missing) *P.oob_flag = 1;
         if (total > 0.f) {
             alpha = fmaxf(fast_rcp((float)spp), P.second_blend_alpha);  // bmfr.cl:838-839
             const float inv = fast_rcp(total);
@@ -241,17 +244,16 @@ __device__ __forceinline__ bool history_sample(const KParams& P, float2 pp, f3& 
     const float w[4] = {omx * omy, frx * omy, omx * fry, frx * fry};
     f3 prev = make_f3(0.f, 0.f, 0.f);
     float total = 0.f;
+    bool missing = false;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {  // bmfr.cl:929-960
         const int dx = i & 1, dy = i >> 1;
         const bool ok_y = dy ? (piy < P.H - 1) : (piy >= 0);
         const bool ok_x = dx ? (pix < P.W - 1) : (pix >= 0);
-        if (ok_x && ok_y) {
-            const int sy = piy + dy;
-            if (STRIP && (sy < P.state2_row0 || sy >= P.state2_row1)) {
-                *P.oob_flag = 1;
-                continue;
-            }
+        const int sy = piy + dy;
+        const bool held = !STRIP || (sy >= P.state2_row0 && sy < P.state2_row1);
+        missing = missing || (ok_x && ok_y && !held);
+        if (ok_x && ok_y && held) {
             const f3 pc = ldf3<WIDE>(P.result_prev, pix_index(P, pix + dx, sy));
             prev.x = fmaf(w[i], pc.x, prev.x);
             prev.y = fmaf(w[i], pc.y, prev.y);
@@ -259,6 +261,7 @@ __device__ __forceinline__ bool history_sample(const KParams& P, float2 pp, f3& 
             total += w[i];
         }
     }
+    if (STRIP && missing) *P.oob_flag = 1;
     const float inv = fast_rcp(total);  // 0 * inf = NaN on the image edge like the 0/0 of bmfr.cl:962
     hist = to_ycocg(make_f3(prev.x * inv, prev.y * inv, prev.z * inv));
     return true;
@@ -336,7 +339,7 @@ __device__ __forceinline__ void prefetch_taps(const KParams& P, float2 pp) {
 template <bool STRIP, bool WIDE>
 __global__ void __launch_bounds__(256, BMFR_POST_MIN_BLOCKS) post_kernel(const __grid_constant__ KParams P) {
     __shared__ __align__(16) PostShared sh;
-    const int bx = blockIdx.x, by = P.by0 + blockIdx.y;
+    const int bx = blockIdx.x, by = P.by0 + (STRIP ? halo_row_order(P.halo_p, blockIdx.y, gridDim.y) : (int)blockIdx.y);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int x0 = bx * 32 - 16 + P.off_x, y0 = by * 32 - 16 + P.off_y;  // tile origin in image coordinates
     constexpr int NW = BMFR_FEATURES * 3, NM = BMFR_FEATURES_SCALED * 2;
@@ -584,16 +587,17 @@ __device__ __forceinline__ bool resolve_pixel(PostStage& sh, const KParams& P, c
                                               bool own, f3& hist) {
     f3 prev = make_f3(0.f, 0.f, 0.f);
     float alpha = 1.f;
+    // A strip that does not hold a wanted tap's row reports it (once, at the end: a store inside the loops would keep the
+    // compiler from predicating the taps); the tap itself was fetched from a clamped address and the run is invalid anyway.
+    const bool out0 = STRIP && (t.piy < P.state2_row0 || t.piy >= P.state2_row1);
+    const bool out1 = STRIP && (t.piy + 1 < P.state2_row0 || t.piy + 1 >= P.state2_row1);
+    bool missing = false;
     if (in.accept != 0) {
         float total = 0.f;
+        missing = ((in.accept & 3u) != 0 && out0) || ((in.accept & 12u) != 0 && out1);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             if (in.accept & (1u << i)) {  // taps are trusted, not re-checked: bmfr.cl:801-832
-                const int sy = t.piy + (i >> 1);
-                if (STRIP && (sy < P.state2_row0 || sy >= P.state2_row1)) {
-                    *P.oob_flag = 1;
-                    continue;
-                }
                 const f3 pc = (i >> 1) ? a1[i & 1] : a0[i & 1];
                 total += t.w[i];
                 prev.x = fmaf(t.w[i], pc.x, prev.x);
@@ -615,7 +619,7 @@ __device__ __forceinline__ bool resolve_pixel(PostStage& sh, const KParams& P, c
     put_ycc_i(sh, P, G, hx, hy, x, y, to_ycocg(tone));
 
     hist = make_f3(0.f, 0.f, 0.f);
-    if (!own || t.pix < -1 || t.piy < -1 || t.pix >= P.W || t.piy >= P.H) return false;  // bmfr.cl:884-890
+    const bool temporal = own && !(t.pix < -1 || t.piy < -1 || t.pix >= P.W || t.piy >= P.H);  // bmfr.cl:884-890
     f3 hp = make_f3(0.f, 0.f, 0.f);
     float total = 0.f;
 #pragma unroll
@@ -623,12 +627,8 @@ __device__ __forceinline__ bool resolve_pixel(PostStage& sh, const KParams& P, c
         const int dx = i & 1, dy = i >> 1;
         const bool ok_y = dy ? (t.piy < P.H - 1) : (t.piy >= 0);
         const bool ok_x = dx ? (t.pix < P.W - 1) : (t.pix >= 0);
+        missing = missing || (temporal && ok_x && ok_y && (dy ? out1 : out0));
         if (ok_x && ok_y) {
-            const int sy = t.piy + dy;
-            if (STRIP && (sy < P.state2_row0 || sy >= P.state2_row1)) {
-                *P.oob_flag = 1;
-                continue;
-            }
             const f3 pc = dy ? r1[dx] : r0[dx];
             hp.x = fmaf(t.w[i], pc.x, hp.x);
             hp.y = fmaf(t.w[i], pc.y, hp.y);
@@ -636,6 +636,8 @@ __device__ __forceinline__ bool resolve_pixel(PostStage& sh, const KParams& P, c
             total += t.w[i];
         }
     }
+    if (STRIP && missing) *P.oob_flag = 1;
+    if (!temporal) return false;
     const float inv = fast_rcp(total);  // 0 * inf = NaN on the image edge like the 0/0 of bmfr.cl:962
     hist = to_ycocg(make_f3(hp.x * inv, hp.y * inv, hp.z * inv));
     return true;
@@ -652,7 +654,7 @@ template <bool STRIP>
 __global__ void __launch_bounds__(256, BMFR_POST_TMA_MIN_BLOCKS) post_tma_kernel(const __grid_constant__ KParams P, const __grid_constant__ PostMaps M) {
     extern __shared__ __align__(128) unsigned char post_smem[];
     PostStage& sh = *reinterpret_cast<PostStage*>(post_smem);
-    const int bx = blockIdx.x, by = P.by0 + blockIdx.y;
+    const int bx = blockIdx.x, by = P.by0 + (STRIP ? halo_row_order(P.halo_p, blockIdx.y, gridDim.y) : (int)blockIdx.y);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     TileGeom G;
     G.x0 = bx * 32 - 16 + P.off_x;
