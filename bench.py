@@ -498,6 +498,7 @@ def main():
     ap.add_argument("--parity-frames", type=int, default=3, help="N > 1: frames compared bit for bit with a whole-image run (outside the timed region)")
     ap.add_argument("--sustain-seconds", type=float, default=1.0, help="length of the extra long timed region reported as `sustained`")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="halo transport of the sharded run (N > 1)")
+    ap.add_argument("--halo-rows", type=int, default=0, help="N > 1: halo_rows of the strip contexts (0 = sharding.default_halo(height))")
     ap.add_argument("--overlap", type=int, default=1, choices=[0, 1],
                     help="bmfr_params.overlap_frames of the timed contexts: 1 = consecutive frames overlap on the device "
                          "(three event-linked streams), 0 = one in-order stream")

@@ -60,16 +60,55 @@ __device__ __forceinline__ void reproject_noise_tile(const KParams& P, int tid) 
     }
 }
 
+// Zone CTAs of a strip stage the rows a neighbour mirrors in shared memory and send them as 16-byte peer stores, one
+// full 384-byte row segment per 24 lanes: single 4-byte stores at a 12-byte stride make poor NVLink packets, and at 8K
+// over eight GPUs a rank pushes ~12 MB per frame from this kernel.  (Whole-image instantiations carry no staging.)
+template <bool STRIP, bool WITH_RGB>
+struct ReprojectPushStage {
+    float rgb[WITH_RGB ? 32 : 1][96];
+    unsigned char spp[32][32];
+};
+template <bool WITH_RGB>
+struct ReprojectPushStage<false, WITH_RGB> {
+    float rgb[1][96];  // (never touched)
+    unsigned char spp[1][32];
+};
+
+// All threads of a zone CTA, after a barrier: rows [cta_y0, cta_y0 + 32) x columns [x0, x0 + 32) of the stage -> the
+// neighbours that mirror them.  Needs W % 32 == 0 (full tiles, 16-byte aligned row segments).
+__device__ __forceinline__ void reproject_push_rows(const KParams& P, const float (*rgb)[96], const unsigned char (*spp)[32], int x0, int cta_y0, int tid) {
+    const HaloK& h = P.halo_r;
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        if (!h.side_on[s]) continue;
+        const int ya = max(h.push_y0[s], cta_y0), yb = min(h.push_y1[s], cta_y0 + 32);
+        const int items = (yb - ya) * 26;  // per row: 24 x 16 B of colour, 2 x 16 B of sample counts
+        for (int i = tid; i < items; i += 256) {
+            const int y = ya + i / 26, k = i % 26, r = y - cta_y0;
+            const long long pix = (long long)(y - h.peer_row0[s]) * P.W + x0;
+            if (k < 24) reinterpret_cast<float4*>(h.peer_a[s] + pix * 3)[k] = reinterpret_cast<const float4*>(&rgb[r][0])[k];
+            else reinterpret_cast<uint4*>(h.peer_c[s] + pix)[k - 24] = reinterpret_cast<const uint4*>(&spp[r][0])[k - 24];
+        }
+    }
+}
+
 // The four per-pixel outputs of bmfr.cl:478-484; in the zone of a strip the accumulated colour and the sample count of a
 // row a neighbour mirrors go to its halo as well (peer memory over NVLink).
 template <bool STRIP>
-__device__ __forceinline__ void reproject_store(const KParams& P, int x, int y, const K1Pixel& r, bool zone) {
+__device__ __forceinline__ void reproject_store(const KParams& P, int x, int y, const K1Pixel& r, bool zone, float (*st_rgb)[96],
+                                                unsigned char (*st_spp)[32], int tx, int row_in_cta) {
     const unsigned int lp = pix_index(P, x, y);
     store_f3(P.cur_noisy_acc, lp, r.new_color);
     P.cur_spp[lp] = r.spp;
     P.prev_pixels[lp] = make_float2(r.prev_x, r.prev_y);
     P.accept[lp] = r.accept;
-    if (STRIP && zone) {
+    if constexpr (STRIP) {
+        if (!zone) return;
+        if ((P.W & 31) == 0) {  // staged, sent row by row after the CTA's last pixel (reproject_push_rows)
+            st_rgb[row_in_cta][3 * tx] = r.new_color.x; st_rgb[row_in_cta][3 * tx + 1] = r.new_color.y; st_rgb[row_in_cta][3 * tx + 2] = r.new_color.z;
+            st_spp[row_in_cta][tx] = r.spp;
+            return;
+        }
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
             const long long pi = halo_peer_index(P.halo_r, P, s, x, y);
@@ -93,6 +132,7 @@ __global__ void __launch_bounds__(256, BMFR_REPROJECT_MIN_BLOCKS) reproject_kern
     // normals / positions tiles (the caller's inputs) before its own wait
     pdl_trigger();  // the fit's CTAs may take SM slots as this grid drains
     reproject_noise_tile(P, threadIdx.y * BMFR_REPROJECT_BX + threadIdx.x);
+    __shared__ __align__(16) ReprojectPushStage<STRIP, true> push_stage;
     const int x = blockIdx.x * BMFR_REPROJECT_BX + threadIdx.x;
     const int cta_y0 = P.k1_y0 + (STRIP ? halo_row_order(P.halo_r, blockIdx.y, gridDim.y) : (int)blockIdx.y) * (BMFR_REPROJECT_BY * BMFR_REPROJECT_PIXELS);
     const int ybase = cta_y0 + threadIdx.y;
@@ -119,10 +159,18 @@ __global__ void __launch_bounds__(256, BMFR_REPROJECT_MIN_BLOCKS) reproject_kern
             if (k + 1 < BMFR_REPROJECT_PIXELS && yn >= ylo && yn < yhi) wp_next = load_f3_stream(P.cur_positions, pix_index(P, x, yn));
             if (y < ylo) continue;
             const K1Pixel r = k1_pixel<STRIP>(P, x, y, wp);
-            reproject_store<STRIP>(P, x, y, r, zone);
+            reproject_store<STRIP>(P, x, y, r, zone, push_stage.rgb, push_stage.spp, threadIdx.x, y - cta_y0);
         }
     }
-    if (zone) halo_finish(P.halo_r);
+    if constexpr (STRIP) {
+        if (zone) {
+            if ((P.W & 31) == 0) {
+                __syncthreads();
+                reproject_push_rows(P, push_stage.rgb, push_stage.spp, blockIdx.x * BMFR_REPROJECT_BX, cta_y0, threadIdx.y * BMFR_REPROJECT_BX + threadIdx.x);
+            }
+            halo_finish(P.halo_r);
+        }
+    }
 }
 
 // --------------------------------------------------------------------------------------------
@@ -147,6 +195,7 @@ template <bool STRIP>
 __global__ void __launch_bounds__(256, BMFR_REPROJECT_MIN_BLOCKS) reproject_tma_kernel(const __grid_constant__ KParams P,
                                                                                        const __grid_constant__ ReprojectMaps M) {
     __shared__ __align__(128) ReprojectShared sh;
+    __shared__ __align__(16) ReprojectPushStage<STRIP, false> push_stage;  // the colour rows are staged over the noisy-colour tile
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int x0 = blockIdx.x * 32, y0 = P.k1_y0 + (STRIP ? halo_row_order(P.halo_r, blockIdx.y, gridDim.y) : (int)blockIdx.y) * 32;
     if (threadIdx.x == 0) {
@@ -182,10 +231,18 @@ __global__ void __launch_bounds__(256, BMFR_REPROJECT_MIN_BLOCKS) reproject_tma_
             const f3 wp = make_f3(sh.pos[r][3 * tx], sh.pos[r][3 * tx + 1], sh.pos[r][3 * tx + 2]);
             const f3 n = make_f3(sh.nrm[r][3 * tx], sh.nrm[r][3 * tx + 1], sh.nrm[r][3 * tx + 2]);
             const f3 cur = make_f3(sh.col[r][3 * tx], sh.col[r][3 * tx + 1], sh.col[r][3 * tx + 2]);
-            reproject_store<STRIP>(P, x, y, k1_pixel_core<STRIP>(P, x, y, wp, n, cur), zone);
+            reproject_store<STRIP>(P, x, y, k1_pixel_core<STRIP>(P, x, y, wp, n, cur), zone, sh.col, push_stage.spp, tx, r);
         }
     }
-    if (zone) halo_finish(P.halo_r);
+    if constexpr (STRIP) {
+        if (zone) {
+            if ((P.W & 31) == 0) {
+                __syncthreads();
+                reproject_push_rows(P, sh.col, push_stage.spp, x0, y0, threadIdx.x);
+            }
+            halo_finish(P.halo_r);
+        }
+    }
 }
 
 // --------------------------------------------------------------------------------------------
@@ -887,6 +944,21 @@ __device__ __noinline__ void gram_solve_mine(const KParams& P, SH& sh, int count
     __syncthreads();
 }
 
+// Tuning builds (-DBMFR_QR_TIMING): globaltimer stamps of every CTA's first thread — [0] start, [1] first tiles landed,
+// [2 + 2 it] block it's data ready, [3 + 2 it] block it done (it < 6), [14] level 1 done, [15] solves done.
+#ifdef BMFR_QR_TIMING
+__device__ long long g_gram_cta[1024 * 16];
+#define GRAM_STAMP(k)                                                                                  \
+    do {                                                                                               \
+        if (tid == 0 && blockIdx.x < 1024 && (k) < 16) g_gram_cta[blockIdx.x * 16 + (k)] = qr_globaltimer(); \
+    } while (0)
+extern "C" int bmfr_debug_gram_cta(long long* out, int n) {
+    return (int)cudaMemcpyFromSymbol(out, g_gram_cta, sizeof(long long) * (n < 1024 * 16 ? n : 1024 * 16));
+}
+#else
+#define GRAM_STAMP(k) do { } while (0)
+#endif
+
 template <bool STRIP>
 __global__ void __launch_bounds__(QR_THREADS, BMFR_GRAM_MIN_BLOCKS) fit_gram_kernel(const __grid_constant__ KParams P,
                                                                                     const __grid_constant__ QrMaps M) {
@@ -899,6 +971,7 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_GRAM_MIN_BLOCKS) fit_gram_ker
     const int stride = gridDim.x;
     if ((int)blockIdx.x >= nblocks) return;
     const int first = qr_block_of_draw(blockIdx.x, nblocks, P.blocks_x);
+    GRAM_STAMP(0);
 
     if (tid == 0) {
         mbar_init(&sh.data_full, 1);
@@ -921,6 +994,7 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_GRAM_MIN_BLOCKS) fit_gram_ker
         mbar_wait_hot(&sh.data_full, it & 1);
         const int local = sh.blk[it & 1];
         if (local >= nblocks) break;
+        if (it < 6) GRAM_STAMP(2 + 2 * it);
         const int group = P.by0 * P.blocks_x + local;
         const int bx = local % P.blocks_x, by = P.by0 + local / P.blocks_x;
 
@@ -1113,8 +1187,11 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_GRAM_MIN_BLOCKS) fit_gram_ker
             mine = 0;
         }
         if (tid == 0 && late_draw) qr_draw_next(P, M, sh, it, nblocks, stride);
+        if (it < 6) GRAM_STAMP(3 + 2 * it);
     }
+    GRAM_STAMP(14);
     gram_solve_mine(P, sh, mine, warp, lane);
+    GRAM_STAMP(15);
 }
 
 // --------------------------------------------------------------------------------------------

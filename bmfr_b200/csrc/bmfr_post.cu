@@ -160,7 +160,8 @@ __device__ __forceinline__ void weighted_sum_px4(const f3 (&n)[4], const f3 (&p)
 // albedo, fetched by the caller together with the features (one round of independent loads).
 template <bool STRIP, bool WIDE>
 __device__ __forceinline__ f3 accumulate_filtered_px(const KParams& P, unsigned int lp, f3 filtered, unsigned int accept,
-                                                     float2 pp, unsigned int spp, f3 alb, bool store, int x, int y) {
+                                                     float2 pp, unsigned int spp, f3 alb, bool store, int x, int y,
+                                                     bool push = true, f3* accum_out = nullptr) {
     f3 prev = make_f3(0.f, 0.f, 0.f);
     float alpha = 1.f;
     if (P.frame > 0 && accept != 0) {
@@ -200,8 +201,9 @@ __device__ __forceinline__ f3 accumulate_filtered_px(const KParams& P, unsigned 
                              fmaf(alpha, filtered.z, oma * prev.z));
     if (store) {
         stf3<WIDE>(P.accum_cur, lp, accum);
-        post_push<STRIP>(P, 0, x, y, accum);
+        if (push) post_push<STRIP>(P, 0, x, y, accum);
     }
+    if (accum_out) *accum_out = accum;
     return make_f3(tone_map_fast(alb.x * accum.x), tone_map_fast(alb.y * accum.y), tone_map_fast(alb.z * accum.z));
 }
 
@@ -553,14 +555,48 @@ __device__ __forceinline__ PixelIn load_pixel_staged(const PostStage& sh, const 
     in.spp = sh.spp[hy][G.sh_u8 + hx];
     return in;
 }
+// Zone CTAs of a strip (HaloK) do not send a mirrored row pixel by pixel: a pixel's accumulated colour goes into its own
+// (already consumed) normal cell, its TAA result into its position cell, and after the last pixel the CTA sends whole row
+// segments as 8-byte peer stores (post_push_rows) — 4-byte stores at a 12-byte stride make poor NVLink packets.
+__device__ __forceinline__ void stage_accum(PostStage& sh, const TileGeom& G, int hx, int hy, f3 v) {
+    float* p = &sh.nrm[hy][G.sh_rgb + 3 * hx];
+    p[0] = v.x; p[1] = v.y; p[2] = v.z;
+}
+__device__ __forceinline__ void stage_result(PostStage& sh, const TileGeom& G, int hx, int hy, f3 v) {
+    float* p = &sh.pos[hy][G.sh_rgb + 3 * hx];
+    p[0] = v.x; p[1] = v.y; p[2] = v.z;
+}
+// All threads of a zone CTA, after a barrier: the tile's rows that a neighbour mirrors, both buffers.
+__device__ __forceinline__ void post_push_rows(const KParams& P, const PostStage& sh, const TileGeom& G, int tid) {
+    const HaloK& h = P.halo_p;
+    const int xa = max(G.x0, 0), xb = min(G.x0 + 32, P.W);  // the tile's columns inside the image (both even)
+    const int per_row = (xb - xa) * 3 / 2;                  // 8-byte items per row and buffer
+    if (per_row <= 0) return;
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        if (!h.side_on[s]) continue;
+        const int ya = max(h.push_y0[s], G.y0), yb = min(h.push_y1[s], G.y0 + 32);
+        const int items = (yb - ya) * per_row * 2;
+        for (int i = tid; i < items; i += 256) {
+            const int which = i / ((yb - ya) * per_row), j = i % ((yb - ya) * per_row);
+            const int y = ya + j / per_row, k = j % per_row;
+            const float* src = (which ? &sh.pos[y - G.y0 + 1][0] : &sh.nrm[y - G.y0 + 1][0]) + G.sh_rgb + 3 * (xa - G.x0 + 1);
+            float* dst = (which ? h.peer_b[s] : h.peer_a[s]) + ((long long)(y - h.peer_row0[s]) * P.W + xa) * 3;
+            reinterpret_cast<float2*>(dst)[k] = reinterpret_cast<const float2*>(src)[k];
+        }
+    }
+}
+
 // One pixel whose inputs are staged: ring pixels, and the pixels of a pair cut by a strip or image edge.
 template <bool STRIP>
 __device__ __forceinline__ bool staged_pixel(PostStage& sh, const KParams& P, const TileGeom& G, const float* cf, int hx, int hy, int x, int y,
-                                             bool store, bool own, f3& hist) {
+                                             bool store, bool own, f3& hist, bool zone) {
     const PixelIn in = load_pixel_staged(sh, P, G, hx, hy, x, y);
     const f3 filtered = weighted_sum_px(in.n, in.p, cf);
     const bool temporal = own && history_sample<STRIP, false>(P, in.pp, hist);
-    const f3 tone = accumulate_filtered_px<STRIP, false>(P, in.lp, filtered, in.accept, in.pp, in.spp, in.alb, store, x, y);
+    f3 accum;
+    const f3 tone = accumulate_filtered_px<STRIP, false>(P, in.lp, filtered, in.accept, in.pp, in.spp, in.alb, store, x, y, false, &accum);
+    if (STRIP && zone && store) stage_accum(sh, G, hx, hy, accum);
     put_ycc_i(sh, P, G, hx, hy, x, y, to_ycocg(tone));
     return temporal;
 }
@@ -584,7 +620,7 @@ __device__ __forceinline__ TapGeom tap_geom(float2 pp) {
 template <bool STRIP>
 __device__ __forceinline__ bool resolve_pixel(PostStage& sh, const KParams& P, const TileGeom& G, const PixelIn& in, const TapGeom& t, f3 filtered,
                                               const f3 (&a0)[2], const f3 (&a1)[2], const f3 (&r0)[2], const f3 (&r1)[2], int hx, int hy, int x, int y,
-                                              bool own, f3& hist) {
+                                              bool own, f3& hist, bool zone) {
     f3 prev = make_f3(0.f, 0.f, 0.f);
     float alpha = 1.f;
     // A strip that does not hold a wanted tap's row reports it (once, at the end: a store inside the loops would keep the
@@ -614,7 +650,7 @@ __device__ __forceinline__ bool resolve_pixel(PostStage& sh, const KParams& P, c
     const float oma = 1.f - alpha;
     const f3 accum = make_f3(fmaf(alpha, filtered.x, oma * prev.x), fmaf(alpha, filtered.y, oma * prev.y), fmaf(alpha, filtered.z, oma * prev.z));
     store_f3(P.accum_cur, in.lp, accum);
-    post_push<STRIP>(P, 0, x, y, accum);
+    if (STRIP && zone) stage_accum(sh, G, hx, hy, accum);
     const f3 tone = make_f3(tone_map_fast(in.alb.x * accum.x), tone_map_fast(in.alb.y * accum.y), tone_map_fast(in.alb.z * accum.z));
     put_ycc_i(sh, P, G, hx, hy, x, y, to_ycocg(tone));
 
@@ -748,7 +784,7 @@ __global__ void __launch_bounds__(256, BMFR_POST_TMA_MIN_BLOCKS) post_tma_kernel
                 else
 #endif
                 weighted_sum_px2(i0.n, i0.p, i1.n, i1.p, sh.coef[4], fl0, fl1);  // its arithmetic overlaps the gathers
-                t0 = resolve_pixel<STRIP>(sh, P, G, i0, g0, fl0, A[0], A[1], R[0], R[1], lane + 1, ty + 1, x, y, own0, hist[s]);
+                t0 = resolve_pixel<STRIP>(sh, P, G, i0, g0, fl0, A[0], A[1], R[0], R[1], lane + 1, ty + 1, x, y, own0, hist[s], zone);
                 if (!(cx1[0] == cx0[0] && cx1[1] == cx0[1] && ry1[0] == ry0[1])) {  // footprints not stacked (rare): fetch the row
 #pragma unroll
                     for (int dx = 0; dx < 2; ++dx) {
@@ -757,7 +793,7 @@ __global__ void __launch_bounds__(256, BMFR_POST_TMA_MIN_BLOCKS) post_tma_kernel
                         R[1][dx] = load_f3(P.result_prev, l);
                     }
                 }
-                t1 = resolve_pixel<STRIP>(sh, P, G, i1, g1, fl1, A[1], A[2], R[1], R[2], lane + 1, ty + 2, x, y + 1, own1, hist[s + 1]);
+                t1 = resolve_pixel<STRIP>(sh, P, G, i1, g1, fl1, A[1], A[2], R[1], R[2], lane + 1, ty + 2, x, y + 1, own1, hist[s + 1], zone);
             } else {  // frame 0: no temporal path, alpha = 1 (bmfr.cl:784, 884)
                 f3 fl0, fl1;
 #if BMFR_POST_WS4
@@ -767,8 +803,10 @@ __global__ void __launch_bounds__(256, BMFR_POST_TMA_MIN_BLOCKS) post_tma_kernel
                 weighted_sum_px2(i0.n, i0.p, i1.n, i1.p, sh.coef[4], fl0, fl1);
                 store_f3(P.accum_cur, i0.lp, fl0);
                 store_f3(P.accum_cur, i1.lp, fl1);
-                post_push<STRIP>(P, 0, x, y, fl0);
-                post_push<STRIP>(P, 0, x, y + 1, fl1);
+                if (STRIP && zone) {
+                    stage_accum(sh, G, lane + 1, ty + 1, fl0);
+                    stage_accum(sh, G, lane + 1, ty + 2, fl1);
+                }
                 put_ycc_i(sh, P, G, lane + 1, ty + 1, x, y,
                           to_ycocg(make_f3(tone_map_fast(i0.alb.x * fl0.x), tone_map_fast(i0.alb.y * fl0.y), tone_map_fast(i0.alb.z * fl0.z))));
                 put_ycc_i(sh, P, G, lane + 1, ty + 2, x, y + 1,
@@ -777,10 +815,10 @@ __global__ void __launch_bounds__(256, BMFR_POST_TMA_MIN_BLOCKS) post_tma_kernel
             live |= ((own0 ? 1u : 0u) | (t0 ? 16u : 0u)) << s;
             live |= ((own1 ? 1u : 0u) | (t1 ? 16u : 0u)) << (s + 1);
         } else if (v0) {  // a strip or image edge cuts the pair
-            const bool t = staged_pixel<STRIP>(sh, P, G, sh.coef[4], lane + 1, ty + 1, x, y, true, own0, hist[s]);
+            const bool t = staged_pixel<STRIP>(sh, P, G, sh.coef[4], lane + 1, ty + 1, x, y, true, own0, hist[s], zone);
             live |= ((own0 ? 1u : 0u) | (t ? 16u : 0u)) << s;
         } else if (v1) {
-            const bool t = staged_pixel<STRIP>(sh, P, G, sh.coef[4], lane + 1, ty + 2, x, y + 1, true, own1, hist[s + 1]);
+            const bool t = staged_pixel<STRIP>(sh, P, G, sh.coef[4], lane + 1, ty + 2, x, y + 1, true, own1, hist[s + 1], zone);
             live |= ((own1 ? 1u : 0u) | (t ? 16u : 0u)) << (s + 1);
         }
     }
@@ -796,7 +834,7 @@ __global__ void __launch_bounds__(256, BMFR_POST_TMA_MIN_BLOCKS) post_tma_kernel
         if (rx >= 0 && rx < P.W && ry >= P.py0 && ry < P.py1) {
             const int nb = ((hy == 0) ? 0 : (hy == PT_HALO - 1) ? 6 : 3) + ((hx == 0) ? 0 : (hx == PT_HALO - 1) ? 2 : 1);
             f3 unused;
-            staged_pixel<STRIP>(sh, P, G, sh.coef[nb], hx, hy, rx, ry, false, false, unused);
+            staged_pixel<STRIP>(sh, P, G, sh.coef[nb], hx, hy, rx, ry, false, false, unused, zone);
         }
     }
     __syncthreads();
@@ -841,9 +879,13 @@ __global__ void __launch_bounds__(256, BMFR_POST_TMA_MIN_BLOCKS) post_tma_kernel
         }
         store_f3(P.result_cur, lp, out);
         if (P.user_out) store_f3(P.user_out, lp, out);
-        post_push<STRIP>(P, 1, x, G.y0 + 4 * warp + s, out);
+        if (STRIP && zone) stage_result(sh, G, lane + 1, 4 * warp + s + 1, out);
     }
-    if (zone) halo_finish(P.halo_p);
+    if (STRIP && zone) {
+        __syncthreads();  // the staged rows are complete
+        post_push_rows(P, sh, G, tid);
+        halo_finish(P.halo_p);
+    }
 }
 
 #ifndef BMFR_POST_TMA

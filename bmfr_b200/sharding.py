@@ -36,6 +36,14 @@ _BYTES_PER_PIXEL = dict(noisy_acc=12, spp=1, accum=12, result=12)
 DEFAULT_HALO = 48
 
 
+def default_halo(height: int) -> int:
+    """halo_rows for the synthetic sequence at this image height: 34 rows (one straddling block row + the TAA ring) + the
+    largest vertical reprojection distance (5.6 pixels per frame at 1080 rows in synth-v1, measured with the oracle over the
+    60 frames; it scales with the height) + the second bilinear tap row + one row of slack.  A gather that leaves strip +
+    halo is reported (BMFR_ERR_HALO_TOO_SMALL), never silently wrong."""
+    return 36 + (6 * height + 1079) // 1080
+
+
 def partition(height: int, n: int):
     """Contiguous bands of block rows, sizes differing by at most one block row (e.g. 69 -> 35/34)."""
     nb = (height + 31) // 32
@@ -202,9 +210,7 @@ def bench_sharded(args, workload, frames):
     w, h = args.width or workload[0], args.height or workload[1]
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-    # 34 rows (one straddling block + the TAA ring) + the vertical reprojection distance, which grows with
-    # the image height in the synthetic sequence (a few pixels per frame at 1080 rows)
-    halo = 34 + 14 * ((h + 1079) // 1080)
+    halo = int(getattr(args, "halo_rows", 0)) or default_halo(h)
     strips = partition(h, world)
     check_partition(strips, h, halo)
     msgs = halo_messages(strips, h, halo)

@@ -87,9 +87,8 @@ typedef struct bmfr_params {
      * context's stream is then ordered BEFORE a frame's kernels (the caller's producers of the inputs) but
      * not after them: the output (d_out, bmfr_get_buffer) is valid, and the input buffers of the last two
      * frames may be overwritten, only after bmfr_sync() or, on the stream, after bmfr_join().  bmfr_denoise_frame_host handles that ordering
-     * itself.  Strip contexts: the library's own halo exchange (bmfr_halo_connect*) switches to a two-flag
-     * protocol, so all connected contexts must agree on this field, and a caller-driven exchange of the
-     * state rows (which needs the in-order stream) cannot be combined with it.
+     * itself.  Strip contexts may mix both settings (the halo protocol is the same); a caller-driven exchange of the
+     * state rows (which needs the in-order stream) cannot be combined with overlap_frames = 1.
      * 0 (default): one in-order stream, the reference's queue semantics (bmfr.cpp:191). */
     int overlap_frames;
     /* FUSED only: how the per-block least-squares problem of the fitter (bmfr.cl:546-699) is solved.
@@ -222,12 +221,14 @@ typedef struct bmfr_halo_plan {
 } bmfr_halo_plan;
 int bmfr_get_halo_plan(const bmfr_ctx* ctx, int side, bmfr_halo_plan* out);
 
-/* Peer-to-peer halo exchange (option A; no counterpart in the single-device reference).  Once
- * a sharded context is connected to the contexts that own the strips above (side 0) and below (side 1),
- * every bmfr_denoise_frame call copies its boundary rows of the four state buffers straight into the
- * neighbours' halo rows (peer memory over NVLink) after its kernels and waits for the neighbours' rows
- * before the kernels of the next frame — no host round trip, no collective.  All contexts must submit
- * the same frame sequence.
+/* Peer-to-peer halo exchange (option A; no counterpart in the single-device reference).  FUSED contexts
+ * only.  Once a sharded context is connected to the contexts that own the strips above (side 0) and below (side 1),
+ * the kernels of every bmfr_denoise_frame call do the exchange themselves: the CTAs next to a strip edge store the rows
+ * a neighbour mirrors a second time, straight into the neighbour's halo rows (peer memory over NVLink), the last of
+ * them raises a flag in the neighbour's memory, and they poll their own flags before they gather from halo rows — no
+ * copy, signal or wait launches, no host round trip, no collective.  All contexts must submit the same frame sequence
+ * and must be connected before their first frame.  A neighbour that does not deliver within params.halo_timeout_ms
+ * fails the context: bmfr_sync reports BMFR_ERR_SEQUENCE and later frames are refused.
  *   bmfr_halo_export / bmfr_halo_connect : contexts in different processes (one rank per GPU): export an
  *       opaque blob (CUDA IPC handles + geometry), ship it to the neighbour with any transport, connect.
  *   bmfr_halo_connect_local              : both contexts live in this process. */

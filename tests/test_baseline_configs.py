@@ -82,7 +82,7 @@ def _device_sequence(w, h, frames):
 
 
 def _halo(h):
-    return 34 + 14 * ((h + 1079) // 1080)  # what bench.py's sharded arm uses
+    return sharding.default_halo(h)  # what bench.py's sharded arm uses
 
 
 @pytest.mark.parametrize("overlap", [0, 1])
