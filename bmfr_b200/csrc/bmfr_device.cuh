@@ -50,14 +50,21 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-// Zone rows first: CTA row i of n (blockIdx.y, which the hardware hands out in ascending order) -> the row it works on.
-// The zone CTAs' peer stores then travel while the interior CTAs compute, and the neighbours see the flag early in the
-// kernel instead of at its end.  Without neighbours (rows_top = rows_bot = 0) this is the identity.
+// Zone rows early and spread out: CTA row i of n (blockIdx.y, which the hardware hands out in ascending order) -> the row
+// it works on.  The Z zone rows take every k-th position from the start (k = n / Z), the interior rows fill the rest: the
+// zone CTAs' peer stores then drain over NVLink while interior CTAs compute (all zone CTAs at once would hold most of
+// the SM slots while their stores and system fences complete), and the neighbours still see the flag before this
+// kernel ends.  Without neighbours (rows_top = rows_bot = 0) this is the identity.
 __device__ __forceinline__ int halo_row_order(const HaloK& h, int i, int n) {
-    const int top = h.rows_top, bot = h.rows_bot;
-    if (i < top) return i;
-    if (i < top + bot) return n - bot + (i - top);
-    return top + (i - top - bot);
+    const int top = h.rows_top, Z = h.rows_top + h.rows_bot;
+    if (Z <= 0 || Z >= n) return i;
+    const int k = n / Z;
+    const int placed = min(Z, (i + k - 1) / k);  // zone rows at positions before i
+    if (i % k == 0 && i / k < Z) {
+        const int j = i / k;                      // the j-th zone row: top ones first, then the bottom ones
+        return j < top ? j : n - h.rows_bot + (j - top);
+    }
+    return top + (i - placed);                    // the (i - placed)-th interior row
 }
 // Does the CTA that covers image rows [ya, yb) belong to the zone?
 __device__ __forceinline__ bool halo_in_zone(const HaloK& h, int ya, int yb) { return h.active && (ya < h.zone_y[0] || yb > h.zone_y[1]); }
@@ -235,8 +242,16 @@ struct K1Pixel {
 // pixel's position before they start this one, so that the two dependent memory round trips of a pixel
 // — position -> reprojection -> taps — overlap across pixels).
 // n, cur: the pixel's shading normal and this frame's noisy colour, already loaded too.
+// carry: a thread that walks down a column hands the lower tap row of one pixel to the next; when the reprojection is
+// locally uniform (the common case, checked per pixel) that row IS the upper tap row of the pixel below, and its ten
+// values need not be fetched again.  The same values from the same addresses: nothing changes in the arithmetic.
+struct K1Carry {
+    int cx0, cx1, ry;  // clamped coordinates the row was fetched from; ry < 0: nothing carried
+    f3 tp[2], tn[2], tc[2];
+    float ts[2];
+};
 template <bool STRIP>
-__device__ __forceinline__ K1Pixel k1_pixel_core(const KParams& P, int x, int y, f3 wp, f3 n, f3 cur) {
+__device__ __forceinline__ K1Pixel k1_pixel_core(const KParams& P, int x, int y, f3 wp, f3 n, f3 cur, K1Carry* carry = nullptr) {
     K1Pixel r;
     float pfx = (float)x, pfy = (float)y;  // bmfr.cl:325
     unsigned int accept = 0;
@@ -273,21 +288,32 @@ __device__ __forceinline__ K1Pixel k1_pixel_core(const KParams& P, int x, int y,
         f3 tp[4], tn[4], tc[4];
         float ts[4];
         bool valid[4];
+        const int cx[2] = {min(max(pix, 0), P.W - 1), min(max(pix + 1, 0), P.W - 1)};
+        const int ry[2] = {min(max(piy, rlo), rhi), min(max(piy + 1, rlo), rhi)};
+        const bool reuse = carry != nullptr && carry->ry == ry[0] && carry->cx0 == cx[0] && carry->cx1 == cx[1];
+        bool missing = false;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int sx = pix + (i & 1), sy = piy + (i >> 1);
             const bool inimg = sx >= 0 && sy >= 0 && sx < P.W && sy < P.H;  // bmfr.cl:380-381
-            bool held = true;
-            if (STRIP) {
-                held = sy >= P.row0 && sy < P.row1;
-                if (inimg && !held) *P.oob_flag = 1;  // strip + halo does not hold this row
-            }
+            const bool held = !STRIP || (sy >= P.row0 && sy < P.row1);
+            missing = missing || (inimg && !held);  // strip + halo does not hold this row: reported once, below
             valid[i] = inimg && held;
-            const unsigned int ls = pix_index(P, min(max(sx, 0), P.W - 1), min(max(sy, rlo), rhi));
-            tp[i] = load_f3(P.prev_positions, ls);
-            tn[i] = load_f3(P.prev_normals, ls);
-            tc[i] = load_f3(P.prev_noisy_acc, ls);
-            ts[i] = (float)__ldg(P.prev_spp + ls);
+            if (i < 2 && reuse) {  // the row the pixel above left behind
+                tp[i] = carry->tp[i]; tn[i] = carry->tn[i]; tc[i] = carry->tc[i]; ts[i] = carry->ts[i];
+            } else {
+                const unsigned int ls = pix_index(P, cx[i & 1], ry[i >> 1]);
+                tp[i] = load_f3(P.prev_positions, ls);
+                tn[i] = load_f3(P.prev_normals, ls);
+                tc[i] = load_f3(P.prev_noisy_acc, ls);
+                ts[i] = (float)__ldg(P.prev_spp + ls);
+            }
+        }
+        if (STRIP && missing) *P.oob_flag = 1;
+        if (carry != nullptr) {
+            carry->cx0 = cx[0]; carry->cx1 = cx[1]; carry->ry = ry[1];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) { carry->tp[i] = tp[2 + i]; carry->tn[i] = tn[2 + i]; carry->tc[i] = tc[2 + i]; carry->ts[i] = ts[2 + i]; }
         }
         // position and normal differences ride in the two halves of a pair (bmfr.cl:388-404);
         // (sample_spp, prev.x) and (prev.y, prev.z) are accumulated as pairs (bmfr.cl:407-415)

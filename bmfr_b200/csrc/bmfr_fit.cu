@@ -32,6 +32,13 @@
 #define BMFR_REPROJECT_BX 32  // CTA = BX x (256 / BX) pixels
 #endif
 #define BMFR_REPROJECT_BY (256 / BMFR_REPROJECT_BX)
+// 1: a thread walks down four vertically adjacent pixels and hands the lower tap row of one to the next (K1Carry; 25 %
+// fewer tap loads).  Measured at 1080p (profiles/r02_m_*): 69.8 us against 52 us — the eight warps of a CTA then work on
+// rows four apart instead of on eight consecutive rows (the adjacent-row mapping alone: 58.1 us), which costs more L1
+// locality than the shared rows save, and the carried row spills.  Off.
+#ifndef BMFR_REPROJECT_CARRY
+#define BMFR_REPROJECT_CARRY 0
+#endif
 #ifndef BMFR_REPROJECT_PIXELS
 #define BMFR_REPROJECT_PIXELS 4  // pixels per thread (rows BY apart); the next pixel's position is fetched one pixel ahead
 #endif
@@ -135,7 +142,9 @@ __global__ void __launch_bounds__(256, BMFR_REPROJECT_MIN_BLOCKS) reproject_kern
     __shared__ __align__(16) ReprojectPushStage<STRIP, true> push_stage;
     const int x = blockIdx.x * BMFR_REPROJECT_BX + threadIdx.x;
     const int cta_y0 = P.k1_y0 + (STRIP ? halo_row_order(P.halo_r, blockIdx.y, gridDim.y) : (int)blockIdx.y) * (BMFR_REPROJECT_BY * BMFR_REPROJECT_PIXELS);
-    const int ybase = cta_y0 + threadIdx.y;
+    // thread (x, ty) takes rows ty, ty + 8, ty + 16, ty + 24 of the CTA's 32 rows (BMFR_REPROJECT_CARRY: rows 4 ty .. 4 ty + 3)
+    const int ystep = BMFR_REPROJECT_CARRY ? 1 : BMFR_REPROJECT_BY;
+    const int ybase = cta_y0 + (BMFR_REPROJECT_CARRY ? BMFR_REPROJECT_PIXELS : 1) * threadIdx.y;
     // strips: a CTA near a strip edge waits for the neighbours' rows of the previous frame before it gathers from them
     const bool zone = STRIP && halo_in_zone(P.halo_r, cta_y0, cta_y0 + BMFR_REPROJECT_BY * BMFR_REPROJECT_PIXELS);
     if (zone) halo_poll(P.halo_r);
@@ -150,15 +159,19 @@ __global__ void __launch_bounds__(256, BMFR_REPROJECT_MIN_BLOCKS) reproject_kern
         // reprojection -> tap gather chain
         f3 wp_next = make_f3(0.f, 0.f, 0.f);
         if (ybase >= ylo && ybase < yhi) wp_next = load_f3_stream(P.cur_positions, pix_index(P, x, ybase));
+        K1Carry carry;
+        carry.ry = -1;
 #pragma unroll 1
         for (int k = 0; k < BMFR_REPROJECT_PIXELS; ++k) {
-            const int y = ybase + k * BMFR_REPROJECT_BY;
+            const int y = ybase + k * ystep;
             if (y >= yhi) break;
             const f3 wp = wp_next;
-            const int yn = y + BMFR_REPROJECT_BY;
+            const int yn = y + ystep;
             if (k + 1 < BMFR_REPROJECT_PIXELS && yn >= ylo && yn < yhi) wp_next = load_f3_stream(P.cur_positions, pix_index(P, x, yn));
             if (y < ylo) continue;
-            const K1Pixel r = k1_pixel<STRIP>(P, x, y, wp);
+            const unsigned int lp = pix_index(P, x, y);
+            const K1Pixel r = k1_pixel_core<STRIP>(P, x, y, wp, load_f3_stream(P.cur_normals, lp), load_f3_stream(P.cur_noisy, lp),
+                                                   BMFR_REPROJECT_CARRY ? &carry : nullptr);
             reproject_store<STRIP>(P, x, y, r, zone, push_stage.rgb, push_stage.spp, threadIdx.x, y - cta_y0);
         }
     }

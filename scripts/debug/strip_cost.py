@@ -5,7 +5,9 @@ import torch
 sys.path.insert(0, ".")
 from bmfr_b200 import Denoiser, sharding, synth
 
-W, H, frames, halo = 3840, 2160, 12, 62
+W, H, frames, halo = 3840, 2160, 12, 48
+if len(sys.argv) > 2 and sys.argv[2] == "8k":
+    W, H, halo = 7680, 4320, 60
 def inputs(w, h, y0, y1):
     t = torch.empty((frames, 4, y1 - y0, w, 3), dtype=torch.float32, device="cuda")
     for f in range(frames):
@@ -16,19 +18,19 @@ def cams(w, h):
     return [synth.camera(max(f - 1, 0), w, h)[0] for f in range(frames)], [synth.camera(f, w, h)[1] for f in range(frames)]
 def report(tag, d):
     ms = np.array([[d.fused_kernel_ms(f)[k] for k in d.fused_kernels] for f in range(2, frames)]).mean(axis=0)
-    print(f"{tag:46s} " + "  ".join(f"{k} {1e3 * v:7.1f} us" for k, v in zip(d.fused_kernels, ms)), flush=True)
+    print(f"{tag:52s} " + "  ".join(f"{k} {1e3 * v:7.1f} us" for k, v in zip(d.fused_kernels, ms)), flush=True)
 
 # (a) whole image with the pixel count of one strip
-w, h = 3840, 1088
+w, h = (3840, 1088) if W == 3840 else (7680, 544)
 t = inputs(w, h, 0, h); cm, of = cams(w, h)
 with Denoiser(w, h, mode="fused", profile=True) as d:
     for f in range(frames):
         d.denoise_frame(f, *[t[f, k].data_ptr() for k in range(4)], cm[f], of[f], 0)
-    d.sync(); report("whole 3840x1088", d)
+    d.sync(); report(f"whole {w}x{h}", d)
 del t
 # (b) the upper strip of 3840x2160, not connected (no halo duties; halo rows go stale, timing only)
 cm, of = cams(W, H)
-for strip in ((0, 1088), (1088, 2160)):
+for strip in (((0, 1088), (1088, 2160)) if W == 3840 else ((0, 544), (1632, 2176))):
     d = Denoiser(W, H, mode="fused", profile=True, strip=strip, halo_rows=halo)
     g = d.geometry
     t = inputs(W, H, g.row0, g.row1)

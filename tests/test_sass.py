@@ -3,7 +3,8 @@
 * The reprojection must stay bit-exact against the oracle: ptxas 12.9 contracts `mul.rn.f32x2` followed by
   `add/sub.rn.f32x2` into FFMA2 even with --fmad=false, so K1 keeps its products scalar and only packs sums
   (csrc/bmfr_device.cuh).  A fused multiply-add in the K1 kernels would silently break parity.
-* The FUSED fit is the TMA-fed, FFMA2 kernel DESIGN.md describes: its SASS must show it.
+* The FUSED kernels are the TMA-fed kernels DESIGN.md describes: their SASS must show it (UTMALDG = cp.async.bulk.tensor,
+  SYNCS = mbarrier, FFMA2 = packed fp32 fma).
 """
 import re
 import shutil
@@ -51,15 +52,36 @@ def test_reprojection_has_no_fused_multiply_add_pairs(sass):
         assert ops.count("FFMA") <= 12 * ops.count("FCHK") + 8, f"{name}: unexpected scalar FFMA count {ops.count('FFMA')}"
 
 
-def test_fit_kernel_uses_tma_and_packed_fma(sass):
-    fit = [l for n, l in sass.items() if "fit_qr_kernel" in n]
-    assert fit
+@pytest.mark.parametrize("kernel,min_ffma2", [("fit_qr_kernel", 300), ("fit_gram_kernel", 200)])
+def test_fit_kernels_use_tma_and_packed_fma(sass, kernel, min_ffma2):
+    fit = [l for n, l in sass.items() if kernel in n]
+    assert len(fit) == 2, list(sass)
     for lines in fit:
         ops = _ops(lines)
         assert "UTMALDG" in ops, "the TMA tile loads of the fit are gone"
-        assert ops.count("FFMA2") > 300, "the level-1 factorisation is no longer on packed pairs"
+        assert ops.count("FFMA2") > min_ffma2, "the factorisation / the Gram products are no longer on packed pairs"
         assert "SYNCS" in ops, "mbarrier hand-off missing"
         assert len(lines) * 16 < 64 * 1024, f"fit kernel grew to {len(lines) * 16 // 1024} KB of SASS (I-cache)"
         # shared memory must be addressed as such: a struct reached through an integer-rounded pointer
         # turns every access into a generic LD / ST (what the kernel did until r01 v7)
         assert ops.count("LDS") > 100 and ops.count("LD") < 16, (ops.count("LDS"), ops.count("LD"))
+
+
+def test_post_pass_stages_its_tiles_with_tma(sass):
+    post = [l for n, l in sass.items() if "post_tma_kernel" in n]
+    assert len(post) == 2, list(sass)
+    for lines in post:
+        ops = _ops(lines)
+        assert ops.count("UTMALDG") >= 6, "the six bulk tensor copies of a tile (normals, positions, albedo, prev_pixels, accept, spp)"
+        assert "SYNCS" in ops, "mbarrier hand-off missing"
+        assert ops.count("LDS") > 100 and ops.count("LD") < 16, (ops.count("LDS"), ops.count("LD"))
+
+
+def test_strip_kernels_store_to_peers_in_wide_rows(sass):
+    """The in-kernel halo exchange: the strip instantiations poll with volatile loads (LDG.E.STRONG / .SYS), fence at system
+    scope and send staged rows as 128- / 64-bit stores."""
+    for name, width in (("reproject_kernelILb1E", "128"), ("post_tma_kernelILb1E", "64")):
+        lines = next(l for n, l in sass.items() if name in n)
+        text = "\n".join(lines)
+        assert "MEMBAR" in text and ".SYS" in text, f"{name}: no system-scope fence"
+        assert re.search(r"STG\.E\.(\w+\.)*" + width, text), f"{name}: no {width}-bit global stores"
