@@ -89,10 +89,12 @@ __device__ __forceinline__ void halo_poll(const HaloK& h) {
     __syncthreads();
 }
 // Epilogue of a zone CTA (all threads call it, after their last store): the last zone CTA of the launch raises the flags.
-__device__ __forceinline__ void halo_finish(const HaloK& h) {
+__device__ __forceinline__ void halo_finish(const HaloK& h, bool pushed) {
     __syncthreads();  // every thread's peer stores precede ...
     if (threadIdx.x == 0 && threadIdx.y == 0) {
-        __threadfence_system();  // ... this fence (cumulative over what the barrier ordered before it): visible system-wide before the count
+        // ... this fence (cumulative over what the barrier ordered before it): visible system-wide before the count.  A zone
+        // CTA that only read halo rows has nothing to publish.
+        if (pushed) __threadfence_system();
         const unsigned int done = atomicAdd(h.done_counter, 1u);
         if (done + 1 == h.zone_ctas) {
             *h.done_counter = 0;  // for the next launch (ordered after this one by the stream)
@@ -105,6 +107,10 @@ __device__ __forceinline__ void halo_finish(const HaloK& h) {
             }
         }
     }
+}
+// Does a CTA that covers image rows [ya, yb) store any row a neighbour mirrors?
+__device__ __forceinline__ bool halo_cta_pushes(const HaloK& h, int ya, int yb) {
+    return (h.side_on[0] && ya < h.push_y1[0] && yb > h.push_y0[0]) || (h.side_on[1] && ya < h.push_y1[1] && yb > h.push_y0[1]);
 }
 // Index of image pixel (x, y) in the neighbour's buffers on side s, or -1 when the row is not mirrored there.
 __device__ __forceinline__ long long halo_peer_index(const HaloK& h, const KParams& P, int s, int x, int y) {

@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(256, BMFR_REPROJECT_MIN_BLOCKS) reproject_kern
                 __syncthreads();
                 reproject_push_rows(P, push_stage.rgb, push_stage.spp, blockIdx.x * BMFR_REPROJECT_BX, cta_y0, threadIdx.y * BMFR_REPROJECT_BX + threadIdx.x);
             }
-            halo_finish(P.halo_r);
+            halo_finish(P.halo_r, halo_cta_pushes(P.halo_r, cta_y0, cta_y0 + 32));
         }
     }
 }
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(256, BMFR_REPROJECT_MIN_BLOCKS) reproject_tma_
                 __syncthreads();
                 reproject_push_rows(P, sh.col, push_stage.spp, x0, y0, threadIdx.x);
             }
-            halo_finish(P.halo_r);
+            halo_finish(P.halo_r, halo_cta_pushes(P.halo_r, y0, y0 + 32));
         }
     }
 }

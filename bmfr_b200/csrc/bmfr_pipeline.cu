@@ -417,7 +417,23 @@ static void fill_halo(bmfr_ctx* c, KParams& P) {
             h.push_y0[s] = h.push_y1[s] = 0;
             if (!pr.connected) continue;
             int y0, y1;
-            if (halo_rows_for(c, s, late != 0, &y0, &y1)) { h.push_y0[s] = y0; h.push_y1[s] = y1; }
+            if (halo_rows_for(c, s, late != 0, &y0, &y1)) {
+                if (!late) {
+                    // The rows next to the edge that the neighbour reprojects itself this frame — the rows of its blocks that
+                    // straddle the edge, bit-identical to ours by construction — need not travel: they are the rows of its
+                    // first / last block row of this frame (KParams::k1_y0 / k1_y1 on its side, from this frame's block offset).
+                    if (s == 1) {  // neighbour below: it covers [k1_y0', own_y1) itself
+                        const int nb_by0 = (g.own_y1 - 1 + 16 - P.off_y) >> 5;
+                        const int nb_k1_y0 = nb_by0 * 32 - 16 + P.off_y;
+                        if (nb_k1_y0 < y1) y1 = nb_k1_y0 > y0 ? nb_k1_y0 : y0;
+                    } else {       // neighbour above: it covers [own_y0, k1_y1') itself
+                        const int nb_by1 = ((g.own_y0 + 16 - P.off_y) >> 5) + 1;
+                        const int nb_k1_y1 = nb_by1 * 32 - 16 + P.off_y;
+                        if (nb_k1_y1 > y0) y0 = nb_k1_y1 < y1 ? nb_k1_y1 : y1;
+                    }
+                }
+                h.push_y0[s] = y0; h.push_y1[s] = y1;
+            }
             h.peer_row0[s] = pr.row0;
             h.peer_a[s] = late ? pr.accum[cur] : pr.noisy_acc[cur];
             h.peer_b[s] = late ? pr.result[cur] : nullptr;

@@ -476,7 +476,7 @@ __global__ void __launch_bounds__(256, BMFR_POST_MIN_BLOCKS) post_kernel(const _
         if (P.user_out) stf3<WIDE>(P.user_out, lp, out);
         post_push<STRIP>(P, 1, x, y0 + 4 * warp + s, out);
     }
-    if (zone) halo_finish(P.halo_p);
+    if (zone) halo_finish(P.halo_p, halo_cta_pushes(P.halo_p, y0, y0 + 32));
 }
 
 
@@ -884,7 +884,7 @@ __global__ void __launch_bounds__(256, BMFR_POST_TMA_MIN_BLOCKS) post_tma_kernel
     if (STRIP && zone) {
         __syncthreads();  // the staged rows are complete
         post_push_rows(P, sh, G, tid);
-        halo_finish(P.halo_p);
+        halo_finish(P.halo_p, halo_cta_pushes(P.halo_p, G.y0, G.y0 + 32));
     }
 }
 
