@@ -50,6 +50,14 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+// profile = 2 (bmfr_get_fused_kernel_busy_ms): when did the first CTA of kernel k start, when did the last one end?
+__device__ __forceinline__ void stamp_begin(const KParams& P, int k) {
+    if (P.stamps != nullptr && threadIdx.x == 0 && threadIdx.y == 0) atomicMin(P.stamps + 2 * k, globaltimer_ns());
+}
+__device__ __forceinline__ void stamp_end(const KParams& P, int k) {
+    if (P.stamps != nullptr && threadIdx.x == 0 && threadIdx.y == 0) atomicMin(P.stamps + 2 * k + 1, ~globaltimer_ns());
+}
+
 // Zone rows early and spread out: CTA row i of n (blockIdx.y, which the hardware hands out in ascending order) -> the row
 // it works on.  The Z zone rows take every k-th position from the start (k = n / Z), the interior rows fill the rest: the
 // zone CTAs' peer stores then drain over NVLink while interior CTAs compute (all zone CTAs at once would hold most of

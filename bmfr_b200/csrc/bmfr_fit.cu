@@ -138,6 +138,8 @@ __global__ void __launch_bounds__(256, BMFR_REPROJECT_MIN_BLOCKS) reproject_kern
     // after the wait, so that "everything before this grid is complete" is transitive: the fit requests its first
     // normals / positions tiles (the caller's inputs) before its own wait
     pdl_trigger();  // the fit's CTAs may take SM slots as this grid drains
+    stamp_begin(P, 0);
+    if (P.stamps_next != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.y == 0 && threadIdx.x < 6) P.stamps_next[threadIdx.x] = ~0ull;
     reproject_noise_tile(P, threadIdx.y * BMFR_REPROJECT_BX + threadIdx.x);
     __shared__ __align__(16) ReprojectPushStage<STRIP, true> push_stage;
     const int x = blockIdx.x * BMFR_REPROJECT_BX + threadIdx.x;
@@ -184,6 +186,7 @@ __global__ void __launch_bounds__(256, BMFR_REPROJECT_MIN_BLOCKS) reproject_kern
             halo_finish(P.halo_r, halo_cta_pushes(P.halo_r, cta_y0, cta_y0 + 32));
         }
     }
+    stamp_end(P, 0);
 }
 
 // --------------------------------------------------------------------------------------------
@@ -217,6 +220,8 @@ __global__ void __launch_bounds__(256, BMFR_REPROJECT_MIN_BLOCKS) reproject_tma_
     }
     pdl_wait();     // the caller's inputs are complete (see reproject_kernel)
     pdl_trigger();
+    stamp_begin(P, 0);
+    if (P.stamps_next != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 6) P.stamps_next[threadIdx.x] = ~0ull;
     if (threadIdx.x == 0) {  // rows below the image / the strip arrive as zeros and are never used
         mbar_expect_tx(&sh.bar, 3 * 32 * RP_TILE_W * 4);
         tma_load_tile(&sh.pos[0][0], &M.positions, x0 * 3, y0 - P.row0, &sh.bar);
@@ -256,6 +261,7 @@ __global__ void __launch_bounds__(256, BMFR_REPROJECT_MIN_BLOCKS) reproject_tma_
             halo_finish(P.halo_r, halo_cta_pushes(P.halo_r, y0, y0 + 32));
         }
     }
+    stamp_end(P, 0);
 }
 
 // --------------------------------------------------------------------------------------------
@@ -622,6 +628,7 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
     if (tid == 0 && first_by_tma) qr_prefetch(P, M, sh, fox, foy, 1);
     pdl_wait();     // the reprojection of this frame is complete (accumulated colour, noise tile, block counter)
     pdl_trigger();  // after the wait, so that completion of everything before this grid is transitive for the post pass
+    stamp_begin(P, 1);
 
     if (warp == 0) {
         QR_CTA_STAMP(0);
@@ -804,6 +811,7 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
     // ---------------- level 2 + back-substitution of this CTA's blocks ----------------
     qr_solve_mine(P, sh, mine, warp, lane);
     if (warp == 0) QR_CTA_STAMP(2);
+    stamp_end(P, 1);
 }
 
 
@@ -996,6 +1004,7 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_GRAM_MIN_BLOCKS) fit_gram_ker
     if (tid == 0 && first_by_tma) qr_prefetch(P, M, sh, fox, foy, 1);
     pdl_wait();     // the reprojection of this frame is complete (accumulated colour, noise tile, block counter)
     pdl_trigger();  // after the wait, so that completion of everything before this grid is transitive for the post pass
+    stamp_begin(P, 1);
     if (tid == 0) {
         sh.blk[0] = first;
         if (first_by_tma) qr_prefetch(P, M, sh, fox, foy, 2);
@@ -1205,6 +1214,7 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_GRAM_MIN_BLOCKS) fit_gram_ker
     GRAM_STAMP(14);
     gram_solve_mine(P, sh, mine, warp, lane);
     GRAM_STAMP(15);
+    stamp_end(P, 1);
 }
 
 // --------------------------------------------------------------------------------------------

@@ -84,6 +84,10 @@ struct KParams {
     int* oob_flag;                // set when a gather needed a row outside [row0,row1)
     int* block_counter;           // FUSED fit: dynamic block schedule, reset by the reprojection (STAGED: noise-tile kernel) of the frame
     float* tri;                   // FUSED fit: level-1 triangles between the two levels of the TSQR, blocks x 4 x 136 floats
+    // profile = 2: per kernel (reproject, fit, post) the earliest CTA start and the latest CTA end of this frame's launch,
+    // globaltimer ns, both kept with atomicMin (the end as ~t); stamps_next = the next frame's slot, re-armed by the reprojection
+    unsigned long long* stamps;
+    unsigned long long* stamps_next;
     HaloK halo_r, halo_p;         // halo exchange duties of the reprojection / the post pass (FUSED strips)
     int fit_method;               // host side only: BMFR_FIT_GRAM / BMFR_FIT_TSQR (which FUSED fit kernel launch_fit_qr starts)
     int plain_launch;             // host side only: launch the FUSED kernels without programmatic stream serialization

@@ -102,6 +102,8 @@ struct bmfr_ctx {
     bool host_ready = false;
 
     std::vector<StageEvents> prof;
+    unsigned long long* d_stamps = nullptr;  // profile = 2: [kProfileSlots][3 kernels][first start, ~last end] (globaltimer ns)
+    int stamp_frame[kProfileSlots];
 
     // peer-to-peer halo exchange (sharded contexts): the neighbour above (side 0) / below (side 1)
     struct Peer {
@@ -195,6 +197,7 @@ static void free_ctx(bmfr_ctx* c) {
         }
     }
     cudaFree(c->d_flags);
+    cudaFree(c->d_stamps);
     for (int k = 0; k < 4; ++k)
         for (int s = 0; s < kHostSlots; ++s) cudaFree(c->up[k][s]);
     for (int s = 0; s < kHostSlots; ++s) {
@@ -346,8 +349,13 @@ int bmfr_create(const bmfr_params* params, bmfr_ctx** out_ctx) {
     if ((st = bmfr_check_cuda(cudaMemsetAsync(c->weights, 0, nb * BMFR_FEATURES * 3 * sizeof(float), c->stream), "memset")) != 0) return fail(st);
     if ((st = bmfr_check_cuda(cudaMemsetAsync(c->mins_maxs, 0, nb * BMFR_FEATURES_SCALED * 2 * sizeof(float), c->stream), "memset")) != 0) return fail(st);
     if ((st = bmfr_check_cuda(cudaMemsetAsync(c->mins_inv, 0, nb * BMFR_FEATURES_SCALED * 2 * sizeof(float), c->stream), "memset")) != 0) return fail(st);
-    if (p.profile) c->prof.resize(kProfileSlots);
-    if (p.overlap_frames && p.mode == BMFR_MODE_FUSED && !p.profile) {
+    if (p.profile == 1) c->prof.resize(kProfileSlots);
+    if (p.profile == 2 && p.mode == BMFR_MODE_FUSED) {
+        if ((st = dev_alloc(&c->d_stamps, (size_t)kProfileSlots * 6, "kernel stamps")) != 0) return fail(st);
+        if ((st = bmfr_check_cuda(cudaMemsetAsync(c->d_stamps, 0xFF, (size_t)kProfileSlots * 6 * sizeof(unsigned long long), c->stream), "memset")) != 0) return fail(st);
+        for (int i = 0; i < kProfileSlots; ++i) c->stamp_frame[i] = -1;
+    }
+    if (p.overlap_frames && p.mode == BMFR_MODE_FUSED && p.profile != 1) {
         bmfr_ctx::Overlap& o = c->ov;
         if (st == 0) st = dev_alloc(&o.prev_pixels, npix, "prev_pixels (odd frames)");
         if (st == 0) st = dev_alloc(&o.accept, npix, "accept (odd frames)");
@@ -522,6 +530,12 @@ static void fill_params(bmfr_ctx* c, KParams& P, int frame, const float* d_albed
     P.plain_launch = c->ov.on ? 1 : 0;
     P.fit_method = c->prm.fit_method;
     P.tri = c->tri;
+    if (c->d_stamps) {  // this frame's slot was armed by the previous frame's reprojection (the first one at create)
+        const size_t slot = (size_t)c->seq % kProfileSlots, next = (size_t)(c->seq + 1) % kProfileSlots;
+        P.stamps = c->d_stamps + slot * 6;
+        P.stamps_next = c->d_stamps + next * 6;
+        c->stamp_frame[slot] = frame;
+    }
     fill_halo(c, P);
 }
 
@@ -869,6 +883,22 @@ int bmfr_get_fused_kernel_ms(bmfr_ctx* c, int frame, float ms[BMFR_FUSED_KERNEL_
     if (!s.created || s.frame != frame) return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_get_fused_kernel_ms: frame %d not recorded", frame);
     BMFR_CUDA_TRY(cudaEventSynchronize(s.ev[BMFR_FUSED_KERNEL_COUNT]));
     for (int i = 0; i < BMFR_FUSED_KERNEL_COUNT; ++i) BMFR_CUDA_TRY(cudaEventElapsedTime(&ms[i], s.ev[i], s.ev[i + 1]));
+    return BMFR_OK;
+}
+
+int bmfr_get_fused_kernel_busy_ms(bmfr_ctx* c, int frame, float ms[BMFR_FUSED_KERNEL_COUNT], float* frame_ms) {
+    if (!c || !ms) return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_get_fused_kernel_busy_ms: null argument");
+    if (!c->d_stamps) return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_get_fused_kernel_busy_ms: needs a FUSED context created with profile=2");
+    int slot = -1;
+    for (int i = 0; i < kProfileSlots; ++i)
+        if (c->stamp_frame[i] == frame) slot = i;
+    if (slot < 0) return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_get_fused_kernel_busy_ms: frame %d not recorded", frame);
+    int st = bmfr_sync(c);
+    if (st != 0) return st;
+    unsigned long long t[6];
+    BMFR_CUDA_TRY(cudaMemcpy(t, c->d_stamps + (size_t)slot * 6, sizeof(t), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 3; ++k) ms[k] = (float)((double)(~t[2 * k + 1] - t[2 * k]) * 1e-6);
+    if (frame_ms) *frame_ms = (float)((double)(~t[5] - t[0]) * 1e-6);
     return BMFR_OK;
 }
 

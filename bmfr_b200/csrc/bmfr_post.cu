@@ -363,6 +363,7 @@ __global__ void __launch_bounds__(256, BMFR_POST_MIN_BLOCKS) post_kernel(const _
     // Only now: a successor (the next frame's reprojection) starts once every CTA of this grid has passed
     // this point, so "this frame's fit and reprojection are complete" holds for it too.
     pdl_trigger();
+    stamp_begin(P, 2);
     // strips: a CTA near a strip edge waits for the neighbours' accumulated colour / TAA rows of the previous frame
     const bool zone = STRIP && halo_in_zone(P.halo_p, y0 - 1, y0 + 33);
     if (zone) halo_poll(P.halo_p);
@@ -477,6 +478,7 @@ __global__ void __launch_bounds__(256, BMFR_POST_MIN_BLOCKS) post_kernel(const _
         post_push<STRIP>(P, 1, x, y0 + 4 * warp + s, out);
     }
     if (zone) halo_finish(P.halo_p, halo_cta_pushes(P.halo_p, y0, y0 + 32));
+    stamp_end(P, 2);
 }
 
 
@@ -718,6 +720,7 @@ __global__ void __launch_bounds__(256, BMFR_POST_TMA_MIN_BLOCKS) post_tma_kernel
     }
     pdl_wait();     // the fit of this frame is complete (weights, min/max)
     pdl_trigger();  // only now, so that "this frame's fit and reprojection are complete" also holds for the successor
+    stamp_begin(P, 2);
     // strips: a CTA near a strip edge waits for the neighbours' accumulated colour / TAA rows of the previous frame
     const bool zone = STRIP && halo_in_zone(P.halo_p, G.y0 - 1, G.y0 + 33);
     if (zone) halo_poll(P.halo_p);
@@ -886,6 +889,7 @@ __global__ void __launch_bounds__(256, BMFR_POST_TMA_MIN_BLOCKS) post_tma_kernel
         post_push_rows(P, sh, G, tid);
         halo_finish(P.halo_p, halo_cta_pushes(P.halo_p, G.y0, G.y0 + 32));
     }
+    stamp_end(P, 2);
 }
 
 #ifndef BMFR_POST_TMA

@@ -156,6 +156,12 @@ class Denoiser:
         _lib.check(self.lib.bmfr_get_fused_kernel_ms(self._h, frame, ms))
         return dict(zip(self.fused_kernels, ms))
 
+    def fused_kernel_busy_ms(self, frame):
+        """(per-kernel first-CTA-start .. last-CTA-end in ms, the same for the whole frame); FUSED, profile=2."""
+        ms, total = (C.c_float * 3)(), C.c_float()
+        _lib.check(self.lib.bmfr_get_fused_kernel_busy_ms(self._h, frame, ms, C.byref(total)))
+        return dict(zip(self.fused_kernels, ms)), float(total.value)
+
     @property
     def kernel_launches(self):
         return int(self.lib.bmfr_kernel_launches(self._h))

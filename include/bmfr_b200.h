@@ -67,7 +67,9 @@ typedef struct bmfr_params {
     float normal_limit_squared;   /* NORMAL_LIMIT_SQUARED,   bmfr.cpp:227 */
     int tmp_half;                 /* USE_HALF_PRECISION_IN_TMP_DATA, bmfr.cpp:88 (the reference ships 1; the default here
                                      is 0 = fp32 fitter).  1 needs mode = STAGED and implies reference_order = 1 */
-    int profile;                  /* 1: record per-stage CUDA-event times (bmfr.cpp:386-397) */
+    int profile;                  /* 1: record per-stage CUDA-event times (bmfr.cpp:386-397); 2 (FUSED): no events between the
+                                     kernels (their programmatic chaining stays intact), every kernel stamps the start of its
+                                     first and the end of its last CTA instead — bmfr_get_fused_kernel_busy_ms */
     /* Strip sharding (no counterpart in the reference, which is single-device).  The context owns
      * image rows [strip_y0, strip_y1) and stores rows [strip_y0 - halo_rows, strip_y1 + halo_rows)
      * clipped to the image.  strip_y0 = strip_y1 = 0 means the whole image, halo_rows ignored. */
@@ -209,6 +211,11 @@ int bmfr_get_stage_ms(bmfr_ctx* ctx, int frame, float ms[BMFR_STAGE_COUNT]);
 /* FUSED contexts: device time of each of the three kernels of one frame, in launch order. */
 enum { BMFR_FUSED_REPROJECT = 0, BMFR_FUSED_FIT_QR = 1, BMFR_FUSED_POST = 2, BMFR_FUSED_KERNEL_COUNT = 3 };
 int bmfr_get_fused_kernel_ms(bmfr_ctx* ctx, int frame, float ms[BMFR_FUSED_KERNEL_COUNT]);
+/* FUSED contexts created with profile = 2: for each of the three kernels of one frame, the time from the start of its
+ * first CTA to the end of its last one (device globaltimer), measured INSIDE the chained run — unlike the event times
+ * above it contains no launch gap and the kernels may overlap; frame_ms (may be NULL): first CTA of the reprojection to
+ * last CTA of the post pass. */
+int bmfr_get_fused_kernel_busy_ms(bmfr_ctx* ctx, int frame, float ms[BMFR_FUSED_KERNEL_COUNT], float* frame_ms);
 /* Number of kernels this library has launched on the context so far. */
 long long bmfr_kernel_launches(const bmfr_ctx* ctx);
 

@@ -120,6 +120,27 @@ def test_tsqr_fit_still_matches_oracle():
     _check_frames(cuda, ref, False)
 
 
+def test_busy_stamps_do_not_change_results_and_are_plausible():
+    """profile = 2: every kernel stamps the start of its first and the end of its last CTA (device globaltimer) instead of
+    event records between the launches.  Same bits as an unprofiled run; times positive, ordered, below a frame's span."""
+    w, h, frames = 416, 250, 6
+    seq = list(util.sequence(w, h, frames))
+    outs = {}
+    for prof in (0, 2):
+        with Denoiser(w, h, mode="fused", profile=prof) as d:
+            for fr in seq:
+                d.denoise_frame_host(*fr)
+            outs[prof] = {k: d.read(k) for k in ("result", "accum", "spp", "accept")}
+            if prof == 2:
+                for f in range(1, frames):
+                    busy, span = d.fused_kernel_busy_ms(f)
+                    assert set(busy) == set(d.fused_kernels)
+                    assert all(0.0 < v < 5.0 for v in busy.values()), busy
+                    assert max(busy.values()) <= span <= sum(busy.values()) + 1.0, (busy, span)
+    for k in outs[0]:
+        assert util.bits_equal(outs[0][k], outs[2][k]), k
+
+
 def test_staged_and_fused_agree():
     """The two kernel structures share the reprojection code (bit-identical K1 outputs, block min/max
     and noise tile); the fit and the post-fit passes are separate implementations held to the colour
