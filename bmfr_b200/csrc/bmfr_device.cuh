@@ -43,6 +43,35 @@ static inline cudaError_t launch_pdl(bool pdl, void (*kernel)(KArgs...), dim3 gr
 }
 
 // ---------------------------------------------------------------------------------------------
+// Feature lists (bmfr_params.feature_set).  The reference pastes a compile-time string into its kernels
+// (NOT_SCALED_FEATURE_BUFFERS / SCALED_FEATURE_BUFFERS, bmfr.cpp:63-77 -> FEATURE_BUFFERS, bmfr.cl:447-453,724-729); here
+// the FUSED fit and post pass are instantiated for a fixed set of lists.  F = features (the constant 1 first), NSC = the
+// scaled ones (at the end), then three colour columns: NCOL non-constant columns per block matrix.
+// ---------------------------------------------------------------------------------------------
+template <int FS> struct FeatureSet;
+template <> struct FeatureSet<BMFR_FEATURE_SET_DEFAULT> {  // 1, n.xyz | p.xyz, p.xyz^2 (bmfr.cpp:65-77)
+    static constexpr int F = 10, NSC = 6;
+    static constexpr bool NORMALS = true, SQUARES = true;
+};
+template <> struct FeatureSet<BMFR_FEATURE_SET_LINEAR> {   // 1, n.xyz | p.xyz
+    static constexpr int F = 7, NSC = 3;
+    static constexpr bool NORMALS = true, SQUARES = false;
+};
+template <> struct FeatureSet<BMFR_FEATURE_SET_POSITION> { // 1 | p.xyz, p.xyz^2
+    static constexpr int F = 7, NSC = 6;
+    static constexpr bool NORMALS = false, SQUARES = true;
+};
+// the non-constant columns of one matrix row from the pixel's normal, world position and accumulated colour
+template <int FS>
+__device__ __forceinline__ void feature_columns(float* __restrict__ dst, const float* __restrict__ n, const float* __restrict__ p, const float* __restrict__ col) {
+    int k = 0;
+    if (FeatureSet<FS>::NORMALS) { dst[k] = n[0]; dst[k + 1] = n[1]; dst[k + 2] = n[2]; k += 3; }
+    dst[k] = p[0]; dst[k + 1] = p[1]; dst[k + 2] = p[2]; k += 3;
+    if (FeatureSet<FS>::SQUARES) { dst[k] = p[0] * p[0]; dst[k + 1] = p[1] * p[1]; dst[k + 2] = p[2] * p[2]; k += 3; }
+    dst[k] = col[0]; dst[k + 1] = col[1]; dst[k + 2] = col[2];
+}
+
+// ---------------------------------------------------------------------------------------------
 // In-kernel halo exchange of strip contexts (HaloK in bmfr_kernels.h).
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long globaltimer_ns() {

@@ -45,8 +45,8 @@
 // Layout of the fp32 copy of the noise tile (read only by fit_qr_kernel): feature c (0..8 = columns
 // 1..9), pixel (x, y) of the block.  The fit's thread (warp = y / 8, lane = x) owns rows y = 8 warp .. +7
 // and reads them as two float4 per feature, consecutive lanes 16 bytes apart.
-__device__ __forceinline__ int noise_f_index(int c, int y, int x) {
-    return (((((y >> 3) * (BMFR_FEATURES - 1) + c) * 2 + ((y & 7) >> 2)) * 32 + x) << 2) + (y & 3);
+__device__ __forceinline__ int noise_f_index(int c, int y, int x, int noisy_columns) {
+    return (((((y >> 3) * noisy_columns + c) * 2 + ((y & 7) >> 2)) * 32 + x) << 2) + (y & 3);
 }
 
 // The first CTAs of the reprojection also produce this frame's add_random() tile (bmfr.cl:173-182; one 9x1024 tile per
@@ -56,12 +56,12 @@ __device__ __forceinline__ void reproject_noise_tile(const KParams& P, int tid) 
     const int cta = blockIdx.y * gridDim.x + blockIdx.x, ncta = gridDim.x * gridDim.y;
     const int workers = ncta < 36 ? ncta : 36;
     if (cta < workers) {
-        const int n = (BMFR_FEATURES - 1) * BMFR_BLOCK_PIXELS;
+        const int n = (P.n_features - 1) * BMFR_BLOCK_PIXELS;  // columns 1 .. F-1 get noise; BUFFER_COUNT = F + 3 (bmfr.cl:179-181)
         for (int i = cta * 256 + tid; i < n; i += workers * 256) {
-            const int seed = i + BMFR_BLOCK_PIXELS + P.frame * BMFR_BUFFER_COUNT * BMFR_BLOCK_PIXELS;
+            const int seed = i + BMFR_BLOCK_PIXELS + P.frame * (P.n_features + 3) * BMFR_BLOCK_PIXELS;
             const double d = (P.noise_amount * 2.0) * (double)(bmfr_random((unsigned int)seed) - 0.5f);
             P.noise_out[i] = d;
-            P.noise_f_out[noise_f_index(i / BMFR_BLOCK_PIXELS, (i % BMFR_BLOCK_PIXELS) / 32, i % 32)] = (float)d;
+            P.noise_f_out[noise_f_index(i / BMFR_BLOCK_PIXELS, (i % BMFR_BLOCK_PIXELS) / 32, i % 32, P.n_features - 1)] = (float)d;
         }
         if (cta == 0 && tid == 0) *P.block_counter = 0;
     }
@@ -833,8 +833,8 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_QR_MIN_BLOCKS) fit_qr_kernel(
 // relative error of the fitted colour: reference-order fp32 Householder 1.3e-5, this scheme 1.9e-5, uncentred fp32
 // normal equations 3e-4 (scripts/gram_accuracy.py); parity tests hold the frame to 1e-3 / 60 dB as before.
 // ================================================================================================
-#define GR_ENTRIES 90   // upper triangle of the 13x13 Gram matrix without G_00 (= 1024): row 0 first (12 column sums), then rows 1..12
-#define GR_STRIDE 104   // floats per (block, warp) in the scratch: 90 Gram entries, 12 block means (warp 0), padding; <= QR_TRI_G
+// Scratch per (block, warp): QR_TRI_G floats — the Gram entries (90 for the default list), then the block means of the
+// non-constant columns (written by warp 0).
 #define GR_RED_W 36     // floats per row of the transpose buffer: 16-byte aligned rows, conflict-free 128-bit reads
 // CTAs per SM.  Measured at 1080p (profiles/r02_f_*): 3 -> 35.2 us, 4 (with 16-entry reduction rounds, 128 registers) ->
 // 45.3 us: a CTA's first block is its most expensive one (cold landing zone, cold instruction cache) and a fourth CTA
@@ -856,8 +856,7 @@ struct GramShared {
     unsigned long long data_full;
     int blk[2];
 };
-static_assert(GR_STRIDE <= QR_TRI_G, "the Gram scratch reuses the triangle scratch allocation");
-static_assert(2 * BMFR_BUFFER_COUNT * BMFR_FEATURES * sizeof(double) <= GR_CHUNK * GR_RED_W * sizeof(float), "solver workspace fits the transpose buffer");
+static_assert(2 * BMFR_BUFFER_COUNT * BMFR_FEATURES * sizeof(double) <= GR_CHUNK * GR_RED_W * sizeof(float), "solver workspace (largest list) fits the transpose buffer");
 static_assert(GR_CHUNK >= BMFR_BUFFER_COUNT - 1 && GR_CHUNK <= 32, "the column sums of a block go through the buffer in one round");
 
 // Sum of the 32 floats of one row of the transpose buffer (eight 128-bit loads, pairwise tree).
@@ -891,13 +890,15 @@ __device__ __forceinline__ double rcp_f64(double d) {
     return r;
 }
 // index of G_ij (i <= j, (i, j) != (0, 0)) in the scratch order
+template <int NCOL>
 __device__ __forceinline__ int gram_index(int i, int j) {
-    return i == 0 ? j - 1 : 12 + (i - 1) * 12 - ((i - 1) * (i - 2)) / 2 + (j - i);
+    return i == 0 ? j - 1 : NCOL + (i - 1) * NCOL - ((i - 1) * (i - 2)) / 2 + (j - i);
 }
 
-// Cholesky + substitutions for the block `blk` by half a warp (hb = lane & 16): lane i < 13 owns row i of G.
+// Cholesky + substitutions for the block `blk` by half a warp (hb = lane & 16): lane i < NC owns row i of G.
+template <int FS>
 __device__ __forceinline__ void gram_solve(const KParams& P, double* __restrict__ fin, int blk, int lane) {
-    constexpr int NC = BMFR_BUFFER_COUNT, NF = BMFR_FEATURES;
+    constexpr int NF = FeatureSet<FS>::F, NC = NF + 3, NCOL = NC - 1, ENTRIES = NCOL + NCOL * (NCOL + 1) / 2;
     const int i = lane & 15, hb = lane & 16;
     const bool owner = blk >= 0 && i < NC;
     const float* sc = P.tri + (size_t)(blk >= 0 ? blk : 0) * QR_COMPUTE_WARPS * QR_TRI_G;
@@ -906,7 +907,7 @@ __device__ __forceinline__ void gram_solve(const KParams& P, double* __restrict_
     for (int j = 0; j < NC; ++j) {
         double v = 0.0;
         if (owner && (i | j) != 0) {
-            const int e = gram_index(i < j ? i : j, i < j ? j : i);
+            const int e = gram_index<NCOL>(i < j ? i : j, i < j ? j : i);
 #pragma unroll
             for (int w = 0; w < QR_COMPUTE_WARPS; ++w) v += (double)__ldcg(sc + w * QR_TRI_G + e);  // the four warps, in fp64, fixed order
         }
@@ -941,7 +942,7 @@ __device__ __forceinline__ void gram_solve(const KParams& P, double* __restrict_
             x[r] = a * rcp_f64(fin[r * NF + r]);
         }
         // the columns were centred: y - m_y = x_0 + sum_j x_j (a_j - m_j)  ->  intercept of the uncentred model
-        const float* mean = sc + GR_ENTRIES;  // block means of columns 1..12, written by warp 0
+        const float* mean = sc + ENTRIES;  // block means of the non-constant columns, written by warp 0
         double w0 = x[0] + (double)__ldcg(mean + (NF - 1) + i);
 #pragma unroll
         for (int jj = 1; jj < NF; ++jj) w0 -= x[jj] * (double)__ldcg(mean + jj - 1);
@@ -953,14 +954,14 @@ __device__ __forceinline__ void gram_solve(const KParams& P, double* __restrict_
     __syncwarp();  // fin is reused by this half-warp's next block
 }
 
-template <class SH>
+template <int FS, class SH>
 __device__ __noinline__ void gram_solve_mine(const KParams& P, SH& sh, int count, int warp, int lane) {
     __syncthreads();  // this CTA's scratch stores and the list are complete
     // fp64 workspace of the two half-warps: this warp's own transpose buffer (idle between blocks)
     double* fin = reinterpret_cast<double*>(&sh.red[warp][0][0]) + (size_t)(lane >> 4) * (BMFR_BUFFER_COUNT * BMFR_FEATURES);
     for (int t = 0; t * 8 + warp < count; ++t) {
         const int e = t * 8 + (lane >> 4) * 4 + warp;
-        gram_solve(P, fin, e < count ? sh.mine[e] : -1, lane);
+        gram_solve<FS>(P, fin, e < count ? sh.mine[e] : -1, lane);
     }
     __syncthreads();
 }
@@ -980,14 +981,17 @@ extern "C" int bmfr_debug_gram_cta(long long* out, int n) {
 #define GRAM_STAMP(k) do { } while (0)
 #endif
 
-template <bool STRIP>
+template <bool STRIP, int FS>
 __global__ void __launch_bounds__(QR_THREADS, BMFR_GRAM_MIN_BLOCKS) fit_gram_kernel(const __grid_constant__ KParams P,
                                                                                     const __grid_constant__ QrMaps M) {
     extern __shared__ __align__(128) unsigned char qr_smem[];
     GramShared& sh = *reinterpret_cast<GramShared*>(qr_smem);
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform (see fit_qr_kernel)
-    constexpr int NSC = BMFR_FEATURES_SCALED, NNS = BMFR_FEATURES_NOT_SCALED, ROWS = QR_ROWS, NCOL = BMFR_BUFFER_COUNT - 1;
+    using FL = FeatureSet<FS>;
+    constexpr int NF = FL::F, NSC = FL::NSC, NNS = NF - NSC, ROWS = QR_ROWS, NCOL = NF - 1 + 3;
+    constexpr int ENTRIES = NCOL + NCOL * (NCOL + 1) / 2;  // upper triangle of the Gram matrix without G_00 (= 1024): row 0 first, then rows 1..NCOL
+    static_assert(ENTRIES + NCOL <= QR_TRI_G && 2 * NSC + NCOL <= 24, "scratch row / per-warp partials");
     const int nblocks = P.blocks_x * (P.by1 - P.by0);
     const int stride = gridDim.x;
     if ((int)blockIdx.x >= nblocks) return;
@@ -1033,13 +1037,11 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_GRAM_MIN_BLOCKS) fit_gram_ker
                 float v[9];
 #pragma unroll
                 for (int c = 0; c < 9; ++c) {
+                    if (c < 3 && !FL::NORMALS) continue;  // this list does not read the normals
                     v[c] = sh.stage[c / 3][mirror_index(y_in + s, P.H) - oy][col + c % 3];
                     bad = bad || (v[c] != v[c]);
                 }
-                a[s][0] = v[0]; a[s][1] = v[1]; a[s][2] = v[2];
-                a[s][3] = v[3]; a[s][4] = v[4]; a[s][5] = v[5];
-                a[s][6] = v[3] * v[3]; a[s][7] = v[4] * v[4]; a[s][8] = v[5] * v[5];
-                a[s][9] = v[6]; a[s][10] = v[7]; a[s][11] = v[8];
+                feature_columns<FS>(a[s], v, v + 3, v + 6);
             }
             if (__any_sync(0xffffffffu, bad)) {
 #pragma unroll
@@ -1059,14 +1061,13 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_GRAM_MIN_BLOCKS) fit_gram_ker
                     continue;
                 }
                 const unsigned int lp = pix_index(P, x, y);
-                const f3 n = load_f3(P.cur_normals, lp);
+                const f3 n = FL::NORMALS ? load_f3(P.cur_normals, lp) : make_f3(0.f, 0.f, 0.f);
                 const f3 p = load_f3(P.cur_positions, lp);
                 const f3 col = load_f3(P.cur_noisy_acc, lp);
-                const float px = scrub_nan(p.x), py = scrub_nan(p.y), pz = scrub_nan(p.z);
-                a[s][0] = scrub_nan(n.x); a[s][1] = scrub_nan(n.y); a[s][2] = scrub_nan(n.z);
-                a[s][3] = px; a[s][4] = py; a[s][5] = pz;
-                a[s][6] = px * px; a[s][7] = py * py; a[s][8] = pz * pz;
-                a[s][9] = scrub_nan(col.x); a[s][10] = scrub_nan(col.y); a[s][11] = scrub_nan(col.z);
+                const float nv[3] = {scrub_nan(n.x), scrub_nan(n.y), scrub_nan(n.z)};
+                const float pv[3] = {scrub_nan(p.x), scrub_nan(p.y), scrub_nan(p.z)};
+                const float cv[3] = {scrub_nan(col.x), scrub_nan(col.y), scrub_nan(col.z)};
+                feature_columns<FS>(a[s], nv, pv, cv);
             }
         }
 
@@ -1138,7 +1139,7 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_GRAM_MIN_BLOCKS) fit_gram_ker
             float mv = 0.f;
 #pragma unroll
             for (int k = 0; k < NCOL; ++k) mv = (lane == k) ? mean[k] : mv;
-            if (lane < NCOL) P.tri[((size_t)local * QR_COMPUTE_WARPS) * QR_TRI_G + GR_ENTRIES + lane] = mv;
+            if (lane < NCOL) P.tri[((size_t)local * QR_COMPUTE_WARPS) * QR_TRI_G + ENTRIES + lane] = mv;
         }
 
         // scale (bmfr.cl:538-541), first-touch noise on columns 1..9 (bmfr.cl:623-627; from the tile's fp32 rounding as in
@@ -1155,9 +1156,9 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_GRAM_MIN_BLOCKS) fit_gram_ker
             for (int h = 0; h < ROWS / 2; ++h) a2[h][NNS - 1 + f] = fmul2(fsub2(a2[h][NNS - 1 + f], mn2), inv2);
         }
         {
-            const float4* nz4 = reinterpret_cast<const float4*>(P.noise_f) + (size_t)warp * (BMFR_FEATURES - 1) * 2 * 32 + lane;
+            const float4* nz4 = reinterpret_cast<const float4*>(P.noise_f) + (size_t)warp * (NF - 1) * 2 * 32 + lane;
 #pragma unroll
-            for (int c = 0; c < BMFR_FEATURES - 1; ++c) {
+            for (int c = 0; c < NF - 1; ++c) {
                 const float2 m2 = dup2(mean[c]);
 #pragma unroll
                 for (int q = 0; q < ROWS / 4; ++q) {
@@ -1167,7 +1168,7 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_GRAM_MIN_BLOCKS) fit_gram_ker
                 }
             }
 #pragma unroll
-            for (int c = BMFR_FEATURES - 1; c < NCOL; ++c) {
+            for (int c = NF - 1; c < NCOL; ++c) {
                 const float2 m2 = dup2(mean[c]);
 #pragma unroll
                 for (int h = 0; h < ROWS / 2; ++h) a2[h][c] = fsub2(a2[h][c], m2);
@@ -1202,17 +1203,17 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_GRAM_MIN_BLOCKS) fit_gram_ker
                 if (++e % GR_CHUNK == 0) flush(e / GR_CHUNK - 1, GR_CHUNK);
             }
         }
-        if (GR_ENTRIES % GR_CHUNK != 0) flush(GR_ENTRIES / GR_CHUNK, GR_ENTRIES % GR_CHUNK);
+        if (ENTRIES % GR_CHUNK != 0) flush(ENTRIES / GR_CHUNK, ENTRIES % GR_CHUNK);
 
         if (++mine == QR_MINE) {
-            gram_solve_mine(P, sh, mine, warp, lane);
+            gram_solve_mine<FS>(P, sh, mine, warp, lane);
             mine = 0;
         }
         if (tid == 0 && late_draw) qr_draw_next(P, M, sh, it, nblocks, stride);
         if (it < 6) GRAM_STAMP(3 + 2 * it);
     }
     GRAM_STAMP(14);
-    gram_solve_mine(P, sh, mine, warp, lane);
+    gram_solve_mine<FS>(P, sh, mine, warp, lane);
     GRAM_STAMP(15);
     stamp_end(P, 1);
 }
@@ -1275,26 +1276,39 @@ static cudaError_t fit_grid(K0 k_plain, K1 k_strip, int smem, int max_per_sm, in
     return cudaSuccess;
 }
 
-cudaError_t launch_fit_qr(const KParams& P, cudaStream_t st) {
-    static int counts_qr[64] = {}, counts_gram[64] = {};  // resident CTAs per device; 0 = not configured yet
-    const bool gram = P.fit_method == BMFR_FIT_GRAM;
-    const int smem = gram ? (int)sizeof(GramShared) : (int)sizeof(QrShared);
+template <int FS>
+static cudaError_t launch_fit_gram(const KParams& P, const QrMaps& M, int nblocks, cudaStream_t st) {
+    static int counts[64] = {};  // resident CTAs per device; 0 = not configured yet
+    const int smem = (int)sizeof(GramShared);
     int grid = 0;
-    cudaError_t e = gram ? fit_grid(fit_gram_kernel<false>, fit_gram_kernel<true>, smem, BMFR_GRAM_MIN_BLOCKS, counts_gram, &grid)
-                         : fit_grid(fit_qr_kernel<false>, fit_qr_kernel<true>, smem, BMFR_QR_MIN_BLOCKS, counts_qr, &grid);
+    cudaError_t e = fit_grid(fit_gram_kernel<false, FS>, fit_gram_kernel<true, FS>, smem, BMFR_GRAM_MIN_BLOCKS, counts, &grid);
     if (e != cudaSuccess) return e;
-    const int nblocks = P.blocks_x * (P.by1 - P.by0);
     if (grid > nblocks) grid = nblocks;
-    if (grid < 1) return cudaSuccess;
+    if (is_strip(P)) return launch_pdl(!P.plain_launch, fit_gram_kernel<true, FS>, dim3(grid), dim3(QR_THREADS), (size_t)smem, st, P, M);
+    return launch_pdl(!P.plain_launch, fit_gram_kernel<false, FS>, dim3(grid), dim3(QR_THREADS), (size_t)smem, st, P, M);
+}
+
+cudaError_t launch_fit_qr(const KParams& P, cudaStream_t st) {
+    const int nblocks = P.blocks_x * (P.by1 - P.by0);
+    if (nblocks < 1) return cudaSuccess;
     QrMaps M;
     memset(&M, 0, sizeof(M));
     const int rows = P.row1 - P.row0;
     M.use_tma = tile_map(P.cur_normals, P.W, rows, &M.normals) && tile_map(P.cur_positions, P.W, rows, &M.positions) &&
                 tile_map(P.cur_noisy_acc, P.W, rows, &M.colour);
-    if (gram) {
-        if (is_strip(P)) return launch_pdl(!P.plain_launch, fit_gram_kernel<true>, dim3(grid), dim3(QR_THREADS), (size_t)smem, st, P, M);
-        return launch_pdl(!P.plain_launch, fit_gram_kernel<false>, dim3(grid), dim3(QR_THREADS), (size_t)smem, st, P, M);
+    if (P.fit_method == BMFR_FIT_GRAM) {
+        switch (P.feature_set) {
+            case BMFR_FEATURE_SET_LINEAR: return launch_fit_gram<BMFR_FEATURE_SET_LINEAR>(P, M, nblocks, st);
+            case BMFR_FEATURE_SET_POSITION: return launch_fit_gram<BMFR_FEATURE_SET_POSITION>(P, M, nblocks, st);
+            default: return launch_fit_gram<BMFR_FEATURE_SET_DEFAULT>(P, M, nblocks, st);
+        }
     }
+    static int counts_qr[64] = {};
+    const int smem = (int)sizeof(QrShared);
+    int grid = 0;
+    cudaError_t e = fit_grid(fit_qr_kernel<false>, fit_qr_kernel<true>, smem, BMFR_QR_MIN_BLOCKS, counts_qr, &grid);
+    if (e != cudaSuccess) return e;
+    if (grid > nblocks) grid = nblocks;
     if (is_strip(P)) return launch_pdl(!P.plain_launch, fit_qr_kernel<true>, dim3(grid), dim3(QR_THREADS), (size_t)smem, st, P, M);
     return launch_pdl(!P.plain_launch, fit_qr_kernel<false>, dim3(grid), dim3(QR_THREADS), (size_t)smem, st, P, M);
 }

@@ -89,6 +89,9 @@ struct KParams {
     unsigned long long* stamps;
     unsigned long long* stamps_next;
     HaloK halo_r, halo_p;         // halo exchange duties of the reprojection / the post pass (FUSED strips)
+    int feature_set;              // bmfr_feature_set: which instantiation of the FUSED fit / post pass runs
+    int n_features;               // its feature count F (the noise tile has F - 1 columns, BUFFER_COUNT = F + 3)
+    int n_scaled;                 // its scaled features
     int fit_method;               // host side only: BMFR_FIT_GRAM / BMFR_FIT_TSQR (which FUSED fit kernel launch_fit_qr starts)
     int plain_launch;             // host side only: launch the FUSED kernels without programmatic stream serialization
 };

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define BMFR_B200_ABI_VERSION 4
+#define BMFR_B200_ABI_VERSION 5
 
 /* Compile-time constants of the reference that are not tunable (bmfr.cpp:102-118). */
 #define BMFR_BLOCK_EDGE 32          /* BLOCK_EDGE_LENGTH, bmfr.cpp:104 */
@@ -103,9 +103,26 @@ typedef struct bmfr_params {
     /* Strip contexts with a connected neighbour: how long a kernel waits on the device for the neighbour's halo rows
      * before it gives up (the context then fails: every later call returns BMFR_ERR_SEQUENCE).  0 = 10000 ms. */
     int halo_timeout_ms;
+    /* bmfr_feature_set.  Lists other than the default need mode = FUSED and fit_method = BMFR_FIT_GRAM. */
+    int feature_set;
 } bmfr_params;
 
 enum { BMFR_FIT_GRAM = 0, BMFR_FIT_TSQR = 1 };
+
+/* Feature lists.  In the reference the list is a compile-time string (NOT_SCALED_FEATURE_BUFFERS / SCALED_FEATURE_BUFFERS,
+ * bmfr.cpp:63-77; "if you want to use other than normal and world_position data you have to make it available in the
+ * first accumulation kernel and in the weighted sum kernel", :63-64); here the FUSED kernels are instantiated for these
+ * lists over the same two inputs and bmfr_params.feature_set picks one at run time.  BMFR_FEATURES / _SCALED /
+ * BMFR_BUFFER_COUNT above are the sizes of the default list and the maxima. */
+typedef enum bmfr_feature_set {
+    BMFR_FEATURE_SET_DEFAULT = 0,  /* 1, normal.xyz | world_position.xyz, world_position.xyz^2  (10 features, 6 scaled: bmfr.cpp:65-77) */
+    BMFR_FEATURE_SET_LINEAR = 1,   /* 1, normal.xyz | world_position.xyz                         ( 7 features, 3 scaled) */
+    BMFR_FEATURE_SET_POSITION = 2, /* 1             | world_position.xyz, world_position.xyz^2  ( 7 features, 6 scaled) */
+    BMFR_FEATURE_SET_COUNT_ = 3
+} bmfr_feature_set;
+/* Feature count and scaled-feature count of a list (what FEATURES_NOT_SCALED + FEATURES_SCALED / FEATURES_SCALED are in
+ * bmfr.cpp:195-199); sizes of BMFR_BUF_WEIGHTS (NB*F*3), BMFR_BUF_MINS_MAXS (NB*S*2), BMFR_BUF_NOISE_TILE ((F-1)*1024). */
+int bmfr_feature_counts(int feature_set, int* features, int* scaled);
 
 typedef struct bmfr_ctx bmfr_ctx;
 

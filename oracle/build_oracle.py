@@ -26,6 +26,30 @@ REF_LIB = REF_DIR / "libbmfr_clref.so"
 
 CFLAGS = ["-O2", "-ffp-contract=off", "-fno-fast-math", "-fopenmp", "-fPIC", "-shared"]
 
+# Feature lists (include/bmfr_b200.h, bmfr_feature_set).  Set 0 is read from bmfr.cpp itself; the others are what a user
+# of the reference would write into NOT_SCALED_FEATURE_BUFFERS / SCALED_FEATURE_BUFFERS (bmfr.cpp:63-77).
+FEATURE_SETS = {
+    1: ("1.f,normal.x,normal.y,normal.z,", "world_position.x,world_position.y,world_position.z"),
+    2: ("1.f,", "world_position.x,world_position.y,world_position.z,world_position.x*world_position.x,"
+                "world_position.y*world_position.y,world_position.z*world_position.z"),
+}
+
+
+def _suffix(feature_set: int) -> str:
+    return "" if feature_set == 0 else f"_fs{feature_set}"
+
+
+def port_lib(feature_set=0) -> Path:
+    return HERE / f"libbmfr_oracle{_suffix(feature_set)}.so"
+
+
+def ref_lib(feature_set=0) -> Path:
+    return REF_DIR / f"libbmfr_clref{_suffix(feature_set)}.so"
+
+
+def clgpu_lib(feature_set=0) -> Path:
+    return REF_DIR / f"libbmfr_clgpu{_suffix(feature_set)}.so"
+
 # OpenCL C constructs that C++ cannot express through the shim header alone.  Each rewrite is purely
 # syntactic, must match exactly `count` times, and is listed in DESIGN.md.
 REWRITES = [
@@ -45,27 +69,31 @@ def _stamp(paths, extra=""):
     return h.hexdigest()
 
 
-def build_port(force=False) -> Path:
+def build_port(force=False, feature_set=0) -> Path:
     src = [HERE / "bmfr_oracle.c", HERE / "bmfr_oracle.h"]
-    stamp = HERE / "_build" / "port.sha256"
-    digest = _stamp(src, " ".join(CFLAGS))
-    if not force and PORT_LIB.exists() and stamp.exists() and stamp.read_text() == digest:
-        return PORT_LIB
+    lib = port_lib(feature_set)
+    stamp = HERE / "_build" / f"port{_suffix(feature_set)}.sha256"
+    digest = _stamp(src, " ".join(CFLAGS) + str(feature_set))
+    if not force and lib.exists() and stamp.exists() and stamp.read_text() == digest:
+        return lib
     stamp.parent.mkdir(exist_ok=True)
-    cmd = ["gcc", "-std=gnu11", *CFLAGS, "-o", str(PORT_LIB), str(src[0]), "-lm"]
+    cmd = ["gcc", "-std=gnu11", *CFLAGS, f"-DBMFR_FEATURE_SET={feature_set}", "-o", str(lib), str(src[0]), "-lm"]
     subprocess.run(cmd, check=True)
     stamp.write_text(digest)
-    return PORT_LIB
+    return lib
 
 
-def _defines_from_bmfr_cpp(text: str) -> str:
-    """The -D options bmfr.cpp:205-232 derives from its own #defines (bmfr.cpp:56-118)."""
+def _defines_from_bmfr_cpp(text: str, feature_set=0) -> str:
+    """The -D options bmfr.cpp:205-232 derives from its own #defines (bmfr.cpp:56-118); feature_set != 0 replaces the two
+    feature strings the way an edit of bmfr.cpp:65-77 would."""
     def strings_of(name):
         m = re.search(r"#define %s \\\n((?:\".*\"\\?\n)+)" % name, text)
         if not m:
             raise RuntimeError(f"{name} not found in bmfr.cpp")
         return "".join(re.findall(r"\"(.*?)\"", m.group(1)))
     not_scaled, scaled = strings_of("NOT_SCALED_FEATURE_BUFFERS"), strings_of("SCALED_FEATURE_BUFFERS")
+    if feature_set != 0:
+        not_scaled, scaled = FEATURE_SETS[feature_set]
     n_ns = not_scaled.count(",")          # bmfr.cpp:195-196
     n_s = scaled.count(",") + 1           # bmfr.cpp:198-199
     buffers = n_ns + n_s + 3              # bmfr.cpp:202
@@ -87,17 +115,17 @@ def _defines_from_bmfr_cpp(text: str) -> str:
     return "\n".join(out) + "\n"
 
 
-def build_reference(force=False):
+def build_reference(force=False, feature_set=0):
     """Returns the path of the reference-kernel library, or None when it cannot be (re)built."""
-    cl, cpp = REFERENCE / "bmfr.cl", REFERENCE / "bmfr.cpp"
+    REF_LIB, cl, cpp = ref_lib(feature_set), REFERENCE / "bmfr.cl", REFERENCE / "bmfr.cpp"
     shim = [HERE / "cl_shim" / "cl_shim.hpp", HERE / "cl_shim" / "cl_host.cpp", HERE / "bmfr_oracle.h"]
     if not cl.exists() or not cpp.exists():
         return REF_LIB if REF_LIB.exists() else None   # GPU box: use what travelled
-    digest = _stamp([cl, cpp, *shim, Path(__file__)], " ".join(CFLAGS))
-    stamp = REF_DIR / "ref.sha256"
+    digest = _stamp([cl, cpp, *shim, Path(__file__)], " ".join(CFLAGS) + str(feature_set))
+    stamp = REF_DIR / f"ref{_suffix(feature_set)}.sha256"
     if not force and REF_LIB.exists() and stamp.exists() and stamp.read_text() == digest:
         return REF_LIB
-    work = REF_DIR / "gen"
+    work = REF_DIR / f"gen{_suffix(feature_set)}"
     work.mkdir(parents=True, exist_ok=True)
     try:
         src = cl.read_text()
@@ -106,7 +134,7 @@ def build_reference(force=False):
                 raise RuntimeError(f"rewrite {old!r}: expected {count} match(es), found {src.count(old)}")
             src = src.replace(old, new)
         (work / "bmfr_cl.gen.inc").write_text(src)
-        (work / "bmfr_defines.gen.h").write_text(_defines_from_bmfr_cpp(cpp.read_text()))
+        (work / "bmfr_defines.gen.h").write_text(_defines_from_bmfr_cpp(cpp.read_text(), feature_set))
         cmd = ["g++", "-std=gnu++17", *CFLAGS, "-Wno-narrowing", "-Wno-attributes", "-I", str(work),
                "-o", str(REF_LIB), str(HERE / "cl_shim" / "cl_host.cpp"), "-lm"]
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -122,10 +150,10 @@ def build_reference(force=False):
 CLGPU_LIB = REF_DIR / "libbmfr_clgpu.so"
 
 
-def _opencl_header(cl_text: bytes, cpp_text: str) -> str:
+def _opencl_header(cl_text: bytes, cpp_text: str, feature_set=0) -> str:
     """bmfr.cl as a byte array + the feature-list build options of bmfr.cpp:63-77,195-202 — the unmodified
     kernel source is what the OpenCL driver on the GPU box compiles."""
-    defs = dict(re.findall(r"^#define (\w+) (.*)$", _defines_from_bmfr_cpp(cpp_text), re.M))
+    defs = dict(re.findall(r"^#define (\w+) (.*)$", _defines_from_bmfr_cpp(cpp_text, feature_set), re.M))
     out = ["// generated from /root/reference/opencl/{bmfr.cl,bmfr.cpp} by oracle/build_oracle.py — do not commit",
            f"#define BMFR_CL_FEATURE_OPTIONS \"{defs['FEATURE_BUFFERS']}\""]
     for name in ("BUFFER_COUNT", "FEATURES_NOT_SCALED", "FEATURES_SCALED", "LOCAL_WIDTH", "LOCAL_HEIGHT", "LOCAL_SIZE",
@@ -139,21 +167,21 @@ def _opencl_header(cl_text: bytes, cpp_text: str) -> str:
     return "\n".join(out) + "\n"
 
 
-def build_opencl_host(force=False):
+def build_opencl_host(force=False, feature_set=0):
     """oracle/_ref/libbmfr_clgpu.so: the reference's unmodified bmfr.cl + a host that drives it through the box's
     OpenCL ICD (oracle/cl_gpu/cl_gpu_host.c).  Needs no OpenCL at build time (the API is resolved with dlopen)."""
-    cl, cpp = REFERENCE / "bmfr.cl", REFERENCE / "bmfr.cpp"
+    CLGPU_LIB, cl, cpp = clgpu_lib(feature_set), REFERENCE / "bmfr.cl", REFERENCE / "bmfr.cpp"
     host = HERE / "cl_gpu" / "cl_gpu_host.c"
     if not cl.exists() or not cpp.exists():
         return CLGPU_LIB if CLGPU_LIB.exists() else None   # GPU box: use what travelled
-    digest = _stamp([cl, cpp, host, HERE / "bmfr_oracle.h", Path(__file__)])
-    stamp = REF_DIR / "clgpu.sha256"
+    digest = _stamp([cl, cpp, host, HERE / "bmfr_oracle.h", Path(__file__)], str(feature_set))
+    stamp = REF_DIR / f"clgpu{_suffix(feature_set)}.sha256"
     if not force and CLGPU_LIB.exists() and stamp.exists() and stamp.read_text() == digest:
         return CLGPU_LIB
-    work = REF_DIR / "gen_clgpu"
+    work = REF_DIR / f"gen_clgpu{_suffix(feature_set)}"
     work.mkdir(parents=True, exist_ok=True)
     try:
-        (work / "bmfr_cl_source.gen.h").write_text(_opencl_header(cl.read_bytes(), cpp.read_text()))
+        (work / "bmfr_cl_source.gen.h").write_text(_opencl_header(cl.read_bytes(), cpp.read_text(), feature_set))
         cmd = ["gcc", "-std=gnu11", "-O2", "-fPIC", "-shared", "-Wall", "-I", str(work), "-o", str(CLGPU_LIB), str(host), "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
@@ -165,8 +193,13 @@ def build_opencl_host(force=False):
     return CLGPU_LIB
 
 
+def build_all(force=False):
+    out = []
+    for fs in (0, *FEATURE_SETS):
+        out.append((fs, build_port(force, fs), build_reference(force, fs), build_opencl_host(force, fs)))
+    return out
+
+
 if __name__ == "__main__":
-    force = "--force" in sys.argv
-    print("port     :", build_port(force))
-    print("reference:", build_reference(force))
-    print("opencl   :", build_opencl_host(force))
+    for fs, port, ref, clgpu in build_all("--force" in sys.argv):
+        print(f"feature set {fs}: port {port}, reference {ref}, opencl {clgpu}")

@@ -410,7 +410,7 @@ const void* oracle_buffer(oracle_state* s, int id, size_t* bytes) {
         case ORACLE_BUF_PREV_PIXELS: m = s->prev_pixels; n = npix * 8; break;
         case ORACLE_BUF_ACCEPT: m = s->accept; n = npix; break;
         case ORACLE_BUF_WEIGHTS: m = s->weights; n = (size_t)s->NB * (BMFR_CL_BUFFER_COUNT - 3) * 3 * 4; break;
-        case ORACLE_BUF_MINS_MAXS: m = s->mins_maxs; n = (size_t)s->NB * 6 * 8; break;
+        case ORACLE_BUF_MINS_MAXS: m = s->mins_maxs; n = (size_t)s->NB * BMFR_CL_FEATURES_SCALED * 8; break;
         case ORACLE_BUF_FILTERED: m = s->filtered; n = npix * 12; break;
         case ORACLE_BUF_ACCUM: m = db_prev(&s->out); n = npix * 12; break;
         case ORACLE_BUF_TONE_MAPPED: m = s->tone_mapped; n = npix * 12; break;

@@ -28,20 +28,25 @@ class OracleParams(C.Structure):
                 ("keep_tmp", C.c_int), ("k1_schedule", C.c_int), ("threads", C.c_int)]
 
 
-def lib_path(kind: str) -> Path:
-    return {"port": HERE / "libbmfr_oracle.so", "reference": HERE / "_ref" / "libbmfr_clref.so",
-            "opencl": HERE / "_ref" / "libbmfr_clgpu.so"}[kind]
+# feature lists the checkers are built for (include/bmfr_b200.h, bmfr_feature_set): (features, scaled features)
+FEATURE_SETS = {0: (10, 6), 1: (7, 3), 2: (7, 6)}
 
 
-def available(kind: str) -> bool:
-    return lib_path(kind).exists()
+def lib_path(kind: str, feature_set: int = 0) -> Path:
+    sfx = "" if feature_set == 0 else f"_fs{feature_set}"
+    return {"port": HERE / f"libbmfr_oracle{sfx}.so", "reference": HERE / "_ref" / f"libbmfr_clref{sfx}.so",
+            "opencl": HERE / "_ref" / f"libbmfr_clgpu{sfx}.so"}[kind]
 
 
-def _load(kind: str):
-    path = lib_path(kind)
+def available(kind: str, feature_set: int = 0) -> bool:
+    return lib_path(kind, feature_set).exists()
+
+
+def _load(kind: str, feature_set: int = 0):
+    path = lib_path(kind, feature_set)
     if not path.exists():
         from . import build_oracle
-        dict(port=build_oracle.build_port, reference=build_oracle.build_reference, opencl=build_oracle.build_opencl_host)[kind]()
+        dict(port=build_oracle.build_port, reference=build_oracle.build_reference, opencl=build_oracle.build_opencl_host)[kind](False, feature_set)
     if not path.exists():
         raise FileNotFoundError(f"{path} is missing (kind={kind})")
     lib = C.CDLL(str(path))
@@ -77,10 +82,11 @@ class Oracle:
 
     def __init__(self, kind, width, height, *, noise_amount=1e-2, blend_alpha=0.2, second_blend_alpha=0.1,
                  taa_blend_alpha=0.2, position_limit_squared, normal_limit_squared, tmp_half=0, keep_tmp=0,
-                 k1_schedule=0, threads=0):
-        if kind not in _LIBS:
-            _LIBS[kind] = _load(kind)
-        self.lib, self.kind, self.W, self.H = _LIBS[kind], kind, width, height
+                 k1_schedule=0, threads=0, feature_set=0):
+        if (kind, feature_set) not in _LIBS:
+            _LIBS[(kind, feature_set)] = _load(kind, feature_set)
+        self.lib, self.kind, self.W, self.H = _LIBS[(kind, feature_set)], kind, width, height
+        self.features, self.features_scaled = FEATURE_SETS[feature_set]
         self.params = OracleParams(width, height, noise_amount, blend_alpha, second_blend_alpha, taa_blend_alpha,
                                    position_limit_squared, normal_limit_squared, tmp_half, keep_tmp, k1_schedule,
                                    threads)
@@ -116,13 +122,13 @@ class Oracle:
         elif name in ("spp", "accept"):
             a = a.reshape(self.H, self.W)
         elif name == "weights":
-            a = a.reshape(-1, 10, 3)
+            a = a.reshape(-1, self.features, 3)
         elif name == "mins_maxs":
-            a = a.reshape(-1, 6, 2)
+            a = a.reshape(-1, self.features_scaled, 2)
         elif name == "tmp_data":
-            a = a.reshape(-1, 13, 32, 32)
+            a = a.reshape(-1, self.features + 3, 32, 32)
         elif name == "noise_tile":
-            a = a.reshape(9, 1024)
+            a = a.reshape(self.features - 1, 1024)
         return a
 
     @property
@@ -136,6 +142,6 @@ class Oracle:
 
 
 def random_hash(kind, a: int) -> float:
-    if kind not in _LIBS:
-        _LIBS[kind] = _load(kind)
-    return float(_LIBS[kind].oracle_random(C.c_uint(a & 0xFFFFFFFF)))
+    if (kind, 0) not in _LIBS:
+        _LIBS[(kind, 0)] = _load(kind)
+    return float(_LIBS[(kind, 0)].oracle_random(C.c_uint(a & 0xFFFFFFFF)))
