@@ -34,7 +34,7 @@ class Params(C.Structure):
                 ("normal_limit_squared", C.c_float), ("tmp_half", C.c_int), ("profile", C.c_int),
                 ("strip_y0", C.c_int), ("strip_y1", C.c_int), ("halo_rows", C.c_int), ("stream", C.c_void_p),
                 ("reference_order", C.c_int), ("overlap_frames", C.c_int), ("fit_method", C.c_int),
-                ("halo_timeout_ms", C.c_int)]
+                ("halo_timeout_ms", C.c_int), ("feature_set", C.c_int)]
 
 
 class Geometry(C.Structure):
@@ -53,6 +53,7 @@ SYMBOLS = {
     "bmfr_last_error": (C.c_char_p, []),
     "bmfr_abi_version": (_I, []),
     "bmfr_default_params": (None, [C.POINTER(Params), _I, _I]),
+    "bmfr_feature_counts": (_I, [_I, C.POINTER(_I), C.POINTER(_I)]),
     "bmfr_block_offset": (None, [_I, C.POINTER(_I), C.POINTER(_I)]),
     "bmfr_create": (_I, [C.POINTER(Params), C.POINTER(_P)]),
     "bmfr_destroy": (None, [_P]),

@@ -234,6 +234,15 @@ void bmfr_default_params(bmfr_params* p, int width, int height) {
     p->profile = 0;
 }
 
+int bmfr_feature_counts(int feature_set, int* features, int* scaled) {
+    static const int kF[BMFR_FEATURE_SET_COUNT_] = {10, 7, 7}, kS[BMFR_FEATURE_SET_COUNT_] = {6, 3, 6};
+    if (feature_set < 0 || feature_set >= BMFR_FEATURE_SET_COUNT_)
+        return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_feature_counts: unknown feature set %d", feature_set);
+    if (features) *features = kF[feature_set];
+    if (scaled) *scaled = kS[feature_set];
+    return BMFR_OK;
+}
+
 void bmfr_block_offset(int frame, int* off_x, int* off_y) {
     int x, y;
     bmfr_host_block_offset(frame, &x, &y);
@@ -266,6 +275,11 @@ int bmfr_create(const bmfr_params* params, bmfr_ctx** out_ctx) {
     if (p.fit_method != BMFR_FIT_GRAM && p.fit_method != BMFR_FIT_TSQR)
         return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_create: unknown fit_method %d", p.fit_method);
     if (p.halo_timeout_ms < 0) return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_create: negative halo_timeout_ms");
+    if (p.feature_set < 0 || p.feature_set >= BMFR_FEATURE_SET_COUNT_)
+        return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_create: unknown feature_set %d", p.feature_set);
+    if (p.feature_set != BMFR_FEATURE_SET_DEFAULT && (p.mode != BMFR_MODE_FUSED || p.fit_method != BMFR_FIT_GRAM))
+        return bmfr_set_error(BMFR_ERR_UNSUPPORTED, "bmfr_create: feature lists other than the reference's shipped one are instantiated "
+                                                    "for the FUSED kernels with fit_method = BMFR_FIT_GRAM only");
     if ((p.tmp_half != 0 || p.reference_order != 0) && p.mode != BMFR_MODE_STAGED)
         return bmfr_set_error(BMFR_ERR_UNSUPPORTED,
                               "bmfr_create: tmp_half / reference_order are the STAGED compatibility path (the FUSED fit is fp32 and "
@@ -529,6 +543,8 @@ static void fill_params(bmfr_ctx* c, KParams& P, int frame, const float* d_albed
     P.user_out = d_out; P.oob_flag = c->d_oob; P.block_counter = odd ? c->ov.counter : c->d_oob + 1;
     P.plain_launch = c->ov.on ? 1 : 0;
     P.fit_method = c->prm.fit_method;
+    P.feature_set = c->prm.feature_set;
+    bmfr_feature_counts(c->prm.feature_set, &P.n_features, &P.n_scaled);
     P.tri = c->tri;
     if (c->d_stamps) {  // this frame's slot was armed by the previous frame's reprojection (the first one at create)
         const size_t slot = (size_t)c->seq % kProfileSlots, next = (size_t)(c->seq + 1) % kProfileSlots;
@@ -816,6 +832,8 @@ int bmfr_get_buffer(bmfr_ctx* c, int buffer, void** d_ptr, size_t* bytes) {
     if (!c || !d_ptr || !bytes) return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_get_buffer: null argument");
     const size_t npix = rows_of(c) * (size_t)c->geo.width;
     const size_t nb = (size_t)c->geo.blocks_x * c->geo.blocks_y;
+    int nf = BMFR_FEATURES, ns = BMFR_FEATURES_SCALED;
+    bmfr_feature_counts(c->prm.feature_set, &nf, &ns);
     void* p = nullptr;
     size_t n = 0;
     const bool last_odd = c->last_parity() == 1;  // overlapped frames: which copy the last frame wrote
@@ -826,13 +844,13 @@ int bmfr_get_buffer(bmfr_ctx* c, int buffer, void** d_ptr, size_t* bytes) {
         case BMFR_BUF_PREV_PIXELS: p = last_odd ? c->ov.prev_pixels : c->prev_pixels; n = npix * 8; break;
         case BMFR_BUF_ACCEPT: p = last_odd ? c->ov.accept : c->accept; n = npix; break;
         case BMFR_BUF_TMP_DATA: p = c->tmp_data; n = (size_t)c->tmp_block_rows * c->geo.blocks_x * BMFR_BUFFER_COUNT * BMFR_BLOCK_PIXELS * 4; break;
-        case BMFR_BUF_WEIGHTS: p = last_odd ? c->ov.weights : c->weights; n = nb * BMFR_FEATURES * 3 * 4; break;
-        case BMFR_BUF_MINS_MAXS: p = last_odd ? c->ov.mins_maxs : c->mins_maxs; n = nb * BMFR_FEATURES_SCALED * 2 * 4; break;
+        case BMFR_BUF_WEIGHTS: p = last_odd ? c->ov.weights : c->weights; n = nb * nf * 3 * 4; break;
+        case BMFR_BUF_MINS_MAXS: p = last_odd ? c->ov.mins_maxs : c->mins_maxs; n = nb * ns * 2 * 4; break;
         case BMFR_BUF_FILTERED: p = c->filtered; n = npix * 12; break;
         case BMFR_BUF_ACCUM: p = c->accum.previous(); n = npix * 12; break;
         case BMFR_BUF_TONE_MAPPED: p = c->tone_mapped; n = npix * 12; break;
         case BMFR_BUF_RESULT: p = c->result.previous(); n = npix * 12; break;
-        case BMFR_BUF_NOISE_TILE: p = last_odd ? c->ov.noise : c->noise; n = (size_t)(BMFR_FEATURES - 1) * BMFR_BLOCK_PIXELS * 8; break;
+        case BMFR_BUF_NOISE_TILE: p = last_odd ? c->ov.noise : c->noise; n = (size_t)(nf - 1) * BMFR_BLOCK_PIXELS * 8; break;
         default: return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_get_buffer: unknown buffer %d", buffer);
     }
     if (!p)

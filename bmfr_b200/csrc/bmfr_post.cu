@@ -26,7 +26,7 @@
 #define PT_TILE 32
 #define PT_HALO (PT_TILE + 2)
 #define PT_STRIDE 36   // floats per shared-memory row (>= 34)
-#define PT_COEF 52     // per block: 10 x (w_r, w_g, w_b, -) then 6 x (min, 1/range)
+#define PT_COEF 52     // per block: F x (w_r, w_g, w_b, -) then NSC x (min, 1/range); 10 and 6 for the largest list
 
 struct PostShared {
     float ycc[3][PT_HALO][PT_STRIDE];
@@ -76,75 +76,93 @@ __device__ __forceinline__ float tone_map_fast(float v) {  // clamp(powr(max(0,v
     return __saturatef(e);
 }
 
-// weighted_sum for one pixel, bmfr.cl:725-750.  cf: the block's coefficients in shared memory; every
-// lane of a tile-interior warp reads the same address (broadcast), so the 42 coefficients cost 13
-// 128-bit shared loads per pixel instead of 42 registers for the whole kernel.
+// The block's coefficients in shared memory (PostShared::coef / PostStage::coef), for a list of F features of which the
+// last NSC are scaled: F x (w_r, w_g, w_b, -), then NSC x (min, 1/range) — read as 128-bit broadcasts (every lane of a
+// tile-interior warp reads the same address).
+template <int FS>
+struct PostCoef {
+    static constexpr int F = FeatureSet<FS>::F, NSC = FeatureSet<FS>::NSC, NW = 3 * F, NM = 2 * NSC, MINV = 4 * F;
+    float4 m[(NSC + 1) / 2];  // (min, 1/range) pairs, two per float4
+    __device__ __forceinline__ void load(const float* __restrict__ cf) {
+        const float4* c4 = reinterpret_cast<const float4*>(cf);
+#pragma unroll
+        for (int j = 0; j < (NSC + 1) / 2; ++j) m[j] = c4[F + j];
+    }
+    __device__ __forceinline__ float mn(int k) const { return (k & 1) ? m[k >> 1].z : m[k >> 1].x; }
+    __device__ __forceinline__ float inv(int k) const { return (k & 1) ? m[k >> 1].w : m[k >> 1].y; }
+    // the F - 1 non-constant features of a pixel (bmfr.cl:724-741): clean, no noise, no NaN scrub
+    __device__ __forceinline__ void features(f3 n, f3 p, float (&feat)[F - 1]) const {
+        int at = 0;
+        if (FeatureSet<FS>::NORMALS) { feat[0] = n.x; feat[1] = n.y; feat[2] = n.z; at = 3; }
+        const float raw[6] = {p.x, p.y, p.z, p.x * p.x, p.y * p.y, p.z * p.z};
+#pragma unroll
+        for (int k = 0; k < NSC; ++k) feat[at + k] = (raw[k] - mn(k)) * inv(k);
+    }
+};
+__device__ __forceinline__ f3 clamp_negative(f3 c) {  // keeps NaN like the reference, bmfr.cl:750
+    return make_f3(c.x < 0.f ? 0.f : c.x, c.y < 0.f ? 0.f : c.y, c.z < 0.f ? 0.f : c.z);
+}
+
+// weighted_sum for one pixel, bmfr.cl:725-750.
+template <int FS>
 __device__ __forceinline__ f3 weighted_sum_px(f3 n, f3 p, const float* __restrict__ cf) {
+    constexpr int F = FeatureSet<FS>::F;
     const float4* c4 = reinterpret_cast<const float4*>(cf);
-    const float4 m0 = c4[10], m1 = c4[11], m2 = c4[12];  // (min, 1/range) of p.x p.y | p.z p.x^2 | p.y^2 p.z^2
-    const float feat[BMFR_FEATURES - 1] = {n.x,
-                                           n.y,
-                                           n.z,
-                                           (p.x - m0.x) * m0.y,
-                                           (p.y - m0.z) * m0.w,
-                                           (p.z - m1.x) * m1.y,
-                                           (p.x * p.x - m1.z) * m1.w,
-                                           (p.y * p.y - m2.x) * m2.y,
-                                           (p.z * p.z - m2.z) * m2.w};
+    PostCoef<FS> pc;
+    pc.load(cf);
+    float feat[F - 1];
+    pc.features(n, p, feat);
     const float4 w0 = c4[0];
     f3 c = make_f3(w0.x, w0.y, w0.z);
 #pragma unroll
-    for (int f = 1; f < BMFR_FEATURES; ++f) {
+    for (int f = 1; f < F; ++f) {
         const float4 w = c4[f];
         c.x = fmaf(w.x, feat[f - 1], c.x);
         c.y = fmaf(w.y, feat[f - 1], c.y);
         c.z = fmaf(w.z, feat[f - 1], c.z);
     }
-    c.x = c.x < 0.f ? 0.f : c.x;  // keeps NaN like the reference, bmfr.cl:750
-    c.y = c.y < 0.f ? 0.f : c.y;
-    c.z = c.z < 0.f ? 0.f : c.z;
-    return c;
+    return clamp_negative(c);
 }
 
-// accumulate_filtered_data for one pixel, bmfr.cl:778-856.  Returns the tone-mapped colour.
 // The same for two pixels of a strip: every coefficient is fetched once and used twice, which halves
 // the shared-memory wavefronts of the weighted sum (a warp-wide 128-bit broadcast is four wavefronts).
+template <int FS>
 __device__ __forceinline__ void weighted_sum_px2(f3 n0, f3 p0, f3 n1, f3 p1, const float* __restrict__ cf, f3& out0, f3& out1) {
+    constexpr int F = FeatureSet<FS>::F;
     const float4* c4 = reinterpret_cast<const float4*>(cf);
-    const float4 m0 = c4[10], m1 = c4[11], m2 = c4[12];
-    const float f0[BMFR_FEATURES - 1] = {n0.x, n0.y, n0.z, (p0.x - m0.x) * m0.y, (p0.y - m0.z) * m0.w, (p0.z - m1.x) * m1.y,
-                                         (p0.x * p0.x - m1.z) * m1.w, (p0.y * p0.y - m2.x) * m2.y, (p0.z * p0.z - m2.z) * m2.w};
-    const float f1[BMFR_FEATURES - 1] = {n1.x, n1.y, n1.z, (p1.x - m0.x) * m0.y, (p1.y - m0.z) * m0.w, (p1.z - m1.x) * m1.y,
-                                         (p1.x * p1.x - m1.z) * m1.w, (p1.y * p1.y - m2.x) * m2.y, (p1.z * p1.z - m2.z) * m2.w};
+    PostCoef<FS> pc;
+    pc.load(cf);
+    float f0[F - 1], f1[F - 1];
+    pc.features(n0, p0, f0);
+    pc.features(n1, p1, f1);
     const float4 w0 = c4[0];
     f3 a = make_f3(w0.x, w0.y, w0.z), b = a;
 #pragma unroll
-    for (int f = 1; f < BMFR_FEATURES; ++f) {
+    for (int f = 1; f < F; ++f) {
         const float4 w = c4[f];
         a.x = fmaf(w.x, f0[f - 1], a.x); a.y = fmaf(w.y, f0[f - 1], a.y); a.z = fmaf(w.z, f0[f - 1], a.z);
         b.x = fmaf(w.x, f1[f - 1], b.x); b.y = fmaf(w.y, f1[f - 1], b.y); b.z = fmaf(w.z, f1[f - 1], b.z);
     }
-    out0 = make_f3(a.x < 0.f ? 0.f : a.x, a.y < 0.f ? 0.f : a.y, a.z < 0.f ? 0.f : a.z);  // keeps NaN, bmfr.cl:750
-    out1 = make_f3(b.x < 0.f ? 0.f : b.x, b.y < 0.f ? 0.f : b.y, b.z < 0.f ? 0.f : b.z);
+    out0 = clamp_negative(a);
+    out1 = clamp_negative(b);
 }
 
 // The same for the four pixels of a thread's column strip: every coefficient is fetched once and used four times.
+template <int FS>
 __device__ __forceinline__ void weighted_sum_px4(const f3 (&n)[4], const f3 (&p)[4], const float* __restrict__ cf, f3 (&out)[4]) {
+    constexpr int F = FeatureSet<FS>::F;
     const float4* c4 = reinterpret_cast<const float4*>(cf);
-    const float4 m0 = c4[10], m1 = c4[11], m2 = c4[12];
-    float ft[4][BMFR_FEATURES - 1];
+    PostCoef<FS> pc;
+    pc.load(cf);
+    float ft[4][F - 1];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        ft[k][0] = n[k].x; ft[k][1] = n[k].y; ft[k][2] = n[k].z;
-        ft[k][3] = (p[k].x - m0.x) * m0.y; ft[k][4] = (p[k].y - m0.z) * m0.w; ft[k][5] = (p[k].z - m1.x) * m1.y;
-        ft[k][6] = (p[k].x * p[k].x - m1.z) * m1.w; ft[k][7] = (p[k].y * p[k].y - m2.x) * m2.y; ft[k][8] = (p[k].z * p[k].z - m2.z) * m2.w;
-    }
+    for (int k = 0; k < 4; ++k) pc.features(n[k], p[k], ft[k]);
     const float4 w0 = c4[0];
     f3 acc[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) acc[k] = make_f3(w0.x, w0.y, w0.z);
 #pragma unroll
-    for (int f = 1; f < BMFR_FEATURES; ++f) {
+    for (int f = 1; f < F; ++f) {
         const float4 w = c4[f];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -152,8 +170,20 @@ __device__ __forceinline__ void weighted_sum_px4(const f3 (&n)[4], const f3 (&p)
         }
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k)  // keeps NaN, bmfr.cl:750
-        out[k] = make_f3(acc[k].x < 0.f ? 0.f : acc[k].x, acc[k].y < 0.f ? 0.f : acc[k].y, acc[k].z < 0.f ? 0.f : acc[k].z);
+    for (int k = 0; k < 4; ++k) out[k] = clamp_negative(acc[k]);
+}
+
+// The coefficients of the 3x3 block neighbourhood -> shared memory: warp w takes neighbour w (warp 0 also the ninth).
+template <int FS>
+__device__ __forceinline__ void load_coefficients(const KParams& P, float (*coef)[PT_COEF], int bx, int by, int warp, int lane) {
+    using PC = PostCoef<FS>;
+    for (int nb = warp; nb < 9; nb += 8) {
+        const int gx = bx + nb % 3 - 1, gy = by + nb / 3 - 1;
+        if (gx < 0 || gx >= P.blocks_x || gy < 0 || gy >= P.blocks_y) continue;
+        const size_t g = (size_t)gy * P.blocks_x + gx;
+        if (lane < PC::NW) coef[nb][(lane / 3) * 4 + lane % 3] = __ldg(P.weights + g * PC::NW + lane);
+        if (lane < PC::NM) coef[nb][PC::MINV + lane] = __ldg(P.mins_inv + g * PC::NM + lane);
+    }
 }
 
 // accept / pp / spp / alb are this pixel's accept mask, previous-frame position, sample count and
@@ -296,11 +326,11 @@ __device__ __forceinline__ bool finish_pixel(PostShared& sh, const KParams& P, c
     put_ycc(sh, P, hx, hy, x, y, to_ycocg(tone));
     return temporal;
 }
-template <bool STRIP, bool WIDE>
+template <bool STRIP, bool WIDE, int FS>
 __device__ __forceinline__ bool phase_a_pixel(PostShared& sh, const KParams& P, const float* cf, int hx, int hy, int x, int y,
                                               bool store, bool own, f3& hist) {
     const PixelIn in = load_pixel<WIDE>(P, x, y);
-    return finish_pixel<STRIP, WIDE>(sh, P, in, weighted_sum_px(in.n, in.p, cf), hx, hy, x, y, store, own, hist);
+    return finish_pixel<STRIP, WIDE>(sh, P, in, weighted_sum_px<FS>(in.n, in.p, cf), hx, hy, x, y, store, own, hist);
 }
 
 #ifndef BMFR_POST_PREFETCH_TAPS
@@ -338,13 +368,12 @@ __device__ __forceinline__ void prefetch_taps(const KParams& P, float2 pp) {
 #define BMFR_POST_MIN_BLOCKS 5
 #endif
 
-template <bool STRIP, bool WIDE>
+template <bool STRIP, bool WIDE, int FS>
 __global__ void __launch_bounds__(256, BMFR_POST_MIN_BLOCKS) post_kernel(const __grid_constant__ KParams P) {
     __shared__ __align__(16) PostShared sh;
     const int bx = blockIdx.x, by = P.by0 + (STRIP ? halo_row_order(P.halo_p, blockIdx.y, gridDim.y) : (int)blockIdx.y);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int x0 = bx * 32 - 16 + P.off_x, y0 = by * 32 - 16 + P.off_y;  // tile origin in image coordinates
-    constexpr int NW = BMFR_FEATURES * 3, NM = BMFR_FEATURES_SCALED * 2;
 #if BMFR_POST_PREFETCH
     // DRAM -> L2 prefetch of the strip's four pixels and of this thread's ring pixel, issued before the
     // wait for the fit: CTAs that became resident while the fit drains warm the L2 for their pixels
@@ -369,15 +398,7 @@ __global__ void __launch_bounds__(256, BMFR_POST_MIN_BLOCKS) post_kernel(const _
     if (zone) halo_poll(P.halo_p);
 
 
-    // coefficients of the 3x3 block neighbourhood -> shared memory: warp w takes neighbour w (warp 0
-    // also the ninth), lanes 0..29 the weights, lanes 0..11 the (min, 1/range) pairs
-    for (int nb = warp; nb < 9; nb += 8) {
-        const int gx = bx + nb % 3 - 1, gy = by + nb / 3 - 1;
-        if (gx < 0 || gx >= P.blocks_x || gy < 0 || gy >= P.blocks_y) continue;
-        const size_t g = (size_t)gy * P.blocks_x + gx;
-        if (lane < NW) sh.coef[nb][(lane / 3) * 4 + lane % 3] = __ldg(P.weights + g * NW + lane);
-        if (lane < NM) sh.coef[nb][40 + lane] = __ldg(P.mins_inv + g * NM + lane);
-    }
+    load_coefficients<FS>(P, sh.coef, bx, by, warp, lane);
     __syncthreads();
 
     const int x = x0 + lane;
@@ -402,7 +423,7 @@ __global__ void __launch_bounds__(256, BMFR_POST_MIN_BLOCKS) post_kernel(const _
             }
 #endif
             f3 fl0, fl1;
-            weighted_sum_px2(i0.n, i0.p, i1.n, i1.p, sh.coef[4], fl0, fl1);
+            weighted_sum_px2<FS>(i0.n, i0.p, i1.n, i1.p, sh.coef[4], fl0, fl1);
             const bool own0 = y >= P.own_y0 && y < P.own_y1, own1 = y + 1 >= P.own_y0 && y + 1 < P.own_y1;
             const bool t0 = finish_pixel<STRIP, WIDE>(sh, P, i0, fl0, lane + 1, ty + 1, x, y, true, own0, hist[s]);
             const bool t1 = finish_pixel<STRIP, WIDE>(sh, P, i1, fl1, lane + 1, ty + 2, x, y + 1, true, own1, hist[s + 1]);
@@ -410,11 +431,11 @@ __global__ void __launch_bounds__(256, BMFR_POST_MIN_BLOCKS) post_kernel(const _
             live |= ((own1 ? 1u : 0u) | (t1 ? 16u : 0u)) << (s + 1);
         } else if (v0) {  // a strip or image edge cuts the pair
             const bool own = y >= P.own_y0 && y < P.own_y1;
-            const bool t = phase_a_pixel<STRIP, WIDE>(sh, P, sh.coef[4], lane + 1, ty + 1, x, y, true, own, hist[s]);
+            const bool t = phase_a_pixel<STRIP, WIDE, FS>(sh, P, sh.coef[4], lane + 1, ty + 1, x, y, true, own, hist[s]);
             live |= ((own ? 1u : 0u) | (t ? 16u : 0u)) << s;
         } else if (v1) {
             const bool own = y + 1 >= P.own_y0 && y + 1 < P.own_y1;
-            const bool t = phase_a_pixel<STRIP, WIDE>(sh, P, sh.coef[4], lane + 1, ty + 2, x, y + 1, true, own, hist[s + 1]);
+            const bool t = phase_a_pixel<STRIP, WIDE, FS>(sh, P, sh.coef[4], lane + 1, ty + 2, x, y + 1, true, own, hist[s + 1]);
             live |= ((own ? 1u : 0u) | (t ? 16u : 0u)) << (s + 1);
         }
     }
@@ -430,7 +451,7 @@ __global__ void __launch_bounds__(256, BMFR_POST_MIN_BLOCKS) post_kernel(const _
         if (rx >= 0 && rx < P.W && ry >= P.py0 && ry < P.py1) {
             const int nb = ((hy == 0) ? 0 : (hy == PT_HALO - 1) ? 6 : 3) + ((hx == 0) ? 0 : (hx == PT_HALO - 1) ? 2 : 1);
             f3 unused;
-            phase_a_pixel<STRIP, WIDE>(sh, P, sh.coef[nb], hx, hy, rx, ry, false, false, unused);
+            phase_a_pixel<STRIP, WIDE, FS>(sh, P, sh.coef[nb], hx, hy, rx, ry, false, false, unused);
         }
     }
     __syncthreads();
@@ -590,11 +611,11 @@ __device__ __forceinline__ void post_push_rows(const KParams& P, const PostStage
 }
 
 // One pixel whose inputs are staged: ring pixels, and the pixels of a pair cut by a strip or image edge.
-template <bool STRIP>
+template <bool STRIP, int FS>
 __device__ __forceinline__ bool staged_pixel(PostStage& sh, const KParams& P, const TileGeom& G, const float* cf, int hx, int hy, int x, int y,
                                              bool store, bool own, f3& hist, bool zone) {
     const PixelIn in = load_pixel_staged(sh, P, G, hx, hy, x, y);
-    const f3 filtered = weighted_sum_px(in.n, in.p, cf);
+    const f3 filtered = weighted_sum_px<FS>(in.n, in.p, cf);
     const bool temporal = own && history_sample<STRIP, false>(P, in.pp, hist);
     f3 accum;
     const f3 tone = accumulate_filtered_px<STRIP, false>(P, in.lp, filtered, in.accept, in.pp, in.spp, in.alb, store, x, y, false, &accum);
@@ -688,7 +709,7 @@ __device__ __forceinline__ bool resolve_pixel(PostStage& sh, const KParams& P, c
 #define BMFR_POST_WS4 0
 #endif
 
-template <bool STRIP>
+template <bool STRIP, int FS>
 __global__ void __launch_bounds__(256, BMFR_POST_TMA_MIN_BLOCKS) post_tma_kernel(const __grid_constant__ KParams P, const __grid_constant__ PostMaps M) {
     extern __shared__ __align__(128) unsigned char post_smem[];
     PostStage& sh = *reinterpret_cast<PostStage*>(post_smem);
@@ -700,7 +721,6 @@ __global__ void __launch_bounds__(256, BMFR_POST_TMA_MIN_BLOCKS) post_tma_kernel
     const int f_rgb = 3 * (G.x0 - 1), f_pp = 2 * (G.x0 - 1), b_u8 = G.x0 - 1;
     const int c_rgb = f_rgb & ~3, c_pp = f_pp & ~3, c_u8 = b_u8 & ~15;  // 16-byte aligned box starts (floor, also for negatives)
     G.sh_rgb = f_rgb - c_rgb; G.sh_pp = f_pp - c_pp; G.sh_u8 = b_u8 - c_u8;
-    constexpr int NW = BMFR_FEATURES * 3, NM = BMFR_FEATURES_SCALED * 2;
 
     if (tid == 0) {
         mbar_init(&sh.bar, 1);
@@ -725,14 +745,7 @@ __global__ void __launch_bounds__(256, BMFR_POST_TMA_MIN_BLOCKS) post_tma_kernel
     const bool zone = STRIP && halo_in_zone(P.halo_p, G.y0 - 1, G.y0 + 33);
     if (zone) halo_poll(P.halo_p);
 
-    // coefficients of the 3x3 block neighbourhood -> shared memory (as in post_kernel)
-    for (int nb = warp; nb < 9; nb += 8) {
-        const int gx = bx + nb % 3 - 1, gy = by + nb / 3 - 1;
-        if (gx < 0 || gx >= P.blocks_x || gy < 0 || gy >= P.blocks_y) continue;
-        const size_t g = (size_t)gy * P.blocks_x + gx;
-        if (lane < NW) sh.coef[nb][(lane / 3) * 4 + lane % 3] = __ldg(P.weights + g * NW + lane);
-        if (lane < NM) sh.coef[nb][40 + lane] = __ldg(P.mins_inv + g * NM + lane);
-    }
+    load_coefficients<FS>(P, sh.coef, bx, by, warp, lane);
     __syncthreads();  // the coefficients and the barrier's initialisation are visible
     mbar_wait_hot(&sh.bar, 0);
 
@@ -754,7 +767,7 @@ __global__ void __launch_bounds__(256, BMFR_POST_TMA_MIN_BLOCKS) post_tma_kernel
             n4[k] = cell_f3(sh.nrm, G, lane + 1, 4 * warp + k + 1);
             p4[k] = cell_f3(sh.pos, G, lane + 1, 4 * warp + k + 1);
         }
-        weighted_sum_px4(n4, p4, sh.coef[4], fl4);
+        weighted_sum_px4<FS>(n4, p4, sh.coef[4], fl4);
     }
 #endif
 #pragma unroll
@@ -786,7 +799,7 @@ __global__ void __launch_bounds__(256, BMFR_POST_TMA_MIN_BLOCKS) post_tma_kernel
                 if (strip_whole) { fl0 = fl4[s]; fl1 = fl4[s + 1]; }
                 else
 #endif
-                weighted_sum_px2(i0.n, i0.p, i1.n, i1.p, sh.coef[4], fl0, fl1);  // its arithmetic overlaps the gathers
+                weighted_sum_px2<FS>(i0.n, i0.p, i1.n, i1.p, sh.coef[4], fl0, fl1);  // its arithmetic overlaps the gathers
                 t0 = resolve_pixel<STRIP>(sh, P, G, i0, g0, fl0, A[0], A[1], R[0], R[1], lane + 1, ty + 1, x, y, own0, hist[s], zone);
                 if (!(cx1[0] == cx0[0] && cx1[1] == cx0[1] && ry1[0] == ry0[1])) {  // footprints not stacked (rare): fetch the row
 #pragma unroll
@@ -803,7 +816,7 @@ __global__ void __launch_bounds__(256, BMFR_POST_TMA_MIN_BLOCKS) post_tma_kernel
                 if (strip_whole) { fl0 = fl4[s]; fl1 = fl4[s + 1]; }
                 else
 #endif
-                weighted_sum_px2(i0.n, i0.p, i1.n, i1.p, sh.coef[4], fl0, fl1);
+                weighted_sum_px2<FS>(i0.n, i0.p, i1.n, i1.p, sh.coef[4], fl0, fl1);
                 store_f3(P.accum_cur, i0.lp, fl0);
                 store_f3(P.accum_cur, i1.lp, fl1);
                 if (STRIP && zone) {
@@ -818,10 +831,10 @@ __global__ void __launch_bounds__(256, BMFR_POST_TMA_MIN_BLOCKS) post_tma_kernel
             live |= ((own0 ? 1u : 0u) | (t0 ? 16u : 0u)) << s;
             live |= ((own1 ? 1u : 0u) | (t1 ? 16u : 0u)) << (s + 1);
         } else if (v0) {  // a strip or image edge cuts the pair
-            const bool t = staged_pixel<STRIP>(sh, P, G, sh.coef[4], lane + 1, ty + 1, x, y, true, own0, hist[s], zone);
+            const bool t = staged_pixel<STRIP, FS>(sh, P, G, sh.coef[4], lane + 1, ty + 1, x, y, true, own0, hist[s], zone);
             live |= ((own0 ? 1u : 0u) | (t ? 16u : 0u)) << s;
         } else if (v1) {
-            const bool t = staged_pixel<STRIP>(sh, P, G, sh.coef[4], lane + 1, ty + 2, x, y + 1, true, own1, hist[s + 1], zone);
+            const bool t = staged_pixel<STRIP, FS>(sh, P, G, sh.coef[4], lane + 1, ty + 2, x, y + 1, true, own1, hist[s + 1], zone);
             live |= ((own1 ? 1u : 0u) | (t ? 16u : 0u)) << (s + 1);
         }
     }
@@ -837,7 +850,7 @@ __global__ void __launch_bounds__(256, BMFR_POST_TMA_MIN_BLOCKS) post_tma_kernel
         if (rx >= 0 && rx < P.W && ry >= P.py0 && ry < P.py1) {
             const int nb = ((hy == 0) ? 0 : (hy == PT_HALO - 1) ? 6 : 3) + ((hx == 0) ? 0 : (hx == PT_HALO - 1) ? 2 : 1);
             f3 unused;
-            staged_pixel<STRIP>(sh, P, G, sh.coef[nb], hx, hy, rx, ry, false, false, unused, zone);
+            staged_pixel<STRIP, FS>(sh, P, G, sh.coef[nb], hx, hy, rx, ry, false, false, unused, zone);
         }
     }
     __syncthreads();
@@ -908,40 +921,43 @@ static bool post_maps(const KParams& P, PostMaps* M) {
            bmfr_tensor_map_2d(P.cur_spp, 1, (long long)P.W, rows, PT_U8_W, PT_HALO, &M->spp);
 }
 
-static cudaError_t post_tma_configure() {
-    static bool done[64] = {};
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return e;
-    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
-    if (!done[dev]) {
-        e = cudaFuncSetAttribute(post_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PostStage));
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(post_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PostStage));
-        if (e != cudaSuccess) return e;
-        done[dev] = true;
-    }
-    return cudaSuccess;
-}
-
-cudaError_t launch_post(const KParams& P, cudaStream_t st) {
+template <int FS>
+static cudaError_t launch_post_fs(const KParams& P, cudaStream_t st) {
     const dim3 grid(P.blocks_x, P.by1 - P.by0);
     const bool strip = P.row0 != 0 || P.row1 != P.H;
     PostMaps M;
     if (post_maps(P, &M)) {
-        cudaError_t e = post_tma_configure();
+        static bool done[64] = {};
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
         if (e != cudaSuccess) return e;
-        if (strip) return launch_pdl(!P.plain_launch, post_tma_kernel<true>, grid, dim3(256), sizeof(PostStage), st, P, M);
-        return launch_pdl(!P.plain_launch, post_tma_kernel<false>, grid, dim3(256), sizeof(PostStage), st, P, M);
+        if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+        if (!done[dev]) {
+            e = cudaFuncSetAttribute(post_tma_kernel<false, FS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PostStage));
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(post_tma_kernel<true, FS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PostStage));
+            if (e != cudaSuccess) return e;
+            done[dev] = true;
+        }
+        if (strip) return launch_pdl(!P.plain_launch, post_tma_kernel<true, FS>, grid, dim3(256), sizeof(PostStage), st, P, M);
+        return launch_pdl(!P.plain_launch, post_tma_kernel<false, FS>, grid, dim3(256), sizeof(PostStage), st, P, M);
     }
+    // widths that are no multiple of 16 (no tensor maps): the per-thread-load variant.  (Its 64+32-bit pixel accesses,
+    // BMFR_POST_WIDE_ACCESS, cost 38 % more instructions for the same L1 wavefronts and stay a tuning switch.)
     const uintptr_t bits = (uintptr_t)P.cur_normals | (uintptr_t)P.cur_positions | (uintptr_t)P.albedo | (uintptr_t)P.accum_prev |
                            (uintptr_t)P.accum_cur | (uintptr_t)P.result_prev | (uintptr_t)P.result_cur | (uintptr_t)P.user_out;
-    // measured on B200 (profiles/): the 64+32-bit form costs 38% more instructions (selects, address
-    // arithmetic) and the same number of L1 wavefronts, so it is kept only as a tuning switch
     const bool wide = BMFR_POST_WIDE_ACCESS && (bits & 7) == 0;
     if (strip) {
-        if (wide) return launch_pdl(!P.plain_launch, post_kernel<true, true>, grid, dim3(256), 0, st, P);
-        return launch_pdl(!P.plain_launch, post_kernel<true, false>, grid, dim3(256), 0, st, P);
+        if (wide) return launch_pdl(!P.plain_launch, post_kernel<true, true, FS>, grid, dim3(256), 0, st, P);
+        return launch_pdl(!P.plain_launch, post_kernel<true, false, FS>, grid, dim3(256), 0, st, P);
     }
-    if (wide) return launch_pdl(!P.plain_launch, post_kernel<false, true>, grid, dim3(256), 0, st, P);
-    return launch_pdl(!P.plain_launch, post_kernel<false, false>, grid, dim3(256), 0, st, P);
+    if (wide) return launch_pdl(!P.plain_launch, post_kernel<false, true, FS>, grid, dim3(256), 0, st, P);
+    return launch_pdl(!P.plain_launch, post_kernel<false, false, FS>, grid, dim3(256), 0, st, P);
+}
+
+cudaError_t launch_post(const KParams& P, cudaStream_t st) {
+    switch (P.feature_set) {
+        case BMFR_FEATURE_SET_LINEAR: return launch_post_fs<BMFR_FEATURE_SET_LINEAR>(P, st);
+        case BMFR_FEATURE_SET_POSITION: return launch_post_fs<BMFR_FEATURE_SET_POSITION>(P, st);
+        default: return launch_post_fs<BMFR_FEATURE_SET_DEFAULT>(P, st);
+    }
 }

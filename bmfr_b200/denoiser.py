@@ -43,7 +43,7 @@ class Denoiser:
     def __init__(self, width, height, *, mode="fused", device=0, profile=False, stream=0, strip=None, halo_rows=0,
                  position_limit_squared=None, normal_limit_squared=None, noise_amount=None, blend_alpha=None,
                  second_blend_alpha=None, taa_blend_alpha=None, tmp_half=0, reference_order=0, overlap_frames=0, fit="gram",
-                 halo_timeout_ms=0):
+                 halo_timeout_ms=0, feature_set=0):
         self.lib = _lib.load()
         p = Params()
         self.lib.bmfr_default_params(C.byref(p), width, height)
@@ -54,6 +54,10 @@ class Denoiser:
         p.overlap_frames = int(overlap_frames)
         p.fit_method = {"gram": 0, "tsqr": 1}[fit]
         p.halo_timeout_ms = int(halo_timeout_ms)
+        p.feature_set = int(feature_set)
+        nf, ns = C.c_int(), C.c_int()
+        _lib.check(self.lib.bmfr_feature_counts(p.feature_set, C.byref(nf), C.byref(ns)))
+        self.features, self.features_scaled = nf.value, ns.value
         p.stream = C.c_void_p(stream or None)
         if strip is not None:
             p.strip_y0, p.strip_y1, p.halo_rows = int(strip[0]), int(strip[1]), int(halo_rows)
@@ -136,13 +140,13 @@ class Denoiser:
         if name in ("spp", "accept"):
             return a.reshape(self.rows, self.W)
         if name == "weights":
-            return a.reshape(-1, 10, 3)
+            return a.reshape(-1, self.features, 3)
         if name == "mins_maxs":
-            return a.reshape(-1, 6, 2)
+            return a.reshape(-1, self.features_scaled, 2)
         if name == "tmp_data":
             return a.reshape(-1, 13, 32, 32)
         if name == "noise_tile":
-            return a.reshape(9, 1024)
+            return a.reshape(self.features - 1, 1024)
         return a
 
     def stage_ms(self, frame):

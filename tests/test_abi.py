@@ -19,11 +19,11 @@ def declared_functions():
 
 def test_header_symbols_are_exported(lib):
     names = declared_functions()
-    assert len(names) >= 19
+    assert len(names) >= 26
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/bmfr_b200.h but not exported"
     assert set(names) == set(_lib.SYMBOLS), "ctypes table and header disagree"
-    assert lib.bmfr_abi_version() == 4
+    assert lib.bmfr_abi_version() == 5
 
 
 def test_block_offsets_table():

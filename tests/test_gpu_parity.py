@@ -141,6 +141,27 @@ def test_busy_stamps_do_not_change_results_and_are_plausible():
         assert util.bits_equal(outs[0][k], outs[2][k]), k
 
 
+@pytest.mark.parametrize("size", [(416, 250), (200, 120)])
+@pytest.mark.parametrize("feature_set", [1, 2])
+def test_other_feature_lists_match_their_oracle(feature_set, size):
+    """bmfr_params.feature_set: the FUSED kernels instantiated for 1, n | p (7 features, 3 scaled) and 1 | p, p^2 (7 features,
+    6 scaled), against the port built for the same list (which equals the reference's kernels compiled with that list,
+    tests/test_oracle_pin.py).  Same bars as the default list; 416 wide runs the TMA post pass, 200 the per-thread one."""
+    w, h = size
+    ref = util.run_oracle("port", w, h, 18, keep=KEEP_FUSED, feature_set=feature_set)
+    cuda = util.run_cuda(w, h, 18, mode="fused", keep=KEEP_FUSED, feature_set=feature_set)
+    assert cuda[0]["weights"].shape == ref[0]["weights"].shape and cuda[0]["mins_maxs"].shape == ref[0]["mins_maxs"].shape
+    _check_frames(cuda, ref, False)
+
+
+def test_feature_lists_need_the_fused_gram_path():
+    from bmfr_b200 import BmfrError
+    for kw in (dict(mode="staged"), dict(mode="fused", fit="tsqr")):
+        with pytest.raises(BmfrError) as e:
+            Denoiser(160, 96, feature_set=1, **kw)
+        assert e.value.status == -5
+
+
 def test_staged_and_fused_agree():
     """The two kernel structures share the reprojection code (bit-identical K1 outputs, block min/max
     and noise tile); the fit and the post-fit passes are separate implementations held to the colour

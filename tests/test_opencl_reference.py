@@ -18,15 +18,15 @@ from tests import util
 pytestmark = pytest.mark.gpu
 
 
-def _opencl(w, h, strict):
+def _opencl(w, h, strict, feature_set=0):
     from bmfr_b200 import synth
     from oracle import oracle as orc
-    if not orc.available("opencl"):
-        pytest.skip("oracle/_ref/libbmfr_clgpu.so was not built (needs /root/reference at build time)")
+    if not orc.available("opencl", feature_set):
+        pytest.skip("oracle/_ref/libbmfr_clgpu*.so was not built (needs /root/reference at build time)")
     os.environ["BMFR_OPENCL_STRICT_FP"] = "1" if strict else "0"
     pl, nl = synth.limits()
     try:
-        return orc.Oracle("opencl", w, h, position_limit_squared=pl, normal_limit_squared=nl)
+        return orc.Oracle("opencl", w, h, position_limit_squared=pl, normal_limit_squared=nl, feature_set=feature_set)
     except RuntimeError as e:
         pytest.skip(f"no usable OpenCL platform here: {e}")
 
@@ -55,11 +55,14 @@ def test_vendor_compiled_reference_kernels_match_the_port():
     cl.close(); port.close()
 
 
-def test_cuda_path_matches_the_reference_kernels_on_the_same_gpu():
+@pytest.mark.parametrize("feature_set,size", [(0, (1280, 720)), (1, (416, 250)), (2, (416, 250))])
+def test_cuda_path_matches_the_reference_kernels_on_the_same_gpu(feature_set, size):
+    """... for the reference's shipped feature list at 720p and for the two other lists (the -D FEATURE_BUFFERS strings of
+    oracle/build_oracle.py FEATURE_SETS, compiled by the OpenCL driver)."""
     from bmfr_b200 import Denoiser
-    w, h, frames = 1280, 720, 12
-    cl = _opencl(w, h, strict=False)
-    with Denoiser(w, h, mode="fused") as d:
+    (w, h), frames = size, 12
+    cl = _opencl(w, h, strict=False, feature_set=feature_set)
+    with Denoiser(w, h, mode="fused", feature_set=feature_set) as d:
         for fr in util.sequence(w, h, frames):
             cl.frame(*fr)
             d.denoise_frame_host(*fr)

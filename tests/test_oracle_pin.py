@@ -37,6 +37,19 @@ def test_port_equals_reference_kernels_jitter():
     _compare(200, 120, 6, jitter=True)
 
 
+@pytest.mark.parametrize("feature_set", [1, 2])
+@pytest.mark.parametrize("half", [0, 1])
+def test_port_equals_reference_kernels_other_feature_lists(feature_set, half):
+    """The reference's feature list is a compile-time string (bmfr.cpp:63-77).  For the two other lists the CUDA library
+    instantiates, the reference's bmfr.cl is compiled through the shim with those strings (oracle/build_oracle.py
+    FEATURE_SETS) and the port with -DBMFR_FEATURE_SET: every buffer of every frame bit for bit again."""
+    if not orc.available("reference", feature_set):
+        from oracle import build_oracle
+        if build_oracle.build_reference(False, feature_set) is None:
+            pytest.skip("the shim build for this feature list is absent and /root/reference not mounted")
+    _compare(200, 120, 17, feature_set=feature_set, tmp_half=half)
+
+
 def test_port_equals_reference_kernels_half_tmp_data():
     """USE_HALF_PRECISION_IN_TMP_DATA=1, the reference's shipped default (bmfr.cpp:88)."""
     _compare(160, 96, 5, tmp_half=1)
