@@ -945,12 +945,14 @@ static cudaError_t launch_post_fs(const KParams& P, cudaStream_t st) {
     // BMFR_POST_WIDE_ACCESS, cost 38 % more instructions for the same L1 wavefronts and stay a tuning switch.)
     const uintptr_t bits = (uintptr_t)P.cur_normals | (uintptr_t)P.cur_positions | (uintptr_t)P.albedo | (uintptr_t)P.accum_prev |
                            (uintptr_t)P.accum_cur | (uintptr_t)P.result_prev | (uintptr_t)P.result_cur | (uintptr_t)P.user_out;
-    const bool wide = BMFR_POST_WIDE_ACCESS && (bits & 7) == 0;
-    if (strip) {
-        if (wide) return launch_pdl(!P.plain_launch, post_kernel<true, true, FS>, grid, dim3(256), 0, st, P);
-        return launch_pdl(!P.plain_launch, post_kernel<true, false, FS>, grid, dim3(256), 0, st, P);
+    if constexpr (BMFR_POST_WIDE_ACCESS != 0) {
+        if ((bits & 7) == 0) {
+            if (strip) return launch_pdl(!P.plain_launch, post_kernel<true, true, FS>, grid, dim3(256), 0, st, P);
+            return launch_pdl(!P.plain_launch, post_kernel<false, true, FS>, grid, dim3(256), 0, st, P);
+        }
     }
-    if (wide) return launch_pdl(!P.plain_launch, post_kernel<false, true, FS>, grid, dim3(256), 0, st, P);
+    (void)bits;
+    if (strip) return launch_pdl(!P.plain_launch, post_kernel<true, false, FS>, grid, dim3(256), 0, st, P);
     return launch_pdl(!P.plain_launch, post_kernel<false, false, FS>, grid, dim3(256), 0, st, P);
 }
 
