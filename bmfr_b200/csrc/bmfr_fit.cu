@@ -25,13 +25,18 @@
 // (bmfr.cl:314-325) and store nothing per pixel (bmfr.cl:478), so the image pixels are the whole
 // job; the fit re-derives margin rows from these outputs.
 // --------------------------------------------------------------------------------------------
+// CTAs per SM and CTA shape of the whole-image instantiation.  Measured at 1080p (profiles/r02_u_*): 4 CTAs x (32 x 8
+// threads) 52.1 us; 5 CTAs (48 registers, no spills) 48.4 us; 5 CTAs x (64 x 4 threads) 48.0 us; 6 CTAs (40 registers,
+// spills) 65.5 us.  The strip instantiation keeps 4 x (32 x 8): its row staging is laid out for 32 x 32 tiles and it
+// spills at 48 registers.
 #ifndef BMFR_REPROJECT_MIN_BLOCKS
-#define BMFR_REPROJECT_MIN_BLOCKS 4
+#define BMFR_REPROJECT_MIN_BLOCKS 5
 #endif
 #ifndef BMFR_REPROJECT_BX
-#define BMFR_REPROJECT_BX 32  // CTA = BX x (256 / BX) pixels
+#define BMFR_REPROJECT_BX 64  // CTA = BX x (256 / BX) threads
 #endif
-#define BMFR_REPROJECT_BY (256 / BMFR_REPROJECT_BX)
+#define BMFR_REPROJECT_STRIP_MIN_BLOCKS 4
+#define BMFR_REPROJECT_STRIP_BX 32
 // 1: a thread walks down four vertically adjacent pixels and hands the lower tap row of one to the next (K1Carry; 25 %
 // fewer tap loads).  Measured at 1080p (profiles/r02_m_*): 69.8 us against 52 us — the eight warps of a CTA then work on
 // rows four apart instead of on eight consecutive rows (the adjacent-row mapping alone: 58.1 us), which costs more L1
@@ -129,7 +134,9 @@ __device__ __forceinline__ void reproject_store(const KParams& P, int x, int y, 
 }
 
 template <bool STRIP>
-__global__ void __launch_bounds__(256, BMFR_REPROJECT_MIN_BLOCKS) reproject_kernel(const __grid_constant__ KParams P) {
+__global__ void __launch_bounds__(256, STRIP ? BMFR_REPROJECT_STRIP_MIN_BLOCKS : BMFR_REPROJECT_MIN_BLOCKS) reproject_kernel(const __grid_constant__ KParams P) {
+    constexpr int BX = STRIP ? BMFR_REPROJECT_STRIP_BX : BMFR_REPROJECT_BX, BY = 256 / BX, CTA_ROWS = BY * BMFR_REPROJECT_PIXELS;
+    static_assert(!STRIP || (BX == 32 && CTA_ROWS == 32), "the strip staging (ReprojectPushStage) holds 32 x 32 pixels");
     // Everything below reads the caller's inputs.  Their producer may be the kernel right before this one on the
     // context's stream — then it is this grid's programmatic-launch primary, and if it triggers its dependents early
     // its writes are only guaranteed visible after the wait.  So the wait comes first; what the programmatic launch
@@ -140,15 +147,15 @@ __global__ void __launch_bounds__(256, BMFR_REPROJECT_MIN_BLOCKS) reproject_kern
     pdl_trigger();  // the fit's CTAs may take SM slots as this grid drains
     stamp_begin(P, 0);
     if (P.stamps_next != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.y == 0 && threadIdx.x < 6) P.stamps_next[threadIdx.x] = ~0ull;
-    reproject_noise_tile(P, threadIdx.y * BMFR_REPROJECT_BX + threadIdx.x);
+    reproject_noise_tile(P, threadIdx.y * BX + threadIdx.x);
     __shared__ __align__(16) ReprojectPushStage<STRIP, true> push_stage;
-    const int x = blockIdx.x * BMFR_REPROJECT_BX + threadIdx.x;
-    const int cta_y0 = P.k1_y0 + (STRIP ? halo_row_order(P.halo_r, blockIdx.y, gridDim.y) : (int)blockIdx.y) * (BMFR_REPROJECT_BY * BMFR_REPROJECT_PIXELS);
-    // thread (x, ty) takes rows ty, ty + 8, ty + 16, ty + 24 of the CTA's 32 rows (BMFR_REPROJECT_CARRY: rows 4 ty .. 4 ty + 3)
-    const int ystep = BMFR_REPROJECT_CARRY ? 1 : BMFR_REPROJECT_BY;
+    const int x = blockIdx.x * BX + threadIdx.x;
+    const int cta_y0 = P.k1_y0 + (STRIP ? halo_row_order(P.halo_r, blockIdx.y, gridDim.y) : (int)blockIdx.y) * CTA_ROWS;
+    // thread (x, ty) takes rows ty, ty + BY, ty + 2 BY, ty + 3 BY of the CTA's rows (BMFR_REPROJECT_CARRY: rows 4 ty .. 4 ty + 3)
+    const int ystep = BMFR_REPROJECT_CARRY ? 1 : BY;
     const int ybase = cta_y0 + (BMFR_REPROJECT_CARRY ? BMFR_REPROJECT_PIXELS : 1) * threadIdx.y;
     // strips: a CTA near a strip edge waits for the neighbours' rows of the previous frame before it gathers from them
-    const bool zone = STRIP && halo_in_zone(P.halo_r, cta_y0, cta_y0 + BMFR_REPROJECT_BY * BMFR_REPROJECT_PIXELS);
+    const bool zone = STRIP && halo_in_zone(P.halo_r, cta_y0, cta_y0 + CTA_ROWS);
     if (zone) halo_poll(P.halo_r);
     int ylo = P.k1_y0, yhi = P.k1_y1;
     if (STRIP) {  // rows outside the strip + halo cannot be reprojected here: flag and skip them
@@ -181,7 +188,7 @@ __global__ void __launch_bounds__(256, BMFR_REPROJECT_MIN_BLOCKS) reproject_kern
         if (zone) {
             if ((P.W & 31) == 0) {
                 __syncthreads();
-                reproject_push_rows(P, push_stage.rgb, push_stage.spp, blockIdx.x * BMFR_REPROJECT_BX, cta_y0, threadIdx.y * BMFR_REPROJECT_BX + threadIdx.x);
+                reproject_push_rows(P, push_stage.rgb, push_stage.spp, blockIdx.x * BX, cta_y0, threadIdx.y * BX + threadIdx.x);
             }
             halo_finish(P.halo_r, halo_cta_pushes(P.halo_r, cta_y0, cta_y0 + 32));
         }
@@ -208,7 +215,7 @@ struct ReprojectMaps {
 };
 
 template <bool STRIP>
-__global__ void __launch_bounds__(256, BMFR_REPROJECT_MIN_BLOCKS) reproject_tma_kernel(const __grid_constant__ KParams P,
+__global__ void __launch_bounds__(256, BMFR_REPROJECT_STRIP_MIN_BLOCKS) reproject_tma_kernel(const __grid_constant__ KParams P,
                                                                                        const __grid_constant__ ReprojectMaps M) {
     __shared__ __align__(128) ReprojectShared sh;
     __shared__ __align__(16) ReprojectPushStage<STRIP, false> push_stage;  // the colour rows are staged over the noisy-colour tile
@@ -275,6 +282,17 @@ __device__ __forceinline__ float warp_min(float v) {
 __device__ __forceinline__ float warp_max(float v) {
     float r;
     asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+    return r;
+}
+// three-input minimum / maximum (FMNMX3, sm_100)
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+    float r;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
     return r;
 }
 __device__ __forceinline__ float rcp_approx(float v) {
@@ -875,19 +893,12 @@ __device__ __forceinline__ double shfl_f64(double v, int src) {
     const int lo = __shfl_sync(0xffffffffu, __double2loint(v), src), hi = __shfl_sync(0xffffffffu, __double2hiint(v), src);
     return __hiloint2double(hi, lo);
 }
-// 1 / sqrt(d) and 1 / d in fp64 from the fp32 approximation and two Newton steps (no DSQRT / DDIV sequences: this code
-// runs once per block and is fetched cold, so it is written for size)
-__device__ __forceinline__ double rsqrt_f64(double d) {
-    double r = (double)rsqrt_approx((float)d);
-    r = r * (1.5 - 0.5 * d * r * r);
-    r = r * (1.5 - 0.5 * d * r * r);
-    return r;
-}
+// 1 / d in fp64 from the fp32 approximation (relative error 2^-22) and one Newton step (-> 2^-43; the Gram entries carry
+// 2^-24).  No DDIV sequence: this code runs once per block and is fetched cold, so it is written for size and for a short
+// dependent chain.
 __device__ __forceinline__ double rcp_f64(double d) {
-    double r = (double)rcp_approx((float)d);
-    r = r * (2.0 - d * r);
-    r = r * (2.0 - d * r);
-    return r;
+    const double r = (double)rcp_approx((float)d);
+    return fma(fma(-d, r, 1.0), r, r);
 }
 // index of G_ij (i <= j, (i, j) != (0, 0)) in the scratch order
 template <int NCOL>
@@ -895,7 +906,10 @@ __device__ __forceinline__ int gram_index(int i, int j) {
     return i == 0 ? j - 1 : NCOL + (i - 1) * NCOL - ((i - 1) * (i - 2)) / 2 + (j - i);
 }
 
-// Cholesky + substitutions for the block `blk` by half a warp (hb = lane & 16): lane i < NC owns row i of G.
+// Factorisation + substitution for the block `blk` by half a warp (hb = lane & 16): lane i < NC owns row i of G.
+// G = L D L^T with a unit lower triangle (no square roots, and the pivot row's entries are broadcast while its reciprocal
+// is still being refined); carried through the three colour rows it leaves them as D^-1 L^-1 [A^T y], so the weights are
+// the solution of the unit triangular system L^T x = that — no division (bmfr.cl:659-692 does the same job on R).
 template <int FS>
 __device__ __forceinline__ void gram_solve(const KParams& P, double* __restrict__ fin, int blk, int lane) {
     constexpr int NF = FeatureSet<FS>::F, NC = NF + 3, NCOL = NC - 1, ENTRIES = NCOL + NCOL * (NCOL + 1) / 2;
@@ -919,14 +933,16 @@ __device__ __forceinline__ void gram_solve(const KParams& P, double* __restrict_
         for (int j = 0; j < NC; ++j) g[j] = (j == i) ? 1.0 : 0.0;
     }
 #pragma unroll
-    for (int k = 0; k < NF; ++k) {  // right-looking Cholesky on the first ten pivots; rows 10..12 become L^-1 [A^T y]
-        const double dk = shfl_f64(g[k], hb + k);
-        const double lik = g[k] * rsqrt_f64(dk);  // L_ik (lane k: sqrt(G_kk))
-        g[k] = lik;
+    for (int k = 0; k < NF; ++k) {  // right-looking elimination on the first NF pivots
+        double pr[NC];              // the pivot row (= pivot column, G is symmetric) as lane k holds it now
 #pragma unroll
-        for (int j = k + 1; j < NC; ++j) g[j] -= lik * shfl_f64(lik, hb + j);
+        for (int j = k; j < NC; ++j) pr[j] = shfl_f64(g[j], hb + k);
+        const double lik = g[k] * rcp_f64(pr[k]);  // L_ik for i > k (lane k itself: 1; lanes above: stale, never read)
+#pragma unroll
+        for (int j = k + 1; j < NC; ++j) g[j] = fma(-lik, pr[j], g[j]);
+        g[k] = lik;
     }
-    // L (rows 0..9) and z (rows 10..12) -> shared memory, then one colour channel per lane solves L^T x = z (bmfr.cl:659-692)
+    // L (rows 0..NF-1) and the colour rows -> shared memory, then one colour channel per lane solves L^T x = row (NF + channel)
     if (owner) {
 #pragma unroll
         for (int k = 0; k < NF; ++k) fin[i * NF + k] = g[k];
@@ -935,11 +951,11 @@ __device__ __forceinline__ void gram_solve(const KParams& P, double* __restrict_
     if (blk >= 0 && i < 3) {
         double x[NF];
 #pragma unroll
-        for (int r = NF - 1; r >= 0; --r) {
-            double a = fin[(NF + i) * NF + r];
+        for (int r = 0; r < NF; ++r) x[r] = fin[(NF + i) * NF + r];
 #pragma unroll
-            for (int jj = r + 1; jj < NF; ++jj) a -= fin[jj * NF + r] * x[jj];
-            x[r] = a * rcp_f64(fin[r * NF + r]);
+        for (int r = NF - 1; r > 0; --r) {  // column-oriented: x_r is final, every row above it takes its share at once
+#pragma unroll
+            for (int q = 0; q < r; ++q) x[q] = fma(-fin[r * NF + q], x[r], x[q]);
         }
         // the columns were centred: y - m_y = x_0 + sum_j x_j (a_j - m_j)  ->  intercept of the uncentred model
         const float* mean = sc + ENTRIES;  // block means of the non-constant columns, written by warp 0
@@ -1027,11 +1043,11 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_GRAM_MIN_BLOCKS) fit_gram_ker
         // a[s][c-1] = column c of row (x_in = lane, y_in = 8 warp + s): the 12 non-constant K1 values (bmfr.cl:448-453), NaN -> 0
         float a[ROWS][NCOL];
         int ox, oy;
-        if (qr_block_box(P, bx, by, ox, oy) && M.use_tma) {
+        const bool by_tma = qr_block_box(P, bx, by, ox, oy) && M.use_tma;
+        if (by_tma) {
             // this lane's pixel column and this thread's eight rows inside the 32x32 window, mirrored like bmfr.cl:314-316
             const int col = ((ox * 3) & 3) + 3 * (mirror_index(bx * 32 + lane - 16 + P.off_x, P.W) - ox);
             const int y_in = by * 32 + warp * ROWS - 16 + P.off_y;
-            bool bad = false;
 #pragma unroll
             for (int s = 0; s < ROWS; ++s) {
                 float v[9];
@@ -1039,15 +1055,8 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_GRAM_MIN_BLOCKS) fit_gram_ker
                 for (int c = 0; c < 9; ++c) {
                     if (c < 3 && !FL::NORMALS) continue;  // this list does not read the normals
                     v[c] = sh.stage[c / 3][mirror_index(y_in + s, P.H) - oy][col + c % 3];
-                    bad = bad || (v[c] != v[c]);
                 }
-                feature_columns<FS>(a[s], v, v + 3, v + 6);
-            }
-            if (__any_sync(0xffffffffu, bad)) {
-#pragma unroll
-                for (int s = 0; s < ROWS; ++s)
-#pragma unroll
-                    for (int c = 0; c < NCOL; ++c) a[s][c] = scrub_nan(a[s][c]);
+                feature_columns<FS>(a[s], v, v + 3, v + 6);  // NaNs are found and scrubbed below
             }
         } else {  // the window leaves the rows this strip holds (or no tensor maps): pixel by pixel
             const int x = mirror_index(bx * 32 + lane - 16 + P.off_x, P.W);
@@ -1071,18 +1080,42 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_GRAM_MIN_BLOCKS) fit_gram_ker
             }
         }
 
-        // (i) block min / max of the six scaled features (bmfr.cl:511-535; exact, order-free) and, for the centring, the
-        // sums of all twelve columns: per thread, then over the warp (redux for the extrema, the transpose buffer for the sums)
+        // a2[h][c]: rows (2h, 2h + 1) of column c + 1 as one register pair (FADD2 / FFMA2 operands from here on)
+        float2 a2[ROWS / 2][NCOL];
+#pragma unroll
+        for (int h = 0; h < ROWS / 2; ++h)
+#pragma unroll
+            for (int c = 0; c < NCOL; ++c) a2[h][c] = make_float2(a[2 * h][c], a[2 * h + 1][c]);
+        // (i) for the centring, the sums of all twelve columns: per thread, then over the warp through the transpose buffer.
+        // A NaN input (bmfr.cl:448-453 turns it into 0) poisons its column's sum, so the sums double as the NaN test of
+        // the thread's 72 tile values; the scrub itself is the rare path.
+        float colsum[NCOL];
+        bool bad = false;
+#pragma unroll
+        for (int c = 0; c < NCOL; ++c) {
+            const float2 t = fadd2(fadd2(a2[0][c], a2[1][c]), fadd2(a2[2][c], a2[3][c]));
+            colsum[c] = t.x + t.y;
+            bad = bad || (colsum[c] != colsum[c]);
+        }
+        if (by_tma && __any_sync(0xffffffffu, bad)) {
+#pragma unroll
+            for (int c = 0; c < NCOL; ++c) {
+#pragma unroll
+                for (int h = 0; h < ROWS / 2; ++h) a2[h][c] = make_float2(scrub_nan(a2[h][c].x), scrub_nan(a2[h][c].y));
+                const float2 t = fadd2(fadd2(a2[0][c], a2[1][c]), fadd2(a2[2][c], a2[3][c]));
+                colsum[c] = t.x + t.y;
+            }
+        }
+        // block min / max of the scaled features (bmfr.cl:511-535; exact, order-free): three-input min / max per thread,
+        // redux over the warp
         float* part = &sh.part[it & 1][warp][0];
 #pragma unroll
         for (int f = 0; f < NSC; ++f) {
             const int c = NNS - 1 + f;
-            float lo = a[0][c], hi = a[0][c];
-#pragma unroll
-            for (int s = 1; s < ROWS; ++s) {
-                lo = fminf(lo, a[s][c]);
-                hi = fmaxf(hi, a[s][c]);
-            }
+            float lo = fmin3(a2[0][c].x, a2[0][c].y, a2[1][c].x), hi = fmax3(a2[0][c].x, a2[0][c].y, a2[1][c].x);
+            lo = fmin3(lo, a2[1][c].y, a2[2][c].x); hi = fmax3(hi, a2[1][c].y, a2[2][c].x);
+            lo = fmin3(lo, a2[2][c].y, a2[3][c].x); hi = fmax3(hi, a2[2][c].y, a2[3][c].x);
+            lo = fminf(lo, a2[3][c].y); hi = fmaxf(hi, a2[3][c].y);
             const float wlo = warp_min(lo), whi = warp_max(hi);
             if (lane == 0) {
                 part[f] = wlo;
@@ -1090,11 +1123,7 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_GRAM_MIN_BLOCKS) fit_gram_ker
             }
         }
 #pragma unroll
-        for (int c = 0; c < NCOL; ++c) {
-            float t = (a[0][c] + a[1][c]) + (a[2][c] + a[3][c]);
-            t += (a[4][c] + a[5][c]) + (a[6][c] + a[7][c]);
-            red[c * GR_RED_W + lane] = t;
-        }
+        for (int c = 0; c < NCOL; ++c) red[c * GR_RED_W + lane] = colsum[c];
         __syncwarp();
         if (lane < NCOL) part[2 * NSC + lane] = gram_row_sum(red + lane * GR_RED_W);
         __syncthreads();  // the per-warp extrema and sums are visible, and every thread is done with the stage
@@ -1105,8 +1134,8 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_GRAM_MIN_BLOCKS) fit_gram_ker
                 late_draw = nblocks - stride - *(volatile int*)P.block_counter < stride / (BMFR_QR_LAZY_DIV > 0 ? BMFR_QR_LAZY_DIV : 1);
             if (!late_draw) qr_draw_next(P, M, sh, it, nblocks, stride);
         }
-        // every warp finishes the reductions itself: lane f < 6 owns scaled feature f, lane c < 12 the mean of column c + 1
-        float mn[NSC], inv[NSC], mean[NCOL];
+        // every warp finishes the reductions itself: lane f < NSC owns scaled feature f, lane c < NCOL the mean of column c + 1
+        float inv[NSC], mean[NCOL];
         {
             const int f = lane < NSC ? lane : 0, c = lane < NCOL ? lane : 0;
             float lo = sh.part[it & 1][0][f], hi = sh.part[it & 1][0][NSC + f], sum = sh.part[it & 1][0][2 * NSC + c];
@@ -1125,53 +1154,44 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_GRAM_MIN_BLOCKS) fit_gram_ker
             }
             const float m_raw = sum * (1.0f / BMFR_BLOCK_PIXELS);
 #pragma unroll
-            for (int k = 0; k < NSC; ++k) {
-                mn[k] = __shfl_sync(0xffffffffu, lo, k);
-                inv[k] = __shfl_sync(0xffffffffu, iv, k);
-            }
+            for (int k = 0; k < NSC; ++k) inv[k] = __shfl_sync(0xffffffffu, iv, k);
 #pragma unroll
             for (int k = 0; k < NCOL; ++k) mean[k] = __shfl_sync(0xffffffffu, m_raw, k);
-#pragma unroll
-            for (int k = 0; k < NSC; ++k) mean[NNS - 1 + k] = (mean[NNS - 1 + k] - mn[k]) * inv[k];  // mean of the scaled column (the noise averages to ~0)
-        }
-        // the solver needs the means to recover the intercept: one per lane, in the scratch of warp 0
-        if (warp == 0) {
-            float mv = 0.f;
-#pragma unroll
-            for (int k = 0; k < NCOL; ++k) mv = (lane == k) ? mean[k] : mv;
-            if (lane < NCOL) P.tri[((size_t)local * QR_COMPUTE_WARPS) * QR_TRI_G + ENTRIES + lane] = mv;
+            // the solver needs the means of the columns as the reference defines them (scaled: (a - min) * inv; the noise
+            // averages to ~0) to recover the intercept: one per lane, in the scratch of warp 0
+            const int fc = min(max(c - (NNS - 1), 0), NSC - 1);
+            const float lo_c = __shfl_sync(0xffffffffu, lo, fc), iv_c = __shfl_sync(0xffffffffu, iv, fc);
+            if (warp == 0 && lane < NCOL) {
+                const bool scaled = lane >= NNS - 1 && lane < NNS - 1 + NSC;
+                P.tri[((size_t)local * QR_COMPUTE_WARPS) * QR_TRI_G + ENTRIES + lane] = scaled ? (m_raw - lo_c) * iv_c : m_raw;
+            }
         }
 
-        // scale (bmfr.cl:538-541), first-touch noise on columns 1..9 (bmfr.cl:623-627; from the tile's fp32 rounding as in
-        // fit_qr_kernel), centre.  a2[h][c]: rows (2h, 2h+1) packed.
-        float2 a2[ROWS / 2][NCOL];
+        // centre on the raw block means, then scale (bmfr.cl:538-541; (a - min) inv - mean_scaled = (a - mean_raw) inv) and
+        // add the first-touch noise on columns 1..F-1 (bmfr.cl:623-627; from the tile's fp32 rounding as in fit_qr_kernel)
 #pragma unroll
-        for (int h = 0; h < ROWS / 2; ++h)
+        for (int c = 0; c < NCOL; ++c) {
+            const float2 m2 = dup2(mean[c]);
 #pragma unroll
-            for (int c = 0; c < NCOL; ++c) a2[h][c] = make_float2(a[2 * h][c], a[2 * h + 1][c]);
-#pragma unroll
-        for (int f = 0; f < NSC; ++f) {
-            const float2 mn2 = dup2(mn[f]), inv2 = dup2(inv[f]);
-#pragma unroll
-            for (int h = 0; h < ROWS / 2; ++h) a2[h][NNS - 1 + f] = fmul2(fsub2(a2[h][NNS - 1 + f], mn2), inv2);
+            for (int h = 0; h < ROWS / 2; ++h) a2[h][c] = fsub2(a2[h][c], m2);
         }
         {
             const float4* nz4 = reinterpret_cast<const float4*>(P.noise_f) + (size_t)warp * (NF - 1) * 2 * 32 + lane;
 #pragma unroll
             for (int c = 0; c < NF - 1; ++c) {
-                const float2 m2 = dup2(mean[c]);
+                const bool scaled = c >= NNS - 1;
+                const float2 inv2 = dup2(scaled ? inv[scaled ? c - (NNS - 1) : 0] : 1.f);
 #pragma unroll
                 for (int q = 0; q < ROWS / 4; ++q) {
                     const float4 nz = __ldg(nz4 + (c * 2 + q) * 32);
-                    a2[2 * q][c] = fsub2(fadd2(a2[2 * q][c], make_float2(nz.x, nz.y)), m2);
-                    a2[2 * q + 1][c] = fsub2(fadd2(a2[2 * q + 1][c], make_float2(nz.z, nz.w)), m2);
+                    if (scaled) {
+                        a2[2 * q][c] = ffma2(a2[2 * q][c], inv2, make_float2(nz.x, nz.y));
+                        a2[2 * q + 1][c] = ffma2(a2[2 * q + 1][c], inv2, make_float2(nz.z, nz.w));
+                    } else {
+                        a2[2 * q][c] = fadd2(a2[2 * q][c], make_float2(nz.x, nz.y));
+                        a2[2 * q + 1][c] = fadd2(a2[2 * q + 1][c], make_float2(nz.z, nz.w));
+                    }
                 }
-            }
-#pragma unroll
-            for (int c = NF - 1; c < NCOL; ++c) {
-                const float2 m2 = dup2(mean[c]);
-#pragma unroll
-                for (int h = 0; h < ROWS / 2; ++h) a2[h][c] = fsub2(a2[h][c], m2);
             }
         }
 
@@ -1240,9 +1260,8 @@ cudaError_t launch_reproject(const KParams& P, cudaStream_t st) {
         if (is_strip(P)) return launch_pdl(!P.plain_launch, reproject_tma_kernel<true>, grid, dim3(256), 0, st, P, M);
         return launch_pdl(!P.plain_launch, reproject_tma_kernel<false>, grid, dim3(256), 0, st, P, M);
     }
-    const int rows_per_cta = BMFR_REPROJECT_BY * BMFR_REPROJECT_PIXELS;
-    const dim3 grid((P.W + BMFR_REPROJECT_BX - 1) / BMFR_REPROJECT_BX, (P.k1_y1 - P.k1_y0 + rows_per_cta - 1) / rows_per_cta),
-        block(BMFR_REPROJECT_BX, BMFR_REPROJECT_BY);
+    const int bx = is_strip(P) ? BMFR_REPROJECT_STRIP_BX : BMFR_REPROJECT_BX, by = 256 / bx, rows_per_cta = by * BMFR_REPROJECT_PIXELS;
+    const dim3 grid((P.W + bx - 1) / bx, (P.k1_y1 - P.k1_y0 + rows_per_cta - 1) / rows_per_cta), block(bx, by);
     if (is_strip(P)) return launch_pdl(!P.plain_launch, reproject_kernel<true>, grid, block, 0, st, P);
     return launch_pdl(!P.plain_launch, reproject_kernel<false>, grid, block, 0, st, P);
 }
