@@ -87,6 +87,16 @@ __device__ __forceinline__ void stamp_end(const KParams& P, int k) {
     if (P.stamps != nullptr && threadIdx.x == 0 && threadIdx.y == 0) atomicMin(P.stamps + 2 * k + 1, ~globaltimer_ns());
 }
 
+// Sweep direction of the whole-image kernels.  The three kernels of a frame read the same 75 MB (normals, world positions,
+// accumulated colour) one after the other and the L2 holds the part touched last, so each kernel starts where its
+// predecessor finished: reprojection and post pass run down the image, the fit up (BMFR_ZIGZAG: and the next frame the other
+// way round, because the post pass of frame f ends where the reprojection of frame f + 1 finds its history).
+#ifndef BMFR_ZIGZAG
+#define BMFR_ZIGZAG 0
+#endif
+__device__ __forceinline__ bool sweep_down(int frame) { return !BMFR_ZIGZAG || (frame & 1) == 0; }
+__device__ __forceinline__ int sweep_row(const KParams& P, int i, int n) { return sweep_down(P.frame) ? i : n - 1 - i; }
+
 // Zone rows early and spread out: CTA row i of n (blockIdx.y, which the hardware hands out in ascending order) -> the row
 // it works on.  The Z zone rows take every k-th position from the start (k = n / Z), the interior rows fill the rest: the
 // zone CTAs' peer stores then drain over NVLink while interior CTAs compute (all zone CTAs at once would hold most of
@@ -174,6 +184,32 @@ __device__ __forceinline__ float ldg_stream(const float* p) {
     float v;
     asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
     return v;
+}
+// L2 eviction priorities (tuning switch BMFR_L2_HINTS): a frame's normals, world positions and
+// accumulated colour are read by all three kernels within ~100 us — "keep" asks the L2 to hold on to them; inputs that are
+// read exactly once are marked "once".  The operand is the descriptor createpolicy.fractional.L2::evict_* ... 1.0 produces.
+#ifndef BMFR_L2_HINTS
+#define BMFR_L2_HINTS 2
+#endif
+#define BMFR_L2_KEEP 0x14F0000000000000ull  // evict_last
+#define BMFR_L2_ONCE 0x12F0000000000000ull  // evict_first
+__device__ __forceinline__ float ldg_hint(const float* p, unsigned long long policy) {
+    float v;
+    asm("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(policy));  // read-only data: free to move
+    return v;
+}
+__device__ __forceinline__ void stg_hint(float* p, float v, unsigned long long policy) {
+    asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(policy) : "memory");
+}
+__device__ __forceinline__ f3 load_f3_hint(const float* __restrict__ b, unsigned int i, unsigned long long policy) {
+    const float* p = b + (size_t)(i * 3u);
+    return f3{ldg_hint(p, policy), ldg_hint(p + 1, policy), ldg_hint(p + 2, policy)};
+}
+__device__ __forceinline__ void store_f3_hint(float* __restrict__ b, unsigned int i, f3 v, unsigned long long policy) {
+    float* p = b + (size_t)(i * 3u);
+    stg_hint(p, v.x, policy);
+    stg_hint(p + 1, v.y, policy);
+    stg_hint(p + 2, v.z, policy);
 }
 __device__ __forceinline__ f3 load_f3_stream(const float* __restrict__ b, unsigned int i) {
 #if BMFR_STREAM_LOADS

@@ -371,7 +371,7 @@ __device__ __forceinline__ void prefetch_taps(const KParams& P, float2 pp) {
 template <bool STRIP, bool WIDE, int FS>
 __global__ void __launch_bounds__(256, BMFR_POST_MIN_BLOCKS) post_kernel(const __grid_constant__ KParams P) {
     __shared__ __align__(16) PostShared sh;
-    const int bx = blockIdx.x, by = P.by0 + (STRIP ? halo_row_order(P.halo_p, blockIdx.y, gridDim.y) : (int)blockIdx.y);
+    const int bx = blockIdx.x, by = P.by0 + (STRIP ? halo_row_order(P.halo_p, blockIdx.y, gridDim.y) : sweep_row(P, blockIdx.y, gridDim.y));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int x0 = bx * 32 - 16 + P.off_x, y0 = by * 32 - 16 + P.off_y;  // tile origin in image coordinates
 #if BMFR_POST_PREFETCH
@@ -713,7 +713,7 @@ template <bool STRIP, int FS>
 __global__ void __launch_bounds__(256, BMFR_POST_TMA_MIN_BLOCKS) post_tma_kernel(const __grid_constant__ KParams P, const __grid_constant__ PostMaps M) {
     extern __shared__ __align__(128) unsigned char post_smem[];
     PostStage& sh = *reinterpret_cast<PostStage*>(post_smem);
-    const int bx = blockIdx.x, by = P.by0 + (STRIP ? halo_row_order(P.halo_p, blockIdx.y, gridDim.y) : (int)blockIdx.y);
+    const int bx = blockIdx.x, by = P.by0 + (STRIP ? halo_row_order(P.halo_p, blockIdx.y, gridDim.y) : sweep_row(P, blockIdx.y, gridDim.y));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     TileGeom G;
     G.x0 = bx * 32 - 16 + P.off_x;
@@ -731,12 +731,21 @@ __global__ void __launch_bounds__(256, BMFR_POST_TMA_MIN_BLOCKS) post_tma_kernel
         // event already orders this launch.  Rows / columns outside the image (or the strip) arrive as zeros.
         const int c1 = G.y0 - 1 - P.row0;
         mbar_expect_tx(&sh.bar, PT_STAGE_TX);
+#if BMFR_L2_HINTS >= 2  // last readers of the reprojection's per-pixel outputs, only reader of the albedo
+        tma_load_tile_hint(&sh.pp[0][0], &M.pp, c_pp, c1, &sh.bar, BMFR_L2_ONCE);
+        tma_load_tile_hint(&sh.acc[0][0], &M.accept, c_u8, c1, &sh.bar, BMFR_L2_ONCE);
+        tma_load_tile(&sh.spp[0][0], &M.spp, c_u8, c1, &sh.bar);
+        tma_load_tile(&sh.nrm[0][0], &M.normals, c_rgb, c1, &sh.bar);
+        tma_load_tile(&sh.pos[0][0], &M.positions, c_rgb, c1, &sh.bar);
+        tma_load_tile_hint(&sh.alb[0][0], &M.albedo, c_rgb, c1, &sh.bar, BMFR_L2_ONCE);
+#else
         tma_load_tile(&sh.pp[0][0], &M.pp, c_pp, c1, &sh.bar);
         tma_load_tile(&sh.acc[0][0], &M.accept, c_u8, c1, &sh.bar);
         tma_load_tile(&sh.spp[0][0], &M.spp, c_u8, c1, &sh.bar);
         tma_load_tile(&sh.nrm[0][0], &M.normals, c_rgb, c1, &sh.bar);
         tma_load_tile(&sh.pos[0][0], &M.positions, c_rgb, c1, &sh.bar);
         tma_load_tile(&sh.alb[0][0], &M.albedo, c_rgb, c1, &sh.bar);
+#endif
     }
     pdl_wait();     // the fit of this frame is complete (weights, min/max)
     pdl_trigger();  // only now, so that "this frame's fit and reprojection are complete" also holds for the successor

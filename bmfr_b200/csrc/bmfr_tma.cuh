@@ -44,6 +44,15 @@ __device__ __forceinline__ void tma_load_tile(void* dst_smem, const CUtensorMap*
         : "memory");
 }
 
+__device__ __forceinline__ void tma_load_tile_hint(void* dst_smem, const CUtensorMap* map, int c0, int c1, unsigned long long* bar,
+                                                   unsigned long long policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+
 // ---- host side ----------------------------------------------------------------------------------------
 typedef CUresult (*BmfrEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                       const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
