@@ -66,6 +66,7 @@ SYMBOLS = {
     "bmfr_read_buffer": (_I, [_P, _I, _P, C.c_size_t]),
     "bmfr_get_stage_ms": (_I, [_P, _I, _F]),
     "bmfr_get_fused_kernel_busy_ms": (_I, [_P, _I, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "bmfr_get_fused_kernel_stamps": (_I, [_P, _I, C.POINTER(C.c_ulonglong)]),
     "bmfr_get_fused_kernel_ms": (_I, [_P, _I, _F]),
     "bmfr_kernel_launches": (C.c_longlong, [_P]),
     "bmfr_get_halo_plan": (_I, [_P, _I, C.POINTER(HaloPlan)]),

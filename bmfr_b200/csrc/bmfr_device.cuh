@@ -113,39 +113,84 @@ __device__ __forceinline__ int halo_row_order(const HaloK& h, int i, int n) {
     }
     return top + (i - placed);                    // the (i - placed)-th interior row
 }
+#ifndef BMFR_HALO_RELEASE_GPU
+#define BMFR_HALO_RELEASE_GPU 1
+#endif
+#ifndef BMFR_HALO_ACQUIRE_FENCE
+#define BMFR_HALO_ACQUIRE_FENCE 0
+#endif
 // Does the CTA that covers image rows [ya, yb) belong to the zone?
 __device__ __forceinline__ bool halo_in_zone(const HaloK& h, int ya, int yb) { return h.active && (ya < h.zone_y[0] || yb > h.zone_y[1]); }
 // Prologue of a zone CTA (all threads call it): wait for the neighbours' rows.  Bounded: after timeout_ns the context is
 // marked failed (flags[2], sticky) and the kernel goes on with whatever it finds; a failed context never signals.
-__device__ __forceinline__ void halo_poll(const HaloK& h) {
+//
+// No acquire fence follows the poll.  A fence.acq_rel (what __threadfence_system() is) ends in CCTL.IVALL: it drops the
+// whole L1 of the SM, under every co-resident CTA's tap gathers — with 40 % of a strip's CTAs in the zone that cost 19 us
+// of the reprojection's 118 and 25 us of the post pass's 144 at 8K over eight GPUs (profiles/r02_n8_timeline.md).  What
+// the fence would protect against is a stale L1 copy of a halo row.  There is none: the L1 is invalidated when a grid
+// starts, and within a grid nothing reads a neighbour-written row before this poll has seen the flag — interior CTAs
+// never touch such rows (that is what makes a CTA a zone CTA), zone CTAs poll first, and the fit and the TMA-staged
+// inputs of the post pass only read rows this context wrote itself.  The neighbour's rows are in this GPU's L2 (the
+// point of coherence for peer stores) before its flag is: it raises the flag behind a system-scope release.  The poll is
+// a volatile (strong, system-scope) load, the barrier orders the CTA's later loads after it, and an SM does not issue a
+// load ahead of the branch that depends on the polled value.
+// The flags only grow, so a zone CTA reads them once at its very start (halo_peek, thread 0: four independent loads whose L2
+// round trip hides behind the CTA's set-up and its wait for the predecessor grid) and polls only if that look was too early.
+struct HaloPeek {
+    unsigned int e0, e1, l0, l1;
+};
+__device__ __forceinline__ HaloPeek halo_peek(const HaloK& h, bool zone) {
+    HaloPeek k{0u, 0u, 0u, 0u};
+    if (zone && threadIdx.x == 0 && threadIdx.y == 0) {
+        volatile unsigned int* f = h.flags;
+        k.e0 = f[0]; k.e1 = f[1]; k.l0 = f[4]; k.l1 = f[5];
+    }
+    return k;
+}
+__device__ __forceinline__ void halo_poll(const HaloK& h, HaloPeek k) {
+#ifdef BMFR_DEBUG_NO_POLL  // timing experiments only: results are wrong
+    return;
+#endif
     if (threadIdx.x == 0 && threadIdx.y == 0 && (h.wait_early | h.wait_late) != 0) {
         volatile unsigned int* f = h.flags;
-        const unsigned long long t0 = globaltimer_ns();
-        for (;;) {
-            const bool a = !h.side_on[0] || (f[0] >= h.wait_early && f[4] >= h.wait_late);
-            const bool b = !h.side_on[1] || (f[1] >= h.wait_early && f[5] >= h.wait_late);
+        unsigned long long t0 = 0;
+        for (bool first = true;; first = false) {
+            unsigned int e0 = k.e0, e1 = k.e1, l0 = k.l0, l1 = k.l1;
+            if (!first) { e0 = f[0]; e1 = f[1]; l0 = f[4]; l1 = f[5]; }  // four independent loads: one L2 round trip
+            const bool a = !h.side_on[0] || (e0 >= h.wait_early && l0 >= h.wait_late);
+            const bool b = !h.side_on[1] || (e1 >= h.wait_early && l1 >= h.wait_late);
             if (a && b) break;
-            if (globaltimer_ns() - t0 > h.timeout_ns) {
+            const unsigned long long now = globaltimer_ns();
+            if (t0 == 0) t0 = now;
+            if (now - t0 > h.timeout_ns) {
                 f[2] = 1;
                 break;
             }
             __nanosleep(100);
         }
+#if BMFR_HALO_ACQUIRE_FENCE
         __threadfence_system();
+#endif
     }
     __syncthreads();
 }
 // Epilogue of a zone CTA (all threads call it, after their last store): the last zone CTA of the launch raises the flags.
+// A CTA that pushed rows counts itself with a system-scope RELEASE (its peer stores, ordered before thread 0 by the
+// barrier, are performed before the count; unlike a fence this carries no L1 invalidation); the last one to arrive reads the
+// count at the end of that release sequence, fences once (acquire + release) and stores the flags.
 __device__ __forceinline__ void halo_finish(const HaloK& h, bool pushed) {
-    __syncthreads();  // every thread's peer stores precede ...
+    __syncthreads();
     if (threadIdx.x == 0 && threadIdx.y == 0) {
-        // ... this fence (cumulative over what the barrier ordered before it): visible system-wide before the count.  A zone
-        // CTA that only read halo rows has nothing to publish.
-        if (pushed) __threadfence_system();
-        const unsigned int done = atomicAdd(h.done_counter, 1u);
+        unsigned int done;
+#if BMFR_HALO_RELEASE_GPU
+        if (pushed) asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(done) : "l"(h.done_counter) : "memory");
+#else
+        if (pushed) asm volatile("atom.add.release.sys.global.u32 %0, [%1], 1;" : "=r"(done) : "l"(h.done_counter) : "memory");
+#endif
+        else done = atomicAdd(h.done_counter, 1u);  // only read halo rows: nothing to publish
         if (done + 1 == h.zone_ctas) {
-            *h.done_counter = 0;  // for the next launch (ordered after this one by the stream)
             __threadfence_system();
+            *h.done_counter = 0;  // for the next launch (ordered after this one by the stream)
             if (*(volatile unsigned int*)(h.flags + 2) == 0) {
 #pragma unroll
                 for (int s = 0; s < 2; ++s)
@@ -157,6 +202,9 @@ __device__ __forceinline__ void halo_finish(const HaloK& h, bool pushed) {
 }
 // Does a CTA that covers image rows [ya, yb) store any row a neighbour mirrors?
 __device__ __forceinline__ bool halo_cta_pushes(const HaloK& h, int ya, int yb) {
+#ifdef BMFR_DEBUG_NO_PUSH  // timing experiments only: results are wrong
+    return false;
+#endif
     return (h.side_on[0] && ya < h.push_y1[0] && yb > h.push_y0[0]) || (h.side_on[1] && ya < h.push_y1[1] && yb > h.push_y0[1]);
 }
 // Index of image pixel (x, y) in the neighbour's buffers on side s, or -1 when the row is not mirrored there.

@@ -35,7 +35,9 @@
 #ifndef BMFR_REPROJECT_BX
 #define BMFR_REPROJECT_BX 64  // CTA = BX x (256 / BX) threads
 #endif
+#ifndef BMFR_REPROJECT_STRIP_MIN_BLOCKS
 #define BMFR_REPROJECT_STRIP_MIN_BLOCKS 4
+#endif
 #define BMFR_REPROJECT_STRIP_BX 32
 // 1: a thread walks down four vertically adjacent pixels and hands the lower tap row of one to the next (K1Carry; 25 %
 // fewer tap loads).  Measured at 1080p (profiles/r02_m_*): 69.8 us against 52 us — the eight warps of a CTA then work on
@@ -106,6 +108,9 @@ struct ReprojectPushStage<false, WITH_RGB> {
 // neighbours that mirror them.  Needs W % 32 == 0 (full tiles, 16-byte aligned row segments).
 __device__ __forceinline__ void reproject_push_rows(const KParams& P, const float (*rgb)[96], const unsigned char (*spp)[32], int x0, int cta_y0, int tid) {
     const HaloK& h = P.halo_r;
+#ifdef BMFR_DEBUG_NO_PUSH
+    return;
+#endif
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
         if (!h.side_on[s]) continue;
@@ -165,6 +170,12 @@ __global__ void __launch_bounds__(256, STRIP ? BMFR_REPROJECT_STRIP_MIN_BLOCKS :
     // context's stream — then it is this grid's programmatic-launch primary, and if it triggers its dependents early
     // its writes are only guaranteed visible after the wait.  So the wait comes first; what the programmatic launch
     // still buys is that this grid's CTAs are resident when the previous frame's post pass retires.
+    const int x = blockIdx.x * BX + threadIdx.x;
+    const int cta_y0 = P.k1_y0 + (STRIP ? halo_row_order(P.halo_r, blockIdx.y, gridDim.y) : sweep_row(P, blockIdx.y, gridDim.y)) * CTA_ROWS;
+    // strips: a CTA near a strip edge waits for the neighbours' rows of the previous frame before it gathers from them; its
+    // first look at the flags is in flight across the wait for the predecessor
+    const bool zone = STRIP && halo_in_zone(P.halo_r, cta_y0, cta_y0 + CTA_ROWS);
+    const HaloPeek peek = halo_peek(P.halo_r, zone);
     pdl_wait();
     // after the wait, so that "everything before this grid is complete" is transitive: the fit requests its first
     // normals / positions tiles (the caller's inputs) before its own wait
@@ -173,25 +184,21 @@ __global__ void __launch_bounds__(256, STRIP ? BMFR_REPROJECT_STRIP_MIN_BLOCKS :
     if (P.stamps_next != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.y == 0 && threadIdx.x < 6) P.stamps_next[threadIdx.x] = ~0ull;
     reproject_noise_tile(P, threadIdx.y * BX + threadIdx.x);
     __shared__ __align__(16) ReprojectPushStage<STRIP, true> push_stage;
-    const int x = blockIdx.x * BX + threadIdx.x;
-    const int cta_y0 = P.k1_y0 + (STRIP ? halo_row_order(P.halo_r, blockIdx.y, gridDim.y) : sweep_row(P, blockIdx.y, gridDim.y)) * CTA_ROWS;
     // thread (x, ty) takes rows ty, ty + BY, ty + 2 BY, ty + 3 BY of the CTA's rows (BMFR_REPROJECT_CARRY: rows 4 ty .. 4 ty + 3)
     const int ystep = BMFR_REPROJECT_CARRY ? 1 : BY;
     const int ybase = cta_y0 + (BMFR_REPROJECT_CARRY ? BMFR_REPROJECT_PIXELS : 1) * threadIdx.y;
-    // strips: a CTA near a strip edge waits for the neighbours' rows of the previous frame before it gathers from them
-    const bool zone = STRIP && halo_in_zone(P.halo_r, cta_y0, cta_y0 + CTA_ROWS);
-    if (zone) halo_poll(P.halo_r);
     int ylo = P.k1_y0, yhi = P.k1_y1;
     if (STRIP) {  // rows outside the strip + halo cannot be reprojected here: flag and skip them
         if (ylo < P.row0 || yhi > P.row1) *P.oob_flag = 1;
         ylo = max(ylo, P.row0);
         yhi = min(yhi, P.row1);
     }
+    // software pipeline over the thread's pixels: position of pixel k+1 in flight while pixel k runs its
+    // reprojection -> tap gather chain
+    f3 wp_next = make_f3(0.f, 0.f, 0.f);
+    if (x < P.W && ybase >= ylo && ybase < yhi) wp_next = load_cur(P.cur_positions, pix_index(P, x, ybase));
+    if (zone) halo_poll(P.halo_r, peek);  // (this frame's own inputs never wait for a neighbour)
     if (x < P.W) {
-        // software pipeline over the thread's pixels: position of pixel k+1 in flight while pixel k runs its
-        // reprojection -> tap gather chain
-        f3 wp_next = make_f3(0.f, 0.f, 0.f);
-        if (ybase >= ylo && ybase < yhi) wp_next = load_cur(P.cur_positions, pix_index(P, x, ybase));
         K1Carry carry;
         carry.ry = -1;
 #pragma unroll 1
@@ -262,7 +269,7 @@ __global__ void __launch_bounds__(256, BMFR_REPROJECT_STRIP_MIN_BLOCKS) reprojec
     reproject_noise_tile(P, threadIdx.x);
     __syncthreads();  // the barrier's initialisation is visible
     const bool zone = STRIP && halo_in_zone(P.halo_r, y0, y0 + 32);
-    if (zone) halo_poll(P.halo_r);
+    if (zone) halo_poll(P.halo_r, halo_peek(P.halo_r, zone));
     int ylo = P.k1_y0, yhi = P.k1_y1;
     if (STRIP) {  // rows outside the strip + halo cannot be reprojected here: flag and skip them
         if (ylo < P.row0 || yhi > P.row1) *P.oob_flag = 1;

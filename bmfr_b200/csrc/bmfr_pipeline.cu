@@ -431,8 +431,12 @@ static void fill_halo(bmfr_ctx* c, KParams& P) {
         h.signal_value = f + 1;
         h.done_counter = c->d_flags + 8 + late;
         h.timeout_ns = timeout_ns;
-        h.zone_y[0] = c->peer[0].connected ? g.own_y0 + c->prm.halo_rows : -(1 << 30);
-        h.zone_y[1] = c->peer[1].connected ? g.own_y1 - c->prm.halo_rows : (1 << 30);
+        // The zone: rows whose CTAs can gather from halo rows or own rows a neighbour mirrors.  The reprojection mirrors
+        // halo_rows rows; the post pass gathers from, and mirrors, halo_rows - 32 (halo_rows_for) around the owned rows +- 1.
+        const int h2 = c->prm.halo_rows > 32 ? c->prm.halo_rows - 32 : 0;
+        const int zone_rows = late ? (h2 + 2 < c->prm.halo_rows ? h2 + 2 : c->prm.halo_rows) : c->prm.halo_rows;
+        h.zone_y[0] = c->peer[0].connected ? g.own_y0 + zone_rows : -(1 << 30);
+        h.zone_y[1] = c->peer[1].connected ? g.own_y1 - zone_rows : (1 << 30);
         for (int s = 0; s < 2; ++s) {
             const bmfr_ctx::Peer& pr = c->peer[s];
             h.side_on[s] = pr.connected ? 1 : 0;
@@ -917,6 +921,20 @@ int bmfr_get_fused_kernel_busy_ms(bmfr_ctx* c, int frame, float ms[BMFR_FUSED_KE
     BMFR_CUDA_TRY(cudaMemcpy(t, c->d_stamps + (size_t)slot * 6, sizeof(t), cudaMemcpyDeviceToHost));
     for (int k = 0; k < 3; ++k) ms[k] = (float)((double)(~t[2 * k + 1] - t[2 * k]) * 1e-6);
     if (frame_ms) *frame_ms = (float)((double)(~t[5] - t[0]) * 1e-6);
+    return BMFR_OK;
+}
+
+int bmfr_get_fused_kernel_stamps(bmfr_ctx* c, int frame, unsigned long long ns[2 * BMFR_FUSED_KERNEL_COUNT]) {
+    if (!c || !ns) return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_get_fused_kernel_stamps: null argument");
+    if (!c->d_stamps) return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_get_fused_kernel_stamps: needs a FUSED context created with profile=2");
+    int slot = -1;
+    for (int i = 0; i < kProfileSlots; ++i)
+        if (c->stamp_frame[i] == frame) slot = i;
+    if (slot < 0) return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_get_fused_kernel_stamps: frame %d not recorded", frame);
+    int st = bmfr_sync(c);
+    if (st != 0) return st;
+    BMFR_CUDA_TRY(cudaMemcpy(ns, c->d_stamps + (size_t)slot * 6, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 3; ++k) ns[2 * k + 1] = ~ns[2 * k + 1];  // the end is kept as its complement (atomicMin)
     return BMFR_OK;
 }
 

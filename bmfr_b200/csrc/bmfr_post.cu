@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(256, BMFR_POST_MIN_BLOCKS) post_kernel(const _
     stamp_begin(P, 2);
     // strips: a CTA near a strip edge waits for the neighbours' accumulated colour / TAA rows of the previous frame
     const bool zone = STRIP && halo_in_zone(P.halo_p, y0 - 1, y0 + 33);
-    if (zone) halo_poll(P.halo_p);
+    if (zone) halo_poll(P.halo_p, halo_peek(P.halo_p, zone));
 
 
     load_coefficients<FS>(P, sh.coef, bx, by, warp, lane);
@@ -592,6 +592,9 @@ __device__ __forceinline__ void stage_result(PostStage& sh, const TileGeom& G, i
 // All threads of a zone CTA, after a barrier: the tile's rows that a neighbour mirrors, both buffers.
 __device__ __forceinline__ void post_push_rows(const KParams& P, const PostStage& sh, const TileGeom& G, int tid) {
     const HaloK& h = P.halo_p;
+#ifdef BMFR_DEBUG_NO_PUSH
+    return;
+#endif
     const int xa = max(G.x0, 0), xb = min(G.x0 + 32, P.W);  // the tile's columns inside the image (both even)
     const int per_row = (xb - xa) * 3 / 2;                  // 8-byte items per row and buffer
     if (per_row <= 0) return;
@@ -747,12 +750,14 @@ __global__ void __launch_bounds__(256, BMFR_POST_TMA_MIN_BLOCKS) post_tma_kernel
         tma_load_tile(&sh.alb[0][0], &M.albedo, c_rgb, c1, &sh.bar);
 #endif
     }
+    // strips: a CTA near a strip edge waits for the neighbours' accumulated colour / TAA rows of the previous frame; its
+    // first look at the flags is in flight across the wait for the fit
+    const bool zone = STRIP && halo_in_zone(P.halo_p, G.y0 - 1, G.y0 + 33);
+    const HaloPeek peek = halo_peek(P.halo_p, zone);
     pdl_wait();     // the fit of this frame is complete (weights, min/max)
     pdl_trigger();  // only now, so that "this frame's fit and reprojection are complete" also holds for the successor
     stamp_begin(P, 2);
-    // strips: a CTA near a strip edge waits for the neighbours' accumulated colour / TAA rows of the previous frame
-    const bool zone = STRIP && halo_in_zone(P.halo_p, G.y0 - 1, G.y0 + 33);
-    if (zone) halo_poll(P.halo_p);
+    if (zone) halo_poll(P.halo_p, peek);
 
     load_coefficients<FS>(P, sh.coef, bx, by, warp, lane);
     __syncthreads();  // the coefficients and the barrier's initialisation are visible

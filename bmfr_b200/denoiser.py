@@ -166,6 +166,12 @@ class Denoiser:
         _lib.check(self.lib.bmfr_get_fused_kernel_busy_ms(self._h, frame, ms, C.byref(total)))
         return dict(zip(self.fused_kernels, ms)), float(total.value)
 
+    def fused_kernel_stamps(self, frame):
+        """[(first CTA start, last CTA end)] of reproject / fit / post in ns of the device's globaltimer; FUSED, profile=2."""
+        ns = (C.c_ulonglong * 6)()
+        _lib.check(self.lib.bmfr_get_fused_kernel_stamps(self._h, frame, ns))
+        return [(int(ns[2 * k]), int(ns[2 * k + 1])) for k in range(3)]
+
     @property
     def kernel_launches(self):
         return int(self.lib.bmfr_kernel_launches(self._h))

@@ -345,6 +345,41 @@ def bench_sharded(args, workload, frames):
                     "what": "rank 0's strip: bytes of the rows it owns / the kernel's mean launch duration on rank 0"}
         ctx = replace_ctx(ctx, overlap_frames=overlap)
 
+    # timeline of the timed configuration (overlapped, connected) from the kernels' own globaltimer stamps (profile = 2),
+    # every rank, and next to it the same strip without neighbours (what the strip geometry alone costs: halo rows
+    # reprojected twice, partial tiles at the strip edges); the difference is the exchange
+    timeline = None
+    if args.mode == "fused" and exchange == "p2p":
+        def stamps_summary(c):
+            run_sequence(c)
+            run_sequence(c)
+            c.d.sync()
+            t = np.array([[x for pair in c.d.fused_kernel_stamps(f) for x in pair] for f in range(8, frames)], dtype=np.float64) * 1e-3
+            r0 = t[:, 0:1]
+            rel = (t - r0).mean(axis=0)
+            return [float(np.diff(t[:, 0]).mean())] + [float(v) for v in rel[1:]] + [float((t[:, 2 * k + 1] - t[:, 2 * k]).mean()) for k in range(3)]
+        ctx = replace_ctx(ctx, overlap_frames=overlap, profile=2)
+        mine = stamps_summary(ctx)
+        ctx.d.sync()
+        torch.cuda.synchronize()
+        dist.barrier()
+        lone = StripContext(w, h, strips[rank], halo, local, sp, args.mode, fit=fit, overlap_frames=overlap, profile=2)
+        try:
+            alone = stamps_summary(lone)
+        except Exception:  # (stale halo rows can trip the out-of-rows flag; timing only)
+            alone = [float("nan")] * 9
+        lone.close()
+        both = torch.tensor([mine, alone], device="cuda", dtype=torch.float64)
+        gathered = [torch.zeros_like(both) for _ in range(world)]
+        dist.all_gather(gathered, both)
+        keys = ("period", "reproject_end", "fit_start", "fit_end", "post_start", "post_end", "reproject_busy", "fit_busy", "post_busy")
+        timeline = {"unit": "us", "what": "per rank, mean over frames 8.. of one pass: frame period (start of reprojection to the next one) "
+                    "and first-CTA-start / last-CTA-end of the three kernels relative to the start of the frame's reprojection; "
+                    "'connected' = the timed configuration, 'alone' = the same strip without neighbours",
+                    "connected": {k: [round(float(g[0][i]), 1) for g in gathered] for i, k in enumerate(keys)},
+                    "alone": {k: [round(float(g[1][i]), 1) for g in gathered] for i, k in enumerate(keys)}}
+        ctx = replace_ctx(ctx, overlap_frames=overlap)
+
     # end to end: every rank uploads its strip of each frame from pinned host memory and reads its rows of the
     # result back, through the C ABI's host entry (bounded to the first frames of the sequence to bound pinned memory)
     e2e = None
@@ -388,7 +423,7 @@ def bench_sharded(args, workload, frames):
             "run": {"mode": args.mode, "overlap_frames": overlap, "fit_method": fit, "strips": strips, "halo_rows": halo,
                     "exchange": ("in-kernel peer stores of the state halo rows over NVLink (CUDA IPC mappings), device-side flags"
                                  if exchange == "p2p" else "NCCL send/recv of state halo rows, neighbours only")},
-            "parity": parity, "in_order": in_order, "kernels": kernels, "roofline": roofline,
+            "parity": parity, "in_order": in_order, "kernels": kernels, "roofline": roofline, "timeline": timeline,
             "halo_bytes_per_frame_rank0": halo_bytes, "gpu_launches": int(launches),
             "cpu_baseline": None, "e2e": e2e, "clocks": clock_summary,
         }

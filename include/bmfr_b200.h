@@ -233,6 +233,11 @@ int bmfr_get_fused_kernel_ms(bmfr_ctx* ctx, int frame, float ms[BMFR_FUSED_KERNE
  * above it contains no launch gap and the kernels may overlap; frame_ms (may be NULL): first CTA of the reprojection to
  * last CTA of the post pass. */
 int bmfr_get_fused_kernel_busy_ms(bmfr_ctx* ctx, int frame, float ms[BMFR_FUSED_KERNEL_COUNT], float* frame_ms);
+/* The stamps behind it: ns[2k] = start of the first CTA, ns[2k + 1] = end of the last CTA of kernel k of that frame, in
+ * nanoseconds of the device's globaltimer (one clock per GPU: comparable between the frames and contexts of one device,
+ * not between devices).  With them a caller draws the timeline of a chained / overlapped run — the stand-in for the
+ * per-kernel CL_PROFILING_COMMAND_START / _END pairs the reference's GPUTimer reads (CLUtils.hpp:296-311). */
+int bmfr_get_fused_kernel_stamps(bmfr_ctx* ctx, int frame, unsigned long long ns[2 * BMFR_FUSED_KERNEL_COUNT]);
 /* Number of kernels this library has launched on the context so far. */
 long long bmfr_kernel_launches(const bmfr_ctx* ctx);
 
