@@ -137,6 +137,15 @@ def test_busy_stamps_do_not_change_results_and_are_plausible():
                     assert set(busy) == set(d.fused_kernels)
                     assert all(0.0 < v < 5.0 for v in busy.values()), busy
                     assert max(busy.values()) <= span <= sum(busy.values()) + 1.0, (busy, span)
+                    # the stamps behind them: start <= end per kernel, the chain R -> F -> P starts in that order, and
+                    # their differences are the busy times
+                    st = d.fused_kernel_stamps(f)
+                    assert all(a <= b for a, b in st) and st[0][0] <= st[1][0] <= st[2][0], st
+                    for (a, b), v in zip(st, busy.values()):
+                        assert abs((b - a) * 1e-6 - v) < 1e-3
+                    if f > 1:  # one clock for all frames of a device: frames follow each other
+                        assert st[0][0] > prev_start
+                    prev_start = st[0][0]
     for k in outs[0]:
         assert util.bits_equal(outs[0][k], outs[2][k]), k
 
