@@ -175,9 +175,9 @@ __device__ __forceinline__ void weighted_sum_px4(const f3 (&n)[4], const f3 (&p)
 
 // The coefficients of the 3x3 block neighbourhood -> shared memory: warp w takes neighbour w (warp 0 also the ninth).
 template <int FS>
-__device__ __forceinline__ void load_coefficients(const KParams& P, float (*coef)[PT_COEF], int bx, int by, int warp, int lane) {
+__device__ __forceinline__ void load_coefficients(const KParams& P, float (*coef)[PT_COEF], int bx, int by, int warp, int lane, int nwarps = 8) {
     using PC = PostCoef<FS>;
-    for (int nb = warp; nb < 9; nb += 8) {
+    for (int nb = warp; nb < 9; nb += nwarps) {
         const int gx = bx + nb % 3 - 1, gy = by + nb / 3 - 1;
         if (gx < 0 || gx >= P.blocks_x || gy < 0 || gy >= P.blocks_y) continue;
         const size_t g = (size_t)gy * P.blocks_x + gx;
@@ -525,18 +525,22 @@ __global__ void __launch_bounds__(256, BMFR_POST_MIN_BLOCKS) post_kernel(const _
 #define PT_PP_W 72    // floats per staged row of prev_pixels: 34 float2 + 2 floats of shift
 #define PT_U8_W 64    // bytes per staged row of accept / spp: 34 + up to 15 bytes of shift
 
-struct __align__(128) PostStage {  // every TMA destination starts on a 128-byte boundary
-    float nrm[PT_HALO][PT_RGB_W]; char pad0[32];
-    float pos[PT_HALO][PT_RGB_W]; char pad1[32];
-    float alb[PT_HALO][PT_RGB_W]; char pad2[32];  // albedo, then (cell by cell) the tone-mapped colour as YCoCg
-    float pp[PT_HALO][PT_PP_W];   char pad3[64];
-    unsigned char acc[PT_HALO][PT_U8_W];
-    unsigned char spp[PT_HALO][PT_U8_W];
+// A tile is 32 pixels wide and ROWS (32 or 16) high; the stage holds it with its one-pixel ring: HY = ROWS + 2 rows.
+template <int HY_>
+struct __align__(128) PostStageT {  // every TMA destination starts on a 128-byte boundary
+    static constexpr int HY = HY_;
+    static constexpr int TX = 3 * HY_ * PT_RGB_W * 4 + HY_ * PT_PP_W * 4 + 2 * HY_ * PT_U8_W;  // bytes of the six bulk copies
+    float nrm[HY_][PT_RGB_W]; char pad0[32];
+    float pos[HY_][PT_RGB_W]; char pad1[32];
+    float alb[HY_][PT_RGB_W]; char pad2[32];  // albedo, then (cell by cell) the tone-mapped colour as YCoCg
+    float pp[HY_][PT_PP_W];   char pad3[64];
+    unsigned char acc[HY_][PT_U8_W];
+    unsigned char spp[HY_][PT_U8_W];
     float coef[9][PT_COEF];
     unsigned long long bar;
+    static_assert(sizeof(float[HY_][PT_RGB_W]) % 128 == 96 && sizeof(float[HY_][PT_PP_W]) % 128 == 64 && (HY_ * PT_U8_W) % 128 == 0,
+                  "TMA destinations must stay 128-byte aligned");
 };
-static_assert(sizeof(float[PT_HALO][PT_RGB_W]) % 128 == 96 && sizeof(float[PT_HALO][PT_PP_W]) % 128 == 64, "TMA destinations must stay 128-byte aligned");
-#define PT_STAGE_TX (3 * PT_HALO * PT_RGB_W * 4 + PT_HALO * PT_PP_W * 4 + 2 * PT_HALO * PT_U8_W)
 
 struct PostMaps {
     CUtensorMap normals, positions, albedo, pp, accept, spp;
@@ -551,23 +555,26 @@ __device__ __forceinline__ f3 cell_f3(const float (*buf)[PT_RGB_W], const TileGe
     const float* p = &buf[hy][G.sh_rgb + 3 * hx];
     return make_f3(p[0], p[1], p[2]);
 }
-__device__ __forceinline__ void put_cell_i(PostStage& sh, const TileGeom& G, int hx, int hy, f3 v) {
+template <class SH>
+__device__ __forceinline__ void put_cell_i(SH& sh, const TileGeom& G, int hx, int hy, f3 v) {
     float* p = &sh.alb[hy][G.sh_rgb + 3 * hx];
     p[0] = v.x; p[1] = v.y; p[2] = v.z;
 }
 // put_ycc() for the interleaved cells: the value of image pixel (x,y) also fills the out-of-image cells whose
 // nearest in-image pixel it is (nobody reads an albedo there).
-__device__ __forceinline__ void put_ycc_i(PostStage& sh, const KParams& P, const TileGeom& G, int hx, int hy, int x, int y, f3 v) {
+template <class SH>
+__device__ __forceinline__ void put_ycc_i(SH& sh, const KParams& P, const TileGeom& G, int hx, int hy, int x, int y, f3 v) {
     put_cell_i(sh, G, hx, hy, v);
     const int ex = (x == 0) ? -1 : (x == P.W - 1) ? 1 : 0;
     const int ey = (y == 0) ? -1 : (y == P.H - 1) ? 1 : 0;
     if ((ex | ey) == 0) return;
-    const bool okx = ex != 0 && (unsigned)(hx + ex) < PT_HALO, oky = ey != 0 && (unsigned)(hy + ey) < PT_HALO;
+    const bool okx = ex != 0 && (unsigned)(hx + ex) < PT_HALO, oky = ey != 0 && (unsigned)(hy + ey) < SH::HY;
     if (okx) put_cell_i(sh, G, hx + ex, hy, v);
     if (oky) put_cell_i(sh, G, hx, hy + ey, v);
     if (okx && oky) put_cell_i(sh, G, hx + ex, hy + ey, v);
 }
-__device__ __forceinline__ PixelIn load_pixel_staged(const PostStage& sh, const KParams& P, const TileGeom& G, int hx, int hy, int x, int y) {
+template <class SH>
+__device__ __forceinline__ PixelIn load_pixel_staged(const SH& sh, const KParams& P, const TileGeom& G, int hx, int hy, int x, int y) {
     PixelIn in;
     in.lp = pix_index(P, x, y);
     in.n = cell_f3(sh.nrm, G, hx, hy);
@@ -581,16 +588,20 @@ __device__ __forceinline__ PixelIn load_pixel_staged(const PostStage& sh, const 
 // Zone CTAs of a strip (HaloK) do not send a mirrored row pixel by pixel: a pixel's accumulated colour goes into its own
 // (already consumed) normal cell, its TAA result into its position cell, and after the last pixel the CTA sends whole row
 // segments as 8-byte peer stores (post_push_rows) — 4-byte stores at a 12-byte stride make poor NVLink packets.
-__device__ __forceinline__ void stage_accum(PostStage& sh, const TileGeom& G, int hx, int hy, f3 v) {
+template <class SH>
+__device__ __forceinline__ void stage_accum(SH& sh, const TileGeom& G, int hx, int hy, f3 v) {
     float* p = &sh.nrm[hy][G.sh_rgb + 3 * hx];
     p[0] = v.x; p[1] = v.y; p[2] = v.z;
 }
-__device__ __forceinline__ void stage_result(PostStage& sh, const TileGeom& G, int hx, int hy, f3 v) {
+template <class SH>
+__device__ __forceinline__ void stage_result(SH& sh, const TileGeom& G, int hx, int hy, f3 v) {
     float* p = &sh.pos[hy][G.sh_rgb + 3 * hx];
     p[0] = v.x; p[1] = v.y; p[2] = v.z;
 }
 // All threads of a zone CTA, after a barrier: the tile's rows that a neighbour mirrors, both buffers.
-__device__ __forceinline__ void post_push_rows(const KParams& P, const PostStage& sh, const TileGeom& G, int tid) {
+template <class SH>
+__device__ __forceinline__ void post_push_rows(const KParams& P, const SH& sh, const TileGeom& G, int tid) {
+    constexpr int ROWS = SH::HY - 2, THREADS = 8 * ROWS;
     const HaloK& h = P.halo_p;
 #ifdef BMFR_DEBUG_NO_PUSH
     return;
@@ -601,9 +612,9 @@ __device__ __forceinline__ void post_push_rows(const KParams& P, const PostStage
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
         if (!h.side_on[s]) continue;
-        const int ya = max(h.push_y0[s], G.y0), yb = min(h.push_y1[s], G.y0 + 32);
+        const int ya = max(h.push_y0[s], G.y0), yb = min(h.push_y1[s], G.y0 + ROWS);
         const int items = (yb - ya) * per_row * 2;
-        for (int i = tid; i < items; i += 256) {
+        for (int i = tid; i < items; i += THREADS) {
             const int which = i / ((yb - ya) * per_row), j = i % ((yb - ya) * per_row);
             const int y = ya + j / per_row, k = j % per_row;
             const float* src = (which ? &sh.pos[y - G.y0 + 1][0] : &sh.nrm[y - G.y0 + 1][0]) + G.sh_rgb + 3 * (xa - G.x0 + 1);
@@ -614,8 +625,8 @@ __device__ __forceinline__ void post_push_rows(const KParams& P, const PostStage
 }
 
 // One pixel whose inputs are staged: ring pixels, and the pixels of a pair cut by a strip or image edge.
-template <bool STRIP, int FS>
-__device__ __forceinline__ bool staged_pixel(PostStage& sh, const KParams& P, const TileGeom& G, const float* cf, int hx, int hy, int x, int y,
+template <bool STRIP, int FS, class SH>
+__device__ __forceinline__ bool staged_pixel(SH& sh, const KParams& P, const TileGeom& G, const float* cf, int hx, int hy, int x, int y,
                                              bool store, bool own, f3& hist, bool zone) {
     const PixelIn in = load_pixel_staged(sh, P, G, hx, hy, x, y);
     const f3 filtered = weighted_sum_px<FS>(in.n, in.p, cf);
@@ -643,8 +654,8 @@ __device__ __forceinline__ TapGeom tap_geom(float2 pp) {
 // accumulate_filtered_data (bmfr.cl:778-849) and the TAA history sample (bmfr.cl:884-965) of one pixel from taps that
 // are already in registers: a0 / r0 = the footprint's upper row (dx = 0, 1) of accumulated colour / TAA history, a1 / r1
 // its lower row.  Same operation order as accumulate_filtered_px() / history_sample().
-template <bool STRIP>
-__device__ __forceinline__ bool resolve_pixel(PostStage& sh, const KParams& P, const TileGeom& G, const PixelIn& in, const TapGeom& t, f3 filtered,
+template <bool STRIP, class SH>
+__device__ __forceinline__ bool resolve_pixel(SH& sh, const KParams& P, const TileGeom& G, const PixelIn& in, const TapGeom& t, f3 filtered,
                                               const f3 (&a0)[2], const f3 (&a1)[2], const f3 (&r0)[2], const f3 (&r1)[2], int hx, int hy, int x, int y,
                                               bool own, f3& hist, bool zone) {
     f3 prev = make_f3(0.f, 0.f, 0.f);
@@ -706,21 +717,37 @@ __device__ __forceinline__ bool resolve_pixel(PostStage& sh, const KParams& P, c
 }
 
 #ifndef BMFR_POST_TMA_MIN_BLOCKS
-#define BMFR_POST_TMA_MIN_BLOCKS 3
+#define BMFR_POST_TMA_MIN_BLOCKS 3  // per SM for 32-row tiles; 16-row tiles: twice as many
+#endif
+#ifndef BMFR_POST_SMEM_PAD
+#define BMFR_POST_SMEM_PAD 0  // extra dynamic shared memory per CTA of the whole-image instantiation: fewer CTAs per SM, more L1
+#endif
+#ifndef BMFR_POST_TILE_ROWS
+// Tile height of the whole-image instantiation.  Measured at 1080p (profiles/r02 r3a): 16 (six 128-thread CTAs per SM, or
+// five / four with more L1 through BMFR_POST_SMEM_PAD) 63.8 / 65.5 / 71.4 us against 57.7 us for 32 — 200 instead of 132 ring
+// pixels per block and twice the per-CTA set-up cost more than the finer interleaving of the CTAs' waits gives.
+#define BMFR_POST_TILE_ROWS 32
 #endif
 #ifndef BMFR_POST_WS4
 #define BMFR_POST_WS4 0
 #endif
 
-template <bool STRIP, int FS>
-__global__ void __launch_bounds__(256, BMFR_POST_TMA_MIN_BLOCKS) post_tma_kernel(const __grid_constant__ KParams P, const __grid_constant__ PostMaps M) {
+// ROWS = 32 (default): one CTA of 256 threads per block, three per SM.  ROWS = 16 (tuning switch BMFR_POST_TILE_ROWS, slower):
+// one CTA of 128 threads per half block, six per SM — the same 24 warps in six independent groups.
+template <bool STRIP, int FS, int ROWS>
+__global__ void __launch_bounds__(8 * ROWS, BMFR_POST_TMA_MIN_BLOCKS * 32 / ROWS) post_tma_kernel(const __grid_constant__ KParams P, const __grid_constant__ PostMaps M) {
+    static_assert(ROWS == 32 || ROWS == 16, "a tile is a block or half a block");
+    using Stage = PostStageT<ROWS + 2>;
+    constexpr int HY = ROWS + 2, THREADS = 8 * ROWS;
     extern __shared__ __align__(128) unsigned char post_smem[];
-    PostStage& sh = *reinterpret_cast<PostStage*>(post_smem);
-    const int bx = blockIdx.x, by = P.by0 + (STRIP ? halo_row_order(P.halo_p, blockIdx.y, gridDim.y) : sweep_row(P, blockIdx.y, gridDim.y));
+    Stage& sh = *reinterpret_cast<Stage*>(post_smem);
+    const int trow = STRIP ? halo_row_order(P.halo_p, blockIdx.y, gridDim.y) : sweep_row(P, blockIdx.y, gridDim.y);  // tile row of the launch
+    const int half = ROWS == 32 ? 0 : (trow & 1);
+    const int bx = blockIdx.x, by = P.by0 + (ROWS == 32 ? trow : (trow >> 1));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     TileGeom G;
     G.x0 = bx * 32 - 16 + P.off_x;
-    G.y0 = by * 32 - 16 + P.off_y;
+    G.y0 = by * 32 - 16 + P.off_y + ROWS * half;
     const int f_rgb = 3 * (G.x0 - 1), f_pp = 2 * (G.x0 - 1), b_u8 = G.x0 - 1;
     const int c_rgb = f_rgb & ~3, c_pp = f_pp & ~3, c_u8 = b_u8 & ~15;  // 16-byte aligned box starts (floor, also for negatives)
     G.sh_rgb = f_rgb - c_rgb; G.sh_pp = f_pp - c_pp; G.sh_u8 = b_u8 - c_u8;
@@ -733,7 +760,7 @@ __global__ void __launch_bounds__(256, BMFR_POST_TMA_MIN_BLOCKS) post_tma_kernel
         // its own wait for the reprojection (which waited for the caller's producer), in the overlapped mode the fit's
         // event already orders this launch.  Rows / columns outside the image (or the strip) arrive as zeros.
         const int c1 = G.y0 - 1 - P.row0;
-        mbar_expect_tx(&sh.bar, PT_STAGE_TX);
+        mbar_expect_tx(&sh.bar, Stage::TX);
 #if BMFR_L2_HINTS >= 2  // last readers of the reprojection's per-pixel outputs, only reader of the albedo
         tma_load_tile_hint(&sh.pp[0][0], &M.pp, c_pp, c1, &sh.bar, BMFR_L2_ONCE);
         tma_load_tile_hint(&sh.acc[0][0], &M.accept, c_u8, c1, &sh.bar, BMFR_L2_ONCE);
@@ -752,14 +779,14 @@ __global__ void __launch_bounds__(256, BMFR_POST_TMA_MIN_BLOCKS) post_tma_kernel
     }
     // strips: a CTA near a strip edge waits for the neighbours' accumulated colour / TAA rows of the previous frame; its
     // first look at the flags is in flight across the wait for the fit
-    const bool zone = STRIP && halo_in_zone(P.halo_p, G.y0 - 1, G.y0 + 33);
+    const bool zone = STRIP && halo_in_zone(P.halo_p, G.y0 - 1, G.y0 + ROWS + 1);
     const HaloPeek peek = halo_peek(P.halo_p, zone);
     pdl_wait();     // the fit of this frame is complete (weights, min/max)
     pdl_trigger();  // only now, so that "this frame's fit and reprojection are complete" also holds for the successor
     stamp_begin(P, 2);
     if (zone) halo_poll(P.halo_p, peek);
 
-    load_coefficients<FS>(P, sh.coef, bx, by, warp, lane);
+    load_coefficients<FS>(P, sh.coef, bx, by, warp, lane, THREADS / 32);
     __syncthreads();  // the coefficients and the barrier's initialisation are visible
     mbar_wait_hot(&sh.bar, 0);
 
@@ -852,17 +879,18 @@ __global__ void __launch_bounds__(256, BMFR_POST_TMA_MIN_BLOCKS) post_tma_kernel
             live |= ((own1 ? 1u : 0u) | (t ? 16u : 0u)) << (s + 1);
         }
     }
-    // phase A, ring: 4 * 33 = 132 pixels, coefficients of the pixel's own block
-    if (tid < 4 * (PT_HALO - 1)) {
-        const int side = tid / (PT_HALO - 1), k = tid % (PT_HALO - 1);
+    // phase A, ring: 2 * 33 + 2 * (HY - 1) pixels (132 / 100), coefficients of the pixel's own block — for a half tile the
+    // row below the upper half / above the lower half belongs to the same block
+    if (tid < 2 * (PT_HALO - 1) + 2 * (HY - 1)) {
         int hx, hy;
-        if (side == 0) { hx = k; hy = 0; }
-        else if (side == 1) { hx = PT_HALO - 1; hy = k; }
-        else if (side == 2) { hx = PT_HALO - 1 - k; hy = PT_HALO - 1; }
-        else { hx = 0; hy = PT_HALO - 1 - k; }
+        if (tid < PT_HALO - 1) { hx = tid; hy = 0; }
+        else if (tid < PT_HALO - 1 + HY - 1) { hx = PT_HALO - 1; hy = tid - (PT_HALO - 1); }
+        else if (tid < 2 * (PT_HALO - 1) + HY - 1) { hx = PT_HALO - 1 - (tid - (PT_HALO - 1 + HY - 1)); hy = HY - 1; }
+        else { hx = 0; hy = HY - 1 - (tid - (2 * (PT_HALO - 1) + HY - 1)); }
         const int rx = G.x0 + hx - 1, ry = G.y0 + hy - 1;
         if (rx >= 0 && rx < P.W && ry >= P.py0 && ry < P.py1) {
-            const int nb = ((hy == 0) ? 0 : (hy == PT_HALO - 1) ? 6 : 3) + ((hx == 0) ? 0 : (hx == PT_HALO - 1) ? 2 : 1);
+            const int nrow = (hy == 0) ? ((ROWS == 32 || half == 0) ? 0 : 3) : (hy == HY - 1) ? ((ROWS == 32 || half == 1) ? 6 : 3) : 3;
+            const int nb = nrow + ((hx == 0) ? 0 : (hx == PT_HALO - 1) ? 2 : 1);
             f3 unused;
             staged_pixel<STRIP, FS>(sh, P, G, sh.coef[nb], hx, hy, rx, ry, false, false, unused, zone);
         }
@@ -914,7 +942,7 @@ __global__ void __launch_bounds__(256, BMFR_POST_TMA_MIN_BLOCKS) post_tma_kernel
     if (STRIP && zone) {
         __syncthreads();  // the staged rows are complete
         post_push_rows(P, sh, G, tid);
-        halo_finish(P.halo_p, halo_cta_pushes(P.halo_p, G.y0, G.y0 + 32));
+        halo_finish(P.halo_p, halo_cta_pushes(P.halo_p, G.y0, G.y0 + ROWS));
     }
     stamp_end(P, 2);
 }
@@ -924,36 +952,43 @@ __global__ void __launch_bounds__(256, BMFR_POST_TMA_MIN_BLOCKS) post_tma_kernel
 #endif
 
 // Tensor maps of the frame's six read-once inputs, or false when the TMA path cannot be used (then post_kernel runs).
-static bool post_maps(const KParams& P, PostMaps* M) {
+static bool post_maps(const KParams& P, PostMaps* M, int box_rows) {
     const int rows = P.row1 - P.row0;
     if (!BMFR_POST_TMA || (P.W & 15) != 0 || rows < PT_HALO || P.W * 3 < PT_RGB_W) return false;
-    return bmfr_tensor_map_2d(P.cur_normals, 4, (long long)P.W * 3, rows, PT_RGB_W, PT_HALO, &M->normals) &&
-           bmfr_tensor_map_2d(P.cur_positions, 4, (long long)P.W * 3, rows, PT_RGB_W, PT_HALO, &M->positions) &&
-           bmfr_tensor_map_2d(P.albedo, 4, (long long)P.W * 3, rows, PT_RGB_W, PT_HALO, &M->albedo) &&
-           bmfr_tensor_map_2d(P.prev_pixels, 4, (long long)P.W * 2, rows, PT_PP_W, PT_HALO, &M->pp) &&
-           bmfr_tensor_map_2d(P.accept, 1, (long long)P.W, rows, PT_U8_W, PT_HALO, &M->accept) &&
-           bmfr_tensor_map_2d(P.cur_spp, 1, (long long)P.W, rows, PT_U8_W, PT_HALO, &M->spp);
+    return bmfr_tensor_map_2d(P.cur_normals, 4, (long long)P.W * 3, rows, PT_RGB_W, box_rows, &M->normals) &&
+           bmfr_tensor_map_2d(P.cur_positions, 4, (long long)P.W * 3, rows, PT_RGB_W, box_rows, &M->positions) &&
+           bmfr_tensor_map_2d(P.albedo, 4, (long long)P.W * 3, rows, PT_RGB_W, box_rows, &M->albedo) &&
+           bmfr_tensor_map_2d(P.prev_pixels, 4, (long long)P.W * 2, rows, PT_PP_W, box_rows, &M->pp) &&
+           bmfr_tensor_map_2d(P.accept, 1, (long long)P.W, rows, PT_U8_W, box_rows, &M->accept) &&
+           bmfr_tensor_map_2d(P.cur_spp, 1, (long long)P.W, rows, PT_U8_W, box_rows, &M->spp);
 }
 
 template <int FS>
 static cudaError_t launch_post_fs(const KParams& P, cudaStream_t st) {
     const dim3 grid(P.blocks_x, P.by1 - P.by0);
     const bool strip = P.row0 != 0 || P.row1 != P.H;
+    // tile height: whole images run half tiles (six 128-thread CTAs per SM), strips whole blocks — their zone bookkeeping
+    // (fill_halo counts zone CTAs per block row) and row staging are laid out for 32 x 32 tiles
+    constexpr int WHOLE_ROWS = BMFR_POST_TILE_ROWS;
+    using StageW = PostStageT<WHOLE_ROWS + 2>;
+    using StageS = PostStageT<32 + 2>;
+    constexpr size_t smem_w = sizeof(StageW) + BMFR_POST_SMEM_PAD;
     PostMaps M;
-    if (post_maps(P, &M)) {
+    if (post_maps(P, &M, (strip ? 32 : WHOLE_ROWS) + 2)) {
         static bool done[64] = {};
         int dev = 0;
         cudaError_t e = cudaGetDevice(&dev);
         if (e != cudaSuccess) return e;
         if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
         if (!done[dev]) {
-            e = cudaFuncSetAttribute(post_tma_kernel<false, FS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PostStage));
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(post_tma_kernel<true, FS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PostStage));
+            e = cudaFuncSetAttribute(post_tma_kernel<false, FS, WHOLE_ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(post_tma_kernel<true, FS, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StageS));
             if (e != cudaSuccess) return e;
             done[dev] = true;
         }
-        if (strip) return launch_pdl(!P.plain_launch, post_tma_kernel<true, FS>, grid, dim3(256), sizeof(PostStage), st, P, M);
-        return launch_pdl(!P.plain_launch, post_tma_kernel<false, FS>, grid, dim3(256), sizeof(PostStage), st, P, M);
+        if (strip) return launch_pdl(!P.plain_launch, post_tma_kernel<true, FS, 32>, grid, dim3(256), sizeof(StageS), st, P, M);
+        const dim3 grid_w(P.blocks_x, (P.by1 - P.by0) * (32 / WHOLE_ROWS));
+        return launch_pdl(!P.plain_launch, post_tma_kernel<false, FS, WHOLE_ROWS>, grid_w, dim3(8 * WHOLE_ROWS), smem_w, st, P, M);
     }
     // widths that are no multiple of 16 (no tensor maps): the per-thread-load variant.  (Its 64+32-bit pixel accesses,
     // BMFR_POST_WIDE_ACCESS, cost 38 % more instructions for the same L1 wavefronts and stay a tuning switch.)
