@@ -923,8 +923,24 @@ static_assert(2 * BMFR_BUFFER_COUNT * BMFR_FEATURES * sizeof(double) <= GR_CHUNK
 static_assert(GR_CHUNK >= BMFR_BUFFER_COUNT - 1 && GR_CHUNK <= 32, "the column sums of a block go through the buffer in one round");
 
 // Sum of the 32 floats of one row of the transpose buffer (eight 128-bit loads, pairwise tree).
+#ifndef BMFR_GRAM_PACKED_SUM
+#define BMFR_GRAM_PACKED_SUM 1  // the tree on packed pairs: 15 FADD2 + 1 FADD instead of 31 FADD
+#endif
+#ifndef BMFR_GRAM_INTERIOR_LOADS
+#define BMFR_GRAM_INTERIOR_LOADS 1
+#endif
 __device__ __forceinline__ float gram_row_sum(const float* __restrict__ row) {
     const float4* r4 = reinterpret_cast<const float4*>(row);
+#if BMFR_GRAM_PACKED_SUM
+    float2 t[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float4 v = r4[i];
+        t[i] = fadd2(make_float2(v.x, v.y), make_float2(v.z, v.w));
+    }
+    const float2 u = fadd2(fadd2(fadd2(t[0], t[1]), fadd2(t[2], t[3])), fadd2(fadd2(t[4], t[5]), fadd2(t[6], t[7])));
+    return u.x + u.y;
+#else
     float t[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -932,6 +948,7 @@ __device__ __forceinline__ float gram_row_sum(const float* __restrict__ row) {
         t[i] = (v.x + v.y) + (v.z + v.w);
     }
     return ((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7]));
+#endif
 }
 
 __device__ __forceinline__ double shfl_f64(double v, int src) {
@@ -1089,7 +1106,22 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_GRAM_MIN_BLOCKS) fit_gram_ker
         float a[ROWS][NCOL];
         int ox, oy;
         const bool by_tma = qr_block_box(P, bx, by, ox, oy) && M.use_tma;
-        if (by_tma) {
+        if (BMFR_GRAM_INTERIOR_LOADS && by_tma && ox == bx * 32 - 16 + P.off_x && oy == by * 32 - 16 + P.off_y) {
+            // the block lies inside the image (all but the border blocks): the window is the block, nothing is mirrored —
+            // one base address, 72 loads at immediate offsets (the mirrored path below spends 3 instructions per load
+            // on per-row index arithmetic and its branches, ahead of the loads)
+            const float* base = &sh.stage[0][warp * ROWS][((ox * 3) & 3) + 3 * lane];
+#pragma unroll
+            for (int s = 0; s < ROWS; ++s) {
+                float v[9];
+#pragma unroll
+                for (int c = 0; c < 9; ++c) {
+                    if (c < 3 && !FL::NORMALS) continue;  // this list does not read the normals
+                    v[c] = base[(c / 3) * QR_TILE_FLOATS + s * QR_TILE_W + c % 3];
+                }
+                feature_columns<FS>(a[s], v, v + 3, v + 6);  // NaNs are found and scrubbed below
+            }
+        } else if (by_tma) {
             // this lane's pixel column and this thread's eight rows inside the 32x32 window, mirrored like bmfr.cl:314-316
             const int col = ((ox * 3) & 3) + 3 * (mirror_index(bx * 32 + lane - 16 + P.off_x, P.W) - ox);
             const int y_in = by * 32 + warp * ROWS - 16 + P.off_y;
@@ -1131,6 +1163,13 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_GRAM_MIN_BLOCKS) fit_gram_ker
         for (int h = 0; h < ROWS / 2; ++h)
 #pragma unroll
             for (int c = 0; c < NCOL; ++c) a2[h][c] = make_float2(a[2 * h][c], a[2 * h + 1][c]);
+        if (FL::SQUARES) {  // the squared positions as packed products (the same correctly rounded products, half the instructions)
+            constexpr int LIN = FL::NORMALS ? 3 : 0;
+#pragma unroll
+            for (int h = 0; h < ROWS / 2; ++h)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) a2[h][LIN + 3 + j] = fmul2(a2[h][LIN + j], a2[h][LIN + j]);
+        }
         // (i) for the centring, the sums of all twelve columns: per thread, then over the warp through the transpose buffer.
         // A NaN input (bmfr.cl:448-453 turns it into 0) poisons its column's sum, so the sums double as the NaN test of
         // the thread's 72 tile values; the scrub itself is the rare path.

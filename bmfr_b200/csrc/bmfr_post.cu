@@ -75,7 +75,6 @@ __device__ __forceinline__ float tone_map_fast(float v) {  // clamp(powr(max(0,v
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(l));
     return __saturatef(e);
 }
-
 // The block's coefficients in shared memory (PostShared::coef / PostStage::coef), for a list of F features of which the
 // last NSC are scaled: F x (w_r, w_g, w_b, -), then NSC x (min, 1/range) — read as 128-bit broadcasts (every lane of a
 // tile-interior warp reads the same address).
@@ -147,32 +146,6 @@ __device__ __forceinline__ void weighted_sum_px2(f3 n0, f3 p0, f3 n1, f3 p1, con
     out1 = clamp_negative(b);
 }
 
-// The same for the four pixels of a thread's column strip: every coefficient is fetched once and used four times.
-template <int FS>
-__device__ __forceinline__ void weighted_sum_px4(const f3 (&n)[4], const f3 (&p)[4], const float* __restrict__ cf, f3 (&out)[4]) {
-    constexpr int F = FeatureSet<FS>::F;
-    const float4* c4 = reinterpret_cast<const float4*>(cf);
-    PostCoef<FS> pc;
-    pc.load(cf);
-    float ft[4][F - 1];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) pc.features(n[k], p[k], ft[k]);
-    const float4 w0 = c4[0];
-    f3 acc[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) acc[k] = make_f3(w0.x, w0.y, w0.z);
-#pragma unroll
-    for (int f = 1; f < F; ++f) {
-        const float4 w = c4[f];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            acc[k].x = fmaf(w.x, ft[k][f - 1], acc[k].x); acc[k].y = fmaf(w.y, ft[k][f - 1], acc[k].y); acc[k].z = fmaf(w.z, ft[k][f - 1], acc[k].z);
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) out[k] = clamp_negative(acc[k]);
-}
-
 // The coefficients of the 3x3 block neighbourhood -> shared memory: warp w takes neighbour w (warp 0 also the ninth).
 template <int FS>
 __device__ __forceinline__ void load_coefficients(const KParams& P, float (*coef)[PT_COEF], int bx, int by, int warp, int lane, int nwarps = 8) {
@@ -237,8 +210,9 @@ __device__ __forceinline__ f3 accumulate_filtered_px(const KParams& P, unsigned 
     return make_f3(tone_map_fast(alb.x * accum.x), tone_map_fast(alb.y * accum.y), tone_map_fast(alb.z * accum.z));
 }
 
-__device__ __forceinline__ f3 to_ycocg(f3 c) {  // bmfr.cl:184-190
-    return make_f3(c.x + 2.f * c.y + c.z, 2.f * c.x - 2.f * c.z, -c.x + 2.f * c.y - c.z);
+__device__ __forceinline__ f3 to_ycocg(f3 c) {  // bmfr.cl:184-190: (r + 2g + b, 2r - 2b, -r + 2g - b), five operations
+    const float t = c.x + c.z, d = c.x - c.z;
+    return make_f3(fmaf(2.f, c.y, t), d + d, fmaf(2.f, c.y, -t));
 }
 __device__ __forceinline__ f3 from_ycocg(f3 c) {  // bmfr.cl:192-198
     return make_f3(0.25f * (c.x + c.y - c.z), 0.25f * (c.x + c.z), 0.25f * (c.x - c.y - c.z));
@@ -511,21 +485,39 @@ __global__ void __launch_bounds__(256, BMFR_POST_MIN_BLOCKS) post_kernel(const _
 // one elected thread, one mbarrier) instead of ~2000 L1 wavefronts of per-thread loads: an interleaved-RGB
 // image read component by component touches 3-4 cache lines per 32-bit warp load, and the ring columns one line
 // per pixel.  The copies are requested before the wait for the fit (everything they read is complete by then,
-// see the kernel), so with three CTAs per SM a tile's inputs land while its neighbours compute.  From shared
-// memory a warp reads the same values at a stride of three words, which is bank-conflict free.
+// see the kernel), so a tile's inputs land while its neighbours on the SM compute.  From shared memory a warp reads
+// the same values at a stride of three words, which is bank-conflict free.
 //   * Each pixel's tone-mapped YCoCg value is written over its own albedo cell (only that pixel's thread ever
 //     reads the cell), so the neighbourhood planes of phase B need no memory of their own.
 //   * What still goes through the L1 are the two 4-tap gathers.  A thread's vertically adjacent pixels share
 //     their middle tap row whenever the reprojection is locally uniform (the common case; checked per pair), so
-//     a pair loads three tap rows instead of four; all taps come from clamped addresses in one round of
-//     independent loads, issued before the weighted sum so that its arithmetic overlaps their latency.
-// Arithmetic and operation order per pixel are those of the per-thread-load variant above.
+//     a pair loads three tap rows instead of four; all taps come in one round of independent loads, issued
+//     before the weighted sum so that its arithmetic overlaps their latency.
+//   * Interior tiles (BMFR_POST_FAST) — halo inside the image, every pixel owned, no strip edge near: 88 % of the tiles
+//     at 1080p — take a phase A without the per-pixel image-edge / strip / ownership tests of the general one: the
+//     source-level profile of the general body (profiles/r02_final_ncu_full.md, 486 warp instructions per pixel) has a
+//     quarter of its issue slots in predicates, clamps, index arithmetic, the replication of edge cells and the
+//     divergence bookkeeping of rarely taken branches.  There, after a warp-uniform test per pixel pair (every lane's
+//     stacked 2x3 footprint inside the rows / columns held) the 36 tap loads use three row pointers per buffer and
+//     immediate offsets, every tap of the TAA history is valid and nothing is clamped; pairs that fail the test take
+//     the general pair code.
+//   * ONE arithmetic per pixel.  Whichever path computes a pixel — interior or general tile, pair or single, tile or
+//     ring, whole image or strip — it runs the same rounded operations in the same order (the helpers below, written
+//     with explicit intrinsics so that the compiler's contraction cannot differ between inlining sites): a strip run
+//     stays bit-identical to the whole-image run although the two sort different tiles into the two paths
+//     (tests/test_sharding.py, tests/test_baseline_configs.py).
+//     The block's coefficients are pre-multiplied by 1/range when they are loaded (one record of F x (w_r, w_g, w_b, min)
+//     per block: a scaled feature is one subtraction), the accumulation is written without branches (selects on
+//     total_weight > 0 instead of the nested ifs of bmfr.cl:784-841), the clamp of the tone map sits in front of the
+//     power (a saturating multiply), a TAA history sample whose four taps are all valid is not divided by its weight
+//     sum (1 +- 2 ulp), and the TAA blend is done in YCoCg (the transform is linear: one conversion back instead of two).
+// Everything here is tolerance-only arithmetic (tests/test_gpu_parity.py: 1e-3 / 60 dB against the oracle).
 // ================================================================================================
 #define PT_RGB_W 108  // floats per staged row of an interleaved-RGB image: 34 pixels + up to 3 floats of alignment shift
 #define PT_PP_W 72    // floats per staged row of prev_pixels: 34 float2 + 2 floats of shift
 #define PT_U8_W 64    // bytes per staged row of accept / spp: 34 + up to 15 bytes of shift
 
-// A tile is 32 pixels wide and ROWS (32 or 16) high; the stage holds it with its one-pixel ring: HY = ROWS + 2 rows.
+// A tile is 32 x 32 pixels; the stage holds it with its one-pixel ring: HY = 34 rows.
 template <int HY_>
 struct __align__(128) PostStageT {  // every TMA destination starts on a 128-byte boundary
     static constexpr int HY = HY_;
@@ -541,6 +533,7 @@ struct __align__(128) PostStageT {  // every TMA destination starts on a 128-byt
     static_assert(sizeof(float[HY_][PT_RGB_W]) % 128 == 96 && sizeof(float[HY_][PT_PP_W]) % 128 == 64 && (HY_ * PT_U8_W) % 128 == 0,
                   "TMA destinations must stay 128-byte aligned");
 };
+using PostStage = PostStageT<PT_HALO>;
 
 struct PostMaps {
     CUtensorMap normals, positions, albedo, pp, accept, spp;
@@ -555,26 +548,23 @@ __device__ __forceinline__ f3 cell_f3(const float (*buf)[PT_RGB_W], const TileGe
     const float* p = &buf[hy][G.sh_rgb + 3 * hx];
     return make_f3(p[0], p[1], p[2]);
 }
-template <class SH>
-__device__ __forceinline__ void put_cell_i(SH& sh, const TileGeom& G, int hx, int hy, f3 v) {
+__device__ __forceinline__ void put_cell_i(PostStage& sh, const TileGeom& G, int hx, int hy, f3 v) {
     float* p = &sh.alb[hy][G.sh_rgb + 3 * hx];
     p[0] = v.x; p[1] = v.y; p[2] = v.z;
 }
 // put_ycc() for the interleaved cells: the value of image pixel (x,y) also fills the out-of-image cells whose
 // nearest in-image pixel it is (nobody reads an albedo there).
-template <class SH>
-__device__ __forceinline__ void put_ycc_i(SH& sh, const KParams& P, const TileGeom& G, int hx, int hy, int x, int y, f3 v) {
+__device__ __forceinline__ void put_ycc_i(PostStage& sh, const KParams& P, const TileGeom& G, int hx, int hy, int x, int y, f3 v) {
     put_cell_i(sh, G, hx, hy, v);
     const int ex = (x == 0) ? -1 : (x == P.W - 1) ? 1 : 0;
     const int ey = (y == 0) ? -1 : (y == P.H - 1) ? 1 : 0;
     if ((ex | ey) == 0) return;
-    const bool okx = ex != 0 && (unsigned)(hx + ex) < PT_HALO, oky = ey != 0 && (unsigned)(hy + ey) < SH::HY;
+    const bool okx = ex != 0 && (unsigned)(hx + ex) < PT_HALO, oky = ey != 0 && (unsigned)(hy + ey) < PT_HALO;
     if (okx) put_cell_i(sh, G, hx + ex, hy, v);
     if (oky) put_cell_i(sh, G, hx, hy + ey, v);
     if (okx && oky) put_cell_i(sh, G, hx + ex, hy + ey, v);
 }
-template <class SH>
-__device__ __forceinline__ PixelIn load_pixel_staged(const SH& sh, const KParams& P, const TileGeom& G, int hx, int hy, int x, int y) {
+__device__ __forceinline__ PixelIn load_pixel_staged(const PostStage& sh, const KParams& P, const TileGeom& G, int hx, int hy, int x, int y) {
     PixelIn in;
     in.lp = pix_index(P, x, y);
     in.n = cell_f3(sh.nrm, G, hx, hy);
@@ -588,20 +578,18 @@ __device__ __forceinline__ PixelIn load_pixel_staged(const SH& sh, const KParams
 // Zone CTAs of a strip (HaloK) do not send a mirrored row pixel by pixel: a pixel's accumulated colour goes into its own
 // (already consumed) normal cell, its TAA result into its position cell, and after the last pixel the CTA sends whole row
 // segments as 8-byte peer stores (post_push_rows) — 4-byte stores at a 12-byte stride make poor NVLink packets.
-template <class SH>
-__device__ __forceinline__ void stage_accum(SH& sh, const TileGeom& G, int hx, int hy, f3 v) {
+__device__ __forceinline__ void stage_accum(PostStage& sh, const TileGeom& G, int hx, int hy, f3 v) {
     float* p = &sh.nrm[hy][G.sh_rgb + 3 * hx];
     p[0] = v.x; p[1] = v.y; p[2] = v.z;
 }
-template <class SH>
-__device__ __forceinline__ void stage_result(SH& sh, const TileGeom& G, int hx, int hy, f3 v) {
+__device__ __forceinline__ void stage_result(PostStage& sh, const TileGeom& G, int hx, int hy, f3 v) {
     float* p = &sh.pos[hy][G.sh_rgb + 3 * hx];
     p[0] = v.x; p[1] = v.y; p[2] = v.z;
 }
 // All threads of a zone CTA, after a barrier: the tile's rows that a neighbour mirrors, both buffers.
-template <class SH>
-__device__ __forceinline__ void post_push_rows(const KParams& P, const SH& sh, const TileGeom& G, int tid) {
-    constexpr int ROWS = SH::HY - 2, THREADS = 8 * ROWS;
+template <int THREADS>
+__device__ __forceinline__ void post_push_rows(const KParams& P, const PostStage& sh, const TileGeom& G, int tid) {
+    constexpr int ROWS = PT_TILE;
     const HaloK& h = P.halo_p;
 #ifdef BMFR_DEBUG_NO_PUSH
     return;
@@ -624,18 +612,81 @@ __device__ __forceinline__ void post_push_rows(const KParams& P, const SH& sh, c
     }
 }
 
-// One pixel whose inputs are staged: ring pixels, and the pixels of a pair cut by a strip or image edge.
-template <bool STRIP, int FS, class SH>
-__device__ __forceinline__ bool staged_pixel(SH& sh, const KParams& P, const TileGeom& G, const float* cf, int hx, int hy, int x, int y,
-                                             bool store, bool own, f3& hist, bool zone) {
-    const PixelIn in = load_pixel_staged(sh, P, G, hx, hy, x, y);
-    const f3 filtered = weighted_sum_px<FS>(in.n, in.p, cf);
-    const bool temporal = own && history_sample<STRIP, false>(P, in.pp, hist);
-    f3 accum;
-    const f3 tone = accumulate_filtered_px<STRIP, false>(P, in.lp, filtered, in.accept, in.pp, in.spp, in.alb, store, x, y, false, &accum);
-    if (STRIP && zone && store) stage_accum(sh, G, hx, hy, accum);
-    put_ycc_i(sh, P, G, hx, hy, x, y, to_ycocg(tone));
-    return temporal;
+// ---- the arithmetic of one pixel (shared by every path; explicit intrinsics, see the banner) ----------------------------
+// F x (w_r * s_f, w_g * s_f, w_b * s_f, min_f) per block, s_f = 1/range (scale_factor()) for the scaled features, 1 and
+// min = 0 otherwise: warp w takes neighbour w of the 3x3 block neighbourhood, (dy + 1) * 3 + dx + 1 (warp 0 also the ninth).
+template <int FS>
+__device__ __forceinline__ void load_coefficients_scaled(const KParams& P, float (*coef)[PT_COEF], int bx, int by, int warp, int lane, int nwarps) {
+    constexpr int F = FeatureSet<FS>::F, NSC = FeatureSet<FS>::NSC, NNS = F - NSC;
+    const int f = lane / 3, c = lane - 3 * f;
+    for (int nb = warp; nb < 9; nb += nwarps) {
+        const int q = (nb * 11) >> 5;  // nb / 3 for nb < 9 (a 16-bit division would be a library call here)
+        const int gx = bx + nb - 3 * q - 1, gy = by + q - 1;
+        if (gx < 0 || gx >= P.blocks_x || gy < 0 || gy >= P.blocks_y) continue;
+        const size_t g = (size_t)gy * P.blocks_x + gx;
+        if (lane < 3 * F) {
+            float w = __ldg(P.weights + g * (3 * F) + lane);
+            if (f >= NNS) w = __fmul_rn(w, __ldg(P.mins_inv + g * (2 * NSC) + 2 * (f - NNS) + 1));
+            coef[nb][4 * f + c] = w;
+        }
+        if (lane < F) coef[nb][4 * lane + 3] = lane >= NNS ? __ldg(P.mins_inv + g * (2 * NSC) + 2 * (lane - NNS)) : 0.f;
+    }
+}
+// the F - 1 non-constant features of a pixel (bmfr.cl:724-741: clean, no noise, no NaN scrub) with the minimum taken off the
+// scaled ones (their 1/range lives in the coefficients)
+template <int FS>
+__device__ __forceinline__ void features_offset(f3 n, f3 p, const float4 (&w)[FeatureSet<FS>::F], float (&feat)[FeatureSet<FS>::F - 1]) {
+    constexpr int F = FeatureSet<FS>::F, NSC = FeatureSet<FS>::NSC, NNS = F - NSC;
+    int at = 0;
+    if (FeatureSet<FS>::NORMALS) { feat[0] = n.x; feat[1] = n.y; feat[2] = n.z; at = 3; }
+    const float lin[3] = {p.x, p.y, p.z};
+#pragma unroll
+    for (int k = 0; k < NSC; ++k) {
+        const float mn = w[NNS + k].w;
+        feat[at + k] = k < 3 ? __fsub_rn(lin[k], mn) : fmaf(lin[k - 3], lin[k - 3], -mn);
+    }
+}
+__device__ __forceinline__ float max_nan(float a, float b) {
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ f3 clamp_negative_nan(f3 c) {  // bmfr.cl:750 (a NaN stays a NaN) in one instruction per component
+    return make_f3(max_nan(c.x, 0.f), max_nan(c.y, 0.f), max_nan(c.z, 0.f));
+}
+// weighted_sum (bmfr.cl:725-750) of two pixels from one set of coefficient loads / of one pixel: the same chain per pixel
+template <int FS>
+__device__ __forceinline__ void weighted_sum_scaled_px2(f3 n0, f3 p0, f3 n1, f3 p1, const float* __restrict__ cf, f3& out0, f3& out1) {
+    constexpr int F = FeatureSet<FS>::F;
+    const float4* c4 = reinterpret_cast<const float4*>(cf);
+    float4 w[F];
+#pragma unroll
+    for (int f = 0; f < F; ++f) w[f] = c4[f];
+    float f0[F - 1], f1[F - 1];
+    features_offset<FS>(n0, p0, w, f0);
+    features_offset<FS>(n1, p1, w, f1);
+    f3 a = make_f3(w[0].x, w[0].y, w[0].z), b = a;
+#pragma unroll
+    for (int f = 1; f < F; ++f) {
+        a.x = fmaf(w[f].x, f0[f - 1], a.x); a.y = fmaf(w[f].y, f0[f - 1], a.y); a.z = fmaf(w[f].z, f0[f - 1], a.z);
+        b.x = fmaf(w[f].x, f1[f - 1], b.x); b.y = fmaf(w[f].y, f1[f - 1], b.y); b.z = fmaf(w[f].z, f1[f - 1], b.z);
+    }
+    out0 = clamp_negative_nan(a);
+    out1 = clamp_negative_nan(b);
+}
+template <int FS>
+__device__ __forceinline__ f3 weighted_sum_scaled_px(f3 n, f3 p, const float* __restrict__ cf) {
+    constexpr int F = FeatureSet<FS>::F;
+    const float4* c4 = reinterpret_cast<const float4*>(cf);
+    float4 w[F];
+#pragma unroll
+    for (int f = 0; f < F; ++f) w[f] = c4[f];
+    float ft[F - 1];
+    features_offset<FS>(n, p, w, ft);
+    f3 a = make_f3(w[0].x, w[0].y, w[0].z);
+#pragma unroll
+    for (int f = 1; f < F; ++f) { a.x = fmaf(w[f].x, ft[f - 1], a.x); a.y = fmaf(w[f].y, ft[f - 1], a.y); a.z = fmaf(w[f].z, ft[f - 1], a.z); }
+    return clamp_negative_nan(a);
 }
 
 struct TapGeom {  // the 2x2 bilinear footprint of one pixel in the previous frame
@@ -646,108 +697,160 @@ __device__ __forceinline__ TapGeom tap_geom(float2 pp) {
     TapGeom t;
     t.pix = __float2int_rd(pp.x);
     t.piy = __float2int_rd(pp.y);
-    const float frx = pp.x - (float)t.pix, fry = pp.y - (float)t.piy;
-    const float omx = 1.f - frx, omy = 1.f - fry;
-    t.w[0] = omx * omy; t.w[1] = frx * omy; t.w[2] = omx * fry; t.w[3] = frx * fry;
+    const float frx = __fsub_rn(pp.x, (float)t.pix), fry = __fsub_rn(pp.y, (float)t.piy);
+    const float omx = __fsub_rn(1.f, frx), omy = __fsub_rn(1.f, fry);
+    t.w[0] = __fmul_rn(omx, omy); t.w[1] = __fmul_rn(frx, omy); t.w[2] = __fmul_rn(omx, fry); t.w[3] = __fmul_rn(frx, fry);
     return t;
 }
-// accumulate_filtered_data (bmfr.cl:778-849) and the TAA history sample (bmfr.cl:884-965) of one pixel from taps that
-// are already in registers: a0 / r0 = the footprint's upper row (dx = 0, 1) of accumulated colour / TAA history, a1 / r1
-// its lower row.  Same operation order as accumulate_filtered_px() / history_sample().
-template <bool STRIP, class SH>
-__device__ __forceinline__ bool resolve_pixel(SH& sh, const KParams& P, const TileGeom& G, const PixelIn& in, const TapGeom& t, f3 filtered,
-                                              const f3 (&a0)[2], const f3 (&a1)[2], const f3 (&r0)[2], const f3 (&r1)[2], int hx, int hy, int x, int y,
-                                              bool own, f3& hist, bool zone) {
+// accumulate_filtered_data of one pixel (bmfr.cl:778-849) from its four taps (upper row a0[0..5] = two pixels, lower row
+// a1), without branches: an unaccepted tap is predicated off as in the reference (its value may be anything), the two
+// nested conditions of bmfr.cl:789,834 become selects.  accept = 0 (and frame 0) gives the filtered colour itself.
+__device__ __forceinline__ f3 accumulate_taps(const KParams& P, unsigned int accept, unsigned int spp, const float (&w)[4], f3 filtered,
+                                              const float* __restrict__ a0, const float* __restrict__ a1) {
     f3 prev = make_f3(0.f, 0.f, 0.f);
-    float alpha = 1.f;
-    // A strip that does not hold a wanted tap's row reports it (once, at the end: a store inside the loops would keep the
-    // compiler from predicating the taps); the tap itself was fetched from a clamped address and the run is invalid anyway.
-    const bool out0 = STRIP && (t.piy < P.state2_row0 || t.piy >= P.state2_row1);
-    const bool out1 = STRIP && (t.piy + 1 < P.state2_row0 || t.piy + 1 >= P.state2_row1);
-    bool missing = false;
-    if (in.accept != 0) {
-        float total = 0.f;
-        missing = ((in.accept & 3u) != 0 && out0) || ((in.accept & 12u) != 0 && out1);
+    float total = 0.f;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            if (in.accept & (1u << i)) {  // taps are trusted, not re-checked: bmfr.cl:801-832
-                const f3 pc = (i >> 1) ? a1[i & 1] : a0[i & 1];
-                total += t.w[i];
-                prev.x = fmaf(t.w[i], pc.x, prev.x);
-                prev.y = fmaf(t.w[i], pc.y, prev.y);
-                prev.z = fmaf(t.w[i], pc.z, prev.z);
-            }
-        }
-        if (total > 0.f) {
-            alpha = fmaxf(fast_rcp((float)in.spp), P.second_blend_alpha);  // bmfr.cl:838-839
-            const float inv = fast_rcp(total);
-            prev.x *= inv; prev.y *= inv; prev.z *= inv;
+    for (int i = 0; i < 4; ++i) {
+        if (accept & (1u << i)) {  // taps are trusted, not re-checked: bmfr.cl:801-832
+            const float* t = ((i >> 1) ? a1 : a0) + 3 * (i & 1);
+            total = __fadd_rn(total, w[i]);
+            prev.x = fmaf(w[i], t[0], prev.x);
+            prev.y = fmaf(w[i], t[1], prev.y);
+            prev.z = fmaf(w[i], t[2], prev.z);
         }
     }
-    const float oma = 1.f - alpha;
-    const f3 accum = make_f3(fmaf(alpha, filtered.x, oma * prev.x), fmaf(alpha, filtered.y, oma * prev.y), fmaf(alpha, filtered.z, oma * prev.z));
-    store_f3(P.accum_cur, in.lp, accum);
-    if (STRIP && zone) stage_accum(sh, G, hx, hy, accum);
-    const f3 tone = make_f3(tone_map_fast(in.alb.x * accum.x), tone_map_fast(in.alb.y * accum.y), tone_map_fast(in.alb.z * accum.z));
-    put_ycc_i(sh, P, G, hx, hy, x, y, to_ycocg(tone));
-
-    hist = make_f3(0.f, 0.f, 0.f);
-    const bool temporal = own && !(t.pix < -1 || t.piy < -1 || t.pix >= P.W || t.piy >= P.H);  // bmfr.cl:884-890
+    const bool any = total > 0.f;
+    const float alpha = any ? fmaxf(fast_rcp((float)spp), P.second_blend_alpha) : 1.f;  // bmfr.cl:838-839
+    const float k = any ? __fmul_rn(__fsub_rn(1.f, alpha), fast_rcp(total)) : 0.f;       // (1 - alpha) / total_weight
+    return make_f3(fmaf(alpha, filtered.x, __fmul_rn(k, prev.x)), fmaf(alpha, filtered.y, __fmul_rn(k, prev.y)),
+                   fmaf(alpha, filtered.z, __fmul_rn(k, prev.z)));
+}
+// clamp(powr(max(0, a * b), 0.454545f), 0, 1), bmfr.cl:852-856, with the clamp in front of the power (x -> x^0.4545 is
+// monotonic and maps [0, 1] onto itself): the saturating multiply is one instruction, and a NaN product becomes 0 like
+// fmax(0.f, NaN) in OpenCL.  0 -> lg2 = -inf -> ex2 = 0, like powr(0, y > 0).
+__device__ __forceinline__ float tone_map_product(float a, float b) {
+    float v, l, e;
+    asm("mul.rn.ftz.sat.f32 %0, %1, %2;" : "=f"(v) : "f"(a), "f"(b));
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(v));
+    l = __fmul_rn(l, 0.454545f);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(l));
+    return e;
+}
+__device__ __forceinline__ f3 to_ycocg_rn(f3 c) {  // bmfr.cl:184-190: (r + 2g + b, 2r - 2b, -r + 2g - b) in five operations
+    const float t = __fadd_rn(c.x, c.z), d = __fsub_rn(c.x, c.z);
+    return make_f3(fmaf(2.f, c.y, t), __fadd_rn(d, d), fmaf(2.f, c.y, -t));
+}
+// bmfr.cl:192-198 for a colour that already carries the factor 0.25 (the blend of phase B folds it into its weights)
+__device__ __forceinline__ f3 from_quarter_ycocg(f3 c) {
+    const float u = __fsub_rn(c.x, c.z);
+    return make_f3(__fadd_rn(u, c.y), __fadd_rn(c.x, c.z), __fsub_rn(u, c.y));
+}
+__device__ __forceinline__ f3 tone_ycocg(f3 alb, f3 accum) {
+    return to_ycocg_rn(make_f3(tone_map_product(alb.x, accum.x), tone_map_product(alb.y, accum.y), tone_map_product(alb.z, accum.z)));
+}
+// Bilinear sample of the previous TAA result in YCoCg (bmfr.cl:922-965) from taps in registers; bit i of ok: tap i lies in
+// the image (ALL: every one does).  With all four taps the weights sum to 1 +- 2 ulp and the division of bmfr.cl:962 is
+// left out; with fewer, 0 * inf = NaN on the image edge like its 0 / 0.
+template <bool ALL>
+__device__ __forceinline__ f3 history_ycc(const float (&w)[4], const float* __restrict__ r0, const float* __restrict__ r1, unsigned int ok) {
     f3 hp = make_f3(0.f, 0.f, 0.f);
     float total = 0.f;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {  // bmfr.cl:929-960
-        const int dx = i & 1, dy = i >> 1;
-        const bool ok_y = dy ? (t.piy < P.H - 1) : (t.piy >= 0);
-        const bool ok_x = dx ? (t.pix < P.W - 1) : (t.pix >= 0);
-        missing = missing || (temporal && ok_x && ok_y && (dy ? out1 : out0));
-        if (ok_x && ok_y) {
-            const f3 pc = dy ? r1[dx] : r0[dx];
-            hp.x = fmaf(t.w[i], pc.x, hp.x);
-            hp.y = fmaf(t.w[i], pc.y, hp.y);
-            hp.z = fmaf(t.w[i], pc.z, hp.z);
-            total += t.w[i];
+        if (ALL || (ok & (1u << i))) {
+            const float* t = ((i >> 1) ? r1 : r0) + 3 * (i & 1);
+            hp.x = fmaf(w[i], t[0], hp.x);
+            hp.y = fmaf(w[i], t[1], hp.y);
+            hp.z = fmaf(w[i], t[2], hp.z);
+            if (!ALL) total = __fadd_rn(total, w[i]);
         }
     }
-    if (STRIP && missing) *P.oob_flag = 1;
-    if (!temporal) return false;
-    const float inv = fast_rcp(total);  // 0 * inf = NaN on the image edge like the 0/0 of bmfr.cl:962
-    hist = to_ycocg(make_f3(hp.x * inv, hp.y * inv, hp.z * inv));
-    return true;
+    if (!ALL && ok != 15u) {
+        const float inv = fast_rcp(total);
+        hp = make_f3(__fmul_rn(hp.x, inv), __fmul_rn(hp.y, inv), __fmul_rn(hp.z, inv));
+    }
+    return to_ycocg_rn(hp);
+}
+// which taps of the history sample lie in the image (bmfr.cl:929-960), and does the pixel take the temporal path (bmfr.cl:884-890)?
+__device__ __forceinline__ unsigned int history_taps_ok(const KParams& P, const TapGeom& t) {
+    const bool x0 = t.pix >= 0, x1 = t.pix < P.W - 1, y0 = t.piy >= 0, y1 = t.piy < P.H - 1;
+    return (x0 && y0 ? 1u : 0u) | (x1 && y0 ? 2u : 0u) | (x0 && y1 ? 4u : 0u) | (x1 && y1 ? 8u : 0u);
+}
+__device__ __forceinline__ bool history_in_reach(const KParams& P, const TapGeom& t) {
+    return !(t.pix < -1 || t.piy < -1 || t.pix >= P.W || t.piy >= P.H);
+}
+__device__ __forceinline__ void f3_to(float* d, f3 v) { d[0] = v.x; d[1] = v.y; d[2] = v.z; }
+
+// One pixel on its own — a ring pixel, or a pixel of a pair that a strip or image edge cuts: taps fetched from clamped
+// addresses (an accepted tap is in the image, bmfr.cl:386-392, so its clamped address is its own), then the shared arithmetic.
+// store: the pixel belongs to the tile (accumulated colour written, history sampled if owned); returns the temporal flag.
+template <bool STRIP, int FS>
+__device__ __forceinline__ bool single_pixel(PostStage& sh, const KParams& P, const TileGeom& G, const float* cf, int hx, int hy, int x, int y,
+                                             bool store, bool own, f3& hist, bool zone) {
+    const PixelIn in = load_pixel_staged(sh, P, G, hx, hy, x, y);
+    const f3 filtered = weighted_sum_scaled_px<FS>(in.n, in.p, cf);
+    const TapGeom t = tap_geom(in.pp);
+    const bool want_hist = store && own && P.frame > 0 && history_in_reach(P, t);
+    float a0[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, a1[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, r0[6], r1[6];
+    unsigned int accept = 0;
+    hist = make_f3(0.f, 0.f, 0.f);
+    if (P.frame > 0) {
+        accept = in.accept;
+        const int rlo = STRIP ? P.state2_row0 : 0, rhi = (STRIP ? P.state2_row1 : P.H) - 1;
+        const int cx[2] = {min(max(t.pix, 0), P.W - 1), min(max(t.pix + 1, 0), P.W - 1)};
+        const int cy[2] = {min(max(t.piy, rlo), rhi), min(max(t.piy + 1, rlo), rhi)};
+        const unsigned int ok = history_taps_ok(P, t);
+        if (STRIP) {  // a wanted tap whose row this strip does not hold: reported once, the run is invalid
+            const bool out0 = t.piy < P.state2_row0 || t.piy >= P.state2_row1, out1 = t.piy + 1 < P.state2_row0 || t.piy + 1 >= P.state2_row1;
+            const unsigned int wanted = accept | (want_hist ? ok : 0u);
+            if (((wanted & 3u) != 0 && out0) || ((wanted & 12u) != 0 && out1)) *P.oob_flag = 1;
+        }
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+            const unsigned int l0 = pix_index(P, cx[dx], cy[0]), l1 = pix_index(P, cx[dx], cy[1]);
+            f3_to(a0 + 3 * dx, load_f3(P.accum_prev, l0));
+            f3_to(a1 + 3 * dx, load_f3(P.accum_prev, l1));
+            if (want_hist) {
+                f3_to(r0 + 3 * dx, load_f3(P.result_prev, l0));
+                f3_to(r1 + 3 * dx, load_f3(P.result_prev, l1));
+            }
+        }
+        if (want_hist) hist = history_ycc<false>(t.w, r0, r1, ok);
+    }
+    const f3 accum = accumulate_taps(P, accept, in.spp, t.w, filtered, a0, a1);
+    if (store) {
+        store_f3(P.accum_cur, in.lp, accum);
+        if (STRIP && zone) stage_accum(sh, G, hx, hy, accum);
+    }
+    put_ycc_i(sh, P, G, hx, hy, x, y, tone_ycocg(in.alb, accum));
+    return want_hist;
 }
 
+#ifndef BMFR_POST_FAST
+#define BMFR_POST_FAST 1
+#endif
 #ifndef BMFR_POST_TMA_MIN_BLOCKS
-#define BMFR_POST_TMA_MIN_BLOCKS 3  // per SM for 32-row tiles; 16-row tiles: twice as many
+#define BMFR_POST_TMA_MIN_BLOCKS 3  // CTAs per SM with four pixels per thread (256 threads); two pixels per thread: 512 threads, two CTAs
+#endif
+#ifndef BMFR_POST_PX
+#define BMFR_POST_PX 4  // pixels per thread of the whole-image instantiation (4: 8 warps per tile, 2: 16)
 #endif
 #ifndef BMFR_POST_SMEM_PAD
 #define BMFR_POST_SMEM_PAD 0  // extra dynamic shared memory per CTA of the whole-image instantiation: fewer CTAs per SM, more L1
 #endif
-#ifndef BMFR_POST_TILE_ROWS
-// Tile height of the whole-image instantiation.  Measured at 1080p (profiles/r02 r3a): 16 (six 128-thread CTAs per SM, or
-// five / four with more L1 through BMFR_POST_SMEM_PAD) 63.8 / 65.5 / 71.4 us against 57.7 us for 32 — 200 instead of 132 ring
-// pixels per block and twice the per-CTA set-up cost more than the finer interleaving of the CTAs' waits gives.
-#define BMFR_POST_TILE_ROWS 32
-#endif
-#ifndef BMFR_POST_WS4
-#define BMFR_POST_WS4 0
-#endif
 
-// ROWS = 32 (default): one CTA of 256 threads per block, three per SM.  ROWS = 16 (tuning switch BMFR_POST_TILE_ROWS, slower):
-// one CTA of 128 threads per half block, six per SM — the same 24 warps in six independent groups.
-template <bool STRIP, int FS, int ROWS>
-__global__ void __launch_bounds__(8 * ROWS, BMFR_POST_TMA_MIN_BLOCKS * 32 / ROWS) post_tma_kernel(const __grid_constant__ KParams P, const __grid_constant__ PostMaps M) {
-    static_assert(ROWS == 32 || ROWS == 16, "a tile is a block or half a block");
-    using Stage = PostStageT<ROWS + 2>;
-    constexpr int HY = ROWS + 2, THREADS = 8 * ROWS;
+// One CTA per 32 x 32 tile; thread (lane, warp) owns the column strip x = x0 + lane, rows PX * warp .. + PX - 1.
+template <bool STRIP, int FS, int PX>
+__global__ void __launch_bounds__(1024 / PX, PX == 4 ? BMFR_POST_TMA_MIN_BLOCKS : 2) post_tma_kernel(const __grid_constant__ KParams P, const __grid_constant__ PostMaps M) {
+    static_assert(PX == 4 || PX == 2, "pixels per thread: two pairs or one");
+    constexpr int THREADS = 1024 / PX, WARPS = 32 / PX;
     extern __shared__ __align__(128) unsigned char post_smem[];
-    Stage& sh = *reinterpret_cast<Stage*>(post_smem);
-    const int trow = STRIP ? halo_row_order(P.halo_p, blockIdx.y, gridDim.y) : sweep_row(P, blockIdx.y, gridDim.y);  // tile row of the launch
-    const int half = ROWS == 32 ? 0 : (trow & 1);
-    const int bx = blockIdx.x, by = P.by0 + (ROWS == 32 ? trow : (trow >> 1));
+    PostStage& sh = *reinterpret_cast<PostStage*>(post_smem);
+    const int bx = blockIdx.x, by = P.by0 + (STRIP ? halo_row_order(P.halo_p, blockIdx.y, gridDim.y) : sweep_row(P, blockIdx.y, gridDim.y));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     TileGeom G;
     G.x0 = bx * 32 - 16 + P.off_x;
-    G.y0 = by * 32 - 16 + P.off_y + ROWS * half;
+    G.y0 = by * 32 - 16 + P.off_y;
     const int f_rgb = 3 * (G.x0 - 1), f_pp = 2 * (G.x0 - 1), b_u8 = G.x0 - 1;
     const int c_rgb = f_rgb & ~3, c_pp = f_pp & ~3, c_u8 = b_u8 & ~15;  // 16-byte aligned box starts (floor, also for negatives)
     G.sh_rgb = f_rgb - c_rgb; G.sh_pp = f_pp - c_pp; G.sh_u8 = b_u8 - c_u8;
@@ -760,7 +863,7 @@ __global__ void __launch_bounds__(8 * ROWS, BMFR_POST_TMA_MIN_BLOCKS * 32 / ROWS
         // its own wait for the reprojection (which waited for the caller's producer), in the overlapped mode the fit's
         // event already orders this launch.  Rows / columns outside the image (or the strip) arrive as zeros.
         const int c1 = G.y0 - 1 - P.row0;
-        mbar_expect_tx(&sh.bar, Stage::TX);
+        mbar_expect_tx(&sh.bar, PostStage::TX);
 #if BMFR_L2_HINTS >= 2  // last readers of the reprojection's per-pixel outputs, only reader of the albedo
         tma_load_tile_hint(&sh.pp[0][0], &M.pp, c_pp, c1, &sh.bar, BMFR_L2_ONCE);
         tma_load_tile_hint(&sh.acc[0][0], &M.accept, c_u8, c1, &sh.bar, BMFR_L2_ONCE);
@@ -779,170 +882,246 @@ __global__ void __launch_bounds__(8 * ROWS, BMFR_POST_TMA_MIN_BLOCKS * 32 / ROWS
     }
     // strips: a CTA near a strip edge waits for the neighbours' accumulated colour / TAA rows of the previous frame; its
     // first look at the flags is in flight across the wait for the fit
-    const bool zone = STRIP && halo_in_zone(P.halo_p, G.y0 - 1, G.y0 + ROWS + 1);
+    const bool zone = STRIP && halo_in_zone(P.halo_p, G.y0 - 1, G.y0 + PT_TILE + 1);
     const HaloPeek peek = halo_peek(P.halo_p, zone);
     pdl_wait();     // the fit of this frame is complete (weights, min/max)
     pdl_trigger();  // only now, so that "this frame's fit and reprojection are complete" also holds for the successor
     stamp_begin(P, 2);
     if (zone) halo_poll(P.halo_p, peek);
 
-    load_coefficients<FS>(P, sh.coef, bx, by, warp, lane, THREADS / 32);
+    load_coefficients_scaled<FS>(P, sh.coef, bx, by, warp, lane, WARPS);
     __syncthreads();  // the coefficients and the barrier's initialisation are visible
     mbar_wait_hot(&sh.bar, 0);
 
     const int x = G.x0 + lane;
-    const bool col_ok = x >= 0 && x < P.W;
-    const int rlo = STRIP ? P.state2_row0 : 0, rhi = (STRIP ? P.state2_row1 : P.H) - 1;
-    // phase A, interior: column strip x, rows 4*warp .. 4*warp+3, two vertically adjacent pixels at a time
-    f3 hist[4];
-    unsigned int live = 0;  // bit s: pixel s is written; bit 4+s: it takes the temporal path
-#if BMFR_POST_WS4
-    // the weighted sum of the whole strip first (shared-memory operands only), so that the coefficients are read once for
-    // four pixels; strips cut by an edge take the pair path below
-    f3 fl4[4];
-    const bool strip_whole = col_ok && G.y0 + 4 * warp >= P.py0 && G.y0 + 4 * warp + 3 < P.py1;
-    if (strip_whole) {
-        f3 n4[4], p4[4];
+    const int rlo = STRIP ? P.state2_row0 : 0, rhi = (STRIP ? P.state2_row1 : P.H) - 1;  // rows of accum / result this context holds
+    // interior tile (CTA-uniform): the halo lies inside the image and inside the rows phase A covers, every pixel is owned,
+    // no strip edge is near (no zone duties), frame > 0
+    const bool interior = BMFR_POST_FAST != 0 && P.frame > 0 && !zone && G.x0 >= 1 && G.x0 + 33 <= P.W && G.y0 >= 1 && G.y0 + 33 <= P.H &&
+                          G.y0 - 1 >= P.py0 && G.y0 + 33 <= P.py1 && G.y0 >= P.own_y0 && G.y0 + 32 <= P.own_y1;
+    f3 hist[PX];
+    unsigned int live = 0;  // bit s: pixel s is written; bit 4 + s: it takes the temporal path of the TAA
+    if (interior) {
+        const int W3 = 3 * P.W;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            n4[k] = cell_f3(sh.nrm, G, lane + 1, 4 * warp + k + 1);
-            p4[k] = cell_f3(sh.pos, G, lane + 1, 4 * warp + k + 1);
-        }
-        weighted_sum_px4<FS>(n4, p4, sh.coef[4], fl4);
-    }
-#endif
-#pragma unroll
-    for (int s = 0; s < 4; s += 2) {
-        const int ty = 4 * warp + s, y = G.y0 + ty;
-        hist[s] = hist[s + 1] = make_f3(0.f, 0.f, 0.f);
-        const bool v0 = col_ok && y >= P.py0 && y < P.py1, v1 = col_ok && y + 1 >= P.py0 && y + 1 < P.py1;
-        const bool own0 = y >= P.own_y0 && y < P.own_y1, own1 = y + 1 >= P.own_y0 && y + 1 < P.own_y1;
-        if (v0 && v1) {
+        for (int s = 0; s < PX; s += 2) {
+            const int ty = PX * warp + s, y = G.y0 + ty;
             const PixelIn i0 = load_pixel_staged(sh, P, G, lane + 1, ty + 1, x, y), i1 = load_pixel_staged(sh, P, G, lane + 1, ty + 2, x, y + 1);
-            bool t0 = false, t1 = false;
-            if (P.frame > 0) {
-                const TapGeom g0 = tap_geom(i0.pp), g1 = tap_geom(i1.pp);
-                // one round of independent loads from clamped addresses: tap rows R0, R1 of the upper pixel, R2 of the lower;
-                // the lower pixel's upper row is R1 when the two footprints are stacked (checked below)
+            const TapGeom g0 = tap_geom(i0.pp), g1 = tap_geom(i1.pp);
+            // the pair's footprints: stacked (rows piy, piy + 1, piy + 2 of columns pix, pix + 1) and inside the image / the rows held?
+            const bool easy = (unsigned int)g0.pix < (unsigned int)(P.W - 1) && g0.piy >= rlo && g0.piy + 2 <= rhi && g1.pix == g0.pix &&
+                              g1.piy == g0.piy + 1;
+            float A[3][6], R[3][6];
+            f3 fl0, fl1;
+            if (__all_sync(0xffffffffu, easy)) {
+                const size_t base = (size_t)(pix_index(P, g0.pix, g0.piy) * 3u);
+                const float* a = P.accum_prev + base;
+                const float* r = P.result_prev + base;
+#pragma unroll
+                for (int row = 0; row < 3; ++row) {
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) {
+                        A[row][k] = __ldg(a + row * W3 + k);
+                        R[row][k] = __ldg(r + row * W3 + k);
+                    }
+                }
+                weighted_sum_scaled_px2<FS>(i0.n, i0.p, i1.n, i1.p, sh.coef[4], fl0, fl1);  // its arithmetic overlaps the gathers
+                hist[s] = history_ycc<true>(g0.w, R[0], R[1], 15u);
+                hist[s + 1] = history_ycc<true>(g1.w, R[1], R[2], 15u);
+                live |= 0x33u << s;
+            } else {  // some lane's footprint touches an edge or its pair is not stacked: clamped addresses, per-tap validity
                 const int cx0[2] = {min(max(g0.pix, 0), P.W - 1), min(max(g0.pix + 1, 0), P.W - 1)};
                 const int cx1[2] = {min(max(g1.pix, 0), P.W - 1), min(max(g1.pix + 1, 0), P.W - 1)};
                 const int ry0[2] = {min(max(g0.piy, rlo), rhi), min(max(g0.piy + 1, rlo), rhi)};
                 const int ry1[2] = {min(max(g1.piy, rlo), rhi), min(max(g1.piy + 1, rlo), rhi)};
-                f3 A[3][2], R[3][2];
 #pragma unroll
                 for (int dx = 0; dx < 2; ++dx) {
                     const unsigned int l0 = pix_index(P, cx0[dx], ry0[0]), l1 = pix_index(P, cx0[dx], ry0[1]), l2 = pix_index(P, cx1[dx], ry1[1]);
-                    A[0][dx] = load_f3(P.accum_prev, l0); A[1][dx] = load_f3(P.accum_prev, l1); A[2][dx] = load_f3(P.accum_prev, l2);
-                    R[0][dx] = load_f3(P.result_prev, l0); R[1][dx] = load_f3(P.result_prev, l1); R[2][dx] = load_f3(P.result_prev, l2);
+                    f3_to(&A[0][3 * dx], load_f3(P.accum_prev, l0)); f3_to(&A[1][3 * dx], load_f3(P.accum_prev, l1)); f3_to(&A[2][3 * dx], load_f3(P.accum_prev, l2));
+                    f3_to(&R[0][3 * dx], load_f3(P.result_prev, l0)); f3_to(&R[1][3 * dx], load_f3(P.result_prev, l1)); f3_to(&R[2][3 * dx], load_f3(P.result_prev, l2));
                 }
-                f3 fl0, fl1;
-#if BMFR_POST_WS4
-                if (strip_whole) { fl0 = fl4[s]; fl1 = fl4[s + 1]; }
-                else
-#endif
-                weighted_sum_px2<FS>(i0.n, i0.p, i1.n, i1.p, sh.coef[4], fl0, fl1);  // its arithmetic overlaps the gathers
-                t0 = resolve_pixel<STRIP>(sh, P, G, i0, g0, fl0, A[0], A[1], R[0], R[1], lane + 1, ty + 1, x, y, own0, hist[s], zone);
-                if (!(cx1[0] == cx0[0] && cx1[1] == cx0[1] && ry1[0] == ry0[1])) {  // footprints not stacked (rare): fetch the row
+                weighted_sum_scaled_px2<FS>(i0.n, i0.p, i1.n, i1.p, sh.coef[4], fl0, fl1);
+                const bool t0 = history_in_reach(P, g0), t1 = history_in_reach(P, g1);
+                const unsigned int ok0 = history_taps_ok(P, g0), ok1 = history_taps_ok(P, g1);
+                if (STRIP) {
+                    const bool o00 = g0.piy < P.state2_row0 || g0.piy >= P.state2_row1, o01 = g0.piy + 1 < P.state2_row0 || g0.piy + 1 >= P.state2_row1;
+                    const bool o10 = g1.piy < P.state2_row0 || g1.piy >= P.state2_row1, o11 = g1.piy + 1 < P.state2_row0 || g1.piy + 1 >= P.state2_row1;
+                    const unsigned int w0 = i0.accept | (t0 ? ok0 : 0u), w1 = i1.accept | (t1 ? ok1 : 0u);
+                    if (((w0 & 3u) != 0 && o00) || ((w0 & 12u) != 0 && o01) || ((w1 & 3u) != 0 && o10) || ((w1 & 12u) != 0 && o11)) *P.oob_flag = 1;
+                }
+                hist[s] = history_ycc<false>(g0.w, R[0], R[1], ok0);
+                if (!(cx1[0] == cx0[0] && cx1[1] == cx0[1] && ry1[0] == ry0[1])) {  // footprints not stacked: fetch the lower pixel's upper row
+                    // (the upper pixel's accumulation below needs its own lower row: finish it first)
+                    const f3 acc0 = accumulate_taps(P, i0.accept, i0.spp, g0.w, fl0, A[0], A[1]);
+                    store_f3(P.accum_cur, i0.lp, acc0);
+                    put_cell_i(sh, G, lane + 1, ty + 1, tone_ycocg(i0.alb, acc0));
 #pragma unroll
                     for (int dx = 0; dx < 2; ++dx) {
                         const unsigned int l = pix_index(P, cx1[dx], ry1[0]);
-                        A[1][dx] = load_f3(P.accum_prev, l);
-                        R[1][dx] = load_f3(P.result_prev, l);
+                        f3_to(&A[1][3 * dx], load_f3(P.accum_prev, l));
+                        f3_to(&R[1][3 * dx], load_f3(P.result_prev, l));
                     }
+                    hist[s + 1] = history_ycc<false>(g1.w, R[1], R[2], ok1);
+                    const f3 acc1 = accumulate_taps(P, i1.accept, i1.spp, g1.w, fl1, A[1], A[2]);
+                    store_f3(P.accum_cur, i1.lp, acc1);
+                    put_cell_i(sh, G, lane + 1, ty + 2, tone_ycocg(i1.alb, acc1));
+                    live |= ((1u | (t0 ? 16u : 0u)) | ((1u | (t1 ? 16u : 0u)) << 1)) << s;
+                    continue;
                 }
-                t1 = resolve_pixel<STRIP>(sh, P, G, i1, g1, fl1, A[1], A[2], R[1], R[2], lane + 1, ty + 2, x, y + 1, own1, hist[s + 1], zone);
-            } else {  // frame 0: no temporal path, alpha = 1 (bmfr.cl:784, 884)
-                f3 fl0, fl1;
-#if BMFR_POST_WS4
-                if (strip_whole) { fl0 = fl4[s]; fl1 = fl4[s + 1]; }
-                else
-#endif
-                weighted_sum_px2<FS>(i0.n, i0.p, i1.n, i1.p, sh.coef[4], fl0, fl1);
-                store_f3(P.accum_cur, i0.lp, fl0);
-                store_f3(P.accum_cur, i1.lp, fl1);
-                if (STRIP && zone) {
-                    stage_accum(sh, G, lane + 1, ty + 1, fl0);
-                    stage_accum(sh, G, lane + 1, ty + 2, fl1);
-                }
-                put_ycc_i(sh, P, G, lane + 1, ty + 1, x, y,
-                          to_ycocg(make_f3(tone_map_fast(i0.alb.x * fl0.x), tone_map_fast(i0.alb.y * fl0.y), tone_map_fast(i0.alb.z * fl0.z))));
-                put_ycc_i(sh, P, G, lane + 1, ty + 2, x, y + 1,
-                          to_ycocg(make_f3(tone_map_fast(i1.alb.x * fl1.x), tone_map_fast(i1.alb.y * fl1.y), tone_map_fast(i1.alb.z * fl1.z))));
+                hist[s + 1] = history_ycc<false>(g1.w, R[1], R[2], ok1);
+                live |= ((1u | (t0 ? 16u : 0u)) | ((1u | (t1 ? 16u : 0u)) << 1)) << s;
             }
-            live |= ((own0 ? 1u : 0u) | (t0 ? 16u : 0u)) << s;
-            live |= ((own1 ? 1u : 0u) | (t1 ? 16u : 0u)) << (s + 1);
-        } else if (v0) {  // a strip or image edge cuts the pair
-            const bool t = staged_pixel<STRIP, FS>(sh, P, G, sh.coef[4], lane + 1, ty + 1, x, y, true, own0, hist[s], zone);
-            live |= ((own0 ? 1u : 0u) | (t ? 16u : 0u)) << s;
-        } else if (v1) {
-            const bool t = staged_pixel<STRIP, FS>(sh, P, G, sh.coef[4], lane + 1, ty + 2, x, y + 1, true, own1, hist[s + 1], zone);
-            live |= ((own1 ? 1u : 0u) | (t ? 16u : 0u)) << (s + 1);
+            const f3 acc0 = accumulate_taps(P, i0.accept, i0.spp, g0.w, fl0, A[0], A[1]);
+            const f3 acc1 = accumulate_taps(P, i1.accept, i1.spp, g1.w, fl1, A[1], A[2]);
+            store_f3(P.accum_cur, i0.lp, acc0);
+            store_f3(P.accum_cur, i1.lp, acc1);
+            put_cell_i(sh, G, lane + 1, ty + 1, tone_ycocg(i0.alb, acc0));
+            put_cell_i(sh, G, lane + 1, ty + 2, tone_ycocg(i1.alb, acc1));
+        }
+    } else {
+        // general tile: image edges, strip edges, rows that are only partly covered or owned, zone duties, frame 0
+        const bool col_ok = x >= 0 && x < P.W;
+#pragma unroll
+        for (int s = 0; s < PX; s += 2) {
+            const int ty = PX * warp + s, y = G.y0 + ty;
+            hist[s] = hist[s + 1] = make_f3(0.f, 0.f, 0.f);
+            const bool v0 = col_ok && y >= P.py0 && y < P.py1, v1 = col_ok && y + 1 >= P.py0 && y + 1 < P.py1;
+            const bool own0 = y >= P.own_y0 && y < P.own_y1, own1 = y + 1 >= P.own_y0 && y + 1 < P.own_y1;
+            if (v0 && v1) {
+                const PixelIn i0 = load_pixel_staged(sh, P, G, lane + 1, ty + 1, x, y), i1 = load_pixel_staged(sh, P, G, lane + 1, ty + 2, x, y + 1);
+                const TapGeom g0 = tap_geom(i0.pp), g1 = tap_geom(i1.pp);
+                float A[3][6], R[3][6];
+                f3 fl0, fl1;
+                bool t0 = false, t1 = false;
+                unsigned int acc_bits0 = 0, acc_bits1 = 0;
+                bool stacked = true;
+                if (P.frame > 0) {
+                    // one round of independent loads from clamped addresses: tap rows R0, R1 of the upper pixel, R2 of the lower;
+                    // the lower pixel's upper row is R1 when the two footprints are stacked (checked below)
+                    const int cx0[2] = {min(max(g0.pix, 0), P.W - 1), min(max(g0.pix + 1, 0), P.W - 1)};
+                    const int cx1[2] = {min(max(g1.pix, 0), P.W - 1), min(max(g1.pix + 1, 0), P.W - 1)};
+                    const int ry0[2] = {min(max(g0.piy, rlo), rhi), min(max(g0.piy + 1, rlo), rhi)};
+                    const int ry1[2] = {min(max(g1.piy, rlo), rhi), min(max(g1.piy + 1, rlo), rhi)};
+#pragma unroll
+                    for (int dx = 0; dx < 2; ++dx) {
+                        const unsigned int l0 = pix_index(P, cx0[dx], ry0[0]), l1 = pix_index(P, cx0[dx], ry0[1]), l2 = pix_index(P, cx1[dx], ry1[1]);
+                        f3_to(&A[0][3 * dx], load_f3(P.accum_prev, l0)); f3_to(&A[1][3 * dx], load_f3(P.accum_prev, l1)); f3_to(&A[2][3 * dx], load_f3(P.accum_prev, l2));
+                        f3_to(&R[0][3 * dx], load_f3(P.result_prev, l0)); f3_to(&R[1][3 * dx], load_f3(P.result_prev, l1)); f3_to(&R[2][3 * dx], load_f3(P.result_prev, l2));
+                    }
+                    weighted_sum_scaled_px2<FS>(i0.n, i0.p, i1.n, i1.p, sh.coef[4], fl0, fl1);  // its arithmetic overlaps the gathers
+                    acc_bits0 = i0.accept; acc_bits1 = i1.accept;
+                    t0 = own0 && history_in_reach(P, g0);
+                    t1 = own1 && history_in_reach(P, g1);
+                    const unsigned int ok0 = history_taps_ok(P, g0), ok1 = history_taps_ok(P, g1);
+                    if (STRIP) {  // a wanted tap whose row this strip does not hold: reported once, the run is invalid
+                        const bool o00 = g0.piy < P.state2_row0 || g0.piy >= P.state2_row1, o01 = g0.piy + 1 < P.state2_row0 || g0.piy + 1 >= P.state2_row1;
+                        const bool o10 = g1.piy < P.state2_row0 || g1.piy >= P.state2_row1, o11 = g1.piy + 1 < P.state2_row0 || g1.piy + 1 >= P.state2_row1;
+                        const unsigned int w0 = i0.accept | (t0 ? ok0 : 0u), w1 = i1.accept | (t1 ? ok1 : 0u);
+                        if (((w0 & 3u) != 0 && o00) || ((w0 & 12u) != 0 && o01) || ((w1 & 3u) != 0 && o10) || ((w1 & 12u) != 0 && o11)) *P.oob_flag = 1;
+                    }
+                    if (t0) hist[s] = history_ycc<false>(g0.w, R[0], R[1], ok0);
+                    stacked = cx1[0] == cx0[0] && cx1[1] == cx0[1] && ry1[0] == ry0[1];
+                    if (!stacked) {  // rare: finish the upper pixel, then fetch the lower pixel's own upper row
+                        const f3 acc0 = accumulate_taps(P, acc_bits0, i0.spp, g0.w, fl0, A[0], A[1]);
+                        store_f3(P.accum_cur, i0.lp, acc0);
+                        if (STRIP && zone) stage_accum(sh, G, lane + 1, ty + 1, acc0);
+                        put_ycc_i(sh, P, G, lane + 1, ty + 1, x, y, tone_ycocg(i0.alb, acc0));
+#pragma unroll
+                        for (int dx = 0; dx < 2; ++dx) {
+                            const unsigned int l = pix_index(P, cx1[dx], ry1[0]);
+                            f3_to(&A[1][3 * dx], load_f3(P.accum_prev, l));
+                            f3_to(&R[1][3 * dx], load_f3(P.result_prev, l));
+                        }
+                    }
+                    if (t1) hist[s + 1] = history_ycc<false>(g1.w, R[1], R[2], ok1);
+                } else {  // frame 0: no temporal path (bmfr.cl:784, 884): accept = 0 makes the accumulated colour the filtered one
+#pragma unroll
+                    for (int row = 0; row < 3; ++row)
+#pragma unroll
+                        for (int k = 0; k < 6; ++k) A[row][k] = 0.f;
+                    weighted_sum_scaled_px2<FS>(i0.n, i0.p, i1.n, i1.p, sh.coef[4], fl0, fl1);
+                }
+                if (stacked) {
+                    const f3 acc0 = accumulate_taps(P, acc_bits0, i0.spp, g0.w, fl0, A[0], A[1]);
+                    store_f3(P.accum_cur, i0.lp, acc0);
+                    if (STRIP && zone) stage_accum(sh, G, lane + 1, ty + 1, acc0);
+                    put_ycc_i(sh, P, G, lane + 1, ty + 1, x, y, tone_ycocg(i0.alb, acc0));
+                }
+                const f3 acc1 = accumulate_taps(P, acc_bits1, i1.spp, g1.w, fl1, A[1], A[2]);
+                store_f3(P.accum_cur, i1.lp, acc1);
+                if (STRIP && zone) stage_accum(sh, G, lane + 1, ty + 2, acc1);
+                put_ycc_i(sh, P, G, lane + 1, ty + 2, x, y + 1, tone_ycocg(i1.alb, acc1));
+                live |= ((own0 ? 1u : 0u) | (t0 ? 16u : 0u)) << s;
+                live |= ((own1 ? 1u : 0u) | (t1 ? 16u : 0u)) << (s + 1);
+            } else if (v0) {  // a strip or image edge cuts the pair
+                const bool t = single_pixel<STRIP, FS>(sh, P, G, sh.coef[4], lane + 1, ty + 1, x, y, true, own0, hist[s], zone);
+                live |= ((own0 ? 1u : 0u) | (t ? 16u : 0u)) << s;
+            } else if (v1) {
+                const bool t = single_pixel<STRIP, FS>(sh, P, G, sh.coef[4], lane + 1, ty + 2, x, y + 1, true, own1, hist[s + 1], zone);
+                live |= ((own1 ? 1u : 0u) | (t ? 16u : 0u)) << (s + 1);
+            }
         }
     }
-    // phase A, ring: 2 * 33 + 2 * (HY - 1) pixels (132 / 100), coefficients of the pixel's own block — for a half tile the
-    // row below the upper half / above the lower half belongs to the same block
-    if (tid < 2 * (PT_HALO - 1) + 2 * (HY - 1)) {
+    // phase A, ring: 4 * 33 = 132 pixels, coefficients of the pixel's own block
+    if (tid < 4 * (PT_HALO - 1)) {
         int hx, hy;
         if (tid < PT_HALO - 1) { hx = tid; hy = 0; }
-        else if (tid < PT_HALO - 1 + HY - 1) { hx = PT_HALO - 1; hy = tid - (PT_HALO - 1); }
-        else if (tid < 2 * (PT_HALO - 1) + HY - 1) { hx = PT_HALO - 1 - (tid - (PT_HALO - 1 + HY - 1)); hy = HY - 1; }
-        else { hx = 0; hy = HY - 1 - (tid - (2 * (PT_HALO - 1) + HY - 1)); }
+        else if (tid < 2 * (PT_HALO - 1)) { hx = PT_HALO - 1; hy = tid - (PT_HALO - 1); }
+        else if (tid < 3 * (PT_HALO - 1)) { hx = PT_HALO - 1 - (tid - 2 * (PT_HALO - 1)); hy = PT_HALO - 1; }
+        else { hx = 0; hy = PT_HALO - 1 - (tid - 3 * (PT_HALO - 1)); }
         const int rx = G.x0 + hx - 1, ry = G.y0 + hy - 1;
-        if (rx >= 0 && rx < P.W && ry >= P.py0 && ry < P.py1) {
-            const int nrow = (hy == 0) ? ((ROWS == 32 || half == 0) ? 0 : 3) : (hy == HY - 1) ? ((ROWS == 32 || half == 1) ? 6 : 3) : 3;
-            const int nb = nrow + ((hx == 0) ? 0 : (hx == PT_HALO - 1) ? 2 : 1);
+        if (interior || (rx >= 0 && rx < P.W && ry >= P.py0 && ry < P.py1)) {
+            const int nb = ((hy == 0) ? 0 : (hy == PT_HALO - 1) ? 6 : 3) + ((hx == 0) ? 0 : (hx == PT_HALO - 1) ? 2 : 1);
             f3 unused;
-            staged_pixel<STRIP, FS>(sh, P, G, sh.coef[nb], hx, hy, rx, ry, false, false, unused, zone);
+            single_pixel<STRIP, FS>(sh, P, G, sh.coef[nb], hx, hy, rx, ry, false, false, unused, zone);
         }
     }
     __syncthreads();
 
-    // phase B: clamp the history samples to the neighbourhood box, component by component (bmfr.cl:893-920, 967-969).  Halo
-    // rows 4*warp .. 4*warp+5 cover the 3x3 neighbourhoods of the strip; this thread's column is lane+1.
-    f3 mine[4];
+    // phase B: clamp the history samples to the neighbourhood box, component by component (bmfr.cl:893-920, 967-969), blend
+    // (bmfr.cl:971-973; in YCoCg, the weights carry the 0.25 of the conversion back) and store.  Halo rows PX * warp ..
+    // PX * warp + PX + 1 cover the 3x3 neighbourhoods of the strip; this thread's column is lane + 1.  A pixel on the
+    // copy-through path of bmfr.cl:884-890 keeps its own colour.
+    const float a = __fmul_rn(0.25f, P.taa_blend_alpha), oma = __fmul_rn(0.25f, __fsub_rn(1.f, P.taa_blend_alpha));
+    f3 out[PX];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        float ctr[6], rmin[6], rmax[6];
+        float ctr[PX + 2], rmin[PX + 2], rmax[PX + 2];
 #pragma unroll
-        for (int r = 0; r < 6; ++r) {
-            const float* row = &sh.alb[4 * warp + r][G.sh_rgb + c];
+        for (int r = 0; r < PX + 2; ++r) {
+            const float* row = &sh.alb[PX * warp + r][G.sh_rgb + c];
             const float l = row[3 * lane], m = row[3 * lane + 3], rr = row[3 * lane + 6];
             ctr[r] = m;
             rmin[r] = fminf(fminf(l, m), rr);
             rmax[r] = fmaxf(fmaxf(l, m), rr);
         }
 #pragma unroll
-        for (int s = 0; s < 4; ++s) {
+        for (int s = 0; s < PX; ++s) {
             const float min_box = fminf(fminf(rmin[s], rmin[s + 1]), rmin[s + 2]);
             const float max_box = fmaxf(fmaxf(rmax[s], rmax[s + 1]), rmax[s + 2]);
             const float min_cross = fminf(fminf(ctr[s], rmin[s + 1]), ctr[s + 2]);
             const float max_cross = fmaxf(fmaxf(ctr[s], rmax[s + 1]), ctr[s + 2]);
-            const float lo = (min_box + min_cross) * 0.5f, hi = (max_box + max_cross) * 0.5f;
-            float& h = (c == 0) ? hist[s].x : (c == 1) ? hist[s].y : hist[s].z;
-            h = fminf(fmaxf(h, lo), hi);
-            float& m = (c == 0) ? mine[s].x : (c == 1) ? mine[s].y : mine[s].z;
-            m = ctr[s + 1];
+            const float lo = __fmul_rn(__fadd_rn(min_box, min_cross), 0.5f), hi = __fmul_rn(__fadd_rn(max_box, max_cross), 0.5f);
+            const float h = (c == 0) ? hist[s].x : (c == 1) ? hist[s].y : hist[s].z;
+            const float hc = fminf(fmaxf(h, lo), hi);
+            const float mine = ctr[s + 1];
+            const float v = (live & (16u << s)) ? fmaf(a, mine, __fmul_rn(oma, hc)) : __fmul_rn(0.25f, mine);
+            if (c == 0) out[s].x = v; else if (c == 1) out[s].y = v; else out[s].z = v;
         }
     }
-    // blend and store (bmfr.cl:971-973)
-    const float a = P.taa_blend_alpha, oma = 1.f - P.taa_blend_alpha;
 #pragma unroll
-    for (int s = 0; s < 4; ++s) {
+    for (int s = 0; s < PX; ++s) {
         if (!(live & (1u << s))) continue;
-        const unsigned int lp = pix_index(P, x, G.y0 + 4 * warp + s);
-        f3 out = from_ycocg(mine[s]);  // this pixel's tone-mapped colour
-        if (live & (16u << s)) {
-            const f3 pr = from_ycocg(hist[s]);
-            out = make_f3(fmaf(a, out.x, oma * pr.x), fmaf(a, out.y, oma * pr.y), fmaf(a, out.z, oma * pr.z));
-        }
-        store_f3(P.result_cur, lp, out);
-        if (P.user_out) store_f3(P.user_out, lp, out);
-        if (STRIP && zone) stage_result(sh, G, lane + 1, 4 * warp + s + 1, out);
+        const unsigned int lp = pix_index(P, x, G.y0 + PX * warp + s);
+        const f3 rgb = from_quarter_ycocg(out[s]);
+        store_f3(P.result_cur, lp, rgb);
+        if (P.user_out) store_f3(P.user_out, lp, rgb);
+        if (STRIP && zone) stage_result(sh, G, lane + 1, PX * warp + s + 1, rgb);
     }
     if (STRIP && zone) {
         __syncthreads();  // the staged rows are complete
-        post_push_rows(P, sh, G, tid);
-        halo_finish(P.halo_p, halo_cta_pushes(P.halo_p, G.y0, G.y0 + ROWS));
+        post_push_rows<THREADS>(P, sh, G, tid);
+        halo_finish(P.halo_p, halo_cta_pushes(P.halo_p, G.y0, G.y0 + PT_TILE));
     }
     stamp_end(P, 2);
 }
@@ -952,43 +1131,38 @@ __global__ void __launch_bounds__(8 * ROWS, BMFR_POST_TMA_MIN_BLOCKS * 32 / ROWS
 #endif
 
 // Tensor maps of the frame's six read-once inputs, or false when the TMA path cannot be used (then post_kernel runs).
-static bool post_maps(const KParams& P, PostMaps* M, int box_rows) {
+static bool post_maps(const KParams& P, PostMaps* M) {
     const int rows = P.row1 - P.row0;
     if (!BMFR_POST_TMA || (P.W & 15) != 0 || rows < PT_HALO || P.W * 3 < PT_RGB_W) return false;
-    return bmfr_tensor_map_2d(P.cur_normals, 4, (long long)P.W * 3, rows, PT_RGB_W, box_rows, &M->normals) &&
-           bmfr_tensor_map_2d(P.cur_positions, 4, (long long)P.W * 3, rows, PT_RGB_W, box_rows, &M->positions) &&
-           bmfr_tensor_map_2d(P.albedo, 4, (long long)P.W * 3, rows, PT_RGB_W, box_rows, &M->albedo) &&
-           bmfr_tensor_map_2d(P.prev_pixels, 4, (long long)P.W * 2, rows, PT_PP_W, box_rows, &M->pp) &&
-           bmfr_tensor_map_2d(P.accept, 1, (long long)P.W, rows, PT_U8_W, box_rows, &M->accept) &&
-           bmfr_tensor_map_2d(P.cur_spp, 1, (long long)P.W, rows, PT_U8_W, box_rows, &M->spp);
+    return bmfr_tensor_map_2d(P.cur_normals, 4, (long long)P.W * 3, rows, PT_RGB_W, PT_HALO, &M->normals) &&
+           bmfr_tensor_map_2d(P.cur_positions, 4, (long long)P.W * 3, rows, PT_RGB_W, PT_HALO, &M->positions) &&
+           bmfr_tensor_map_2d(P.albedo, 4, (long long)P.W * 3, rows, PT_RGB_W, PT_HALO, &M->albedo) &&
+           bmfr_tensor_map_2d(P.prev_pixels, 4, (long long)P.W * 2, rows, PT_PP_W, PT_HALO, &M->pp) &&
+           bmfr_tensor_map_2d(P.accept, 1, (long long)P.W, rows, PT_U8_W, PT_HALO, &M->accept) &&
+           bmfr_tensor_map_2d(P.cur_spp, 1, (long long)P.W, rows, PT_U8_W, PT_HALO, &M->spp);
 }
 
 template <int FS>
 static cudaError_t launch_post_fs(const KParams& P, cudaStream_t st) {
     const dim3 grid(P.blocks_x, P.by1 - P.by0);
     const bool strip = P.row0 != 0 || P.row1 != P.H;
-    // tile height: whole images run half tiles (six 128-thread CTAs per SM), strips whole blocks — their zone bookkeeping
-    // (fill_halo counts zone CTAs per block row) and row staging are laid out for 32 x 32 tiles
-    constexpr int WHOLE_ROWS = BMFR_POST_TILE_ROWS;
-    using StageW = PostStageT<WHOLE_ROWS + 2>;
-    using StageS = PostStageT<32 + 2>;
-    constexpr size_t smem_w = sizeof(StageW) + BMFR_POST_SMEM_PAD;
+    constexpr int PXW = BMFR_POST_PX, PXS = 4;  // pixels per thread: whole image / strips
+    constexpr size_t smem_w = sizeof(PostStage) + BMFR_POST_SMEM_PAD;
     PostMaps M;
-    if (post_maps(P, &M, (strip ? 32 : WHOLE_ROWS) + 2)) {
+    if (post_maps(P, &M)) {
         static bool done[64] = {};
         int dev = 0;
         cudaError_t e = cudaGetDevice(&dev);
         if (e != cudaSuccess) return e;
         if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
         if (!done[dev]) {
-            e = cudaFuncSetAttribute(post_tma_kernel<false, FS, WHOLE_ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(post_tma_kernel<true, FS, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StageS));
+            e = cudaFuncSetAttribute(post_tma_kernel<false, FS, PXW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(post_tma_kernel<true, FS, PXS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PostStage));
             if (e != cudaSuccess) return e;
             done[dev] = true;
         }
-        if (strip) return launch_pdl(!P.plain_launch, post_tma_kernel<true, FS, 32>, grid, dim3(256), sizeof(StageS), st, P, M);
-        const dim3 grid_w(P.blocks_x, (P.by1 - P.by0) * (32 / WHOLE_ROWS));
-        return launch_pdl(!P.plain_launch, post_tma_kernel<false, FS, WHOLE_ROWS>, grid_w, dim3(8 * WHOLE_ROWS), smem_w, st, P, M);
+        if (strip) return launch_pdl(!P.plain_launch, post_tma_kernel<true, FS, PXS>, grid, dim3(1024 / PXS), sizeof(PostStage), st, P, M);
+        return launch_pdl(!P.plain_launch, post_tma_kernel<false, FS, PXW>, grid, dim3(1024 / PXW), smem_w, st, P, M);
     }
     // widths that are no multiple of 16 (no tensor maps): the per-thread-load variant.  (Its 64+32-bit pixel accesses,
     // BMFR_POST_WIDE_ACCESS, cost 38 % more instructions for the same L1 wavefronts and stay a tuning switch.)
