@@ -536,6 +536,19 @@ __device__ __forceinline__ void qr_draw_next(const KParams& P, const QrMaps& M, 
     else mbar_arrive(&sh.data_full);
 }
 
+// The second half of qr_draw_next() for a draw that was issued earlier (fit_gram_kernel): publish the block, start its loads.
+template <class SH>
+__device__ __forceinline__ void qr_start_next(const KParams& P, const QrMaps& M, SH& sh, int it, int nblocks, int draw) {
+    const int nl = draw < nblocks ? qr_block_of_draw(draw, nblocks, P.blocks_x, P.frame) : nblocks;
+    sh.blk[(it + 1) & 1] = nl;
+    int ox, oy;
+    if (nl < nblocks && qr_block_box(P, nl % P.blocks_x, P.by0 + nl / P.blocks_x, ox, oy) && M.use_tma) qr_prefetch(P, M, sh, ox, oy);
+    else mbar_arrive(&sh.data_full);
+}
+#ifndef BMFR_GRAM_EARLY_DRAW
+#define BMFR_GRAM_EARLY_DRAW 1
+#endif
+
 #ifndef BMFR_QR_MIN_BLOCKS
 #define BMFR_QR_MIN_BLOCKS 4
 #endif
@@ -1101,6 +1114,14 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_GRAM_MIN_BLOCKS) fit_gram_ker
         if (it < 6) GRAM_STAMP(2 + 2 * it);
         const int group = P.by0 * P.blocks_x + local;
         const int bx = local % P.blocks_x, by = P.by0 + local / P.blocks_x;
+#if BMFR_GRAM_EARLY_DRAW
+        // The draw of the next block, issued a phase ahead of its use: the atomic's round trip to the L2 (and, with the lazy
+        // draws, the read of the counter in front of it) used to sit on thread 0's path behind the block barrier — the source-
+        // level profile had 9.6 % of ALL warp samples there, i.e. 38 % of warp 0's time, with the next block's tiles requested
+        // that much later and the other three warps waiting for them at the top of the next iteration.
+        int next_draw = 0;
+        if (tid == 0) next_draw = stride + atomicAdd(P.block_counter, 1);
+#endif
 
         // a[s][c-1] = column c of row (x_in = lane, y_in = 8 warp + s): the 12 non-constant K1 values (bmfr.cl:448-453), NaN -> 0
         float a[ROWS][NCOL];
@@ -1214,9 +1235,13 @@ __global__ void __launch_bounds__(QR_THREADS, BMFR_GRAM_MIN_BLOCKS) fit_gram_ker
         bool late_draw = false;
         if (tid == 0) {
             sh.mine[mine] = local;
+#if BMFR_GRAM_EARLY_DRAW
+            qr_start_next(P, M, sh, it, nblocks, next_draw);
+#else
             if (BMFR_QR_LAZY_DIV > 0)
                 late_draw = nblocks - stride - *(volatile int*)P.block_counter < stride / (BMFR_QR_LAZY_DIV > 0 ? BMFR_QR_LAZY_DIV : 1);
             if (!late_draw) qr_draw_next(P, M, sh, it, nblocks, stride);
+#endif
         }
         // every warp finishes the reductions itself: lane f < NSC owns scaled feature f, lane c < NCOL the mean of column c + 1
         float inv[NSC], mean[NCOL];

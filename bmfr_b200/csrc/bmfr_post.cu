@@ -516,6 +516,7 @@ __global__ void __launch_bounds__(256, BMFR_POST_MIN_BLOCKS) post_kernel(const _
 #define PT_RGB_W 108  // floats per staged row of an interleaved-RGB image: 34 pixels + up to 3 floats of alignment shift
 #define PT_PP_W 72    // floats per staged row of prev_pixels: 34 float2 + 2 floats of shift
 #define PT_U8_W 64    // bytes per staged row of accept / spp: 34 + up to 15 bytes of shift
+#define PT_COEF_S 40  // floats of a block's pre-scaled coefficient record: F x (w_r, w_g, w_b, min), F <= 10
 
 // A tile is 32 x 32 pixels; the stage holds it with its one-pixel ring: HY = 34 rows.
 template <int HY_>
@@ -528,8 +529,9 @@ struct __align__(128) PostStageT {  // every TMA destination starts on a 128-byt
     float pp[HY_][PT_PP_W];   char pad3[64];
     unsigned char acc[HY_][PT_U8_W];
     unsigned char spp[HY_][PT_U8_W];
-    float coef[9][PT_COEF];
-    unsigned long long bar;
+    float coef[2][9][PT_COEF_S];  // two tiles' worth: the persistent kernel loads the next tile's while this one is in phase B
+    unsigned long long bar;      // the tile's inputs have landed (persistent kernel: all but the albedo)
+    unsigned long long bar_alb;  // persistent kernel: the tile's albedo has landed
     static_assert(sizeof(float[HY_][PT_RGB_W]) % 128 == 96 && sizeof(float[HY_][PT_PP_W]) % 128 == 64 && (HY_ * PT_U8_W) % 128 == 0,
                   "TMA destinations must stay 128-byte aligned");
 };
@@ -569,11 +571,20 @@ __device__ __forceinline__ PixelIn load_pixel_staged(const PostStage& sh, const 
     in.lp = pix_index(P, x, y);
     in.n = cell_f3(sh.nrm, G, hx, hy);
     in.p = cell_f3(sh.pos, G, hx, hy);
-    in.alb = cell_f3(sh.alb, G, hx, hy);
     in.pp = *reinterpret_cast<const float2*>(&sh.pp[hy][G.sh_pp + 2 * hx]);
     in.accept = sh.acc[hy][G.sh_u8 + hx];
     in.spp = sh.spp[hy][G.sh_u8 + hx];
     return in;
+}
+// The pixel's albedo (its cell later holds the pixel's YCoCg value).  The persistent kernel fetches a tile's albedo box behind
+// the other inputs (the cells are busy with the previous tile's phase B until then), on a barrier of its own: gate.bar != nullptr.
+struct AlbGate {
+    unsigned long long* bar;
+    unsigned int parity;
+};
+__device__ __forceinline__ f3 albedo_cell(const PostStage& sh, const TileGeom& G, const AlbGate& gate, int hx, int hy) {
+    if (gate.bar != nullptr) mbar_wait_hot(gate.bar, gate.parity);
+    return cell_f3(sh.alb, G, hx, hy);
 }
 // Zone CTAs of a strip (HaloK) do not send a mirrored row pixel by pixel: a pixel's accumulated colour goes into its own
 // (already consumed) normal cell, its TAA result into its position cell, and after the last pixel the CTA sends whole row
@@ -615,22 +626,46 @@ __device__ __forceinline__ void post_push_rows(const KParams& P, const PostStage
 // ---- the arithmetic of one pixel (shared by every path; explicit intrinsics, see the banner) ----------------------------
 // F x (w_r * s_f, w_g * s_f, w_b * s_f, min_f) per block, s_f = 1/range (scale_factor()) for the scaled features, 1 and
 // min = 0 otherwise: warp w takes neighbour w of the 3x3 block neighbourhood, (dy + 1) * 3 + dx + 1 (warp 0 also the ninth).
+struct CoefRegs {  // what one lane holds of the (up to two) neighbour blocks its warp loads
+    float w[2], s[2], m[2];
+};
 template <int FS>
-__device__ __forceinline__ void load_coefficients_scaled(const KParams& P, float (*coef)[PT_COEF], int bx, int by, int warp, int lane, int nwarps) {
+__device__ __forceinline__ CoefRegs fetch_coefficients(const KParams& P, int bx, int by, int warp, int lane, int nwarps) {
     constexpr int F = FeatureSet<FS>::F, NSC = FeatureSet<FS>::NSC, NNS = F - NSC;
-    const int f = lane / 3, c = lane - 3 * f;
-    for (int nb = warp; nb < 9; nb += nwarps) {
+    const int f = lane / 3;
+    CoefRegs r;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int nb = warp + j * nwarps;
+        r.w[j] = 0.f; r.s[j] = 1.f; r.m[j] = 0.f;
+        if (nb >= 9) continue;
         const int q = (nb * 11) >> 5;  // nb / 3 for nb < 9 (a 16-bit division would be a library call here)
         const int gx = bx + nb - 3 * q - 1, gy = by + q - 1;
         if (gx < 0 || gx >= P.blocks_x || gy < 0 || gy >= P.blocks_y) continue;
         const size_t g = (size_t)gy * P.blocks_x + gx;
         if (lane < 3 * F) {
-            float w = __ldg(P.weights + g * (3 * F) + lane);
-            if (f >= NNS) w = __fmul_rn(w, __ldg(P.mins_inv + g * (2 * NSC) + 2 * (f - NNS) + 1));
-            coef[nb][4 * f + c] = w;
+            r.w[j] = __ldg(P.weights + g * (3 * F) + lane);
+            if (f >= NNS) r.s[j] = __ldg(P.mins_inv + g * (2 * NSC) + 2 * (f - NNS) + 1);
         }
-        if (lane < F) coef[nb][4 * lane + 3] = lane >= NNS ? __ldg(P.mins_inv + g * (2 * NSC) + 2 * (lane - NNS)) : 0.f;
+        if (lane < F && lane >= NNS) r.m[j] = __ldg(P.mins_inv + g * (2 * NSC) + 2 * (lane - NNS));
     }
+    return r;
+}
+template <int FS>
+__device__ __forceinline__ void store_coefficients(const CoefRegs& r, float (*coef)[PT_COEF_S], int warp, int lane, int nwarps) {
+    constexpr int F = FeatureSet<FS>::F;
+    const int f = lane / 3, c = lane - 3 * f;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int nb = warp + j * nwarps;
+        if (nb >= 9) continue;
+        if (lane < 3 * F) coef[nb][4 * f + c] = __fmul_rn(r.w[j], r.s[j]);  // (a block outside the grid: zeros, never read)
+        if (lane < F) coef[nb][4 * lane + 3] = r.m[j];
+    }
+}
+template <int FS>
+__device__ __forceinline__ void load_coefficients_scaled(const KParams& P, float (*coef)[PT_COEF_S], int bx, int by, int warp, int lane, int nwarps) {
+    store_coefficients<FS>(fetch_coefficients<FS>(P, bx, by, warp, lane, nwarps), coef, warp, lane, nwarps);
 }
 // the F - 1 non-constant features of a pixel (bmfr.cl:724-741: clean, no noise, no NaN scrub) with the minimum taken off the
 // scaled ones (their 1/range lives in the coefficients)
@@ -785,8 +820,8 @@ __device__ __forceinline__ void f3_to(float* d, f3 v) { d[0] = v.x; d[1] = v.y; 
 // addresses (an accepted tap is in the image, bmfr.cl:386-392, so its clamped address is its own), then the shared arithmetic.
 // store: the pixel belongs to the tile (accumulated colour written, history sampled if owned); returns the temporal flag.
 template <bool STRIP, int FS>
-__device__ __forceinline__ bool single_pixel(PostStage& sh, const KParams& P, const TileGeom& G, const float* cf, int hx, int hy, int x, int y,
-                                             bool store, bool own, f3& hist, bool zone) {
+__device__ __forceinline__ bool single_pixel(PostStage& sh, const KParams& P, const TileGeom& G, const AlbGate& gate, const float* cf, int hx, int hy,
+                                             int x, int y, bool store, bool own, f3& hist, bool zone) {
     const PixelIn in = load_pixel_staged(sh, P, G, hx, hy, x, y);
     const f3 filtered = weighted_sum_scaled_px<FS>(in.n, in.p, cf);
     const TapGeom t = tap_geom(in.pp);
@@ -822,7 +857,7 @@ __device__ __forceinline__ bool single_pixel(PostStage& sh, const KParams& P, co
         store_f3(P.accum_cur, in.lp, accum);
         if (STRIP && zone) stage_accum(sh, G, hx, hy, accum);
     }
-    put_ycc_i(sh, P, G, hx, hy, x, y, tone_ycocg(in.alb, accum));
+    put_ycc_i(sh, P, G, hx, hy, x, y, tone_ycocg(albedo_cell(sh, G, gate, hx, hy), accum));
     return want_hist;
 }
 
@@ -835,11 +870,254 @@ __device__ __forceinline__ bool single_pixel(PostStage& sh, const KParams& P, co
 #ifndef BMFR_POST_PX
 #define BMFR_POST_PX 4  // pixels per thread of the whole-image instantiation (4: 8 warps per tile, 2: 16)
 #endif
+#ifndef BMFR_POST_RING_SPREAD
+#define BMFR_POST_RING_SPREAD 0
+#endif
 #ifndef BMFR_POST_SMEM_PAD
 #define BMFR_POST_SMEM_PAD 0  // extra dynamic shared memory per CTA of the whole-image instantiation: fewer CTAs per SM, more L1
 #endif
 
 // One CTA per 32 x 32 tile; thread (lane, warp) owns the column strip x = x0 + lane, rows PX * warp .. + PX - 1.
+// Phase A of one tile: filtered -> accumulated -> tone-mapped colour of the tile's pixels and of its ring (YCoCg values into the
+// albedo cells), the TAA history samples of the tile's pixels (hist) and their flags (live: bit s = pixel s is written, bit
+// 4 + s = it takes the temporal path).  The caller puts a CTA barrier behind it.
+template <bool STRIP, int FS, int PX>
+__device__ __forceinline__ void post_phase_a(PostStage& sh, const KParams& P, const TileGeom& G, const AlbGate& gate, const float (*coef)[PT_COEF_S],
+                                             int tid, int lane, int warp, bool zone, f3 (&hist)[PX], unsigned int& live) {
+    const int x = G.x0 + lane;
+    const int rlo = STRIP ? P.state2_row0 : 0, rhi = (STRIP ? P.state2_row1 : P.H) - 1;  // rows of accum / result this context holds
+    // interior tile (CTA-uniform): the halo lies inside the image and inside the rows phase A covers, every pixel is owned,
+    // no strip edge is near (no zone duties), frame > 0
+    const bool interior = BMFR_POST_FAST != 0 && P.frame > 0 && !zone && G.x0 >= 1 && G.x0 + 33 <= P.W && G.y0 >= 1 && G.y0 + 33 <= P.H &&
+                          G.y0 - 1 >= P.py0 && G.y0 + 33 <= P.py1 && G.y0 >= P.own_y0 && G.y0 + 32 <= P.own_y1;
+    live = 0;
+    if (interior) {
+        const int W3 = 3 * P.W;
+#pragma unroll
+        for (int s = 0; s < PX; s += 2) {
+            const int ty = PX * warp + s, y = G.y0 + ty;
+            const PixelIn i0 = load_pixel_staged(sh, P, G, lane + 1, ty + 1, x, y), i1 = load_pixel_staged(sh, P, G, lane + 1, ty + 2, x, y + 1);
+            const TapGeom g0 = tap_geom(i0.pp), g1 = tap_geom(i1.pp);
+            // the pair's footprints: stacked (rows piy, piy + 1, piy + 2 of columns pix, pix + 1) and inside the image / the rows held?
+            const bool easy = (unsigned int)g0.pix < (unsigned int)(P.W - 1) && g0.piy >= rlo && g0.piy + 2 <= rhi && g1.pix == g0.pix &&
+                              g1.piy == g0.piy + 1;
+            float A[3][6], R[3][6];
+            f3 fl0, fl1;
+            if (__all_sync(0xffffffffu, easy)) {
+                const size_t base = (size_t)(pix_index(P, g0.pix, g0.piy) * 3u);
+                const float* a = P.accum_prev + base;
+                const float* r = P.result_prev + base;
+#pragma unroll
+                for (int row = 0; row < 3; ++row) {
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) {
+                        A[row][k] = __ldg(a + row * W3 + k);
+                        R[row][k] = __ldg(r + row * W3 + k);
+                    }
+                }
+                weighted_sum_scaled_px2<FS>(i0.n, i0.p, i1.n, i1.p, coef[4], fl0, fl1);  // its arithmetic overlaps the gathers
+                hist[s] = history_ycc<true>(g0.w, R[0], R[1], 15u);
+                hist[s + 1] = history_ycc<true>(g1.w, R[1], R[2], 15u);
+                live |= 0x33u << s;
+            } else {  // some lane's footprint touches an edge or its pair is not stacked: clamped addresses, per-tap validity
+                const int cx0[2] = {min(max(g0.pix, 0), P.W - 1), min(max(g0.pix + 1, 0), P.W - 1)};
+                const int cx1[2] = {min(max(g1.pix, 0), P.W - 1), min(max(g1.pix + 1, 0), P.W - 1)};
+                const int ry0[2] = {min(max(g0.piy, rlo), rhi), min(max(g0.piy + 1, rlo), rhi)};
+                const int ry1[2] = {min(max(g1.piy, rlo), rhi), min(max(g1.piy + 1, rlo), rhi)};
+#pragma unroll
+                for (int dx = 0; dx < 2; ++dx) {
+                    const unsigned int l0 = pix_index(P, cx0[dx], ry0[0]), l1 = pix_index(P, cx0[dx], ry0[1]), l2 = pix_index(P, cx1[dx], ry1[1]);
+                    f3_to(&A[0][3 * dx], load_f3(P.accum_prev, l0)); f3_to(&A[1][3 * dx], load_f3(P.accum_prev, l1)); f3_to(&A[2][3 * dx], load_f3(P.accum_prev, l2));
+                    f3_to(&R[0][3 * dx], load_f3(P.result_prev, l0)); f3_to(&R[1][3 * dx], load_f3(P.result_prev, l1)); f3_to(&R[2][3 * dx], load_f3(P.result_prev, l2));
+                }
+                weighted_sum_scaled_px2<FS>(i0.n, i0.p, i1.n, i1.p, coef[4], fl0, fl1);
+                const bool t0 = history_in_reach(P, g0), t1 = history_in_reach(P, g1);
+                const unsigned int ok0 = history_taps_ok(P, g0), ok1 = history_taps_ok(P, g1);
+                if (STRIP) {
+                    const bool o00 = g0.piy < P.state2_row0 || g0.piy >= P.state2_row1, o01 = g0.piy + 1 < P.state2_row0 || g0.piy + 1 >= P.state2_row1;
+                    const bool o10 = g1.piy < P.state2_row0 || g1.piy >= P.state2_row1, o11 = g1.piy + 1 < P.state2_row0 || g1.piy + 1 >= P.state2_row1;
+                    const unsigned int w0 = i0.accept | (t0 ? ok0 : 0u), w1 = i1.accept | (t1 ? ok1 : 0u);
+                    if (((w0 & 3u) != 0 && o00) || ((w0 & 12u) != 0 && o01) || ((w1 & 3u) != 0 && o10) || ((w1 & 12u) != 0 && o11)) *P.oob_flag = 1;
+                }
+                hist[s] = history_ycc<false>(g0.w, R[0], R[1], ok0);
+                if (!(cx1[0] == cx0[0] && cx1[1] == cx0[1] && ry1[0] == ry0[1])) {  // footprints not stacked: fetch the lower pixel's upper row
+                    // (the upper pixel's accumulation below needs its own lower row: finish it first)
+                    const f3 acc0 = accumulate_taps(P, i0.accept, i0.spp, g0.w, fl0, A[0], A[1]);
+                    store_f3(P.accum_cur, i0.lp, acc0);
+                    put_cell_i(sh, G, lane + 1, ty + 1, tone_ycocg(albedo_cell(sh, G, gate, lane + 1, ty + 1), acc0));
+#pragma unroll
+                    for (int dx = 0; dx < 2; ++dx) {
+                        const unsigned int l = pix_index(P, cx1[dx], ry1[0]);
+                        f3_to(&A[1][3 * dx], load_f3(P.accum_prev, l));
+                        f3_to(&R[1][3 * dx], load_f3(P.result_prev, l));
+                    }
+                    hist[s + 1] = history_ycc<false>(g1.w, R[1], R[2], ok1);
+                    const f3 acc1 = accumulate_taps(P, i1.accept, i1.spp, g1.w, fl1, A[1], A[2]);
+                    store_f3(P.accum_cur, i1.lp, acc1);
+                    put_cell_i(sh, G, lane + 1, ty + 2, tone_ycocg(albedo_cell(sh, G, gate, lane + 1, ty + 2), acc1));
+                    live |= ((1u | (t0 ? 16u : 0u)) | ((1u | (t1 ? 16u : 0u)) << 1)) << s;
+                    continue;
+                }
+                hist[s + 1] = history_ycc<false>(g1.w, R[1], R[2], ok1);
+                live |= ((1u | (t0 ? 16u : 0u)) | ((1u | (t1 ? 16u : 0u)) << 1)) << s;
+            }
+            const f3 acc0 = accumulate_taps(P, i0.accept, i0.spp, g0.w, fl0, A[0], A[1]);
+            const f3 acc1 = accumulate_taps(P, i1.accept, i1.spp, g1.w, fl1, A[1], A[2]);
+            store_f3(P.accum_cur, i0.lp, acc0);
+            store_f3(P.accum_cur, i1.lp, acc1);
+            put_cell_i(sh, G, lane + 1, ty + 1, tone_ycocg(albedo_cell(sh, G, gate, lane + 1, ty + 1), acc0));
+            put_cell_i(sh, G, lane + 1, ty + 2, tone_ycocg(albedo_cell(sh, G, gate, lane + 1, ty + 2), acc1));
+        }
+    } else {
+        // general tile: image edges, strip edges, rows that are only partly covered or owned, zone duties, frame 0
+        const bool col_ok = x >= 0 && x < P.W;
+#pragma unroll
+        for (int s = 0; s < PX; s += 2) {
+            const int ty = PX * warp + s, y = G.y0 + ty;
+            hist[s] = hist[s + 1] = make_f3(0.f, 0.f, 0.f);
+            const bool v0 = col_ok && y >= P.py0 && y < P.py1, v1 = col_ok && y + 1 >= P.py0 && y + 1 < P.py1;
+            const bool own0 = y >= P.own_y0 && y < P.own_y1, own1 = y + 1 >= P.own_y0 && y + 1 < P.own_y1;
+            if (v0 && v1) {
+                const PixelIn i0 = load_pixel_staged(sh, P, G, lane + 1, ty + 1, x, y), i1 = load_pixel_staged(sh, P, G, lane + 1, ty + 2, x, y + 1);
+                const TapGeom g0 = tap_geom(i0.pp), g1 = tap_geom(i1.pp);
+                float A[3][6], R[3][6];
+                f3 fl0, fl1;
+                bool t0 = false, t1 = false;
+                unsigned int acc_bits0 = 0, acc_bits1 = 0;
+                bool stacked = true;
+                if (P.frame > 0) {
+                    // one round of independent loads from clamped addresses: tap rows R0, R1 of the upper pixel, R2 of the lower;
+                    // the lower pixel's upper row is R1 when the two footprints are stacked (checked below)
+                    const int cx0[2] = {min(max(g0.pix, 0), P.W - 1), min(max(g0.pix + 1, 0), P.W - 1)};
+                    const int cx1[2] = {min(max(g1.pix, 0), P.W - 1), min(max(g1.pix + 1, 0), P.W - 1)};
+                    const int ry0[2] = {min(max(g0.piy, rlo), rhi), min(max(g0.piy + 1, rlo), rhi)};
+                    const int ry1[2] = {min(max(g1.piy, rlo), rhi), min(max(g1.piy + 1, rlo), rhi)};
+#pragma unroll
+                    for (int dx = 0; dx < 2; ++dx) {
+                        const unsigned int l0 = pix_index(P, cx0[dx], ry0[0]), l1 = pix_index(P, cx0[dx], ry0[1]), l2 = pix_index(P, cx1[dx], ry1[1]);
+                        f3_to(&A[0][3 * dx], load_f3(P.accum_prev, l0)); f3_to(&A[1][3 * dx], load_f3(P.accum_prev, l1)); f3_to(&A[2][3 * dx], load_f3(P.accum_prev, l2));
+                        f3_to(&R[0][3 * dx], load_f3(P.result_prev, l0)); f3_to(&R[1][3 * dx], load_f3(P.result_prev, l1)); f3_to(&R[2][3 * dx], load_f3(P.result_prev, l2));
+                    }
+                    weighted_sum_scaled_px2<FS>(i0.n, i0.p, i1.n, i1.p, coef[4], fl0, fl1);  // its arithmetic overlaps the gathers
+                    acc_bits0 = i0.accept; acc_bits1 = i1.accept;
+                    t0 = own0 && history_in_reach(P, g0);
+                    t1 = own1 && history_in_reach(P, g1);
+                    const unsigned int ok0 = history_taps_ok(P, g0), ok1 = history_taps_ok(P, g1);
+                    if (STRIP) {  // a wanted tap whose row this strip does not hold: reported once, the run is invalid
+                        const bool o00 = g0.piy < P.state2_row0 || g0.piy >= P.state2_row1, o01 = g0.piy + 1 < P.state2_row0 || g0.piy + 1 >= P.state2_row1;
+                        const bool o10 = g1.piy < P.state2_row0 || g1.piy >= P.state2_row1, o11 = g1.piy + 1 < P.state2_row0 || g1.piy + 1 >= P.state2_row1;
+                        const unsigned int w0 = i0.accept | (t0 ? ok0 : 0u), w1 = i1.accept | (t1 ? ok1 : 0u);
+                        if (((w0 & 3u) != 0 && o00) || ((w0 & 12u) != 0 && o01) || ((w1 & 3u) != 0 && o10) || ((w1 & 12u) != 0 && o11)) *P.oob_flag = 1;
+                    }
+                    if (t0) hist[s] = history_ycc<false>(g0.w, R[0], R[1], ok0);
+                    stacked = cx1[0] == cx0[0] && cx1[1] == cx0[1] && ry1[0] == ry0[1];
+                    if (!stacked) {  // rare: finish the upper pixel, then fetch the lower pixel's own upper row
+                        const f3 acc0 = accumulate_taps(P, acc_bits0, i0.spp, g0.w, fl0, A[0], A[1]);
+                        store_f3(P.accum_cur, i0.lp, acc0);
+                        if (STRIP && zone) stage_accum(sh, G, lane + 1, ty + 1, acc0);
+                        put_ycc_i(sh, P, G, lane + 1, ty + 1, x, y, tone_ycocg(albedo_cell(sh, G, gate, lane + 1, ty + 1), acc0));
+#pragma unroll
+                        for (int dx = 0; dx < 2; ++dx) {
+                            const unsigned int l = pix_index(P, cx1[dx], ry1[0]);
+                            f3_to(&A[1][3 * dx], load_f3(P.accum_prev, l));
+                            f3_to(&R[1][3 * dx], load_f3(P.result_prev, l));
+                        }
+                    }
+                    if (t1) hist[s + 1] = history_ycc<false>(g1.w, R[1], R[2], ok1);
+                } else {  // frame 0: no temporal path (bmfr.cl:784, 884): accept = 0 makes the accumulated colour the filtered one
+#pragma unroll
+                    for (int row = 0; row < 3; ++row)
+#pragma unroll
+                        for (int k = 0; k < 6; ++k) A[row][k] = 0.f;
+                    weighted_sum_scaled_px2<FS>(i0.n, i0.p, i1.n, i1.p, coef[4], fl0, fl1);
+                }
+                if (stacked) {
+                    const f3 acc0 = accumulate_taps(P, acc_bits0, i0.spp, g0.w, fl0, A[0], A[1]);
+                    store_f3(P.accum_cur, i0.lp, acc0);
+                    if (STRIP && zone) stage_accum(sh, G, lane + 1, ty + 1, acc0);
+                    put_ycc_i(sh, P, G, lane + 1, ty + 1, x, y, tone_ycocg(albedo_cell(sh, G, gate, lane + 1, ty + 1), acc0));
+                }
+                const f3 acc1 = accumulate_taps(P, acc_bits1, i1.spp, g1.w, fl1, A[1], A[2]);
+                store_f3(P.accum_cur, i1.lp, acc1);
+                if (STRIP && zone) stage_accum(sh, G, lane + 1, ty + 2, acc1);
+                put_ycc_i(sh, P, G, lane + 1, ty + 2, x, y + 1, tone_ycocg(albedo_cell(sh, G, gate, lane + 1, ty + 2), acc1));
+                live |= ((own0 ? 1u : 0u) | (t0 ? 16u : 0u)) << s;
+                live |= ((own1 ? 1u : 0u) | (t1 ? 16u : 0u)) << (s + 1);
+            } else if (v0) {  // a strip or image edge cuts the pair
+                const bool t = single_pixel<STRIP, FS>(sh, P, G, gate, coef[4], lane + 1, ty + 1, x, y, true, own0, hist[s], zone);
+                live |= ((own0 ? 1u : 0u) | (t ? 16u : 0u)) << s;
+            } else if (v1) {
+                const bool t = single_pixel<STRIP, FS>(sh, P, G, gate, coef[4], lane + 1, ty + 2, x, y + 1, true, own1, hist[s + 1], zone);
+                live |= ((own1 ? 1u : 0u) | (t ? 16u : 0u)) << (s + 1);
+            }
+        }
+    }
+    // phase A, ring: 4 * 33 = 132 pixels, coefficients of the pixel's own block.  BMFR_POST_RING_SPREAD: 17 per warp (with
+    // four pixels per thread) instead of the first 132 threads — every warp then reaches the phase barrier after the same
+    // work, at the price of the ring code being issued by all warps
+    const int rid = BMFR_POST_RING_SPREAD && PX == 4 ? (lane < 17 ? warp * 17 + lane : 4 * (PT_HALO - 1)) : tid;
+    if (rid < 4 * (PT_HALO - 1)) {
+        int hx, hy;
+        if (rid < PT_HALO - 1) { hx = rid; hy = 0; }
+        else if (rid < 2 * (PT_HALO - 1)) { hx = PT_HALO - 1; hy = rid - (PT_HALO - 1); }
+        else if (rid < 3 * (PT_HALO - 1)) { hx = PT_HALO - 1 - (rid - 2 * (PT_HALO - 1)); hy = PT_HALO - 1; }
+        else { hx = 0; hy = PT_HALO - 1 - (rid - 3 * (PT_HALO - 1)); }
+        const int rx = G.x0 + hx - 1, ry = G.y0 + hy - 1;
+        if (interior || (rx >= 0 && rx < P.W && ry >= P.py0 && ry < P.py1)) {
+            const int nb = ((hy == 0) ? 0 : (hy == PT_HALO - 1) ? 6 : 3) + ((hx == 0) ? 0 : (hx == PT_HALO - 1) ? 2 : 1);
+            f3 unused;
+            single_pixel<STRIP, FS>(sh, P, G, gate, coef[nb], hx, hy, rx, ry, false, false, unused, zone);
+        }
+    }
+}
+
+// Phase B of one tile (after the barrier): neighbourhood clamp of the history samples, blend, TAA result stored.
+template <bool STRIP, int PX>
+__device__ __forceinline__ void post_phase_b(PostStage& sh, const KParams& P, const TileGeom& G, int lane, int warp, bool zone, const f3 (&hist)[PX],
+                                             unsigned int live) {
+    const int x = G.x0 + lane;
+    // phase B: clamp the history samples to the neighbourhood box, component by component (bmfr.cl:893-920, 967-969), blend
+    // (bmfr.cl:971-973; in YCoCg, the weights carry the 0.25 of the conversion back) and store.  Halo rows PX * warp ..
+    // PX * warp + PX + 1 cover the 3x3 neighbourhoods of the strip; this thread's column is lane + 1.  A pixel on the
+    // copy-through path of bmfr.cl:884-890 keeps its own colour.
+    const float a = __fmul_rn(0.25f, P.taa_blend_alpha), oma = __fmul_rn(0.25f, __fsub_rn(1.f, P.taa_blend_alpha));
+    f3 out[PX];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float ctr[PX + 2], rmin[PX + 2], rmax[PX + 2];
+#pragma unroll
+        for (int r = 0; r < PX + 2; ++r) {
+            const float* row = &sh.alb[PX * warp + r][G.sh_rgb + c];
+            const float l = row[3 * lane], m = row[3 * lane + 3], rr = row[3 * lane + 6];
+            ctr[r] = m;
+            rmin[r] = fminf(fminf(l, m), rr);
+            rmax[r] = fmaxf(fmaxf(l, m), rr);
+        }
+#pragma unroll
+        for (int s = 0; s < PX; ++s) {
+            const float min_box = fminf(fminf(rmin[s], rmin[s + 1]), rmin[s + 2]);
+            const float max_box = fmaxf(fmaxf(rmax[s], rmax[s + 1]), rmax[s + 2]);
+            const float min_cross = fminf(fminf(ctr[s], rmin[s + 1]), ctr[s + 2]);
+            const float max_cross = fmaxf(fmaxf(ctr[s], rmax[s + 1]), ctr[s + 2]);
+            const float lo = __fmul_rn(__fadd_rn(min_box, min_cross), 0.5f), hi = __fmul_rn(__fadd_rn(max_box, max_cross), 0.5f);
+            const float h = (c == 0) ? hist[s].x : (c == 1) ? hist[s].y : hist[s].z;
+            const float hc = fminf(fmaxf(h, lo), hi);
+            const float mine = ctr[s + 1];
+            const float v = (live & (16u << s)) ? fmaf(a, mine, __fmul_rn(oma, hc)) : __fmul_rn(0.25f, mine);
+            if (c == 0) out[s].x = v; else if (c == 1) out[s].y = v; else out[s].z = v;
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < PX; ++s) {
+        if (!(live & (1u << s))) continue;
+        const unsigned int lp = pix_index(P, x, G.y0 + PX * warp + s);
+        const f3 rgb = from_quarter_ycocg(out[s]);
+        store_f3(P.result_cur, lp, rgb);
+        if (P.user_out) store_f3(P.user_out, lp, rgb);
+        if (STRIP && zone) stage_result(sh, G, lane + 1, PX * warp + s + 1, rgb);
+    }
+}
+
 template <bool STRIP, int FS, int PX>
 __global__ void __launch_bounds__(1024 / PX, PX == 4 ? BMFR_POST_TMA_MIN_BLOCKS : 2) post_tma_kernel(const __grid_constant__ KParams P, const __grid_constant__ PostMaps M) {
     static_assert(PX == 4 || PX == 2, "pixels per thread: two pairs or one");
@@ -889,239 +1167,170 @@ __global__ void __launch_bounds__(1024 / PX, PX == 4 ? BMFR_POST_TMA_MIN_BLOCKS 
     stamp_begin(P, 2);
     if (zone) halo_poll(P.halo_p, peek);
 
-    load_coefficients_scaled<FS>(P, sh.coef, bx, by, warp, lane, WARPS);
+    load_coefficients_scaled<FS>(P, sh.coef[0], bx, by, warp, lane, WARPS);
     __syncthreads();  // the coefficients and the barrier's initialisation are visible
     mbar_wait_hot(&sh.bar, 0);
 
-    const int x = G.x0 + lane;
-    const int rlo = STRIP ? P.state2_row0 : 0, rhi = (STRIP ? P.state2_row1 : P.H) - 1;  // rows of accum / result this context holds
-    // interior tile (CTA-uniform): the halo lies inside the image and inside the rows phase A covers, every pixel is owned,
-    // no strip edge is near (no zone duties), frame > 0
-    const bool interior = BMFR_POST_FAST != 0 && P.frame > 0 && !zone && G.x0 >= 1 && G.x0 + 33 <= P.W && G.y0 >= 1 && G.y0 + 33 <= P.H &&
-                          G.y0 - 1 >= P.py0 && G.y0 + 33 <= P.py1 && G.y0 >= P.own_y0 && G.y0 + 32 <= P.own_y1;
     f3 hist[PX];
-    unsigned int live = 0;  // bit s: pixel s is written; bit 4 + s: it takes the temporal path of the TAA
-    if (interior) {
-        const int W3 = 3 * P.W;
-#pragma unroll
-        for (int s = 0; s < PX; s += 2) {
-            const int ty = PX * warp + s, y = G.y0 + ty;
-            const PixelIn i0 = load_pixel_staged(sh, P, G, lane + 1, ty + 1, x, y), i1 = load_pixel_staged(sh, P, G, lane + 1, ty + 2, x, y + 1);
-            const TapGeom g0 = tap_geom(i0.pp), g1 = tap_geom(i1.pp);
-            // the pair's footprints: stacked (rows piy, piy + 1, piy + 2 of columns pix, pix + 1) and inside the image / the rows held?
-            const bool easy = (unsigned int)g0.pix < (unsigned int)(P.W - 1) && g0.piy >= rlo && g0.piy + 2 <= rhi && g1.pix == g0.pix &&
-                              g1.piy == g0.piy + 1;
-            float A[3][6], R[3][6];
-            f3 fl0, fl1;
-            if (__all_sync(0xffffffffu, easy)) {
-                const size_t base = (size_t)(pix_index(P, g0.pix, g0.piy) * 3u);
-                const float* a = P.accum_prev + base;
-                const float* r = P.result_prev + base;
-#pragma unroll
-                for (int row = 0; row < 3; ++row) {
-#pragma unroll
-                    for (int k = 0; k < 6; ++k) {
-                        A[row][k] = __ldg(a + row * W3 + k);
-                        R[row][k] = __ldg(r + row * W3 + k);
-                    }
-                }
-                weighted_sum_scaled_px2<FS>(i0.n, i0.p, i1.n, i1.p, sh.coef[4], fl0, fl1);  // its arithmetic overlaps the gathers
-                hist[s] = history_ycc<true>(g0.w, R[0], R[1], 15u);
-                hist[s + 1] = history_ycc<true>(g1.w, R[1], R[2], 15u);
-                live |= 0x33u << s;
-            } else {  // some lane's footprint touches an edge or its pair is not stacked: clamped addresses, per-tap validity
-                const int cx0[2] = {min(max(g0.pix, 0), P.W - 1), min(max(g0.pix + 1, 0), P.W - 1)};
-                const int cx1[2] = {min(max(g1.pix, 0), P.W - 1), min(max(g1.pix + 1, 0), P.W - 1)};
-                const int ry0[2] = {min(max(g0.piy, rlo), rhi), min(max(g0.piy + 1, rlo), rhi)};
-                const int ry1[2] = {min(max(g1.piy, rlo), rhi), min(max(g1.piy + 1, rlo), rhi)};
-#pragma unroll
-                for (int dx = 0; dx < 2; ++dx) {
-                    const unsigned int l0 = pix_index(P, cx0[dx], ry0[0]), l1 = pix_index(P, cx0[dx], ry0[1]), l2 = pix_index(P, cx1[dx], ry1[1]);
-                    f3_to(&A[0][3 * dx], load_f3(P.accum_prev, l0)); f3_to(&A[1][3 * dx], load_f3(P.accum_prev, l1)); f3_to(&A[2][3 * dx], load_f3(P.accum_prev, l2));
-                    f3_to(&R[0][3 * dx], load_f3(P.result_prev, l0)); f3_to(&R[1][3 * dx], load_f3(P.result_prev, l1)); f3_to(&R[2][3 * dx], load_f3(P.result_prev, l2));
-                }
-                weighted_sum_scaled_px2<FS>(i0.n, i0.p, i1.n, i1.p, sh.coef[4], fl0, fl1);
-                const bool t0 = history_in_reach(P, g0), t1 = history_in_reach(P, g1);
-                const unsigned int ok0 = history_taps_ok(P, g0), ok1 = history_taps_ok(P, g1);
-                if (STRIP) {
-                    const bool o00 = g0.piy < P.state2_row0 || g0.piy >= P.state2_row1, o01 = g0.piy + 1 < P.state2_row0 || g0.piy + 1 >= P.state2_row1;
-                    const bool o10 = g1.piy < P.state2_row0 || g1.piy >= P.state2_row1, o11 = g1.piy + 1 < P.state2_row0 || g1.piy + 1 >= P.state2_row1;
-                    const unsigned int w0 = i0.accept | (t0 ? ok0 : 0u), w1 = i1.accept | (t1 ? ok1 : 0u);
-                    if (((w0 & 3u) != 0 && o00) || ((w0 & 12u) != 0 && o01) || ((w1 & 3u) != 0 && o10) || ((w1 & 12u) != 0 && o11)) *P.oob_flag = 1;
-                }
-                hist[s] = history_ycc<false>(g0.w, R[0], R[1], ok0);
-                if (!(cx1[0] == cx0[0] && cx1[1] == cx0[1] && ry1[0] == ry0[1])) {  // footprints not stacked: fetch the lower pixel's upper row
-                    // (the upper pixel's accumulation below needs its own lower row: finish it first)
-                    const f3 acc0 = accumulate_taps(P, i0.accept, i0.spp, g0.w, fl0, A[0], A[1]);
-                    store_f3(P.accum_cur, i0.lp, acc0);
-                    put_cell_i(sh, G, lane + 1, ty + 1, tone_ycocg(i0.alb, acc0));
-#pragma unroll
-                    for (int dx = 0; dx < 2; ++dx) {
-                        const unsigned int l = pix_index(P, cx1[dx], ry1[0]);
-                        f3_to(&A[1][3 * dx], load_f3(P.accum_prev, l));
-                        f3_to(&R[1][3 * dx], load_f3(P.result_prev, l));
-                    }
-                    hist[s + 1] = history_ycc<false>(g1.w, R[1], R[2], ok1);
-                    const f3 acc1 = accumulate_taps(P, i1.accept, i1.spp, g1.w, fl1, A[1], A[2]);
-                    store_f3(P.accum_cur, i1.lp, acc1);
-                    put_cell_i(sh, G, lane + 1, ty + 2, tone_ycocg(i1.alb, acc1));
-                    live |= ((1u | (t0 ? 16u : 0u)) | ((1u | (t1 ? 16u : 0u)) << 1)) << s;
-                    continue;
-                }
-                hist[s + 1] = history_ycc<false>(g1.w, R[1], R[2], ok1);
-                live |= ((1u | (t0 ? 16u : 0u)) | ((1u | (t1 ? 16u : 0u)) << 1)) << s;
-            }
-            const f3 acc0 = accumulate_taps(P, i0.accept, i0.spp, g0.w, fl0, A[0], A[1]);
-            const f3 acc1 = accumulate_taps(P, i1.accept, i1.spp, g1.w, fl1, A[1], A[2]);
-            store_f3(P.accum_cur, i0.lp, acc0);
-            store_f3(P.accum_cur, i1.lp, acc1);
-            put_cell_i(sh, G, lane + 1, ty + 1, tone_ycocg(i0.alb, acc0));
-            put_cell_i(sh, G, lane + 1, ty + 2, tone_ycocg(i1.alb, acc1));
-        }
-    } else {
-        // general tile: image edges, strip edges, rows that are only partly covered or owned, zone duties, frame 0
-        const bool col_ok = x >= 0 && x < P.W;
-#pragma unroll
-        for (int s = 0; s < PX; s += 2) {
-            const int ty = PX * warp + s, y = G.y0 + ty;
-            hist[s] = hist[s + 1] = make_f3(0.f, 0.f, 0.f);
-            const bool v0 = col_ok && y >= P.py0 && y < P.py1, v1 = col_ok && y + 1 >= P.py0 && y + 1 < P.py1;
-            const bool own0 = y >= P.own_y0 && y < P.own_y1, own1 = y + 1 >= P.own_y0 && y + 1 < P.own_y1;
-            if (v0 && v1) {
-                const PixelIn i0 = load_pixel_staged(sh, P, G, lane + 1, ty + 1, x, y), i1 = load_pixel_staged(sh, P, G, lane + 1, ty + 2, x, y + 1);
-                const TapGeom g0 = tap_geom(i0.pp), g1 = tap_geom(i1.pp);
-                float A[3][6], R[3][6];
-                f3 fl0, fl1;
-                bool t0 = false, t1 = false;
-                unsigned int acc_bits0 = 0, acc_bits1 = 0;
-                bool stacked = true;
-                if (P.frame > 0) {
-                    // one round of independent loads from clamped addresses: tap rows R0, R1 of the upper pixel, R2 of the lower;
-                    // the lower pixel's upper row is R1 when the two footprints are stacked (checked below)
-                    const int cx0[2] = {min(max(g0.pix, 0), P.W - 1), min(max(g0.pix + 1, 0), P.W - 1)};
-                    const int cx1[2] = {min(max(g1.pix, 0), P.W - 1), min(max(g1.pix + 1, 0), P.W - 1)};
-                    const int ry0[2] = {min(max(g0.piy, rlo), rhi), min(max(g0.piy + 1, rlo), rhi)};
-                    const int ry1[2] = {min(max(g1.piy, rlo), rhi), min(max(g1.piy + 1, rlo), rhi)};
-#pragma unroll
-                    for (int dx = 0; dx < 2; ++dx) {
-                        const unsigned int l0 = pix_index(P, cx0[dx], ry0[0]), l1 = pix_index(P, cx0[dx], ry0[1]), l2 = pix_index(P, cx1[dx], ry1[1]);
-                        f3_to(&A[0][3 * dx], load_f3(P.accum_prev, l0)); f3_to(&A[1][3 * dx], load_f3(P.accum_prev, l1)); f3_to(&A[2][3 * dx], load_f3(P.accum_prev, l2));
-                        f3_to(&R[0][3 * dx], load_f3(P.result_prev, l0)); f3_to(&R[1][3 * dx], load_f3(P.result_prev, l1)); f3_to(&R[2][3 * dx], load_f3(P.result_prev, l2));
-                    }
-                    weighted_sum_scaled_px2<FS>(i0.n, i0.p, i1.n, i1.p, sh.coef[4], fl0, fl1);  // its arithmetic overlaps the gathers
-                    acc_bits0 = i0.accept; acc_bits1 = i1.accept;
-                    t0 = own0 && history_in_reach(P, g0);
-                    t1 = own1 && history_in_reach(P, g1);
-                    const unsigned int ok0 = history_taps_ok(P, g0), ok1 = history_taps_ok(P, g1);
-                    if (STRIP) {  // a wanted tap whose row this strip does not hold: reported once, the run is invalid
-                        const bool o00 = g0.piy < P.state2_row0 || g0.piy >= P.state2_row1, o01 = g0.piy + 1 < P.state2_row0 || g0.piy + 1 >= P.state2_row1;
-                        const bool o10 = g1.piy < P.state2_row0 || g1.piy >= P.state2_row1, o11 = g1.piy + 1 < P.state2_row0 || g1.piy + 1 >= P.state2_row1;
-                        const unsigned int w0 = i0.accept | (t0 ? ok0 : 0u), w1 = i1.accept | (t1 ? ok1 : 0u);
-                        if (((w0 & 3u) != 0 && o00) || ((w0 & 12u) != 0 && o01) || ((w1 & 3u) != 0 && o10) || ((w1 & 12u) != 0 && o11)) *P.oob_flag = 1;
-                    }
-                    if (t0) hist[s] = history_ycc<false>(g0.w, R[0], R[1], ok0);
-                    stacked = cx1[0] == cx0[0] && cx1[1] == cx0[1] && ry1[0] == ry0[1];
-                    if (!stacked) {  // rare: finish the upper pixel, then fetch the lower pixel's own upper row
-                        const f3 acc0 = accumulate_taps(P, acc_bits0, i0.spp, g0.w, fl0, A[0], A[1]);
-                        store_f3(P.accum_cur, i0.lp, acc0);
-                        if (STRIP && zone) stage_accum(sh, G, lane + 1, ty + 1, acc0);
-                        put_ycc_i(sh, P, G, lane + 1, ty + 1, x, y, tone_ycocg(i0.alb, acc0));
-#pragma unroll
-                        for (int dx = 0; dx < 2; ++dx) {
-                            const unsigned int l = pix_index(P, cx1[dx], ry1[0]);
-                            f3_to(&A[1][3 * dx], load_f3(P.accum_prev, l));
-                            f3_to(&R[1][3 * dx], load_f3(P.result_prev, l));
-                        }
-                    }
-                    if (t1) hist[s + 1] = history_ycc<false>(g1.w, R[1], R[2], ok1);
-                } else {  // frame 0: no temporal path (bmfr.cl:784, 884): accept = 0 makes the accumulated colour the filtered one
-#pragma unroll
-                    for (int row = 0; row < 3; ++row)
-#pragma unroll
-                        for (int k = 0; k < 6; ++k) A[row][k] = 0.f;
-                    weighted_sum_scaled_px2<FS>(i0.n, i0.p, i1.n, i1.p, sh.coef[4], fl0, fl1);
-                }
-                if (stacked) {
-                    const f3 acc0 = accumulate_taps(P, acc_bits0, i0.spp, g0.w, fl0, A[0], A[1]);
-                    store_f3(P.accum_cur, i0.lp, acc0);
-                    if (STRIP && zone) stage_accum(sh, G, lane + 1, ty + 1, acc0);
-                    put_ycc_i(sh, P, G, lane + 1, ty + 1, x, y, tone_ycocg(i0.alb, acc0));
-                }
-                const f3 acc1 = accumulate_taps(P, acc_bits1, i1.spp, g1.w, fl1, A[1], A[2]);
-                store_f3(P.accum_cur, i1.lp, acc1);
-                if (STRIP && zone) stage_accum(sh, G, lane + 1, ty + 2, acc1);
-                put_ycc_i(sh, P, G, lane + 1, ty + 2, x, y + 1, tone_ycocg(i1.alb, acc1));
-                live |= ((own0 ? 1u : 0u) | (t0 ? 16u : 0u)) << s;
-                live |= ((own1 ? 1u : 0u) | (t1 ? 16u : 0u)) << (s + 1);
-            } else if (v0) {  // a strip or image edge cuts the pair
-                const bool t = single_pixel<STRIP, FS>(sh, P, G, sh.coef[4], lane + 1, ty + 1, x, y, true, own0, hist[s], zone);
-                live |= ((own0 ? 1u : 0u) | (t ? 16u : 0u)) << s;
-            } else if (v1) {
-                const bool t = single_pixel<STRIP, FS>(sh, P, G, sh.coef[4], lane + 1, ty + 2, x, y + 1, true, own1, hist[s + 1], zone);
-                live |= ((own1 ? 1u : 0u) | (t ? 16u : 0u)) << (s + 1);
-            }
-        }
-    }
-    // phase A, ring: 4 * 33 = 132 pixels, coefficients of the pixel's own block
-    if (tid < 4 * (PT_HALO - 1)) {
-        int hx, hy;
-        if (tid < PT_HALO - 1) { hx = tid; hy = 0; }
-        else if (tid < 2 * (PT_HALO - 1)) { hx = PT_HALO - 1; hy = tid - (PT_HALO - 1); }
-        else if (tid < 3 * (PT_HALO - 1)) { hx = PT_HALO - 1 - (tid - 2 * (PT_HALO - 1)); hy = PT_HALO - 1; }
-        else { hx = 0; hy = PT_HALO - 1 - (tid - 3 * (PT_HALO - 1)); }
-        const int rx = G.x0 + hx - 1, ry = G.y0 + hy - 1;
-        if (interior || (rx >= 0 && rx < P.W && ry >= P.py0 && ry < P.py1)) {
-            const int nb = ((hy == 0) ? 0 : (hy == PT_HALO - 1) ? 6 : 3) + ((hx == 0) ? 0 : (hx == PT_HALO - 1) ? 2 : 1);
-            f3 unused;
-            single_pixel<STRIP, FS>(sh, P, G, sh.coef[nb], hx, hy, rx, ry, false, false, unused, zone);
-        }
-    }
+    unsigned int live;
+    const AlbGate gate{nullptr, 0u};  // the albedo came with the other inputs
+    post_phase_a<STRIP, FS, PX>(sh, P, G, gate, sh.coef[0], tid, lane, warp, zone, hist, live);
     __syncthreads();
-
-    // phase B: clamp the history samples to the neighbourhood box, component by component (bmfr.cl:893-920, 967-969), blend
-    // (bmfr.cl:971-973; in YCoCg, the weights carry the 0.25 of the conversion back) and store.  Halo rows PX * warp ..
-    // PX * warp + PX + 1 cover the 3x3 neighbourhoods of the strip; this thread's column is lane + 1.  A pixel on the
-    // copy-through path of bmfr.cl:884-890 keeps its own colour.
-    const float a = __fmul_rn(0.25f, P.taa_blend_alpha), oma = __fmul_rn(0.25f, __fsub_rn(1.f, P.taa_blend_alpha));
-    f3 out[PX];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        float ctr[PX + 2], rmin[PX + 2], rmax[PX + 2];
-#pragma unroll
-        for (int r = 0; r < PX + 2; ++r) {
-            const float* row = &sh.alb[PX * warp + r][G.sh_rgb + c];
-            const float l = row[3 * lane], m = row[3 * lane + 3], rr = row[3 * lane + 6];
-            ctr[r] = m;
-            rmin[r] = fminf(fminf(l, m), rr);
-            rmax[r] = fmaxf(fmaxf(l, m), rr);
-        }
-#pragma unroll
-        for (int s = 0; s < PX; ++s) {
-            const float min_box = fminf(fminf(rmin[s], rmin[s + 1]), rmin[s + 2]);
-            const float max_box = fmaxf(fmaxf(rmax[s], rmax[s + 1]), rmax[s + 2]);
-            const float min_cross = fminf(fminf(ctr[s], rmin[s + 1]), ctr[s + 2]);
-            const float max_cross = fmaxf(fmaxf(ctr[s], rmax[s + 1]), ctr[s + 2]);
-            const float lo = __fmul_rn(__fadd_rn(min_box, min_cross), 0.5f), hi = __fmul_rn(__fadd_rn(max_box, max_cross), 0.5f);
-            const float h = (c == 0) ? hist[s].x : (c == 1) ? hist[s].y : hist[s].z;
-            const float hc = fminf(fmaxf(h, lo), hi);
-            const float mine = ctr[s + 1];
-            const float v = (live & (16u << s)) ? fmaf(a, mine, __fmul_rn(oma, hc)) : __fmul_rn(0.25f, mine);
-            if (c == 0) out[s].x = v; else if (c == 1) out[s].y = v; else out[s].z = v;
-        }
-    }
-#pragma unroll
-    for (int s = 0; s < PX; ++s) {
-        if (!(live & (1u << s))) continue;
-        const unsigned int lp = pix_index(P, x, G.y0 + PX * warp + s);
-        const f3 rgb = from_quarter_ycocg(out[s]);
-        store_f3(P.result_cur, lp, rgb);
-        if (P.user_out) store_f3(P.user_out, lp, rgb);
-        if (STRIP && zone) stage_result(sh, G, lane + 1, PX * warp + s + 1, rgb);
-    }
+    post_phase_b<STRIP, PX>(sh, P, G, lane, warp, zone, hist, live);
     if (STRIP && zone) {
         __syncthreads();  // the staged rows are complete
         post_push_rows<THREADS>(P, sh, G, tid);
         halo_finish(P.halo_p, halo_cta_pushes(P.halo_p, G.y0, G.y0 + PT_TILE));
+    }
+    stamp_end(P, 2);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Persistent variant (BMFR_POST_PERSIST, the default): min(tiles, 3 x SMs) CTAs, each walks over tiles t = blockIdx.x,
+// + gridDim.x, ... of the launch.  What it buys: a tile's inputs no longer arrive while its CTA sits idle — the source-
+// level profile of the one-tile-per-CTA kernel has 13 % of the warp time in that wait (tile + coefficients) on top of
+// the launch of 2135 CTAs.  The stage is not doubled (three CTAs per SM must keep fitting, and the L1 beside them keeps its
+// 60 KB for the tap gathers: 28 KB measured +3 %); instead
+//   * normals, positions, previous-pixel positions, accept masks and sample counts of the NEXT tile are requested right
+//     behind the phase barrier of this one — phase A is their last reader — and land during phase B;
+//   * the albedo cells hold this tile's YCoCg values until phase B is over, so the next tile's albedo box is requested
+//     behind the next barrier, on a barrier of its own, and is waited for where phase A first needs it: after the weighted
+//     sum and the tap gathers of the thread's first pixel pair (AlbGate);
+//   * the next tile's coefficients are loaded (into the other half of coef) between the phase barrier and phase B.
+// Zone tiles of a strip stage their outgoing rows in the normal / position cells until they are pushed: for them the next
+// tile's inputs are requested after the push.  Arithmetic, tile order of a CTA row and the zone bookkeeping are those of
+// post_tma_kernel (same functions), so results are bit-identical to it.
+// ------------------------------------------------------------------------------------------------
+#ifndef BMFR_POST_PERSIST
+#define BMFR_POST_PERSIST 0
+#endif
+#ifndef BMFR_POST_STAGGER_NS
+#define BMFR_POST_STAGGER_NS 0
+#endif
+struct TileBoxes {  // 16-byte aligned box starts of a tile's six TMA copies (floor, also for negatives)
+    int c_rgb, c_pp, c_u8, c1;
+};
+__device__ __forceinline__ void tile_geometry(const KParams& P, int bx, int by, TileGeom& G, TileBoxes& B) {
+    G.x0 = bx * 32 - 16 + P.off_x;
+    G.y0 = by * 32 - 16 + P.off_y;
+    const int f_rgb = 3 * (G.x0 - 1), f_pp = 2 * (G.x0 - 1), b_u8 = G.x0 - 1;
+    B.c_rgb = f_rgb & ~3; B.c_pp = f_pp & ~3; B.c_u8 = b_u8 & ~15;
+    B.c1 = G.y0 - 1 - P.row0;
+    G.sh_rgb = f_rgb - B.c_rgb; G.sh_pp = f_pp - B.c_pp; G.sh_u8 = b_u8 - B.c_u8;
+}
+// one thread: everything phase A reads except the albedo / the albedo.  Rows and columns outside the image (or the strip)
+// arrive as zeros.
+__device__ __forceinline__ void tile_request_inputs(PostStage& sh, const PostMaps& M, const TileBoxes& B) {
+    mbar_expect_tx(&sh.bar, PostStage::TX - PT_HALO * PT_RGB_W * 4);
+#if BMFR_L2_HINTS >= 2  // last readers of the reprojection's per-pixel outputs
+    tma_load_tile_hint(&sh.pp[0][0], &M.pp, B.c_pp, B.c1, &sh.bar, BMFR_L2_ONCE);
+    tma_load_tile_hint(&sh.acc[0][0], &M.accept, B.c_u8, B.c1, &sh.bar, BMFR_L2_ONCE);
+#else
+    tma_load_tile(&sh.pp[0][0], &M.pp, B.c_pp, B.c1, &sh.bar);
+    tma_load_tile(&sh.acc[0][0], &M.accept, B.c_u8, B.c1, &sh.bar);
+#endif
+    tma_load_tile(&sh.spp[0][0], &M.spp, B.c_u8, B.c1, &sh.bar);
+    tma_load_tile(&sh.nrm[0][0], &M.normals, B.c_rgb, B.c1, &sh.bar);
+    tma_load_tile(&sh.pos[0][0], &M.positions, B.c_rgb, B.c1, &sh.bar);
+}
+__device__ __forceinline__ void tile_request_albedo(PostStage& sh, const PostMaps& M, const TileBoxes& B) {
+    mbar_expect_tx(&sh.bar_alb, PT_HALO * PT_RGB_W * 4);
+#if BMFR_L2_HINTS >= 2  // only reader of the albedo
+    tma_load_tile_hint(&sh.alb[0][0], &M.albedo, B.c_rgb, B.c1, &sh.bar_alb, BMFR_L2_ONCE);
+#else
+    tma_load_tile(&sh.alb[0][0], &M.albedo, B.c_rgb, B.c1, &sh.bar_alb);
+#endif
+}
+
+template <bool STRIP, int FS>
+__global__ void __launch_bounds__(256, BMFR_POST_TMA_MIN_BLOCKS) post_persist_kernel(const __grid_constant__ KParams P, const __grid_constant__ PostMaps M) {
+    constexpr int PX = 4, THREADS = 256, WARPS = 8;
+    extern __shared__ __align__(128) unsigned char post_smem[];
+    PostStage& sh = *reinterpret_cast<PostStage*>(post_smem);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tiles_x = P.blocks_x, nrows = P.by1 - P.by0, ntiles = tiles_x * nrows;
+    if ((int)blockIdx.x >= ntiles) return;
+    // tile (column bx, row i of the launch) -> block coordinates, geometry and box starts; a CTA's next tile is gridDim.x tiles
+    // further (row-major): one division for the whole loop
+    const int step_rows = (int)gridDim.x / tiles_x, step_cols = (int)gridDim.x - step_rows * tiles_x;
+    auto locate = [&](int bx, int i, int& by, TileGeom& G, TileBoxes& B) {
+        by = P.by0 + (STRIP ? halo_row_order(P.halo_p, i, nrows) : sweep_row(P, i, nrows));
+        tile_geometry(P, bx, by, G, B);
+    };
+    auto advance = [&](int& bx, int& i) {
+        bx += step_cols;
+        i += step_rows;
+        if (bx >= tiles_x) { bx -= tiles_x; ++i; }
+    };
+    int bx, ti;  // this CTA's current tile
+    {
+        ti = (int)blockIdx.x / tiles_x;
+        bx = (int)blockIdx.x - ti * tiles_x;
+        int by;
+        TileGeom G;
+        TileBoxes B;
+        locate(bx, ti, by, G, B);
+        if (tid == 0) {
+            mbar_init(&sh.bar, 1);
+            mbar_init(&sh.bar_alb, 1);
+            mbar_fence_init();
+            // Requested before the grid dependency is resolved: the caller's inputs and the reprojection's outputs are
+            // complete by now (see post_tma_kernel).
+            tile_request_inputs(sh, M, B);
+            tile_request_albedo(sh, M, B);
+        }
+        pdl_wait();     // the fit of this frame is complete (weights, min/max)
+        pdl_trigger();  // only now, so that "this frame's fit and reprojection are complete" also holds for the successor
+        stamp_begin(P, 2);
+#if BMFR_POST_STAGGER_NS > 0  // tuning: the CTAs of an SM (blockIdx.x = slot * SMs + SM, presumably) start their loops apart
+        if (tid == 0) __nanosleep((blockIdx.x / (gridDim.x / BMFR_POST_TMA_MIN_BLOCKS)) * BMFR_POST_STAGGER_NS);
+#endif
+        load_coefficients_scaled<FS>(P, sh.coef[0], bx, by, warp, lane, WARPS);
+    }
+    for (int k = 0; ti < nrows; ++k) {
+        int by;
+        TileGeom G;
+        TileBoxes B;
+        locate(bx, ti, by, G, B);
+        // strips: a tile near a strip edge waits for the neighbours' accumulated colour / TAA rows of the previous frame
+        const bool zone = STRIP && halo_in_zone(P.halo_p, G.y0 - 1, G.y0 + PT_TILE + 1);
+        if (zone) halo_poll(P.halo_p, halo_peek(P.halo_p, zone));
+        __syncthreads();  // this tile's coefficients (and, k = 0, the barriers' initialisation) are visible; phase B of the previous tile is over
+        if (k > 0 && tid == 0) tile_request_albedo(sh, M, B);
+        mbar_wait_hot(&sh.bar, k & 1);
+        f3 hist[PX];
+        unsigned int live;
+        const AlbGate gate{&sh.bar_alb, (unsigned int)(k & 1)};
+        post_phase_a<STRIP, FS, PX>(sh, P, G, gate, sh.coef[k & 1], tid, lane, warp, zone, hist, live);
+        __syncthreads();  // the YCoCg cells are complete; nobody reads this tile's other inputs any more
+        int bxn = bx, tin = ti;
+        advance(bxn, tin);
+        const bool more = tin < nrows;
+        CoefRegs next_coef;
+        if (more) {
+            int byn;
+            TileGeom Gn;
+            TileBoxes Bn;
+            locate(bxn, tin, byn, Gn, Bn);
+            if (tid == 0 && !(STRIP && zone)) tile_request_inputs(sh, M, Bn);
+            next_coef = fetch_coefficients<FS>(P, bxn, byn, warp, lane, WARPS);  // in flight across phase B
+        }
+        post_phase_b<STRIP, PX>(sh, P, G, lane, warp, zone, hist, live);
+        if (more) store_coefficients<FS>(next_coef, sh.coef[(k + 1) & 1], warp, lane, WARPS);
+        if (STRIP && zone) {
+            __syncthreads();  // the staged rows are complete
+            post_push_rows<THREADS>(P, sh, G, tid);
+            halo_finish(P.halo_p, halo_cta_pushes(P.halo_p, G.y0, G.y0 + PT_TILE));  // (starts with a barrier: the staged rows are read)
+            if (more && tid == 0) {
+                int byn;
+                TileGeom Gn;
+                TileBoxes Bn;
+                locate(bxn, tin, byn, Gn, Bn);
+                tile_request_inputs(sh, M, Bn);
+            }
+        }
+        bx = bxn;
+        ti = tin;
     }
     stamp_end(P, 2);
 }
@@ -1155,11 +1364,21 @@ static cudaError_t launch_post_fs(const KParams& P, cudaStream_t st) {
         cudaError_t e = cudaGetDevice(&dev);
         if (e != cudaSuccess) return e;
         if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+        static int sms[64] = {};
         if (!done[dev]) {
             e = cudaFuncSetAttribute(post_tma_kernel<false, FS, PXW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(post_tma_kernel<true, FS, PXS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PostStage));
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(post_persist_kernel<false, FS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(post_persist_kernel<true, FS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PostStage));
+            if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
             if (e != cudaSuccess) return e;
             done[dev] = true;
+        }
+        if (BMFR_POST_PERSIST) {
+            const int ntiles = P.blocks_x * (P.by1 - P.by0);
+            const dim3 pgrid(ntiles < BMFR_POST_TMA_MIN_BLOCKS * sms[dev] ? ntiles : BMFR_POST_TMA_MIN_BLOCKS * sms[dev]);
+            if (strip) return launch_pdl(!P.plain_launch, post_persist_kernel<true, FS>, pgrid, dim3(256), sizeof(PostStage), st, P, M);
+            return launch_pdl(!P.plain_launch, post_persist_kernel<false, FS>, pgrid, dim3(256), smem_w, st, P, M);
         }
         if (strip) return launch_pdl(!P.plain_launch, post_tma_kernel<true, FS, PXS>, grid, dim3(1024 / PXS), sizeof(PostStage), st, P, M);
         return launch_pdl(!P.plain_launch, post_tma_kernel<false, FS, PXW>, grid, dim3(1024 / PXW), smem_w, st, P, M);
