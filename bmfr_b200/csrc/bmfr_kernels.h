@@ -94,6 +94,8 @@ struct KParams {
     int n_scaled;                 // its scaled features
     int fit_method;               // host side only: BMFR_FIT_GRAM / BMFR_FIT_TSQR (which FUSED fit kernel launch_fit_qr starts)
     int plain_launch;             // host side only: launch the FUSED kernels without programmatic stream serialization
+    int hist_stride;              // floats per pixel of accum_* / result_*: 3 (bmfr.cl:224-241), or 4 = padded to 16 bytes (whole-image
+                                  // FUSED contexts on the TMA post pass, see load_hist() in bmfr_post.cu)
 };
 
 
@@ -109,3 +111,4 @@ cudaError_t launch_k5(const KParams& P, cudaStream_t st);
 cudaError_t launch_reproject(const KParams& P, cudaStream_t st);
 cudaError_t launch_fit_qr(const KParams& P, cudaStream_t st);
 cudaError_t launch_post(const KParams& P, cudaStream_t st);
+bool post_uses_tma(int width, int rows);

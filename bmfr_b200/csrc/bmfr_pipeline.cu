@@ -62,6 +62,10 @@ struct StageEvents {
 
 }  // namespace
 
+#ifndef BMFR_HISTORY_PADDED
+#define BMFR_HISTORY_PADDED 0  // measured at 1080p: post 60.2 vs 55.8 us (profiles/r02_u_*): the 16 B per pixel of extra DRAM traffic cost more than the L1 wavefronts save
+#endif
+
 struct bmfr_ctx {
     bmfr_params prm;
     bmfr_geometry geo;
@@ -95,6 +99,13 @@ struct bmfr_ctx {
 
     // host-pointer entry
     float* up[4][kHostSlots] = {};          // albedo, normal, position, noisy upload ring
+    // Layout of accum / result: 3 floats per pixel (bmfr.cl:224-241), or 4 — a pixel padded to 16 bytes, so that a tap of the
+    // post pass's gathers is one 128-bit load (whole-image FUSED contexts whose post pass is the TMA kernel; bmfr_post.cu).
+    // Callers never see the padding: bmfr_get_buffer() hands out a compacted copy, the host entry reads the result through
+    // the post pass's user_out copy.
+    int hist_stride = 3;
+    float* hist_compact[2] = {nullptr, nullptr};  // bmfr_get_buffer(ACCUM / RESULT) of a padded context
+    float* out_stage[2] = {nullptr, nullptr};     // host entry of a padded context: the frame's result, 3 floats per pixel
     cudaEvent_t up_done[kHostSlots] = {};   // H2D of the slot finished
     cudaEvent_t frame_done[kHostSlots] = {};  // kernels that read the slot finished
     cudaEvent_t d2h_done[2] = {};
@@ -162,6 +173,8 @@ static void free_ctx(bmfr_ctx* c) {
         cudaFree(c->spp.buf[i]);
         cudaFree(c->accum.buf[i]);
         cudaFree(c->result.buf[i]);
+        cudaFree(c->hist_compact[i]);
+        cudaFree(c->out_stage[i]);
         if (c->d2h_done[i]) cudaEventDestroy(c->d2h_done[i]);
     }
     cudaFree(c->prev_pixels);
@@ -335,11 +348,13 @@ int bmfr_create(const bmfr_params* params, bmfr_ctx** out_ctx) {
     }
     const size_t npix = rows_of(c) * (size_t)p.width;
     const size_t nb = (size_t)g.blocks_x * g.blocks_y;
+    const bool whole_image = g.row0 == 0 && g.row1 == p.height;
+    c->hist_stride = (BMFR_HISTORY_PADDED && p.mode == BMFR_MODE_FUSED && whole_image && post_uses_tma(p.width, p.height)) ? 4 : 3;
     for (int i = 0; i < 2 && st == 0; ++i) {
         if (st == 0) st = dev_alloc(&c->noisy_acc.buf[i], npix * 3, "noisy_acc");
         if (st == 0) st = dev_alloc(&c->spp.buf[i], npix, "spp");
-        if (st == 0) st = dev_alloc(&c->accum.buf[i], npix * 3, "accum");
-        if (st == 0) st = dev_alloc(&c->result.buf[i], npix * 3, "result");
+        if (st == 0) st = dev_alloc(&c->accum.buf[i], npix * c->hist_stride, "accum");
+        if (st == 0) st = dev_alloc(&c->result.buf[i], npix * c->hist_stride, "result");
     }
     if (st == 0) st = dev_alloc(&c->prev_pixels, npix, "prev_pixels");
     if (st == 0) st = dev_alloc(&c->accept, npix, "accept");
@@ -546,6 +561,7 @@ static void fill_params(bmfr_ctx* c, KParams& P, int frame, const float* d_albed
     P.result_prev = c->result.previous(); P.result_cur = c->result.current();
     P.user_out = d_out; P.oob_flag = c->d_oob; P.block_counter = odd ? c->ov.counter : c->d_oob + 1;
     P.plain_launch = c->ov.on ? 1 : 0;
+    P.hist_stride = c->hist_stride;
     P.fit_method = c->prm.fit_method;
     P.feature_set = c->prm.feature_set;
     bmfr_feature_counts(c->prm.feature_set, &P.n_features, &P.n_scaled);
@@ -748,6 +764,11 @@ static int host_path_init(bmfr_ctx* c) {
         BMFR_CUDA_TRY(cudaEventCreateWithFlags(&c->frame_done[s], cudaEventDisableTiming));
     }
     for (int i = 0; i < 2; ++i) BMFR_CUDA_TRY(cudaEventCreateWithFlags(&c->d2h_done[i], cudaEventDisableTiming));
+    if (c->hist_stride != 3)
+        for (int i = 0; i < 2; ++i) {
+            int st = dev_alloc(&c->out_stage[i], n, "result staging");
+            if (st != 0) return st;
+        }
     c->host_ready = true;
     return BMFR_OK;
 }
@@ -775,9 +796,10 @@ int bmfr_denoise_frame_host(bmfr_ctx* c, int frame, const float* h_albedo, const
     // "the kernels of this frame are done")
     cudaStream_t done_stream = c->ov.on ? c->ov.s_p : c->stream;
     if (c->host_frames >= 2) BMFR_CUDA_TRY(cudaStreamWaitEvent(done_stream, c->d2h_done[rslot], 0));
-    float* d_result = c->result.current();
+    // (a padded context hands the frame's result out through the post pass's user_out copy)
+    float* d_result = c->hist_stride == 3 ? c->result.current() : c->out_stage[rslot];
     st = bmfr_denoise_frame(c, frame, c->up[0][slot], c->up[1][slot], c->up[2][slot], c->up[3][slot], cam_prev,
-                            pixel_offset, nullptr);
+                            pixel_offset, c->hist_stride == 3 ? nullptr : d_result);
     if (st != 0) return st;
     // the previous frame's slot is released once this frame's kernels (which read it as "previous") are done
     BMFR_CUDA_TRY(cudaEventRecord(c->frame_done[slot], done_stream));
@@ -832,6 +854,22 @@ int bmfr_sync(bmfr_ctx* c) {
     return BMFR_OK;
 }
 
+// accum / result as the caller expects them (3 floats per pixel): the buffer itself, or — padded context — a compacted copy
+// made on the context's stream (valid until the next call for the same buffer; device work is ordered by that stream).
+__global__ void hist_compact_kernel(const float4* __restrict__ src, float* __restrict__ dst, size_t npix) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    const float4 v = src[i];
+    dst[3 * i] = v.x; dst[3 * i + 1] = v.y; dst[3 * i + 2] = v.z;
+}
+static float* hist_view(bmfr_ctx* c, int which, float* buf, size_t npix) {
+    if (c->hist_stride == 3) return buf;
+    if (!c->hist_compact[which] && dev_alloc(&c->hist_compact[which], npix * 3, "compacted history") != 0) return nullptr;
+    if (c->ov.on) bmfr_join(c);  // overlapped frames: the post pass that wrote it runs on its own stream
+    hist_compact_kernel<<<(unsigned int)((npix + 255) / 256), 256, 0, c->stream>>>(reinterpret_cast<const float4*>(buf), c->hist_compact[which], npix);
+    return cudaGetLastError() == cudaSuccess ? c->hist_compact[which] : nullptr;
+}
+
 int bmfr_get_buffer(bmfr_ctx* c, int buffer, void** d_ptr, size_t* bytes) {
     if (!c || !d_ptr || !bytes) return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_get_buffer: null argument");
     const size_t npix = rows_of(c) * (size_t)c->geo.width;
@@ -851,9 +889,9 @@ int bmfr_get_buffer(bmfr_ctx* c, int buffer, void** d_ptr, size_t* bytes) {
         case BMFR_BUF_WEIGHTS: p = last_odd ? c->ov.weights : c->weights; n = nb * nf * 3 * 4; break;
         case BMFR_BUF_MINS_MAXS: p = last_odd ? c->ov.mins_maxs : c->mins_maxs; n = nb * ns * 2 * 4; break;
         case BMFR_BUF_FILTERED: p = c->filtered; n = npix * 12; break;
-        case BMFR_BUF_ACCUM: p = c->accum.previous(); n = npix * 12; break;
+        case BMFR_BUF_ACCUM: p = hist_view(c, 0, c->accum.previous(), npix); n = npix * 12; break;
         case BMFR_BUF_TONE_MAPPED: p = c->tone_mapped; n = npix * 12; break;
-        case BMFR_BUF_RESULT: p = c->result.previous(); n = npix * 12; break;
+        case BMFR_BUF_RESULT: p = hist_view(c, 1, c->result.previous(), npix); n = npix * 12; break;
         case BMFR_BUF_NOISE_TILE: p = last_odd ? c->ov.noise : c->noise; n = (size_t)(nf - 1) * BMFR_BLOCK_PIXELS * 8; break;
         default: return bmfr_set_error(BMFR_ERR_INVALID_ARGUMENT, "bmfr_get_buffer: unknown buffer %d", buffer);
     }

@@ -816,10 +816,43 @@ __device__ __forceinline__ bool history_in_reach(const KParams& P, const TapGeom
 }
 __device__ __forceinline__ void f3_to(float* d, f3 v) { d[0] = v.x; d[1] = v.y; d[2] = v.z; }
 
+// The accumulated filtered colour and the TAA result ("history": gathered from by the next frame, four taps per pixel and
+// buffer) are HS floats per pixel.  HS = 3 is the reference's layout (bmfr.cl:224-241).  HS = 4 (whole-image FUSED contexts whose
+// post pass runs this kernel, KParams::hist_stride) pads a pixel to 16 bytes: a tap is ONE 128-bit load whose warp-wide
+// footprint is four cache lines in four L1 wavefronts, where three 32-bit loads at a 12-byte stride take ten to twelve —
+// and the L1 data pipe is what the gathers of this kernel saturate (57 % of its peak on average, in bursts of a whole CTA;
+// prefetching the taps into the L2 and more warps both measured nothing or worse).  Costs 16 B per pixel of DRAM traffic
+// (two reads, two writes of the padding) against 62 L1 wavefronts per pixel.
+template <int HS>
+__device__ __forceinline__ f3 load_hist(const float* __restrict__ b, unsigned int i) {
+    if (HS == 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(b) + i);
+        return make_f3(v.x, v.y, v.z);
+    }
+    return load_f3(b, i);
+}
+template <int HS>
+__device__ __forceinline__ void store_hist(float* __restrict__ b, unsigned int i, f3 v) {
+    if (HS == 4) reinterpret_cast<float4*>(b)[i] = make_float4(v.x, v.y, v.z, 0.f);
+    else store_f3(b, i, v);
+}
+// six floats = the pixels i and i + 1 of one tap row
+template <int HS>
+__device__ __forceinline__ void load_hist_pair(float* __restrict__ d, const float* __restrict__ row, unsigned int i) {
+    if (HS == 4) {
+        const float4 u = __ldg(reinterpret_cast<const float4*>(row) + i), v = __ldg(reinterpret_cast<const float4*>(row) + i + 1);
+        d[0] = u.x; d[1] = u.y; d[2] = u.z; d[3] = v.x; d[4] = v.y; d[5] = v.z;
+    } else {
+        const float* p = row + (size_t)(i * 3u);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) d[k] = __ldg(p + k);
+    }
+}
+
 // One pixel on its own — a ring pixel, or a pixel of a pair that a strip or image edge cuts: taps fetched from clamped
 // addresses (an accepted tap is in the image, bmfr.cl:386-392, so its clamped address is its own), then the shared arithmetic.
 // store: the pixel belongs to the tile (accumulated colour written, history sampled if owned); returns the temporal flag.
-template <bool STRIP, int FS>
+template <bool STRIP, int FS, int HS>
 __device__ __forceinline__ bool single_pixel(PostStage& sh, const KParams& P, const TileGeom& G, const AlbGate& gate, const float* cf, int hx, int hy,
                                              int x, int y, bool store, bool own, f3& hist, bool zone) {
     const PixelIn in = load_pixel_staged(sh, P, G, hx, hy, x, y);
@@ -843,18 +876,18 @@ __device__ __forceinline__ bool single_pixel(PostStage& sh, const KParams& P, co
 #pragma unroll
         for (int dx = 0; dx < 2; ++dx) {
             const unsigned int l0 = pix_index(P, cx[dx], cy[0]), l1 = pix_index(P, cx[dx], cy[1]);
-            f3_to(a0 + 3 * dx, load_f3(P.accum_prev, l0));
-            f3_to(a1 + 3 * dx, load_f3(P.accum_prev, l1));
+            f3_to(a0 + 3 * dx, load_hist<HS>(P.accum_prev, l0));
+            f3_to(a1 + 3 * dx, load_hist<HS>(P.accum_prev, l1));
             if (want_hist) {
-                f3_to(r0 + 3 * dx, load_f3(P.result_prev, l0));
-                f3_to(r1 + 3 * dx, load_f3(P.result_prev, l1));
+                f3_to(r0 + 3 * dx, load_hist<HS>(P.result_prev, l0));
+                f3_to(r1 + 3 * dx, load_hist<HS>(P.result_prev, l1));
             }
         }
         if (want_hist) hist = history_ycc<false>(t.w, r0, r1, ok);
     }
     const f3 accum = accumulate_taps(P, accept, in.spp, t.w, filtered, a0, a1);
     if (store) {
-        store_f3(P.accum_cur, in.lp, accum);
+        store_hist<HS>(P.accum_cur, in.lp, accum);
         if (STRIP && zone) stage_accum(sh, G, hx, hy, accum);
     }
     put_ycc_i(sh, P, G, hx, hy, x, y, tone_ycocg(albedo_cell(sh, G, gate, hx, hy), accum));
@@ -870,6 +903,9 @@ __device__ __forceinline__ bool single_pixel(PostStage& sh, const KParams& P, co
 #ifndef BMFR_POST_PX
 #define BMFR_POST_PX 4  // pixels per thread of the whole-image instantiation (4: 8 warps per tile, 2: 16)
 #endif
+#ifndef BMFR_POST_HISTORY_PREFETCH
+#define BMFR_POST_HISTORY_PREFETCH 0  // margin in pixels around the tile (0: off)
+#endif
 #ifndef BMFR_POST_RING_SPREAD
 #define BMFR_POST_RING_SPREAD 0
 #endif
@@ -881,7 +917,7 @@ __device__ __forceinline__ bool single_pixel(PostStage& sh, const KParams& P, co
 // Phase A of one tile: filtered -> accumulated -> tone-mapped colour of the tile's pixels and of its ring (YCoCg values into the
 // albedo cells), the TAA history samples of the tile's pixels (hist) and their flags (live: bit s = pixel s is written, bit
 // 4 + s = it takes the temporal path).  The caller puts a CTA barrier behind it.
-template <bool STRIP, int FS, int PX>
+template <bool STRIP, int FS, int PX, int HS>
 __device__ __forceinline__ void post_phase_a(PostStage& sh, const KParams& P, const TileGeom& G, const AlbGate& gate, const float (*coef)[PT_COEF_S],
                                              int tid, int lane, int warp, bool zone, f3 (&hist)[PX], unsigned int& live) {
     const int x = G.x0 + lane;
@@ -892,7 +928,7 @@ __device__ __forceinline__ void post_phase_a(PostStage& sh, const KParams& P, co
                           G.y0 - 1 >= P.py0 && G.y0 + 33 <= P.py1 && G.y0 >= P.own_y0 && G.y0 + 32 <= P.own_y1;
     live = 0;
     if (interior) {
-        const int W3 = 3 * P.W;
+        const int WH = HS * P.W;  // floats per row of the history buffers
 #pragma unroll
         for (int s = 0; s < PX; s += 2) {
             const int ty = PX * warp + s, y = G.y0 + ty;
@@ -904,16 +940,11 @@ __device__ __forceinline__ void post_phase_a(PostStage& sh, const KParams& P, co
             float A[3][6], R[3][6];
             f3 fl0, fl1;
             if (__all_sync(0xffffffffu, easy)) {
-                const size_t base = (size_t)(pix_index(P, g0.pix, g0.piy) * 3u);
-                const float* a = P.accum_prev + base;
-                const float* r = P.result_prev + base;
+                const unsigned int base = pix_index(P, g0.pix, g0.piy);
 #pragma unroll
                 for (int row = 0; row < 3; ++row) {
-#pragma unroll
-                    for (int k = 0; k < 6; ++k) {
-                        A[row][k] = __ldg(a + row * W3 + k);
-                        R[row][k] = __ldg(r + row * W3 + k);
-                    }
+                    load_hist_pair<HS>(A[row], P.accum_prev + (size_t)row * WH, base);
+                    load_hist_pair<HS>(R[row], P.result_prev + (size_t)row * WH, base);
                 }
                 weighted_sum_scaled_px2<FS>(i0.n, i0.p, i1.n, i1.p, coef[4], fl0, fl1);  // its arithmetic overlaps the gathers
                 hist[s] = history_ycc<true>(g0.w, R[0], R[1], 15u);
@@ -927,8 +958,8 @@ __device__ __forceinline__ void post_phase_a(PostStage& sh, const KParams& P, co
 #pragma unroll
                 for (int dx = 0; dx < 2; ++dx) {
                     const unsigned int l0 = pix_index(P, cx0[dx], ry0[0]), l1 = pix_index(P, cx0[dx], ry0[1]), l2 = pix_index(P, cx1[dx], ry1[1]);
-                    f3_to(&A[0][3 * dx], load_f3(P.accum_prev, l0)); f3_to(&A[1][3 * dx], load_f3(P.accum_prev, l1)); f3_to(&A[2][3 * dx], load_f3(P.accum_prev, l2));
-                    f3_to(&R[0][3 * dx], load_f3(P.result_prev, l0)); f3_to(&R[1][3 * dx], load_f3(P.result_prev, l1)); f3_to(&R[2][3 * dx], load_f3(P.result_prev, l2));
+                    f3_to(&A[0][3 * dx], load_hist<HS>(P.accum_prev, l0)); f3_to(&A[1][3 * dx], load_hist<HS>(P.accum_prev, l1)); f3_to(&A[2][3 * dx], load_hist<HS>(P.accum_prev, l2));
+                    f3_to(&R[0][3 * dx], load_hist<HS>(P.result_prev, l0)); f3_to(&R[1][3 * dx], load_hist<HS>(P.result_prev, l1)); f3_to(&R[2][3 * dx], load_hist<HS>(P.result_prev, l2));
                 }
                 weighted_sum_scaled_px2<FS>(i0.n, i0.p, i1.n, i1.p, coef[4], fl0, fl1);
                 const bool t0 = history_in_reach(P, g0), t1 = history_in_reach(P, g1);
@@ -943,17 +974,17 @@ __device__ __forceinline__ void post_phase_a(PostStage& sh, const KParams& P, co
                 if (!(cx1[0] == cx0[0] && cx1[1] == cx0[1] && ry1[0] == ry0[1])) {  // footprints not stacked: fetch the lower pixel's upper row
                     // (the upper pixel's accumulation below needs its own lower row: finish it first)
                     const f3 acc0 = accumulate_taps(P, i0.accept, i0.spp, g0.w, fl0, A[0], A[1]);
-                    store_f3(P.accum_cur, i0.lp, acc0);
+                    store_hist<HS>(P.accum_cur, i0.lp, acc0);
                     put_cell_i(sh, G, lane + 1, ty + 1, tone_ycocg(albedo_cell(sh, G, gate, lane + 1, ty + 1), acc0));
 #pragma unroll
                     for (int dx = 0; dx < 2; ++dx) {
                         const unsigned int l = pix_index(P, cx1[dx], ry1[0]);
-                        f3_to(&A[1][3 * dx], load_f3(P.accum_prev, l));
-                        f3_to(&R[1][3 * dx], load_f3(P.result_prev, l));
+                        f3_to(&A[1][3 * dx], load_hist<HS>(P.accum_prev, l));
+                        f3_to(&R[1][3 * dx], load_hist<HS>(P.result_prev, l));
                     }
                     hist[s + 1] = history_ycc<false>(g1.w, R[1], R[2], ok1);
                     const f3 acc1 = accumulate_taps(P, i1.accept, i1.spp, g1.w, fl1, A[1], A[2]);
-                    store_f3(P.accum_cur, i1.lp, acc1);
+                    store_hist<HS>(P.accum_cur, i1.lp, acc1);
                     put_cell_i(sh, G, lane + 1, ty + 2, tone_ycocg(albedo_cell(sh, G, gate, lane + 1, ty + 2), acc1));
                     live |= ((1u | (t0 ? 16u : 0u)) | ((1u | (t1 ? 16u : 0u)) << 1)) << s;
                     continue;
@@ -963,8 +994,8 @@ __device__ __forceinline__ void post_phase_a(PostStage& sh, const KParams& P, co
             }
             const f3 acc0 = accumulate_taps(P, i0.accept, i0.spp, g0.w, fl0, A[0], A[1]);
             const f3 acc1 = accumulate_taps(P, i1.accept, i1.spp, g1.w, fl1, A[1], A[2]);
-            store_f3(P.accum_cur, i0.lp, acc0);
-            store_f3(P.accum_cur, i1.lp, acc1);
+            store_hist<HS>(P.accum_cur, i0.lp, acc0);
+            store_hist<HS>(P.accum_cur, i1.lp, acc1);
             put_cell_i(sh, G, lane + 1, ty + 1, tone_ycocg(albedo_cell(sh, G, gate, lane + 1, ty + 1), acc0));
             put_cell_i(sh, G, lane + 1, ty + 2, tone_ycocg(albedo_cell(sh, G, gate, lane + 1, ty + 2), acc1));
         }
@@ -995,8 +1026,8 @@ __device__ __forceinline__ void post_phase_a(PostStage& sh, const KParams& P, co
 #pragma unroll
                     for (int dx = 0; dx < 2; ++dx) {
                         const unsigned int l0 = pix_index(P, cx0[dx], ry0[0]), l1 = pix_index(P, cx0[dx], ry0[1]), l2 = pix_index(P, cx1[dx], ry1[1]);
-                        f3_to(&A[0][3 * dx], load_f3(P.accum_prev, l0)); f3_to(&A[1][3 * dx], load_f3(P.accum_prev, l1)); f3_to(&A[2][3 * dx], load_f3(P.accum_prev, l2));
-                        f3_to(&R[0][3 * dx], load_f3(P.result_prev, l0)); f3_to(&R[1][3 * dx], load_f3(P.result_prev, l1)); f3_to(&R[2][3 * dx], load_f3(P.result_prev, l2));
+                        f3_to(&A[0][3 * dx], load_hist<HS>(P.accum_prev, l0)); f3_to(&A[1][3 * dx], load_hist<HS>(P.accum_prev, l1)); f3_to(&A[2][3 * dx], load_hist<HS>(P.accum_prev, l2));
+                        f3_to(&R[0][3 * dx], load_hist<HS>(P.result_prev, l0)); f3_to(&R[1][3 * dx], load_hist<HS>(P.result_prev, l1)); f3_to(&R[2][3 * dx], load_hist<HS>(P.result_prev, l2));
                     }
                     weighted_sum_scaled_px2<FS>(i0.n, i0.p, i1.n, i1.p, coef[4], fl0, fl1);  // its arithmetic overlaps the gathers
                     acc_bits0 = i0.accept; acc_bits1 = i1.accept;
@@ -1013,14 +1044,14 @@ __device__ __forceinline__ void post_phase_a(PostStage& sh, const KParams& P, co
                     stacked = cx1[0] == cx0[0] && cx1[1] == cx0[1] && ry1[0] == ry0[1];
                     if (!stacked) {  // rare: finish the upper pixel, then fetch the lower pixel's own upper row
                         const f3 acc0 = accumulate_taps(P, acc_bits0, i0.spp, g0.w, fl0, A[0], A[1]);
-                        store_f3(P.accum_cur, i0.lp, acc0);
+                        store_hist<HS>(P.accum_cur, i0.lp, acc0);
                         if (STRIP && zone) stage_accum(sh, G, lane + 1, ty + 1, acc0);
                         put_ycc_i(sh, P, G, lane + 1, ty + 1, x, y, tone_ycocg(albedo_cell(sh, G, gate, lane + 1, ty + 1), acc0));
 #pragma unroll
                         for (int dx = 0; dx < 2; ++dx) {
                             const unsigned int l = pix_index(P, cx1[dx], ry1[0]);
-                            f3_to(&A[1][3 * dx], load_f3(P.accum_prev, l));
-                            f3_to(&R[1][3 * dx], load_f3(P.result_prev, l));
+                            f3_to(&A[1][3 * dx], load_hist<HS>(P.accum_prev, l));
+                            f3_to(&R[1][3 * dx], load_hist<HS>(P.result_prev, l));
                         }
                     }
                     if (t1) hist[s + 1] = history_ycc<false>(g1.w, R[1], R[2], ok1);
@@ -1033,21 +1064,21 @@ __device__ __forceinline__ void post_phase_a(PostStage& sh, const KParams& P, co
                 }
                 if (stacked) {
                     const f3 acc0 = accumulate_taps(P, acc_bits0, i0.spp, g0.w, fl0, A[0], A[1]);
-                    store_f3(P.accum_cur, i0.lp, acc0);
+                    store_hist<HS>(P.accum_cur, i0.lp, acc0);
                     if (STRIP && zone) stage_accum(sh, G, lane + 1, ty + 1, acc0);
                     put_ycc_i(sh, P, G, lane + 1, ty + 1, x, y, tone_ycocg(albedo_cell(sh, G, gate, lane + 1, ty + 1), acc0));
                 }
                 const f3 acc1 = accumulate_taps(P, acc_bits1, i1.spp, g1.w, fl1, A[1], A[2]);
-                store_f3(P.accum_cur, i1.lp, acc1);
+                store_hist<HS>(P.accum_cur, i1.lp, acc1);
                 if (STRIP && zone) stage_accum(sh, G, lane + 1, ty + 2, acc1);
                 put_ycc_i(sh, P, G, lane + 1, ty + 2, x, y + 1, tone_ycocg(albedo_cell(sh, G, gate, lane + 1, ty + 2), acc1));
                 live |= ((own0 ? 1u : 0u) | (t0 ? 16u : 0u)) << s;
                 live |= ((own1 ? 1u : 0u) | (t1 ? 16u : 0u)) << (s + 1);
             } else if (v0) {  // a strip or image edge cuts the pair
-                const bool t = single_pixel<STRIP, FS>(sh, P, G, gate, coef[4], lane + 1, ty + 1, x, y, true, own0, hist[s], zone);
+                const bool t = single_pixel<STRIP, FS, HS>(sh, P, G, gate, coef[4], lane + 1, ty + 1, x, y, true, own0, hist[s], zone);
                 live |= ((own0 ? 1u : 0u) | (t ? 16u : 0u)) << s;
             } else if (v1) {
-                const bool t = single_pixel<STRIP, FS>(sh, P, G, gate, coef[4], lane + 1, ty + 2, x, y + 1, true, own1, hist[s + 1], zone);
+                const bool t = single_pixel<STRIP, FS, HS>(sh, P, G, gate, coef[4], lane + 1, ty + 2, x, y + 1, true, own1, hist[s + 1], zone);
                 live |= ((own1 ? 1u : 0u) | (t ? 16u : 0u)) << (s + 1);
             }
         }
@@ -1066,13 +1097,13 @@ __device__ __forceinline__ void post_phase_a(PostStage& sh, const KParams& P, co
         if (interior || (rx >= 0 && rx < P.W && ry >= P.py0 && ry < P.py1)) {
             const int nb = ((hy == 0) ? 0 : (hy == PT_HALO - 1) ? 6 : 3) + ((hx == 0) ? 0 : (hx == PT_HALO - 1) ? 2 : 1);
             f3 unused;
-            single_pixel<STRIP, FS>(sh, P, G, gate, coef[nb], hx, hy, rx, ry, false, false, unused, zone);
+            single_pixel<STRIP, FS, HS>(sh, P, G, gate, coef[nb], hx, hy, rx, ry, false, false, unused, zone);
         }
     }
 }
 
 // Phase B of one tile (after the barrier): neighbourhood clamp of the history samples, blend, TAA result stored.
-template <bool STRIP, int PX>
+template <bool STRIP, int PX, int HS>
 __device__ __forceinline__ void post_phase_b(PostStage& sh, const KParams& P, const TileGeom& G, int lane, int warp, bool zone, const f3 (&hist)[PX],
                                              unsigned int live) {
     const int x = G.x0 + lane;
@@ -1112,13 +1143,13 @@ __device__ __forceinline__ void post_phase_b(PostStage& sh, const KParams& P, co
         if (!(live & (1u << s))) continue;
         const unsigned int lp = pix_index(P, x, G.y0 + PX * warp + s);
         const f3 rgb = from_quarter_ycocg(out[s]);
-        store_f3(P.result_cur, lp, rgb);
+        store_hist<HS>(P.result_cur, lp, rgb);
         if (P.user_out) store_f3(P.user_out, lp, rgb);
         if (STRIP && zone) stage_result(sh, G, lane + 1, PX * warp + s + 1, rgb);
     }
 }
 
-template <bool STRIP, int FS, int PX>
+template <bool STRIP, int FS, int PX, int HS>
 __global__ void __launch_bounds__(1024 / PX, PX == 4 ? BMFR_POST_TMA_MIN_BLOCKS : 2) post_tma_kernel(const __grid_constant__ KParams P, const __grid_constant__ PostMaps M) {
     static_assert(PX == 4 || PX == 2, "pixels per thread: two pairs or one");
     constexpr int THREADS = 1024 / PX, WARPS = 32 / PX;
@@ -1162,6 +1193,26 @@ __global__ void __launch_bounds__(1024 / PX, PX == 4 ? BMFR_POST_TMA_MIN_BLOCKS 
     // first look at the flags is in flight across the wait for the fit
     const bool zone = STRIP && halo_in_zone(P.halo_p, G.y0 - 1, G.y0 + PT_TILE + 1);
     const HaloPeek peek = halo_peek(P.halo_p, zone);
+#if BMFR_POST_HISTORY_PREFETCH > 0
+    // The two tap gathers of phase A are this kernel's exposed latency (long-scoreboard stalls: 3.8 per issued instruction,
+    // 2/3 of their L1 misses also miss the L2: the previous frame's accumulated colour and TAA result were written a frame
+    // ago).  Where the taps will land is only known once the tile's previous-pixel positions have arrived, but it is
+    // almost always near the tile itself: start the DRAM -> L2 fetch of the tile's own area (+ a margin) of both buffers
+    // now, a tile-load latency ahead of the gathers.  Lines a neighbouring tile asks for as well are fetched once.
+    if (P.frame > 0 && !(STRIP && zone)) {
+        constexpr int MARGIN = BMFR_POST_HISTORY_PREFETCH;
+        const int hr0 = STRIP ? P.state2_row0 : 0, hr1 = STRIP ? P.state2_row1 : P.H;
+        const int ya = max(G.y0 - MARGIN, hr0), yb = min(G.y0 + PT_TILE + MARGIN, hr1);
+        const int ba = (max(G.x0 - MARGIN, 0) * 12) & ~127, bb = min(G.x0 + PT_TILE + MARGIN, P.W) * 12;  // byte range of a row
+        const int lines = (bb - ba + 127) >> 7;
+        const int total = (yb - ya) * lines * 2;
+        for (int i = tid; i < total; i += THREADS) {
+            const int j = i >> 1, r = j / lines, l = j - r * lines;
+            const char* base = reinterpret_cast<const char*>((i & 1) ? P.result_prev : P.accum_prev);
+            prefetch_l2(base + ((size_t)(ya + r - P.row0) * P.W * 12 + ba + l * 128));
+        }
+    }
+#endif
     pdl_wait();     // the fit of this frame is complete (weights, min/max)
     pdl_trigger();  // only now, so that "this frame's fit and reprojection are complete" also holds for the successor
     stamp_begin(P, 2);
@@ -1174,9 +1225,9 @@ __global__ void __launch_bounds__(1024 / PX, PX == 4 ? BMFR_POST_TMA_MIN_BLOCKS 
     f3 hist[PX];
     unsigned int live;
     const AlbGate gate{nullptr, 0u};  // the albedo came with the other inputs
-    post_phase_a<STRIP, FS, PX>(sh, P, G, gate, sh.coef[0], tid, lane, warp, zone, hist, live);
+    post_phase_a<STRIP, FS, PX, HS>(sh, P, G, gate, sh.coef[0], tid, lane, warp, zone, hist, live);
     __syncthreads();
-    post_phase_b<STRIP, PX>(sh, P, G, lane, warp, zone, hist, live);
+    post_phase_b<STRIP, PX, HS>(sh, P, G, lane, warp, zone, hist, live);
     if (STRIP && zone) {
         __syncthreads();  // the staged rows are complete
         post_push_rows<THREADS>(P, sh, G, tid);
@@ -1242,6 +1293,7 @@ __device__ __forceinline__ void tile_request_albedo(PostStage& sh, const PostMap
 #endif
 }
 
+#if BMFR_POST_PERSIST
 template <bool STRIP, int FS>
 __global__ void __launch_bounds__(256, BMFR_POST_TMA_MIN_BLOCKS) post_persist_kernel(const __grid_constant__ KParams P, const __grid_constant__ PostMaps M) {
     constexpr int PX = 4, THREADS = 256, WARPS = 8;
@@ -1301,7 +1353,7 @@ __global__ void __launch_bounds__(256, BMFR_POST_TMA_MIN_BLOCKS) post_persist_ke
         f3 hist[PX];
         unsigned int live;
         const AlbGate gate{&sh.bar_alb, (unsigned int)(k & 1)};
-        post_phase_a<STRIP, FS, PX>(sh, P, G, gate, sh.coef[k & 1], tid, lane, warp, zone, hist, live);
+        post_phase_a<STRIP, FS, PX, 3>(sh, P, G, gate, sh.coef[k & 1], tid, lane, warp, zone, hist, live);
         __syncthreads();  // the YCoCg cells are complete; nobody reads this tile's other inputs any more
         int bxn = bx, tin = ti;
         advance(bxn, tin);
@@ -1315,7 +1367,7 @@ __global__ void __launch_bounds__(256, BMFR_POST_TMA_MIN_BLOCKS) post_persist_ke
             if (tid == 0 && !(STRIP && zone)) tile_request_inputs(sh, M, Bn);
             next_coef = fetch_coefficients<FS>(P, bxn, byn, warp, lane, WARPS);  // in flight across phase B
         }
-        post_phase_b<STRIP, PX>(sh, P, G, lane, warp, zone, hist, live);
+        post_phase_b<STRIP, PX, 3>(sh, P, G, lane, warp, zone, hist, live);
         if (more) store_coefficients<FS>(next_coef, sh.coef[(k + 1) & 1], warp, lane, WARPS);
         if (STRIP && zone) {
             __syncthreads();  // the staged rows are complete
@@ -1334,6 +1386,7 @@ __global__ void __launch_bounds__(256, BMFR_POST_TMA_MIN_BLOCKS) post_persist_ke
     }
     stamp_end(P, 2);
 }
+#endif  // BMFR_POST_PERSIST
 
 #ifndef BMFR_POST_TMA
 #define BMFR_POST_TMA 1
@@ -1351,6 +1404,11 @@ static bool post_maps(const KParams& P, PostMaps* M) {
            bmfr_tensor_map_2d(P.cur_spp, 1, (long long)P.W, rows, PT_U8_W, PT_HALO, &M->spp);
 }
 
+// Would launch_post() run the TMA-staged kernel for a whole image of this size?  (bmfr_create picks the history layout with it.)
+bool post_uses_tma(int width, int rows) {
+    return BMFR_POST_TMA && (width & 15) == 0 && rows >= PT_HALO && width * 3 >= PT_RGB_W && bmfr_encode_tiled_fn() != nullptr;
+}
+
 template <int FS>
 static cudaError_t launch_post_fs(const KParams& P, cudaStream_t st) {
     const dim3 grid(P.blocks_x, P.by1 - P.by0);
@@ -1366,23 +1424,33 @@ static cudaError_t launch_post_fs(const KParams& P, cudaStream_t st) {
         if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
         static int sms[64] = {};
         if (!done[dev]) {
-            e = cudaFuncSetAttribute(post_tma_kernel<false, FS, PXW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(post_tma_kernel<true, FS, PXS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PostStage));
+            e = cudaFuncSetAttribute(post_tma_kernel<false, FS, PXW, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(post_tma_kernel<false, FS, PXW, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(post_tma_kernel<true, FS, PXS, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PostStage));
+#if BMFR_POST_PERSIST
             if (e == cudaSuccess) e = cudaFuncSetAttribute(post_persist_kernel<false, FS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(post_persist_kernel<true, FS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PostStage));
+#endif
             if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
             if (e != cudaSuccess) return e;
             done[dev] = true;
         }
-        if (BMFR_POST_PERSIST) {
+        if (P.hist_stride == 4) {  // padded history: whole-image contexts only (bmfr_create decides)
+            if (strip) return cudaErrorInvalidValue;
+            return launch_pdl(!P.plain_launch, post_tma_kernel<false, FS, PXW, 4>, grid, dim3(1024 / PXW), smem_w, st, P, M);
+        }
+#if BMFR_POST_PERSIST
+        {
             const int ntiles = P.blocks_x * (P.by1 - P.by0);
             const dim3 pgrid(ntiles < BMFR_POST_TMA_MIN_BLOCKS * sms[dev] ? ntiles : BMFR_POST_TMA_MIN_BLOCKS * sms[dev]);
             if (strip) return launch_pdl(!P.plain_launch, post_persist_kernel<true, FS>, pgrid, dim3(256), sizeof(PostStage), st, P, M);
             return launch_pdl(!P.plain_launch, post_persist_kernel<false, FS>, pgrid, dim3(256), smem_w, st, P, M);
         }
-        if (strip) return launch_pdl(!P.plain_launch, post_tma_kernel<true, FS, PXS>, grid, dim3(1024 / PXS), sizeof(PostStage), st, P, M);
-        return launch_pdl(!P.plain_launch, post_tma_kernel<false, FS, PXW>, grid, dim3(1024 / PXW), smem_w, st, P, M);
+#endif
+        if (strip) return launch_pdl(!P.plain_launch, post_tma_kernel<true, FS, PXS, 3>, grid, dim3(1024 / PXS), sizeof(PostStage), st, P, M);
+        return launch_pdl(!P.plain_launch, post_tma_kernel<false, FS, PXW, 3>, grid, dim3(1024 / PXW), smem_w, st, P, M);
     }
+    if (P.hist_stride != 3) return cudaErrorInvalidValue;  // the per-thread-load variant reads the reference's layout
     // widths that are no multiple of 16 (no tensor maps): the per-thread-load variant.  (Its 64+32-bit pixel accesses,
     // BMFR_POST_WIDE_ACCESS, cost 38 % more instructions for the same L1 wavefronts and stay a tuning switch.)
     const uintptr_t bits = (uintptr_t)P.cur_normals | (uintptr_t)P.cur_positions | (uintptr_t)P.albedo | (uintptr_t)P.accum_prev |

@@ -69,7 +69,7 @@ def test_fit_kernels_use_tma_and_packed_fma(sass, kernel, count, min_ffma2):
 
 def test_post_pass_stages_its_tiles_with_tma(sass):
     post = [l for n, l in sass.items() if "post_tma_kernel" in n]
-    assert len(post) == 6, list(sass)  # whole image / strip x the three feature lists
+    assert len(post) == 9, list(sass)  # (whole image, whole image with padded history, strip) x the three feature lists
     for lines in post:
         ops = _ops(lines)
         assert ops.count("UTMALDG") >= 6, "the six bulk tensor copies of a tile (normals, positions, albedo, prev_pixels, accept, spp)"
