@@ -24,10 +24,18 @@ def test_reference_arm_line():
     assert "workload" in line["config"] and "model" not in line["config"]
 
 
-def test_committed_b200_line_has_the_contract_keys():
-    line = json.loads((ROOT / "profiles" / "r01_v8_bench.json").read_text().strip().splitlines()[-1])
+import pytest
+
+
+@pytest.mark.parametrize("name", ["r01_v8_bench.json", "r02_z_bench.json"])
+def test_committed_b200_line_has_the_contract_keys(name):
+    line = json.loads((ROOT / "profiles" / name).read_text().strip().splitlines()[-1])
     assert BASE_KEYS | {"roofline", "gpu_launches", "clocks"} <= set(line)
     assert line["n_gpus"] == 1 and line["data"] == "synthetic" and line["dtype"] == "f32" and line["vs_baseline"] is None
+    if name.startswith("r02"):  # the round-2 line: roofline of the dominant kernel, kernels inside the timed region
+        r = line["roofline"]
+        assert r["bound"] == "hbm" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["traffic"] > 0
+        assert line["gpu_launches"] == 3 * 60 * line["steps"] and line["e2e"]["h2d_bytes_per_step"] > 0
     rf = line["roofline"]
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(rf) and rf["bound"] == "hbm" and rf["unit"] == "GB/s"
     assert abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
