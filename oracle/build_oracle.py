@@ -43,8 +43,13 @@ def port_lib(feature_set=0) -> Path:
     return HERE / f"libbmfr_oracle{_suffix(feature_set)}.so"
 
 
-def ref_lib(feature_set=0) -> Path:
-    return REF_DIR / f"libbmfr_clref{_suffix(feature_set)}.so"
+# The reference's two fitter tuning toggles (bmfr.cpp:82-84 -> bmfr.cl:100-119,609-649,664-688): builds of the shim library with
+# the other value, for tests/test_oracle_pin.py (test_compressed_r_toggle_*, test_cache_tmp_data_toggle_*).
+TOGGLE_VARIANTS = {"r0": {"COMPRESSED_R": 0}, "c0": {"CACHE_TMP_DATA": 0}}
+
+
+def ref_lib(feature_set=0, variant="") -> Path:
+    return REF_DIR / f"libbmfr_clref{_suffix(feature_set)}{'_' + variant if variant else ''}.so"
 
 
 def clgpu_lib(feature_set=0) -> Path:
@@ -83,7 +88,7 @@ def build_port(force=False, feature_set=0) -> Path:
     return lib
 
 
-def _defines_from_bmfr_cpp(text: str, feature_set=0) -> str:
+def _defines_from_bmfr_cpp(text: str, feature_set=0, toggles=None) -> str:
     """The -D options bmfr.cpp:205-232 derives from its own #defines (bmfr.cpp:56-118); feature_set != 0 replaces the two
     feature strings the way an edit of bmfr.cpp:65-77 would."""
     def strings_of(name):
@@ -110,22 +115,24 @@ def _defines_from_bmfr_cpp(text: str, feature_set=0) -> str:
         m = re.search(r"^#define %s (\d+)\s*$" % name, text, re.M)
         if not m:
             raise RuntimeError(f"{name} not found in bmfr.cpp")
-        out.append(f"#define {name} {m.group(1)}")
+        out.append(f"#define {name} {(toggles or {}).get(name, m.group(1))}")
     out.append("#define BLOCK_PIXELS (BLOCK_EDGE_LENGTH * BLOCK_EDGE_LENGTH)")
     return "\n".join(out) + "\n"
 
 
-def build_reference(force=False, feature_set=0):
-    """Returns the path of the reference-kernel library, or None when it cannot be (re)built."""
-    REF_LIB, cl, cpp = ref_lib(feature_set), REFERENCE / "bmfr.cl", REFERENCE / "bmfr.cpp"
+def build_reference(force=False, feature_set=0, variant=""):
+    """Returns the path of the reference-kernel library, or None when it cannot be (re)built.  variant: a key of
+    TOGGLE_VARIANTS (the reference's fitter tuning toggles set the other way), "" = bmfr.cpp as shipped."""
+    REF_LIB, cl, cpp = ref_lib(feature_set, variant), REFERENCE / "bmfr.cl", REFERENCE / "bmfr.cpp"
+    toggles = TOGGLE_VARIANTS[variant] if variant else None
     shim = [HERE / "cl_shim" / "cl_shim.hpp", HERE / "cl_shim" / "cl_host.cpp", HERE / "bmfr_oracle.h"]
     if not cl.exists() or not cpp.exists():
         return REF_LIB if REF_LIB.exists() else None   # GPU box: use what travelled
-    digest = _stamp([cl, cpp, *shim, Path(__file__)], " ".join(CFLAGS) + str(feature_set))
-    stamp = REF_DIR / f"ref{_suffix(feature_set)}.sha256"
+    digest = _stamp([cl, cpp, *shim, Path(__file__)], " ".join(CFLAGS) + str(feature_set) + variant)
+    stamp = REF_DIR / f"ref{_suffix(feature_set)}{variant}.sha256"
     if not force and REF_LIB.exists() and stamp.exists() and stamp.read_text() == digest:
         return REF_LIB
-    work = REF_DIR / f"gen{_suffix(feature_set)}"
+    work = REF_DIR / f"gen{_suffix(feature_set)}{variant}"
     work.mkdir(parents=True, exist_ok=True)
     try:
         src = cl.read_text()
@@ -134,7 +141,7 @@ def build_reference(force=False, feature_set=0):
                 raise RuntimeError(f"rewrite {old!r}: expected {count} match(es), found {src.count(old)}")
             src = src.replace(old, new)
         (work / "bmfr_cl.gen.inc").write_text(src)
-        (work / "bmfr_defines.gen.h").write_text(_defines_from_bmfr_cpp(cpp.read_text(), feature_set))
+        (work / "bmfr_defines.gen.h").write_text(_defines_from_bmfr_cpp(cpp.read_text(), feature_set, toggles))
         cmd = ["g++", "-std=gnu++17", *CFLAGS, "-Wno-narrowing", "-Wno-attributes", "-I", str(work),
                "-o", str(REF_LIB), str(HERE / "cl_shim" / "cl_host.cpp"), "-lm"]
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -32,21 +32,25 @@ class OracleParams(C.Structure):
 FEATURE_SETS = {0: (10, 6), 1: (7, 3), 2: (7, 6)}
 
 
-def lib_path(kind: str, feature_set: int = 0) -> Path:
+def lib_path(kind: str, feature_set: int = 0, variant: str = "") -> Path:
     sfx = "" if feature_set == 0 else f"_fs{feature_set}"
-    return {"port": HERE / f"libbmfr_oracle{sfx}.so", "reference": HERE / "_ref" / f"libbmfr_clref{sfx}.so",
+    var = f"_{variant}" if variant else ""  # reference only: build_oracle.TOGGLE_VARIANTS
+    return {"port": HERE / f"libbmfr_oracle{sfx}.so", "reference": HERE / "_ref" / f"libbmfr_clref{sfx}{var}.so",
             "opencl": HERE / "_ref" / f"libbmfr_clgpu{sfx}.so"}[kind]
 
 
-def available(kind: str, feature_set: int = 0) -> bool:
-    return lib_path(kind, feature_set).exists()
+def available(kind: str, feature_set: int = 0, variant: str = "") -> bool:
+    return lib_path(kind, feature_set, variant).exists()
 
 
-def _load(kind: str, feature_set: int = 0):
-    path = lib_path(kind, feature_set)
+def _load(kind: str, feature_set: int = 0, variant: str = ""):
+    path = lib_path(kind, feature_set, variant)
     if not path.exists():
         from . import build_oracle
-        dict(port=build_oracle.build_port, reference=build_oracle.build_reference, opencl=build_oracle.build_opencl_host)[kind](False, feature_set)
+        if variant:
+            build_oracle.build_reference(False, feature_set, variant)
+        else:
+            dict(port=build_oracle.build_port, reference=build_oracle.build_reference, opencl=build_oracle.build_opencl_host)[kind](False, feature_set)
     if not path.exists():
         raise FileNotFoundError(f"{path} is missing (kind={kind})")
     lib = C.CDLL(str(path))
@@ -82,10 +86,12 @@ class Oracle:
 
     def __init__(self, kind, width, height, *, noise_amount=1e-2, blend_alpha=0.2, second_blend_alpha=0.1,
                  taa_blend_alpha=0.2, position_limit_squared, normal_limit_squared, tmp_half=0, keep_tmp=0,
-                 k1_schedule=0, threads=0, feature_set=0):
-        if (kind, feature_set) not in _LIBS:
-            _LIBS[(kind, feature_set)] = _load(kind, feature_set)
-        self.lib, self.kind, self.W, self.H = _LIBS[(kind, feature_set)], kind, width, height
+                 k1_schedule=0, threads=0, feature_set=0, variant=""):
+        if variant and kind != "reference":
+            raise ValueError("variant: the reference's tuning toggles only exist in the shim build of its kernels")
+        if (kind, feature_set, variant) not in _LIBS:
+            _LIBS[(kind, feature_set, variant)] = _load(kind, feature_set, variant)
+        self.lib, self.kind, self.W, self.H = _LIBS[(kind, feature_set, variant)], kind, width, height
         self.features, self.features_scaled = FEATURE_SETS[feature_set]
         self.params = OracleParams(width, height, noise_amount, blend_alpha, second_blend_alpha, taa_blend_alpha,
                                    position_limit_squared, normal_limit_squared, tmp_half, keep_tmp, k1_schedule,

@@ -73,3 +73,38 @@ def test_k1_race_is_confined_to_margin_blocks():
     by = (32 * ((h + 31) // 32) + 32) // 32
     wa, wb = a["weights"].reshape(by, bx, 30), b["weights"].reshape(by, bx, 30)
     assert np.array_equal(wa[2:-2, 2:-2], wb[2:-2, 2:-2])
+
+
+def _toggle_runs(variant, half):
+    from oracle import build_oracle
+    if not orc.available("reference", 0, variant) and build_oracle.build_reference(False, 0, variant) is None:
+        pytest.skip("the shim build for this toggle is absent and /root/reference not mounted")
+    a = util.run_oracle("reference", 160, 96, 6, keep=ALL, tmp_half=half)
+    b = util.run_oracle("reference", 160, 96, 6, keep=ALL, tmp_half=half, variant=variant)
+    return a, b
+
+
+@pytest.mark.parametrize("half", [0, 1])
+def test_compressed_r_toggle_does_not_change_any_buffer(half):
+    """COMPRESSED_R 0 (bmfr.cpp:82): the reference's fitter keeps R as a full R_EDGE x R_EDGE array in local memory instead
+    of the packed triangle (bmfr.cl:100-119,664-688; local size bmfr.cpp:355-361).  The reference's kernels compiled that
+    way produce every buffer of every frame bit for bit: a scratch layout, not a behaviour — the compatibility mode
+    (csrc/bmfr_reforder.cu) needs no second code path for it."""
+    a, b = _toggle_runs("r0", half)
+    for f, (x, y) in enumerate(zip(a, b)):
+        for k in ALL:
+            assert util.bits_equal(x[k], y[k]), f"frame {f}, tmp_half={half}: {k} differs with COMPRESSED_R=0"
+
+
+def test_cache_tmp_data_toggle_is_a_different_filter():
+    """CACHE_TMP_DATA 0 (bmfr.cpp:84) is NOT a tuning switch: without the private cache the transform loop re-reads the column
+    and calls add_random() on it again — unconditionally, in every reflector pass and on the colour columns too
+    (bmfr.cl:643-649), while the dot product in front of it saw the noise only in the first pass on the feature columns
+    (bmfr.cl:623-627).  The reference's own kernels compiled that way give other weights from frame 0 on (everything in
+    front of the fit is untouched); the reference ships with 1 and the compatibility mode reproduces that."""
+    a, b = _toggle_runs("c0", 0)
+    for k in ("noisy_acc", "spp", "prev_pixels", "accept", "mins_maxs", "noise_tile"):
+        assert util.bits_equal(a[0][k], b[0][k]), f"{k} is computed in front of the fit and cannot depend on the toggle"
+    assert not util.bits_equal(a[0]["weights"], b[0]["weights"])
+    rel = np.abs(a[0]["result"] - b[0]["result"]).max() / max(np.abs(a[0]["result"]).max(), 1e-6)
+    assert rel > 1e-4, rel  # visibly another result, not a rounding difference
