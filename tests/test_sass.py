@@ -85,3 +85,33 @@ def test_strip_kernels_store_to_peers_in_wide_rows(sass):
         text = "\n".join(lines)
         assert "MEMBAR" in text and ".SYS" in text, f"{name}: no system-scope fence"
         assert re.search(r"STG\.E\.(\w+\.)*" + width, text), f"{name}: no {width}-bit global stores"
+
+
+def test_post_pass_has_its_interior_path_and_the_shared_arithmetic(sass):
+    """The interior tiles' phase A starts with a warp-uniform test per pixel pair (VOTE.ALL), the weighted sum clamps with the
+    NaN-propagating maximum, the tone map multiplies with saturation; the padded-history instantiation gathers with
+    128-bit loads."""
+    for name, lines in sass.items():
+        if "post_tma_kernel" not in name:
+            continue
+        text = "\n".join(lines)
+        assert "VOTE.ALL" in text, f"{name}: the per-pair footprint test of the interior path is gone"
+        assert re.search(r"FMNMX(3)?\.NAN", text), f"{name}: clamp_negative_nan no longer compiles to a NaN-propagating maximum"
+        assert re.search(r"FMUL(\.\w+)*\.SAT", text), f"{name}: the tone map's saturating multiply is gone"
+        if "ELi4ELi4E" in name:  # <.., PX = 4, HS = 4>
+            assert len(re.findall(r"LDG\.E\.128", text)) >= 24, f"{name}: padded history is not gathered with 128-bit loads"
+
+
+def test_fit_draws_its_next_block_ahead_of_the_barrier(sass):
+    """fit_gram_kernel: the atomic on the block counter is issued before the block barrier that precedes its use (the L2
+    round trip used to sit behind it on thread 0's path)."""
+    for name, lines in sass.items():
+        if "fit_gram_kernel" not in name:
+            continue
+        ops = _ops(lines)
+        atom = next(i for i, o in enumerate(ops) if o.startswith("ATOMG") or o.startswith("ATOM"))
+        bars = [i for i, o in enumerate(ops) if o == "BAR"]
+        assert any(b > atom for b in bars), name
+        # between the draw and the next CTA barrier lies the whole first phase of a block: its tile loads
+        nxt = min(b for b in bars if b > atom)
+        assert ops[atom:nxt].count("LDS") >= 72, (name, ops[atom:nxt].count("LDS"))
