@@ -817,12 +817,12 @@ __device__ __forceinline__ bool history_in_reach(const KParams& P, const TapGeom
 __device__ __forceinline__ void f3_to(float* d, f3 v) { d[0] = v.x; d[1] = v.y; d[2] = v.z; }
 
 // The accumulated filtered colour and the TAA result ("history": gathered from by the next frame, four taps per pixel and
-// buffer) are HS floats per pixel.  HS = 3 is the reference's layout (bmfr.cl:224-241).  HS = 4 (whole-image FUSED contexts whose
-// post pass runs this kernel, KParams::hist_stride) pads a pixel to 16 bytes: a tap is ONE 128-bit load whose warp-wide
-// footprint is four cache lines in four L1 wavefronts, where three 32-bit loads at a 12-byte stride take ten to twelve —
-// and the L1 data pipe is what the gathers of this kernel saturate (57 % of its peak on average, in bursts of a whole CTA;
-// prefetching the taps into the L2 and more warps both measured nothing or worse).  Costs 16 B per pixel of DRAM traffic
-// (two reads, two writes of the padding) against 62 L1 wavefronts per pixel.
+// buffer) are HS floats per pixel.  HS = 3 is the reference's layout (bmfr.cl:224-241) and the default.  HS = 4 (tuning switch
+// BMFR_HISTORY_PADDED in bmfr_pipeline.cu: whole-image FUSED contexts whose post pass runs this kernel, KParams::hist_stride)
+// pads a pixel to 16 bytes: a tap is ONE 128-bit load whose warp-wide footprint is four cache lines in four L1 wavefronts,
+// where three 32-bit loads at a 12-byte stride take ten to twelve.  Measured at 1080p with every GPU test green: 60.2 against
+// 55.8 us — the 16 B per pixel of extra DRAM traffic (two reads, two writes of the padding, +17 %) cost more than the 62 L1
+// wavefronts per pixel it saves: the kernel follows its bytes, not its L1 requests.  Kept, off.
 template <int HS>
 __device__ __forceinline__ f3 load_hist(const float* __restrict__ b, unsigned int i) {
     if (HS == 4) {
