@@ -115,3 +115,39 @@ def test_fit_draws_its_next_block_ahead_of_the_barrier(sass):
         # between the draw and the next CTA barrier lies the whole first phase of a block: its tile loads
         nxt = min(b for b in bars if b > atom)
         assert ops[atom:nxt].count("LDS") >= 72, (name, ops[atom:nxt].count("LDS"))
+
+
+def _region_counts(tmp_path, source, kernel, regions):
+    """scripts/sass_region_count.py on the built library: static SASS count per source-line range, following inline chains."""
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    subprocess.run([exe, "-xelf", source, str(_lib.LIB_PATH)], cwd=tmp_path, check=True, capture_output=True)
+    cubin = next(tmp_path.glob("*.cubin"))
+    args = [f"{f}:{lo}-{hi}:{name}" for name, (f, lo, hi) in regions.items()]
+    out = subprocess.run([sys.executable, str(root / "scripts" / "sass_region_count.py"), str(cubin), kernel, *args], capture_output=True,
+                         text=True, check=True).stdout
+    return {l.split()[1].rstrip(":"): int(l.split()[0]) for l in out.splitlines() if l.strip()}
+
+
+def _line_of(path, marker):
+    for i, l in enumerate(path.read_text().splitlines(), 1):
+        if marker in l:
+            return i
+    raise AssertionError(f"{marker!r} not found in {path}")
+
+
+def test_fit_interior_blocks_load_their_tile_at_immediate_offsets(tmp_path):
+    """The tile loads of a block inside the image: 72 LDS from one base address; the mirrored path next to it pays per-row index
+    arithmetic and branches (what the source-level profile showed at 17 % of the kernel's instructions)."""
+    from pathlib import Path
+    if not shutil.which("nvdisasm") and not Path("/usr/local/cuda/bin/nvdisasm").exists():
+        pytest.skip("nvdisasm not available")
+    src = Path(__file__).resolve().parent.parent / "bmfr_b200" / "csrc" / "bmfr_fit.cu"
+    a = _line_of(src, "if (BMFR_GRAM_INTERIOR_LOADS && by_tma")
+    b = _line_of(src, "} else if (by_tma) {")
+    counts = _region_counts(tmp_path, "bmfr_fit", "fit_gram_kernelILb0ELi0",
+                            {"interior": ("bmfr_fit.cu", a, b - 1), "mirrored": ("bmfr_fit.cu", b, b + 13)})
+    assert 72 <= counts["interior"] <= 110, counts
+    assert counts["mirrored"] >= 2 * counts["interior"], counts
